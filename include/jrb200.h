@@ -1,0 +1,158 @@
+/*
+ * jrb200.h — C ABI of libjrb200.so, the B200 (sm_100a) backend for the
+ * pseudo-transient (PT) hot path of PTsolvers/JustRelax.jl.
+ *
+ * This is the drop-in boundary: the entry points below are what a
+ * `JustRelaxB200Ext` Julia package extension binds with `ccall` in place of
+ * the ParallelStencil/CUDA.jl kernels that ext/JustRelaxCUDAExt.jl +
+ * src/ext/CUDA/{2D,3D}.jl provide today (INTEGRATION.md shows the Julia side).
+ * Plain C: POD structs, raw device pointers, sizes; no torch / C++ types.
+ *
+ * Conventions
+ *  - Every array is Float64, dense, column-major (x fastest) — the memory
+ *    layout of the Julia arrays in StokesArrays / ThermalArrays
+ *    (src/types/constructors/stokes.jl, src/types/constructors/heat_diffusion.jl).
+ *  - All pointers in jr_fields / jr_thermal_fields are DEVICE pointers on the
+ *    context's device unless a function name says `_host`.
+ *  - Functions return 0 (JR_OK) or a negative jr_status; jr_last_error() gives
+ *    the message.  There is no CPU fallback anywhere in this library.
+ *  - One context per GPU / host thread; calls on a context are blocking unless
+ *    stated otherwise and are not re-entrant.
+ */
+#ifndef JRB200_H
+#define JRB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JRB200_ABI_VERSION 1
+
+typedef enum {
+    JR_OK = 0,
+    JR_ERR_CUDA = -1,          /* CUDA runtime error (message has the cudaError string)          */
+    JR_ERR_SHAPE = -2,         /* inconsistent sizes / null required field                        */
+    JR_ERR_NAN = -3,           /* residual became NaN — reference: error("NaN(s)") Stokes3D.jl:162 */
+    JR_ERR_UNSUPPORTED = -4,   /* rheology / BC / option outside the supported subset             */
+    JR_ERR_NCCL = -5,
+    JR_ERR_ARG = -6
+} jr_status;
+
+/* ------------------------------------------------------------------------- *
+ * Field slots of a StokesArrays object — replaces the struct-of-CuArrays the
+ * reference passes to its kernels (src/types/stokes.jl:161-183; shapes
+ * src/types/constructors/stokes.jl:10-302).  Unused slots are NULL.
+ * Naming: t=τ, e=ε, p=ε_pl, d=Δε, w=ω, `_o` = τ_o, `_c` = shear @ centres,
+ * `_v` = normal @ vertices (2D), lam=λ, lamv=λv, etatau=ητ, divV=∇V, divU=∇U,
+ * rhog*=ρg tuple, K/G = bulk/shear modulus arrays (VA/V2 variants),
+ * T/Pargs = args.T (ghosted, ni.+2) and args.P (ni).
+ * ------------------------------------------------------------------------- */
+#define JR_STOKES_FIELDS(X)                                                    \
+    X(P) X(P0) X(divV) X(Q)                                                    \
+    X(Vx) X(Vy) X(Vz) X(Ux) X(Uy) X(Uz)                                        \
+    X(txx) X(tyy) X(tzz) X(tyz) X(txz) X(txy) X(tyz_c) X(txz_c) X(txy_c) X(tII) \
+    X(txx_o) X(tyy_o) X(tzz_o) X(tyz_o) X(txz_o) X(txy_o)                      \
+    X(tyz_o_c) X(txz_o_c) X(txy_o_c) X(tII_o)                                  \
+    X(exx) X(eyy) X(ezz) X(eyz) X(exz) X(exy) X(eyz_c) X(exz_c) X(exy_c) X(eII) \
+    X(pxx) X(pyy) X(pzz) X(pyz) X(pxz) X(pxy) X(pyz_c) X(pxz_c) X(pxy_c) X(pII) \
+    X(dxx) X(dyy) X(dzz) X(dyz) X(dxz) X(dxy) X(dyz_c) X(dxz_c) X(dxy_c) X(dII) \
+    X(EII_pl) X(EVol_pl) X(e_vol_pl)                                           \
+    X(eta) X(etav) X(eta_vep) X(etatau)                                        \
+    X(Rx) X(Ry) X(Rz) X(RP)                                                    \
+    X(wyz) X(wxz) X(wxy)                                                       \
+    X(divU) X(lam) X(lamv) X(dPpsi)                                            \
+    X(rhogx) X(rhogy) X(rhogz)                                                 \
+    X(K) X(G) X(T) X(Pargs)                                                    \
+    X(txx_v) X(tyy_v) X(txx_o_v) X(tyy_o_v)
+
+typedef enum {
+#define X(n) JR_F_##n,
+    JR_STOKES_FIELDS(X)
+#undef X
+    JR_F_COUNT
+} jr_field;
+
+typedef struct {
+    int32_t ndim;            /* 2 or 3                                  */
+    int32_t n[3];            /* local cells nx, ny, nz (nz = 1 in 2D)   */
+    double *f[JR_F_COUNT];   /* device pointers                         */
+} jr_fields;
+
+/* PTStokesCoeffs (src/types/stokes.jl:203-229), grid spacing (uniform
+ * Geometry, src/grid/Cartesian.jl:42-58), VelocityBoundaryConditions flags
+ * (src/boundaryconditions/types.jl:110-157) and the `kwargs` NamedTuple of
+ * solve! (src/stokes/Stokes3D.jl:35-40, 458-465; Stokes2D.jl:588-598). */
+typedef struct {
+    double r, theta_dtau, eta_dtau, eps_rel, eps_abs;
+    double _di[3];
+    double dt;
+    int64_t iterMax, nout;
+    int32_t n_g[3];                 /* nx_g(), ny_g(), nz_g()                         */
+    int32_t free_slip[6], no_slip[6], periodic[6]; /* left,right,front,back,top,bot   */
+    double viscosity_relaxation, lambda_relaxation, visc_cutoff_lo, visc_cutoff_hi;
+    int64_t iterMin;
+    int32_t strain_rate_ni_only;
+} jr_stokes_opts;
+
+typedef struct {
+    int64_t iter;
+    int64_t nhist;
+    double err;
+    double *err_evo1; int64_t *err_evo2;         /* HOST arrays, capacity iterMax/nout + 2 */
+    double *norm_Rx, *norm_Ry, *norm_Rz, *norm_divV;
+    double time_s;               /* device time of the PT loop (CUDA events), = `time`     */
+    int64_t kernel_launches;     /* kernels launched by this call                          */
+} jr_stokes_result;
+
+typedef struct jr_context jr_context;
+
+/* flags for jr_context_set_flags */
+#define JR_FLAG_UNFUSED   1u  /* run the reference-structured one-kernel-per-@parallel path */
+#define JR_FLAG_DIAG_EVERY_ITER 2u /* fused path: write ∇V, ε, R, U every iteration (default: only when read) */
+
+const char *jr_last_error(void);
+int jr_abi_version(void);
+int jr_field_count(void);
+const char *jr_field_name(int i);
+
+/* device / context management.  `stream` is a cudaStream_t (0 = create an own stream). */
+int jr_context_create(int device, void *stream, jr_context **out);
+int jr_context_destroy(jr_context *ctx);
+int jr_context_set_flags(jr_context *ctx, uint32_t flags);
+int jr_context_synchronize(jr_context *ctx);
+
+/* memory helpers — what PTArray(B200Backend) / Array(::B200Array) bind
+ * (ext/JustRelaxCUDAExt.jl:7-10, src/types/type_conversions.jl:20-63). */
+int jr_malloc(jr_context *ctx, size_t bytes, void **dptr);
+int jr_free(jr_context *ctx, void *dptr);
+int jr_memcpy_h2d(jr_context *ctx, void *dst, const void *src_host, size_t bytes);
+int jr_memcpy_d2h(jr_context *ctx, void *dst_host, const void *src, size_t bytes);
+int jr_memcpy_d2d(jr_context *ctx, void *dst, const void *src, size_t bytes);
+int jr_fill_f64(jr_context *ctx, double *dptr, double value, size_t count);
+
+/* --- 3D Stokes, visco-elastic variant with K,G arrays ----------------------
+ * replaces JR3D.solve!(::CUDABackendTrait, stokes, pt_stokes, grid, flow_bcs, ρg, K, G, dt, igg; kwargs)
+ * (src/ext/CUDA/3D.jl:375-377 → src/stokes/Stokes3D.jl:25-186). */
+int jr_stokes3d_solve_VA(jr_context *ctx, const jr_fields *s, const jr_stokes_opts *o, jr_stokes_result *res);
+/* exactly `niter` PT iterations, no convergence test (benchmark / fixed-iteration parity). */
+int jr_stokes3d_iterate_VA(jr_context *ctx, const jr_fields *s, const jr_stokes_opts *o, int64_t niter,
+                           jr_stokes_result *res);
+
+/* --- stand-alone kernels the reference exposes outside the loops ----------- */
+/* flow_bcs!(stokes, bcs)  src/ext/CUDA/3D.jl:195-218 → BoundaryConditions.jl:65-100 */
+int jr_flow_bcs3d(jr_context *ctx, double *Ax, double *Ay, double *Az, const int32_t n[3],
+                  const int32_t free_slip[6], const int32_t no_slip[6], const int32_t periodic[6]);
+/* compute_maxloc!(B, A; window)  src/Utils.jl:409-461 */
+int jr_maxloc3d(jr_context *ctx, double *B, const double *A, const int32_t n[3], const int32_t window[3]);
+/* velocity2displacement!/displacement2velocity!  src/ext/CUDA/3D.jl:358-372 */
+int jr_scale_copy(jr_context *ctx, double *dst, const double *src, double factor, size_t count);
+/* Σ A[2:end-1,…]^2 (interior != 0) or Σ A^2 — the local part of norm_mpi, src/Utils.jl:698-701 */
+int jr_sumsq(jr_context *ctx, const double *A, const int32_t n[3], int interior, double *out_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JRB200_H */

@@ -1,0 +1,125 @@
+"""ctypes binding of include/jrb200.h (libjrb200.so, CUDA sm_100a).
+
+This is the Python twin of the `ccall` stubs a Julia `JustRelaxB200Ext` would hold
+(INTEGRATION.md).  Loading fails loudly when the CUDA library is missing: there is no
+CPU fallback behind this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libjrb200.so")
+
+
+class JRError(RuntimeError):
+    """Error raised for a negative jr_status (message = jr_last_error())."""
+
+    def __init__(self, status: int, msg: str):
+        super().__init__(f"libjrb200 status {status}: {msg}")
+        self.status = status
+        self.msg = msg
+
+
+JR_OK, JR_ERR_CUDA, JR_ERR_SHAPE, JR_ERR_NAN, JR_ERR_UNSUPPORTED, JR_ERR_NCCL, JR_ERR_ARG = 0, -1, -2, -3, -4, -5, -6
+JR_FLAG_UNFUSED = 1
+JR_FLAG_DIAG_EVERY_ITER = 2
+
+_lib = None
+_field_names = None
+
+
+def lib():
+    """Load libjrb200.so (built by `make -C justrelax_jl_b200/csrc` / __graft_entry__.build())."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). justrelax_jl_b200 has no CPU fallback."
+        )
+    L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    L.jr_last_error.restype = C.c_char_p
+    L.jr_field_name.restype = C.c_char_p
+    L.jr_field_name.argtypes = [C.c_int]
+    _lib = L
+    _declare(L)
+    return L
+
+
+def field_names():
+    global _field_names
+    if _field_names is None:
+        L = lib()
+        _field_names = [L.jr_field_name(i).decode() for i in range(L.jr_field_count())]
+    return _field_names
+
+
+def check(status: int):
+    if status != 0:
+        raise JRError(status, lib().jr_last_error().decode())
+
+
+def make_fields_struct(nfields: int):
+    class Fields(C.Structure):
+        _fields_ = [("ndim", C.c_int32), ("n", C.c_int32 * 3), ("f", C.c_void_p * nfields)]
+
+    return Fields
+
+
+class StokesOpts(C.Structure):
+    _fields_ = [
+        ("r", C.c_double), ("theta_dtau", C.c_double), ("eta_dtau", C.c_double),
+        ("eps_rel", C.c_double), ("eps_abs", C.c_double),
+        ("_di", C.c_double * 3),
+        ("dt", C.c_double),
+        ("iterMax", C.c_int64), ("nout", C.c_int64),
+        ("n_g", C.c_int32 * 3),
+        ("free_slip", C.c_int32 * 6), ("no_slip", C.c_int32 * 6), ("periodic", C.c_int32 * 6),
+        ("viscosity_relaxation", C.c_double), ("lambda_relaxation", C.c_double),
+        ("visc_cutoff_lo", C.c_double), ("visc_cutoff_hi", C.c_double),
+        ("iterMin", C.c_int64),
+        ("strain_rate_ni_only", C.c_int32),
+    ]
+
+
+class StokesResult(C.Structure):
+    _fields_ = [
+        ("iter", C.c_int64), ("nhist", C.c_int64), ("err", C.c_double),
+        ("err_evo1", C.POINTER(C.c_double)), ("err_evo2", C.POINTER(C.c_int64)),
+        ("norm_Rx", C.POINTER(C.c_double)), ("norm_Ry", C.POINTER(C.c_double)),
+        ("norm_Rz", C.POINTER(C.c_double)), ("norm_divV", C.POINTER(C.c_double)),
+        ("time_s", C.c_double), ("kernel_launches", C.c_int64),
+    ]
+
+
+class OracleStokesResult(C.Structure):
+    """orc_stokes_result (oracle/jr_oracle.h) — same head, no timing tail."""
+
+    _fields_ = StokesResult._fields_[:9]
+
+
+def _declare(L):
+    vp, i32p = C.c_void_p, C.POINTER(C.c_int32)
+    L.jr_context_create.argtypes = [C.c_int, vp, C.POINTER(vp)]
+    L.jr_context_destroy.argtypes = [vp]
+    L.jr_context_set_flags.argtypes = [vp, C.c_uint32]
+    L.jr_context_synchronize.argtypes = [vp]
+    L.jr_malloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
+    L.jr_free.argtypes = [vp, vp]
+    L.jr_memcpy_h2d.argtypes = [vp, vp, vp, C.c_size_t]
+    L.jr_memcpy_d2h.argtypes = [vp, vp, vp, C.c_size_t]
+    L.jr_memcpy_d2d.argtypes = [vp, vp, vp, C.c_size_t]
+    L.jr_fill_f64.argtypes = [vp, vp, C.c_double, C.c_size_t]
+    L.jr_scale_copy.argtypes = [vp, vp, vp, C.c_double, C.c_size_t]
+    L.jr_sumsq.argtypes = [vp, vp, i32p, C.c_int, C.POINTER(C.c_double)]
+    L.jr_flow_bcs3d.argtypes = [vp, vp, vp, vp, i32p, i32p, i32p, i32p]
+    L.jr_maxloc3d.argtypes = [vp, vp, vp, i32p, i32p]
+    L.jr_stokes3d_solve_VA.argtypes = [vp, vp, C.POINTER(StokesOpts), C.POINTER(StokesResult)]
+    L.jr_stokes3d_iterate_VA.argtypes = [vp, vp, C.POINTER(StokesOpts), C.c_int64, C.POINTER(StokesResult)]
+
+
+def i32x(vals):
+    return (C.c_int32 * len(vals))(*[int(v) for v in vals])

@@ -1,0 +1,97 @@
+"""Synthetic model setups (the callers either side of the hot path) restated from the reference's
+miniapps/tests so that tests and bench.py run THE configurations BASELINE.json names.
+
+Everything here is host-side numpy (setup runs once; it is not the hot path).  Each function returns
+host arrays keyed by ABI slot name plus the scalar parameters, so the same inputs can be handed to the
+B200 backend and to the CPU oracle.
+"""
+from __future__ import annotations
+
+import math
+from types import SimpleNamespace
+
+import numpy as np
+
+from .types import Geometry, IGG, PTStokesCoeffs, VelocityBoundaryConditions
+
+
+def _smooth3(A: np.ndarray, fact: float) -> np.ndarray:
+    """smooth!  miniapps/benchmarks/stokes3D/solvi/SolVi3D.jl:9-12 (ParallelStencil @inn/@d2_*i)."""
+    A2 = A.copy(order="F")
+    c = A[1:-1, 1:-1, 1:-1]
+    d2x = (A[2:, 1:-1, 1:-1] - c) - (c - A[:-2, 1:-1, 1:-1])
+    d2y = (A[1:-1, 2:, 1:-1] - c) - (c - A[1:-1, :-2, 1:-1])
+    d2z = (A[1:-1, 1:-1, 2:] - c) - (c - A[1:-1, 1:-1, :-2])
+    A2[1:-1, 1:-1, 1:-1] = c + 1.0 / 6.1 / fact * (d2x + d2y + d2z)
+    return A2
+
+
+def solvi3d(nx=31, ny=31, nz=31, *, Δη=1.0e-3, lx=1.0e1, ly=1.0e1, lz=1.0e1, rc=1.0e0, εbg=1.0e0, igg: IGG | None = None,
+            smooth_passes: int = 10):
+    """3D SolVi inclusion benchmark (config 4): miniapps/benchmarks/stokes3D/solvi/SolVi3D.jl:45-130.
+
+    Returns host fields (numpy, column-major) and parameters for variant 3D-VA:
+    η with a low-viscosity sphere smoothed 10×, G = 1, Kb = Inf, dt = Inf, pure-shear velocity
+    (pureshear_bc!, src/boundaryconditions/pure_shear.jl:15-32 incl. quirk Q18), free slip on all six faces,
+    ρg = 0, PTStokesCoeffs(li, di; CFL = 1/√3), kwargs = (iterMax = 5000, nout = 100).
+    """
+    igg = igg or IGG()
+    ni = (nx, ny, nz)
+    li = (lx, ly, lz)
+    grid = Geometry(ni, li, origin=(0.0, 0.0, 0.0), igg=igg)
+    di = grid.di.center
+    dx, dy, dz = di
+    pt_stokes = PTStokesCoeffs(li, di, CFL=1 / math.sqrt(3))
+
+    # viscosity  SolVi3D.jl:14-45  (local indices, exactly as the reference kernel)
+    ix = np.arange(nx, dtype=np.float64)[:, None, None]
+    iy = np.arange(ny, dtype=np.float64)[None, :, None]
+    iz = np.arange(nz, dtype=np.float64)[None, None, :]
+    rad = np.sqrt((ix * dx + 0.5 * dx - 0.5 * lx) ** 2 + (iy * dy + 0.5 * dy - 0.5 * ly) ** 2 + (iz * dz + 0.5 * dz - 0.5 * lz) ** 2)
+    η = np.full(ni, 1.0, order="F")
+    η[rad <= rc] = Δη
+    for _ in range(smooth_passes):
+        η = _smooth3(η, 1.0)
+    η = np.asfortranarray(η)
+
+    xv, yv, zv = grid.xvi
+    Vx = np.zeros((nx + 1, ny + 2, nz + 2), order="F")
+    Vy = np.zeros((nx + 2, ny + 1, nz + 2), order="F")
+    Vz = np.zeros((nx + 2, ny + 2, nz + 1), order="F")
+    Vx[:, 1:-1, 1:-1] = (εbg * xv)[:, None, None]
+    # Q18: the reference uses the x-vertex coordinates for Vy (only well-formed when nx == ny)
+    Vy[1:-1, :, 1:-1] = (εbg * (xv if nx == ny else yv))[None, :, None]
+    Vz[1:-1, 1:-1, :] = (-εbg * zv)[None, None, :]
+
+    flow_bcs = VelocityBoundaryConditions(
+        free_slip=dict(left=True, right=True, top=True, bot=True, back=True, front=True),
+        no_slip=dict(left=False, right=False, top=False, bot=False, back=False, front=False),
+    )
+    fields = dict(Vx=Vx, Vy=Vy, Vz=Vz, eta=η, G=np.full(ni, 1.0, order="F"), K=np.full(ni, np.inf, order="F"),
+                  rhogx=np.zeros(ni, order="F"), rhogy=np.zeros(ni, order="F"), rhogz=np.zeros(ni, order="F"))
+    return SimpleNamespace(ni=ni, li=li, di=di, grid=grid, igg=igg, pt_stokes=pt_stokes, flow_bcs=flow_bcs, dt=math.inf,
+                           fields=fields, kwargs=dict(iterMax=5000, nout=100, verbose=False))
+
+
+def random_stokes3d(ni, seed=20261017, *, dt=0.7, finite_K=True):
+    """Seeded random state for kernel-level parity fuzzing of variant 3D-VA:
+    V, τ ~ U(−1,1), P ~ U(0,1), η ~ 10^U(−3,0), G ~ U(0.5,2), K ~ U(1,4) (or Inf), ρg ~ U(−1,1)."""
+    rng = np.random.default_rng(seed)
+    nx, ny, nz = ni
+    U = lambda *s: np.asfortranarray(rng.uniform(-1.0, 1.0, size=s))
+    f = dict(
+        Vx=U(nx + 1, ny + 2, nz + 2), Vy=U(nx + 2, ny + 1, nz + 2), Vz=U(nx + 2, ny + 2, nz + 1),
+        P=np.asfortranarray(rng.uniform(0, 1, size=ni)), P0=np.asfortranarray(rng.uniform(0, 1, size=ni)),
+        Q=np.asfortranarray(rng.uniform(-0.1, 0.1, size=ni)),
+        txx=U(*ni), tyy=U(*ni), tzz=U(*ni), tyz=U(nx, ny + 1, nz + 1), txz=U(nx + 1, ny, nz + 1), txy=U(nx + 1, ny + 1, nz),
+        txx_o=U(*ni), tyy_o=U(*ni), tzz_o=U(*ni), tyz_o=U(nx, ny + 1, nz + 1), txz_o=U(nx + 1, ny, nz + 1),
+        txy_o=U(nx + 1, ny + 1, nz),
+        eta=np.asfortranarray(10.0 ** rng.uniform(-3, 0, size=ni)),
+        G=np.asfortranarray(rng.uniform(0.5, 2.0, size=ni)),
+        K=np.asfortranarray(rng.uniform(1.0, 4.0, size=ni)) if finite_K else np.full(ni, np.inf, order="F"),
+        rhogx=U(*ni), rhogy=U(*ni), rhogz=U(*ni),
+    )
+    li = (1.0, 1.3, 0.9)
+    grid = Geometry(ni, li)
+    pt = PTStokesCoeffs(li, grid.di.center)
+    return SimpleNamespace(ni=tuple(ni), li=li, di=grid.di.center, grid=grid, igg=IGG(), pt_stokes=pt, dt=dt, fields=f)

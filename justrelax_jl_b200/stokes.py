@@ -1,0 +1,227 @@
+"""Host side of the Stokes PT solvers — the Python twin of the methods a Julia
+`JustRelaxB200Ext` adds to JustRelax{2,3}D (src/ext/CUDA/3D.jl:375-377, 195-218, 358-372):
+
+    solve_(stokes, pt_stokes, grid|di, flow_bcs, ρg, K, G, dt, igg; kwargs=dict(iterMax, nout, ...))   3D-VA
+    flow_bcs_(stokes, bcs), compute_maxloc_(B, A, window), velocity2displacement_(stokes, dt) ...
+
+Python has no `!`: a trailing underscore marks the mutating functions (`solve!` → `solve_`).
+Like the reference, the solver options travel in ONE keyword literally named `kwargs`
+(quirk Q1, src/stokes/Stokes3D.jl:18-23).  Every function here only marshals arguments into the
+C ABI of libjrb200 (include/jrb200.h); there is no numerical code and no CPU fallback on this side.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from types import SimpleNamespace
+from typing import Optional
+
+import numpy as np
+
+from . import _abi
+from .types import (B200BackendTrait, CPUBackendTrait, Geometry, IGG, StokesArrays, VelocityBoundaryConditions,
+                    DisplacementBoundaryConditions, AbstractFlowBoundaryConditions, backend, data_ptr, is_device_array,
+                    legacy_uniform_grid)
+
+_ctx_cache = {}
+
+
+def context(device: Optional[int] = None):
+    """One libjrb200 context per CUDA device, running on torch's current stream of that device."""
+    import torch
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("justrelax_jl_b200 needs a CUDA device (B200); there is no CPU fallback")
+    dev = torch.cuda.current_device() if device is None else int(device)
+    if dev not in _ctx_cache:
+        h = C.c_void_p()
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _abi.check(_abi.lib().jr_context_create(dev, C.c_void_p(stream) if stream else None, C.byref(h)))
+        _ctx_cache[dev] = h
+    return _ctx_cache[dev]
+
+
+def set_flags(flags: int, device: Optional[int] = None):
+    _abi.check(_abi.lib().jr_context_set_flags(context(device), int(flags)))
+
+
+def build_fields(slots: dict, ni):
+    """Pack name→array into a jr_fields struct; returns (struct, keepalive)."""
+    names = _abi.field_names()
+    Fields = _abi.make_fields_struct(len(names))
+    fs = Fields()
+    fs.ndim = len(ni)
+    for d in range(3):
+        fs.n[d] = int(ni[d]) if d < len(ni) else 1
+    for i, nm in enumerate(names):
+        a = slots.get(nm)
+        fs.f[i] = None if a is None else data_ptr(a)
+    unknown = set(slots) - set(names)
+    if unknown:
+        raise KeyError(f"unknown field slots {sorted(unknown)}")
+    return fs
+
+
+def build_opts(pt_stokes, _di, dt, flow_bcs, n_g, *, iterMax, nout, OptsType=_abi.StokesOpts, viscosity_relaxation=1e-2,
+               λ_relaxation=0.2, viscosity_cutoff=(-math.inf, math.inf), iterMin=100, strain_rate_ni_only=0):
+    o = OptsType()
+    o.r, o.theta_dtau, o.eta_dtau = pt_stokes.r, pt_stokes.θ_dτ, pt_stokes.ηdτ
+    o.eps_rel, o.eps_abs = pt_stokes.ϵ_rel, pt_stokes.ϵ_abs
+    for d in range(3):
+        o._di[d] = float(_di[d]) if d < len(_di) else 0.0
+        o.n_g[d] = int(n_g[d]) if d < len(n_g) else 1
+    o.dt = float(dt)
+    o.iterMax, o.nout = int(iterMax), int(nout)
+    for name in ("free_slip", "no_slip", "periodic"):
+        fl = flow_bcs.flags(name)
+        arr = getattr(o, name)
+        for q in range(6):
+            arr[q] = fl[q]
+    o.viscosity_relaxation, o.lambda_relaxation = float(viscosity_relaxation), float(λ_relaxation)
+    o.visc_cutoff_lo, o.visc_cutoff_hi = float(viscosity_cutoff[0]), float(viscosity_cutoff[1])
+    o.iterMin = int(iterMin)
+    o.strain_rate_ni_only = int(strain_rate_ni_only)
+    return o
+
+
+class _Hist:
+    """history vectors of the returned NamedTuple (Stokes3D.jl:64-69)"""
+
+    def __init__(self, cap: int, ResultType):
+        self.cap = cap
+        self.err_evo1 = np.zeros(cap)
+        self.err_evo2 = np.zeros(cap, dtype=np.int64)
+        self.norm_Rx, self.norm_Ry, self.norm_Rz, self.norm_divV = (np.zeros(cap) for _ in range(4))
+        r = ResultType()
+        dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+        r.err_evo1, r.err_evo2 = dp(self.err_evo1), self.err_evo2.ctypes.data_as(C.POINTER(C.c_int64))
+        r.norm_Rx, r.norm_Ry, r.norm_Rz, r.norm_divV = dp(self.norm_Rx), dp(self.norm_Ry), dp(self.norm_Rz), dp(self.norm_divV)
+        self.res = r
+
+    def named(self, ndim: int, with_time=True):
+        n = int(self.res.nhist)
+        out = dict(iter=int(self.res.iter), err_evo1=self.err_evo1[:n].copy(), err_evo2=self.err_evo2[:n].copy(),
+                   norm_Rx=self.norm_Rx[:n].copy(), norm_Ry=self.norm_Ry[:n].copy())
+        if ndim == 3:
+            out["norm_Rz"] = self.norm_Rz[:n].copy()
+        out["norm_divV"] = self.norm_divV[:n].copy()
+        if with_time and hasattr(self.res, "time_s"):
+            it = max(int(self.res.iter) - 1, 1)
+            out["time"] = float(self.res.time_s)
+            out["av_time"] = float(self.res.time_s) / it
+            out["kernel_launches"] = int(self.res.kernel_launches)
+        return SimpleNamespace(**out)
+
+
+def _grid_of(stokes, grid_or_di, igg):
+    if isinstance(grid_or_di, Geometry):
+        return grid_or_di
+    di = grid_or_di.center if hasattr(grid_or_di, "center") else grid_or_di
+    return legacy_uniform_grid(stokes.ni, tuple(di), igg)
+
+
+def va_slots(stokes: StokesArrays, ρg, K, G) -> dict:
+    d = stokes.slots()
+    d["rhogx"], d["rhogy"] = ρg[0], ρg[1]
+    if len(ρg) > 2:
+        d["rhogz"] = ρg[2]
+    d["K"], d["G"] = K, G
+    return d
+
+
+def solve_(stokes: StokesArrays, pt_stokes, grid, flow_bcs, ρg, K, G, dt, igg: Optional[IGG] = None, *, kwargs=None):
+    """3D visco-elastic Stokes solve with K, G arrays (variant 3D-VA).
+
+    Reference: solve!(stokes, pt_stokes, grid::Geometry{3}|di, flow_bcs, ρg, K, G, dt, igg; kwargs)
+    src/stokes/Stokes3D.jl:18-41 (entry), :25-186 (loop) — dispatched like src/ext/CUDA/3D.jl:375-377.
+    Returns (iter, err_evo1, err_evo2, norm_Rx, norm_Ry, norm_Rz, norm_∇V→norm_divV, time, av_time).
+    """
+    kw = dict(iterMax=10e3, nout=500, b_width=(4, 4, 4), verbose=True, viscosity_relaxation=1e-2)
+    kw.update(kwargs or {})
+    tr = backend(stokes)
+    if isinstance(tr, CPUBackendTrait):
+        raise RuntimeError("solve_: StokesArrays live on the host (CPUBackend). This package only provides the B200 "
+                           "backend; the CPU solver is JustRelax.jl's own. No CPU fallback.")
+    if not isinstance(flow_bcs, AbstractFlowBoundaryConditions):
+        raise TypeError(f"Unknown boundary conditions type: {type(flow_bcs)}")  # types/displacement.jl:68-70
+    if len(stokes.ni) != 3:
+        raise NotImplementedError("2D solve_ with K,G arrays is provided by stokes2d.solve_")
+    if isinstance(flow_bcs, DisplacementBoundaryConditions):
+        raise NotImplementedError("DisplacementBoundaryConditions are outside the supported subset (SURVEY §8f-3)")
+    for a in (*ρg, K, G):
+        if not is_device_array(a):
+            raise ValueError("ρg, K, G must be B200 arrays (use PTArray(B200Backend)(x))")
+    igg = igg or IGG()
+    grid = _grid_of(stokes, grid, igg)
+    _di = grid._di.center
+    opts = build_opts(pt_stokes, _di, dt, flow_bcs, igg.n_g(stokes.ni), iterMax=kw["iterMax"], nout=kw["nout"],
+                      viscosity_relaxation=kw["viscosity_relaxation"])
+    fs = build_fields(va_slots(stokes, ρg, K, G), stokes.ni)
+    hist = _Hist(int(opts.iterMax // max(opts.nout, 1)) + 3, _abi.StokesResult)
+    st = _abi.lib().jr_stokes3d_solve_VA(context(), C.byref(fs), C.byref(opts), C.byref(hist.res))
+    if st == _abi.JR_ERR_NAN:
+        raise RuntimeError("NaN(s)")  # Stokes3D.jl:162
+    _abi.check(st)
+    out = hist.named(3)
+    if kw.get("verbose") and igg.me == 0:
+        for c in range(len(out.err_evo1)):
+            print("iter = %d, abs_err = %1.3e [norm_Rx=%1.3e, norm_Ry=%1.3e, norm_Rz=%1.3e, norm_∇V=%1.3e]" % (
+                out.err_evo2[c], out.err_evo1[c], out.norm_Rx[c], out.norm_Ry[c], out.norm_Rz[c], out.norm_divV[c]))
+    return out
+
+
+def iterate_(stokes: StokesArrays, pt_stokes, grid, flow_bcs, ρg, K, G, dt, niter: int, igg: Optional[IGG] = None):
+    """Run exactly `niter` PT iterations of variant 3D-VA (benchmark / fixed-iteration parity)."""
+    igg = igg or IGG()
+    grid = _grid_of(stokes, grid, igg)
+    opts = build_opts(pt_stokes, grid._di.center, dt, flow_bcs, igg.n_g(stokes.ni), iterMax=niter, nout=max(niter, 1))
+    fs = build_fields(va_slots(stokes, ρg, K, G), stokes.ni)
+    res = _abi.StokesResult()
+    _abi.check(_abi.lib().jr_stokes3d_iterate_VA(context(), C.byref(fs), C.byref(opts), int(niter), C.byref(res)))
+    return SimpleNamespace(iter=int(res.iter), time=float(res.time_s), kernel_launches=int(res.kernel_launches))
+
+
+def flow_bcs_(stokes, bcs: AbstractFlowBoundaryConditions):
+    """flow_bcs!(stokes, bcs) — src/ext/CUDA/3D.jl:195-218 → BoundaryConditions.jl:65-100."""
+    if isinstance(backend(stokes), CPUBackendTrait):
+        raise RuntimeError("flow_bcs_: host arrays; this package only provides the B200 backend")
+    A = stokes.U if isinstance(bcs, DisplacementBoundaryConditions) else stokes.V
+    comps = list(A)
+    if len(stokes.ni) != 3:
+        raise NotImplementedError("2D flow_bcs_ lives in stokes2d")
+    _abi.check(_abi.lib().jr_flow_bcs3d(context(), data_ptr(comps[0]), data_ptr(comps[1]), data_ptr(comps[2]),
+                                         _abi.i32x(stokes.ni), _abi.i32x(bcs.flags("free_slip")),
+                                         _abi.i32x(bcs.flags("no_slip")), _abi.i32x(bcs.flags("periodic"))))
+
+
+def compute_maxloc_(B, A, window=(1, 1, 1)):
+    """compute_maxloc!(B, A; window) — src/Utils.jl:409-461."""
+    if not (is_device_array(A) and is_device_array(B)):
+        raise RuntimeError("compute_maxloc_: B200 arrays required")
+    if A.dim() != 3:
+        raise NotImplementedError
+    _abi.check(_abi.lib().jr_maxloc3d(context(), data_ptr(B), data_ptr(A), _abi.i32x(A.shape), _abi.i32x(window)))
+
+
+def velocity2displacement_(stokes, dt):
+    """velocity2displacement!(stokes, dt) — src/types/displacement.jl:1-29."""
+    for u, v in zip(stokes.U, stokes.V):
+        if v is not None:
+            _abi.check(_abi.lib().jr_scale_copy(context(), data_ptr(u), data_ptr(v), float(dt), int(np.prod(v.shape))))
+    _abi.check(_abi.lib().jr_context_synchronize(context()))
+
+
+def displacement2velocity_(stokes, dt):
+    """displacement2velocity!(stokes, dt) — src/types/displacement.jl:33-60 (V = U * inv(dt))."""
+    for u, v in zip(stokes.U, stokes.V):
+        if v is not None:
+            _abi.check(_abi.lib().jr_scale_copy(context(), data_ptr(v), data_ptr(u), 1.0 / float(dt), int(np.prod(v.shape))))
+    _abi.check(_abi.lib().jr_context_synchronize(context()))
+
+
+def norm_interior(A, interior: bool = True) -> float:
+    """sqrt(Σ A[2:end-1,…]^2): local part of norm_mpi (src/Utils.jl:698-701)."""
+    out = C.c_double()
+    shp = list(A.shape) + [1] * (3 - A.dim())
+    _abi.check(_abi.lib().jr_sumsq(context(), data_ptr(A), _abi.i32x(shp), int(interior), C.byref(out)))
+    return math.sqrt(out.value)

@@ -1,0 +1,201 @@
+"""ctypes wrapper of the CPU ORACLE (oracle/libjr_oracle.so) — test infrastructure, NOT product code.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / `--impl reference` legs import this.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libjr_oracle.so")
+_lib = None
+
+
+def build(force: bool = False):
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".c", ".h"))]
+    if force or not os.path.exists(LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            build()
+        L = C.CDLL(LIB_PATH)
+        L.orc_field_name.restype = C.c_char_p
+        L.orc_mini3.restype = C.c_double
+        L.orc_mini2.restype = C.c_double
+        L.orc_sumsq_interior.restype = C.c_double
+        _lib = L
+    return _lib
+
+
+def field_names():
+    L = lib()
+    return [L.orc_field_name(i).decode() for i in range(L.orc_field_count())]
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def mini3(name, A, _d, i, j, k):
+    A = np.asfortranarray(A, dtype=np.float64)
+    return lib().orc_mini3(name.encode(), _dp(A), *map(C.c_int, A.shape), C.c_double(_d), C.c_int(i), C.c_int(j), C.c_int(k))
+
+
+def mini2(name, A, _d, i, j):
+    A = np.asfortranarray(A, dtype=np.float64)
+    shp = A.shape if A.ndim == 2 else (A.shape[0], 1)
+    return lib().orc_mini2(name.encode(), _dp(A), *map(C.c_int, shp), C.c_double(_d), C.c_int(i), C.c_int(j))
+
+
+def make_fields(slots: dict, ni):
+    """slots: name -> column-major float64 numpy array (kept alive by the caller)."""
+    names = field_names()
+
+    class Fields(C.Structure):
+        _fields_ = [("ndim", C.c_int32), ("n", C.c_int32 * 3), ("f", C.c_void_p * len(names))]
+
+    fs = Fields()
+    fs.ndim = len(ni)
+    for d in range(3):
+        fs.n[d] = int(ni[d]) if d < len(ni) else 1
+    for i, nm in enumerate(names):
+        a = slots.get(nm)
+        if a is None:
+            fs.f[i] = None
+        else:
+            assert a.dtype == np.float64 and a.flags.f_contiguous, nm
+            fs.f[i] = a.ctypes.data
+    unknown = set(slots) - set(names)
+    assert not unknown, unknown
+    return fs
+
+
+def alloc_stokes(ni, init: dict | None = None) -> dict:
+    """Host StokesArrays (all slots the solvers touch), zero-initialised like constructors/stokes.jl,
+    η = η_vep = ηv = 1, then overwritten by `init`."""
+    nd = len(ni)
+    z = lambda *s: np.zeros(s, order="F")
+    d = {}
+    if nd == 3:
+        nx, ny, nz = ni
+        c, v = (nx, ny, nz), (nx + 1, ny + 1, nz + 1)
+        shapes = dict(Vx=(nx + 1, ny + 2, nz + 2), Vy=(nx + 2, ny + 1, nz + 2), Vz=(nx + 2, ny + 2, nz + 1),
+                      xy=(nx + 1, ny + 1, nz), yz=(nx, ny + 1, nz + 1), xz=(nx + 1, ny, nz + 1),
+                      Rx=(nx - 1, ny, nz), Ry=(nx, ny - 1, nz), Rz=(nx, ny, nz - 1))
+    else:
+        nx, ny = ni
+        c, v = (nx, ny), (nx + 1, ny + 1)
+        shapes = dict(Vx=(nx + 1, ny + 2), Vy=(nx + 2, ny + 1), xy=(nx + 1, ny + 1), Rx=(nx - 1, ny), Ry=(nx, ny - 1))
+    for nm in ("P", "P0", "divV", "Q", "EII_pl", "EVol_pl", "e_vol_pl", "eta_vep", "etatau", "RP", "divU", "lam", "dPpsi",
+               "eta", "rhogx", "rhogy", "K", "G"):
+        d[nm] = z(*c)
+    d["eta"][...] = 1.0
+    d["eta_vep"][...] = 1.0
+    d["etav"] = np.ones(v, order="F")
+    d["lamv"] = z(*v)
+    d["Vx"], d["Vy"], d["Ux"], d["Uy"] = z(*shapes["Vx"]), z(*shapes["Vy"]), z(*shapes["Vx"]), z(*shapes["Vy"])
+    d["Rx"], d["Ry"] = z(*shapes["Rx"]), z(*shapes["Ry"])
+    comps_c = ("xx", "yy", "zz") if nd == 3 else ("xx", "yy")
+    shear = ("yz", "xz", "xy") if nd == 3 else ("xy",)
+    for pre, suf in (("t", ""), ("t", "_o"), ("e", ""), ("p", ""), ("d", "")):
+        for cc in comps_c:
+            d[f"{pre}{cc}{suf}"] = z(*c)
+        for sh in shear:
+            d[f"{pre}{sh}{suf}"] = z(*shapes[sh])
+            d[f"{pre}{sh}{suf}_c"] = z(*c)
+        d[f"{pre}II{suf}"] = z(*c)
+    if nd == 3:
+        d["Vz"], d["Uz"], d["Rz"], d["rhogz"] = z(*shapes["Vz"]), z(*shapes["Vz"]), z(*shapes["Rz"]), z(*c)
+        d["wyz"], d["wxz"], d["wxy"] = z(*shapes["yz"]), z(*shapes["xz"]), z(*shapes["xy"])
+    else:
+        d["wxy"] = z(*shapes["xy"])
+        for nm in ("txx_v", "tyy_v", "txx_o_v", "tyy_o_v"):
+            d[nm] = z(*v)
+    if init:
+        for k, a in init.items():
+            assert k in d, k
+            assert d[k].shape == a.shape, (k, d[k].shape, a.shape)
+            d[k][...] = a
+    return d
+
+
+class StokesOpts(C.Structure):
+    _fields_ = [
+        ("r", C.c_double), ("theta_dtau", C.c_double), ("eta_dtau", C.c_double),
+        ("eps_rel", C.c_double), ("eps_abs", C.c_double),
+        ("_di", C.c_double * 3), ("dt", C.c_double),
+        ("iterMax", C.c_int64), ("nout", C.c_int64),
+        ("n_g", C.c_int32 * 3),
+        ("free_slip", C.c_int32 * 6), ("no_slip", C.c_int32 * 6), ("periodic", C.c_int32 * 6),
+        ("viscosity_relaxation", C.c_double), ("lambda_relaxation", C.c_double),
+        ("visc_cutoff_lo", C.c_double), ("visc_cutoff_hi", C.c_double),
+        ("iterMin", C.c_int64), ("strain_rate_ni_only", C.c_int32),
+    ]
+
+
+class StokesResult(C.Structure):
+    _fields_ = [
+        ("iter", C.c_int64), ("nhist", C.c_int64), ("err", C.c_double),
+        ("err_evo1", C.POINTER(C.c_double)), ("err_evo2", C.POINTER(C.c_int64)),
+        ("norm_Rx", C.POINTER(C.c_double)), ("norm_Ry", C.POINTER(C.c_double)),
+        ("norm_Rz", C.POINTER(C.c_double)), ("norm_divV", C.POINTER(C.c_double)),
+    ]
+
+
+def make_opts(pt, _di, dt, flags: dict, n_g, *, iterMax, nout, viscosity_relaxation=1e-2, lambda_relaxation=0.2,
+              viscosity_cutoff=(-np.inf, np.inf), iterMin=100, strain_rate_ni_only=0):
+    """pt: object with r, θ_dτ, ηdτ, ϵ_rel, ϵ_abs; flags: dict(free_slip=[6], no_slip=[6], periodic=[6])."""
+    o = StokesOpts()
+    o.r, o.theta_dtau, o.eta_dtau, o.eps_rel, o.eps_abs = pt.r, pt.θ_dτ, pt.ηdτ, pt.ϵ_rel, pt.ϵ_abs
+    for d in range(3):
+        o._di[d] = float(_di[d]) if d < len(_di) else 0.0
+        o.n_g[d] = int(n_g[d]) if d < len(n_g) else 1
+    o.dt = float(dt)
+    o.iterMax, o.nout = int(iterMax), int(nout)
+    for nm in ("free_slip", "no_slip", "periodic"):
+        arr = getattr(o, nm)
+        for q in range(6):
+            arr[q] = int(flags.get(nm, [0] * 6)[q])
+    o.viscosity_relaxation, o.lambda_relaxation = viscosity_relaxation, lambda_relaxation
+    o.visc_cutoff_lo, o.visc_cutoff_hi = viscosity_cutoff
+    o.iterMin, o.strain_rate_ni_only = int(iterMin), int(strain_rate_ni_only)
+    return o
+
+
+class Hist:
+    def __init__(self, cap):
+        self.err_evo1 = np.zeros(cap)
+        self.err_evo2 = np.zeros(cap, dtype=np.int64)
+        self.norm_Rx, self.norm_Ry, self.norm_Rz, self.norm_divV = (np.zeros(cap) for _ in range(4))
+        r = StokesResult()
+        r.err_evo1, r.err_evo2 = _dp(self.err_evo1), self.err_evo2.ctypes.data_as(C.POINTER(C.c_int64))
+        r.norm_Rx, r.norm_Ry, r.norm_Rz, r.norm_divV = _dp(self.norm_Rx), _dp(self.norm_Ry), _dp(self.norm_Rz), _dp(self.norm_divV)
+        self.res = r
+
+    def out(self):
+        n = int(self.res.nhist)
+        return dict(iter=int(self.res.iter), err_evo1=self.err_evo1[:n].copy(), err_evo2=self.err_evo2[:n].copy(),
+                    norm_Rx=self.norm_Rx[:n].copy(), norm_Ry=self.norm_Ry[:n].copy(), norm_Rz=self.norm_Rz[:n].copy(),
+                    norm_divV=self.norm_divV[:n].copy())
+
+
+def solve3d_VA(slots, ni, opts):
+    fs = make_fields(slots, ni)
+    h = Hist(int(opts.iterMax // max(opts.nout, 1)) + 3)
+    st = lib().orc_solve3d_VA(C.byref(fs), C.byref(opts), C.byref(h.res))
+    out = h.out()
+    out["status"] = st
+    return out
+
+
+def iterate3d_VA(slots, ni, opts, niter):
+    fs = make_fields(slots, ni)
+    return lib().orc_iterate3d_VA(C.byref(fs), C.byref(opts), C.c_int64(niter))

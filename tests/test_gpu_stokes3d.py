@@ -1,0 +1,147 @@
+"""GPU parity tests for variant 3D-VA (through the C ABI) against the CPU oracle.
+
+Tolerances (north star): per-field max relative difference <= 1e-12 after a fixed number of PT iterations,
+iteration count to convergence within ±1 %, converged fields within 1e-8.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from util import bc_flags, compare_slots, device_stokes
+
+pytestmark = pytest.mark.gpu
+
+FIELDS_STATE = ["Vx", "Vy", "Vz", "P", "txx", "tyy", "tzz", "tyz", "txz", "txy"]
+FIELDS_DIAG = ["divV", "RP", "exx", "eyy", "ezz", "eyz", "exz", "exy", "Rx", "Ry", "Rz", "Ux", "Uy", "Uz", "etatau"]
+TOL = 1.0e-12
+
+
+def _run_both(oracle, s, niter, flags, unfused):
+    from justrelax_jl_b200 import _abi, stokes as jst
+    from justrelax_jl_b200.types import VelocityBoundaryConditions
+
+    d = oracle.alloc_stokes(s.ni, s.fields)
+    st, extra = device_stokes(s.ni, d)
+    opts = oracle.make_opts(s.pt_stokes, s.grid._di.center, s.dt, flags, s.ni, iterMax=niter, nout=niter)
+    oracle.iterate3d_VA(d, s.ni, opts, niter)
+    names6 = ("left", "right", "front", "back", "top", "bot")
+    bcs = VelocityBoundaryConditions(free_slip={k: bool(v) for k, v in zip(names6, flags["free_slip"])},
+                                     no_slip={k: bool(v) for k, v in zip(names6, flags["no_slip"])},
+                                     periodic={k: bool(v) for k, v in zip(names6, flags["periodic"])})
+    jst.set_flags(_abi.JR_FLAG_UNFUSED if unfused else 0)
+    try:
+        ρg = (extra["rhogx"], extra["rhogy"], extra["rhogz"])
+        r = jst.iterate_(st, s.pt_stokes, s.grid, bcs, ρg, extra["K"], extra["G"], s.dt, niter)
+    finally:
+        jst.set_flags(0)
+    assert r.kernel_launches > 0
+    return st, d
+
+
+@pytest.mark.parametrize("unfused", [True, False], ids=["unfused", "fused"])
+@pytest.mark.parametrize("ni", [(16, 16, 16), (33, 17, 15), (7, 6, 5), (40, 37, 66)])
+@pytest.mark.parametrize("dt,finite_K", [(0.7, True), (np.inf, False)])
+def test_fixed_iterations_random_state(oracle, ni, dt, finite_K, unfused):
+    from justrelax_jl_b200 import setups
+
+    s = setups.random_stokes3d(ni, seed=20261017 + ni[0], dt=dt, finite_K=finite_K)
+    flags = dict(free_slip=[1] * 6, no_slip=[0] * 6, periodic=[0] * 6)
+    for niter in (1, 2, 5):
+        st, d = _run_both(oracle, s, niter, flags, unfused)
+        compare_slots(st.slots(), d, FIELDS_STATE + FIELDS_DIAG, TOL, f"ni={ni} niter={niter}")
+
+
+@pytest.mark.parametrize("unfused", [True, False], ids=["unfused", "fused"])
+def test_mixed_boundary_flags(oracle, unfused):
+    from justrelax_jl_b200 import setups
+
+    s = setups.random_stokes3d((12, 10, 9), seed=5)
+    flags = dict(free_slip=[1, 0, 1, 0, 0, 1], no_slip=[0, 1, 0, 0, 1, 0], periodic=[0] * 6)
+    st, d = _run_both(oracle, s, 3, flags, unfused)
+    compare_slots(st.slots(), d, FIELDS_STATE + FIELDS_DIAG, TOL, "mixed BC")
+
+
+@pytest.mark.parametrize("unfused", [True, False], ids=["unfused", "fused"])
+def test_solvi3d_fixed_iterations(oracle, unfused):
+    from justrelax_jl_b200 import setups
+
+    s = setups.solvi3d(31, 31, 31)
+    dd = oracle.alloc_stokes(s.ni, s.fields)
+    opts = oracle.make_opts(s.pt_stokes, s.grid._di.center, s.dt, bc_flags(s.flow_bcs), s.ni, iterMax=1, nout=1)
+    fs = oracle.make_fields(dd, s.ni)
+    oracle.lib().orc_flow_bcs3(C.byref(fs), C.byref(opts), 0)
+    s.fields = {k: dd[k] for k in s.fields}
+    st, d = _run_both(oracle, s, 50, bc_flags(s.flow_bcs), unfused)
+    w = compare_slots(st.slots(), d, FIELDS_STATE + FIELDS_DIAG, TOL, "solvi3d 31^3 x50")
+    print("worst rel diff:", max(w.values()))
+
+
+@pytest.mark.parametrize("unfused", [True, False], ids=["unfused", "fused"])
+def test_solvi3d_solve_matches_reference_test(oracle, unfused):
+    """test/test_stokes_solvi3D.jl through the public API: 16^3, norm_Rx[end] < 1e-8, and the same iteration
+    count / history / converged fields as the oracle."""
+    from justrelax_jl_b200 import _abi, setups, stokes as jst, to_host
+
+    s = setups.solvi3d(16, 16, 16)
+    d = oracle.alloc_stokes(s.ni, s.fields)
+    st, extra = device_stokes(s.ni, d)
+    jst.flow_bcs_(st, s.flow_bcs)
+    opts = oracle.make_opts(s.pt_stokes, s.grid._di.center, s.dt, bc_flags(s.flow_bcs), s.ni, iterMax=5000, nout=100)
+    fs = oracle.make_fields(d, s.ni)
+    oracle.lib().orc_flow_bcs3(C.byref(fs), C.byref(opts), 0)
+    assert np.array_equal(to_host(st.V.Vx), d["Vx"]) and np.array_equal(to_host(st.V.Vz), d["Vz"])
+    ref = oracle.solve3d_VA(d, s.ni, opts)
+    jst.set_flags(_abi.JR_FLAG_UNFUSED if unfused else 0)
+    try:
+        out = jst.solve_(st, s.pt_stokes, s.grid, s.flow_bcs, (extra["rhogx"], extra["rhogy"], extra["rhogz"]), extra["K"],
+                         extra["G"], s.dt, s.igg, kwargs=s.kwargs)
+    finally:
+        jst.set_flags(0)
+    assert out.norm_Rx[-1] < 1.0e-8  # the reference test's own criterion
+    assert abs(out.iter - ref["iter"]) <= 0.01 * ref["iter"]
+    assert np.array_equal(out.err_evo2, ref["err_evo2"])
+    assert np.allclose(out.norm_divV, ref["norm_divV"], rtol=1e-10)
+    assert np.allclose(out.norm_Rx[:10], ref["norm_Rx"][:10], rtol=1e-8)
+    compare_slots(st.slots(), d, FIELDS_STATE + ["txx_o", "tyz_o"], 1.0e-8, "converged fields")
+
+
+def test_standalone_kernels(oracle):
+    from justrelax_jl_b200 import B200Backend, PTArray, stokes as jst, to_host, StokesArrays
+    from justrelax_jl_b200.types import VelocityBoundaryConditions
+
+    rng = np.random.default_rng(7)
+    A = np.asfortranarray(rng.uniform(size=(9, 8, 7)))
+    dA, dB = PTArray(B200Backend)(A), PTArray(B200Backend)(np.zeros_like(A, order="F"))
+    jst.compute_maxloc_(dB, dA)
+    B = np.zeros_like(A, order="F")
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    oracle.lib().orc_maxloc3(dp(B), dp(A), 9, 8, 7, 1, 1, 1)
+    assert np.array_equal(to_host(dB), B)
+    n = jst.norm_interior(dA)
+    assert n == pytest.approx(np.sqrt(np.sum(A[1:-1, 1:-1, 1:-1] ** 2)), rel=1e-14)
+    # BCs incl. periodic
+    ni = (6, 5, 4)
+    st = StokesArrays(B200Backend, *ni, vertex_normals=False)
+    h = {k: np.asfortranarray(rng.uniform(size=tuple(v.shape))) for k, v in (("Vx", st.V.Vx), ("Vy", st.V.Vy), ("Vz", st.V.Vz))}
+    for per in (False, True):
+        for k in h:
+            st.slots()[k].copy_(PTArray(B200Backend)(h[k]))
+        if per:
+            bcs = VelocityBoundaryConditions(free_slip=dict(left=False, right=False, front=True, back=True, top=False, bot=False),
+                                             no_slip=dict(left=False, right=False, front=False, back=False, top=False, bot=False),
+                                             periodic=dict(left=True, right=True, front=False, back=False, top=True, bot=True))
+        else:
+            bcs = VelocityBoundaryConditions(free_slip=dict(left=True, right=True, front=False, back=False, top=True, bot=False),
+                                             no_slip=dict(left=False, right=False, front=True, back=True, top=False, bot=True))
+        jst.flow_bcs_(st, bcs)
+        hh = {k: v.copy(order="F") for k, v in h.items()}
+        i32 = lambda v: (C.c_int32 * len(v))(*v)
+        L = oracle.lib()
+        if any(bcs.flags("no_slip")):
+            L.orc_no_slip3(dp(hh["Vx"]), dp(hh["Vy"]), dp(hh["Vz"]), i32(ni), i32(bcs.flags("no_slip")))
+        L.orc_free_slip3(dp(hh["Vx"]), dp(hh["Vy"]), dp(hh["Vz"]), i32(ni), i32(bcs.flags("free_slip")))
+        if any(bcs.flags("periodic")):
+            L.orc_periodic3(dp(hh["Vx"]), dp(hh["Vy"]), dp(hh["Vz"]), i32(ni), i32(bcs.flags("periodic")))
+        for k in h:
+            assert np.array_equal(to_host(st.slots()[k]), hh[k]), (k, per)
