@@ -74,6 +74,7 @@ int jr_stokes3d_iterate_VA(jr_context *ctx, const jr_fields *s, const jr_stokes_
         if ((st = one_iter_VA(ctx, s, o, fused, diag, it))) return st;
     }
     JR_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+    if (fused && (niter & 1) && (st = jr_stokes3d_VA_fused_finish(ctx, s))) return st;
     JR_CUDA(cudaStreamSynchronize(ctx->stream));
     if (res) {
         float ms = 0.f;
@@ -139,12 +140,15 @@ int jr_stokes3d_solve_VA(jr_context *ctx, const jr_fields *s, const jr_stokes_op
             err_it1 = fmax(fmax(res->norm_Rx[0], res->norm_Ry[0]), fmax(res->norm_Rz[0], res->norm_divV[0]));
             if (std::isnan(err)) {
                 res->iter = iter; res->nhist = cont; res->err = err;
+                if (fused && (iter & 1)) jr_stokes3d_VA_fused_finish(ctx, s);
+                cudaStreamSynchronize(ctx->stream);
                 jr_set_error("NaN(s)");  // reference: isnan(err) && error("NaN(s)")  Stokes3D.jl:162
                 return JR_ERR_NAN;
             }
         }
     }
     JR_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+    if (fused && (iter & 1) && (st = jr_stokes3d_VA_fused_finish(ctx, s))) return st;
     if ((st = post_VA(ctx, s))) return st;
     JR_CUDA(cudaStreamSynchronize(ctx->stream));
     float ms = 0.f;
