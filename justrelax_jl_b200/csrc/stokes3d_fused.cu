@@ -332,7 +332,7 @@ struct BcArr {
 };
 struct BcArgs {
     BcArr A[3];
-    int lo_kind[3], hi_kind[3];  // per dimension: 0 none, 1 free slip, 2 no slip
+    int lo_fs[3], hi_fs[3], lo_ns[3], hi_ns[3];  // per dimension and side: free-slip / no-slip active
     int diag;
     double dt;
 };
@@ -359,12 +359,14 @@ __global__ void k_bc_pingpong3(const BcArgs b)
     for (int e = 0; e < 3; e++) {
         const bool lo_e = c[e] == 0, hi_e = c[e] == A.n[e] - 1;
         if (!lo_e && !hi_e) continue;
-        const int kind = lo_e ? b.lo_kind[e] : b.hi_kind[e];
+        // no_slip! runs before free_slip! (BoundaryConditions.jl:86-99): on a side that carries both
+        // (possible through quirk Q2) the free-slip copy wins for the tangential ghosts, the normal face stays 0
+        const bool fsl = lo_e ? b.lo_fs[e] : b.hi_fs[e], nsl = lo_e ? b.lo_ns[e] : b.hi_ns[e];
         if (e == A.normal) {
-            if (kind == 2) zero = true;
-        } else if (kind != 0) {
+            if (nsl) zero = true;
+        } else if (fsl || nsl) {
             s[e] = lo_e ? 1 : A.n[e] - 2;
-            if (kind == 2) sign = -sign;
+            if (!fsl) sign = -sign;
         }
     }
     const size_t ic = ((size_t)c[2] * A.n[1] + c[1]) * A.n[0] + c[0];
@@ -444,9 +446,9 @@ int jr_stokes3d_VA_fused_iter(jr_context *ctx, const jr_fields *s, const jr_stok
     b.A[2] = BcArr{in[2], out[2], F(Uz), {nx + 2, ny + 2, nz + 1}, 2};
     // flags: left,right,front,back,top,bot.  no_slip: bot → z lo, top → z hi; free_slip (Q2): top → z lo, bot → z hi
     const int32_t *fs = o->free_slip, *ns = o->no_slip;
-    b.lo_kind[0] = ns[0] ? 2 : (fs[0] ? 1 : 0); b.hi_kind[0] = ns[1] ? 2 : (fs[1] ? 1 : 0);
-    b.lo_kind[1] = ns[2] ? 2 : (fs[2] ? 1 : 0); b.hi_kind[1] = ns[3] ? 2 : (fs[3] ? 1 : 0);
-    b.lo_kind[2] = ns[5] ? 2 : (fs[4] ? 1 : 0); b.hi_kind[2] = ns[4] ? 2 : (fs[5] ? 1 : 0);
+    b.lo_fs[0] = fs[0]; b.hi_fs[0] = fs[1]; b.lo_ns[0] = ns[0]; b.hi_ns[0] = ns[1];
+    b.lo_fs[1] = fs[2]; b.hi_fs[1] = fs[3]; b.lo_ns[1] = ns[2]; b.hi_ns[1] = ns[3];
+    b.lo_fs[2] = fs[4]; b.hi_fs[2] = fs[5]; b.lo_ns[2] = ns[5]; b.hi_ns[2] = ns[4];
     b.diag = diag; b.dt = o->dt;
     int m = nx > ny ? nx : ny;
     m = (m > nz ? m : nz) + 2;
