@@ -68,13 +68,15 @@ int jr_stokes3d_iterate_VA(jr_context *ctx, const jr_fields *s, const jr_stokes_
     const bool fused = !(ctx->flags & JR_FLAG_UNFUSED) && jr_stokes3d_VA_fused_supported(s, o) == JR_OK;
     ctx->launches = 0;
     if ((st = pre_VA(ctx, s))) return st;
+    // the timed region includes packing the dense arrays into the TMA box layout and unpacking them again
     JR_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    if (fused && (st = jr_stokes3d_VA_fused_begin(ctx, s, o))) return st;
     for (int64_t it = 0; it < niter; it++) {
         const int diag = (ctx->flags & JR_FLAG_DIAG_EVERY_ITER) ? 1 : (it == niter - 1);
         if ((st = one_iter_VA(ctx, s, o, fused, diag, it))) return st;
     }
+    if (fused && (st = jr_stokes3d_VA_fused_finish(ctx, s, niter))) return st;
     JR_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
-    if (fused && (niter & 1) && (st = jr_stokes3d_VA_fused_finish(ctx, s))) return st;
     JR_CUDA(cudaStreamSynchronize(ctx->stream));
     if (res) {
         float ms = 0.f;
@@ -109,6 +111,7 @@ int jr_stokes3d_solve_VA(jr_context *ctx, const jr_fields *s, const jr_stokes_op
     int64_t iter = 0, cont = 0;
     if ((st = pre_VA(ctx, s))) return st;
     JR_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    if (fused && (st = jr_stokes3d_VA_fused_begin(ctx, s, o))) return st;
     while (iter < 2 || (((err / err_it1) > o->eps_rel && err > o->eps_abs) && iter <= o->iterMax)) {
         // diagnostics (∇V, ε, R, U) are only read at `nout` samples and after the loop; the loop can only
         // end right after a sample or once iter > iterMax, so writing them on those iterations reproduces
@@ -140,15 +143,15 @@ int jr_stokes3d_solve_VA(jr_context *ctx, const jr_fields *s, const jr_stokes_op
             err_it1 = fmax(fmax(res->norm_Rx[0], res->norm_Ry[0]), fmax(res->norm_Rz[0], res->norm_divV[0]));
             if (std::isnan(err)) {
                 res->iter = iter; res->nhist = cont; res->err = err;
-                if (fused && (iter & 1)) jr_stokes3d_VA_fused_finish(ctx, s);
+                if (fused) jr_stokes3d_VA_fused_finish(ctx, s, iter);
                 cudaStreamSynchronize(ctx->stream);
                 jr_set_error("NaN(s)");  // reference: isnan(err) && error("NaN(s)")  Stokes3D.jl:162
                 return JR_ERR_NAN;
             }
         }
     }
+    if (fused && (st = jr_stokes3d_VA_fused_finish(ctx, s, iter))) return st;
     JR_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
-    if (fused && (iter & 1) && (st = jr_stokes3d_VA_fused_finish(ctx, s))) return st;
     if ((st = post_VA(ctx, s))) return st;
     JR_CUDA(cudaStreamSynchronize(ctx->stream));
     float ms = 0.f;

@@ -1,0 +1,714 @@
+// stokes3d_tma.cu — the fused sm_100a kernel of the 3D visco-elastic Stokes PT iteration (variant 3D-VA):
+// ONE kernel per PT iteration, inputs staged by TMA (cp.async.bulk.tensor + mbarrier ring), 2.5D z-marching.
+//
+// What it replaces (reference, one @parallel launch each, ≈75 array passes = 600 B/cell/iteration):
+//   compute_∇V! → compute_P! → compute_strain_rate! → compute_τ! → compute_V! → velocity2displacement!
+//   (src/stokes/Stokes3D.jl:78-119; kernels VelocityKernels.jl:3-6,59-104,182-242, PressureKernels.jl:10-15,
+//   StressKernels.jl:149-230) and flow_bcs! (BoundaryConditions.jl:86-99).
+//
+// Data layout in HBM ("box sets", owned by the library for the duration of a solve):
+//   every staggered array of the iteration is stored in ONE common index space, the box
+//   (X,Y,Z) ∈ [0,PX)×[0,PY)×[0,PZ), PX = nx+2 rounded to 32 B, PY = ny+2, PZ = nz+2, with
+//        cell centre (i,j,k)      → (i+1, j+1, k+1)      P, τxx, τyy, τzz, η, ητ, ρg, K, G, P0, Q
+//        Vx(I, J, K) (I face)     → (I+1, J,   K  )      J,K ghosted indices of the reference
+//        Vy(I, J, K)              → (I,   J+1, K  )
+//        Vz(I, J, K)              → (I,   J,   K+1)
+//        τxy(I, J, k) / τxz(I, j, K) / τyz(i, J, K) (edges) → (I+1, J+1, k+1) etc. (edge = low corner of its cell)
+//   so ONE offset addresses all 25 arrays at a thread's position.  Arrays of a set are interleaved plane-wise:
+//   element (a, X, Y, Z) of a set with NA arrays lives at ((Z·NA + a)·PY + Y)·PX + X — a 4-D tensor that one
+//   CUtensorMap describes, with 16-B aligned pitches whatever nx is (255, 511 … are odd).  η and G carry their
+//   clamped-index ghost copies in the box, everything else is zero outside its own extent.
+//   Sets: S0/S1 (state ping-pong: Vx,Vy,Vz,P,τxx,τyy,τzz,τyz,τxz,τxy), C (η,ητ,ρgx,ρgy,ρgz), D (finite dt only:
+//   G,K,P0,Q,τ_o×6).  The user's dense arrays are packed at solve entry and unpacked at exit.
+//
+// Kernel: a CTA owns a (30 × BY−2) column tile (+1 halo ring = 32 × BY threads, a warp = one x-row) and marches a
+// z-chunk.  Per z-step ONE elected thread issues 15 (25) TMA box loads (32 × BY × 1 doubles each) into the next
+// slot of a 3-deep shared-memory ring; completion arrives on the slot's mbarrier.  Threads read their own and
+// their neighbours' values from the slot, keep the z-direction state in a register queue, publish the new
+// stresses IN PLACE in the slot (one __syncthreads per step), then form the momentum residuals and the new
+// velocities and store the 10 outputs straight from registers (coalesced 240-B rows).  No global load
+// instruction, no address arithmetic and no bounds predicate is left on the load side.
+// Jacobi-exact (in → out sets), arithmetic identical operation for operation to the reference
+// (same fma placement, same summation order) ⇒ bit-comparable with the CPU oracle.
+#include "common.cuh"
+#include "tma.cuh"
+
+// set orders: arrays that are loaded at the same box plane are adjacent, so ONE TMA box (32 × BY × n × 1) brings n tiles
+enum { S_tzz = 0, S_P, S_txx, S_tyy, S_txy, /* plane k+1 */ S_Vx, S_Vy, S_Vz, S_tyz, S_txz, /* plane k+2 */ S_N };
+enum { C_eta = 0, /* plane k+2 */ C_ett, C_fx, C_fy, C_fz, /* plane k+1 */ C_N };
+enum { D_G = 0, D_oyz, D_oxz, /* plane k+2 */ D_K, D_P0, D_Q, D_oxx, D_oyy, D_ozz, D_oxy, /* plane k+1 */ D_N };
+// tiles of one ring slot.  The first (τzz) and the last (ρgz) tile are only ever read at a thread's own position:
+// the ±1 / ±32 / −33 neighbour reads of rim lanes then stay inside the slot without any index clamping.
+enum { T_tzz = 0, T_P, T_txx, T_tyy, T_txy, T_Vx, T_Vy, T_Vz, T_tyz, T_txz, T_eta, T_NEXT };
+template <bool FIN> struct SlotMap {
+    static constexpr int G = T_NEXT, oyz = G + 1, oxz = G + 2, K = G + 3, P0 = G + 4, Q = G + 5, oxx = G + 6, oyy = G + 7, ozz = G + 8,
+                         oxy = G + 9;
+    static constexpr int ett = FIN ? G + 10 : T_NEXT, fx = ett + 1, fy = ett + 2, fz = ett + 3, NARR = ett + 4;
+};
+
+struct alignas(64) VaArgs {
+    CUtensorMap mS5, mC1, mC4, mD1, mD2, mD7;  // in-state set (5-array boxes), const set, finite-dt set
+    double *out;                               // out-state set base
+    double *divV, *RP, *exx, *eyy, *ezz, *eyz, *exz, *exy, *Rx, *Ry, *Rz, *Ux, *Uy, *Uz;  // dense user arrays (DIAG)
+    int nx, ny, nz, PX, PY, kchunk;
+    double _dx, _dy, _dz, dt, r, theta_dtau, eta_dtau;
+};
+
+#define TXW 30  // owned columns per tile
+
+__device__ __forceinline__ bool jr_elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+    return pred != 0;
+}
+
+template <int BY, bool FINITE_DT, bool DIAG, int NST>
+__global__ void __launch_bounds__(32 * BY, (BY <= 10 ? 2 : 1)) k_va_tma(const __grid_constant__ VaArgs a)
+{
+    using M = SlotMap<FINITE_DT>;
+    constexpr int TY = BY - 2, TILE = 32 * BY;
+    constexpr int NARR = M::NARR, SLOT = NARR * TILE;
+    constexpr uint32_t TILE_BYTES = TILE * 8;
+    constexpr int DEPTH = NST - 1;  // prefetch distance in z-steps
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[NST];
+    double *const sm = reinterpret_cast<double *>(smem_raw);
+
+    const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 32 + tx;
+    const int x0 = blockIdx.x * TXW, y0 = blockIdx.y * TY;
+    const int X = x0 + tx, Y = y0 + ty;  // box coordinates of this thread; cell (gi, gj) = (X-1, Y-1)
+    const int gi = X - 1, gj = Y - 1;
+    const int nx = a.nx, ny = a.ny, nz = a.nz;
+    const int kb = blockIdx.z * a.kchunk, ke = min(kb + a.kchunk, nz);
+
+    const bool own = tx >= 1 && tx <= TXW && ty >= 1 && ty <= TY;
+    const bool cell = own && gi < nx && gj < ny;
+    const bool vxy = own && gi <= nx && gj <= ny;  // xy edge exists
+    const bool vxz = own && gi <= nx && gj < ny;   // xz edge exists
+    const bool vyz = own && gi < nx && gj <= ny;   // yz edge exists
+    const bool stVx = cell && gi >= 1, stVy = cell && gj >= 1;
+
+    const double _dx = a._dx, _dy = a._dy, _dz = a._dz, th = a.theta_dtau;
+    const double inv3 = jr_inv(3.0);
+    const double dtr_inf = jr_inv(th + 1.0);  // compute_dτ_r with 1/(G dt) = 0: fma(η, 0, 1) = 1
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < NST; s++) jr_mbar_init(&full_bar[s], 1);
+        jr_fence_mbar_init();
+    }
+    __syncthreads();
+
+    // producer (one elected lane of warp 0): loads of z-step k into ring slot `slot`.
+    // `full` = false loads only what the queue-filling first step of a chunk needs (V, η[, G] of plane k+1).
+    auto issue = [&](int k, int slot, bool full) {
+        uint64_t *bar = &full_bar[slot];
+        double *d = sm + (size_t)slot * SLOT;
+        const int za = k + 2, zc = k + 1;  // arrival plane (V, η, top edges) / compute plane
+        uint32_t bytes = (5 + 1 + (FINITE_DT ? 1 : 0)) * TILE_BYTES;
+        if (full) bytes = NARR * TILE_BYTES;
+        jr_mbar_arrive_expect_tx(bar, bytes);
+        jr_tma_load_4d(d + T_Vx * TILE, &a.mS5, x0, y0, S_Vx, za, bar);
+        jr_tma_load_4d(d + T_eta * TILE, &a.mC1, x0, y0, C_eta, za, bar);
+        if (FINITE_DT) jr_tma_load_4d(d + M::G * TILE, &a.mD1, x0, y0, D_G, za, bar);
+        if (full) {
+            jr_tma_load_4d(d + T_tzz * TILE, &a.mS5, x0, y0, S_tzz, zc, bar);
+            if (FINITE_DT) {
+                jr_tma_load_4d(d + M::oyz * TILE, &a.mD2, x0, y0, D_oyz, za, bar);
+                jr_tma_load_4d(d + M::K * TILE, &a.mD7, x0, y0, D_K, zc, bar);
+            }
+            jr_tma_load_4d(d + M::ett * TILE, &a.mC4, x0, y0, C_ett, zc, bar);
+        }
+    };
+
+    if (ty == 0) {
+        if (jr_elect_one()) {
+            jr_tma_prefetch_desc(&a.mS5);
+            jr_tma_prefetch_desc(&a.mC1);
+            jr_tma_prefetch_desc(&a.mC4);
+#pragma unroll
+            for (int d = 0; d < DEPTH; d++)
+                if (kb - 2 + d < ke) issue(kb - 2 + d, d, d > 0);
+        }
+    }
+
+    // ---- register queue: state of plane k carried along z ----
+    double vx0, vy0, vz0;                          // V(k) at this thread's position
+    double dxx0, dyy0, exy0;                       // ∂xVx, ∂yVy, ε_xy of plane k
+    double eta0, etaxy0, sxz0, syz0;               // η(k), η̄xy(k), η pair sums of plane k
+    double g0 = 1, gxy0 = 1, gsxz0 = 0, gsyz0 = 0; // same for G (finite dt)
+    double tzz_p = 0, P_p = 0, fz_p = 0, ett_p = 1;  // plane k−1: new τzz, new P, ρgz, ητ
+    double txz_b = 0, tyz_b = 0, sRz = 0;            // new bottom-edge stresses (kz = k), partial Rz of face k
+
+    // queue entries of plane A from the slot that holds V(A), η(A) (reads at own position and W/E/S/N/SW neighbours)
+#define JR_FILL_QUEUE(p)                                                                                  \
+    do {                                                                                                  \
+        vx0 = (p)[T_Vx * TILE]; vy0 = (p)[T_Vy * TILE]; vz0 = (p)[T_Vz * TILE]; eta0 = (p)[T_eta * TILE]; \
+        dxx0 = (-vx0 + (p)[T_Vx * TILE + 1]) * _dx;                                                       \
+        dyy0 = (-vy0 + (p)[T_Vy * TILE + 32]) * _dy;                                                      \
+        exy0 = 0.5 * (_dy * (vx0 - (p)[T_Vx * TILE - 32]) + _dx * (vy0 - (p)[T_Vy * TILE - 1]));          \
+        {                                                                                                 \
+            const double eW_ = (p)[T_eta * TILE - 1], eS_ = (p)[T_eta * TILE - 32], eSW_ = (p)[T_eta * TILE - 33]; \
+            etaxy0 = 0.25 * (eSW_ + eS_ + eW_ + eta0);                                                    \
+            sxz0 = eW_ + eta0;                                                                            \
+            syz0 = eS_ + eta0;                                                                            \
+        }                                                                                                 \
+        if (FINITE_DT) {                                                                                  \
+            g0 = (p)[M::G * TILE];                                                                        \
+            const double gW_ = (p)[M::G * TILE - 1], gS_ = (p)[M::G * TILE - 32], gSW_ = (p)[M::G * TILE - 33]; \
+            gxy0 = 0.25 * (gSW_ + gS_ + gW_ + g0);                                                        \
+            gsxz0 = gW_ + g0;                                                                             \
+            gsyz0 = gS_ + g0;                                                                             \
+        }                                                                                                 \
+    } while (0)
+
+    // out-set pointer of (X, Y) in plane group Z = k+1: ((Z·10 + a)·PY + Y)·PX + X
+    const size_t pxy = (size_t)a.PX * a.PY;
+    double *po = a.out + ((size_t)kb * S_N) * pxy + (size_t)Y * a.PX + X;  // plane group Z = kb (step k = kb−1)
+
+    // ---- first step of the chunk (k = kb−2): fill the queue with plane kb−1 ----
+    jr_mbar_wait(&full_bar[0], 0);
+    {
+        const double *p = sm + tid;
+        JR_FILL_QUEUE(p);
+    }
+    __syncthreads();
+    if (ty == 0 && kb - 2 + DEPTH < ke) {
+        if (jr_elect_one()) {
+            jr_fence_proxy_async();
+            issue(kb - 2 + DEPTH, DEPTH % NST, true);
+        }
+    }
+
+    int slot = 1 % NST;
+    uint32_t parity = (NST == 1) ? 1u : 0u;
+    for (int k = kb - 1; k < ke; ++k) {
+        jr_mbar_wait(&full_bar[slot], parity);
+        double *const p = sm + (size_t)slot * SLOT + tid;
+
+        // ---- R1: top-edge strain rates / viscosities (plane k+1 arrives), centre of plane k, six new stresses ----
+        double txx_n, tyy_n, tzz_n, txy_n, txz_n, tyz_n, P_n, divV, RP, exx, eyy, ezz, exz_t, eyz_t;
+        {
+            const double vz1 = p[T_Vz * TILE], eta1 = p[T_eta * TILE];
+            exz_t = 0.5 * (_dz * (p[T_Vx * TILE] - vx0) + _dx * (vz1 - p[T_Vz * TILE - 1]));
+            eyz_t = 0.5 * (_dz * (p[T_Vy * TILE] - vy0) + _dy * (vz1 - p[T_Vz * TILE - 32]));
+            const double etaxz_t = 0.25 * (sxz0 + p[T_eta * TILE - 1] + eta1);
+            const double etayz_t = 0.25 * (syz0 + p[T_eta * TILE - 32] + eta1);
+            const double c_txx = p[T_txx * TILE], c_tyy = p[T_tyy * TILE], c_tzz = p[T_tzz * TILE];
+            const double c_txy = p[T_txy * TILE], c_txz = p[T_txz * TILE], c_tyz = p[T_tyz * TILE];
+            const double c_P = p[T_P * TILE];
+            const double dzz = (-vz0 + vz1) * _dz;
+            divV = dxx0 + dyy0 + dzz;
+            const double d3 = divV * inv3;
+            exx = dxx0 - d3; eyy = dyy0 - d3; ezz = dzz - d3;
+            if (FINITE_DT) {
+                const double dt = a.dt;
+                const double g1 = p[M::G * TILE];
+                const double gxz_t = 0.25 * (gsxz0 + p[M::G * TILE - 1] + g1);
+                const double gyz_t = 0.25 * (gsyz0 + p[M::G * TILE - 32] + g1);
+                P_n = c_P;
+                jr_compute_P_point(RP, P_n, p[M::P0 * TILE], divV, p[M::Q * TILE], eta0, p[M::K * TILE], g0, dt, a.r, th);
+                {
+                    const double _Gdt = jr_inv(g0 * dt), dtr = jr_dtau_r(th, eta0, _Gdt);
+                    txx_n = c_txx + jr_stress_increment(c_txx, p[M::oxx * TILE], eta0, exx, _Gdt, dtr);
+                    tyy_n = c_tyy + jr_stress_increment(c_tyy, p[M::oyy * TILE], eta0, eyy, _Gdt, dtr);
+                    tzz_n = c_tzz + jr_stress_increment(c_tzz, p[M::ozz * TILE], eta0, ezz, _Gdt, dtr);
+                }
+                {
+                    const double _Gdt = jr_inv(gxy0 * dt), dtr = jr_dtau_r(th, etaxy0, _Gdt);
+                    txy_n = c_txy + jr_stress_increment(c_txy, p[M::oxy * TILE], etaxy0, exy0, _Gdt, dtr);
+                }
+                {
+                    const double _Gdt = jr_inv(gxz_t * dt), dtr = jr_dtau_r(th, etaxz_t, _Gdt);
+                    txz_n = c_txz + jr_stress_increment(c_txz, p[M::oxz * TILE], etaxz_t, exz_t, _Gdt, dtr);
+                }
+                {
+                    const double _Gdt = jr_inv(gyz_t * dt), dtr = jr_dtau_r(th, etayz_t, _Gdt);
+                    tyz_n = c_tyz + jr_stress_increment(c_tyz, p[M::oyz * TILE], etayz_t, eyz_t, _Gdt, dtr);
+                }
+            } else {
+                // _Kdt = _Gdt = _dt = 0 exactly (PressureKernels.jl:186-195 with dt = Inf)
+                RP = -divV;
+                const double psi = jr_inv(jr_inv(eta0)) * a.r / th;
+                P_n = (-divV) * psi + c_P;
+                txx_n = c_txx + dtr_inf * fma(2.0 * eta0, exx, -c_txx);
+                tyy_n = c_tyy + dtr_inf * fma(2.0 * eta0, eyy, -c_tyy);
+                tzz_n = c_tzz + dtr_inf * fma(2.0 * eta0, ezz, -c_tzz);
+                txy_n = c_txy + dtr_inf * fma(2.0 * etaxy0, exy0, -c_txy);
+                txz_n = c_txz + dtr_inf * fma(2.0 * etaxz_t, exz_t, -c_txz);
+                tyz_n = c_tyz + dtr_inf * fma(2.0 * etayz_t, eyz_t, -c_tyz);
+            }
+        }
+        // ---- publish the new stresses / pressure in place (only their owner read the old values) ----
+        p[T_txx * TILE] = txx_n; p[T_tyy * TILE] = tyy_n; p[T_P * TILE] = P_n;
+        p[T_txy * TILE] = txy_n; p[T_txz * TILE] = txz_n; p[T_tyz * TILE] = tyz_n;
+        __syncthreads();
+        // every thread is past its reads of the previous slot: refill it with the loads of step k+DEPTH
+        if (ty == 0 && k + DEPTH < ke) {
+            if (jr_elect_one()) {
+                jr_fence_proxy_async();
+                int ns = slot + DEPTH;
+                if (ns >= NST) ns -= NST;
+                issue(k + DEPTH, ns, true);
+            }
+        }
+
+        // ---- R2: momentum residuals and velocity update of plane k, partial Rz of face k+1 ----
+        const double c_fz = p[M::fz * TILE], c_ett = p[M::ett * TILE];
+        const double sRz_next = _dx * (p[T_txz * TILE + 1] - txz_n) + _dy * (p[T_tyz * TILE + 32] - tyz_n);
+        const bool kin = k >= kb;  // this chunk owns plane k (k = kb−1 is the warm-up plane)
+        if (kin) {
+            if (cell) {
+                po[S_P * pxy] = P_n; po[S_txx * pxy] = txx_n; po[S_tyy * pxy] = tyy_n; po[S_tzz * pxy] = tzz_n;
+                if (DIAG) {
+                    const size_t c = ((size_t)k * ny + gj) * nx + gi;
+                    a.divV[c] = divV; a.RP[c] = RP; a.exx[c] = exx; a.eyy[c] = eyy; a.ezz[c] = ezz;
+                }
+            }
+            if (vxy) {
+                po[S_txy * pxy] = txy_n;
+                if (DIAG) a.exy[((size_t)k * (ny + 1) + gj) * (nx + 1) + gi] = exy0;
+            }
+            // x-momentum: face gi between cells gi−1 (W) and gi
+            if (stVx) {
+                const double R = (-p[T_txx * TILE - 1] + txx_n) * _dx + _dy * (p[T_txy * TILE + 32] - txy_n) + _dz * (txz_n - txz_b) -
+                                 (-p[T_P * TILE - 1] + P_n) * _dx - 0.5 * (p[M::fx * TILE - 1] + p[M::fx * TILE]);
+                const double vn = vx0 + R * a.eta_dtau / (0.5 * (p[M::ett * TILE - 1] + c_ett));
+                po[S_Vx * pxy] = vn;
+                if (DIAG) {
+                    a.Rx[((size_t)k * ny + gj) * (nx - 1) + (gi - 1)] = R;
+                    a.Ux[((size_t)(k + 1) * (ny + 2) + gj + 1) * (nx + 1) + gi] = vn * a.dt;
+                }
+            }
+            // y-momentum: face gj between cells gj−1 (S) and gj
+            if (stVy) {
+                const double R = _dx * (p[T_txy * TILE + 1] - txy_n) + _dy * (tyy_n - p[T_tyy * TILE - 32]) + _dz * (tyz_n - tyz_b) -
+                                 (-p[T_P * TILE - 32] + P_n) * _dy - 0.5 * (p[M::fy * TILE - 32] + p[M::fy * TILE]);
+                const double vn = vy0 + R * a.eta_dtau / (0.5 * (p[M::ett * TILE - 32] + c_ett));
+                po[S_Vy * pxy] = vn;
+                if (DIAG) {
+                    a.Ry[((size_t)k * (ny - 1) + (gj - 1)) * nx + gi] = R;
+                    a.Uy[((size_t)(k + 1) * (ny + 1) + gj) * (nx + 2) + gi + 1] = vn * a.dt;
+                }
+            }
+            // z-momentum: face k between planes k−1 and k
+            if (cell && k >= 1) {
+                const double R = sRz + (-tzz_p + tzz_n) * _dz - (-P_p + P_n) * _dz - 0.5 * (fz_p + c_fz);
+                const double vn = vz0 + R * a.eta_dtau / (0.5 * (ett_p + c_ett));
+                po[S_Vz * pxy] = vn;
+                if (DIAG) {
+                    a.Rz[((size_t)(k - 1) * ny + gj) * nx + gi] = R;
+                    a.Uz[((size_t)k * (ny + 2) + gj + 1) * (nx + 2) + gi + 1] = vn * a.dt;
+                }
+            }
+        }
+        // top edges (kz = k+1) belong to the chunk that owns plane k; the kz = 0 edges to chunk 0's warm-up
+        if (kin || kb == 0) {
+            double *const pe = po + S_N * pxy;
+            if (vxz) {
+                pe[S_txz * pxy] = txz_n;
+                if (DIAG) a.exz[((size_t)(k + 1) * ny + gj) * (nx + 1) + gi] = exz_t;
+            }
+            if (vyz) {
+                pe[S_tyz * pxy] = tyz_n;
+                if (DIAG) a.eyz[((size_t)(k + 1) * (ny + 1) + gj) * nx + gi] = eyz_t;
+            }
+        }
+        // ---- the queue for the next step: plane k+1 becomes plane k ----
+        tzz_p = tzz_n; P_p = P_n; fz_p = c_fz; ett_p = c_ett;
+        txz_b = txz_n; tyz_b = tyz_n; sRz = sRz_next;
+        JR_FILL_QUEUE(p);
+        po += S_N * pxy;
+        if (++slot == NST) { slot = 0; parity ^= 1u; }
+    }
+#undef JR_FILL_QUEUE
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Box-layout helpers
+struct BoxArr {       // one array of a box set
+    double *p;        // set base + a·pxy
+    long sy, sz;      // strides in elements: PX, NA·pxy
+};
+__device__ __forceinline__ size_t box_idx(const BoxArr &b, int X, int Y, int Z) { return (size_t)Z * b.sz + (size_t)Y * b.sy + X; }
+
+// dense (n0,n1,n2) ↔ box at offset (o0,o1,o2).  mode 0: dense → box, 1: box → dense,
+// 2: dense → box over the whole ghosted extent (n+2)^3 with clamped source indices (η, G: the reference's clamped
+//    neighbour reads, MiniKernels.jl:133-147, become plain reads of the ghost copies)
+struct PackJob {
+    double *dense;
+    BoxArr box;
+    int n[3], o[3], mode;
+};
+#define PACK_MAX 25
+struct PackArgs {
+    PackJob j[PACK_MAX];
+    int njobs;
+};
+__global__ void k_box_pack(const __grid_constant__ PackArgs pa)
+{
+    const PackJob &J = pa.j[blockIdx.y];
+    const int g = J.mode == 2 ? 2 : 0;
+    const int e0 = J.n[0] + g, e1 = J.n[1] + g, e2 = J.n[2] + g;
+    for (long r = blockIdx.x; r < (long)e1 * e2; r += gridDim.x) {
+        const int j = (int)(r % e1), k = (int)(r / e1);
+        for (int i = threadIdx.x; i < e0; i += blockDim.x) {
+            if (J.mode == 2) {
+                const int si = jr_clamp(i - 1, 0, J.n[0] - 1), sj = jr_clamp(j - 1, 0, J.n[1] - 1), sk = jr_clamp(k - 1, 0, J.n[2] - 1);
+                J.box.p[box_idx(J.box, i, j, k)] = J.dense[((size_t)sk * J.n[1] + sj) * J.n[0] + si];
+            } else {
+                const size_t d = ((size_t)k * J.n[1] + j) * J.n[0] + i;
+                const size_t b = box_idx(J.box, i + J.o[0], j + J.o[1], k + J.o[2]);
+                if (J.mode == 0) J.box.p[b] = J.dense[d];
+                else J.dense[d] = J.box.p[b];
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Ping-pong boundary kernel on the box layout: fills every element of V_out the fused kernel does not compute,
+// i.e. the tangential ghost layers and the boundary-normal faces, from (a) the freshly computed interior of
+// V_out and (b) V_in for layers no boundary condition touches (prescribed values, or halo planes that the
+// exchange overwrites afterwards).  Semantics = no_slip! → free_slip! of the reference applied as complete
+// sweeps (no_slip.jl:21-54, free_slip.jl:15-70 incl. quirk Q2); every ghost value is gathered from its
+// fully-clamped source with the product of the per-dimension signs, so ghost edges/corners are deterministic.
+// With diag set it also writes U = V·dt (dense user array) for those elements from V_in — the reference takes U
+// before flow_bcs! (Stokes3D.jl:118-119).
+struct BcArrB {
+    BoxArr in, out;
+    double *U;   // dense
+    int n[3];    // dense extents of this velocity component
+    int o[3];    // dense → box offset
+    int normal;  // normal dimension of this component
+};
+struct BcArgsB {
+    BcArrB A[3];
+    int lo_fs[3], hi_fs[3], lo_ns[3], hi_ns[3];  // per dimension and side: free-slip / no-slip active
+    int diag;
+    double dt;
+};
+
+__global__ void k_bc_box3(const __grid_constant__ BcArgsB b)
+{
+    const int which = blockIdx.z / 6, plane = blockIdx.z % 6;  // component, (dim, lo/hi)
+    const BcArrB &A = b.A[which];
+    const int d = plane >> 1, hi = plane & 1;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x, q = blockIdx.y * blockDim.y + threadIdx.y;
+    // fastest-varying free coordinate on threadIdx.x: for d = 0 planes use (dim1, dim2), else dim0 first
+    int c[3];
+    const int u = (d == 0) ? 1 : 0, v = (d == 2) ? 1 : 2;
+    if (p >= A.n[u] || q >= A.n[v]) return;
+    c[d] = hi ? A.n[d] - 1 : 0;
+    c[u] = p;
+    c[v] = q;
+    int s[3] = {c[0], c[1], c[2]};
+    double sign = 1.0;
+    bool zero = false;
+#pragma unroll
+    for (int e = 0; e < 3; e++) {
+        const bool lo_e = c[e] == 0, hi_e = c[e] == A.n[e] - 1;
+        if (!lo_e && !hi_e) continue;
+        // no_slip! runs before free_slip! (BoundaryConditions.jl:86-99): on a side that carries both
+        // (possible through quirk Q2) the free-slip copy wins for the tangential ghosts, the normal face stays 0
+        const bool fsl = lo_e ? b.lo_fs[e] : b.hi_fs[e], nsl = lo_e ? b.lo_ns[e] : b.hi_ns[e];
+        if (e == A.normal) {
+            if (nsl) zero = true;
+        } else if (fsl || nsl) {
+            s[e] = lo_e ? 1 : A.n[e] - 2;
+            if (!fsl) sign = -sign;
+        }
+    }
+    const size_t ic = box_idx(A.out, c[0] + A.o[0], c[1] + A.o[1], c[2] + A.o[2]);
+    const size_t is = box_idx(A.out, s[0] + A.o[0], s[1] + A.o[1], s[2] + A.o[2]);
+    bool computed = true;
+#pragma unroll
+    for (int e = 0; e < 3; e++) computed = computed && s[e] >= 1 && s[e] <= A.n[e] - 2;
+    double val;
+    if (zero) val = 0.0;
+    else val = sign * (computed ? A.out.p[is] : A.in.p[is]);
+    A.out.p[ic] = val;
+    if (b.diag) A.U[((size_t)c[2] * A.n[1] + c[1]) * A.n[0] + c[0]] = A.in.p[ic] * b.dt;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int jr_encode_tensor_map_f64(CUtensorMap *out, void *base, int rank, const uint64_t *dims, const uint64_t *strides_bytes,
+                             const uint32_t *box)
+{
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        JR_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+        JR_REQUIRE(p && qres == cudaDriverEntryPointSuccess, JR_ERR_CUDA, "cuTensorMapEncodeTiled not available in this driver");
+        fn = (PFN_encodeTiled)p;
+    }
+    cuuint64_t gd[5], gs[4];
+    cuuint32_t bd[5], es[5];
+    for (int i = 0; i < rank; i++) {
+        gd[i] = dims[i];
+        bd[i] = box[i];
+        es[i] = 1;
+        if (i < rank - 1) gs[i] = strides_bytes[i];
+    }
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, (cuuint32_t)rank, base, gd, gs, bd, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    JR_REQUIRE(r == CUDA_SUCCESS, JR_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %llu %llu %llu)", (int)r,
+               rank, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2]);
+    return JR_OK;
+}
+
+#define F(name) (s->f[JR_F_##name])
+
+struct VaPlan {
+    int nx = 0, ny = 0, nz = 0, PX = 0, PY = 0, PZ = 0;
+    bool finite_dt = false;
+    size_t pxy = 0;
+    double *S[2] = {nullptr, nullptr}, *C = nullptr, *D = nullptr;
+    CUtensorMap mS5[2], mC1, mC4, mD1, mD2, mD7;
+    int BY = 0, nchunk = 1;
+};
+static std::map<jr_context *, VaPlan> g_plans;
+
+int jr_stokes3d_VA_fused_supported(const jr_fields *s, const jr_stokes_opts *o)
+{
+    for (int q = 0; q < 6; q++)
+        if (o->periodic[q]) return JR_ERR_UNSUPPORTED;  // periodic wrap: reference-structured path
+    if (s->n[0] < 3 || s->n[1] < 3 || s->n[2] < 3) return JR_ERR_UNSUPPORTED;
+    return JR_OK;
+}
+
+static int set_tma_map(CUtensorMap *m, double *base, const VaPlan &P, int NA, int nbox)
+{
+    const uint64_t dims[4] = {(uint64_t)P.PX, (uint64_t)P.PY, (uint64_t)NA, (uint64_t)P.PZ};
+    const uint64_t str[3] = {(uint64_t)P.PX * 8, (uint64_t)P.pxy * 8, (uint64_t)NA * P.pxy * 8};
+    const uint32_t box[4] = {32, (uint32_t)P.BY, (uint32_t)nbox, 1};
+    return jr_encode_tensor_map_f64(m, base, 4, dims, str, box);
+}
+
+static int run_pack(jr_context *ctx, const PackArgs &pa, int maxrows)
+{
+    if (pa.njobs == 0) return JR_OK;
+    dim3 grid(maxrows < 4096 ? maxrows : 4096, pa.njobs, 1), block(128, 1, 1);
+    k_box_pack<<<grid, block, 0, ctx->stream>>>(pa);
+    ctx->launches++;
+    JR_CHECK_LAUNCH();
+    return JR_OK;
+}
+
+static BoxArr box_arr(double *set, int a, int NA, const VaPlan &P) { return BoxArr{set + (size_t)a * P.pxy, (long)P.PX, (long)NA * (long)P.pxy}; }
+
+// choose the tile height and z-chunking: maximise (wave efficiency) × (1 − warm-up share) × (owned-row share)
+static void choose_tiling(VaPlan &P, int sm_count)
+{
+    const int cand[3] = {10, 8, 16};
+    double best = -1;
+    for (int c = 0; c < 3; c++) {
+        if (P.finite_dt && cand[c] != 8) continue;  // 25 tiles per slot: only the 8-row tile fits two CTAs per SM
+        const int BY = cand[c], TY = BY - 2;
+        const long tiles = (long)((P.nx + 1 + TXW - 1) / TXW) * ((P.ny + 1 + TY - 1) / TY);
+        const long slots = (long)sm_count * (BY <= 10 ? 2 : 1);
+        const double row_eff = (double)(P.ny + 1) / ((double)((P.ny + 1 + TY - 1) / TY) * BY);
+        for (int nch = 1; nch <= 16; nch++) {
+            const int kch = (P.nz + nch - 1) / nch;
+            if (nch > 1 && kch < 16) break;
+            const int real = (P.nz + kch - 1) / kch;
+            const double waves = (double)(tiles * real) / slots;
+            const double eff = waves / ceil(waves) * (double)kch / (kch + 1.4) * row_eff;
+            if (eff > best * 1.0001) { best = eff; P.BY = BY; P.nchunk = real; }
+        }
+    }
+}
+
+int jr_stokes3d_VA_fused_begin(jr_context *ctx, const jr_fields *s, const jr_stokes_opts *o)
+{
+    VaPlan &P = g_plans[ctx];
+    const int nx = s->n[0], ny = s->n[1], nz = s->n[2];
+    const bool fin = std::isfinite(o->dt);
+    P.nx = nx; P.ny = ny; P.nz = nz;
+    P.PX = (nx + 2 + 3) & ~3; P.PY = ny + 2; P.PZ = nz + 2;
+    P.pxy = (size_t)P.PX * P.PY;
+    P.finite_dt = fin;
+    const size_t plane = P.pxy * sizeof(double);
+    void *p = nullptr;
+    int st;
+    const char *names[4] = {"box_S0", "box_S1", "box_C", "box_D"};
+    const int NA[4] = {S_N, S_N, C_N, D_N};
+    double **dst[4] = {&P.S[0], &P.S[1], &P.C, &P.D};
+    for (int q = 0; q < 4; q++) {
+        if (q == 3 && !fin) { P.D = nullptr; continue; }
+        const size_t bytes = plane * NA[q] * P.PZ;
+        if ((st = jr_ctx_scratch(ctx, names[q], bytes, &p))) return st;
+        *dst[q] = (double *)p;
+        JR_CUDA(cudaMemsetAsync(p, 0, bytes, ctx->stream));
+    }
+    choose_tiling(P, ctx->sm_count);
+    // test / tuning overrides of the tiling heuristic
+    if (const char *fb = getenv("JRB200_VA_BY")) {
+        const int b = atoi(fb);
+        if (!fin && (b == 8 || b == 10 || b == 16)) P.BY = b;
+    }
+    if (const char *fc = getenv("JRB200_VA_NCHUNK")) {
+        const int c = atoi(fc);
+        if (c >= 1 && c <= nz) {
+            const int kch = (nz + c - 1) / c;
+            P.nchunk = (nz + kch - 1) / kch;
+        }
+    }
+    if ((st = set_tma_map(&P.mS5[0], P.S[0], P, S_N, 5))) return st;
+    if ((st = set_tma_map(&P.mS5[1], P.S[1], P, S_N, 5))) return st;
+    if ((st = set_tma_map(&P.mC1, P.C, P, C_N, 1))) return st;
+    if ((st = set_tma_map(&P.mC4, P.C, P, C_N, 4))) return st;
+    if (fin) {
+        if ((st = set_tma_map(&P.mD1, P.D, P, D_N, 1))) return st;
+        if ((st = set_tma_map(&P.mD2, P.D, P, D_N, 2))) return st;
+        if ((st = set_tma_map(&P.mD7, P.D, P, D_N, 7))) return st;
+    }
+
+    // pack the user's dense arrays into the box sets
+    PackArgs pa;
+    pa.njobs = 0;
+    auto add = [&](double *dense, double *set, int a, int NAq, int n0, int n1, int n2, int o0, int o1, int o2, int mode) {
+        PackJob &J = pa.j[pa.njobs++];
+        J.dense = dense; J.box = box_arr(set, a, NAq, P);
+        J.n[0] = n0; J.n[1] = n1; J.n[2] = n2; J.o[0] = o0; J.o[1] = o1; J.o[2] = o2; J.mode = mode;
+    };
+    add(F(Vx), P.S[0], S_Vx, S_N, nx + 1, ny + 2, nz + 2, 1, 0, 0, 0);
+    add(F(Vy), P.S[0], S_Vy, S_N, nx + 2, ny + 1, nz + 2, 0, 1, 0, 0);
+    add(F(Vz), P.S[0], S_Vz, S_N, nx + 2, ny + 2, nz + 1, 0, 0, 1, 0);
+    add(F(P), P.S[0], S_P, S_N, nx, ny, nz, 1, 1, 1, 0);
+    add(F(txx), P.S[0], S_txx, S_N, nx, ny, nz, 1, 1, 1, 0);
+    add(F(tyy), P.S[0], S_tyy, S_N, nx, ny, nz, 1, 1, 1, 0);
+    add(F(tzz), P.S[0], S_tzz, S_N, nx, ny, nz, 1, 1, 1, 0);
+    add(F(tyz), P.S[0], S_tyz, S_N, nx, ny + 1, nz + 1, 1, 1, 1, 0);
+    add(F(txz), P.S[0], S_txz, S_N, nx + 1, ny, nz + 1, 1, 1, 1, 0);
+    add(F(txy), P.S[0], S_txy, S_N, nx + 1, ny + 1, nz, 1, 1, 1, 0);
+    add(F(eta), P.C, C_eta, C_N, nx, ny, nz, 0, 0, 0, 2);
+    add(F(etatau), P.C, C_ett, C_N, nx, ny, nz, 1, 1, 1, 0);
+    add(F(rhogx), P.C, C_fx, C_N, nx, ny, nz, 1, 1, 1, 0);
+    add(F(rhogy), P.C, C_fy, C_N, nx, ny, nz, 1, 1, 1, 0);
+    add(F(rhogz), P.C, C_fz, C_N, nx, ny, nz, 1, 1, 1, 0);
+    if (fin) {
+        add(F(G), P.D, D_G, D_N, nx, ny, nz, 0, 0, 0, 2);
+        add(F(K), P.D, D_K, D_N, nx, ny, nz, 1, 1, 1, 0);
+        add(F(P0), P.D, D_P0, D_N, nx, ny, nz, 1, 1, 1, 0);
+        add(F(Q), P.D, D_Q, D_N, nx, ny, nz, 1, 1, 1, 0);
+        add(F(txx_o), P.D, D_oxx, D_N, nx, ny, nz, 1, 1, 1, 0);
+        add(F(tyy_o), P.D, D_oyy, D_N, nx, ny, nz, 1, 1, 1, 0);
+        add(F(tzz_o), P.D, D_ozz, D_N, nx, ny, nz, 1, 1, 1, 0);
+        add(F(tyz_o), P.D, D_oyz, D_N, nx, ny + 1, nz + 1, 1, 1, 1, 0);
+        add(F(txz_o), P.D, D_oxz, D_N, nx + 1, ny, nz + 1, 1, 1, 1, 0);
+        add(F(txy_o), P.D, D_oxy, D_N, nx + 1, ny + 1, nz, 1, 1, 1, 0);
+    }
+    if ((st = run_pack(ctx, pa, (ny + 2) * (nz + 2)))) return st;
+    return JR_OK;
+}
+
+template <int BY, bool FIN, bool DG, int NSTv>
+static int launch_one(jr_context *ctx, const VaPlan &P, const VaArgs &a)
+{
+    constexpr int TY = BY - 2;
+    constexpr int smem = NSTv * SlotMap<FIN>::NARR * 32 * BY * 8;
+    static bool attr_set = false;
+    if (!attr_set) {
+        JR_CUDA(cudaFuncSetAttribute(k_va_tma<BY, FIN, DG, NSTv>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        JR_CUDA(cudaFuncSetAttribute(k_va_tma<BY, FIN, DG, NSTv>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                     cudaSharedmemCarveoutMaxShared));
+        if (getenv("JRB200_VERBOSE")) {
+            int nb = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_va_tma<BY, FIN, DG, NSTv>, 32 * BY, smem);
+            fprintf(stderr, "[jrb200] k_va_tma<BY=%d,finite_dt=%d,diag=%d,stages=%d>: %d B smem, %d CTA/SM, nchunk=%d\n", BY, (int)FIN,
+                    (int)DG, NSTv, smem, nb, P.nchunk);
+        }
+        attr_set = true;
+    }
+    dim3 grid((P.nx + 1 + TXW - 1) / TXW, (P.ny + 1 + TY - 1) / TY, (P.nz + a.kchunk - 1) / a.kchunk), block(32, BY, 1);
+    k_va_tma<BY, FIN, DG, NSTv><<<grid, block, smem, ctx->stream>>>(a);
+    return JR_OK;
+}
+
+static int launch_va(jr_context *ctx, const VaPlan &P, const VaArgs &a, int diag)
+{
+    if (P.finite_dt) return diag ? launch_one<8, true, true, 2>(ctx, P, a) : launch_one<8, true, false, 2>(ctx, P, a);
+    switch (P.BY) {
+    case 8: return diag ? launch_one<8, false, true, 3>(ctx, P, a) : launch_one<8, false, false, 3>(ctx, P, a);
+    case 10: return diag ? launch_one<10, false, true, 3>(ctx, P, a) : launch_one<10, false, false, 3>(ctx, P, a);
+    default: return diag ? launch_one<16, false, true, 3>(ctx, P, a) : launch_one<16, false, false, 3>(ctx, P, a);
+    }
+}
+
+// `parity` 0: set S0 → S1, 1: S1 → S0.
+int jr_stokes3d_VA_fused_iter(jr_context *ctx, const jr_fields *s, const jr_stokes_opts *o, int diag, int parity)
+{
+    auto it = g_plans.find(ctx);
+    JR_REQUIRE(it != g_plans.end() && it->second.S[0], JR_ERR_ARG, "fused iteration without jr_stokes3d_VA_fused_begin");
+    const VaPlan &P = it->second;
+    const int nx = P.nx, ny = P.ny, nz = P.nz;
+    double *in = P.S[parity ? 1 : 0], *out = P.S[parity ? 0 : 1];
+
+    VaArgs a;
+    a.mS5 = P.mS5[parity ? 1 : 0]; a.mC1 = P.mC1; a.mC4 = P.mC4;
+    if (P.finite_dt) { a.mD1 = P.mD1; a.mD2 = P.mD2; a.mD7 = P.mD7; }
+    else { a.mD1 = P.mC1; a.mD2 = P.mC1; a.mD7 = P.mC1; }
+    a.out = out;
+    a.divV = F(divV); a.RP = F(RP); a.exx = F(exx); a.eyy = F(eyy); a.ezz = F(ezz); a.eyz = F(eyz); a.exz = F(exz); a.exy = F(exy);
+    a.Rx = F(Rx); a.Ry = F(Ry); a.Rz = F(Rz); a.Ux = F(Ux); a.Uy = F(Uy); a.Uz = F(Uz);
+    a.nx = nx; a.ny = ny; a.nz = nz; a.PX = P.PX; a.PY = P.PY;
+    a.kchunk = (nz + P.nchunk - 1) / P.nchunk;
+    a._dx = o->_di[0]; a._dy = o->_di[1]; a._dz = o->_di[2]; a.dt = o->dt; a.r = o->r; a.theta_dtau = o->theta_dtau;
+    a.eta_dtau = o->eta_dtau;
+    int st = launch_va(ctx, P, a, diag);
+    if (st) return st;
+
+    BcArgsB b;
+    b.A[0] = BcArrB{box_arr(in, S_Vx, S_N, P), box_arr(out, S_Vx, S_N, P), F(Ux), {nx + 1, ny + 2, nz + 2}, {1, 0, 0}, 0};
+    b.A[1] = BcArrB{box_arr(in, S_Vy, S_N, P), box_arr(out, S_Vy, S_N, P), F(Uy), {nx + 2, ny + 1, nz + 2}, {0, 1, 0}, 1};
+    b.A[2] = BcArrB{box_arr(in, S_Vz, S_N, P), box_arr(out, S_Vz, S_N, P), F(Uz), {nx + 2, ny + 2, nz + 1}, {0, 0, 1}, 2};
+    // flags: left,right,front,back,top,bot.  no_slip: bot → z lo, top → z hi; free_slip (Q2): top → z lo, bot → z hi
+    const int32_t *fs = o->free_slip, *ns = o->no_slip;
+    b.lo_fs[0] = fs[0]; b.hi_fs[0] = fs[1]; b.lo_ns[0] = ns[0]; b.hi_ns[0] = ns[1];
+    b.lo_fs[1] = fs[2]; b.hi_fs[1] = fs[3]; b.lo_ns[1] = ns[2]; b.hi_ns[1] = ns[3];
+    b.lo_fs[2] = fs[4]; b.hi_fs[2] = fs[5]; b.lo_ns[2] = ns[5]; b.hi_ns[2] = ns[4];
+    b.diag = diag; b.dt = o->dt;
+    int m = nx > ny ? nx : ny;
+    m = (m > nz ? m : nz) + 2;
+    dim3 bgrid((m + 31) / 32, (m + 7) / 8, 18), bblock(32, 8, 1);
+    k_bc_box3<<<bgrid, bblock, 0, ctx->stream>>>(b);
+    ctx->launches += 2;
+    JR_CHECK_LAUNCH();
+    return JR_OK;
+}
+
+// unpack the current state set into the user's dense arrays; `niter` = iterations done since begin
+int jr_stokes3d_VA_fused_finish(jr_context *ctx, const jr_fields *s, int64_t niter)
+{
+    auto it = g_plans.find(ctx);
+    JR_REQUIRE(it != g_plans.end() && it->second.S[0], JR_ERR_ARG, "fused finish without begin");
+    const VaPlan &P = it->second;
+    const int nx = P.nx, ny = P.ny, nz = P.nz;
+    double *cur = P.S[niter & 1];
+    PackArgs pa;
+    pa.njobs = 0;
+    auto add = [&](double *dense, int a, int n0, int n1, int n2, int o0, int o1, int o2) {
+        PackJob &J = pa.j[pa.njobs++];
+        J.dense = dense; J.box = box_arr(cur, a, S_N, P);
+        J.n[0] = n0; J.n[1] = n1; J.n[2] = n2; J.o[0] = o0; J.o[1] = o1; J.o[2] = o2; J.mode = 1;
+    };
+    add(F(Vx), S_Vx, nx + 1, ny + 2, nz + 2, 1, 0, 0);
+    add(F(Vy), S_Vy, nx + 2, ny + 1, nz + 2, 0, 1, 0);
+    add(F(Vz), S_Vz, nx + 2, ny + 2, nz + 1, 0, 0, 1);
+    add(F(P), S_P, nx, ny, nz, 1, 1, 1);
+    add(F(txx), S_txx, nx, ny, nz, 1, 1, 1);
+    add(F(tyy), S_tyy, nx, ny, nz, 1, 1, 1);
+    add(F(tzz), S_tzz, nx, ny, nz, 1, 1, 1);
+    add(F(tyz), S_tyz, nx, ny + 1, nz + 1, 1, 1, 1);
+    add(F(txz), S_txz, nx + 1, ny, nz + 1, 1, 1, 1);
+    add(F(txy), S_txy, nx + 1, ny + 1, nz, 1, 1, 1);
+    return run_pack(ctx, pa, (ny + 2) * (nz + 2));
+}

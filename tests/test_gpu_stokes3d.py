@@ -52,6 +52,22 @@ def test_fixed_iterations_random_state(oracle, ni, dt, finite_K, unfused):
         compare_slots(st.slots(), d, FIELDS_STATE + FIELDS_DIAG, TOL, f"ni={ni} niter={niter}")
 
 
+@pytest.mark.parametrize("BY,nchunk", [(8, 1), (8, 3), (10, 1), (10, 2), (16, 1), (16, 4)])
+@pytest.mark.parametrize("dt,finite_K", [(0.7, True), (np.inf, False)])
+def test_fused_tilings(oracle, monkeypatch, BY, nchunk, dt, finite_K):
+    """every tile height / z-chunking of the TMA kernel gives the same (oracle) result: tile seams in x, y and z"""
+    from justrelax_jl_b200 import setups
+
+    monkeypatch.setenv("JRB200_VA_BY", str(BY))
+    monkeypatch.setenv("JRB200_VA_NCHUNK", str(nchunk))
+    ni = (67, 35, 41)
+    s = setups.random_stokes3d(ni, seed=99, dt=dt, finite_K=finite_K)
+    flags = dict(free_slip=[1] * 6, no_slip=[0] * 6, periodic=[0] * 6)
+    for niter in (1, 4):
+        st, d = _run_both(oracle, s, niter, flags, False)
+        compare_slots(st.slots(), d, FIELDS_STATE + FIELDS_DIAG, TOL, f"BY={BY} nchunk={nchunk} niter={niter}")
+
+
 @pytest.mark.parametrize("unfused", [True, False], ids=["unfused", "fused"])
 def test_mixed_boundary_flags(oracle, unfused):
     from justrelax_jl_b200 import setups
