@@ -249,7 +249,7 @@ def run_ours(args):
                    "decomposition": "independent blocks per rank" if world > 1 else "single block"},
         "T_eff_GBs_per_gpu": achieved, "T_eff_frac_of_8TBs": achieved / 8000.0,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_kind": peak_kind, "kernel": "k_stokes3d_va_fused<8,false>",
+                     "traffic": None, "peak_kind": peak_kind, "kernel": "k_va_tma (TMA-staged fused 3D-VA iteration)",
                      "algorithmic_bytes_per_launch": A_EFF_BYTES_PER_CELL * cells},
         "e2e": {"value": e2e_ips, "unit": "iters/s", "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": d2h / args.steps,
                 "note": f"one solve of {args.steps} PT iterations incl. upload of 12 input arrays and download of V,P,τ"},

@@ -50,7 +50,12 @@ struct alignas(64) VaArgs {
     CUtensorMap mS5, mC1, mC4, mD1, mD2, mD7;  // in-state set (5-array boxes), const set, finite-dt set
     double *out;                               // out-state set base
     double *divV, *RP, *exx, *eyy, *ezz, *eyz, *exz, *exy, *Rx, *Ry, *Rz, *Ux, *Uy, *Uz;  // dense user arrays (DIAG)
+    unsigned long long *progress;              // grid-wide step counter (soft lock-step of the resident CTAs)
+    unsigned long long progress_base;          // counter value at launch
     int nx, ny, nz, PX, PY, kchunk;
+    int ntx, nty, nchunk;                      // work items: ntx · nty column tiles × nchunk z-chunks
+    int slack;                                 // a CTA may run at most DEPTH + slack z-steps ahead of the slowest one
+    int pol_ld, pol_st;  // L2 eviction policy of the TMA loads / output stores (0 normal, 1 evict_first, 2 evict_last)
     double _dx, _dy, _dz, dt, r, theta_dtau, eta_dtau;
 };
 
@@ -63,6 +68,15 @@ __device__ __forceinline__ bool jr_elect_one()
     return pred != 0;
 }
 
+// Persistent kernel.  grid = min(resident CTA slots, work items), launched cooperatively so that every CTA is
+// resident.  Work item = (column tile, z-chunk), numbered z-chunk-major / y / x-fastest; CTA c takes items
+// c, c+G, c+2G, …; every item is kchunk+2 z-steps (step 0 fills the register queue, step 1 is the warm-up plane).
+//   producer = one elected lane of warp 0 (the southern halo row: it has no momentum/store work after the
+//       barrier, so the TMA issue rides in its idle time).  It issues the loads of z-step g+DEPTH into the ring slot
+//       the barrier has just freed, but only once every CTA of the grid has reached step g − slack (grid-wide
+//       progress counter, polled before the barrier so the L2 round trip is hidden): neighbouring tiles then load
+//       their shared halo rows within a few steps of each other and the second reader hits L2 instead of HBM.
+//   all warps: wait on the slot's full mbarrier, update, ONE __syncthreads per step, store.
 template <int BY, bool FINITE_DT, bool DIAG, int NST>
 __global__ void __launch_bounds__(32 * BY, (BY <= 10 ? 2 : 1)) k_va_tma(const __grid_constant__ VaArgs a)
 {
@@ -76,22 +90,12 @@ __global__ void __launch_bounds__(32 * BY, (BY <= 10 ? 2 : 1)) k_va_tma(const __
     double *const sm = reinterpret_cast<double *>(smem_raw);
 
     const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 32 + tx;
-    const int x0 = blockIdx.x * TXW, y0 = blockIdx.y * TY;
-    const int X = x0 + tx, Y = y0 + ty;  // box coordinates of this thread; cell (gi, gj) = (X-1, Y-1)
-    const int gi = X - 1, gj = Y - 1;
     const int nx = a.nx, ny = a.ny, nz = a.nz;
-    const int kb = blockIdx.z * a.kchunk, ke = min(kb + a.kchunk, nz);
-
-    const bool own = tx >= 1 && tx <= TXW && ty >= 1 && ty <= TY;
-    const bool cell = own && gi < nx && gj < ny;
-    const bool vxy = own && gi <= nx && gj <= ny;  // xy edge exists
-    const bool vxz = own && gi <= nx && gj < ny;   // xz edge exists
-    const bool vyz = own && gi < nx && gj <= ny;   // yz edge exists
-    const bool stVx = cell && gi >= 1, stVy = cell && gj >= 1;
-
-    const double _dx = a._dx, _dy = a._dy, _dz = a._dz, th = a.theta_dtau;
-    const double inv3 = jr_inv(3.0);
-    const double dtr_inf = jr_inv(th + 1.0);  // compute_dτ_r with 1/(G dt) = 0: fma(η, 0, 1) = 1
+    const int G = gridDim.x, cta = blockIdx.x;
+    const int nstep = a.kchunk + 2;
+    const int ntile = a.ntx * a.nty, nitem = ntile * a.nchunk;
+    const int my_rounds = cta < nitem ? (nitem - cta + G - 1) / G : 0;
+    const int my_steps = my_rounds * nstep;
 
     if (tid == 0) {
 #pragma unroll
@@ -100,46 +104,85 @@ __global__ void __launch_bounds__(32 * BY, (BY <= 10 ? 2 : 1)) k_va_tma(const __
     }
     __syncthreads();
 
-    // producer (one elected lane of warp 0): loads of z-step k into ring slot `slot`.
-    // `full` = false loads only what the queue-filling first step of a chunk needs (V, η[, G] of plane k+1).
-    auto issue = [&](int k, int slot, bool full) {
-        uint64_t *bar = &full_bar[slot];
-        double *d = sm + (size_t)slot * SLOT;
+    // ---- producer state (CTA-uniform): the next z-step to load ----
+    int p_g = 0, p_r = 0, p_l = 0, p_slot = 0, p_x0 = 0, p_y0 = 0, p_kb = 0;
+    auto p_decode = [&]() {
+        const int item = p_r * G + cta;
+        const int chunk = item / ntile, t = item - chunk * ntile;
+        const int by = t / a.ntx, bx = t - by * a.ntx;
+        p_x0 = bx * TXW; p_y0 = by * TY; p_kb = chunk * a.kchunk;
+    };
+    p_decode();
+    // loads of step p_g (one elected lane).  Step 0 of an item only needs V, η[, G] of plane kb−1 (queue fill).
+    auto p_issue = [&]() {
+        const uint64_t pld = jr_l2_policy(a.pol_ld);
+        const int k = p_kb - 2 + p_l;
+        const bool full = p_l > 0;
+        uint64_t *bar = &full_bar[p_slot];
+        double *d = sm + (size_t)p_slot * SLOT;
         const int za = k + 2, zc = k + 1;  // arrival plane (V, η, top edges) / compute plane
         uint32_t bytes = (5 + 1 + (FINITE_DT ? 1 : 0)) * TILE_BYTES;
         if (full) bytes = NARR * TILE_BYTES;
         jr_mbar_arrive_expect_tx(bar, bytes);
-        jr_tma_load_4d(d + T_Vx * TILE, &a.mS5, x0, y0, S_Vx, za, bar);
-        jr_tma_load_4d(d + T_eta * TILE, &a.mC1, x0, y0, C_eta, za, bar);
-        if (FINITE_DT) jr_tma_load_4d(d + M::G * TILE, &a.mD1, x0, y0, D_G, za, bar);
+        jr_tma_load_4d_hint(d + T_Vx * TILE, &a.mS5, p_x0, p_y0, S_Vx, za, bar, pld);
+        jr_tma_load_4d_hint(d + T_eta * TILE, &a.mC1, p_x0, p_y0, C_eta, za, bar, pld);
+        if (FINITE_DT) jr_tma_load_4d_hint(d + M::G * TILE, &a.mD1, p_x0, p_y0, D_G, za, bar, pld);
         if (full) {
-            jr_tma_load_4d(d + T_tzz * TILE, &a.mS5, x0, y0, S_tzz, zc, bar);
+            jr_tma_load_4d_hint(d + T_tzz * TILE, &a.mS5, p_x0, p_y0, S_tzz, zc, bar, pld);
             if (FINITE_DT) {
-                jr_tma_load_4d(d + M::oyz * TILE, &a.mD2, x0, y0, D_oyz, za, bar);
-                jr_tma_load_4d(d + M::K * TILE, &a.mD7, x0, y0, D_K, zc, bar);
+                jr_tma_load_4d_hint(d + M::oyz * TILE, &a.mD2, p_x0, p_y0, D_oyz, za, bar, pld);
+                jr_tma_load_4d_hint(d + M::K * TILE, &a.mD7, p_x0, p_y0, D_K, zc, bar, pld);
             }
-            jr_tma_load_4d(d + M::ett * TILE, &a.mC4, x0, y0, C_ett, zc, bar);
+            jr_tma_load_4d_hint(d + M::ett * TILE, &a.mC4, p_x0, p_y0, C_ett, zc, bar, pld);
         }
     };
-
-    if (ty == 0) {
-        if (jr_elect_one()) {
-            jr_tma_prefetch_desc(&a.mS5);
-            jr_tma_prefetch_desc(&a.mC1);
-            jr_tma_prefetch_desc(&a.mC4);
+    auto p_advance = [&]() {
+        ++p_g;
+        if (++p_slot == NST) p_slot = 0;
+        if (++p_l == nstep) {
+            p_l = 0;
+            ++p_r;
+            if (p_r < my_rounds) p_decode();
+        }
+    };
+    // progress-counter value that says "every active CTA has reached global step gt"
+    auto p_target = [&](int gt) -> unsigned long long {
+        const int rr = gt / nstep, ll = gt - rr * nstep;
+        const int act = min(G, nitem - rr * G);
+        return a.progress_base + (unsigned long long)G * nstep * rr + (unsigned long long)act * (ll + 1);
+    };
+    // prologue: the first DEPTH steps
 #pragma unroll
-            for (int d = 0; d < DEPTH; d++)
-                if (kb - 2 + d < ke) issue(kb - 2 + d, d, d > 0);
+    for (int d = 0; d < DEPTH; d++) {
+        if (p_g < my_steps) {
+            if (ty == 0) {
+                if (jr_elect_one()) {
+                    if (d == 0) {
+                        jr_tma_prefetch_desc(&a.mS5);
+                        jr_tma_prefetch_desc(&a.mC1);
+                        jr_tma_prefetch_desc(&a.mC4);
+                    }
+                    p_issue();
+                }
+            }
+            p_advance();
         }
     }
 
+    const double _dx = a._dx, _dy = a._dy, _dz = a._dz, th = a.theta_dtau;
+    const double inv3 = jr_inv(3.0);
+    const double dtr_inf = jr_inv(th + 1.0);  // compute_dτ_r with 1/(G dt) = 0: fma(η, 0, 1) = 1
+    const double r_th = jr_div_rcp(th);       // refined 1/θ_dτ for the exact quotient x / θ_dτ
+    const uint64_t pst = jr_l2_policy(a.pol_st);
+    const size_t pxy = (size_t)a.PX * a.PY;
+
     // ---- register queue: state of plane k carried along z ----
-    double vx0, vy0, vz0;                          // V(k) at this thread's position
-    double dxx0, dyy0, exy0;                       // ∂xVx, ∂yVy, ε_xy of plane k
-    double eta0, etaxy0, sxz0, syz0;               // η(k), η̄xy(k), η pair sums of plane k
-    double g0 = 1, gxy0 = 1, gsxz0 = 0, gsyz0 = 0; // same for G (finite dt)
-    double tzz_p = 0, P_p = 0, fz_p = 0, ett_p = 1;  // plane k−1: new τzz, new P, ρgz, ητ
-    double txz_b = 0, tyz_b = 0, sRz = 0;            // new bottom-edge stresses (kz = k), partial Rz of face k
+    double vx0 = 0, vy0 = 0, vz0 = 0;                  // V(k) at this thread's position
+    double dxx0 = 0, dyy0 = 0, exy0 = 0;               // ∂xVx, ∂yVy, ε_xy of plane k
+    double eta0 = 1, etaxy0 = 1, sxz0 = 0, syz0 = 0;   // η(k), η̄xy(k), η pair sums of plane k
+    double g0 = 1, gxy0 = 1, gsxz0 = 0, gsyz0 = 0;     // same for G (finite dt)
+    double tzz_p = 0, P_p = 0, fz_p = 0, ett_p = 1;    // plane k−1: new τzz, new P, ρgz, ητ
+    double txz_b = 0, tyz_b = 0, sRz = 0;              // new bottom-edge stresses (kz = k), partial Rz of face k
 
     // queue entries of plane A from the slot that holds V(A), η(A) (reads at own position and W/E/S/N/SW neighbours)
 #define JR_FILL_QUEUE(p)                                                                                  \
@@ -163,164 +206,181 @@ __global__ void __launch_bounds__(32 * BY, (BY <= 10 ? 2 : 1)) k_va_tma(const __
         }                                                                                                 \
     } while (0)
 
-    // out-set pointer of (X, Y) in plane group Z = k+1: ((Z·10 + a)·PY + Y)·PX + X
-    const size_t pxy = (size_t)a.PX * a.PY;
-    double *po = a.out + ((size_t)kb * S_N) * pxy + (size_t)Y * a.PX + X;  // plane group Z = kb (step k = kb−1)
+    int slot = 0, g = 0;
+    uint32_t parity = 0;
+    for (int r = 0; r < my_rounds; ++r) {
+        const int item = r * G + cta;
+        const int chunk = item / ntile, t = item - chunk * ntile;
+        const int by = t / a.ntx, bx = t - by * a.ntx;
+        const int X = bx * TXW + tx, Y = by * TY + ty;  // box coordinates of this thread; cell (gi, gj) = (X-1, Y-1)
+        const int gi = X - 1, gj = Y - 1;
+        const int kb = chunk * a.kchunk, ke = min(kb + a.kchunk, nz);
+        const bool own = tx >= 1 && tx <= TXW && ty >= 1 && ty <= TY;
+        const bool cell = own && gi < nx && gj < ny;
+        const bool vxy = own && gi <= nx && gj <= ny;  // xy edge exists
+        const bool vxz = own && gi <= nx && gj < ny;   // xz edge exists
+        const bool vyz = own && gi < nx && gj <= ny;   // yz edge exists
+        const bool stVx = cell && gi >= 1, stVy = cell && gj >= 1;
+        // out-set pointer of (X, Y) in plane group Z = k+1: ((Z·10 + a)·PY + Y)·PX + X; starts at Z = kb (step k = kb−1)
+        double *po = a.out + ((size_t)kb * S_N) * pxy + (size_t)Y * a.PX + X;
 
-    // ---- first step of the chunk (k = kb−2): fill the queue with plane kb−1 ----
-    jr_mbar_wait(&full_bar[0], 0);
-    {
-        const double *p = sm + tid;
-        JR_FILL_QUEUE(p);
-    }
-    __syncthreads();
-    if (ty == 0 && kb - 2 + DEPTH < ke) {
-        if (jr_elect_one()) {
-            jr_fence_proxy_async();
-            issue(kb - 2 + DEPTH, DEPTH % NST, true);
-        }
-    }
+        for (int l = 0; l < nstep; ++l) {
+            const int k = kb - 2 + l;
+            jr_mbar_wait(&full_bar[slot], parity);
+            double *const p = sm + (size_t)slot * SLOT + tid;
 
-    int slot = 1 % NST;
-    uint32_t parity = (NST == 1) ? 1u : 0u;
-    for (int k = kb - 1; k < ke; ++k) {
-        jr_mbar_wait(&full_bar[slot], parity);
-        double *const p = sm + (size_t)slot * SLOT + tid;
+            double txx_n, tyy_n, tzz_n, txy_n, txz_n, tyz_n, P_n, divV, RP, exx, eyy, ezz, exz_t, eyz_t;
+            if (l > 0) {
+                // ---- R1: top-edge strain rates / viscosities (plane k+1 arrives), centre of plane k, six new stresses ----
+                const double vz1 = p[T_Vz * TILE], eta1 = p[T_eta * TILE];
+                exz_t = 0.5 * (_dz * (p[T_Vx * TILE] - vx0) + _dx * (vz1 - p[T_Vz * TILE - 1]));
+                eyz_t = 0.5 * (_dz * (p[T_Vy * TILE] - vy0) + _dy * (vz1 - p[T_Vz * TILE - 32]));
+                const double etaxz_t = 0.25 * (sxz0 + p[T_eta * TILE - 1] + eta1);
+                const double etayz_t = 0.25 * (syz0 + p[T_eta * TILE - 32] + eta1);
+                const double c_txx = p[T_txx * TILE], c_tyy = p[T_tyy * TILE], c_tzz = p[T_tzz * TILE];
+                const double c_txy = p[T_txy * TILE], c_txz = p[T_txz * TILE], c_tyz = p[T_tyz * TILE];
+                const double c_P = p[T_P * TILE];
+                const double dzz = (-vz0 + vz1) * _dz;
+                divV = dxx0 + dyy0 + dzz;
+                const double d3 = divV * inv3;
+                exx = dxx0 - d3; eyy = dyy0 - d3; ezz = dzz - d3;
+                if (FINITE_DT) {
+                    const double dt = a.dt;
+                    const double g1 = p[M::G * TILE];
+                    const double gxz_t = 0.25 * (gsxz0 + p[M::G * TILE - 1] + g1);
+                    const double gyz_t = 0.25 * (gsyz0 + p[M::G * TILE - 32] + g1);
+                    P_n = c_P;
+                    jr_compute_P_point(RP, P_n, p[M::P0 * TILE], divV, p[M::Q * TILE], eta0, p[M::K * TILE], g0, dt, a.r, th);
+                    {
+                        const double _Gdt = jr_inv(g0 * dt), dtr = jr_dtau_r(th, eta0, _Gdt);
+                        txx_n = c_txx + jr_stress_increment(c_txx, p[M::oxx * TILE], eta0, exx, _Gdt, dtr);
+                        tyy_n = c_tyy + jr_stress_increment(c_tyy, p[M::oyy * TILE], eta0, eyy, _Gdt, dtr);
+                        tzz_n = c_tzz + jr_stress_increment(c_tzz, p[M::ozz * TILE], eta0, ezz, _Gdt, dtr);
+                    }
+                    {
+                        const double _Gdt = jr_inv(gxy0 * dt), dtr = jr_dtau_r(th, etaxy0, _Gdt);
+                        txy_n = c_txy + jr_stress_increment(c_txy, p[M::oxy * TILE], etaxy0, exy0, _Gdt, dtr);
+                    }
+                    {
+                        const double _Gdt = jr_inv(gxz_t * dt), dtr = jr_dtau_r(th, etaxz_t, _Gdt);
+                        txz_n = c_txz + jr_stress_increment(c_txz, p[M::oxz * TILE], etaxz_t, exz_t, _Gdt, dtr);
+                    }
+                    {
+                        const double _Gdt = jr_inv(gyz_t * dt), dtr = jr_dtau_r(th, etayz_t, _Gdt);
+                        tyz_n = c_tyz + jr_stress_increment(c_tyz, p[M::oyz * TILE], etayz_t, eyz_t, _Gdt, dtr);
+                    }
+                } else {
+                    // _Kdt = _Gdt = _dt = 0 exactly (PressureKernels.jl:186-195 with dt = Inf)
+                    RP = -divV;
+                    const double psi = jr_div_by(jr_inv_nr(jr_inv_nr(eta0)) * a.r, th, r_th);
+                    P_n = (-divV) * psi + c_P;
+                    txx_n = c_txx + dtr_inf * fma(2.0 * eta0, exx, -c_txx);
+                    tyy_n = c_tyy + dtr_inf * fma(2.0 * eta0, eyy, -c_tyy);
+                    tzz_n = c_tzz + dtr_inf * fma(2.0 * eta0, ezz, -c_tzz);
+                    txy_n = c_txy + dtr_inf * fma(2.0 * etaxy0, exy0, -c_txy);
+                    txz_n = c_txz + dtr_inf * fma(2.0 * etaxz_t, exz_t, -c_txz);
+                    tyz_n = c_tyz + dtr_inf * fma(2.0 * etayz_t, eyz_t, -c_tyz);
+                }
+                // ---- publish the new stresses / pressure in place (only their owner read the old values) ----
+                p[T_txx * TILE] = txx_n; p[T_tyy * TILE] = tyy_n; p[T_P * TILE] = P_n;
+                p[T_txy * TILE] = txy_n; p[T_txz * TILE] = txz_n; p[T_tyz * TILE] = tyz_n;
+            }
+            // lane 0 of warp 0 samples the grid-wide progress before the barrier (latency hidden behind it)
+            unsigned long long seen = 0;
+            if (tid == 0) asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(a.progress) : "memory");
+            __syncthreads();
+            // every thread is past its reads of the previous step's slot: refill it with the loads of step g+DEPTH
+            if (ty == 0) {
+                if (tid == 0) {
+                    asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(a.progress), "l"(1ull) : "memory");
+                    if (p_g < my_steps) {
+                        const int gt = g - a.slack;  // soft lock-step: everybody has reached step g − slack
+                        if (gt >= 0) {
+                            const unsigned long long target = p_target(gt);
+                            while (seen < target) asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(a.progress) : "memory");
+                        }
+                        jr_fence_proxy_async();
+                        p_issue();
+                    }
+                }
+                __syncwarp();
+            }
+            if (p_g < my_steps) p_advance();
+            ++g;
 
-        // ---- R1: top-edge strain rates / viscosities (plane k+1 arrives), centre of plane k, six new stresses ----
-        double txx_n, tyy_n, tzz_n, txy_n, txz_n, tyz_n, P_n, divV, RP, exx, eyy, ezz, exz_t, eyz_t;
-        {
-            const double vz1 = p[T_Vz * TILE], eta1 = p[T_eta * TILE];
-            exz_t = 0.5 * (_dz * (p[T_Vx * TILE] - vx0) + _dx * (vz1 - p[T_Vz * TILE - 1]));
-            eyz_t = 0.5 * (_dz * (p[T_Vy * TILE] - vy0) + _dy * (vz1 - p[T_Vz * TILE - 32]));
-            const double etaxz_t = 0.25 * (sxz0 + p[T_eta * TILE - 1] + eta1);
-            const double etayz_t = 0.25 * (syz0 + p[T_eta * TILE - 32] + eta1);
-            const double c_txx = p[T_txx * TILE], c_tyy = p[T_tyy * TILE], c_tzz = p[T_tzz * TILE];
-            const double c_txy = p[T_txy * TILE], c_txz = p[T_txz * TILE], c_tyz = p[T_tyz * TILE];
-            const double c_P = p[T_P * TILE];
-            const double dzz = (-vz0 + vz1) * _dz;
-            divV = dxx0 + dyy0 + dzz;
-            const double d3 = divV * inv3;
-            exx = dxx0 - d3; eyy = dyy0 - d3; ezz = dzz - d3;
-            if (FINITE_DT) {
-                const double dt = a.dt;
-                const double g1 = p[M::G * TILE];
-                const double gxz_t = 0.25 * (gsxz0 + p[M::G * TILE - 1] + g1);
-                const double gyz_t = 0.25 * (gsyz0 + p[M::G * TILE - 32] + g1);
-                P_n = c_P;
-                jr_compute_P_point(RP, P_n, p[M::P0 * TILE], divV, p[M::Q * TILE], eta0, p[M::K * TILE], g0, dt, a.r, th);
-                {
-                    const double _Gdt = jr_inv(g0 * dt), dtr = jr_dtau_r(th, eta0, _Gdt);
-                    txx_n = c_txx + jr_stress_increment(c_txx, p[M::oxx * TILE], eta0, exx, _Gdt, dtr);
-                    tyy_n = c_tyy + jr_stress_increment(c_tyy, p[M::oyy * TILE], eta0, eyy, _Gdt, dtr);
-                    tzz_n = c_tzz + jr_stress_increment(c_tzz, p[M::ozz * TILE], eta0, ezz, _Gdt, dtr);
+            if (l > 0) {
+                // ---- R2: momentum residuals and velocity update of plane k, partial Rz of face k+1 ----
+                const double c_fz = p[M::fz * TILE], c_ett = p[M::ett * TILE];
+                const double sRz_next = _dx * (p[T_txz * TILE + 1] - txz_n) + _dy * (p[T_tyz * TILE + 32] - tyz_n);
+                const bool kin = k >= kb && k < ke;  // this chunk owns plane k (k = kb−1 is the warm-up plane)
+                if (kin) {
+                    if (cell) {
+                        jr_st_hint(&po[S_P * pxy], P_n, pst); jr_st_hint(&po[S_txx * pxy], txx_n, pst);
+                        jr_st_hint(&po[S_tyy * pxy], tyy_n, pst); jr_st_hint(&po[S_tzz * pxy], tzz_n, pst);
+                        if (DIAG) {
+                            const size_t c = ((size_t)k * ny + gj) * nx + gi;
+                            a.divV[c] = divV; a.RP[c] = RP; a.exx[c] = exx; a.eyy[c] = eyy; a.ezz[c] = ezz;
+                        }
+                    }
+                    if (vxy) {
+                        jr_st_hint(&po[S_txy * pxy], txy_n, pst);
+                        if (DIAG) a.exy[((size_t)k * (ny + 1) + gj) * (nx + 1) + gi] = exy0;
+                    }
+                    // x-momentum: face gi between cells gi−1 (W) and gi
+                    if (stVx) {
+                        const double R = (-p[T_txx * TILE - 1] + txx_n) * _dx + _dy * (p[T_txy * TILE + 32] - txy_n) +
+                                         _dz * (txz_n - txz_b) - (-p[T_P * TILE - 1] + P_n) * _dx -
+                                         0.5 * (p[M::fx * TILE - 1] + p[M::fx * TILE]);
+                        const double vn = vx0 + jr_div_nr(R * a.eta_dtau, 0.5 * (p[M::ett * TILE - 1] + c_ett));
+                        jr_st_hint(&po[S_Vx * pxy], vn, pst);
+                        if (DIAG) {
+                            a.Rx[((size_t)k * ny + gj) * (nx - 1) + (gi - 1)] = R;
+                            a.Ux[((size_t)(k + 1) * (ny + 2) + gj + 1) * (nx + 1) + gi] = vn * a.dt;
+                        }
+                    }
+                    // y-momentum: face gj between cells gj−1 (S) and gj
+                    if (stVy) {
+                        const double R = _dx * (p[T_txy * TILE + 1] - txy_n) + _dy * (tyy_n - p[T_tyy * TILE - 32]) +
+                                         _dz * (tyz_n - tyz_b) - (-p[T_P * TILE - 32] + P_n) * _dy -
+                                         0.5 * (p[M::fy * TILE - 32] + p[M::fy * TILE]);
+                        const double vn = vy0 + jr_div_nr(R * a.eta_dtau, 0.5 * (p[M::ett * TILE - 32] + c_ett));
+                        jr_st_hint(&po[S_Vy * pxy], vn, pst);
+                        if (DIAG) {
+                            a.Ry[((size_t)k * (ny - 1) + (gj - 1)) * nx + gi] = R;
+                            a.Uy[((size_t)(k + 1) * (ny + 1) + gj) * (nx + 2) + gi + 1] = vn * a.dt;
+                        }
+                    }
+                    // z-momentum: face k between planes k−1 and k
+                    if (cell && k >= 1) {
+                        const double R = sRz + (-tzz_p + tzz_n) * _dz - (-P_p + P_n) * _dz - 0.5 * (fz_p + c_fz);
+                        const double vn = vz0 + jr_div_nr(R * a.eta_dtau, 0.5 * (ett_p + c_ett));
+                        jr_st_hint(&po[S_Vz * pxy], vn, pst);
+                        if (DIAG) {
+                            a.Rz[((size_t)(k - 1) * ny + gj) * nx + gi] = R;
+                            a.Uz[((size_t)k * (ny + 2) + gj + 1) * (nx + 2) + gi + 1] = vn * a.dt;
+                        }
+                    }
                 }
-                {
-                    const double _Gdt = jr_inv(gxy0 * dt), dtr = jr_dtau_r(th, etaxy0, _Gdt);
-                    txy_n = c_txy + jr_stress_increment(c_txy, p[M::oxy * TILE], etaxy0, exy0, _Gdt, dtr);
+                // top edges (kz = k+1) belong to the chunk that owns plane k; the kz = 0 edges to chunk 0's warm-up
+                if (kin || k == -1) {
+                    double *const pe = po + S_N * pxy;
+                    if (vxz) {
+                        jr_st_hint(&pe[S_txz * pxy], txz_n, pst);
+                        if (DIAG) a.exz[((size_t)(k + 1) * ny + gj) * (nx + 1) + gi] = exz_t;
+                    }
+                    if (vyz) {
+                        jr_st_hint(&pe[S_tyz * pxy], tyz_n, pst);
+                        if (DIAG) a.eyz[((size_t)(k + 1) * (ny + 1) + gj) * nx + gi] = eyz_t;
+                    }
                 }
-                {
-                    const double _Gdt = jr_inv(gxz_t * dt), dtr = jr_dtau_r(th, etaxz_t, _Gdt);
-                    txz_n = c_txz + jr_stress_increment(c_txz, p[M::oxz * TILE], etaxz_t, exz_t, _Gdt, dtr);
-                }
-                {
-                    const double _Gdt = jr_inv(gyz_t * dt), dtr = jr_dtau_r(th, etayz_t, _Gdt);
-                    tyz_n = c_tyz + jr_stress_increment(c_tyz, p[M::oyz * TILE], etayz_t, eyz_t, _Gdt, dtr);
-                }
-            } else {
-                // _Kdt = _Gdt = _dt = 0 exactly (PressureKernels.jl:186-195 with dt = Inf)
-                RP = -divV;
-                const double psi = jr_inv(jr_inv(eta0)) * a.r / th;
-                P_n = (-divV) * psi + c_P;
-                txx_n = c_txx + dtr_inf * fma(2.0 * eta0, exx, -c_txx);
-                tyy_n = c_tyy + dtr_inf * fma(2.0 * eta0, eyy, -c_tyy);
-                tzz_n = c_tzz + dtr_inf * fma(2.0 * eta0, ezz, -c_tzz);
-                txy_n = c_txy + dtr_inf * fma(2.0 * etaxy0, exy0, -c_txy);
-                txz_n = c_txz + dtr_inf * fma(2.0 * etaxz_t, exz_t, -c_txz);
-                tyz_n = c_tyz + dtr_inf * fma(2.0 * etayz_t, eyz_t, -c_tyz);
+                tzz_p = tzz_n; P_p = P_n; fz_p = c_fz; ett_p = c_ett;
+                txz_b = txz_n; tyz_b = tyz_n; sRz = sRz_next;
+                po += S_N * pxy;
             }
+            // ---- the queue for the next step: plane k+1 becomes plane k ----
+            JR_FILL_QUEUE(p);
+            if (++slot == NST) { slot = 0; parity ^= 1u; }
         }
-        // ---- publish the new stresses / pressure in place (only their owner read the old values) ----
-        p[T_txx * TILE] = txx_n; p[T_tyy * TILE] = tyy_n; p[T_P * TILE] = P_n;
-        p[T_txy * TILE] = txy_n; p[T_txz * TILE] = txz_n; p[T_tyz * TILE] = tyz_n;
-        __syncthreads();
-        // every thread is past its reads of the previous slot: refill it with the loads of step k+DEPTH
-        if (ty == 0 && k + DEPTH < ke) {
-            if (jr_elect_one()) {
-                jr_fence_proxy_async();
-                int ns = slot + DEPTH;
-                if (ns >= NST) ns -= NST;
-                issue(k + DEPTH, ns, true);
-            }
-        }
-
-        // ---- R2: momentum residuals and velocity update of plane k, partial Rz of face k+1 ----
-        const double c_fz = p[M::fz * TILE], c_ett = p[M::ett * TILE];
-        const double sRz_next = _dx * (p[T_txz * TILE + 1] - txz_n) + _dy * (p[T_tyz * TILE + 32] - tyz_n);
-        const bool kin = k >= kb;  // this chunk owns plane k (k = kb−1 is the warm-up plane)
-        if (kin) {
-            if (cell) {
-                po[S_P * pxy] = P_n; po[S_txx * pxy] = txx_n; po[S_tyy * pxy] = tyy_n; po[S_tzz * pxy] = tzz_n;
-                if (DIAG) {
-                    const size_t c = ((size_t)k * ny + gj) * nx + gi;
-                    a.divV[c] = divV; a.RP[c] = RP; a.exx[c] = exx; a.eyy[c] = eyy; a.ezz[c] = ezz;
-                }
-            }
-            if (vxy) {
-                po[S_txy * pxy] = txy_n;
-                if (DIAG) a.exy[((size_t)k * (ny + 1) + gj) * (nx + 1) + gi] = exy0;
-            }
-            // x-momentum: face gi between cells gi−1 (W) and gi
-            if (stVx) {
-                const double R = (-p[T_txx * TILE - 1] + txx_n) * _dx + _dy * (p[T_txy * TILE + 32] - txy_n) + _dz * (txz_n - txz_b) -
-                                 (-p[T_P * TILE - 1] + P_n) * _dx - 0.5 * (p[M::fx * TILE - 1] + p[M::fx * TILE]);
-                const double vn = vx0 + R * a.eta_dtau / (0.5 * (p[M::ett * TILE - 1] + c_ett));
-                po[S_Vx * pxy] = vn;
-                if (DIAG) {
-                    a.Rx[((size_t)k * ny + gj) * (nx - 1) + (gi - 1)] = R;
-                    a.Ux[((size_t)(k + 1) * (ny + 2) + gj + 1) * (nx + 1) + gi] = vn * a.dt;
-                }
-            }
-            // y-momentum: face gj between cells gj−1 (S) and gj
-            if (stVy) {
-                const double R = _dx * (p[T_txy * TILE + 1] - txy_n) + _dy * (tyy_n - p[T_tyy * TILE - 32]) + _dz * (tyz_n - tyz_b) -
-                                 (-p[T_P * TILE - 32] + P_n) * _dy - 0.5 * (p[M::fy * TILE - 32] + p[M::fy * TILE]);
-                const double vn = vy0 + R * a.eta_dtau / (0.5 * (p[M::ett * TILE - 32] + c_ett));
-                po[S_Vy * pxy] = vn;
-                if (DIAG) {
-                    a.Ry[((size_t)k * (ny - 1) + (gj - 1)) * nx + gi] = R;
-                    a.Uy[((size_t)(k + 1) * (ny + 1) + gj) * (nx + 2) + gi + 1] = vn * a.dt;
-                }
-            }
-            // z-momentum: face k between planes k−1 and k
-            if (cell && k >= 1) {
-                const double R = sRz + (-tzz_p + tzz_n) * _dz - (-P_p + P_n) * _dz - 0.5 * (fz_p + c_fz);
-                const double vn = vz0 + R * a.eta_dtau / (0.5 * (ett_p + c_ett));
-                po[S_Vz * pxy] = vn;
-                if (DIAG) {
-                    a.Rz[((size_t)(k - 1) * ny + gj) * nx + gi] = R;
-                    a.Uz[((size_t)k * (ny + 2) + gj + 1) * (nx + 2) + gi + 1] = vn * a.dt;
-                }
-            }
-        }
-        // top edges (kz = k+1) belong to the chunk that owns plane k; the kz = 0 edges to chunk 0's warm-up
-        if (kin || kb == 0) {
-            double *const pe = po + S_N * pxy;
-            if (vxz) {
-                pe[S_txz * pxy] = txz_n;
-                if (DIAG) a.exz[((size_t)(k + 1) * ny + gj) * (nx + 1) + gi] = exz_t;
-            }
-            if (vyz) {
-                pe[S_tyz * pxy] = tyz_n;
-                if (DIAG) a.eyz[((size_t)(k + 1) * (ny + 1) + gj) * nx + gi] = eyz_t;
-            }
-        }
-        // ---- the queue for the next step: plane k+1 becomes plane k ----
-        tzz_p = tzz_n; P_p = P_n; fz_p = c_fz; ett_p = c_ett;
-        txz_b = txz_n; tyz_b = tyz_n; sRz = sRz_next;
-        JR_FILL_QUEUE(p);
-        po += S_N * pxy;
-        if (++slot == NST) { slot = 0; parity ^= 1u; }
     }
 #undef JR_FILL_QUEUE
 }
@@ -439,7 +499,7 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 int jr_encode_tensor_map_f64(CUtensorMap *out, void *base, int rank, const uint64_t *dims, const uint64_t *strides_bytes,
-                             const uint32_t *box)
+                             const uint32_t *box, int l2promo)
 {
     static PFN_encodeTiled fn = nullptr;
     if (!fn) {
@@ -458,7 +518,12 @@ int jr_encode_tensor_map_f64(CUtensorMap *out, void *base, int rank, const uint6
         if (i < rank - 1) gs[i] = strides_bytes[i];
     }
     CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, (cuuint32_t)rank, base, gd, gs, bd, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    CU_TENSOR_MAP_SWIZZLE_NONE,
+                    l2promo == 0   ? CU_TENSOR_MAP_L2_PROMOTION_NONE
+                    : l2promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                    : l2promo == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                                   : CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     JR_REQUIRE(r == CUDA_SUCCESS, JR_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %llu %llu %llu)", (int)r,
                rank, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2]);
     return JR_OK;
@@ -473,6 +538,8 @@ struct VaPlan {
     double *S[2] = {nullptr, nullptr}, *C = nullptr, *D = nullptr;
     CUtensorMap mS5[2], mC1, mC4, mD1, mD2, mD7;
     int BY = 0, nchunk = 1;
+    int pol_ld = 2, pol_st = 1, l2promo = 2, slack = 1;
+    unsigned long long *progress = nullptr, progress_base = 0;
 };
 static std::map<jr_context *, VaPlan> g_plans;
 
@@ -489,7 +556,7 @@ static int set_tma_map(CUtensorMap *m, double *base, const VaPlan &P, int NA, in
     const uint64_t dims[4] = {(uint64_t)P.PX, (uint64_t)P.PY, (uint64_t)NA, (uint64_t)P.PZ};
     const uint64_t str[3] = {(uint64_t)P.PX * 8, (uint64_t)P.pxy * 8, (uint64_t)NA * P.pxy * 8};
     const uint32_t box[4] = {32, (uint32_t)P.BY, (uint32_t)nbox, 1};
-    return jr_encode_tensor_map_f64(m, base, 4, dims, str, box);
+    return jr_encode_tensor_map_f64(m, base, 4, dims, str, box, P.l2promo);
 }
 
 static int run_pack(jr_context *ctx, const PackArgs &pa, int maxrows)
@@ -504,7 +571,8 @@ static int run_pack(jr_context *ctx, const PackArgs &pa, int maxrows)
 
 static BoxArr box_arr(double *set, int a, int NA, const VaPlan &P) { return BoxArr{set + (size_t)a * P.pxy, (long)P.PX, (long)NA * (long)P.pxy}; }
 
-// choose the tile height and z-chunking: maximise (wave efficiency) × (1 − warm-up share) × (owned-row share)
+// choose the tile height and z-chunking: maximise (round efficiency) × (1 − warm-up share) × (owned-row share).
+// With the persistent grid G = min(resident slots, items) a CTA runs ceil(items / G) items.
 static void choose_tiling(VaPlan &P, int sm_count)
 {
     const int cand[3] = {10, 8, 16};
@@ -515,12 +583,17 @@ static void choose_tiling(VaPlan &P, int sm_count)
         const long tiles = (long)((P.nx + 1 + TXW - 1) / TXW) * ((P.ny + 1 + TY - 1) / TY);
         const long slots = (long)sm_count * (BY <= 10 ? 2 : 1);
         const double row_eff = (double)(P.ny + 1) / ((double)((P.ny + 1 + TY - 1) / TY) * BY);
-        for (int nch = 1; nch <= 16; nch++) {
+        for (int nch = 1; nch <= 32; nch++) {
             const int kch = (P.nz + nch - 1) / nch;
-            if (nch > 1 && kch < 16) break;
+            if (nch > 1 && kch < 12) break;
             const int real = (P.nz + kch - 1) / kch;
-            const double waves = (double)(tiles * real) / slots;
-            const double eff = waves / ceil(waves) * (double)kch / (kch + 1.4) * row_eff;
+            const long items = tiles * real;
+            const long G = items < slots ? items : slots;
+            const long rounds = (items + G - 1) / G;
+            // useful plane-steps / (slots × steps every slot is held)
+            // measured on B200: the one-CTA-per-SM tile (16 rows) hides latency worse than two CTAs of 8 / 10 rows
+            const double occ = BY <= 10 ? 1.0 : 0.92;
+            const double eff = (double)tiles * P.nz / ((double)slots * rounds * (kch + 2)) * row_eff * occ;
             if (eff > best * 1.0001) { best = eff; P.BY = BY; P.nchunk = real; }
         }
     }
@@ -561,6 +634,14 @@ int jr_stokes3d_VA_fused_begin(jr_context *ctx, const jr_fields *s, const jr_sto
             P.nchunk = (nz + kch - 1) / kch;
         }
     }
+    if ((st = jr_ctx_scratch(ctx, "va_progress", 64, &p))) return st;
+    P.progress = (unsigned long long *)p;
+    P.progress_base = 0;
+    JR_CUDA(cudaMemsetAsync(p, 0, 64, ctx->stream));
+    if (const char *e = getenv("JRB200_VA_SLACK")) P.slack = atoi(e);
+    if (const char *e = getenv("JRB200_VA_POL_LD")) P.pol_ld = atoi(e);
+    if (const char *e = getenv("JRB200_VA_POL_ST")) P.pol_st = atoi(e);
+    if (const char *e = getenv("JRB200_VA_L2PROMO")) P.l2promo = atoi(e);
     if ((st = set_tma_map(&P.mS5[0], P.S[0], P, S_N, 5))) return st;
     if ((st = set_tma_map(&P.mS5[1], P.S[1], P, S_N, 5))) return st;
     if ((st = set_tma_map(&P.mC1, P.C, P, C_N, 1))) return st;
@@ -611,29 +692,41 @@ int jr_stokes3d_VA_fused_begin(jr_context *ctx, const jr_fields *s, const jr_sto
 }
 
 template <int BY, bool FIN, bool DG, int NSTv>
-static int launch_one(jr_context *ctx, const VaPlan &P, const VaArgs &a)
+static int launch_one(jr_context *ctx, VaPlan &P, VaArgs &a)
 {
     constexpr int TY = BY - 2;
     constexpr int smem = NSTv * SlotMap<FIN>::NARR * 32 * BY * 8;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static int cta_per_sm = 0;
+    if (!cta_per_sm) {
         JR_CUDA(cudaFuncSetAttribute(k_va_tma<BY, FIN, DG, NSTv>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         JR_CUDA(cudaFuncSetAttribute(k_va_tma<BY, FIN, DG, NSTv>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                      cudaSharedmemCarveoutMaxShared));
-        if (getenv("JRB200_VERBOSE")) {
-            int nb = 0;
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_va_tma<BY, FIN, DG, NSTv>, 32 * BY, smem);
-            fprintf(stderr, "[jrb200] k_va_tma<BY=%d,finite_dt=%d,diag=%d,stages=%d>: %d B smem, %d CTA/SM, nchunk=%d\n", BY, (int)FIN,
-                    (int)DG, NSTv, smem, nb, P.nchunk);
-        }
-        attr_set = true;
+        int nb = 0;
+        JR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_va_tma<BY, FIN, DG, NSTv>, 32 * BY, smem));
+        JR_REQUIRE(nb >= 1, JR_ERR_CUDA, "k_va_tma<%d> does not fit on an SM (%d B shared memory)", BY, smem);
+        cta_per_sm = nb;
+        if (getenv("JRB200_VERBOSE"))
+            fprintf(stderr, "[jrb200] k_va_tma<BY=%d,finite_dt=%d,diag=%d,stages=%d>: %d B smem, %d CTA/SM, nchunk=%d slack=%d\n",
+                    BY, (int)FIN, (int)DG, NSTv, smem, nb, P.nchunk, P.slack);
     }
-    dim3 grid((P.nx + 1 + TXW - 1) / TXW, (P.ny + 1 + TY - 1) / TY, (P.nz + a.kchunk - 1) / a.kchunk), block(32, BY, 1);
-    k_va_tma<BY, FIN, DG, NSTv><<<grid, block, smem, ctx->stream>>>(a);
+    a.ntx = (P.nx + 1 + TXW - 1) / TXW;
+    a.nty = (P.ny + 1 + TY - 1) / TY;
+    a.nchunk = (P.nz + a.kchunk - 1) / a.kchunk;
+    const long items = (long)a.ntx * a.nty * a.nchunk;
+    const long slots = (long)ctx->sm_count * cta_per_sm;
+    const int G = (int)(items < slots ? items : slots);
+    a.progress = P.progress;
+    a.progress_base = P.progress_base;
+    a.slack = P.slack;
+    P.progress_base += (unsigned long long)items * (a.kchunk + 2);  // every item posts kchunk+2 steps
+    void *args[1] = {(void *)&a};
+    // cooperative launch: the soft lock-step spins on other CTAs, so all G CTAs must be resident
+    JR_CUDA(cudaLaunchCooperativeKernel((const void *)k_va_tma<BY, FIN, DG, NSTv>, dim3(G, 1, 1), dim3(32, BY, 1), args, smem,
+                                        ctx->stream));
     return JR_OK;
 }
 
-static int launch_va(jr_context *ctx, const VaPlan &P, const VaArgs &a, int diag)
+static int launch_va(jr_context *ctx, VaPlan &P, VaArgs &a, int diag)
 {
     if (P.finite_dt) return diag ? launch_one<8, true, true, 2>(ctx, P, a) : launch_one<8, true, false, 2>(ctx, P, a);
     switch (P.BY) {
@@ -648,7 +741,7 @@ int jr_stokes3d_VA_fused_iter(jr_context *ctx, const jr_fields *s, const jr_stok
 {
     auto it = g_plans.find(ctx);
     JR_REQUIRE(it != g_plans.end() && it->second.S[0], JR_ERR_ARG, "fused iteration without jr_stokes3d_VA_fused_begin");
-    const VaPlan &P = it->second;
+    VaPlan &P = it->second;
     const int nx = P.nx, ny = P.ny, nz = P.nz;
     double *in = P.S[parity ? 1 : 0], *out = P.S[parity ? 0 : 1];
 
@@ -661,6 +754,7 @@ int jr_stokes3d_VA_fused_iter(jr_context *ctx, const jr_fields *s, const jr_stok
     a.Rx = F(Rx); a.Ry = F(Ry); a.Rz = F(Rz); a.Ux = F(Ux); a.Uy = F(Uy); a.Uz = F(Uz);
     a.nx = nx; a.ny = ny; a.nz = nz; a.PX = P.PX; a.PY = P.PY;
     a.kchunk = (nz + P.nchunk - 1) / P.nchunk;
+    a.pol_ld = P.pol_ld; a.pol_st = P.pol_st;
     a._dx = o->_di[0]; a._dy = o->_di[1]; a._dz = o->_di[2]; a.dt = o->dt; a.r = o->r; a.theta_dtau = o->theta_dtau;
     a.eta_dtau = o->eta_dtau;
     int st = launch_va(ctx, P, a, diag);
