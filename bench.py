@@ -33,6 +33,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 A_EFF_BYTES_PER_CELL = 192  # (2*D_u + D_k)*8 with D_u=10 (V×3,P,τ×6), D_k=4 (η,ρg×3) — SURVEY.md §8d config 4
+A_EFF_CONST_RHOG = 168      # the same with D_k=1: the library does not stream spatially constant ρg (SolVi: ρg ≡ 0)
 
 
 def peaks():
@@ -193,6 +194,20 @@ def run_ours(args):
     t = float(t_dev.item())
     ips = args.steps / t
     cells = n ** 3
+    info = jst.plan_info()
+    a_eff = A_EFF_CONST_RHOG if info["rhog_const"] else A_EFF_BYTES_PER_CELL
+
+    # the same K steps with the body-force arrays streamed (what a setup with spatially varying ρg costs;
+    # A_eff = 192 B/cell, the PTsolvers convention of SURVEY.md §8d)
+    os.environ["JRB200_VA_STREAM_RHOG"] = "1"
+    run(3)
+    barrier()
+    r_s = run(args.steps)
+    del os.environ["JRB200_VA_STREAM_RHOG"]
+    t_s = torch.tensor([r_s.time], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_s, op=dist.ReduceOp.MAX)
+    ips_streamed = args.steps / float(t_s.item())
 
     # optional: the reference's kernel split on the same GPU (unfused CUDA path of this library)
     unfused_ips = None
@@ -239,18 +254,24 @@ def run_ours(args):
         return
 
     peak, peak_kind = peaks()
-    achieved = A_EFF_BYTES_PER_CELL * cells / (t / args.steps) / 1e9
+    achieved = a_eff * cells / (t / args.steps) / 1e9
+    achieved_streamed = A_EFF_BYTES_PER_CELL * cells * ips_streamed / 1e9
     line = {
         "metric": "3D Stokes PT iterations/s (SolVi3D, Float64)", "value": ips * 1.0, "unit": "iters/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * t / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"3D SolVi inclusion Stokes {n}^3 per GPU, variant 3D-VA (K,G arrays), dt=Inf, free slip",
                    "grid_per_gpu": [n, n, n], "l2": f"working set {25 * 8 * cells / 1e9:.2f} GB/iteration >> 126 MB L2 (no flush needed)",
-                   "decomposition": "independent blocks per rank" if world > 1 else "single block"},
-        "T_eff_GBs_per_gpu": achieved, "T_eff_frac_of_8TBs": achieved / 8000.0,
+                   "decomposition": "independent blocks per rank" if world > 1 else "single block",
+                   "plan": info},
+        "T_eff_GBs_per_gpu": achieved, "T_eff_frac_of_8TBs": achieved / 8000.0, "A_eff_bytes_per_cell": a_eff,
+        "streamed_rhog": {"value": ips_streamed, "unit": "iters/s", "A_eff_bytes_per_cell": A_EFF_BYTES_PER_CELL,
+                          "T_eff_GBs_per_gpu": achieved_streamed, "T_eff_frac_of_measured_peak": achieved_streamed / peak,
+                          "T_eff_frac_of_8TBs": achieved_streamed / 8000.0,
+                          "note": "same run with JRB200_VA_STREAM_RHOG=1: the three (zero) body-force arrays are read every iteration"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "peak_kind": peak_kind, "kernel": "k_va_tma (TMA-staged fused 3D-VA iteration)",
-                     "algorithmic_bytes_per_launch": A_EFF_BYTES_PER_CELL * cells},
+                     "algorithmic_bytes_per_launch": a_eff * cells},
         "e2e": {"value": e2e_ips, "unit": "iters/s", "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": d2h / args.steps,
                 "note": f"one solve of {args.steps} PT iterations incl. upload of 12 input arrays and download of V,P,τ"},
         "gpu_launches": int(r.kernel_launches),

@@ -141,6 +141,11 @@ int jr_stokes3d_solve_VA(jr_context *ctx, const jr_fields *s, const jr_stokes_op
 int jr_stokes3d_iterate_VA(jr_context *ctx, const jr_fields *s, const jr_stokes_opts *o, int64_t niter,
                            jr_stokes_result *res);
 
+/* facts about the fused plan the last VA solve on this context used:
+ * info = {tile rows BY, z-chunks, 1 if the body-force arrays were constant and not streamed, finite dt,
+ *         box pitch PX, PY, PZ, lock-step slack}.  No reference counterpart (reporting only). */
+int jr_stokes3d_VA_plan_info(jr_context *ctx, int32_t info[8]);
+
 /* --- stand-alone kernels the reference exposes outside the loops ----------- */
 /* flow_bcs!(stokes, bcs)  src/ext/CUDA/3D.jl:195-218 → BoundaryConditions.jl:65-100 */
 int jr_flow_bcs3d(jr_context *ctx, double *Ax, double *Ay, double *Az, const int32_t n[3],

@@ -119,6 +119,7 @@ def _declare(L):
     L.jr_maxloc3d.argtypes = [vp, vp, vp, i32p, i32p]
     L.jr_stokes3d_solve_VA.argtypes = [vp, vp, C.POINTER(StokesOpts), C.POINTER(StokesResult)]
     L.jr_stokes3d_iterate_VA.argtypes = [vp, vp, C.POINTER(StokesOpts), C.c_int64, C.POINTER(StokesResult)]
+    L.jr_stokes3d_VA_plan_info.argtypes = [vp, i32p]
 
 
 def i32x(vals):

@@ -40,10 +40,12 @@ enum { D_G = 0, D_oyz, D_oxz, /* plane k+2 */ D_K, D_P0, D_Q, D_oxx, D_oyy, D_oz
 // tiles of one ring slot.  The first (τzz) and the last (ρgz) tile are only ever read at a thread's own position:
 // the ±1 / ±32 / −33 neighbour reads of rim lanes then stay inside the slot without any index clamping.
 enum { T_tzz = 0, T_P, T_txx, T_tyy, T_txy, T_Vx, T_Vy, T_Vz, T_tyz, T_txz, T_eta, T_NEXT };
-template <bool FIN> struct SlotMap {
+// RHOG = false: the three body-force arrays are spatially constant (ρg ≡ 0 in SolVi, gravity-free benchmarks) and
+// are not streamed at all — their value travels as a kernel argument.
+template <bool FIN, bool RHOG> struct SlotMap {
     static constexpr int G = T_NEXT, oyz = G + 1, oxz = G + 2, K = G + 3, P0 = G + 4, Q = G + 5, oxx = G + 6, oyy = G + 7, ozz = G + 8,
                          oxy = G + 9;
-    static constexpr int ett = FIN ? G + 10 : T_NEXT, fx = ett + 1, fy = ett + 2, fz = ett + 3, NARR = ett + 4;
+    static constexpr int ett = FIN ? G + 10 : T_NEXT, fx = ett + 1, fy = ett + 2, fz = ett + 3, NARR = ett + (RHOG ? 4 : 1);
 };
 
 struct alignas(64) VaArgs {
@@ -57,6 +59,7 @@ struct alignas(64) VaArgs {
     int slack;                                 // a CTA may run at most DEPTH + slack z-steps ahead of the slowest one
     int pol_ld, pol_st;  // L2 eviction policy of the TMA loads / output stores (0 normal, 1 evict_first, 2 evict_last)
     double _dx, _dy, _dz, dt, r, theta_dtau, eta_dtau;
+    double fxc, fyc, fzc;  // constant body force (RHOG = false)
 };
 
 #define TXW 30  // owned columns per tile
@@ -77,10 +80,10 @@ __device__ __forceinline__ bool jr_elect_one()
 //       progress counter, polled before the barrier so the L2 round trip is hidden): neighbouring tiles then load
 //       their shared halo rows within a few steps of each other and the second reader hits L2 instead of HBM.
 //   all warps: wait on the slot's full mbarrier, update, ONE __syncthreads per step, store.
-template <int BY, bool FINITE_DT, bool DIAG, int NST>
+template <int BY, bool FINITE_DT, bool DIAG, int NST, bool RHOG>
 __global__ void __launch_bounds__(32 * BY, (BY <= 10 ? 2 : 1)) k_va_tma(const __grid_constant__ VaArgs a)
 {
-    using M = SlotMap<FINITE_DT>;
+    using M = SlotMap<FINITE_DT, RHOG>;
     constexpr int TY = BY - 2, TILE = 32 * BY;
     constexpr int NARR = M::NARR, SLOT = NARR * TILE;
     constexpr uint32_t TILE_BYTES = TILE * 8;
@@ -133,7 +136,8 @@ __global__ void __launch_bounds__(32 * BY, (BY <= 10 ? 2 : 1)) k_va_tma(const __
                 jr_tma_load_4d_hint(d + M::oyz * TILE, &a.mD2, p_x0, p_y0, D_oyz, za, bar, pld);
                 jr_tma_load_4d_hint(d + M::K * TILE, &a.mD7, p_x0, p_y0, D_K, zc, bar, pld);
             }
-            jr_tma_load_4d_hint(d + M::ett * TILE, &a.mC4, p_x0, p_y0, C_ett, zc, bar, pld);
+            if (RHOG) jr_tma_load_4d_hint(d + M::ett * TILE, &a.mC4, p_x0, p_y0, C_ett, zc, bar, pld);
+            else jr_tma_load_4d_hint(d + M::ett * TILE, &a.mC1, p_x0, p_y0, C_ett, zc, bar, pld);
         }
     };
     auto p_advance = [&]() {
@@ -310,7 +314,7 @@ __global__ void __launch_bounds__(32 * BY, (BY <= 10 ? 2 : 1)) k_va_tma(const __
 
             if (l > 0) {
                 // ---- R2: momentum residuals and velocity update of plane k, partial Rz of face k+1 ----
-                const double c_fz = p[M::fz * TILE], c_ett = p[M::ett * TILE];
+                const double c_fz = RHOG ? p[M::fz * TILE] : a.fzc, c_ett = p[M::ett * TILE];
                 const double sRz_next = _dx * (p[T_txz * TILE + 1] - txz_n) + _dy * (p[T_tyz * TILE + 32] - tyz_n);
                 const bool kin = k >= kb && k < ke;  // this chunk owns plane k (k = kb−1 is the warm-up plane)
                 if (kin) {
@@ -330,7 +334,7 @@ __global__ void __launch_bounds__(32 * BY, (BY <= 10 ? 2 : 1)) k_va_tma(const __
                     if (stVx) {
                         const double R = (-p[T_txx * TILE - 1] + txx_n) * _dx + _dy * (p[T_txy * TILE + 32] - txy_n) +
                                          _dz * (txz_n - txz_b) - (-p[T_P * TILE - 1] + P_n) * _dx -
-                                         0.5 * (p[M::fx * TILE - 1] + p[M::fx * TILE]);
+                                         0.5 * (RHOG ? (p[M::fx * TILE - 1] + p[M::fx * TILE]) : (a.fxc + a.fxc));
                         const double vn = vx0 + jr_div_nr(R * a.eta_dtau, 0.5 * (p[M::ett * TILE - 1] + c_ett));
                         jr_st_hint(&po[S_Vx * pxy], vn, pst);
                         if (DIAG) {
@@ -342,7 +346,7 @@ __global__ void __launch_bounds__(32 * BY, (BY <= 10 ? 2 : 1)) k_va_tma(const __
                     if (stVy) {
                         const double R = _dx * (p[T_txy * TILE + 1] - txy_n) + _dy * (tyy_n - p[T_tyy * TILE - 32]) +
                                          _dz * (tyz_n - tyz_b) - (-p[T_P * TILE - 32] + P_n) * _dy -
-                                         0.5 * (p[M::fy * TILE - 32] + p[M::fy * TILE]);
+                                         0.5 * (RHOG ? (p[M::fy * TILE - 32] + p[M::fy * TILE]) : (a.fyc + a.fyc));
                         const double vn = vy0 + jr_div_nr(R * a.eta_dtau, 0.5 * (p[M::ett * TILE - 32] + c_ett));
                         jr_st_hint(&po[S_Vy * pxy], vn, pst);
                         if (DIAG) {
@@ -493,6 +497,45 @@ __global__ void k_bc_box3(const __grid_constant__ BcArgsB b)
 }
 
 // ------------------------------------------------------------------------------------------------------
+// min / max of up to three equally sized arrays (constant-field detection at solve entry)
+#define MINMAX_BLOCKS 512
+__global__ void k_minmax3(const double *a0, const double *a1, const double *a2, size_t n, double *part)
+{
+    __shared__ double sm[6][8];
+    const double *A[3] = {a0, a1, a2};
+    double mn[3], mx[3];
+#pragma unroll
+    for (int q = 0; q < 3; q++) {
+        mn[q] = INFINITY; mx[q] = -INFINITY;
+        for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+            const double v = A[q][i];
+            mn[q] = fmin(mn[q], v); mx[q] = fmax(mx[q], v);
+            if (v != v) { mn[q] = v; mx[q] = -v; }  // NaN poisons the range (never "constant")
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[q] = fmin(mn[q], __shfl_down_sync(0xffffffffu, mn[q], o));
+            mx[q] = fmax(mx[q], __shfl_down_sync(0xffffffffu, mx[q], o));
+        }
+        if ((threadIdx.x & 31) == 0) { sm[2 * q][threadIdx.x >> 5] = mn[q]; sm[2 * q + 1][threadIdx.x >> 5] = mx[q]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        double v = sm[threadIdx.x][0];
+        for (int w = 1; w < (int)(blockDim.x >> 5); w++) v = (threadIdx.x & 1) ? fmax(v, sm[threadIdx.x][w]) : fmin(v, sm[threadIdx.x][w]);
+        part[blockIdx.x * 6 + threadIdx.x] = v;
+    }
+}
+__global__ void k_minmax3_final(const double *part, int nparts, double *out)
+{
+    if (threadIdx.x < 6) {
+        double v = part[threadIdx.x];
+        for (int b = 1; b < nparts; b++) v = (threadIdx.x & 1) ? fmax(v, part[b * 6 + threadIdx.x]) : fmin(v, part[b * 6 + threadIdx.x]);
+        out[threadIdx.x] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
 // host side
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                     const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -538,8 +581,10 @@ struct VaPlan {
     double *S[2] = {nullptr, nullptr}, *C = nullptr, *D = nullptr;
     CUtensorMap mS5[2], mC1, mC4, mD1, mD2, mD7;
     int BY = 0, nchunk = 1;
-    int pol_ld = 2, pol_st = 1, l2promo = 2, slack = 1;
+    int pol_ld = 2, pol_st = 1, l2promo = 3, slack = 1;
     unsigned long long *progress = nullptr, progress_base = 0;
+    bool rhog_const = false;  // ρg arrays are spatially constant: not streamed
+    double fc[3] = {0, 0, 0};
 };
 static std::map<jr_context *, VaPlan> g_plans;
 
@@ -638,6 +683,20 @@ int jr_stokes3d_VA_fused_begin(jr_context *ctx, const jr_fields *s, const jr_sto
     P.progress = (unsigned long long *)p;
     P.progress_base = 0;
     JR_CUDA(cudaMemsetAsync(p, 0, 64, ctx->stream));
+    // constant body force?  (one pass over ρg per solve; ρg ≡ 0 in SolVi / Taylor-Green / Burstedde-type benchmarks)
+    {
+        void *part = nullptr, *mm = nullptr;
+        if ((st = jr_ctx_scratch(ctx, "minmax_part", (MINMAX_BLOCKS * 6 + 8) * sizeof(double), &part))) return st;
+        mm = (double *)part + MINMAX_BLOCKS * 6;
+        k_minmax3<<<MINMAX_BLOCKS, 256, 0, ctx->stream>>>(F(rhogx), F(rhogy), F(rhogz), (size_t)nx * ny * nz, (double *)part);
+        k_minmax3_final<<<1, 32, 0, ctx->stream>>>((const double *)part, MINMAX_BLOCKS, (double *)mm);
+        ctx->launches += 2;
+        JR_CUDA(cudaMemcpyAsync(ctx->h_pinned, mm, 6 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        JR_CUDA(cudaStreamSynchronize(ctx->stream));
+        const double *h = ctx->h_pinned;
+        P.rhog_const = h[0] == h[1] && h[2] == h[3] && h[4] == h[5] && !getenv("JRB200_VA_STREAM_RHOG");
+        P.fc[0] = h[0]; P.fc[1] = h[2]; P.fc[2] = h[4];
+    }
     if (const char *e = getenv("JRB200_VA_SLACK")) P.slack = atoi(e);
     if (const char *e = getenv("JRB200_VA_POL_LD")) P.pol_ld = atoi(e);
     if (const char *e = getenv("JRB200_VA_POL_ST")) P.pol_st = atoi(e);
@@ -691,18 +750,18 @@ int jr_stokes3d_VA_fused_begin(jr_context *ctx, const jr_fields *s, const jr_sto
     return JR_OK;
 }
 
-template <int BY, bool FIN, bool DG, int NSTv>
+template <int BY, bool FIN, bool DG, int NSTv, bool RHOG>
 static int launch_one(jr_context *ctx, VaPlan &P, VaArgs &a)
 {
     constexpr int TY = BY - 2;
-    constexpr int smem = NSTv * SlotMap<FIN>::NARR * 32 * BY * 8;
+    constexpr int smem = NSTv * SlotMap<FIN, RHOG>::NARR * 32 * BY * 8;
     static int cta_per_sm = 0;
     if (!cta_per_sm) {
-        JR_CUDA(cudaFuncSetAttribute(k_va_tma<BY, FIN, DG, NSTv>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        JR_CUDA(cudaFuncSetAttribute(k_va_tma<BY, FIN, DG, NSTv>, cudaFuncAttributePreferredSharedMemoryCarveout,
+        JR_CUDA(cudaFuncSetAttribute(k_va_tma<BY, FIN, DG, NSTv, RHOG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        JR_CUDA(cudaFuncSetAttribute(k_va_tma<BY, FIN, DG, NSTv, RHOG>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                      cudaSharedmemCarveoutMaxShared));
         int nb = 0;
-        JR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_va_tma<BY, FIN, DG, NSTv>, 32 * BY, smem));
+        JR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_va_tma<BY, FIN, DG, NSTv, RHOG>, 32 * BY, smem));
         JR_REQUIRE(nb >= 1, JR_ERR_CUDA, "k_va_tma<%d> does not fit on an SM (%d B shared memory)", BY, smem);
         cta_per_sm = nb;
         if (getenv("JRB200_VERBOSE"))
@@ -721,19 +780,25 @@ static int launch_one(jr_context *ctx, VaPlan &P, VaArgs &a)
     P.progress_base += (unsigned long long)items * (a.kchunk + 2);  // every item posts kchunk+2 steps
     void *args[1] = {(void *)&a};
     // cooperative launch: the soft lock-step spins on other CTAs, so all G CTAs must be resident
-    JR_CUDA(cudaLaunchCooperativeKernel((const void *)k_va_tma<BY, FIN, DG, NSTv>, dim3(G, 1, 1), dim3(32, BY, 1), args, smem,
+    JR_CUDA(cudaLaunchCooperativeKernel((const void *)k_va_tma<BY, FIN, DG, NSTv, RHOG>, dim3(G, 1, 1), dim3(32, BY, 1), args, smem,
                                         ctx->stream));
     return JR_OK;
 }
 
+template <bool RHOG>
+static int launch_va_t(jr_context *ctx, VaPlan &P, VaArgs &a, int diag)
+{
+    if (P.finite_dt)
+        return diag ? launch_one<8, true, true, 2, RHOG>(ctx, P, a) : launch_one<8, true, false, 2, RHOG>(ctx, P, a);
+    switch (P.BY) {
+    case 8: return diag ? launch_one<8, false, true, 3, RHOG>(ctx, P, a) : launch_one<8, false, false, 3, RHOG>(ctx, P, a);
+    case 10: return diag ? launch_one<10, false, true, 3, RHOG>(ctx, P, a) : launch_one<10, false, false, 3, RHOG>(ctx, P, a);
+    default: return diag ? launch_one<16, false, true, 3, RHOG>(ctx, P, a) : launch_one<16, false, false, 3, RHOG>(ctx, P, a);
+    }
+}
 static int launch_va(jr_context *ctx, VaPlan &P, VaArgs &a, int diag)
 {
-    if (P.finite_dt) return diag ? launch_one<8, true, true, 2>(ctx, P, a) : launch_one<8, true, false, 2>(ctx, P, a);
-    switch (P.BY) {
-    case 8: return diag ? launch_one<8, false, true, 3>(ctx, P, a) : launch_one<8, false, false, 3>(ctx, P, a);
-    case 10: return diag ? launch_one<10, false, true, 3>(ctx, P, a) : launch_one<10, false, false, 3>(ctx, P, a);
-    default: return diag ? launch_one<16, false, true, 3>(ctx, P, a) : launch_one<16, false, false, 3>(ctx, P, a);
-    }
+    return P.rhog_const ? launch_va_t<false>(ctx, P, a, diag) : launch_va_t<true>(ctx, P, a, diag);
 }
 
 // `parity` 0: set S0 → S1, 1: S1 → S0.
@@ -755,6 +820,7 @@ int jr_stokes3d_VA_fused_iter(jr_context *ctx, const jr_fields *s, const jr_stok
     a.nx = nx; a.ny = ny; a.nz = nz; a.PX = P.PX; a.PY = P.PY;
     a.kchunk = (nz + P.nchunk - 1) / P.nchunk;
     a.pol_ld = P.pol_ld; a.pol_st = P.pol_st;
+    a.fxc = P.fc[0]; a.fyc = P.fc[1]; a.fzc = P.fc[2];
     a._dx = o->_di[0]; a._dy = o->_di[1]; a._dz = o->_di[2]; a.dt = o->dt; a.r = o->r; a.theta_dtau = o->theta_dtau;
     a.eta_dtau = o->eta_dtau;
     int st = launch_va(ctx, P, a, diag);
@@ -805,4 +871,16 @@ int jr_stokes3d_VA_fused_finish(jr_context *ctx, const jr_fields *s, int64_t nit
     add(F(txz), S_txz, nx + 1, ny, nz + 1, 1, 1, 1);
     add(F(txy), S_txy, nx + 1, ny + 1, nz, 1, 1, 1);
     return run_pack(ctx, pa, (ny + 2) * (nz + 2));
+}
+
+// tiling / layout facts of the last fused plan of this context (benchmarks and tests report them)
+extern "C" int jr_stokes3d_VA_plan_info(jr_context *ctx, int32_t info[8])
+{
+    JR_REQUIRE(ctx && info, JR_ERR_ARG, "null argument");
+    auto it = g_plans.find(ctx);
+    JR_REQUIRE(it != g_plans.end(), JR_ERR_ARG, "no fused plan on this context yet");
+    const VaPlan &P = it->second;
+    info[0] = P.BY; info[1] = P.nchunk; info[2] = P.rhog_const ? 1 : 0; info[3] = P.finite_dt ? 1 : 0;
+    info[4] = P.PX; info[5] = P.PY; info[6] = P.PZ; info[7] = P.slack;
+    return JR_OK;
 }

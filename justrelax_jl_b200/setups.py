@@ -73,7 +73,7 @@ def solvi3d(nx=31, ny=31, nz=31, *, Δη=1.0e-3, lx=1.0e1, ly=1.0e1, lz=1.0e1, r
                            fields=fields, kwargs=dict(iterMax=5000, nout=100, verbose=False))
 
 
-def random_stokes3d(ni, seed=20261017, *, dt=0.7, finite_K=True):
+def random_stokes3d(ni, seed=20261017, *, dt=0.7, finite_K=True, const_rhog=None):
     """Seeded random state for kernel-level parity fuzzing of variant 3D-VA:
     V, τ ~ U(−1,1), P ~ U(0,1), η ~ 10^U(−3,0), G ~ U(0.5,2), K ~ U(1,4) (or Inf), ρg ~ U(−1,1)."""
     rng = np.random.default_rng(seed)
@@ -91,6 +91,9 @@ def random_stokes3d(ni, seed=20261017, *, dt=0.7, finite_K=True):
         K=np.asfortranarray(rng.uniform(1.0, 4.0, size=ni)) if finite_K else np.full(ni, np.inf, order="F"),
         rhogx=U(*ni), rhogy=U(*ni), rhogz=U(*ni),
     )
+    if const_rhog is not None:  # spatially constant body force (exercises the constant-field elision of the fused kernel)
+        for k, v in zip(("rhogx", "rhogy", "rhogz"), const_rhog):
+            f[k] = np.full(ni, float(v), order="F")
     li = (1.0, 1.3, 0.9)
     grid = Geometry(ni, li)
     pt = PTStokesCoeffs(li, grid.di.center)

@@ -181,6 +181,14 @@ def iterate_(stokes: StokesArrays, pt_stokes, grid, flow_bcs, ρg, K, G, dt, nit
     return SimpleNamespace(iter=int(res.iter), time=float(res.time_s), kernel_launches=int(res.kernel_launches))
 
 
+def plan_info():
+    """Facts about the fused plan of the last 3D-VA solve on this device (tile rows, z-chunks, constant-ρg elision …)."""
+    info = (C.c_int32 * 8)()
+    _abi.check(_abi.lib().jr_stokes3d_VA_plan_info(context(), info))
+    keys = ("BY", "nchunk", "rhog_const", "finite_dt", "PX", "PY", "PZ", "slack")
+    return dict(zip(keys, [int(v) for v in info]))
+
+
 def flow_bcs_(stokes, bcs: AbstractFlowBoundaryConditions):
     """flow_bcs!(stokes, bcs) — src/ext/CUDA/3D.jl:195-218 → BoundaryConditions.jl:65-100."""
     if isinstance(backend(stokes), CPUBackendTrait):

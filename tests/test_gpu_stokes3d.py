@@ -68,6 +68,18 @@ def test_fused_tilings(oracle, monkeypatch, BY, nchunk, dt, finite_K):
         compare_slots(st.slots(), d, FIELDS_STATE + FIELDS_DIAG, TOL, f"BY={BY} nchunk={nchunk} niter={niter}")
 
 
+@pytest.mark.parametrize("dt,finite_K", [(0.7, True), (np.inf, False)])
+def test_fused_constant_body_force(oracle, dt, finite_K):
+    """spatially constant ρg is not streamed by the fused kernel (kernel argument instead): same result"""
+    from justrelax_jl_b200 import setups, stokes as jst
+
+    s = setups.random_stokes3d((37, 20, 23), seed=11, dt=dt, finite_K=finite_K, const_rhog=(0.3, -0.2, 0.55))
+    flags = dict(free_slip=[1] * 6, no_slip=[0] * 6, periodic=[0] * 6)
+    st, d = _run_both(oracle, s, 3, flags, False)
+    assert jst.plan_info()["rhog_const"] == 1
+    compare_slots(st.slots(), d, FIELDS_STATE + FIELDS_DIAG, TOL, "constant rhog")
+
+
 @pytest.mark.parametrize("unfused", [True, False], ids=["unfused", "fused"])
 def test_mixed_boundary_flags(oracle, unfused):
     from justrelax_jl_b200 import setups
