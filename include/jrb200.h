@@ -157,6 +157,30 @@ int jr_scale_copy(jr_context *ctx, double *dst, const double *src, double factor
 /* Σ A[2:end-1,…]^2 (interior != 0) or Σ A^2 — the local part of norm_mpi, src/Utils.jl:698-701 */
 int jr_sumsq(jr_context *ctx, const double *A, const int32_t n[3], int interior, double *out_host);
 
+/* --- multi-GPU: ImplicitGlobalGrid-compatible decomposition over CUDA-IPC peer memory (NVLink) -----------------
+ * Replaces IGG's update_halo! (call sites src/stokes/Stokes3D.jl:57,120,515,578-580,596; Stokes2D.jl:655,757,784;
+ * src/thermal_diffusion/DiffusionPT_solver.jl:110,261) and the MPI.Allreduce of norm_mpi/maximum_mpi
+ * (src/Utils.jl:688-730).  One process per GPU; `dims`/`coords` are IGG's Cartesian topology (src/grid/Grid.jl:18-24).
+ * Bootstrap needs ONE host collective, supplied by the caller: an all-gather of `bytes_per_rank` bytes per rank
+ * (MPI.Allgather on igg.comm_cart in Julia; torch.distributed in the Python twin).  Return 0 on success. */
+typedef int (*jr_allgather_fn)(const void *sendbuf, void *recvbuf, size_t bytes_per_rank, void *user);
+typedef struct jr_comm jr_comm;
+int jr_comm_create(jr_context *ctx, int rank, int nranks, const int32_t dims[3], const int32_t coords[3],
+                   jr_allgather_fn allgather, void *user, jr_comm **out);
+int jr_comm_destroy(jr_comm *comm);
+/* solves / halo updates / reductions on `ctx` go through `comm` from now on (NULL detaches) */
+int jr_context_set_comm(jr_context *ctx, jr_comm *comm);
+int jr_comm_barrier(jr_context *ctx);
+/* update_halo!(A1, A2, ...): dense arrays, extents[3*q..3*q+2] = size(Aq), ncell = local (nx,ny,nz); blocking */
+int jr_update_halo3d(jr_context *ctx, int narrays, double *const *arrays, const int32_t *extents, const int32_t ncell[3]);
+/* MPI.Allreduce of n <= 16 host doubles, op 0 = sum, 1 = max, 2 = min; rank-order deterministic; blocking */
+int jr_allreduce_f64(jr_context *ctx, double *vals_host, int n, int op);
+/* host-only index arithmetic of the exchange (no GPU needed): after update_halo!, element idx (0-based) of an array
+ * of extents `ext` on rank `coords` holds the pre-exchange value of element src_idx on rank src_coords.
+ * Returns 1 if the element is overwritten by the exchange, 0 if not, < 0 on error. */
+int jr_halo_source(const int32_t dims[3], const int32_t coords[3], const int32_t ext[3], const int32_t ncell[3],
+                   const int32_t idx[3], int32_t src_coords[3], int32_t src_idx[3]);
+
 #ifdef __cplusplus
 }
 #endif

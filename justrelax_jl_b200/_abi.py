@@ -101,6 +101,9 @@ class OracleStokesResult(C.Structure):
     _fields_ = StokesResult._fields_[:9]
 
 
+ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)
+
+
 def _declare(L):
     vp, i32p = C.c_void_p, C.POINTER(C.c_int32)
     L.jr_context_create.argtypes = [C.c_int, vp, C.POINTER(vp)]
@@ -120,6 +123,13 @@ def _declare(L):
     L.jr_stokes3d_solve_VA.argtypes = [vp, vp, C.POINTER(StokesOpts), C.POINTER(StokesResult)]
     L.jr_stokes3d_iterate_VA.argtypes = [vp, vp, C.POINTER(StokesOpts), C.c_int64, C.POINTER(StokesResult)]
     L.jr_stokes3d_VA_plan_info.argtypes = [vp, i32p]
+    L.jr_comm_create.argtypes = [vp, C.c_int, C.c_int, i32p, i32p, ALLGATHER_FN, vp, C.POINTER(vp)]
+    L.jr_comm_destroy.argtypes = [vp]
+    L.jr_context_set_comm.argtypes = [vp, vp]
+    L.jr_comm_barrier.argtypes = [vp]
+    L.jr_update_halo3d.argtypes = [vp, C.c_int, C.POINTER(vp), i32p, i32p]
+    L.jr_allreduce_f64.argtypes = [vp, C.POINTER(C.c_double), C.c_int, C.c_int]
+    L.jr_halo_source.argtypes = [i32p, i32p, i32p, i32p, i32p, i32p, i32p]
 
 
 def i32x(vals):

@@ -1,0 +1,56 @@
+// comm.cuh — internal types of the multi-GPU layer (comm.cu).  Not part of the C ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <map>
+#include <string>
+#include <vector>
+#include "../../include/jrb200.h"
+
+#define JR_COMM_MAX_RANKS 32
+#define JR_COMM_RED_SLOTS 16
+#define JR_HALO_MAX_ARRAYS 8
+
+// one per rank, in device memory, CUDA-IPC mapped by every other rank
+struct jr_comm_sig {
+    unsigned long long flags[JR_COMM_MAX_RANKS];                // flags[r] = last epoch rank r has reached (written by r)
+    double red[2][JR_COMM_MAX_RANKS][JR_COMM_RED_SLOTS];        // all-reduce slots, double-buffered
+};
+
+// what kernels need (passed by value as a __grid_constant__ parameter)
+struct jr_comm_dev {
+    int rank, nranks;
+    int nbr[27];                                  // rank at coordinate offset (dx,dy,dz): [(dz+1)*9 + (dy+1)*3 + dx+1], −1 = none
+    jr_comm_sig *sig[JR_COMM_MAX_RANKS];          // sig[r]: rank r's signal page (peer mapping; sig[rank] = own)
+    double *stage[JR_COMM_MAX_RANKS][2];          // stage[r][b]: rank r's halo staging buffer b
+};
+
+struct jr_comm {
+    int rank = 0, nranks = 1;
+    int dims[3] = {1, 1, 1}, coords[3] = {0, 0, 0};
+    jr_allgather_fn allgather = nullptr;
+    void *user = nullptr;
+    jr_comm_dev dev;
+    jr_comm_sig *sig_mine = nullptr;
+    void *stage_mine[2] = {nullptr, nullptr};
+    size_t stage_cap = 0;                         // doubles per staging buffer
+    unsigned long long epoch = 0, red_count = 0;
+    size_t halo_bytes = 0;
+    std::map<std::string, void *> ipc_open;       // opened peer handles (handle bytes + rank → mapped pointer)
+    std::vector<void *> retired;                  // outgrown staging buffers (freed at destroy)
+};
+
+// an array taking part in a halo update: dense user array or one array of a box set
+struct jr_harr {
+    double *p;
+    long sy, sz;   // strides (elements) of the 2nd and 3rd index
+    int n[3];      // extents of the array itself
+    int o[3];      // offset of element (0,0,0) inside the addressed space (box layout), 0 for dense arrays
+    int ol[3];     // IGG overlap of this array per dimension: 2 + (n[d] − ncell[d]); < 2 = not exchanged
+};
+
+jr_harr jr_harr_dense(double *p, const int32_t ext[3], const int32_t ncell[3]);
+// update_halo!(arrs...) on ctx's communicator (no-op without one / on a single rank); asynchronous on ctx->stream
+int jr_comm_halo(jr_context *ctx, const jr_harr *arrs, int narr);
+size_t jr_comm_halo_bytes(const jr_comm *cm, const jr_harr *arrs, int narr);
+// in-place all-reduce of n ≤ 16 device doubles (op 0 sum, 1 max, 2 min); asynchronous on ctx->stream
+int jr_comm_allreduce_dev(jr_context *ctx, double *d_vals, int n, int op);

@@ -50,6 +50,7 @@ struct jr_context {
     size_t h_pinned_count = 0;
     int64_t launches = 0;        // kernels launched since last reset
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    struct jr_comm *comm = nullptr;  // multi-GPU communicator (comm.cu); nullptr = single rank
 };
 
 int jr_ctx_scratch(jr_context *ctx, const char *key, size_t bytes, void **out);

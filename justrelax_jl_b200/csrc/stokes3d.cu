@@ -5,6 +5,7 @@
 // vectors; the per-iteration body is one fused sm_100a kernel (stokes3d_fused.cu) or, with
 // JR_FLAG_UNFUSED, the reference-structured kernel sequence (stokes3d_unfused.cu).
 #include "common.cuh"
+#include "comm.cuh"
 
 #define F(name) (s->f[JR_F_##name])
 
@@ -28,7 +29,10 @@ static int check_fields_VA(const jr_fields *s, const jr_stokes_opts *o)
 static int pre_VA(jr_context *ctx, const jr_fields *s)
 {
     const int32_t w[3] = {1, 1, 1};
-    return jr_launch_maxloc3d(ctx, F(etatau), F(eta), s->n, w);
+    int st = jr_launch_maxloc3d(ctx, F(etatau), F(eta), s->n, w);
+    if (st) return st;
+    const jr_harr H = jr_harr_dense(F(etatau), s->n, s->n);
+    return jr_comm_halo(ctx, &H, 1);
 }
 
 static int one_iter_VA(jr_context *ctx, const jr_fields *s, const jr_stokes_opts *o, bool fused, int write_diag, int64_t it)
@@ -126,6 +130,8 @@ int jr_stokes3d_solve_VA(jr_context *ctx, const jr_fields *s, const jr_stokes_op
             if ((st = jr_launch_sumsq(ctx, F(Ry), nRy, 1, slots + 1))) return st;
             if ((st = jr_launch_sumsq(ctx, F(Rz), nRz, 1, slots + 2))) return st;
             if ((st = jr_launch_sumsq(ctx, F(RP), nP, 0, slots + 3))) return st;
+            // norm_mpi: MPI.Allreduce(sum) of the local sums of squares (overlap cells counted twice, as in the reference)
+            if ((st = jr_comm_allreduce_dev(ctx, slots, 4, 0))) return st;
             JR_CUDA(cudaMemcpyAsync(ctx->h_pinned, slots, 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
             JR_CUDA(cudaStreamSynchronize(ctx->stream));
             // normalisers: Stokes3D.jl:129-142 (‖R‖₂ / N, quirk Q4)

@@ -32,6 +32,7 @@
 // (same fma placement, same summation order) ⇒ bit-comparable with the CPU oracle.
 #include "common.cuh"
 #include "tma.cuh"
+#include "comm.cuh"
 
 // set orders: arrays that are loaded at the same box plane are adjacent, so ONE TMA box (32 × BY × n × 1) brings n tiles
 enum { S_tzz = 0, S_P, S_txx, S_tyy, S_txy, /* plane k+1 */ S_Vx, S_Vy, S_Vz, S_tyz, S_txz, /* plane k+2 */ S_N };
@@ -842,6 +843,17 @@ int jr_stokes3d_VA_fused_iter(jr_context *ctx, const jr_fields *s, const jr_stok
     k_bc_box3<<<bgrid, bblock, 0, ctx->stream>>>(b);
     ctx->launches += 2;
     JR_CHECK_LAUNCH();
+    // update_halo!(Vx, Vy, Vz)  Stokes3D.jl:120 — straight on the box set the next iteration reads
+    if (ctx->comm) {
+        jr_harr H[3];
+        for (int q = 0; q < 3; q++) {
+            const BcArrB &A = b.A[q];
+            H[q].p = A.out.p; H[q].sy = A.out.sy; H[q].sz = A.out.sz;
+            for (int d = 0; d < 3; d++) { H[q].n[d] = A.n[d]; H[q].o[d] = A.o[d]; }
+            H[q].ol[0] = 2 + A.n[0] - nx; H[q].ol[1] = 2 + A.n[1] - ny; H[q].ol[2] = 2 + A.n[2] - nz;
+        }
+        return jr_comm_halo(ctx, H, 3);
+    }
     return JR_OK;
 }
 

@@ -5,6 +5,7 @@
 //
 // Reference: src/stokes/Stokes3D.jl:78-121; kernels cited per function.  Indices are 1-based (IX3).
 #include "common.cuh"
+#include "comm.cuh"
 
 #define F(name) (s.f[JR_F_##name])
 
@@ -173,5 +174,10 @@ int jr_stokes3d_VA_unfused_iter(jr_context *ctx, const jr_fields *sp, const jr_s
     k_v2u3<<<ctx->sm_count * 8, 256, 0, st>>>(s, o->dt, nVx, nVy, nVz);
     ctx->launches += 6;
     JR_CHECK_LAUNCH();
-    return jr_launch_flow_bcs3d(ctx, F(Vx), F(Vy), F(Vz), s.n, o->free_slip, o->no_slip, o->periodic);
+    int rc = jr_launch_flow_bcs3d(ctx, F(Vx), F(Vy), F(Vz), s.n, o->free_slip, o->no_slip, o->periodic);
+    if (rc) return rc;
+    // update_halo!(Vx, Vy, Vz)  Stokes3D.jl:120
+    const int32_t eVx[3] = {nx + 1, ny + 2, nz + 2}, eVy[3] = {nx + 2, ny + 1, nz + 2}, eVz[3] = {nx + 2, ny + 2, nz + 1};
+    const jr_harr H[3] = {jr_harr_dense(F(Vx), eVx, s.n), jr_harr_dense(F(Vy), eVy, s.n), jr_harr_dense(F(Vz), eVz, s.n)};
+    return jr_comm_halo(ctx, H, 3);
 }

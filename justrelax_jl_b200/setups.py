@@ -27,13 +27,16 @@ def _smooth3(A: np.ndarray, fact: float) -> np.ndarray:
 
 
 def solvi3d(nx=31, ny=31, nz=31, *, Δη=1.0e-3, lx=1.0e1, ly=1.0e1, lz=1.0e1, rc=1.0e0, εbg=1.0e0, igg: IGG | None = None,
-            smooth_passes: int = 10):
+            smooth_passes: int = 10, update_halo=None, divfree: bool = False, global_coords: bool = False):
     """3D SolVi inclusion benchmark (config 4): miniapps/benchmarks/stokes3D/solvi/SolVi3D.jl:45-130.
 
     Returns host fields (numpy, column-major) and parameters for variant 3D-VA:
     η with a low-viscosity sphere smoothed 10×, G = 1, Kb = Inf, dt = Inf, pure-shear velocity
     (pureshear_bc!, src/boundaryconditions/pure_shear.jl:15-32 incl. quirk Q18), free slip on all six faces,
     ρg = 0, PTStokesCoeffs(li, di; CFL = 1/√3), kwargs = (iterMax = 5000, nout = 100).
+
+    Multi-rank (igg.nprocs > 1): like the miniapp, di = li / (nx_g, ny_g, nz_g), the inclusion test uses LOCAL indices
+    (SolVi3D.jl:14-25), and `update_halo(η)` (in place, host array) is called after every smoothing pass (:38-42).
     """
     igg = igg or IGG()
     ni = (nx, ny, nz)
@@ -48,10 +51,17 @@ def solvi3d(nx=31, ny=31, nz=31, *, Δη=1.0e-3, lx=1.0e1, ly=1.0e1, lz=1.0e1, r
     iy = np.arange(ny, dtype=np.float64)[None, :, None]
     iz = np.arange(nz, dtype=np.float64)[None, None, :]
     rad = np.sqrt((ix * dx + 0.5 * dx - 0.5 * lx) ** 2 + (iy * dy + 0.5 * dy - 0.5 * ly) ** 2 + (iz * dz + 0.5 * dz - 0.5 * lz) ** 2)
+    if global_coords:
+        # NOT the miniapp: inclusion placed by GLOBAL cell-centre coordinates, so that the decomposed viscosity field is
+        # one consistent global field (tests that compare a decomposed solve with the single-block solve)
+        xc, yc, zc = grid.xci
+        rad = np.sqrt((xc[:, None, None] - 0.5 * lx) ** 2 + (yc[None, :, None] - 0.5 * ly) ** 2 + (zc[None, None, :] - 0.5 * lz) ** 2)
     η = np.full(ni, 1.0, order="F")
     η[rad <= rc] = Δη
     for _ in range(smooth_passes):
-        η = _smooth3(η, 1.0)
+        η = np.asfortranarray(_smooth3(η, 1.0))
+        if update_halo is not None:
+            update_halo(η)
     η = np.asfortranarray(η)
 
     xv, yv, zv = grid.xvi
@@ -62,6 +72,11 @@ def solvi3d(nx=31, ny=31, nz=31, *, Δη=1.0e-3, lx=1.0e1, ly=1.0e1, lz=1.0e1, r
     # Q18: the reference uses the x-vertex coordinates for Vy (only well-formed when nx == ny)
     Vy[1:-1, :, 1:-1] = (εbg * (xv if nx == ny else yv))[None, :, None]
     Vz[1:-1, 1:-1, :] = (-εbg * zv)[None, None, :]
+    if divfree:
+        # NOT the reference's pureshear_bc!: a divergence-free variant (Vy from the y vertices, Vz = −2 εbg z) for which
+        # the continuity residual can converge, used by tests that need the loop to END on its tolerance
+        Vy[1:-1, :, 1:-1] = (εbg * yv)[None, :, None]
+        Vz[1:-1, 1:-1, :] = (-2.0 * εbg * zv)[None, None, :]
 
     flow_bcs = VelocityBoundaryConditions(
         free_slip=dict(left=True, right=True, top=True, bot=True, back=True, front=True),

@@ -227,9 +227,13 @@ def displacement2velocity_(stokes, dt):
     _abi.check(_abi.lib().jr_context_synchronize(context()))
 
 
-def norm_interior(A, interior: bool = True) -> float:
-    """sqrt(Σ A[2:end-1,…]^2): local part of norm_mpi (src/Utils.jl:698-701)."""
+def sumsq_interior(A, interior: bool = True) -> float:
+    """Σ A[2:end-1,…]^2 (interior) or Σ A^2: the local part of norm_mpi (src/Utils.jl:698-701)."""
     out = C.c_double()
     shp = list(A.shape) + [1] * (3 - A.dim())
     _abi.check(_abi.lib().jr_sumsq(context(), data_ptr(A), _abi.i32x(shp), int(interior), C.byref(out)))
-    return math.sqrt(out.value)
+    return out.value
+
+
+def norm_interior(A, interior: bool = True) -> float:
+    return math.sqrt(sumsq_interior(A, interior))

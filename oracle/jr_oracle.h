@@ -111,6 +111,9 @@ void orc_multi_copy_tau3(const orc_fields *s);
 int  orc_solve3d_VA(const orc_fields *s, const orc_stokes_opts *o, orc_stokes_result *res);
 /* run exactly `niter` PT iterations (no convergence test) – used for fixed-iteration parity */
 int  orc_iterate3d_VA(const orc_fields *s, const orc_stokes_opts *o, int64_t niter);
+/* loop pieces for multi-rank emulation: pre-loop maxloc, one PT iteration (no halo: the caller exchanges) */
+void orc_pre3d_VA(const orc_fields *s);
+void orc_iterate3d_VA_once(const orc_fields *s, const orc_stokes_opts *o);
 
 /* norms (src/Utils.jl:698-701), interior slice 2:end-1 in every dim when interior!=0 */
 double orc_sumsq_interior(const double *A, int n1, int n2, int n3, int interior);

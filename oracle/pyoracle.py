@@ -199,3 +199,9 @@ def solve3d_VA(slots, ni, opts):
 def iterate3d_VA(slots, ni, opts, niter):
     fs = make_fields(slots, ni)
     return lib().orc_iterate3d_VA(C.byref(fs), C.byref(opts), C.c_int64(niter))
+
+
+def sumsq(A, interior):
+    A = np.asfortranarray(A)
+    shp = list(A.shape) + [1] * (3 - A.ndim)
+    return lib().orc_sumsq_interior(_dp(A), *map(C.c_int, shp), C.c_int(int(interior)))

@@ -439,6 +439,10 @@ static void pre_VA(const orc_fields *s)
     orc_maxloc3(F(etatau), F(eta), s->n[0], s->n[1], s->n[2], 1, 1, 1);
 }
 
+/* pieces of the loop for the multi-rank emulation of the tests (tests/mrank.py does update_halo! between them) */
+void orc_pre3d_VA(const orc_fields *s) { pre_VA(s); }
+void orc_iterate3d_VA_once(const orc_fields *s, const orc_stokes_opts *o) { iterate3d_VA_once(s, o); }
+
 int orc_iterate3d_VA(const orc_fields *s, const orc_stokes_opts *o, int64_t niter)
 {
     pre_VA(s);

@@ -1,0 +1,117 @@
+"""Multi-GPU parity worker (run by tests/test_gpu_multi.py under torch.distributed.run, one rank per GPU).
+
+Every rank emulates ALL ranks on the CPU with the oracle + a literal ImplicitGlobalGrid exchange (tests/mrank.py)
+and compares its own block of the B200 result with its block of the emulation:
+  1. update_halo_ on dense arrays of every staggering, 2. the all-reduce, 3. 3D-VA fixed iterations (fused + unfused),
+  4. 3D-VA solve to convergence: iteration count and norm history."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import mrank  # noqa: E402
+from util import bc_flags, device_stokes, max_rel_diff  # noqa: E402
+
+
+def main():
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from justrelax_jl_b200 import B200Backend, PTArray, _abi, comm, setups, stokes as jst, to_host
+    from oracle import pyoracle as po
+
+    if dist.get_rank() == 0:
+        po.build()
+    dist.barrier()
+    ni = (20, 17, 15)
+    igg = comm.init_global_grid(*ni)
+    rank, dims, world = igg.me, igg.dims, igg.nprocs
+    coords_all = [comm.cart_coords(r, dims) for r in range(world)]
+
+    # ---- 1. dense update_halo_ ---------------------------------------------------------------------------
+    for grow in [(0, 0, 0), (1, 2, 2), (2, 1, 2), (2, 2, 1), (2, 2, 2), (1, 1, 0), (-1, 0, 0)]:
+        ext = tuple(ni[d] + grow[d] for d in range(3))
+        hosts = [np.asfortranarray(np.random.default_rng(11 + r).uniform(size=ext)) for r in range(world)]
+        A = PTArray(B200Backend)(hosts[rank])
+        B = PTArray(B200Backend)(hosts[rank] * 2.0)
+        for _ in range(2):  # twice: the second call reuses the staging buffers (epoch parity)
+            comm.update_halo_(A, B, ni=ni)
+            mrank.update_halo(hosts, dims, ni)
+        assert np.array_equal(to_host(A), hosts[rank]), ("update_halo_", grow, rank)
+        assert np.array_equal(to_host(B), hosts[rank] * 2.0), ("update_halo_ 2nd array", grow, rank)
+
+    # ---- 2. all-reduce -----------------------------------------------------------------------------------
+    vals = [0.1 * (r + 1) for r in range(world)]
+    acc = vals[0]
+    for v in vals[1:]:
+        acc = acc + v
+    assert comm.sum_mpi(vals[rank]) == acc
+    assert comm.maximum_mpi(float(rank)) == float(world - 1)
+    assert comm.minimum_mpi(float(rank) - 3.0) == -3.0
+
+    # ---- 3. 3D-VA, fixed number of iterations -----------------------------------------------------------------
+    names = ["Vx", "Vy", "Vz", "P", "txx", "tyy", "tzz", "tyz", "txz", "txy", "Rx", "Ry", "Rz", "RP", "etatau"]
+    for dt, finite_K, unfused in [(np.inf, False, False), (0.7, True, False), (0.7, True, True)]:
+        blocks = []
+        for r in range(world):
+            s = setups.random_stokes3d(ni, seed=500 + r, dt=dt, finite_K=finite_K)
+            blocks.append(po.alloc_stokes(ni, s.fields))
+        flags = dict(free_slip=[1] * 6, no_slip=[0] * 6, periodic=[0] * 6)
+        n_g = mrank.n_g(ni, dims)
+        opts = po.make_opts(s.pt_stokes, s.grid._di.center, dt, flags, n_g, iterMax=100, nout=100)
+        st, extra = device_stokes(ni, blocks[rank])
+        niter = 7
+        mrank.va_pre(po, blocks, dims, ni)
+        mrank.va_iterate(po, blocks, opts, dims, ni, niter)
+        from justrelax_jl_b200.types import VelocityBoundaryConditions
+        bcs = VelocityBoundaryConditions(free_slip=dict(left=True, right=True, front=True, back=True, top=True, bot=True),
+                                         no_slip=dict(left=False, right=False, front=False, back=False, top=False, bot=False))
+        jst.set_flags(_abi.JR_FLAG_UNFUSED if unfused else 0)
+        jst.iterate_(st, s.pt_stokes, s.grid, bcs, (extra["rhogx"], extra["rhogy"], extra["rhogz"]), extra["K"], extra["G"], dt, niter, igg)
+        jst.set_flags(0)
+        worst = max(max_rel_diff(to_host(st.slots()[nm]), blocks[rank][nm]) for nm in names)
+        assert worst <= 1e-12, ("3D-VA iterate", dt, unfused, rank, worst)
+
+    # ---- 4. SolVi3D solve across ranks: iteration count + norms ----------------------------------------------
+    # (divergence-free pure shear + inclusion placed by global coordinates: the loop ends on its tolerance, see setups.solvi3d)
+    nis = (10, 10, 10)
+    blocks, sets = [], []
+    for r in range(world):
+        ig = type(igg)(me=r, dims=dims, nprocs=world, coords=coords_all[r])
+        s = setups.solvi3d(*nis, igg=ig, smooth_passes=0, divfree=True, global_coords=True)
+        sets.append(s)
+        blocks.append(po.alloc_stokes(nis, s.fields))
+    for _ in range(10):
+        for d in blocks:
+            d["eta"][...] = setups._smooth3(d["eta"], 1.0)
+        mrank.update_halo([d["eta"] for d in blocks], dims, nis)
+    s = sets[rank]
+    import ctypes as C
+    opts = po.make_opts(s.pt_stokes, s.grid._di.center, s.dt, bc_flags(s.flow_bcs), mrank.n_g(nis, dims), iterMax=3000, nout=10)
+    for d in blocks:
+        fs = po.make_fields(d, nis)
+        po.lib().orc_flow_bcs3(C.byref(fs), C.byref(opts), 0)
+    for nm in ("Vx", "Vy", "Vz"):
+        mrank.update_halo([d[nm] for d in blocks], dims, nis)
+    st, extra = device_stokes(nis, blocks[rank])
+    it_ref, hist = mrank.va_solve(po, blocks, opts, dims, nis)
+    out = jst.solve_(st, s.pt_stokes, s.grid, s.flow_bcs, (extra["rhogx"], extra["rhogy"], extra["rhogz"]), extra["K"], extra["G"], s.dt, igg,
+                     kwargs=dict(iterMax=3000, nout=10, verbose=False))
+    assert out.iter == it_ref and it_ref < 3000, ("iteration count", out.iter, it_ref)
+    assert np.allclose(out.err_evo1, [h[1] for h in hist], rtol=1e-9, atol=0), (out.err_evo1[-3:], hist[-3:])
+    worst = max(max_rel_diff(to_host(st.slots()[nm]), blocks[rank][nm]) for nm in names[:10])
+    assert worst <= 1e-8, ("converged fields", worst)
+    dist.barrier()
+    print(f"MGPU_OK rank {rank}/{world} dims {dims}: halo, all-reduce, 3D-VA iterate (fused+unfused), solve iter={out.iter} worst={worst:.2e}", flush=True)
+    comm.finalize_global_grid()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
