@@ -157,6 +157,63 @@ int jr_scale_copy(jr_context *ctx, double *dst, const double *src, double factor
 /* Σ A[2:end-1,…]^2 (interior != 0) or Σ A^2 — the local part of norm_mpi, src/Utils.jl:698-701 */
 int jr_sumsq(jr_context *ctx, const double *A, const int32_t n[3], int interior, double *out_host);
 
+/* --- thermal diffusion: heatdiffusion_PT! ------------------------------------------------------------------------
+ * replaces JR{2,3}D.heatdiffusion_PT!(::CUDABackendTrait, thermal, args...; kwargs) (src/ext/CUDA/3D.jl:383-385 →
+ * src/thermal_diffusion/DiffusionPT_solver.jl:34-149 [K, ρCp arrays] and :181-305 [rheology]).
+ * jr_thermal_fields = ThermalArrays (src/types/heat_diffusion.jl:1-16) + the arrays of PTThermalCoeffs (:30-44) +
+ * the per-solve inputs.  T, Told, dT and the Dirichlet mask/value carry one ghost layer ((n+2)^d); q* are face
+ * arrays; everything else is (n)^d.  Unused pointers are NULL. */
+typedef struct {
+    int32_t ndim;
+    int32_t n[3];
+    double *T, *Told, *dT;
+    double *qTx, *qTy, *qTz, *qTx2, *qTy2, *qTz2;
+    double *H, *shear_heating, *adiabatic, *ResT;
+    double *theta_r_dtau, *dtau_rho;               /* pt_thermal.θr_dτ, pt_thermal.dτ_ρ                       */
+    double *K, *rhoCp;                             /* array form                                              */
+    double *P;                                     /* args.P (rheology form); args.T is T itself               */
+    double *dir_mask, *dir_value;                  /* Dirichlet mask / value on the ghosted grid, or NULL      */
+    double *phase_c, *phase_x, *phase_y, *phase_z; /* phase ratios [phase][node]: centre, Vx, Vy, Vz; or NULL  */
+} jr_thermal_fields;
+
+/* one row of the flat thermal rheology table (GeoParams subset: Constant/PT_/T_Density, ConstantHeatCapacity,
+ * ConstantConductivity, ConstantRadioactiveHeat) — lowered from rheology::NTuple{N,MaterialParams} once per solve */
+typedef struct {
+    int32_t rho_kind; /* 0 ConstantDensity, 1 PT_Density, 2 T_Density */
+    int32_t has_Hr;
+    double rho0, alpha, beta, T0, P0, Cp, k, Hr;
+} jr_thermal_phase;
+
+typedef struct {
+    double _di[3], dt, eps;                        /* grid._di, dt, pt_thermal.ϵ                               */
+    int64_t iterMax, nout;                         /* kwargs                                                   */
+    double max_lxyz, Vpdtau;                       /* pt_thermal.max_lxyz, pt_thermal.Vpdτ                     */
+    int32_t form;                                  /* 0: K, ρCp arrays; 1: rheology table                      */
+    int32_t nphase;
+    const jr_thermal_phase *phases;                /* HOST pointer, nphase rows                                */
+    double dir_const;                              /* ConstantDirichletBoundaryCondition value (dir_value NULL) */
+    /* TemperatureBoundaryConditions (src/boundaryconditions/types.jl:65-99), faces left,right,front,back,top,bot;
+     * cv_active/cf_active: the entry is not `false` / is a number */
+    int32_t no_flux[6], cv_active[6], cf_active[6], periodic[6];
+    double cv_value[6], cf_value[6];
+} jr_thermal_opts;
+
+typedef struct {
+    int64_t iter, nhist, cap;
+    double err;
+    double *norm_ResT; int64_t *iter_count;        /* HOST arrays of capacity cap                              */
+    double time_s; int64_t kernel_launches;
+} jr_thermal_result;
+
+int jr_heatdiffusion_PT(jr_context *ctx, const jr_thermal_fields *f, const jr_thermal_opts *o, const double *stokes_P,
+                        const double *stokes_P0, jr_thermal_result *res);
+/* exactly niter PT iterations (no convergence test; Told is NOT reset) — fixed-iteration parity / benchmark */
+int jr_thermal_iterate(jr_context *ctx, const jr_thermal_fields *f, const jr_thermal_opts *o, int64_t niter, jr_thermal_result *res);
+/* thermal_bcs!(thermal, bcs)  src/ext/CUDA/3D.jl:220-226 → BoundaryConditions.jl:39-54 */
+int jr_thermal_bcs(jr_context *ctx, double *T, int32_t ndim, const int32_t n[3], const jr_thermal_opts *o);
+/* update_thermal_coeffs! / compute_pt_thermal_arrays!  src/ext/CUDA/3D.jl:110-175 → DiffusionPT_coefficients.jl:105-208 */
+int jr_thermal_pt_arrays(jr_context *ctx, const jr_thermal_fields *f, const jr_thermal_opts *o);
+
 /* --- multi-GPU: ImplicitGlobalGrid-compatible decomposition over CUDA-IPC peer memory (NVLink) -----------------
  * Replaces IGG's update_halo! (call sites src/stokes/Stokes3D.jl:57,120,515,578-580,596; Stokes2D.jl:655,757,784;
  * src/thermal_diffusion/DiffusionPT_solver.jl:110,261) and the MPI.Allreduce of norm_mpi/maximum_mpi

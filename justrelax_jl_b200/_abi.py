@@ -101,6 +101,32 @@ class OracleStokesResult(C.Structure):
     _fields_ = StokesResult._fields_[:9]
 
 
+class ThermalFields(C.Structure):
+    """jr_thermal_fields"""
+    names = ("T", "Told", "dT", "qTx", "qTy", "qTz", "qTx2", "qTy2", "qTz2", "H", "shear_heating", "adiabatic", "ResT",
+             "theta_r_dtau", "dtau_rho", "K", "rhoCp", "P", "dir_mask", "dir_value", "phase_c", "phase_x", "phase_y", "phase_z")
+    _fields_ = [("ndim", C.c_int32), ("n", C.c_int32 * 3)] + [(nm, C.c_void_p) for nm in names]
+
+
+class ThermalPhase(C.Structure):
+    _fields_ = [("rho_kind", C.c_int32), ("has_Hr", C.c_int32), ("rho0", C.c_double), ("alpha", C.c_double), ("beta", C.c_double),
+                ("T0", C.c_double), ("P0", C.c_double), ("Cp", C.c_double), ("k", C.c_double), ("Hr", C.c_double)]
+
+
+class ThermalOpts(C.Structure):
+    _fields_ = [("_di", C.c_double * 3), ("dt", C.c_double), ("eps", C.c_double), ("iterMax", C.c_int64), ("nout", C.c_int64),
+                ("max_lxyz", C.c_double), ("Vpdtau", C.c_double), ("form", C.c_int32), ("nphase", C.c_int32),
+                ("phases", C.POINTER(ThermalPhase)), ("dir_const", C.c_double),
+                ("no_flux", C.c_int32 * 6), ("cv_active", C.c_int32 * 6), ("cf_active", C.c_int32 * 6), ("periodic", C.c_int32 * 6),
+                ("cv_value", C.c_double * 6), ("cf_value", C.c_double * 6)]
+
+
+class ThermalResult(C.Structure):
+    _fields_ = [("iter", C.c_int64), ("nhist", C.c_int64), ("cap", C.c_int64), ("err", C.c_double),
+                ("norm_ResT", C.POINTER(C.c_double)), ("iter_count", C.POINTER(C.c_int64)),
+                ("time_s", C.c_double), ("kernel_launches", C.c_int64)]
+
+
 ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)
 
 
@@ -123,6 +149,10 @@ def _declare(L):
     L.jr_stokes3d_solve_VA.argtypes = [vp, vp, C.POINTER(StokesOpts), C.POINTER(StokesResult)]
     L.jr_stokes3d_iterate_VA.argtypes = [vp, vp, C.POINTER(StokesOpts), C.c_int64, C.POINTER(StokesResult)]
     L.jr_stokes3d_VA_plan_info.argtypes = [vp, i32p]
+    L.jr_heatdiffusion_PT.argtypes = [vp, C.POINTER(ThermalFields), C.POINTER(ThermalOpts), vp, vp, C.POINTER(ThermalResult)]
+    L.jr_thermal_iterate.argtypes = [vp, C.POINTER(ThermalFields), C.POINTER(ThermalOpts), C.c_int64, C.POINTER(ThermalResult)]
+    L.jr_thermal_bcs.argtypes = [vp, vp, C.c_int32, i32p, C.POINTER(ThermalOpts)]
+    L.jr_thermal_pt_arrays.argtypes = [vp, C.POINTER(ThermalFields), C.POINTER(ThermalOpts)]
     L.jr_comm_create.argtypes = [vp, C.c_int, C.c_int, i32p, i32p, ALLGATHER_FN, vp, C.POINTER(vp)]
     L.jr_comm_destroy.argtypes = [vp]
     L.jr_context_set_comm.argtypes = [vp, vp]

@@ -1,0 +1,167 @@
+"""GeoParams.jl material laws — the supported subset — and their lowering to the flat per-phase tables libjrb200 takes.
+
+The reference hands `rheology::NTuple{N,MaterialParams}` (GeoParams.jl structs) to its kernels, which dispatch on the
+law types point-wise (src/rheology/*.jl, src/thermal_diffusion/DiffusionPT_GeoParams.jl).  The B200 backend lowers the
+tuple ONCE per solve to plain rows (`jr_thermal_phase`, `jr_stokes_phase` in include/jrb200.h); a law outside the subset
+raises at lowering time — there is no fallback (SURVEY.md §8b, Appendix C lists the struct fields read).
+
+Names, keyword arguments and defaults follow GeoParams 0.7 (SI values, no unit handling: pass numbers).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Optional, Sequence, Tuple
+
+
+class UnsupportedRheology(ValueError):
+    """raised when a material law is outside the subset the device table supports (JR_ERR_UNSUPPORTED on the C side)"""
+
+
+# ---- density ----------------------------------------------------------------------------------------------------
+@dataclass
+class ConstantDensity:
+    ρ: float = 2900.0
+
+
+@dataclass
+class PT_Density:
+    """ρ = ρ0 (1 − α (T − T0) + β (P − P0))"""
+    ρ0: float = 2900.0
+    α: float = 3e-5
+    β: float = 1e-9
+    T0: float = 0.0
+    P0: float = 0.0
+
+
+@dataclass
+class T_Density:
+    """ρ = ρ0 (1 − α (T − T0))"""
+    ρ0: float = 2900.0
+    α: float = 3e-5
+    T0: float = 273.15
+
+
+# ---- thermal ------------------------------------------------------------------------------------------------------
+@dataclass
+class ConstantHeatCapacity:
+    Cp: float = 1050.0
+
+
+@dataclass
+class ConstantConductivity:
+    k: float = 3.0
+
+
+@dataclass
+class ConstantRadioactiveHeat:
+    H_r: float = 1e-6
+
+
+@dataclass
+class ConstantGravity:
+    g: float = 9.81
+
+
+# ---- creep / elasticity / plasticity ---------------------------------------------------------------------------------
+@dataclass
+class LinearViscous:
+    η: float = 1e20
+
+
+@dataclass
+class ConstantElasticity:
+    """G shear modulus, ν Poisson ratio, Kb bulk modulus (GeoParams: Kb = 2G(1+ν)/(3(1−2ν)) unless given)"""
+    G: float = 5e10
+    ν: float = 0.5
+    Kb: Optional[float] = None
+
+    def __post_init__(self):
+        if self.Kb is None:
+            den = 3 * (1 - 2 * self.ν)
+            self.Kb = math.inf if den == 0 else 2 * self.G * (1 + self.ν) / den
+
+
+@dataclass
+class DruckerPrager_regularised:
+    """F = τII − C cosϕ − P sinϕ; ϕ, Ψ in degrees; η_vp regularisation viscosity"""
+    C: float = 10e6
+    ϕ: float = 30.0
+    Ψ: float = 0.0
+    η_vp: float = 1e20
+    softening_C: object = None
+    softening_ϕ: object = None
+
+    @property
+    def sinϕ(self):
+        return math.sin(math.radians(self.ϕ))
+
+    @property
+    def cosϕ(self):
+        return math.cos(math.radians(self.ϕ))
+
+    @property
+    def sinΨ(self):
+        return math.sin(math.radians(self.Ψ))
+
+
+@dataclass
+class DruckerPrager(DruckerPrager_regularised):
+    η_vp: float = 0.0
+
+
+@dataclass
+class CompositeRheology:
+    elements: Tuple
+
+    def __init__(self, elements):
+        self.elements = tuple(elements)
+
+
+@dataclass
+class MaterialParams:
+    Phase: int = 1
+    Density: object = None
+    HeatCapacity: object = None
+    Conductivity: object = None
+    RadioactiveHeat: object = None
+    CompositeRheology: object = None
+    Gravity: object = field(default_factory=ConstantGravity)
+    Elasticity: object = None
+
+
+def SetMaterialParams(**kw) -> MaterialParams:
+    return MaterialParams(**kw)
+
+
+# ---- lowering -----------------------------------------------------------------------------------------------------------
+def _as_tuple(rheology) -> Sequence[MaterialParams]:
+    return tuple(rheology) if isinstance(rheology, (tuple, list)) else (rheology,)
+
+
+def lower_thermal(rheology):
+    """rows of jr_thermal_phase: dict(rho_kind, has_Hr, rho0, alpha, beta, T0, P0, Cp, k, Hr)"""
+    rows = []
+    for p in _as_tuple(rheology):
+        ρ = p.Density
+        if isinstance(ρ, ConstantDensity):
+            row = dict(rho_kind=0, rho0=ρ.ρ, alpha=0.0, beta=0.0, T0=0.0, P0=0.0)
+        elif isinstance(ρ, PT_Density):
+            row = dict(rho_kind=1, rho0=ρ.ρ0, alpha=ρ.α, beta=ρ.β, T0=ρ.T0, P0=ρ.P0)
+        elif isinstance(ρ, T_Density):
+            row = dict(rho_kind=2, rho0=ρ.ρ0, alpha=ρ.α, beta=0.0, T0=ρ.T0, P0=0.0)
+        else:
+            raise UnsupportedRheology(f"density law {type(ρ).__name__} is outside the supported subset")
+        if not isinstance(p.HeatCapacity, ConstantHeatCapacity):
+            raise UnsupportedRheology(f"heat-capacity law {type(p.HeatCapacity).__name__} is outside the supported subset")
+        if not isinstance(p.Conductivity, ConstantConductivity):
+            raise UnsupportedRheology(f"conductivity law {type(p.Conductivity).__name__} is outside the supported subset")
+        row["Cp"], row["k"] = p.HeatCapacity.Cp, p.Conductivity.k
+        if p.RadioactiveHeat is None:
+            row["has_Hr"], row["Hr"] = 0, 0.0
+        elif isinstance(p.RadioactiveHeat, ConstantRadioactiveHeat):
+            row["has_Hr"], row["Hr"] = 1, p.RadioactiveHeat.H_r
+        else:
+            raise UnsupportedRheology(f"radioactive-heat law {type(p.RadioactiveHeat).__name__} is outside the supported subset")
+        rows.append(row)
+    return rows

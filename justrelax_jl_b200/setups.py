@@ -113,3 +113,43 @@ def random_stokes3d(ni, seed=20261017, *, dt=0.7, finite_K=True, const_rhog=None
     grid = Geometry(ni, li)
     pt = PTStokesCoeffs(li, grid.di.center)
     return SimpleNamespace(ni=tuple(ni), li=li, di=grid.di.center, grid=grid, igg=IGG(), pt_stokes=pt, dt=dt, fields=f)
+
+
+# ------------------------------------------------------------------------------------------------------------
+def pt_thermal_coeffs_arrays(K, ρCp, dt, di, li, *, ϵ=1.0e-8, CFL=None):
+    """PTThermalCoeffs(K, ρCp, dt, di, li; ϵ, CFL) — src/thermal_diffusion/DiffusionPT_coefficients.jl:17-26 (host setup)."""
+    CFL = 0.9 / math.sqrt(3) if CFL is None else CFL
+    Vpdτ = min(di) * CFL
+    max_lxyz = max(li)
+    max_lxyz2 = max_lxyz ** 2
+    Re = math.pi + np.sqrt(math.pi * math.pi + ρCp * max_lxyz2 / K / dt)
+    θr_dτ = np.asfortranarray(max_lxyz / Vpdτ / Re)
+    dτ_ρ = np.asfortranarray(Vpdτ * max_lxyz / K / Re)
+    return SimpleNamespace(CFL=CFL, ϵ=ϵ, max_lxyz=max_lxyz, max_lxyz2=max_lxyz2, Vpdτ=Vpdτ, θr_dτ=θr_dτ, dτ_ρ=dτ_ρ)
+
+
+def diffusion2d(nx=32, ny=32, *, lx=100.0e3, ly=100.0e3, ρ0=3.3e3, Cp0=1.2e3, K0=3.0):
+    """Config 1 — test/test_diffusion2D.jl:46-125: 2D thermal diffusion, rheology form with a single MaterialParams
+    (PT_Density(ρ0=3.1e3, β=0, T0=0, α=1.5e-5), ConstantHeatCapacity(Cp0), ConstantConductivity(K0)), H = 1e-6,
+    T(z) linear 1600–1900 K + 100 K disc of radius 10 km, top 300 K / bottom 3500 K, sides no-flux (and
+    constant_value = true, i.e. the number 1, overridden by no-flux: quirk Q16), dt = 50 kyr, 20 steps."""
+    from .types import TemperatureBoundaryConditions
+
+    kyr = 1.0e3 * 3600 * 24 * 365.25
+    dt = 50 * kyr
+    ni, li = (nx, ny), (lx, ly)
+    di = tuple(l / n for l, n in zip(li, ni))
+    grid = Geometry(ni, li, origin=(0.0, -ly))
+    xc, yc = grid.xci
+    T = np.zeros((nx + 2, ny + 2), order="F")
+    T[:, 1:-1] = (yc * (1900.0 - 1600.0) / yc.min() + 1600.0)[None, :]       # init_T!  :29-32
+    bc = TemperatureBoundaryConditions(no_flux=dict(left=True, right=True, top=False, bot=False),
+                                       constant_value=dict(left=True, right=True, top=300.0, bot=3500.0))
+    ρCp = np.full(ni, Cp0 * ρ0, order="F")
+    K = np.full(ni, K0, order="F")
+    pt = pt_thermal_coeffs_arrays(K, ρCp, dt, di, li, CFL=0.95 / math.sqrt(2.1))
+    pert = ((xc[:, None] - lx / 2) ** 2 + (yc[None, :] + ly / 2) ** 2) <= 10.0e3 ** 2                # elliptical_perturbation!
+    phases = [dict(rho_kind=1, has_Hr=0, rho0=3.1e3, alpha=1.5e-5, beta=0.0, T0=0.0, P0=0.0, Cp=Cp0, k=K0, Hr=0.0)]
+    return SimpleNamespace(ni=ni, li=li, di=di, grid=grid, dt=dt, nt=20, T=T, bc=bc, pt=pt, perturbation=pert, δT=100.0,
+                           H=np.full(ni, 1.0e-6, order="F"), P=np.zeros(ni, order="F"), phases=phases, K=K, ρCp=ρCp,
+                           kwargs=dict(iterMax=50e3, nout=1e3, verbose=False))

@@ -205,3 +205,101 @@ def sumsq(A, interior):
     A = np.asfortranarray(A)
     shp = list(A.shape) + [1] * (3 - A.ndim)
     return lib().orc_sumsq_interior(_dp(A), *map(C.c_int, shp), C.c_int(int(interior)))
+
+
+# ------------------------------------------------------------------------------------------------------------
+# thermal (oracle/thermal.c)
+class ThermalFields(C.Structure):
+    _names = ("T", "Told", "dT", "qTx", "qTy", "qTz", "qTx2", "qTy2", "qTz2", "H", "shear_heating", "adiabatic", "ResT",
+              "theta_r_dtau", "dtau_rho", "K", "rhoCp", "P", "dir_mask", "dir_value", "phase_c", "phase_x", "phase_y", "phase_z")
+    _fields_ = [("ndim", C.c_int32), ("n", C.c_int32 * 3)] + [(nm, C.c_void_p) for nm in _names]
+
+
+class ThermalPhase(C.Structure):
+    _fields_ = [("rho_kind", C.c_int32), ("has_Hr", C.c_int32), ("rho0", C.c_double), ("alpha", C.c_double), ("beta", C.c_double),
+                ("T0", C.c_double), ("P0", C.c_double), ("Cp", C.c_double), ("k", C.c_double), ("Hr", C.c_double)]
+
+
+class ThermalOpts(C.Structure):
+    _fields_ = [("_di", C.c_double * 3), ("dt", C.c_double), ("eps", C.c_double), ("iterMax", C.c_int64), ("nout", C.c_int64),
+                ("max_lxyz", C.c_double), ("Vpdtau", C.c_double), ("form", C.c_int32), ("nphase", C.c_int32),
+                ("phases", C.POINTER(ThermalPhase)), ("dir_const", C.c_double),
+                ("no_flux", C.c_int32 * 6), ("cv_active", C.c_int32 * 6), ("cf_active", C.c_int32 * 6), ("periodic", C.c_int32 * 6),
+                ("cv_value", C.c_double * 6), ("cf_value", C.c_double * 6)]
+
+
+class ThermalResult(C.Structure):
+    _fields_ = [("iter", C.c_int64), ("nhist", C.c_int64), ("cap", C.c_int64), ("err", C.c_double),
+                ("norm_ResT", C.POINTER(C.c_double)), ("iter_count", C.POINTER(C.c_int64))]
+
+
+def alloc_thermal(ni, init: dict | None = None) -> dict:
+    """Host ThermalArrays + PTThermalCoeffs arrays (zero-initialised, constructors/heat_diffusion.jl:38-120)."""
+    z = lambda *s: np.zeros(s, order="F")
+    g = tuple(n + 2 for n in ni)
+    d = dict(T=z(*g), Told=z(*g), dT=z(*g))
+    for nm in ("H", "shear_heating", "adiabatic", "ResT", "theta_r_dtau", "dtau_rho"):
+        d[nm] = z(*ni)
+    for a, nm in enumerate(("qTx", "qTy", "qTz")[:len(ni)]):
+        e = tuple(n + (1 if b == a else 0) for b, n in enumerate(ni))
+        d[nm], d[nm + "2"] = z(*e), z(*e)
+    if init:
+        for k, a in init.items():
+            d[k] = np.asfortranarray(a, dtype=np.float64).copy(order="F")
+    return d
+
+
+def thermal_fields(slots: dict, ni):
+    fs = ThermalFields()
+    fs.ndim = len(ni)
+    for q in range(3):
+        fs.n[q] = int(ni[q]) if q < len(ni) else 1
+    for nm in ThermalFields._names:
+        a = slots.get(nm)
+        if a is not None:
+            assert a.dtype == np.float64 and a.flags.f_contiguous, nm
+            setattr(fs, nm, a.ctypes.data)
+    return fs
+
+
+FACES = ("left", "right", "front", "back", "top", "bot")
+
+
+def thermal_opts(*, _di, dt, eps, iterMax, nout, max_lxyz, Vpdtau, form, phases=(), bc=None, dir_const=0.0):
+    """bc: object with dicts no_flux / constant_value / constant_flux / periodic keyed by face name
+    (False = inactive; True counts as the number 1 for constant_value — quirk Q16)."""
+    o = ThermalOpts()
+    for q in range(3):
+        o._di[q] = float(_di[q]) if q < len(_di) else 0.0
+    o.dt, o.eps, o.iterMax, o.nout = float(dt), float(eps), int(iterMax), int(nout)
+    o.max_lxyz, o.Vpdtau, o.form, o.dir_const = float(max_lxyz), float(Vpdtau), int(form), float(dir_const)
+    arr = (ThermalPhase * max(len(phases), 1))()
+    for i, p in enumerate(phases):
+        for k, v in p.items():
+            setattr(arr[i], k, v)
+    o.nphase, o.phases = len(phases), arr
+    o._keep = arr
+    for q, f in enumerate(FACES):
+        if bc is None:
+            continue
+        o.no_flux[q] = int(bool(bc.no_flux.get(f, False)))
+        o.periodic[q] = int(bool(bc.periodic.get(f, False)))
+        cv = bc.constant_value.get(f, False)
+        o.cv_active[q] = int(cv is not False)
+        o.cv_value[q] = float(cv) if cv is not False else 0.0
+        cf = bc.constant_flux.get(f, False)
+        o.cf_active[q] = int(not isinstance(cf, bool))  # !isa(bc_flux.left, Bool)  DiffusionPT_kernels.jl:13
+        o.cf_value[q] = float(cf) if not isinstance(cf, bool) else 0.0
+    return o
+
+
+def heatdiffusion_PT(slots, ni, opts, stokes_P=None, stokes_P0=None):
+    fs = thermal_fields(slots, ni)
+    cap = int(opts.iterMax // max(opts.nout, 1)) + 2
+    nr, ic = np.zeros(cap), np.zeros(cap, dtype=np.int64)
+    r = ThermalResult()
+    r.cap, r.norm_ResT, r.iter_count = cap, _dp(nr), ic.ctypes.data_as(C.POINTER(C.c_int64))
+    lib().orc_heatdiffusion_PT(C.byref(fs), C.byref(opts), None if stokes_P is None else _dp(stokes_P),
+                               None if stokes_P0 is None else _dp(stokes_P0), C.byref(r))
+    n = int(r.nhist)
+    return dict(iter=int(r.iter), iter_count=ic[:n].copy(), norm_ResT=nr[:n].copy(), err=float(r.err))

@@ -1,0 +1,79 @@
+"""CPU oracle of heatdiffusion_PT! pinned on the reference's own goldens (no GPU).
+
+ - test/test_diffusion2D.jl:127-135 (config 1): T[18,18] ≈ 1817.9448461176817, T[17,17] ≈ 1827.4674313638786 (atol 0.1)
+ - thermal_bcs! ghost identities of test/test_boundary_conditions2D.jl (constant value / no flux / periodic)
+"""
+import numpy as np
+
+from justrelax_jl_b200 import setups
+
+
+def run_diffusion2d(oracle, s, fields):
+    o = oracle.thermal_opts(_di=s.grid._di.center, dt=s.dt, eps=s.pt.ϵ, iterMax=s.kwargs["iterMax"], nout=s.kwargs["nout"],
+                            max_lxyz=s.pt.max_lxyz, Vpdtau=s.pt.Vpdτ, form=1, phases=s.phases, bc=s.bc)
+    fs = oracle.thermal_fields(fields, s.ni)
+    oracle.lib().orc_thermal_bcs(__import__("ctypes").byref(fs), __import__("ctypes").byref(o))   # thermal_bcs!  :92
+    fields["T"][1:-1, 1:-1][s.perturbation] += s.δT                                               # :100
+    outs = []
+    for _ in range(s.nt):
+        outs.append(oracle.heatdiffusion_PT(fields, s.ni, o))
+    return outs
+
+
+def test_diffusion2d_reference_golden(oracle):
+    s = setups.diffusion2d()
+    f = oracle.alloc_thermal(s.ni, dict(T=s.T, H=s.H, P=s.P, theta_r_dtau=s.pt.θr_dτ, dtau_rho=s.pt.dτ_ρ))
+    outs = run_diffusion2d(oracle, s, f)
+    T = f["T"]
+    nx_T, ny_T = T.shape
+    nx, ny = s.ni
+    # Julia: T[nx_T >>> 1 + 1, ny_T >>> 1 + 1] and T[(nx >>> 1) + 1, (ny >>> 1) + 1]   (1-based)
+    assert abs(T[(nx_T >> 1), (ny_T >> 1)] - 1817.9448461176817) < 1.0e-1
+    assert abs(T[(nx >> 1), (ny >> 1)] - 1827.4674313638786) < 1.0e-1
+    assert all(o["err"] <= 1e-8 for o in outs)
+    assert np.array_equal(f["dT"], f["T"] - f["Told"])
+
+
+def test_thermal_bcs_identities(oracle):
+    import ctypes as C
+    from justrelax_jl_b200.types import TemperatureBoundaryConditions
+
+    rng = np.random.default_rng(5)
+    # 2D: constant value top/bot, no flux left/right
+    ni = (6, 5)
+    f = oracle.alloc_thermal(ni, dict(T=rng.uniform(size=(8, 7))))
+    bc = TemperatureBoundaryConditions(no_flux=dict(left=True, right=True, top=False, bot=False),
+                                       constant_value=dict(left=False, right=False, top=10.0, bot=20.0))
+    o = oracle.thermal_opts(_di=(1, 1), dt=1, eps=1e-8, iterMax=1, nout=1, max_lxyz=1, Vpdtau=1, form=0, bc=bc)
+    fs = oracle.thermal_fields(f, ni)
+    oracle.lib().orc_thermal_bcs(C.byref(fs), C.byref(o))
+    T = f["T"]
+    assert np.allclose(0.5 * (T[1:-1, 0] + T[1:-1, 1]), 20.0) and np.allclose(0.5 * (T[1:-1, -1] + T[1:-1, -2]), 10.0)
+    assert np.array_equal(T[0, :], T[1, :]) and np.array_equal(T[-1, :], T[-2, :])
+    # 3D periodic in x, no flux elsewhere
+    ni = (5, 4, 3)
+    f = oracle.alloc_thermal(ni, dict(T=rng.uniform(size=(7, 6, 5))))
+    bc = TemperatureBoundaryConditions(no_flux=dict(left=False, right=False, front=True, back=True, top=True, bot=True),
+                                       periodic=dict(left=True, right=True, front=False, back=False, top=False, bot=False))
+    o = oracle.thermal_opts(_di=(1, 1, 1), dt=1, eps=1e-8, iterMax=1, nout=1, max_lxyz=1, Vpdtau=1, form=0, bc=bc)
+    fs = oracle.thermal_fields(f, ni)
+    oracle.lib().orc_thermal_bcs(C.byref(fs), C.byref(o))
+    T = f["T"]
+    assert np.array_equal(T[0, 1:-1, 1:-1], T[-2, 1:-1, 1:-1]) and np.array_equal(T[-1, 1:-1, 1:-1], T[1, 1:-1, 1:-1])
+    assert np.array_equal(T[1:-1, 0, 1:-1], T[1:-1, 1, 1:-1]) and np.array_equal(T[1:-1, 1:-1, -1], T[1:-1, 1:-1, -2])
+
+
+def test_array_form_matches_rheology_form_with_constant_density(oracle):
+    """form A (K, ρCp arrays) and form B (constant-property table) are the same arithmetic when ρ is constant, except for the
+    two extra (zero) source terms of form B — both must converge to the same field."""
+    s = setups.diffusion2d(16, 16)
+    phases = [dict(rho_kind=0, has_Hr=0, rho0=3.3e3, alpha=0.0, beta=0.0, T0=0.0, P0=0.0, Cp=1.2e3, k=3.0, Hr=0.0)]
+    res = []
+    for form in (0, 1):
+        f = oracle.alloc_thermal(s.ni, dict(T=s.T, H=s.H, P=s.P, theta_r_dtau=s.pt.θr_dτ, dtau_rho=s.pt.dτ_ρ, K=s.K, rhoCp=s.ρCp))
+        o = oracle.thermal_opts(_di=s.grid._di.center, dt=s.dt, eps=1e-8, iterMax=50e3, nout=100, max_lxyz=s.pt.max_lxyz,
+                                Vpdtau=s.pt.Vpdτ, form=form, phases=phases, bc=s.bc)
+        out = oracle.heatdiffusion_PT(f, s.ni, o)
+        res.append((f["T"].copy(), out["iter"]))
+    assert res[0][1] == res[1][1]
+    assert np.allclose(res[0][0], res[1][0], rtol=1e-13, atol=0)
