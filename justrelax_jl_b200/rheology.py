@@ -165,3 +165,63 @@ def lower_thermal(rheology):
             raise UnsupportedRheology(f"radioactive-heat law {type(p.RadioactiveHeat).__name__} is outside the supported subset")
         rows.append(row)
     return rows
+
+
+def _elasticity_of(p: MaterialParams):
+    if p.Elasticity is not None:
+        return p.Elasticity
+    if p.CompositeRheology is not None:
+        for e in p.CompositeRheology.elements:
+            if isinstance(e, ConstantElasticity):
+                return e
+    return None
+
+
+def _modulus(x):
+    """get_shear_modulus / get_bulk_modulus: Inf when NaN or zero (src/rheology/GeoParams.jl:1-15)"""
+    return math.inf if (x is None or x != x or x == 0) else float(x)
+
+
+def lower_stokes(rheology):
+    """rows of jr_stokes_phase: dict(eta, G, Kb, has_pl, rho_kind, C, sinphi, cosphi, sinpsi, eta_vp, rho0, alpha, beta, T0, P0).
+    Supported: LinearViscous (exactly one creep element), ConstantElasticity, DruckerPrager[_regularised] without softening
+    (the FIRST plastic element wins, StressUpdate.jl:131-144), Constant/PT_/T_Density."""
+    rows = []
+    for p in _as_tuple(rheology):
+        if p.CompositeRheology is None:
+            raise UnsupportedRheology("MaterialParams without a CompositeRheology")
+        visc = [e for e in p.CompositeRheology.elements if isinstance(e, LinearViscous)]
+        other = [e for e in p.CompositeRheology.elements
+                 if not isinstance(e, (LinearViscous, ConstantElasticity, DruckerPrager_regularised))]
+        if other:
+            raise UnsupportedRheology(f"rheological element {type(other[0]).__name__} is outside the supported subset")
+        if len(visc) != 1:
+            raise UnsupportedRheology("exactly one LinearViscous element per phase is supported")
+        el = _elasticity_of(p)
+        row = dict(eta=float(visc[0].η), G=_modulus(el.G if el else None), Kb=_modulus(el.Kb if el else None))
+        pls = [e for e in p.CompositeRheology.elements if isinstance(e, DruckerPrager_regularised)]
+        if pls:
+            pl = pls[0]
+            if pl.softening_C is not None or pl.softening_ϕ is not None:
+                raise UnsupportedRheology("strain softening is outside the supported subset (SURVEY §8f-1)")
+            row.update(has_pl=1, C=float(pl.C), sinphi=pl.sinϕ, cosphi=pl.cosϕ, sinpsi=pl.sinΨ, eta_vp=float(pl.η_vp))
+        else:
+            row.update(has_pl=0, C=0.0, sinphi=0.0, cosphi=0.0, sinpsi=0.0, eta_vp=0.0)
+        ρ = p.Density
+        if ρ is None or isinstance(ρ, ConstantDensity):
+            row.update(rho_kind=0, rho0=(ρ.ρ if ρ else 0.0), alpha=0.0, beta=0.0, T0=0.0, P0=0.0)
+        elif isinstance(ρ, PT_Density):
+            row.update(rho_kind=1, rho0=ρ.ρ0, alpha=ρ.α, beta=ρ.β, T0=ρ.T0, P0=ρ.P0)
+        elif isinstance(ρ, T_Density):
+            row.update(rho_kind=2, rho0=ρ.ρ0, alpha=ρ.α, beta=0.0, T0=ρ.T0, P0=0.0)
+        else:
+            raise UnsupportedRheology(f"density law {type(ρ).__name__} is outside the supported subset")
+        rows.append(row)
+    return rows
+
+
+def gravity_of(rheology):
+    """compute_gravity(first(rheology)) (BuoyancyForces.jl:25,56): ConstantGravity(g) acts along the LAST axis (0, 0, g)."""
+    g = _as_tuple(rheology)[0].Gravity
+    gv = g.g if g is not None else 0.0
+    return (0.0, 0.0, float(gv))

@@ -153,3 +153,78 @@ def diffusion2d(nx=32, ny=32, *, lx=100.0e3, ly=100.0e3, ρ0=3.3e3, Cp0=1.2e3, K
     return SimpleNamespace(ni=ni, li=li, di=di, grid=grid, dt=dt, nt=20, T=T, bc=bc, pt=pt, perturbation=pert, δT=100.0,
                            H=np.full(ni, 1.0e-6, order="F"), P=np.zeros(ni, order="F"), phases=phases, K=K, ρCp=ρCp,
                            kwargs=dict(iterMax=50e3, nout=1e3, verbose=False))
+
+
+# ------------------------------------------------------------------------------------------------------------
+def _smooth2(A, fact):
+    """smooth!  miniapps/benchmarks/stokes2D/solcx/SolCx.jl:6-11"""
+    A2 = A.copy(order="F")
+    c = A[1:-1, 1:-1]
+    A2[1:-1, 1:-1] = c + 1.0 / 4.1 / fact * (((A[2:, 1:-1] - c) - (c - A[:-2, 1:-1])) + ((A[1:-1, 2:] - c) - (c - A[1:-1, :-2])))
+    return A2
+
+
+def solcx2d(nx=64, ny=64, *, Δη=1.0e6, lx=1.0, ly=1.0):
+    """Config 2 — miniapps/benchmarks/stokes2D/solcx/SolCx.jl:54-145 (variant 2D-V2): η = 1 | Δη across x = 0.5, five
+    smoothing passes with edge copies, ρg_y = −sin(πy) cos(πx), G = K = Inf, solve with dt = 0.1, free slip,
+    PTStokesCoeffs(li, di; CFL = 1/√2.1, ϵ_abs = 1e-8, ϵ_rel = 1e-9), kwargs = (iterMax = 500e3, nout = 5e3)."""
+    ni, li = (nx, ny), (lx, ly)
+    grid = Geometry(ni, li, origin=(0.0, 0.0))
+    di = grid.di.center
+    pt = PTStokesCoeffs(li, di, CFL=1 / math.sqrt(2.1), ϵ_abs=1.0e-8, ϵ_rel=1.0e-9)
+    xc, yc = grid.xci
+    η = np.asfortranarray(np.where(xc[:, None] <= 0.5, 1.0, Δη) * np.ones((1, ny)))
+    ρ = np.asfortranarray(-np.sin(math.pi * yc[None, :]) * np.cos(math.pi * xc[:, None]))
+    η2 = η.copy(order="F")
+    for _ in range(5):
+        η2 = _smooth2(η, 1.0) if True else η2
+        # the reference smooths η into η2 (whose interior is overwritten) and then copies the edges
+        η2[0, :], η2[-1, :] = η2[1, :], η2[-2, :]
+        η2[:, 0], η2[:, -1] = η2[:, 1], η2[:, -2]
+        η, η2 = η2, η
+    flow_bcs = VelocityBoundaryConditions(free_slip=dict(left=True, right=True, top=True, bot=True))
+    fields = dict(eta=np.asfortranarray(η), rhogx=np.zeros(ni, order="F"), rhogy=np.asfortranarray(ρ * 1.0), G=np.full(ni, np.inf, order="F"),
+                  K=np.full(ni, np.inf, order="F"))
+    return SimpleNamespace(ni=ni, li=li, di=di, grid=grid, igg=IGG(), pt_stokes=pt, flow_bcs=flow_bcs, dt=0.1, fields=fields,
+                           kwargs=dict(iterMax=500e3, nout=5e3, verbose=False))
+
+
+def shearband2d(n=32):
+    """Config 3 — test/test_shearband2D.jl:61-192 (variant 2D-VC): unit square, two phases (matrix G = 1, inclusion r = 0.1 with
+    G = 0.5, Kb = 4), η = 1, DruckerPrager_regularised(C = 1.6/cosd(30), ϕ = 30, η_vp = 8e-3, Ψ = 0), dt = 0.25, pure shear
+    εbg = 1, free slip, PTStokesCoeffs(li, di; ϵ_rel = 1e-6, CFL = 0.75/√2.1), kwargs = (iterMax = 50e3, nout = 100), 10 steps."""
+    from . import rheology as R
+
+    ni, li = (n, n), (1.0, 1.0)
+    grid = Geometry(ni, li, origin=(0.0, 0.0))
+    di = grid.di.center
+    η0, G0, εbg = 1.0, 1.0, 1.0
+    Gi = G0 / (6.0 - 4.0)
+    dt = η0 / G0 / 4.0
+    ϕ = 30
+    cosd = math.cos(math.radians(ϕ))
+    visc = R.LinearViscous(η=η0)
+    pl = R.DruckerPrager_regularised(C=1.6 / cosd, ϕ=ϕ, η_vp=8.0e-3, Ψ=0)
+    el_bg, el_inc = R.ConstantElasticity(G=G0, Kb=4), R.ConstantElasticity(G=Gi, Kb=4)
+    rheology = (R.SetMaterialParams(Phase=1, Density=R.ConstantDensity(ρ=0.0), Gravity=R.ConstantGravity(g=0.0),
+                                    CompositeRheology=R.CompositeRheology((visc, el_bg, pl)), Elasticity=el_bg),
+                R.SetMaterialParams(Phase=2, Density=R.ConstantDensity(ρ=0.0), Gravity=R.ConstantGravity(g=0.0),
+                                    CompositeRheology=R.CompositeRheology((visc, el_inc, pl)), Elasticity=el_inc))
+
+    def init_phases(x, y):  # test_shearband2D.jl:37-52
+        out = ((x[:, None] - 0.5) ** 2 + (y[None, :] - 0.5) ** 2) > 0.1 ** 2
+        r = np.zeros(out.shape + (2,), order="F")
+        r[..., 0], r[..., 1] = out, ~out
+        return r
+
+    xc, yc = grid.xci
+    xv, yv = grid.xvi
+    ratios = dict(center=init_phases(xc, yc), vertex=init_phases(xv, yv))
+    pt = PTStokesCoeffs(li, di, ϵ_rel=1.0e-6, CFL=0.75 / math.sqrt(2.1))
+    Vx = np.asfortranarray((xv * εbg)[:, None] * np.ones((1, n + 2)))
+    Vy = np.asfortranarray(np.ones((n + 2, 1)) * (-yv * εbg)[None, :])
+    flow_bcs = VelocityBoundaryConditions(free_slip=dict(left=True, right=True, top=True, bot=True),
+                                          no_slip=dict(left=False, right=False, top=False, bot=False))
+    fields = dict(Vx=Vx, Vy=Vy, T=np.zeros((n + 2, n + 2), order="F"))
+    return SimpleNamespace(ni=ni, li=li, di=di, grid=grid, igg=IGG(), pt_stokes=pt, flow_bcs=flow_bcs, dt=dt, fields=fields, rheology=rheology,
+                           ratios=ratios, nt=10, kwargs=dict(verbose=False, iterMax=50.0e3, nout=1.0e2, viscosity_cutoff=(-math.inf, math.inf)))

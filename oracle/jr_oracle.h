@@ -92,6 +92,27 @@ typedef struct {
     double *norm_Rx, *norm_Ry, *norm_Rz, *norm_divV;
 } orc_stokes_result;
 
+/* flat per-phase rheology row of the Stokes VC variants (lowered GeoParams MaterialParams):
+ * LinearViscous η, ConstantElasticity (G, Kb; Inf when absent / NaN / 0: rheology/GeoParams.jl:1-15),
+ * DruckerPrager[_regularised] (first plastic element wins, StressUpdate.jl:131-144), density law, expansivity. */
+typedef struct {
+    double eta;
+    double G, Kb;
+    int32_t has_pl, rho_kind;          /* rho_kind: 0 ConstantDensity, 1 PT_Density, 2 T_Density */
+    double C, sinphi, cosphi, sinpsi, eta_vp;
+    double rho0, alpha, beta, T0, P0;
+} orc_stokes_phase;
+
+/* extra inputs of the multiphase (VC) solves: rheology table, gravity of phase 1 (BuoyancyForces.jl:25,56),
+ * phase ratios [phase][node] at centres and vertices (2D) / xy, yz, xz edges (3D) */
+typedef struct {
+    int32_t nphase, g_scalar;          /* g_scalar: compute_gravity returned a Number → only the last ρg component is filled */
+    const orc_stokes_phase *phases;
+    double g[3];
+    const double *ph_center, *ph_vertex, *ph_xy, *ph_yz, *ph_xz;
+    double free_surface;               /* dt * free_surface factor of compute_V!/compute_Res! (2D), 0 when off */
+} orc_vc_inputs;
+
 const char *orc_field_name(int i);
 int orc_field_count(void);
 
@@ -114,6 +135,17 @@ int  orc_iterate3d_VA(const orc_fields *s, const orc_stokes_opts *o, int64_t nit
 /* loop pieces for multi-rank emulation: pre-loop maxloc, one PT iteration (no halo: the caller exchanges) */
 void orc_pre3d_VA(const orc_fields *s);
 void orc_iterate3d_VA_once(const orc_fields *s, const orc_stokes_opts *o);
+
+/* ---- 2D (oracle/stokes2d.c) ------------------------------------------------ */
+int  orc_solve2d_V2(const orc_fields *s, const orc_stokes_opts *o, orc_stokes_result *res);
+int  orc_iterate2d_V2(const orc_fields *s, const orc_stokes_opts *o, int64_t niter);
+int  orc_solve2d_VC(const orc_fields *s, const orc_stokes_opts *o, const orc_vc_inputs *vc, orc_stokes_result *res);
+/* niter iterations of the VC loop incl. its pre-loop initialisation, then (if finish) the exit kernels */
+int  orc_iterate2d_VC(const orc_fields *s, const orc_stokes_opts *o, const orc_vc_inputs *vc, int64_t niter, int finish);
+void orc_flow_bcs2(const orc_fields *s, const orc_stokes_opts *o, int displacement);
+void orc_viscosity2d(const orc_fields *s, const orc_stokes_opts *o, const orc_vc_inputs *vc, double nu);
+void orc_rhog2d(const orc_fields *s, const orc_vc_inputs *vc);
+void orc_tensor_invariant2d(double *II, const double *xx, const double *yy, const double *xy, int nx, int ny);
 
 /* norms (src/Utils.jl:698-701), interior slice 2:end-1 in every dim when interior!=0 */
 double orc_sumsq_interior(const double *A, int n1, int n2, int n3, int interior);

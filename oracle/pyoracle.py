@@ -119,6 +119,8 @@ def alloc_stokes(ni, init: dict | None = None) -> dict:
         d["wxy"] = z(*shapes["xy"])
         for nm in ("txx_v", "tyy_v", "txx_o_v", "tyy_o_v"):
             d[nm] = z(*v)
+    d["T"] = z(*(n + 2 for n in ni))      # args.T (ghosted) and args.P of the VC variants
+    d["Pargs"] = z(*c)
     if init:
         for k, a in init.items():
             assert k in d, k
@@ -303,3 +305,75 @@ def heatdiffusion_PT(slots, ni, opts, stokes_P=None, stokes_P0=None):
                                None if stokes_P0 is None else _dp(stokes_P0), C.byref(r))
     n = int(r.nhist)
     return dict(iter=int(r.iter), iter_count=ic[:n].copy(), norm_ResT=nr[:n].copy(), err=float(r.err))
+
+
+# ------------------------------------------------------------------------------------------------------------
+# 2D Stokes (oracle/stokes2d.c) and the multiphase (VC) inputs
+class StokesPhase(C.Structure):
+    _fields_ = [("eta", C.c_double), ("G", C.c_double), ("Kb", C.c_double), ("has_pl", C.c_int32), ("rho_kind", C.c_int32),
+                ("C", C.c_double), ("sinphi", C.c_double), ("cosphi", C.c_double), ("sinpsi", C.c_double), ("eta_vp", C.c_double),
+                ("rho0", C.c_double), ("alpha", C.c_double), ("beta", C.c_double), ("T0", C.c_double), ("P0", C.c_double)]
+
+
+class VcInputs(C.Structure):
+    _fields_ = [("nphase", C.c_int32), ("g_scalar", C.c_int32), ("phases", C.POINTER(StokesPhase)), ("g", C.c_double * 3),
+                ("ph_center", C.c_void_p), ("ph_vertex", C.c_void_p), ("ph_xy", C.c_void_p), ("ph_yz", C.c_void_p), ("ph_xz", C.c_void_p),
+                ("free_surface", C.c_double)]
+
+
+def vc_inputs(rows, g, ratios: dict, *, g_scalar=False, free_surface=0.0, Phase=StokesPhase, Inputs=VcInputs):
+    """rows: list of dicts with the StokesPhase fields; ratios: name -> column-major array [node..., phase]."""
+    arr = (Phase * len(rows))()
+    for i, r in enumerate(rows):
+        for k, v in r.items():
+            setattr(arr[i], k, v)
+    vc = Inputs()
+    vc.nphase, vc.g_scalar, vc.phases, vc.free_surface = len(rows), int(g_scalar), arr, float(free_surface)
+    for q in range(3):
+        vc.g[q] = float(g[q])
+    keep = [arr]
+    for nm in ("center", "vertex", "xy", "yz", "xz"):
+        a = ratios.get(nm)
+        if a is not None:
+            if isinstance(a, np.ndarray):
+                assert a.dtype == np.float64 and a.flags.f_contiguous, nm
+                setattr(vc, "ph_" + nm, a.ctypes.data)
+            else:
+                setattr(vc, "ph_" + nm, a)
+            keep.append(a)
+    vc._keep = keep
+    return vc
+
+
+def solve2d_V2(slots, ni, opts):
+    fs = make_fields(slots, ni)
+    h = Hist(int(opts.iterMax // max(opts.nout, 1)) + 3)
+    st = lib().orc_solve2d_V2(C.byref(fs), C.byref(opts), C.byref(h.res))
+    out = h.out()
+    out["status"] = st
+    return out
+
+
+def iterate2d_V2(slots, ni, opts, niter):
+    fs = make_fields(slots, ni)
+    return lib().orc_iterate2d_V2(C.byref(fs), C.byref(opts), C.c_int64(niter))
+
+
+def solve2d_VC(slots, ni, opts, vc):
+    fs = make_fields(slots, ni)
+    h = Hist(int(opts.iterMax // max(opts.nout, 1)) + 3)
+    st = lib().orc_solve2d_VC(C.byref(fs), C.byref(opts), C.byref(vc), C.byref(h.res))
+    out = h.out()
+    out["status"] = st
+    return out
+
+
+def iterate2d_VC(slots, ni, opts, vc, niter, finish=False):
+    fs = make_fields(slots, ni)
+    return lib().orc_iterate2d_VC(C.byref(fs), C.byref(opts), C.byref(vc), C.c_int64(niter), C.c_int(int(finish)))
+
+
+def tensor_invariant2d(xx, yy, xy):
+    II = np.zeros(xx.shape, order="F")
+    lib().orc_tensor_invariant2d(_dp(II), _dp(xx), _dp(yy), _dp(xy), C.c_int(xx.shape[0]), C.c_int(xx.shape[1]))
+    return II

@@ -1,0 +1,101 @@
+"""CPU oracle of the 2D Stokes PT loops pinned on the reference's goldens (no GPU).
+
+ - test/test_stokes_solcx.jl:26-43   (config 2 at 32²): 2D-V2 converges, err_evo1[end] < 1e-8
+ - test/test_shearband2D.jl:194-202  (config 3 at 32²): 2D-VC + Drucker-Prager, 10 steps: err < 1e-6,
+   extrema(τII) ≈ (1.5128689768248313, 1.6415759440014273) atol 1e-3, maximum(τxx) ≈ 1.6376258215356436 atol 1e-4
+"""
+import ctypes as C
+import math
+
+import numpy as np
+
+from justrelax_jl_b200 import rheology as R, setups
+from util import bc_flags
+
+
+def run_shearband(oracle, s):
+    d = oracle.alloc_stokes(s.ni, s.fields)
+    rows = R.lower_stokes(s.rheology)
+    vc = oracle.vc_inputs(rows, R.gravity_of(s.rheology), s.ratios)
+    kw = s.kwargs
+    opts = oracle.make_opts(s.pt_stokes, s.grid._di.center, s.dt, bc_flags(s.flow_bcs), s.ni, iterMax=kw["iterMax"], nout=kw["nout"],
+                            viscosity_cutoff=kw["viscosity_cutoff"])
+    fs = oracle.make_fields(d, s.ni)
+    # compute_viscosity!(stokes, phase_ratios, args, rheology, (-Inf, Inf)) with relaxation 1   test_shearband2D.jl:133-135
+    oracle.lib().orc_viscosity2d(C.byref(fs), C.byref(opts), C.byref(vc), C.c_double(1.0))
+    oracle.lib().orc_flow_bcs2(C.byref(fs), C.byref(opts), 0)
+    outs, txx_max = [], []
+    for _ in range(s.nt):
+        outs.append(oracle.solve2d_VC(d, s.ni, opts, vc))
+        txx_max.append(d["txx"].max())
+    return d, outs, txx_max
+
+
+def test_shearband2d_reference_golden(oracle):
+    s = setups.shearband2d(32)
+    d, outs, txx_max = run_shearband(oracle, s)
+    assert all(o["status"] == 0 for o in outs)
+    assert outs[-1]["err_evo1"][-1] < 1.0e-6
+    tII = oracle.tensor_invariant2d(d["txx"], d["tyy"], d["txy"])          # tensor_invariant!(stokes.τ)
+    assert abs(tII.min() - 1.5128689768248313) < 1.0e-3
+    assert abs(tII.max() - 1.6415759440014273) < 1.0e-3
+    assert abs(txx_max[-1] - 1.6376258215356436) < 1.0e-4
+    # plasticity was active
+    assert d["EII_pl"].max() > 0 and d["lam"].max() > 0
+
+
+def test_solcx_reference_golden(oracle):
+    s = setups.solcx2d(32, 32)
+    d = oracle.alloc_stokes(s.ni, s.fields)
+    opts = oracle.make_opts(s.pt_stokes, s.grid._di.center, s.dt, bc_flags(s.flow_bcs), s.ni, iterMax=s.kwargs["iterMax"], nout=s.kwargs["nout"])
+    fs = oracle.make_fields(d, s.ni)
+    oracle.lib().orc_flow_bcs2(C.byref(fs), C.byref(opts), 0)
+    out = oracle.solve2d_V2(d, s.ni, opts)
+    assert out["status"] == 0
+    assert out["err_evo1"][-1] < 1.0e-8
+    assert out["iter"] < s.kwargs["iterMax"]
+    for c in ("xx", "yy", "xy"):
+        assert np.array_equal(d["t" + c], d["t" + c + "_o"])
+
+
+def test_v2_iteration_matches_numpy_restatement(oracle):
+    """independent cross-check of the C oracle: one 2D-V2 iteration written with numpy slices"""
+    rng = np.random.default_rng(4)
+    nx, ny = 9, 7
+    ni = (nx, ny)
+    U = lambda *s: np.asfortranarray(rng.uniform(-1, 1, size=s))
+    f = dict(Vx=U(nx + 1, ny + 2), Vy=U(nx + 2, ny + 1), P=U(*ni), P0=U(*ni), Q=U(*ni) * 0.1, txx=U(*ni), tyy=U(*ni), txy=U(nx + 1, ny + 1),
+             txx_o=U(*ni), tyy_o=U(*ni), txy_o=U(nx + 1, ny + 1), eta=np.asfortranarray(10.0 ** rng.uniform(-2, 0, size=ni)),
+             G=np.asfortranarray(rng.uniform(0.5, 2, size=ni)), K=np.asfortranarray(rng.uniform(1, 4, size=ni)), rhogx=U(*ni), rhogy=U(*ni))
+    d = oracle.alloc_stokes(ni, f)
+    ref = {k: v.copy(order="F") for k, v in d.items()}
+    from justrelax_jl_b200.types import Geometry, PTStokesCoeffs
+    li = (1.0, 1.2)
+    grid = Geometry(ni, li)
+    pt = PTStokesCoeffs(li, grid.di.center)
+    dt = 0.6
+    flags = dict(free_slip=[1, 1, 0, 0, 1, 1], no_slip=[0] * 6, periodic=[0] * 6)
+    opts = oracle.make_opts(pt, grid._di.center, dt, flags, ni, iterMax=1, nout=1)
+    oracle.iterate2d_V2(d, ni, opts, 1)
+    _dx, _dy = grid._di.center
+    Vx, Vy, eta, G, K = ref["Vx"], ref["Vy"], ref["eta"], ref["G"], ref["K"]
+    ett = np.zeros(ni)
+    pe = np.pad(eta, 1, mode="edge")
+    for a in range(3):
+        for b in range(3):
+            ett = np.maximum(ett, pe[a:a + nx, b:b + ny]) if (a or b) else pe[a:a + nx, b:b + ny].copy()
+    divV = (Vx[1:, 1:-1] - Vx[:-1, 1:-1]) * _dx + (Vy[1:-1, 1:] - Vy[1:-1, :-1]) * _dy
+    psi = 1.0 / (1.0 / ett + 1.0 / (G * dt)) * pt.r / pt.θ_dτ
+    P = ((ref["P0"] / (K * dt) - divV + ref["Q"] / dt) * psi + ref["P"]) / (1 + psi / (K * dt))
+    exx = (Vx[1:, 1:-1] - Vx[:-1, 1:-1]) * _dx - divV / 3
+    exy = 0.5 * (_dy * (Vx[:, 1:] - Vx[:, :-1]) + _dx * (Vy[1:, :] - Vy[:-1, :]))
+    av = lambda A: 0.25 * (np.pad(A, 1, mode="edge")[:-1, :-1] + np.pad(A, 1, mode="edge")[1:, :-1] + np.pad(A, 1, mode="edge")[:-1, 1:] + np.pad(A, 1, mode="edge")[1:, 1:])
+    upd = lambda t, to, e, et, g: t + (1.0 / (pt.θ_dτ + et / (g * dt) + 1.0)) * (2 * et * e - (t - to) * et / (g * dt) - t)
+    txx, txy = upd(ref["txx"], ref["txx_o"], exx, eta, G), upd(ref["txy"], ref["txy_o"], exy, av(eta), av(G))
+    tol = lambda A: 1e-12 * np.abs(A).max()
+    assert np.allclose(d["etatau"], ett, rtol=0, atol=0)
+    assert np.allclose(d["P"], P, rtol=0, atol=tol(P)) and np.allclose(d["txx"], txx, rtol=0, atol=tol(txx)) and np.allclose(d["txy"], txy, rtol=0, atol=tol(txy))
+    Rx = (d["txx"][1:] - d["txx"][:-1]) * _dx + (d["txy"][1:-1, 1:] - d["txy"][1:-1, :-1]) * _dy - (d["P"][1:] - d["P"][:-1]) * _dx - 0.5 * (ref["rhogx"][1:] + ref["rhogx"][:-1])
+    assert np.allclose(d["Rx"], Rx, rtol=0, atol=tol(Rx))
+    Vxn = ref["Vx"][1:-1, 1:-1] + Rx * pt.ηdτ / (0.5 * (ett[1:] + ett[:-1]))
+    assert np.allclose(d["Vx"][1:-1, 1:-1], Vxn, rtol=0, atol=tol(Vxn))
