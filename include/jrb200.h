@@ -146,6 +146,50 @@ int jr_stokes3d_iterate_VA(jr_context *ctx, const jr_fields *s, const jr_stokes_
  *         box pitch PX, PY, PZ, lock-step slack}.  No reference counterpart (reporting only). */
 int jr_stokes3d_VA_plan_info(jr_context *ctx, int32_t info[8]);
 
+/* --- multiphase visco-elasto-plastic (VC) inputs ---------------------------------------------------------------
+ * One row of the flat Stokes rheology table, lowered from rheology::NTuple{N,MaterialParams} once per solve
+ * (SURVEY.md Appendix C): LinearViscous η; ConstantElasticity G, Kb (Inf when absent / NaN / 0:
+ * src/rheology/GeoParams.jl:1-15); the FIRST DruckerPrager[_regularised] element (src/rheology/StressUpdate.jl:131-144);
+ * Constant/PT_/T_Density.  Anything else must be rejected at lowering time (JR_ERR_UNSUPPORTED, no fallback). */
+typedef struct {
+    double eta;
+    double G, Kb;
+    int32_t has_pl, rho_kind;          /* rho_kind: 0 ConstantDensity, 1 PT_Density, 2 T_Density */
+    double C, sinphi, cosphi, sinpsi, eta_vp;
+    double rho0, alpha, beta, T0, P0;
+} jr_stokes_phase;
+
+/* rheology table (HOST pointer, nphase <= 8 rows), gravity of phase 1 (src/rheology/BuoyancyForces.jl:25,56),
+ * JustPIC PhaseRatios flattened to [phase][node] DEVICE arrays: centres + vertices (2D) / centres + xy, yz, xz edges (3D) */
+typedef struct {
+    int32_t nphase, g_scalar;          /* g_scalar: compute_gravity returned a Number → only the last ρg component is filled */
+    const jr_stokes_phase *phases;
+    double g[3];
+    const double *ph_center, *ph_vertex, *ph_xy, *ph_yz, *ph_xz;
+    double free_surface;               /* dt * free_surface of compute_V!/compute_Res! (2D, VelocityKernels.jl:134-180); 0 = off */
+} jr_vc_inputs;
+
+/* --- 2D Stokes ------------------------------------------------------------------------------------------------
+ * replaces JR2D.solve!(::CUDABackendTrait, stokes, pt_stokes, di, flow_bcs, ρg, G, K, dt, igg; kwargs)
+ * (src/ext/CUDA/2D.jl → src/stokes/Stokes2D.jl:181-325, variant 2D-V2) and the multiphase VEP
+ * solve!(stokes, pt_stokes, di, flow_bcs, ρg, phase_ratios, rheology, args, dt, igg; kwargs)
+ * (src/stokes/Stokes2D.jl:577-866, variant 2D-VC).  One fused sm_100a kernel per PT iteration. */
+int jr_stokes2d_solve_V2(jr_context *ctx, const jr_fields *s, const jr_stokes_opts *o, jr_stokes_result *res);
+int jr_stokes2d_iterate_V2(jr_context *ctx, const jr_fields *s, const jr_stokes_opts *o, int64_t niter, jr_stokes_result *res);
+int jr_stokes2d_solve_VC(jr_context *ctx, const jr_fields *s, const jr_stokes_opts *o, const jr_vc_inputs *vc, jr_stokes_result *res);
+/* pre-loop initialisation + exactly niter iterations (+ the exit kernels when finish != 0); λ, λv are exposed in the lam/lamv slots */
+int jr_stokes2d_iterate_VC(jr_context *ctx, const jr_fields *s, const jr_stokes_opts *o, const jr_vc_inputs *vc, int64_t niter, int finish,
+                           jr_stokes_result *res);
+/* flow_bcs!(stokes, bcs) 2D  src/boundaryconditions/BoundaryConditions.jl:65-100 (flags use slots left,right,top,bot = 0,1,4,5) */
+int jr_flow_bcs2d(jr_context *ctx, double *Ax, double *Ay, const int32_t n[3], const int32_t free_slip[6], const int32_t no_slip[6],
+                  const int32_t periodic[6]);
+/* compute_viscosity!(stokes, phase_ratios, args, rheology, cutoff; relaxation = nu)  src/rheology/Viscosity.jl:67-106,282-323 */
+int jr_compute_viscosity2d(jr_context *ctx, const jr_fields *s, const jr_stokes_opts *o, const jr_vc_inputs *vc, double nu);
+/* compute_ρg!(ρg, phase_ratios, rheology, args)  src/rheology/BuoyancyForces.jl:74-95 */
+int jr_compute_rhog2d(jr_context *ctx, const jr_fields *s, const jr_vc_inputs *vc);
+/* tensor_invariant!(II, xx, yy, xy_vertex)  src/stokes/StressKernels.jl:470-480 */
+int jr_tensor_invariant2d(jr_context *ctx, double *II, const double *xx, const double *yy, const double *xy, const int32_t n[3]);
+
 /* --- stand-alone kernels the reference exposes outside the loops ----------- */
 /* flow_bcs!(stokes, bcs)  src/ext/CUDA/3D.jl:195-218 → BoundaryConditions.jl:65-100 */
 int jr_flow_bcs3d(jr_context *ctx, double *Ax, double *Ay, double *Az, const int32_t n[3],

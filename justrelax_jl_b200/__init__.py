@@ -6,6 +6,6 @@ ThermalArrays, PTStokesCoeffs, boundary-condition and grid types) over the C ABI
 """
 from .types import (AbstractBackend, CPUBackend, B200Backend, CPUBackendTrait, B200BackendTrait, PTArray, backend, zeros,
                     to_host, StokesArrays, ThermalArrays, PTStokesCoeffs, VelocityBoundaryConditions,
-                    DisplacementBoundaryConditions, TemperatureBoundaryConditions, Geometry, IGG, legacy_uniform_grid)
+                    DisplacementBoundaryConditions, TemperatureBoundaryConditions, Geometry, IGG, legacy_uniform_grid, PhaseRatios)
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -127,6 +127,20 @@ class ThermalResult(C.Structure):
                 ("time_s", C.c_double), ("kernel_launches", C.c_int64)]
 
 
+class StokesPhase(C.Structure):
+    """jr_stokes_phase"""
+    _fields_ = [("eta", C.c_double), ("G", C.c_double), ("Kb", C.c_double), ("has_pl", C.c_int32), ("rho_kind", C.c_int32),
+                ("C", C.c_double), ("sinphi", C.c_double), ("cosphi", C.c_double), ("sinpsi", C.c_double), ("eta_vp", C.c_double),
+                ("rho0", C.c_double), ("alpha", C.c_double), ("beta", C.c_double), ("T0", C.c_double), ("P0", C.c_double)]
+
+
+class VcInputs(C.Structure):
+    """jr_vc_inputs"""
+    _fields_ = [("nphase", C.c_int32), ("g_scalar", C.c_int32), ("phases", C.POINTER(StokesPhase)), ("g", C.c_double * 3),
+                ("ph_center", C.c_void_p), ("ph_vertex", C.c_void_p), ("ph_xy", C.c_void_p), ("ph_yz", C.c_void_p), ("ph_xz", C.c_void_p),
+                ("free_surface", C.c_double)]
+
+
 ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)
 
 
@@ -149,6 +163,15 @@ def _declare(L):
     L.jr_stokes3d_solve_VA.argtypes = [vp, vp, C.POINTER(StokesOpts), C.POINTER(StokesResult)]
     L.jr_stokes3d_iterate_VA.argtypes = [vp, vp, C.POINTER(StokesOpts), C.c_int64, C.POINTER(StokesResult)]
     L.jr_stokes3d_VA_plan_info.argtypes = [vp, i32p]
+    so, sr, vc = C.POINTER(StokesOpts), C.POINTER(StokesResult), C.POINTER(VcInputs)
+    L.jr_stokes2d_solve_V2.argtypes = [vp, vp, so, sr]
+    L.jr_stokes2d_iterate_V2.argtypes = [vp, vp, so, C.c_int64, sr]
+    L.jr_stokes2d_solve_VC.argtypes = [vp, vp, so, vc, sr]
+    L.jr_stokes2d_iterate_VC.argtypes = [vp, vp, so, vc, C.c_int64, C.c_int, sr]
+    L.jr_flow_bcs2d.argtypes = [vp, vp, vp, i32p, i32p, i32p, i32p]
+    L.jr_compute_viscosity2d.argtypes = [vp, vp, so, vc, C.c_double]
+    L.jr_compute_rhog2d.argtypes = [vp, vp, vc]
+    L.jr_tensor_invariant2d.argtypes = [vp, vp, vp, vp, vp, i32p]
     L.jr_heatdiffusion_PT.argtypes = [vp, C.POINTER(ThermalFields), C.POINTER(ThermalOpts), vp, vp, C.POINTER(ThermalResult)]
     L.jr_thermal_iterate.argtypes = [vp, C.POINTER(ThermalFields), C.POINTER(ThermalOpts), C.c_int64, C.POINTER(ThermalResult)]
     L.jr_thermal_bcs.argtypes = [vp, vp, C.c_int32, i32p, C.POINTER(ThermalOpts)]

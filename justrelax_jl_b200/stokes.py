@@ -19,8 +19,9 @@ from typing import Optional
 import numpy as np
 
 from . import _abi
+from . import rheology as _rheology
 from .types import (B200BackendTrait, CPUBackendTrait, Geometry, IGG, StokesArrays, VelocityBoundaryConditions,
-                    DisplacementBoundaryConditions, AbstractFlowBoundaryConditions, backend, data_ptr, is_device_array,
+                    DisplacementBoundaryConditions, AbstractFlowBoundaryConditions, PhaseRatios, backend, data_ptr, is_device_array,
                     legacy_uniform_grid)
 
 _ctx_cache = {}
@@ -129,7 +130,26 @@ def va_slots(stokes: StokesArrays, ρg, K, G) -> dict:
     return d
 
 
-def solve_(stokes: StokesArrays, pt_stokes, grid, flow_bcs, ρg, K, G, dt, igg: Optional[IGG] = None, *, kwargs=None):
+def solve_(stokes: StokesArrays, pt_stokes, grid, flow_bcs, ρg, *rest, kwargs=None):
+    """solve!(stokes, pt_stokes, grid|di, flow_bcs, ρg, …) — every Stokes variant of the hot path, selected like the reference's
+    method table by dimension and argument types:
+
+      3D-VA  solve_(stokes, pt, grid, bcs, ρg, K, G, dt, igg)                          Stokes3D.jl:18-41
+      2D-V2  solve_(stokes, pt, di,   bcs, ρg, G, K, dt, igg)                          Stokes2D.jl:181-196   (G before K in 2D)
+      2D-VC  solve_(stokes, pt, di,   bcs, ρg, phase_ratios, rheology, args, dt, igg)  Stokes2D.jl:577-599
+    """
+    if rest and isinstance(rest[0], PhaseRatios):
+        if len(stokes.ni) == 2:
+            return _solve2d_VC(stokes, pt_stokes, grid, flow_bcs, ρg, *rest, kwargs=kwargs)
+        from .stokes3d_vc import solve3d_VC_
+
+        return solve3d_VC_(stokes, pt_stokes, grid, flow_bcs, ρg, *rest, kwargs=kwargs)
+    if len(stokes.ni) == 2:
+        return _solve2d_V2(stokes, pt_stokes, grid, flow_bcs, ρg, *rest, kwargs=kwargs)
+    return _solve3d_VA(stokes, pt_stokes, grid, flow_bcs, ρg, *rest, kwargs=kwargs)
+
+
+def _solve3d_VA(stokes: StokesArrays, pt_stokes, grid, flow_bcs, ρg, K, G, dt, igg: Optional[IGG] = None, *, kwargs=None):
     """3D visco-elastic Stokes solve with K, G arrays (variant 3D-VA).
 
     Reference: solve!(stokes, pt_stokes, grid::Geometry{3}|di, flow_bcs, ρg, K, G, dt, igg; kwargs)
@@ -144,8 +164,6 @@ def solve_(stokes: StokesArrays, pt_stokes, grid, flow_bcs, ρg, K, G, dt, igg: 
                            "backend; the CPU solver is JustRelax.jl's own. No CPU fallback.")
     if not isinstance(flow_bcs, AbstractFlowBoundaryConditions):
         raise TypeError(f"Unknown boundary conditions type: {type(flow_bcs)}")  # types/displacement.jl:68-70
-    if len(stokes.ni) != 3:
-        raise NotImplementedError("2D solve_ with K,G arrays is provided by stokes2d.solve_")
     if isinstance(flow_bcs, DisplacementBoundaryConditions):
         raise NotImplementedError("DisplacementBoundaryConditions are outside the supported subset (SURVEY §8f-3)")
     for a in (*ρg, K, G):
@@ -195,8 +213,11 @@ def flow_bcs_(stokes, bcs: AbstractFlowBoundaryConditions):
         raise RuntimeError("flow_bcs_: host arrays; this package only provides the B200 backend")
     A = stokes.U if isinstance(bcs, DisplacementBoundaryConditions) else stokes.V
     comps = list(A)
-    if len(stokes.ni) != 3:
-        raise NotImplementedError("2D flow_bcs_ lives in stokes2d")
+    if len(stokes.ni) == 2:
+        _abi.check(_abi.lib().jr_flow_bcs2d(context(), data_ptr(comps[0]), data_ptr(comps[1]), _abi.i32x(list(stokes.ni) + [1]),
+                                             _abi.i32x(bcs.flags("free_slip")), _abi.i32x(bcs.flags("no_slip")),
+                                             _abi.i32x(bcs.flags("periodic"))))
+        return
     _abi.check(_abi.lib().jr_flow_bcs3d(context(), data_ptr(comps[0]), data_ptr(comps[1]), data_ptr(comps[2]),
                                          _abi.i32x(stokes.ni), _abi.i32x(bcs.flags("free_slip")),
                                          _abi.i32x(bcs.flags("no_slip")), _abi.i32x(bcs.flags("periodic"))))
@@ -237,3 +258,170 @@ def sumsq_interior(A, interior: bool = True) -> float:
 
 def norm_interior(A, interior: bool = True) -> float:
     return math.sqrt(sumsq_interior(A, interior))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# 2D variants
+def _common_checks(stokes, flow_bcs, arrays):
+    if isinstance(backend(stokes), CPUBackendTrait):
+        raise RuntimeError("solve_: StokesArrays live on the host (CPUBackend). This package only provides the B200 "
+                           "backend; the CPU solver is JustRelax.jl's own. No CPU fallback.")
+    if not isinstance(flow_bcs, AbstractFlowBoundaryConditions):
+        raise TypeError(f"Unknown boundary conditions type: {type(flow_bcs)}")
+    if isinstance(flow_bcs, DisplacementBoundaryConditions):
+        raise NotImplementedError("DisplacementBoundaryConditions are outside the supported subset (SURVEY §8f-3)")
+    for a in arrays:
+        if a is not None and not is_device_array(a):
+            raise ValueError("array arguments must be B200 arrays (use PTArray(B200Backend)(x))")
+
+
+def _print_hist2(out, igg, verbose):
+    if verbose and igg.me == 0:
+        for c in range(len(out.err_evo1)):
+            print("Iteration = %d, err = %1.3e [norm_Rx=%1.3e, norm_Ry=%1.3e, norm_∇V=%1.3e]" % (
+                out.err_evo2[c], out.err_evo1[c], out.norm_Rx[c], out.norm_Ry[c], out.norm_divV[c]))
+
+
+def _solve2d_V2(stokes, pt_stokes, di, flow_bcs, ρg, G, K, dt, igg: Optional[IGG] = None, *, kwargs=None):
+    """2D visco-elastic solve with G, K arrays (variant 2D-V2) — src/stokes/Stokes2D.jl:181-325."""
+    kw = dict(iterMax=10e3, nout=500, b_width=(4, 4, 1), verbose=True)
+    kw.update(kwargs or {})
+    _common_checks(stokes, flow_bcs, (*ρg, G, K))
+    igg = igg or IGG()
+    grid = _grid_of(stokes, di, igg)
+    opts = build_opts(pt_stokes, grid._di.center, dt, flow_bcs, igg.n_g(stokes.ni), iterMax=kw["iterMax"], nout=kw["nout"])
+    fs = build_fields(va_slots(stokes, ρg, K, G), stokes.ni)
+    hist = _Hist(int(opts.iterMax // max(opts.nout, 1)) + 3, _abi.StokesResult)
+    st = _abi.lib().jr_stokes2d_solve_V2(context(), C.byref(fs), C.byref(opts), C.byref(hist.res))
+    if st == _abi.JR_ERR_NAN:
+        raise RuntimeError("NaN(s)")
+    _abi.check(st)
+    out = hist.named(2)
+    _print_hist2(out, igg, kw.get("verbose"))
+    return out
+
+
+def iterate2d_V2_(stokes, pt_stokes, di, flow_bcs, ρg, G, K, dt, niter: int, igg: Optional[IGG] = None):
+    """exactly `niter` PT iterations of variant 2D-V2 (benchmark / fixed-iteration parity)"""
+    igg = igg or IGG()
+    grid = _grid_of(stokes, di, igg)
+    opts = build_opts(pt_stokes, grid._di.center, dt, flow_bcs, igg.n_g(stokes.ni), iterMax=niter, nout=max(niter, 1))
+    fs = build_fields(va_slots(stokes, ρg, K, G), stokes.ni)
+    res = _abi.StokesResult()
+    _abi.check(_abi.lib().jr_stokes2d_iterate_V2(context(), C.byref(fs), C.byref(opts), int(niter), C.byref(res)))
+    return SimpleNamespace(iter=int(res.iter), time=float(res.time_s), kernel_launches=int(res.kernel_launches))
+
+
+def vc_inputs(rheology, phase_ratios: PhaseRatios, *, free_surface: float = 0.0):
+    """lower rheology::NTuple{N,MaterialParams} to the flat table (raises UnsupportedRheology outside the subset) and bind the
+    phase-ratio arrays → jr_vc_inputs"""
+    rows = _rheology.lower_stokes(rheology)
+    arr = (_abi.StokesPhase * len(rows))()
+    for i, r in enumerate(rows):
+        for k, v in r.items():
+            setattr(arr[i], k, v)
+    vc = _abi.VcInputs()
+    vc.nphase, vc.g_scalar, vc.phases, vc.free_surface = len(rows), 0, arr, float(free_surface)
+    g = _rheology.gravity_of(rheology)
+    for q in range(3):
+        vc.g[q] = float(g[q])
+    for nm in ("center", "vertex", "xy", "yz", "xz"):
+        a = getattr(phase_ratios, nm, None)
+        if a is not None:
+            if not is_device_array(a):
+                raise ValueError("phase ratios must be B200 arrays")
+            if a.shape[-1] != len(rows):
+                raise ValueError(f"phase_ratios.{nm} holds {a.shape[-1]} phases, rheology has {len(rows)}")
+            setattr(vc, "ph_" + nm, data_ptr(a))
+    vc._keep = (arr, phase_ratios)
+    return vc
+
+
+def vc_slots(stokes, ρg, args) -> dict:
+    d = stokes.slots()
+    d["rhogx"], d["rhogy"] = ρg[0], ρg[1]
+    if len(ρg) > 2:
+        d["rhogz"] = ρg[2]
+    T, P = (args.get("T"), args.get("P")) if isinstance(args, dict) else (getattr(args, "T", None), getattr(args, "P", None))
+    if T is not None:
+        d["T"] = T
+    if P is not None:
+        d["Pargs"] = P
+    return d
+
+
+def _vc_opts(stokes, pt_stokes, grid, flow_bcs, dt, igg, kw):
+    return build_opts(pt_stokes, grid._di.center, dt, flow_bcs, igg.n_g(stokes.ni), iterMax=kw["iterMax"], nout=kw["nout"],
+                      viscosity_relaxation=kw["viscosity_relaxation"], λ_relaxation=kw["λ_relaxation"],
+                      viscosity_cutoff=kw["viscosity_cutoff"], iterMin=kw["iterMin"])
+
+
+def _solve2d_VC(stokes, pt_stokes, di, flow_bcs, ρg, phase_ratios, rheology, args, dt, igg: Optional[IGG] = None, *, kwargs=None):
+    """2D multiphase visco-elasto-plastic solve (variant 2D-VC) — src/stokes/Stokes2D.jl:577-866."""
+    kw = dict(iterMax=50e3, iterMin=1e2, viscosity_relaxation=1e-2, λ_relaxation=0.2, free_surface=False, nout=500, b_width=(4, 4, 0),
+              verbose=True, viscosity_cutoff=(-math.inf, math.inf), strain_increment=False)
+    kw.update(kwargs or {})
+    if kw["strain_increment"]:
+        raise NotImplementedError("strain_increment = true (Δε form) is outside the supported subset (SURVEY §8f-3)")
+    _common_checks(stokes, flow_bcs, ρg)
+    igg = igg or IGG()
+    grid = _grid_of(stokes, di, igg)
+    opts = _vc_opts(stokes, pt_stokes, grid, flow_bcs, dt, igg, kw)
+    vc = vc_inputs(rheology, phase_ratios, free_surface=float(dt) * float(kw["free_surface"]) if kw["free_surface"] else 0.0)
+    fs = build_fields(vc_slots(stokes, ρg, args), stokes.ni)
+    hist = _Hist(int(opts.iterMax // max(opts.nout, 1)) + 3, _abi.StokesResult)
+    st = _abi.lib().jr_stokes2d_solve_VC(context(), C.byref(fs), C.byref(opts), C.byref(vc), C.byref(hist.res))
+    if st == _abi.JR_ERR_NAN:
+        raise RuntimeError("NaN(s)")  # Stokes2D.jl:836
+    _abi.check(st)
+    out = hist.named(2)
+    _print_hist2(out, igg, kw.get("verbose"))
+    return out
+
+
+def iterate2d_VC_(stokes, pt_stokes, di, flow_bcs, ρg, phase_ratios, rheology, args, dt, niter: int, igg: Optional[IGG] = None, *, finish=False,
+                  kwargs=None):
+    """pre-loop initialisation + exactly `niter` iterations of variant 2D-VC (+ the exit kernels when finish)"""
+    kw = dict(iterMax=niter, iterMin=0, viscosity_relaxation=1e-2, λ_relaxation=0.2, free_surface=False, nout=max(niter, 1),
+              viscosity_cutoff=(-math.inf, math.inf))
+    kw.update(kwargs or {})
+    igg = igg or IGG()
+    grid = _grid_of(stokes, di, igg)
+    opts = _vc_opts(stokes, pt_stokes, grid, flow_bcs, dt, igg, kw)
+    vc = vc_inputs(rheology, phase_ratios, free_surface=float(dt) * float(kw["free_surface"]) if kw["free_surface"] else 0.0)
+    fs = build_fields(vc_slots(stokes, ρg, args), stokes.ni)
+    res = _abi.StokesResult()
+    _abi.check(_abi.lib().jr_stokes2d_iterate_VC(context(), C.byref(fs), C.byref(opts), C.byref(vc), int(niter), int(finish), C.byref(res)))
+    return SimpleNamespace(iter=int(res.iter), time=float(res.time_s), kernel_launches=int(res.kernel_launches))
+
+
+def compute_viscosity_(stokes, phase_ratios, args, rheology, cutoff=(-math.inf, math.inf), *, relaxation=1.0):
+    """compute_viscosity!(stokes, phase_ratios, args, rheology, cutoff; relaxation) — src/rheology/Viscosity.jl:67-106."""
+    if len(stokes.ni) != 2:
+        from .stokes3d_vc import compute_viscosity3d_
+
+        return compute_viscosity3d_(stokes, phase_ratios, args, rheology, cutoff, relaxation=relaxation)
+    vc = vc_inputs(rheology, phase_ratios)
+    o = _abi.StokesOpts()
+    o.visc_cutoff_lo, o.visc_cutoff_hi = float(cutoff[0]), float(cutoff[1])
+    fs = build_fields(vc_slots(stokes, (stokes.P, stokes.P), args), stokes.ni)
+    _abi.check(_abi.lib().jr_compute_viscosity2d(context(), C.byref(fs), C.byref(o), C.byref(vc), float(relaxation)))
+
+
+def compute_ρg_(ρg, phase_ratios, rheology, args, stokes):
+    """compute_ρg!(ρg, phase_ratios, rheology, args) — src/rheology/BuoyancyForces.jl:74-95 (stokes only supplies the grid size)."""
+    if len(stokes.ni) != 2:
+        from .stokes3d_vc import compute_rhog3d_
+
+        return compute_rhog3d_(ρg, phase_ratios, rheology, args, stokes)
+    vc = vc_inputs(rheology, phase_ratios)
+    fs = build_fields(vc_slots(stokes, ρg, args), stokes.ni)
+    _abi.check(_abi.lib().jr_compute_rhog2d(context(), C.byref(fs), C.byref(vc)))
+
+
+def tensor_invariant_(T, ni):
+    """tensor_invariant!(A::SymmetricTensor) — src/stokes/StressKernels.jl:442-480 (2D)."""
+    if len(ni) != 2:
+        raise NotImplementedError
+    _abi.check(_abi.lib().jr_tensor_invariant2d(context(), data_ptr(T.II), data_ptr(T.xx), data_ptr(T.yy), data_ptr(T.xy),
+                                                 _abi.i32x(list(ni) + [1])))

@@ -442,3 +442,41 @@ class ThermalArrays:
             nx, ny, nz = ni
             self.qTx, self.qTy, self.qTz = z(nx + 1, ny, nz), z(nx, ny + 1, nz), z(nx, ny, nz + 1)
             self.qTx2, self.qTy2, self.qTz2 = z(nx + 1, ny, nz), z(nx, ny + 1, nz), z(nx, ny, nz + 1)
+
+
+# ----------------------------------------------------------------------------- phase ratios
+class PhaseRatios:
+    """JustPIC.PhaseRatios as the B200 backend takes it: one array per staggered location of shape (nodes..., nphases),
+    column-major, i.e. [phase][node] in memory (the CellArray layout flattened).  2D: center, vertex (+ Vx, Vy
+    for the thermal solver); 3D: center, vertex, xy, yz, xz (+ Vx, Vy, Vz).  PhaseRatios(backend, nphases, ni) —
+    src/phases/PhaseRatios.jl / JustPIC — allocates zeros; `from_arrays` wraps existing host/device arrays."""
+
+    _names = ("center", "vertex", "xy", "yz", "xz", "Vx", "Vy", "Vz")
+
+    def __init__(self, backend_t=None, nphases: int = 1, ni: Sequence[int] = ()):
+        for nm in self._names:
+            setattr(self, nm, None)
+        self.nphases = int(nphases)
+        if backend_t is None or not ni:
+            return
+        ni = tuple(int(n) for n in ni)
+        nd = len(ni)
+        shp = dict(center=ni, vertex=tuple(n + 1 for n in ni))
+        for a, nm in enumerate(("Vx", "Vy", "Vz")[:nd]):
+            shp[nm] = tuple(n + (1 if b == a else 0) for b, n in enumerate(ni))
+        if nd == 3:
+            nx, ny, nz = ni
+            shp.update(xy=(nx + 1, ny + 1, nz), yz=(nx, ny + 1, nz + 1), xz=(nx + 1, ny, nz + 1))
+        for nm, sh in shp.items():
+            setattr(self, nm, zeros(backend_t, *sh, self.nphases))
+
+    @classmethod
+    def from_arrays(cls, backend_t, **arrays):
+        pr = cls()
+        for nm, a in arrays.items():
+            if nm not in cls._names:
+                raise KeyError(nm)
+            setattr(pr, nm, None if a is None else PTArray(backend_t)(a))
+            if a is not None:
+                pr.nphases = int(a.shape[-1])
+        return pr
