@@ -228,3 +228,167 @@ def shearband2d(n=32):
     fields = dict(Vx=Vx, Vy=Vy, T=np.zeros((n + 2, n + 2), order="F"))
     return SimpleNamespace(ni=ni, li=li, di=di, grid=grid, igg=IGG(), pt_stokes=pt, flow_bcs=flow_bcs, dt=dt, fields=fields, rheology=rheology,
                            ratios=ratios, nt=10, kwargs=dict(verbose=False, iterMax=50.0e3, nout=1.0e2, viscosity_cutoff=(-math.inf, math.inf)))
+
+
+# ------------------------------------------------------------------------------------------------------------
+def _onehot(mask_list):
+    """stack boolean masks into a ratio array (nodes..., nphases), column-major"""
+    r = np.zeros(mask_list[0].shape + (len(mask_list),), order="F")
+    for p, m in enumerate(mask_list):
+        r[..., p] = m
+    return r
+
+
+def _stag_coords3(grid):
+    """node coordinates of the four 3D phase-ratio locations (JustPIC PhaseRatios: center, xy, yz, xz)"""
+    (xc, yc, zc), (xv, yv, zv) = grid.xci, grid.xvi
+    return dict(center=(xc, yc, zc), xy=(xv, yv, zc), yz=(xc, yv, zv), xz=(xv, yc, zv), vertex=(xv, yv, zv))
+
+
+def shearband3d(n=16):
+    """3D shear band — test/test_shearband3D_MPI.jl:75-210 (variant 3D-VC): unit cube, two phases (matrix G = 1, spherical inclusion
+    r = 0.1 with G = 0.5; ν = 0.5 ⇒ Kb = Inf), η = 1, DruckerPrager_regularised(C = 1.6/cosd(30), ϕ = 30, η_vp = 1.25e-2, Ψ = 0),
+    dt = 0.25, Vx = x εbg, Vz = −z εbg, free slip, PTStokesCoeffs(li, di; ϵ_rel = 1e-5, Re = 3, r = 0.7, CFL = 0.9/√3.1),
+    kwargs = (iterMax = 150e3, nout = 1e3).  Phase ratios are sampled at the staggered nodes (grid-based phases) instead of from particles."""
+    from . import rheology as R
+
+    ni, li = (n, n, n), (1.0, 1.0, 1.0)
+    grid = Geometry(ni, li, origin=(0.0, 0.0, 0.0))
+    di = grid.di.center
+    η0, G0, εbg = 1.0, 1.0, 1.0
+    Gi = G0 / (6.0 - 4.0)
+    dt = η0 / G0 / 4.0
+    cosd = math.cos(math.radians(30))
+    visc = R.LinearViscous(η=η0)
+    pl = R.DruckerPrager_regularised(C=1.6 / cosd, ϕ=30, η_vp=1.25e-2, Ψ=0)
+    el_bg, el_inc = R.ConstantElasticity(G=G0, ν=0.5), R.ConstantElasticity(G=Gi, ν=0.5)
+    rheology = (R.SetMaterialParams(Phase=1, Density=R.ConstantDensity(ρ=0.0), Gravity=R.ConstantGravity(g=0.0),
+                                    CompositeRheology=R.CompositeRheology((visc, el_bg, pl)), Elasticity=el_bg),
+                R.SetMaterialParams(Phase=2, Density=R.ConstantDensity(ρ=0.0), Gravity=R.ConstantGravity(g=0.0),
+                                    CompositeRheology=R.CompositeRheology((visc, el_inc, pl)), Elasticity=el_inc))
+    ratios = {}
+    for nm, (x, y, z) in _stag_coords3(grid).items():
+        out = ((x[:, None, None] - 0.5) ** 2 + (y[None, :, None] - 0.5) ** 2 + (z[None, None, :] - 0.5) ** 2) > 0.1 ** 2
+        ratios[nm] = _onehot([out, ~out])
+    pt = PTStokesCoeffs(li, di, ϵ_rel=1.0e-5, Re=3.0, r=0.7, CFL=0.9 / math.sqrt(3.1))
+    xv, yv, zv = grid.xvi
+    Vx = np.asfortranarray(np.broadcast_to((xv * εbg)[:, None, None], (n + 1, n + 2, n + 2)).copy())
+    Vz = np.asfortranarray(np.broadcast_to((-zv * εbg)[None, None, :], (n + 2, n + 2, n + 1)).copy())
+    flow_bcs = VelocityBoundaryConditions(free_slip=dict(left=True, right=True, top=True, bot=True, back=True, front=True),
+                                          no_slip=dict(left=False, right=False, top=False, bot=False, back=False, front=False))
+    fields = dict(Vx=Vx, Vz=Vz, T=np.zeros((n + 2,) * 3, order="F"))
+    return SimpleNamespace(ni=ni, li=li, di=di, grid=grid, igg=IGG(), pt_stokes=pt, flow_bcs=flow_bcs, dt=dt, fields=fields, rheology=rheology,
+                           ratios=ratios, nt=3, kwargs=dict(verbose=False, iterMax=150.0e3, nout=1.0e3, viscosity_cutoff=(-math.inf, math.inf)))
+
+
+def convection3d(nx=32, ny=32, nz=32, *, igg: IGG | None = None, plastic=True):
+    """Config 5 — 3D thermal convection with grid-based phases, modelled on miniapps/convection/RisingBlob3D/Blob3D.jl:132-201,
+    213-300: three phases — crust (LinearViscous + ConstantElasticity + DruckerPrager_regularised, PT_Density),
+    a hot low-density blob (LinearViscous + ConstantElasticity, PT_Density) and a weak top layer (LinearViscous, ConstantDensity) —
+    ConstantHeatCapacity / ConstantConductivity per phase, free slip, T fixed at top and bottom, no flux on the sides.
+    Deviations from the miniapp (stated in DESIGN.md): non-dimensional O(1) parameters instead of GEO_units scaling, no
+    NonLinearSoftening / latent heat / shear heating, phases sampled on the staggered grid instead of from particles.
+    Returns Stokes (3D-VC) and thermal (rheology form with phase ratios) inputs for one coupled time step."""
+    from . import rheology as R
+    from .types import TemperatureBoundaryConditions
+
+    igg = igg or IGG()
+    ni, li = (nx, ny, nz), (1.0, 1.0, 1.0)
+    grid = Geometry(ni, li, origin=(0.0, 0.0, -1.0), igg=igg)
+    di = grid.di.center
+    cosd = math.cos(math.radians(30))
+    pl = R.DruckerPrager_regularised(C=2.0 / cosd, ϕ=30, η_vp=1.0e-2, Ψ=0)
+    el = R.ConstantElasticity(G=10.0, ν=0.25)
+    el_blob = R.ConstantElasticity(G=5.0, ν=0.25)
+    crust = (R.LinearViscous(η=1.0), el, pl) if plastic else (R.LinearViscous(η=1.0), el)
+    rheology = (
+        R.SetMaterialParams(Phase=1, Density=R.PT_Density(ρ0=1.0, α=3.0e-2, β=1.0e-3, T0=0.0, P0=0.0), HeatCapacity=R.ConstantHeatCapacity(Cp=1.0),
+                            Conductivity=R.ConstantConductivity(k=1.0), CompositeRheology=R.CompositeRheology(crust),
+                            Gravity=R.ConstantGravity(g=10.0), Elasticity=el),
+        R.SetMaterialParams(Phase=2, Density=R.PT_Density(ρ0=0.9, α=3.0e-2, β=1.0e-3, T0=0.0, P0=0.0), HeatCapacity=R.ConstantHeatCapacity(Cp=1.0),
+                            Conductivity=R.ConstantConductivity(k=0.5), CompositeRheology=R.CompositeRheology((R.LinearViscous(η=0.1), el_blob)),
+                            Gravity=R.ConstantGravity(g=10.0), Elasticity=el_blob),
+        R.SetMaterialParams(Phase=3, Density=R.ConstantDensity(ρ=0.01), HeatCapacity=R.ConstantHeatCapacity(Cp=1.0),
+                            Conductivity=R.ConstantConductivity(k=5.0), CompositeRheology=R.CompositeRheology((R.LinearViscous(η=0.01),)),
+                            Gravity=R.ConstantGravity(g=10.0)),
+    )
+
+    def phase_masks(x, y, z):
+        X, Y, Z = x[:, None, None], y[None, :, None], z[None, None, :]
+        air = np.broadcast_to(Z > -0.1, (x.size, y.size, z.size))
+        blob = (((X - 0.5) ** 2 + (Y - 0.5) ** 2 + (Z + 0.6) ** 2) <= 0.15 ** 2) & ~air
+        return [~air & ~blob, blob, air]
+
+    locs = _stag_coords3(grid)
+    (xc, yc, zc), (xv, yv, zv) = grid.xci, grid.xvi
+    locs.update(Vx=(xv, yc, zc), Vy=(xc, yv, zc), Vz=(xc, yc, zv))
+    ratios = {nm: _onehot(phase_masks(*xyz)) for nm, xyz in locs.items()}
+    # temperature (ghosted, ni.+2): conductive profile 0 (top) … 1 (bottom) + blob anomaly; ghost cells by edge copy
+    Tc = (-zc)[None, None, :] * np.ones((nx, ny, 1))
+    Tc = Tc + 0.2 * ratios["center"][..., 1]
+    T = np.asfortranarray(np.pad(Tc, 1, mode="edge"))
+    thermal_bc = TemperatureBoundaryConditions(no_flux=dict(left=True, right=True, front=True, back=True, top=False, bot=False),
+                                               constant_value=dict(left=False, right=False, front=False, back=False, top=0.0, bot=1.0))
+    flow_bcs = VelocityBoundaryConditions(free_slip=dict(left=True, right=True, top=True, bot=True, back=True, front=True),
+                                          no_slip=dict(left=False, right=False, top=False, bot=False, back=False, front=False))
+    pt = PTStokesCoeffs(li, di, ϵ_rel=1.0e-5, CFL=0.9 / math.sqrt(3.1))
+    fields = dict(T=T)
+    return SimpleNamespace(ni=ni, li=li, di=di, grid=grid, igg=igg, pt_stokes=pt, flow_bcs=flow_bcs, thermal_bc=thermal_bc, dt=0.05, fields=fields,
+                           rheology=rheology, ratios=ratios, T=T,
+                           kwargs=dict(verbose=False, iterMax=150.0e3, nout=1.0e3, viscosity_cutoff=(1.0e-3, 1.0e3)),
+                           thermal_kwargs=dict(iterMax=150.0e3, nout=1.0e3, verbose=False))
+
+
+def random_vc3d(ni, nphase=3, seed=20261017, *, dt=0.4, mixed=True):
+    """Seeded random state for kernel-level parity fuzzing of variant 3D-VC: V, τ ~ U(−1,1), P ~ U(0,1), η ~ 10^U(−2,0),
+    phase ratios Dirichlet(1,…) with exact zeros and ones mixed in; phases: plastic + compressible, elastic only, viscous only."""
+    from . import rheology as R
+
+    rng = np.random.default_rng(seed)
+    nx, ny, nz = ni
+    U = lambda *s: np.asfortranarray(rng.uniform(-1.0, 1.0, size=s))
+    cshape = dict(center=ni, xy=(nx + 1, ny + 1, nz), yz=(nx, ny + 1, nz + 1), xz=(nx + 1, ny, nz + 1))
+    f = dict(Vx=U(nx + 1, ny + 2, nz + 2), Vy=U(nx + 2, ny + 1, nz + 2), Vz=U(nx + 2, ny + 2, nz + 1),
+             P=np.asfortranarray(rng.uniform(0, 1, size=ni)), Q=np.asfortranarray(rng.uniform(-0.1, 0.1, size=ni)),
+             eta=np.asfortranarray(10.0 ** rng.uniform(-2, 0, size=ni)), EII_pl=np.asfortranarray(rng.uniform(0, 0.1, size=ni)),
+             T=np.asfortranarray(rng.uniform(0, 1, size=(nx + 2, ny + 2, nz + 2))), rhogx=U(*ni), rhogy=U(*ni), rhogz=U(*ni))
+    for pre in ("t", "e"):
+        for c in ("xx", "yy", "zz"):
+            f[f"{pre}{c}"] = U(*ni) * (0.3 if pre == "t" else 1.0)
+        for c in ("yz", "xz", "xy"):
+            f[f"{pre}{c}"] = U(*cshape[c]) * (0.3 if pre == "t" else 1.0)
+    for c in ("xx", "yy", "zz"):
+        f[f"t{c}_o"] = U(*ni) * 0.3
+    for c in ("yz", "xz", "xy"):
+        f[f"t{c}_o"] = U(*cshape[c]) * 0.3
+        f[f"t{c}_c"] = U(*ni) * 0.3
+        f[f"t{c}_o_c"] = U(*ni) * 0.3
+    ratios = {}
+    for nm, sh in cshape.items():
+        r = rng.dirichlet(np.ones(nphase), size=sh)
+        if mixed:
+            pick = rng.integers(0, 3, size=sh)            # 0: keep mixture, 1: one-hot, 2: two-phase mixture with an exact zero
+            hot = np.eye(nphase)[rng.integers(0, nphase, size=sh)]
+            two = r.copy()
+            two[..., -1] = 0.0
+            two /= two.sum(axis=-1, keepdims=True)
+            r = np.where((pick == 1)[..., None], hot, np.where((pick == 2)[..., None], two, r))
+        else:
+            r = np.eye(nphase)[rng.integers(0, nphase, size=sh)]
+        ratios[nm] = np.asfortranarray(r)
+    cosd = math.cos(math.radians(30))
+    pl = R.DruckerPrager_regularised(C=0.05 / cosd, ϕ=30, η_vp=1.0e-2, Ψ=5)
+    el1, el2 = R.ConstantElasticity(G=1.0, Kb=4.0), R.ConstantElasticity(G=0.5, ν=0.5)
+    mats = [
+        R.SetMaterialParams(Phase=1, Density=R.PT_Density(ρ0=1.0, α=3.0e-2, β=1.0e-2, T0=0.1, P0=0.0), Gravity=R.ConstantGravity(g=1.0),
+                            CompositeRheology=R.CompositeRheology((R.LinearViscous(η=1.0), el1, pl)), Elasticity=el1),
+        R.SetMaterialParams(Phase=2, Density=R.ConstantDensity(ρ=0.5), Gravity=R.ConstantGravity(g=1.0),
+                            CompositeRheology=R.CompositeRheology((R.LinearViscous(η=0.1), el2)), Elasticity=el2),
+        R.SetMaterialParams(Phase=3, Density=R.ConstantDensity(ρ=0.1), Gravity=R.ConstantGravity(g=1.0),
+                            CompositeRheology=R.CompositeRheology((R.LinearViscous(η=0.01),))),
+    ][:nphase]
+    li = (1.0, 1.3, 0.9)
+    grid = Geometry(ni, li)
+    pt = PTStokesCoeffs(li, grid.di.center, CFL=0.9 / math.sqrt(3.1))
+    return SimpleNamespace(ni=tuple(ni), li=li, di=grid.di.center, grid=grid, igg=IGG(), pt_stokes=pt, dt=dt, fields=f, ratios=ratios,
+                           rheology=tuple(mats), kwargs=dict(viscosity_cutoff=(1.0e-3, 1.0e2)))

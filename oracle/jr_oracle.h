@@ -147,6 +147,17 @@ void orc_viscosity2d(const orc_fields *s, const orc_stokes_opts *o, const orc_vc
 void orc_rhog2d(const orc_fields *s, const orc_vc_inputs *vc);
 void orc_tensor_invariant2d(double *II, const double *xx, const double *yy, const double *xy, int nx, int ny);
 
+/* ---- 3D multiphase VEP (oracle/stokes3d_vc.c) ---------------------------------- */
+int  orc_solve3d_VC(const orc_fields *s, const orc_stokes_opts *o, const orc_vc_inputs *vc, orc_stokes_result *res);
+/* niter iterations of the 3D-VC loop incl. its pre-loop initialisation, then (if finish) the exit kernels */
+int  orc_iterate3d_VC(const orc_fields *s, const orc_stokes_opts *o, const orc_vc_inputs *vc, int64_t niter, int finish);
+void orc_rhog3d(const orc_fields *s, const orc_vc_inputs *vc);
+void orc_viscosity3d(const orc_fields *s, const orc_stokes_opts *o, const orc_vc_inputs *vc, double nu);
+/* stepwise form for multi-rank emulation: piece 0 = maxloc (then halo ητ), 1 = ∇V…stress (then halo τ shear), 2 = V + BCs (then halo V) */
+void *orc_vc3_begin(const orc_fields *s, const orc_stokes_opts *o, const orc_vc_inputs *vc);
+void orc_vc3_step(const orc_fields *s, const orc_stokes_opts *o, const orc_vc_inputs *vc, void *h, int piece);
+void orc_vc3_end(const orc_fields *s, const orc_stokes_opts *o, void *h, int finish);
+
 /* norms (src/Utils.jl:698-701), interior slice 2:end-1 in every dim when interior!=0 */
 double orc_sumsq_interior(const double *A, int n1, int n2, int n3, int interior);
 

@@ -31,6 +31,7 @@ def lib():
         L.orc_mini3.restype = C.c_double
         L.orc_mini2.restype = C.c_double
         L.orc_sumsq_interior.restype = C.c_double
+        L.orc_vc3_begin.restype = C.c_void_p
         _lib = L
     return _lib
 
@@ -371,6 +372,20 @@ def solve2d_VC(slots, ni, opts, vc):
 def iterate2d_VC(slots, ni, opts, vc, niter, finish=False):
     fs = make_fields(slots, ni)
     return lib().orc_iterate2d_VC(C.byref(fs), C.byref(opts), C.byref(vc), C.c_int64(niter), C.c_int(int(finish)))
+
+
+def solve3d_VC(slots, ni, opts, vc):
+    fs = make_fields(slots, ni)
+    h = Hist(int(opts.iterMax // max(opts.nout, 1)) + 3)
+    st = lib().orc_solve3d_VC(C.byref(fs), C.byref(opts), C.byref(vc), C.byref(h.res))
+    out = h.out()
+    out["status"] = st
+    return out
+
+
+def iterate3d_VC(slots, ni, opts, vc, niter, finish=False):
+    fs = make_fields(slots, ni)
+    return lib().orc_iterate3d_VC(C.byref(fs), C.byref(opts), C.byref(vc), C.c_int64(niter), C.c_int(int(finish)))
 
 
 def tensor_invariant2d(xx, yy, xy):

@@ -253,74 +253,7 @@ int orc_solve2d_V2(const orc_fields *s, const orc_stokes_opts *o, orc_stokes_res
     return 0;
 }
 
-/* ---- rheology table helpers (VC) ----------------------------------------------------------------------------------- */
-static inline double second_invariant3(double xx, double yy, double xy) { return sqrt(0.5 * (xx * xx + yy * yy) + xy * xy); }
-/* fn_ratio(fn, rheology, ratio)  phases.jl:5-16 */
-static double ratio_G(const orc_vc_inputs *vc, const double *ph, size_t stride, size_t idx)
-{
-    double x = 0.0;
-    for (int p = 0; p < vc->nphase; p++) { const double r = ph[(size_t)p * stride + idx]; x += (r == 0.0) ? 0.0 : vc->phases[p].G * r; }
-    return x;
-}
-static double ratio_Kb(const orc_vc_inputs *vc, const double *ph, size_t stride, size_t idx)
-{
-    double x = 0.0;
-    for (int p = 0; p < vc->nphase; p++) { const double r = ph[(size_t)p * stride + idx]; x += (r == 0.0) ? 0.0 : vc->phases[p].Kb * r; }
-    return x;
-}
-/* plastic_params_phase  StressUpdate.jl:153-176: is_pl if any phase with non-zero ratio is plastic; η_reg = Σ η_vp·ratio */
-static void plastic_params(const orc_vc_inputs *vc, const double *ph, size_t stride, size_t idx, int *is_pl, double *eta_reg)
-{
-    *is_pl = 0; *eta_reg = 0.0;
-    for (int p = 0; p < vc->nphase; p++) {
-        const double r = ph[(size_t)p * stride + idx];
-        const int pl = (r != 0.0) && vc->phases[p].has_pl;
-        if (pl) *is_pl = 1;
-        *eta_reg += (pl ? vc->phases[p].eta_vp : 0.0) * r;
-    }
-}
-/* compute_yieldfunction_phase  StressUpdate.jl:384-452: Σ r·F_phase (non-plastic phase: F = τII), zero ratios skipped */
-static double yield_F(const orc_vc_inputs *vc, const double *ph, size_t stride, size_t idx, double P, double tII)
-{
-    double acc = 0.0;
-    for (int p = 0; p < vc->nphase; p++) {
-        const double r = ph[(size_t)p * stride + idx];
-        double v = 0.0;
-        if (r != 0.0) {
-            const orc_stokes_phase *q = &vc->phases[p];
-            const double Fp = q->has_pl ? (tII - q->cosphi * q->C - q->sinphi * (P - 0.0)) - 2 * q->eta_vp * (0.0 * 0.5) : tII;
-            v = r * Fp;
-        }
-        acc = p == 0 ? v : acc + v;
-    }
-    return acc;
-}
-/* compute_plastic_gradients_phase  StressUpdate.jl:463-550 (muladd → fma); t = trial stress (xx, yy, xy) */
-static void plastic_grads(const orc_vc_inputs *vc, const double *ph, size_t stride, size_t idx, const double t[3], double dQdt[3], double *dQdP,
-                          double *dFdP)
-{
-    dQdt[0] = dQdt[1] = dQdt[2] = 0.0; *dQdP = 0.0; *dFdP = 0.0;
-    for (int p = 0; p < vc->nphase; p++) {
-        const double r = ph[(size_t)p * stride + idx];
-        if (r == 0.0) continue;
-        const orc_stokes_phase *q = &vc->phases[p];
-        double g[3] = {0, 0, 0}, qp = 0.0, fp = 0.0;
-        if (q->has_pl) {
-            const double tII = second_invariant3(t[0], t[1], t[2]);
-            g[0] = 0.5 * t[0] / tII; g[1] = 0.5 * t[1] / tII; g[2] = 0.5 * (t[2] / tII);
-            qp = -q->sinpsi; fp = -q->sinphi;
-        }
-        for (int c = 0; c < 3; c++) dQdt[c] = fma(r, g[c], dQdt[c]);
-        *dQdP = fma(r, qp, *dQdP);
-        *dFdP = fma(r, fp, *dFdP);
-    }
-}
-static inline double density(const orc_stokes_phase *p, double T, double P)
-{
-    if (p->rho_kind == 1) return p->rho0 * (1.0 - p->alpha * (T - p->T0) + p->beta * (P - p->P0));
-    if (p->rho_kind == 2) return p->rho0 * (1.0 - p->alpha * (T - p->T0));
-    return p->rho0;
-}
+#include "vc_common.h"
 
 /* compute_ρg!  BuoyancyForces.jl:74-95: fn_ratio(compute_density, …, args) .* (g[1], g[3]); args.T sampled at I+1 (Q17) */
 void orc_rhog2d(const orc_fields *s, const orc_vc_inputs *vc)
@@ -341,26 +274,6 @@ void orc_rhog2d(const orc_fields *s, const orc_vc_inputs *vc)
             else { F(rhogx)[c] = rho * vc->g[0]; F(rhogy)[c] = rho * vc->g[2]; }
         }
 }
-static int density_is_constant(const orc_vc_inputs *vc)
-{
-    for (int p = 0; p < vc->nphase; p++) if (vc->phases[p].rho_kind != 0) return 0;
-    return 1;
-}
-
-/* compute_viscosity_kernel! (τII form), centres and — 2D only — vertices (quirk Q19)  Viscosity.jl:282-323, 382-418 */
-static double phase_viscosity(const orc_vc_inputs *vc, const double *ph, size_t stride, size_t idx)
-{
-    /* compute_phase_viscosity  Viscosity.jl:599-619; per-phase composite: LinearViscous + elastic element at dt = Inf */
-    for (int p = 0; p < vc->nphase; p++)
-        if (ph[(size_t)p * stride + idx] > 0.999) return orc_inv(orc_inv(vc->phases[p].eta) + orc_inv(vc->phases[p].G * INFINITY));
-    double e = 0.0;
-    for (int p = 0; p < vc->nphase; p++) {
-        const double r = ph[(size_t)p * stride + idx];
-        if (r != 0.0) e += orc_inv(orc_inv(orc_inv(vc->phases[p].eta) + orc_inv(vc->phases[p].G * INFINITY))) * r;
-    }
-    return orc_inv(e);
-}
-static inline double clampd(double x, double lo, double hi) { return x < lo ? lo : (x > hi ? hi : x); }
 void orc_viscosity2d(const orc_fields *s, const orc_stokes_opts *o, const orc_vc_inputs *vc, double nu)
 {
     const int nx = s->n[0], ny = s->n[1];
