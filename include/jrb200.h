@@ -190,6 +190,25 @@ int jr_compute_rhog2d(jr_context *ctx, const jr_fields *s, const jr_vc_inputs *v
 /* tensor_invariant!(II, xx, yy, xy_vertex)  src/stokes/StressKernels.jl:470-480 */
 int jr_tensor_invariant2d(jr_context *ctx, double *II, const double *xx, const double *yy, const double *xy, const int32_t n[3]);
 
+/* --- 3D multiphase visco-elasto-plastic Stokes (variant 3D-VC) -------------------------------------------------------
+ * replaces JR3D.solve!(::CUDABackendTrait, stokes, pt_stokes, grid|di, flow_bcs, ρg, phase_ratios, rheology, args, dt, igg; kwargs)
+ * (src/ext/CUDA/3D.jl:375-377 → src/stokes/Stokes3D.jl:447-668).  Three sm_100a kernels per PT iteration, cut where the
+ * reference exchanges halos (ητ | τyz, τxz, τxy | V); with a communicator attached the same kernels run with the peer-memory
+ * halo updates in between.  args.T → slot T (ni.+2), args.P → slot Pargs (may alias P). */
+int jr_stokes3d_solve_VC(jr_context *ctx, const jr_fields *s, const jr_stokes_opts *o, const jr_vc_inputs *vc, jr_stokes_result *res);
+/* pre-loop initialisation + exactly niter iterations (+ the exit kernels when finish != 0); λ is exposed in the lam slot */
+int jr_stokes3d_iterate_VC(jr_context *ctx, const jr_fields *s, const jr_stokes_opts *o, const jr_vc_inputs *vc, int64_t niter, int finish,
+                           jr_stokes_result *res);
+/* compute_viscosity!(stokes, phase_ratios, args, rheology, cutoff; relaxation = nu) 3D  src/ext/CUDA/3D.jl:231-263 → src/rheology/Viscosity.jl:282-323,454-504 */
+int jr_compute_viscosity3d(jr_context *ctx, const jr_fields *s, const jr_stokes_opts *o, const jr_vc_inputs *vc, double nu);
+/* compute_ρg!(ρg, phase_ratios, rheology, args) 3D  src/ext/CUDA/3D.jl:287-299 → src/rheology/BuoyancyForces.jl:38-60 */
+int jr_compute_rhog3d(jr_context *ctx, const jr_fields *s, const jr_vc_inputs *vc);
+/* tensor_invariant!(A::SymmetricTensor) 3D  src/ext/CUDA/3D.jl:266-272 → src/stokes/StressKernels.jl:442-468,482-500 */
+int jr_tensor_invariant3d(jr_context *ctx, double *II, const double *xx, const double *yy, const double *zz, const double *yz, const double *xz,
+                          const double *xy, const int32_t n[3]);
+/* shear2center!(A::SymmetricTensor) 3D  src/ext/CUDA/3D.jl:319-327 → src/Interpolations.jl:313-323 */
+int jr_shear2center3d(jr_context *ctx, double *yz_c, double *xz_c, double *xy_c, const double *yz, const double *xz, const double *xy, const int32_t n[3]);
+
 /* --- stand-alone kernels the reference exposes outside the loops ----------- */
 /* flow_bcs!(stokes, bcs)  src/ext/CUDA/3D.jl:195-218 → BoundaryConditions.jl:65-100 */
 int jr_flow_bcs3d(jr_context *ctx, double *Ax, double *Ay, double *Az, const int32_t n[3],

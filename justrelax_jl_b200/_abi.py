@@ -172,6 +172,12 @@ def _declare(L):
     L.jr_compute_viscosity2d.argtypes = [vp, vp, so, vc, C.c_double]
     L.jr_compute_rhog2d.argtypes = [vp, vp, vc]
     L.jr_tensor_invariant2d.argtypes = [vp, vp, vp, vp, vp, i32p]
+    L.jr_stokes3d_solve_VC.argtypes = [vp, vp, so, vc, sr]
+    L.jr_stokes3d_iterate_VC.argtypes = [vp, vp, so, vc, C.c_int64, C.c_int, sr]
+    L.jr_compute_viscosity3d.argtypes = [vp, vp, so, vc, C.c_double]
+    L.jr_compute_rhog3d.argtypes = [vp, vp, vc]
+    L.jr_tensor_invariant3d.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32p]
+    L.jr_shear2center3d.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32p]
     L.jr_heatdiffusion_PT.argtypes = [vp, C.POINTER(ThermalFields), C.POINTER(ThermalOpts), vp, vp, C.POINTER(ThermalResult)]
     L.jr_thermal_iterate.argtypes = [vp, C.POINTER(ThermalFields), C.POINTER(ThermalOpts), C.c_int64, C.POINTER(ThermalResult)]
     L.jr_thermal_bcs.argtypes = [vp, vp, C.c_int32, i32p, C.POINTER(ThermalOpts)]

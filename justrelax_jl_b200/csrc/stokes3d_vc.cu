@@ -1,0 +1,692 @@
+// stokes3d_vc.cu — the 3D multiphase visco-elasto-plastic Stokes PT loop of libjrb200 (sm_100a), variant 3D-VC
+// (src/stokes/Stokes3D.jl:447-668; config 5 of BASELINE.json: 3D convection with grid-based phases).
+//
+// The reference launches per iteration: compute_maxloc! → update_halo!(ητ) → compute_∇V! → compute_P! → compute_strain_rate! →
+// update_ρg! → update_viscosity_τII! → update_stresses_center_vertex_ps! → update_halo!(τyz, τxz, τxy) → compute_V! →
+// velocity2displacement! → flow_bcs! → update_halo!(V)   (≈ 100 + 4N array passes).  Here one iteration is three kernels,
+// cut exactly where the reference exchanges halos, so the multi-GPU path runs the same kernels:
+//   k_vc3_prep    per cell:  ητ = maxloc(η) | ∇V | θ ← compute_P!(ητ, K, G from phase ratios) | ε (centres and the three edge
+//                            families, launched over `ni` only: quirk Q20) | ρg(T, P) | η ← relaxed phase viscosity (Q10, Q13)
+//   k_vc3_stress  per node:  update_stresses_center_vertex_ps! (yz, xz, xy edges and the centre) as a race-free Jacobi step:
+//                            τ is ping-ponged (set in → set out), the schedule the oracle declares canonical for the racy
+//                            reference kernel (quirk Q7)
+//   k_vc3_vel     per cell:  compute_V! (+ residuals on sampled iterations); then the in-place flow_bcs! kernels of bc.cu
+// Diagnostics nobody reads inside the loop (∇V, RP, ε_pl, τII, η_vep, ε_vol_pl, R, U) are only stored on iterations whose result
+// can be observed (every `nout`, and the last).  Arithmetic is operation for operation the reference's (fma only where it writes
+// fma/muladd; -fmad=false).
+#include "rheo.cuh"
+#include "comm.cuh"
+
+#define F(name) (s->f[JR_F_##name])
+
+struct V3 {
+    int nx, ny, nz;
+    double _dx, _dy, _dz, dt, r, th, edt, rel, nu, cut_lo, cut_hi;
+    double *Vx, *Vy, *Vz, *theta, *P;
+    const double *P0, *Q, *eta_i;
+    double *eta_o, *etatau;
+    double *exx, *eyy, *ezz, *eyz, *exz, *exy;
+    const double *txx_i, *tyy_i, *tzz_i, *tyz_i, *txz_i, *txy_i;
+    double *txx_o, *tyy_o, *tzz_o, *tyz_o, *txz_o, *txy_o;
+    double *tyzc, *txzc, *txyc;
+    const double *oxx, *oyy, *ozz, *oyz, *oxz, *oxy, *oyzc, *oxzc, *oxyc;   // τ_o
+    double *lam, *lamyz, *lamxz, *lamxy;
+    double *rgx, *rgy, *rgz;
+    const double *T, *Pargs, *ph_c, *ph_xy, *ph_yz, *ph_xz;
+    double *divV, *RP, *pxx, *pyy, *pzz, *pyz, *pxz, *pxy, *tII, *eta_vep, *e_vol_pl, *Rx, *Ry, *Rz;
+};
+
+#define CC(A, i, j, k) (A)[IX3(nx, ny, i, j, k)]
+#define YZ(A, i, j, k) (A)[IX3(nx, ny + 1, i, j, k)]
+#define XZ(A, i, j, k) (A)[IX3(nx + 1, ny, i, j, k)]
+#define XY(A, i, j, k) (A)[IX3(nx + 1, ny + 1, i, j, k)]
+#define VX(i, j, k) a.Vx[IX3(nx + 1, ny + 2, i, j, k)]
+#define VY(i, j, k) a.Vy[IX3(nx + 2, ny + 1, i, j, k)]
+#define VZ(i, j, k) a.Vz[IX3(nx + 2, ny + 2, i, j, k)]
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// MAXLOC: compute ητ here (single rank); otherwise ητ was computed by k_maxloc3 and halo-exchanged before this launch
+template <bool DIAG, bool MAXLOC>
+__global__ void __launch_bounds__(256) k_vc3_prep(const __grid_constant__ V3 a, const __grid_constant__ jr_phase_tab pt)
+{
+    const int nx = a.nx, ny = a.ny, nz = a.nz;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x + 1, j = blockIdx.y * blockDim.y + threadIdx.y + 1, k = blockIdx.z + 1;
+    if (i > nx || j > ny || k > nz) return;
+    const size_t nc = (size_t)nx * ny * nz, c = IX3(nx, ny, i, j, k);
+    const double eta = a.eta_i[c];
+    double ett;
+    if (MAXLOC) {  // compute_maxloc!(ητ, η)  Stokes3D.jl:514 ; Utils.jl:409-461
+        double x = -INFINITY;
+        for (int kk = k - 1; kk <= k + 1; kk++)
+            for (int jj = j - 1; jj <= j + 1; jj++)
+                for (int ii = i - 1; ii <= i + 1; ii++) {
+                    const double e = a.eta_i[IX3(nx, ny, jr_clamp(ii, 1, nx), jr_clamp(jj, 1, ny), jr_clamp(kk, 1, nz))];
+                    if (e > x) x = e;
+                }
+        ett = x;
+        a.etatau[c] = ett;
+    } else
+        ett = a.etatau[c];
+    // compute_∇V!  VelocityKernels.jl:3-6
+    const double vx0 = VX(i, j + 1, k + 1), vy0 = VY(i + 1, j, k + 1), vz0 = VZ(i + 1, j + 1, k);
+    const double dVx = (-vx0 + VX(i + 1, j + 1, k + 1)) * a._dx;
+    const double dVy = (-vy0 + VY(i + 1, j + 1, k + 1)) * a._dy;
+    const double dVz = (-vz0 + VZ(i + 1, j + 1, k + 1)) * a._dz;
+    const double divV = dVx + dVy + dVz;
+    // compute_P!(θ, P0, RP, ∇V, Q, ητ, rheology, phase_ratios, …)  Stokes3D.jl:518-531 ; PressureKernels.jl:87-102,186-195
+    const double Kc = jr_ratio_Kb(pt, a.ph_c, nc, c), Gc = jr_ratio_G(pt, a.ph_c, nc, c);
+    double RP, th = a.theta[c];
+    jr_compute_P_point(RP, th, a.P0[c], divV, a.Q[c], ett, Kc, Gc, a.dt, a.r, a.th);
+    a.theta[c] = th;
+    // compute_strain_rate! over ni (quirk Q20)  Stokes3D.jl:533-535 ; VelocityKernels.jl:59-104
+    const double d3 = divV * jr_inv(3.0);
+    a.exx[c] = dVx - d3;
+    a.eyy[c] = dVy - d3;
+    a.ezz[c] = dVz - d3;
+    YZ(a.eyz, i, j, k) = 0.5 * (a._dz * (vy0 - VY(i + 1, j, k)) + a._dy * (vz0 - VZ(i + 1, j, k)));
+    XZ(a.exz, i, j, k) = 0.5 * (a._dz * (vx0 - VX(i, j + 1, k)) + a._dx * (vz0 - VZ(i, j + 1, k)));
+    XY(a.exy, i, j, k) = 0.5 * (a._dy * (vx0 - VX(i, j, k + 1)) + a._dx * (vy0 - VY(i, j, k + 1)));
+    // update_ρg!  Stokes3D.jl:538 ; BuoyancyForces.jl:38-60 (args.T sampled at I+1, quirk Q17)
+    if (!pt.rho_const) {
+        const double Tc = a.T ? a.T[IX3(nx + 2, ny + 2, i + 1, j + 1, k + 1)] : 0.0, Pc = a.Pargs ? a.Pargs[c] : 0.0;
+        const double rho = jr_ratio_density(pt, a.ph_c, nc, c, Tc, Pc);
+        if (!pt.g_scalar) { a.rgx[c] = rho * pt.g[0]; a.rgy[c] = rho * pt.g[1]; }
+        a.rgz[c] = rho * pt.g[2];
+    }
+    // update_viscosity_τII! BEFORE the stress kernel (quirk Q13)  Stokes3D.jl:541-548 ; Viscosity.jl:454-504
+    a.eta_o[c] = jr_clampd((1 - a.nu) * eta + a.nu * jr_phase_viscosity(pt, a.ph_c, nc, c), a.cut_lo, a.cut_hi);
+    if (DIAG) { a.divV[c] = divV; a.RP[c] = RP; }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+struct EdgeIn { double eta, P, e[6], t[6], to[6]; };
+
+// one edge family of update_stresses_center_vertex_ps!  StressKernels.jl:716-778 (yz), :781-849 (xz), :852-921 (xy)
+template <int SLOT, bool DIAG>
+__device__ __forceinline__ void vc3_edge(const V3 &a, const jr_phase_tab &pt, const double *__restrict__ ph, size_t stride, size_t v, const EdgeIn &in,
+                                         double *__restrict__ lamv, double *__restrict__ tau_out, double *__restrict__ epl)
+{
+    bool is_pl;
+    double eta_reg;
+    jr_plastic_params(pt, ph, stride, v, is_pl, eta_reg);
+    const double _Gdt = jr_inv(jr_ratio_G(pt, ph, stride, v) * a.dt), Kv = jr_ratio_Kb(pt, ph, stride, v);
+    const double etav = in.eta, dtr = jr_inv(a.th + etav * _Gdt + 1.0);
+    double d[6], trial[6];
+#pragma unroll
+    for (int q = 0; q < 6; q++) {
+        d[q] = jr_stress_increment(in.t[q], in.to[q], etav, in.e[q], _Gdt, dtr);
+        trial[q] = in.t[q] + d[q];
+    }
+    const double tII = jr_second_invariant<6>(trial);
+    double dQ[6], dQdP, dFdP;
+    jr_plastic_grads<6>(pt, ph, stride, v, trial, dQ, dQdP, dFdP);
+    const double volume = isinf(Kv) ? 0.0 : Kv * a.dt * dFdP * dQdP;
+    const double Fv = jr_yield_F(pt, ph, stride, v, in.P, tII);
+    double tn, ep;
+    if (is_pl && tII != 0.0 && Fv > 0) {
+        const double l = (1.0 - a.rel) * lamv[v] + a.rel * (fmax(Fv, 0.0) / (etav * dtr + eta_reg + volume));
+        lamv[v] = l;
+        ep = l * dQ[SLOT];
+        tn = in.t[SLOT] + fma(-2.0, etav * ep * dtr, d[SLOT]);
+    } else {
+        tn = in.t[SLOT] + d[SLOT];
+        ep = 0.0;
+    }
+    tau_out[v] = tn;
+    if (DIAG) epl[v] = ep;
+}
+
+template <bool DIAG>
+__global__ void __launch_bounds__(256) k_vc3_stress(const __grid_constant__ V3 a, const __grid_constant__ jr_phase_tab pt)
+{
+    const int nx = a.nx, ny = a.ny, nz = a.nz;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x + 1, j = blockIdx.y * blockDim.y + threadIdx.y + 1, k = blockIdx.z + 1;
+    if (i > nx + 1 || j > ny + 1 || k > nz + 1) return;
+    const size_t nc = (size_t)nx * ny * nz, nyz = (size_t)nx * (ny + 1) * (nz + 1), nxz = (size_t)(nx + 1) * ny * (nz + 1),
+                 nxy = (size_t)(nx + 1) * (ny + 1) * nz;
+    const int i0 = jr_clamp(i - 1, 1, nx), ic = jr_clamp(i, 1, nx), i1 = jr_clamp(i + 1, 1, nx);
+    const int j0 = jr_clamp(j - 1, 1, ny), jc = jr_clamp(j, 1, ny), j1 = jr_clamp(j + 1, 1, ny);
+    const int k0 = jr_clamp(k - 1, 1, nz), kc = jr_clamp(k, 1, nz), k1 = jr_clamp(k + 1, 1, nz);
+    const double *eta = a.eta_o;  // the relaxed viscosity of this iteration
+    // clamped averages  StressKernels.jl:620-669 (argument order = summation order)
+#define AV_YZ(A) (0.25 * (CC(A, ic, j0, k0) + CC(A, ic, jc, k0) + CC(A, ic, j0, kc) + CC(A, ic, jc, kc)))
+#define AV_XZ(A) (0.25 * (CC(A, i0, jc, k0) + CC(A, ic, jc, k0) + CC(A, i0, jc, kc) + CC(A, ic, jc, kc)))
+#define AV_XY(A) (0.25 * (CC(A, i0, j0, kc) + CC(A, ic, j0, kc) + CC(A, i0, jc, kc) + CC(A, ic, jc, kc)))
+#define HARM_YZ(A) (4 / (1 / CC(A, ic, j0, k0) + 1 / CC(A, ic, jc, k0) + 1 / CC(A, ic, j0, kc) + 1 / CC(A, ic, jc, kc)))
+#define HARM_XZ(A) (4 / (1 / CC(A, i0, jc, k0) + 1 / CC(A, ic, jc, k0) + 1 / CC(A, i0, jc, kc) + 1 / CC(A, ic, jc, kc)))
+#define HARM_XY(A) (4 / (1 / CC(A, i0, j0, kc) + 1 / CC(A, ic, j0, kc) + 1 / CC(A, i0, jc, kc) + 1 / CC(A, ic, jc, kc)))
+#define AV_YZ_Z(A) (0.25 * (XY(A, ic, jc, k0) + XY(A, i1, jc, k0) + XY(A, ic, jc, kc) + XY(A, i1, jc, kc)))
+#define AV_YZ_Y(A) (0.25 * (XZ(A, ic, j0, kc) + XZ(A, i1, j0, kc) + XZ(A, ic, jc, kc) + XZ(A, i1, jc, kc)))
+#define AV_XZ_Z(A) (0.25 * (XY(A, ic, jc, k0) + XY(A, ic, j1, k0) + XY(A, ic, jc, kc) + XY(A, ic, j1, kc)))
+#define AV_XZ_X(A) (0.25 * (YZ(A, i0, jc, kc) + YZ(A, ic, jc, kc) + YZ(A, ic, j1, kc) + YZ(A, i0, j1, kc)))
+#define AV_XY_Y(A) (0.25 * (XZ(A, ic, j0, kc) + XZ(A, ic, jc, kc) + XZ(A, ic, j0, k1) + XZ(A, ic, jc, k1)))
+#define AV_XY_X(A) (0.25 * (YZ(A, i0, jc, kc) + YZ(A, ic, jc, kc) + YZ(A, i0, jc, k1) + YZ(A, ic, jc, k1)))
+    if (i <= nx && j <= ny + 1 && k <= nz + 1) {  // ---- yz edge
+        const size_t v = IX3(nx, ny + 1, i, j, k);
+        EdgeIn in;
+        in.eta = HARM_YZ(eta); in.P = AV_YZ(a.theta);
+        in.e[0] = AV_YZ(a.exx); in.e[1] = AV_YZ(a.eyy); in.e[2] = AV_YZ(a.ezz);
+        in.e[3] = a.eyz[v]; in.e[4] = AV_YZ_Y(a.exz); in.e[5] = AV_YZ_Z(a.exy);
+        in.t[0] = AV_YZ(a.txx_i); in.t[1] = AV_YZ(a.tyy_i); in.t[2] = AV_YZ(a.tzz_i);
+        in.t[3] = a.tyz_i[v]; in.t[4] = AV_YZ_Y(a.txz_i); in.t[5] = AV_YZ_Z(a.txy_i);
+        in.to[0] = AV_YZ(a.oxx); in.to[1] = AV_YZ(a.oyy); in.to[2] = AV_YZ(a.ozz);
+        in.to[3] = a.oyz[v]; in.to[4] = AV_YZ_Y(a.oxz); in.to[5] = AV_YZ_Z(a.oxy);
+        vc3_edge<3, DIAG>(a, pt, a.ph_yz, nyz, v, in, a.lamyz, a.tyz_o, a.pyz);
+    }
+    if (i <= nx + 1 && j <= ny && k <= nz + 1) {  // ---- xz edge
+        const size_t v = IX3(nx + 1, ny, i, j, k);
+        EdgeIn in;
+        in.eta = HARM_XZ(eta); in.P = AV_XZ(a.theta);
+        in.e[0] = AV_XZ(a.exx); in.e[1] = AV_XZ(a.eyy); in.e[2] = AV_XZ(a.ezz);
+        in.e[3] = AV_XZ_X(a.eyz); in.e[4] = a.exz[v]; in.e[5] = AV_XZ_Z(a.exy);
+        in.t[0] = AV_XZ(a.txx_i); in.t[1] = AV_XZ(a.tyy_i); in.t[2] = AV_XZ(a.tzz_i);
+        in.t[3] = AV_XZ_X(a.tyz_i); in.t[4] = a.txz_i[v]; in.t[5] = AV_XZ_Z(a.txy_i);
+        in.to[0] = AV_XZ(a.oxx); in.to[1] = AV_XZ(a.oyy); in.to[2] = AV_XZ(a.ozz);
+        in.to[3] = AV_XZ_X(a.oyz); in.to[4] = a.oxz[v]; in.to[5] = AV_XZ_Z(a.oxy);
+        vc3_edge<4, DIAG>(a, pt, a.ph_xz, nxz, v, in, a.lamxz, a.txz_o, a.pxz);
+    }
+    if (i <= nx + 1 && j <= ny + 1 && k <= nz) {  // ---- xy edge
+        const size_t v = IX3(nx + 1, ny + 1, i, j, k);
+        EdgeIn in;
+        in.eta = HARM_XY(eta); in.P = AV_XY(a.theta);
+        in.e[0] = AV_XY(a.exx); in.e[1] = AV_XY(a.eyy); in.e[2] = AV_XY(a.ezz);
+        in.e[3] = AV_XY_X(a.eyz); in.e[4] = AV_XY_Y(a.exz); in.e[5] = a.exy[v];
+        in.t[0] = AV_XY(a.txx_i); in.t[1] = AV_XY(a.tyy_i); in.t[2] = AV_XY(a.tzz_i);
+        in.t[3] = AV_XY_X(a.tyz_i); in.t[4] = AV_XY_Y(a.txz_i); in.t[5] = a.txy_i[v];
+        in.to[0] = AV_XY(a.oxx); in.to[1] = AV_XY(a.oyy); in.to[2] = AV_XY(a.ozz);
+        in.to[3] = AV_XY_X(a.oyz); in.to[4] = AV_XY_Y(a.oxz); in.to[5] = a.oxy[v];
+        vc3_edge<5, DIAG>(a, pt, a.ph_xy, nxy, v, in, a.lamxy, a.txy_o, a.pxy);
+    }
+    if (i <= nx && j <= ny && k <= nz) {  // ---- centre  StressKernels.jl:923-986 (plain products and sums: no @muladd there)
+        const size_t c = IX3(nx, ny, i, j, k);
+        const double _Gdt = jr_inv(jr_ratio_G(pt, a.ph_c, nc, c) * a.dt);
+        bool is_pl;
+        double eta_reg;
+        jr_plastic_params(pt, a.ph_c, nc, c, is_pl, eta_reg);
+        const double K = jr_ratio_Kb(pt, a.ph_c, nc, c), et = eta[c];
+        const double dtr = jr_inv(a.th + et * _Gdt + 1.0);
+        // cache_tensors  StressUpdate.jl:248-301 (_av_yz/_av_xz/_av_xy: mysum order k → j → i starting from 0.0, quirk Q15)
+        const double eij[6] = {a.exx[c], a.eyy[c], a.ezz[c],
+                               0.25 * ((((0.0 + YZ(a.eyz, i, j, k)) + YZ(a.eyz, i, j + 1, k)) + YZ(a.eyz, i, j, k + 1)) + YZ(a.eyz, i, j + 1, k + 1)),
+                               0.25 * ((((0.0 + XZ(a.exz, i, j, k)) + XZ(a.exz, i + 1, j, k)) + XZ(a.exz, i, j, k + 1)) + XZ(a.exz, i + 1, j, k + 1)),
+                               0.25 * ((((0.0 + XY(a.exy, i, j, k)) + XY(a.exy, i + 1, j, k)) + XY(a.exy, i, j + 1, k)) + XY(a.exy, i + 1, j + 1, k))};
+        double tij[6] = {a.txx_i[c], a.tyy_i[c], a.tzz_i[c], a.tyzc[c], a.txzc[c], a.txyc[c]};
+        const double tijo[6] = {a.oxx[c], a.oyy[c], a.ozz[c], a.oyzc[c], a.oxzc[c], a.oxyc[c]};
+        double d[6], trial[6];
+#pragma unroll
+        for (int q = 0; q < 6; q++) {
+            d[q] = (-(tij[q] - tijo[q]) * et * _Gdt - tij[q] + 2.0 * et * eij[q]) * dtr;
+            trial[q] = tij[q] + d[q];
+        }
+        double tII = jr_second_invariant<6>(trial);
+        double dQ[6], dQdP, dFdP;
+        const double Pr = a.theta[c];
+        jr_plastic_grads<6>(pt, a.ph_c, nc, c, trial, dQ, dQdP, dFdP);
+        const double volume = isinf(K) ? 0.0 : K * a.dt * dFdP * dQdP;
+        const double Fc = jr_yield_F(pt, a.ph_c, nc, c, Pr, tII);
+        double lam = a.lam[c], evol = 0.0, epl[3] = {0.0, 0.0, 0.0};
+        if (is_pl && tII != 0.0 && Fc > 0) {
+            lam = (1.0 - a.rel) * lam + a.rel * (fmax(Fc, 0.0) / (et * dtr + eta_reg + volume));
+            a.lam[c] = lam;
+#pragma unroll
+            for (int q = 0; q < 6; q++) {
+                const double e = lam * dQ[q];
+                if (q < 3) epl[q] = e;
+                d[q] = d[q] - 2.0 * et * e * dtr;
+                tij[q] = d[q] + tij[q];
+            }
+            evol = -lam * dQdP;
+            tII = jr_second_invariant<6>(tij);
+        } else {
+#pragma unroll
+            for (int q = 0; q < 6; q++) tij[q] = d[q] + tij[q];
+        }
+        a.txx_o[c] = tij[0]; a.tyy_o[c] = tij[1]; a.tzz_o[c] = tij[2];
+        a.tyzc[c] = tij[3]; a.txzc[c] = tij[4]; a.txyc[c] = tij[5];
+        a.P[c] = Pr - (isinf(K) ? 0.0 : K * a.dt * lam * dQdP);
+        if (DIAG) {
+            a.pxx[c] = epl[0]; a.pyy[c] = epl[1]; a.pzz[c] = epl[2];
+            a.e_vol_pl[c] = evol;
+            a.tII[c] = tII;
+            a.eta_vep[c] = tII * 0.5 * jr_inv(jr_second_invariant<6>(eij));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// compute_V! 3D  VelocityKernels.jl:182-242 (reads the NEW stresses, P = Pr_c, ητ)
+template <bool DIAG>
+__global__ void __launch_bounds__(256) k_vc3_vel(const __grid_constant__ V3 a)
+{
+    const int nx = a.nx, ny = a.ny, nz = a.nz;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x + 1, j = blockIdx.y * blockDim.y + threadIdx.y + 1, k = blockIdx.z + 1;
+    if (i > nx || j > ny || k > nz) return;
+    const double *P = a.P, *ett = a.etatau, *txx = a.txx_o, *tyy = a.tyy_o, *tzz = a.tzz_o, *tyz = a.tyz_o, *txz = a.txz_o, *txy = a.txy_o;
+    const double Pc = CC(P, i, j, k), ec = CC(ett, i, j, k);
+    const double xy11 = XY(txy, i + 1, j + 1, k), xz11 = XZ(txz, i + 1, j, k + 1), yz11 = YZ(tyz, i, j + 1, k + 1);
+    if (i <= nx - 1) {
+        const double R = (-CC(txx, i, j, k) + CC(txx, i + 1, j, k)) * a._dx + a._dy * (xy11 - XY(txy, i + 1, j, k)) + a._dz * (xz11 - XZ(txz, i + 1, j, k)) -
+                         (-Pc + CC(P, i + 1, j, k)) * a._dx - 0.5 * (CC(a.rgx, i, j, k) + CC(a.rgx, i + 1, j, k));
+        if (DIAG) a.Rx[IX3(nx - 1, ny, i, j, k)] = R;
+        VX(i + 1, j + 1, k + 1) += R * a.edt / (0.5 * (ec + CC(ett, i + 1, j, k)));
+    }
+    if (j <= ny - 1) {
+        const double R = a._dx * (xy11 - XY(txy, i, j + 1, k)) + a._dy * (CC(tyy, i, j + 1, k) - CC(tyy, i, j, k)) + a._dz * (yz11 - YZ(tyz, i, j + 1, k)) -
+                         (-Pc + CC(P, i, j + 1, k)) * a._dy - 0.5 * (CC(a.rgy, i, j, k) + CC(a.rgy, i, j + 1, k));
+        if (DIAG) a.Ry[IX3(nx, ny - 1, i, j, k)] = R;
+        VY(i + 1, j + 1, k + 1) += R * a.edt / (0.5 * (ec + CC(ett, i, j + 1, k)));
+    }
+    if (k <= nz - 1) {
+        const double R = a._dx * (xz11 - XZ(txz, i, j, k + 1)) + a._dy * (yz11 - YZ(tyz, i, j, k + 1)) + (-CC(tzz, i, j, k) + CC(tzz, i, j, k + 1)) * a._dz -
+                         (-Pc + CC(P, i, j, k + 1)) * a._dz - 0.5 * (CC(a.rgz, i, j, k) + CC(a.rgz, i, j, k + 1));
+        if (DIAG) a.Rz[IX3(nx, ny, i, j, k)] = R;
+        VZ(i + 1, j + 1, k + 1) += R * a.edt / (0.5 * (ec + CC(ett, i, j, k + 1)));
+    }
+}
+
+// compute_ρg! 3D stand-alone  BuoyancyForces.jl:38-60
+__global__ void k_rhog3d(int nx, int ny, int nz, const __grid_constant__ jr_phase_tab pt, const double *__restrict__ ph_c, const double *__restrict__ T,
+                         const double *__restrict__ Pa, double *__restrict__ rgx, double *__restrict__ rgy, double *__restrict__ rgz)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x + 1, j = blockIdx.y * blockDim.y + threadIdx.y + 1, k = blockIdx.z + 1;
+    if (i > nx || j > ny || k > nz) return;
+    const size_t c = IX3(nx, ny, i, j, k);
+    const double Tc = T ? T[IX3(nx + 2, ny + 2, i + 1, j + 1, k + 1)] : 0.0, Pc = Pa ? Pa[c] : 0.0;
+    const double rho = jr_ratio_density(pt, ph_c, (size_t)nx * ny * nz, c, Tc, Pc);
+    if (!pt.g_scalar) { rgx[c] = rho * pt.g[0]; rgy[c] = rho * pt.g[1]; }
+    rgz[c] = rho * pt.g[2];
+}
+// compute_viscosity_kernel! 3D (centres only)  Viscosity.jl:306-308,454-504
+__global__ void k_viscosity3d(size_t n, const __grid_constant__ jr_phase_tab pt, const double *__restrict__ ph, double *__restrict__ eta, double nu,
+                              double lo, double hi)
+{
+    const size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (q < n) eta[q] = jr_clampd((1 - nu) * eta[q] + nu * jr_phase_viscosity(pt, ph, n, q), lo, hi);
+}
+__global__ void k_scale3(size_t n0, size_t n1, size_t n2, double *__restrict__ U0, double *__restrict__ U1, double *__restrict__ U2,
+                         const double *__restrict__ V0, const double *__restrict__ V1, const double *__restrict__ V2, double f)
+{
+    const size_t tot = n0 + n1 + n2;
+    for (size_t I = blockIdx.x * (size_t)blockDim.x + threadIdx.x; I < tot; I += (size_t)gridDim.x * blockDim.x) {
+        if (I < n0) U0[I] = V0[I] * f;
+        else if (I < n0 + n1) U1[I - n0] = V1[I - n0] * f;
+        else U2[I - n0 - n1] = V2[I - n0 - n1] * f;
+    }
+}
+// exit kernels ------------------------------------------------------------------------------------------------------------------
+// compute_vorticity!(ωyz, ωxz, ωxy, V…, _di) over ni.+1  stress_rotation_particles.jl:32-51 (plain _d_*a at I)
+__global__ void k_vorticity3d(const __grid_constant__ V3 a, double *__restrict__ wyz, double *__restrict__ wxz, double *__restrict__ wxy)
+{
+    const int nx = a.nx, ny = a.ny, nz = a.nz;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x + 1, j = blockIdx.y * blockDim.y + threadIdx.y + 1, k = blockIdx.z + 1;
+    if (i > nx + 1 || j > ny + 1 || k > nz + 1) return;
+    if (wyz && i <= nx && j <= ny + 1 && k <= nz + 1) YZ(wyz, i, j, k) = 0.5 * ((-VZ(i, j, k) + VZ(i, j + 1, k)) * a._dy - (-VY(i, j, k) + VY(i, j, k + 1)) * a._dz);
+    if (wxz && i <= nx + 1 && j <= ny && k <= nz + 1) XZ(wxz, i, j, k) = 0.5 * ((-VX(i, j, k) + VX(i, j, k + 1)) * a._dz - (-VZ(i, j, k) + VZ(i + 1, j, k)) * a._dx);
+    if (wxy && i <= nx + 1 && j <= ny + 1 && k <= nz) XY(wxy, i, j, k) = 0.5 * ((-VY(i, j, k) + VY(i + 1, j, k)) * a._dx - (-VX(i, j, k) + VX(i, j + 1, k)) * a._dy);
+}
+// shear2center! 3D  Interpolations.jl:313-323
+__global__ void k_shear2center3d(int nx, int ny, int nz, double *__restrict__ yzc, double *__restrict__ xzc, double *__restrict__ xyc,
+                                 const double *__restrict__ yz, const double *__restrict__ xz, const double *__restrict__ xy)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x + 1, j = blockIdx.y * blockDim.y + threadIdx.y + 1, k = blockIdx.z + 1;
+    if (i > nx || j > ny || k > nz) return;
+    const size_t c = IX3(nx, ny, i, j, k);
+    yzc[c] = 0.25 * (YZ(yz, i, j, k) + YZ(yz, i, j + 1, k) + YZ(yz, i, j, k + 1) + YZ(yz, i, j + 1, k + 1));
+    xzc[c] = 0.25 * (XZ(xz, i, j, k) + XZ(xz, i + 1, j, k) + XZ(xz, i, j, k + 1) + XZ(xz, i + 1, j, k + 1));
+    xyc[c] = 0.25 * (XY(xy, i, j, k) + XY(xy, i + 1, j, k) + XY(xy, i, j + 1, k) + XY(xy, i + 1, j + 1, k));
+}
+// second_invariant_staggered of a 3D tensor with edge shear components (GeoParams; gathers MiniKernels.jl:196-204);
+// mode 0: II = inv (tensor_invariant!) ; mode 1: II += inv * f (accumulate_tensor!  StressKernels.jl:394-408)
+__global__ void k_inv_stag3d(int nx, int ny, int nz, double *__restrict__ II, const double *__restrict__ xx, const double *__restrict__ yy,
+                             const double *__restrict__ zz, const double *__restrict__ yz, const double *__restrict__ xz, const double *__restrict__ xy,
+                             int mode, double f)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x + 1, j = blockIdx.y * blockDim.y + threadIdx.y + 1, k = blockIdx.z + 1;
+    if (i > nx || j > ny || k > nz) return;
+    const size_t c = IX3(nx, ny, i, j, k);
+    const double X = xx[c], Y = yy[c], Z = zz[c];
+    const double a1 = YZ(yz, i, j, k), a2 = YZ(yz, i, j + 1, k), a3 = YZ(yz, i, j, k + 1), a4 = YZ(yz, i, j + 1, k + 1);
+    const double b1 = XZ(xz, i, j, k), b2 = XZ(xz, i + 1, j, k), b3 = XZ(xz, i, j, k + 1), b4 = XZ(xz, i + 1, j, k + 1);
+    const double c1 = XY(xy, i, j, k), c2 = XY(xy, i + 1, j, k), c3 = XY(xy, i, j + 1, k), c4 = XY(xy, i + 1, j + 1, k);
+    const double yz2 = (((a1 * a1 + a2 * a2) + a3 * a3) + a4 * a4) / 4, xz2 = (((b1 * b1 + b2 * b2) + b3 * b3) + b4 * b4) / 4,
+                 xy2 = (((c1 * c1 + c2 * c2) + c3 * c3) + c4 * c4) / 4;
+    const double v = sqrt(0.5 * (X * X + Y * Y + Z * Z) + yz2 + xz2 + xy2);
+    if (mode == 0) II[c] = v;
+    else II[c] += v * f;
+}
+__global__ void k_axpy3(size_t n, double *__restrict__ A, const double *__restrict__ B, double f)
+{
+    const size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (q < n) A[q] += f * B[q];
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// host drivers
+enum { T_xx, T_yy, T_zz, T_yz, T_xz, T_xy, T_COUNT };
+struct Plan3 {
+    int nx, ny, nz;
+    size_t nc, nyz, nxz, nxy;
+    double *tau[2][T_COUNT];   // τ ping-pong sets (set 0 = the caller's arrays)
+    double *eta[2];            // η ping-pong (set 0 = the caller's array)
+    size_t tbytes[T_COUNT];
+    V3 k;
+    jr_phase_tab pt;
+    bool multi;
+    int32_t n[3], fs[6], ns[6], pe[6];
+};
+
+static int check3d_vc(const jr_fields *s, const jr_stokes_opts *o, const jr_vc_inputs *in)
+{
+    JR_REQUIRE(s && o, JR_ERR_ARG, "null fields/opts");
+    JR_REQUIRE(s->ndim == 3, JR_ERR_SHAPE, "3D solver called with ndim=%d", s->ndim);
+    JR_REQUIRE(s->n[0] >= 3 && s->n[1] >= 3 && s->n[2] >= 3, JR_ERR_SHAPE, "grid must be at least 3 cells per dimension");
+    JR_REQUIRE(o->nout >= 1, JR_ERR_ARG, "nout must be >= 1");
+    static const int req[] = {JR_F_P, JR_F_P0, JR_F_divV, JR_F_Q, JR_F_Vx, JR_F_Vy, JR_F_Vz, JR_F_txx, JR_F_tyy, JR_F_tzz, JR_F_tyz, JR_F_txz, JR_F_txy,
+                              JR_F_tyz_c, JR_F_txz_c, JR_F_txy_c, JR_F_txx_o, JR_F_tyy_o, JR_F_tzz_o, JR_F_tyz_o, JR_F_txz_o, JR_F_txy_o, JR_F_tyz_o_c,
+                              JR_F_txz_o_c, JR_F_txy_o_c, JR_F_exx, JR_F_eyy, JR_F_ezz, JR_F_eyz, JR_F_exz, JR_F_exy, JR_F_pxx, JR_F_pyy, JR_F_pzz, JR_F_pyz,
+                              JR_F_pxz, JR_F_pxy, JR_F_tII, JR_F_eta_vep, JR_F_e_vol_pl, JR_F_EII_pl, JR_F_EVol_pl, JR_F_eta, JR_F_etatau, JR_F_Rx, JR_F_Ry,
+                              JR_F_Rz, JR_F_RP, JR_F_rhogx, JR_F_rhogy, JR_F_rhogz};
+    for (int q : req) JR_REQUIRE(s->f[q] != nullptr, JR_ERR_SHAPE, "required field '%s' is NULL", jr_field_name(q));
+    JR_REQUIRE(in && in->ph_center && in->ph_xy && in->ph_yz && in->ph_xz, JR_ERR_SHAPE, "3D-VC needs phase ratios at centres and at the xy, yz, xz edges");
+    return JR_OK;
+}
+
+static inline dim3 grid3(int nx, int ny, int nz) { return dim3((nx + 31) / 32, (ny + 7) / 8, nz); }
+static const dim3 BLK3(32, 8, 1);
+
+static int plan3_begin(jr_context *ctx, const jr_fields *s, const jr_stokes_opts *o, const jr_vc_inputs *in, Plan3 *p)
+{
+    memset(p, 0, sizeof(*p));
+    const int nx = p->nx = s->n[0], ny = p->ny = s->n[1], nz = p->nz = s->n[2];
+    p->nc = (size_t)nx * ny * nz; p->nyz = (size_t)nx * (ny + 1) * (nz + 1); p->nxz = (size_t)(nx + 1) * ny * (nz + 1); p->nxy = (size_t)(nx + 1) * (ny + 1) * nz;
+    const size_t b[T_COUNT] = {p->nc * 8, p->nc * 8, p->nc * 8, p->nyz * 8, p->nxz * 8, p->nxy * 8};
+    size_t off[T_COUNT], tot = 0;
+    for (int q = 0; q < T_COUNT; q++) { p->tbytes[q] = b[q]; off[q] = tot; tot += (b[q] + 255) & ~(size_t)255; }
+    const size_t o_eta = tot; tot += (p->nc * 8 + 255) & ~(size_t)255;
+    const size_t o_th = tot; tot += (p->nc * 8 + 255) & ~(size_t)255;
+    const size_t o_lam = tot; tot += (p->nc * 8 + 255) & ~(size_t)255;
+    const size_t o_lyz = tot; tot += (p->nyz * 8 + 255) & ~(size_t)255;
+    const size_t o_lxz = tot; tot += (p->nxz * 8 + 255) & ~(size_t)255;
+    const size_t o_lxy = tot; tot += (p->nxy * 8 + 255) & ~(size_t)255;
+    void *base = nullptr;
+    int st = jr_ctx_scratch(ctx, "stokes3d_vc", tot, &base);
+    if (st) return st;
+    char *B = (char *)base;
+    double *user[T_COUNT] = {F(txx), F(tyy), F(tzz), F(tyz), F(txz), F(txy)};
+    for (int q = 0; q < T_COUNT; q++) { p->tau[0][q] = user[q]; p->tau[1][q] = (double *)(B + off[q]); }
+    p->eta[0] = F(eta); p->eta[1] = (double *)(B + o_eta);
+    for (int q = 0; q < 3; q++) p->n[q] = s->n[q];
+    for (int q = 0; q < 6; q++) { p->fs[q] = o->free_slip[q]; p->ns[q] = o->no_slip[q]; p->pe[q] = o->periodic[q]; }
+    p->multi = ctx->comm && ctx->comm->nranks > 1;
+    if ((st = jr_make_phase_tab(in, &p->pt))) return st;
+    V3 &k = p->k;
+    k.nx = nx; k.ny = ny; k.nz = nz;
+    k._dx = o->_di[0]; k._dy = o->_di[1]; k._dz = o->_di[2]; k.dt = o->dt; k.r = o->r; k.th = o->theta_dtau; k.edt = o->eta_dtau;
+    k.rel = o->lambda_relaxation; k.nu = o->viscosity_relaxation; k.cut_lo = o->visc_cutoff_lo; k.cut_hi = o->visc_cutoff_hi;
+    k.Vx = F(Vx); k.Vy = F(Vy); k.Vz = F(Vz); k.theta = (double *)(B + o_th); k.P = F(P); k.P0 = F(P0); k.Q = F(Q); k.etatau = F(etatau);
+    k.exx = F(exx); k.eyy = F(eyy); k.ezz = F(ezz); k.eyz = F(eyz); k.exz = F(exz); k.exy = F(exy);
+    k.tyzc = F(tyz_c); k.txzc = F(txz_c); k.txyc = F(txy_c);
+    k.oxx = F(txx_o); k.oyy = F(tyy_o); k.ozz = F(tzz_o); k.oyz = F(tyz_o); k.oxz = F(txz_o); k.oxy = F(txy_o);
+    k.oyzc = F(tyz_o_c); k.oxzc = F(txz_o_c); k.oxyc = F(txy_o_c);
+    k.lam = (double *)(B + o_lam); k.lamyz = (double *)(B + o_lyz); k.lamxz = (double *)(B + o_lxz); k.lamxy = (double *)(B + o_lxy);
+    k.rgx = F(rhogx); k.rgy = F(rhogy); k.rgz = F(rhogz); k.T = F(T); k.Pargs = F(Pargs);
+    k.ph_c = in->ph_center; k.ph_xy = in->ph_xy; k.ph_yz = in->ph_yz; k.ph_xz = in->ph_xz;
+    k.divV = F(divV); k.RP = F(RP); k.pxx = F(pxx); k.pyy = F(pyy); k.pzz = F(pzz); k.pyz = F(pyz); k.pxz = F(pxz); k.pxy = F(pxy);
+    k.tII = F(tII); k.eta_vep = F(eta_vep); k.e_vol_pl = F(e_vol_pl); k.Rx = F(Rx); k.Ry = F(Ry); k.Rz = F(Rz);
+    return JR_OK;
+}
+
+// pre-loop  Stokes3D.jl:493-509
+static int pre_VC3(jr_context *ctx, const jr_fields *s, const jr_stokes_opts *o, Plan3 *p)
+{
+    cudaStream_t st = ctx->stream;
+    const V3 &k = p->k;
+    JR_CUDA(cudaMemcpyAsync(F(P0), F(P), p->nc * 8, cudaMemcpyDeviceToDevice, st));      // @copy stokes.P0 stokes.P   :493
+    JR_CUDA(cudaMemcpyAsync(k.theta, F(P), p->nc * 8, cudaMemcpyDeviceToDevice, st));    // θ = deepcopy(stokes.P)     :494
+    JR_CUDA(cudaMemsetAsync(k.lam, 0, p->nc * 8, st));                                   // λ, λv_* = 0                :495-498
+    JR_CUDA(cudaMemsetAsync(k.lamyz, 0, p->nyz * 8, st));
+    JR_CUDA(cudaMemsetAsync(k.lamxz, 0, p->nxz * 8, st));
+    JR_CUDA(cudaMemsetAsync(k.lamxy, 0, p->nxy * 8, st));
+    JR_CUDA(cudaMemcpyAsync(F(etatau), F(eta), p->nc * 8, cudaMemcpyDeviceToDevice, st));  // ητ = deepcopy(η)         :502
+    k_rhog3d<<<grid3(p->nx, p->ny, p->nz), BLK3, 0, st>>>(p->nx, p->ny, p->nz, p->pt, k.ph_c, F(T), F(Pargs), F(rhogx), F(rhogy), F(rhogz));   // compute_ρg!  :505
+    // compute_viscosity! (εII form, relaxation 1)  :506 — independent of εII for the LinearViscous subset
+    k_viscosity3d<<<(unsigned)((p->nc + 255) / 256), 256, 0, st>>>(p->nc, p->pt, k.ph_c, F(eta), 1.0, o->visc_cutoff_lo, o->visc_cutoff_hi);
+    ctx->launches += 2;
+    JR_CHECK_LAUNCH();
+    return JR_OK;
+}
+
+// one PT iteration: τ set (it & 1) → set ((it + 1) & 1), η likewise
+static int plan3_iter(jr_context *ctx, Plan3 *p, int64_t it, bool diag, const jr_fields *s, const jr_stokes_opts *o)
+{
+    V3 k = p->k;
+    double *const *I = p->tau[it & 1], *const *O = p->tau[(it + 1) & 1];
+    k.txx_i = I[T_xx]; k.tyy_i = I[T_yy]; k.tzz_i = I[T_zz]; k.tyz_i = I[T_yz]; k.txz_i = I[T_xz]; k.txy_i = I[T_xy];
+    k.txx_o = O[T_xx]; k.tyy_o = O[T_yy]; k.tzz_o = O[T_zz]; k.tyz_o = O[T_yz]; k.txz_o = O[T_xz]; k.txy_o = O[T_xy];
+    k.eta_i = p->eta[it & 1]; k.eta_o = p->eta[(it + 1) & 1];
+    cudaStream_t st = ctx->stream;
+    const int nx = p->nx, ny = p->ny, nz = p->nz;
+    int rc;
+    if (p->multi) {  // compute_maxloc!(ητ, η); update_halo!(ητ)  :514-515
+        const int32_t w3[3] = {1, 1, 1};
+        if ((rc = jr_launch_maxloc3d(ctx, k.etatau, k.eta_i, p->n, w3))) return rc;
+        const jr_harr H = jr_harr_dense(k.etatau, p->n, p->n);
+        if ((rc = jr_comm_halo(ctx, &H, 1))) return rc;
+        if (diag) k_vc3_prep<true, false><<<grid3(nx, ny, nz), BLK3, 0, st>>>(k, p->pt);
+        else k_vc3_prep<false, false><<<grid3(nx, ny, nz), BLK3, 0, st>>>(k, p->pt);
+    } else {
+        if (diag) k_vc3_prep<true, true><<<grid3(nx, ny, nz), BLK3, 0, st>>>(k, p->pt);
+        else k_vc3_prep<false, true><<<grid3(nx, ny, nz), BLK3, 0, st>>>(k, p->pt);
+    }
+    if (diag) k_vc3_stress<true><<<grid3(nx + 1, ny + 1, nz + 1), BLK3, 0, st>>>(k, p->pt);
+    else k_vc3_stress<false><<<grid3(nx + 1, ny + 1, nz + 1), BLK3, 0, st>>>(k, p->pt);
+    ctx->launches += 2;
+    JR_CHECK_LAUNCH();
+    if (p->multi) {  // update_halo!(τyz); update_halo!(τxz); update_halo!(τxy)  :578-580
+        const int32_t eyz[3] = {nx, ny + 1, nz + 1}, exz[3] = {nx + 1, ny, nz + 1}, exy[3] = {nx + 1, ny + 1, nz};
+        const jr_harr H[3] = {jr_harr_dense(k.tyz_o, eyz, p->n), jr_harr_dense(k.txz_o, exz, p->n), jr_harr_dense(k.txy_o, exy, p->n)};
+        if ((rc = jr_comm_halo(ctx, H, 3))) return rc;
+    }
+    if (diag) k_vc3_vel<true><<<grid3(nx, ny, nz), BLK3, 0, st>>>(k);
+    else k_vc3_vel<false><<<grid3(nx, ny, nz), BLK3, 0, st>>>(k);
+    ctx->launches++;
+    const size_t nVx = (size_t)(nx + 1) * (ny + 2) * (nz + 2), nVy = (size_t)(nx + 2) * (ny + 1) * (nz + 2), nVz = (size_t)(nx + 2) * (ny + 2) * (nz + 1);
+    if (diag && F(Ux) && F(Uy) && F(Uz)) {  // velocity2displacement!(stokes, dt) BEFORE flow_bcs!  :594
+        k_scale3<<<ctx->sm_count * 8, 256, 0, st>>>(nVx, nVy, nVz, F(Ux), F(Uy), F(Uz), k.Vx, k.Vy, k.Vz, o->dt);
+        ctx->launches++;
+    }
+    JR_CHECK_LAUNCH();
+    if ((rc = jr_launch_flow_bcs3d(ctx, k.Vx, k.Vy, k.Vz, p->n, p->fs, p->ns, p->pe))) return rc;   // flow_bcs!  :595
+    if (p->multi) {  // update_halo!(@velocity(stokes)...)  :596
+        const int32_t eVx[3] = {nx + 1, ny + 2, nz + 2}, eVy[3] = {nx + 2, ny + 1, nz + 2}, eVz[3] = {nx + 2, ny + 2, nz + 1};
+        const jr_harr H[3] = {jr_harr_dense(k.Vx, eVx, p->n), jr_harr_dense(k.Vy, eVy, p->n), jr_harr_dense(k.Vz, eVz, p->n)};
+        if ((rc = jr_comm_halo(ctx, H, 3))) return rc;
+    }
+    return JR_OK;
+}
+
+// bring the final τ and η (sets niter & 1) back into the caller's arrays; expose the solver-local λ
+static int plan3_finish(jr_context *ctx, const jr_fields *s, Plan3 *p, int64_t niter)
+{
+    cudaStream_t st = ctx->stream;
+    if (niter & 1) {
+        for (int q = 0; q < T_COUNT; q++) JR_CUDA(cudaMemcpyAsync(p->tau[0][q], p->tau[1][q], p->tbytes[q], cudaMemcpyDeviceToDevice, st));
+        JR_CUDA(cudaMemcpyAsync(p->eta[0], p->eta[1], p->nc * 8, cudaMemcpyDeviceToDevice, st));
+    }
+    if (F(lam)) JR_CUDA(cudaMemcpyAsync(F(lam), p->k.lam, p->nc * 8, cudaMemcpyDeviceToDevice, st));
+    return JR_OK;
+}
+
+// norms  Stokes3D.jl:601-611 (quirk Q4: ‖R‖₂ / ((nx_g−1)(ny_g−1)(nz_g−1)), RP by the LOCAL length)
+static int norms3d_vc(jr_context *ctx, const jr_fields *s, const jr_stokes_opts *o, Plan3 *p, double e[4])
+{
+    void *slots_v = nullptr;
+    int st = jr_ctx_scratch(ctx, "norm_slots", 16 * sizeof(double), &slots_v);
+    if (st) return st;
+    double *slots = (double *)slots_v;
+    const int nx = p->nx, ny = p->ny, nz = p->nz;
+    const int32_t nRx[3] = {nx - 1, ny, nz}, nRy[3] = {nx, ny - 1, nz}, nRz[3] = {nx, ny, nz - 1}, nP[3] = {nx, ny, nz};
+    if ((st = jr_launch_sumsq(ctx, F(Rx), nRx, 1, slots + 0))) return st;
+    if ((st = jr_launch_sumsq(ctx, F(Ry), nRy, 1, slots + 1))) return st;
+    if ((st = jr_launch_sumsq(ctx, F(Rz), nRz, 1, slots + 2))) return st;
+    if ((st = jr_launch_sumsq(ctx, F(RP), nP, 0, slots + 3))) return st;
+    if ((st = jr_comm_allreduce_dev(ctx, slots, 4, 0))) return st;   // norm_mpi: Allreduce(sum) of the local sums of squares
+    JR_CUDA(cudaMemcpyAsync(ctx->h_pinned, slots, 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    JR_CUDA(cudaStreamSynchronize(ctx->stream));
+    const double ng = (double)(o->n_g[0] - 1) * (o->n_g[1] - 1) * (o->n_g[2] - 1);
+    e[0] = sqrt(ctx->h_pinned[0]) / ng;
+    e[1] = sqrt(ctx->h_pinned[1]) / ng;
+    e[2] = sqrt(ctx->h_pinned[2]) / ng;
+    e[3] = sqrt(ctx->h_pinned[3]) / ((double)nx * ny * nz);
+    return JR_OK;
+}
+
+// exit kernels  Stokes3D.jl:641-655
+static int post_VC3(jr_context *ctx, const jr_fields *s, const jr_stokes_opts *o, Plan3 *p)
+{
+    const int nx = p->nx, ny = p->ny, nz = p->nz;
+    cudaStream_t st = ctx->stream;
+    if (F(wyz) || F(wxz) || F(wxy)) { k_vorticity3d<<<grid3(nx + 1, ny + 1, nz + 1), BLK3, 0, st>>>(p->k, F(wyz), F(wxz), F(wxy)); ctx->launches++; }
+    if (F(eyz_c) && F(exz_c) && F(exy_c)) { k_shear2center3d<<<grid3(nx, ny, nz), BLK3, 0, st>>>(nx, ny, nz, F(eyz_c), F(exz_c), F(exy_c), F(eyz), F(exz), F(exy)); ctx->launches++; }
+    if (F(pyz_c) && F(pxz_c) && F(pxy_c)) { k_shear2center3d<<<grid3(nx, ny, nz), BLK3, 0, st>>>(nx, ny, nz, F(pyz_c), F(pxz_c), F(pxy_c), F(pyz), F(pxz), F(pxy)); ctx->launches++; }
+    if (F(dyz_c) && F(dxz_c) && F(dxy_c) && F(dyz) && F(dxz) && F(dxy)) {
+        k_shear2center3d<<<grid3(nx, ny, nz), BLK3, 0, st>>>(nx, ny, nz, F(dyz_c), F(dxz_c), F(dxy_c), F(dyz), F(dxz), F(dxy));
+        ctx->launches++;
+    }
+    k_inv_stag3d<<<grid3(nx, ny, nz), BLK3, 0, st>>>(nx, ny, nz, F(EII_pl), F(pxx), F(pyy), F(pzz), F(pyz), F(pxz), F(pxy), 1, o->dt);   // accumulate_tensor!
+    k_axpy3<<<(unsigned)((p->nc + 255) / 256), 256, 0, st>>>(p->nc, F(EVol_pl), F(e_vol_pl), o->dt);                                      // accumulate_vol!
+    ctx->launches += 2;
+    JR_CHECK_LAUNCH();
+    // multi_copy! τ → τ_o (edge set over ni.+1, centre set over ni)
+    double *dst[9] = {F(txx_o), F(tyy_o), F(tzz_o), F(tyz_o), F(txz_o), F(txy_o), F(tyz_o_c), F(txz_o_c), F(txy_o_c)};
+    double *src[9] = {F(txx), F(tyy), F(tzz), F(tyz), F(txz), F(txy), F(tyz_c), F(txz_c), F(txy_c)};
+    const size_t by[9] = {p->nc * 8, p->nc * 8, p->nc * 8, p->nyz * 8, p->nxz * 8, p->nxy * 8, p->nc * 8, p->nc * 8, p->nc * 8};
+    for (int q = 0; q < 9; q++) JR_CUDA(cudaMemcpyAsync(dst[q], src[q], by[q], cudaMemcpyDeviceToDevice, st));
+    return JR_OK;
+}
+
+static void fill_result3(jr_context *ctx, jr_stokes_result *res, int64_t iter, int64_t cont, double err)
+{
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    res->iter = iter; res->nhist = cont; res->err = err;
+    res->time_s = ms * 1e-3;
+    res->kernel_launches = ctx->launches;
+}
+
+extern "C" {
+
+int jr_stokes3d_iterate_VC(jr_context *ctx, const jr_fields *s, const jr_stokes_opts *o, const jr_vc_inputs *vc, int64_t niter, int finish,
+                           jr_stokes_result *res)
+{
+    JR_REQUIRE(ctx, JR_ERR_ARG, "null context");
+    int st = check3d_vc(s, o, vc);
+    if (st) return st;
+    JR_CUDA(cudaSetDevice(ctx->device));
+    Plan3 p;
+    ctx->launches = 0;
+    if ((st = plan3_begin(ctx, s, o, vc, &p))) return st;
+    if ((st = pre_VC3(ctx, s, o, &p))) return st;
+    JR_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    for (int64_t it = 0; it < niter; it++)
+        if ((st = plan3_iter(ctx, &p, it, (ctx->flags & JR_FLAG_DIAG_EVERY_ITER) || it == niter - 1, s, o))) return st;
+    JR_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+    if ((st = plan3_finish(ctx, s, &p, niter))) return st;
+    if (finish && (st = post_VC3(ctx, s, o, &p))) return st;
+    JR_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (res) fill_result3(ctx, res, niter, 0, NAN);
+    return JR_OK;
+}
+
+int jr_stokes3d_solve_VC(jr_context *ctx, const jr_fields *s, const jr_stokes_opts *o, const jr_vc_inputs *vc, jr_stokes_result *res)
+{
+    JR_REQUIRE(ctx && res, JR_ERR_ARG, "null context/result");
+    int st = check3d_vc(s, o, vc);
+    if (st) return st;
+    JR_REQUIRE(res->err_evo1 && res->err_evo2 && res->norm_Rx && res->norm_Ry && res->norm_Rz && res->norm_divV, JR_ERR_ARG,
+               "result history arrays must be provided");
+    JR_CUDA(cudaSetDevice(ctx->device));
+    Plan3 p;
+    ctx->launches = 0;
+    if ((st = plan3_begin(ctx, s, o, vc, &p))) return st;
+    if ((st = pre_VC3(ctx, s, o, &p))) return st;
+    double err_it1 = 1.0, err = INFINITY;
+    int64_t iter = 0, cont = 0;
+    int status = JR_OK;
+    JR_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    while (iter < 2 || (((err / err_it1) > o->eps_rel && err > o->eps_abs) && iter <= o->iterMax)) {  // Stokes3D.jl:511
+        const int64_t next = iter + 1;
+        // the loop can only end right after a sample (or at iter = 2 / beyond iterMax): diagnostics written there reproduce the final state
+        const bool diag = (ctx->flags & JR_FLAG_DIAG_EVERY_ITER) || (next % o->nout == 0) || next > o->iterMax || next <= 2;
+        if ((st = plan3_iter(ctx, &p, iter, diag, s, o))) return st;
+        iter += 1;
+        if (iter % o->nout == 0 && iter > 1) {
+            double e[4];
+            if ((st = norms3d_vc(ctx, s, o, &p, e))) return st;
+            res->norm_Rx[cont] = e[0]; res->norm_Ry[cont] = e[1]; res->norm_Rz[cont] = e[2]; res->norm_divV[cont] = e[3];
+            err = fmax(fmax(e[0], e[1]), fmax(e[2], e[3]));
+            if (std::isnan(e[0]) || std::isnan(e[1]) || std::isnan(e[2]) || std::isnan(e[3])) err = NAN;
+            res->err_evo1[cont] = err; res->err_evo2[cont] = iter;
+            cont += 1;
+            err_it1 = fmax(fmax(res->norm_Rx[0], res->norm_Ry[0]), fmax(res->norm_Rz[0], res->norm_divV[0]));
+            if (std::isnan(err)) { status = JR_ERR_NAN; break; }  // isnan(err) && error("NaN(s)")  Stokes3D.jl:631
+        }
+    }
+    JR_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+    if ((st = plan3_finish(ctx, s, &p, iter))) return st;
+    if (status == JR_OK && (st = post_VC3(ctx, s, o, &p))) return st;
+    JR_CUDA(cudaStreamSynchronize(ctx->stream));
+    fill_result3(ctx, res, iter, cont, err);
+    if (status) jr_set_error("NaN(s)");
+    return status;
+}
+
+int jr_compute_viscosity3d(jr_context *ctx, const jr_fields *s, const jr_stokes_opts *o, const jr_vc_inputs *vc, double nu)
+{
+    JR_REQUIRE(ctx && s && o && vc && F(eta) && vc->ph_center, JR_ERR_ARG, "jr_compute_viscosity3d: null argument");
+    jr_phase_tab pt;
+    int st = jr_make_phase_tab(vc, &pt);
+    if (st) return st;
+    const size_t nc = (size_t)s->n[0] * s->n[1] * s->n[2];
+    k_viscosity3d<<<(unsigned)((nc + 255) / 256), 256, 0, ctx->stream>>>(nc, pt, vc->ph_center, F(eta), nu, o->visc_cutoff_lo, o->visc_cutoff_hi);
+    ctx->launches++;
+    JR_CHECK_LAUNCH();
+    JR_CUDA(cudaStreamSynchronize(ctx->stream));
+    return JR_OK;
+}
+
+int jr_compute_rhog3d(jr_context *ctx, const jr_fields *s, const jr_vc_inputs *vc)
+{
+    JR_REQUIRE(ctx && s && vc && F(rhogx) && F(rhogy) && F(rhogz) && vc->ph_center, JR_ERR_ARG, "jr_compute_rhog3d: null argument");
+    jr_phase_tab pt;
+    int st = jr_make_phase_tab(vc, &pt);
+    if (st) return st;
+    k_rhog3d<<<grid3(s->n[0], s->n[1], s->n[2]), BLK3, 0, ctx->stream>>>(s->n[0], s->n[1], s->n[2], pt, vc->ph_center, F(T), F(Pargs), F(rhogx), F(rhogy), F(rhogz));
+    ctx->launches++;
+    JR_CHECK_LAUNCH();
+    JR_CUDA(cudaStreamSynchronize(ctx->stream));
+    return JR_OK;
+}
+
+int jr_tensor_invariant3d(jr_context *ctx, double *II, const double *xx, const double *yy, const double *zz, const double *yz, const double *xz,
+                          const double *xy, const int32_t n[3])
+{
+    JR_REQUIRE(ctx && II && xx && yy && zz && yz && xz && xy && n, JR_ERR_ARG, "jr_tensor_invariant3d: null argument");
+    k_inv_stag3d<<<grid3(n[0], n[1], n[2]), BLK3, 0, ctx->stream>>>(n[0], n[1], n[2], II, xx, yy, zz, yz, xz, xy, 0, 0.0);
+    ctx->launches++;
+    JR_CHECK_LAUNCH();
+    JR_CUDA(cudaStreamSynchronize(ctx->stream));
+    return JR_OK;
+}
+
+int jr_shear2center3d(jr_context *ctx, double *yz_c, double *xz_c, double *xy_c, const double *yz, const double *xz, const double *xy, const int32_t n[3])
+{
+    JR_REQUIRE(ctx && yz_c && xz_c && xy_c && yz && xz && xy && n, JR_ERR_ARG, "jr_shear2center3d: null argument");
+    k_shear2center3d<<<grid3(n[0], n[1], n[2]), BLK3, 0, ctx->stream>>>(n[0], n[1], n[2], yz_c, xz_c, xy_c, yz, xz, xy);
+    ctx->launches++;
+    JR_CHECK_LAUNCH();
+    JR_CUDA(cudaStreamSynchronize(ctx->stream));
+    return JR_OK;
+}
+
+}  // extern "C"

@@ -137,6 +137,7 @@ def solve_(stokes: StokesArrays, pt_stokes, grid, flow_bcs, ρg, *rest, kwargs=N
       3D-VA  solve_(stokes, pt, grid, bcs, ρg, K, G, dt, igg)                          Stokes3D.jl:18-41
       2D-V2  solve_(stokes, pt, di,   bcs, ρg, G, K, dt, igg)                          Stokes2D.jl:181-196   (G before K in 2D)
       2D-VC  solve_(stokes, pt, di,   bcs, ρg, phase_ratios, rheology, args, dt, igg)  Stokes2D.jl:577-599
+      3D-VC  solve_(stokes, pt, grid, bcs, ρg, phase_ratios, rheology, args, dt, igg)  Stokes3D.jl:447-466
     """
     if rest and isinstance(rest[0], PhaseRatios):
         if len(stokes.ni) == 2:
@@ -321,7 +322,8 @@ def vc_inputs(rheology, phase_ratios: PhaseRatios, *, free_surface: float = 0.0)
         for k, v in r.items():
             setattr(arr[i], k, v)
     vc = _abi.VcInputs()
-    vc.nphase, vc.g_scalar, vc.phases, vc.free_surface = len(rows), 0, arr, float(free_surface)
+    # compute_gravity(ConstantGravity) is a Number: only the last ρg component is filled (BuoyancyForces.jl:70-71)
+    vc.nphase, vc.g_scalar, vc.phases, vc.free_surface = len(rows), 1, arr, float(free_surface)
     g = _rheology.gravity_of(rheology)
     for q in range(3):
         vc.g[q] = float(g[q])
@@ -422,6 +424,8 @@ def compute_ρg_(ρg, phase_ratios, rheology, args, stokes):
 def tensor_invariant_(T, ni):
     """tensor_invariant!(A::SymmetricTensor) — src/stokes/StressKernels.jl:442-480 (2D)."""
     if len(ni) != 2:
-        raise NotImplementedError
+        from .stokes3d_vc import tensor_invariant3d_
+
+        return tensor_invariant3d_(T, ni)
     _abi.check(_abi.lib().jr_tensor_invariant2d(context(), data_ptr(T.II), data_ptr(T.xx), data_ptr(T.yy), data_ptr(T.xy),
                                                  _abi.i32x(list(ni) + [1])))

@@ -322,7 +322,7 @@ class VcInputs(C.Structure):
                 ("free_surface", C.c_double)]
 
 
-def vc_inputs(rows, g, ratios: dict, *, g_scalar=False, free_surface=0.0, Phase=StokesPhase, Inputs=VcInputs):
+def vc_inputs(rows, g, ratios: dict, *, g_scalar=True, free_surface=0.0, Phase=StokesPhase, Inputs=VcInputs):
     """rows: list of dicts with the StokesPhase fields; ratios: name -> column-major array [node..., phase]."""
     arr = (Phase * len(rows))()
     for i, r in enumerate(rows):
