@@ -392,3 +392,69 @@ def random_vc3d(ni, nphase=3, seed=20261017, *, dt=0.4, mixed=True):
     pt = PTStokesCoeffs(li, grid.di.center, CFL=0.9 / math.sqrt(3.1))
     return SimpleNamespace(ni=tuple(ni), li=li, di=grid.di.center, grid=grid, igg=IGG(), pt_stokes=pt, dt=dt, fields=f, ratios=ratios,
                            rheology=tuple(mats), kwargs=dict(viscosity_cutoff=(1.0e-3, 1.0e2)))
+
+
+def diffusion_multiphase(nd=3, n=32, *, nsub=8):
+    """test/test_diffusion3D_multiphase.jl:88-203 (nd = 3) and test/test_diffusion2D_multiphase.jl:81-181 (nd = 2): heatdiffusion_PT! in the
+    rheology form with TWO phases (PT_Density ρ0 = 3.0e3 | 3.3e3, Cp = 1.2e3, k = 3, ConstantRadioactiveHeat 1e-6 | 1e-7; phase 2 inside a
+    sphere/disc of radius 10 km at the domain centre), T(z) linear 1600–1900 K + 100 K inside the same sphere, top 300 K / bottom 3500 K,
+    sides no-flux, dt = 50 kyr.  The reference builds the phase ratios from JustPIC particles (20–40 per cell); here they are the
+    (hat-weighted at the face nodes) volume fractions from nsub^nd sub-samples per cell — the goldens hold to the reference tolerance."""
+    from .types import TemperatureBoundaryConditions
+
+    kyr = 1.0e3 * 3600 * 24 * 365.25
+    dt = 50 * kyr
+    ni, li = (n,) * nd, (100.0e3,) * nd
+    origin = (0.0,) * (nd - 1) + (-li[-1],)
+    grid = Geometry(ni, li, origin=origin)
+    di = grid.di.center
+    xci = grid.xci
+    zc = xci[-1]
+    T = np.zeros(tuple(m + 2 for m in ni), order="F")
+    prof = zc * (1900.0 - 1600.0) / zc.min() + 1600.0
+    centre = tuple(0.5 * l for l in li[:-1]) + (-0.5 * li[-1],)
+    r = 10.0e3
+    inside = lambda *X: sum((x - c) ** 2 for x, c in zip(X, centre)) <= r ** 2
+    mesh = lambda cs: np.meshgrid(*cs, indexing="ij")
+    pert = inside(*mesh(xci))
+    if nd == 3:
+        T[:, :, 1:-1] = prof[None, None, :]          # init_T! over (1:nx+2, 1:ny+2, 1:nz)
+        bc = TemperatureBoundaryConditions(no_flux=dict(left=True, right=True, top=False, bot=False, front=True, back=True),
+                                           constant_value=dict(left=True, right=True, top=300.0, bot=3500.0, front=True, back=True))
+        H, ϵ, CFL, nt = 1.0e-6, 1.0e-8, 0.95 / math.sqrt(3.1), 10
+        kwargs = dict(iterMax=10.0e3, nout=1.0e2, verbose=False)
+    else:
+        T[:, 1:-1] = prof[None, :]
+        bc = TemperatureBoundaryConditions(no_flux=dict(left=True, right=True, top=False, bot=False),
+                                           constant_value=dict(left=True, right=True, top=300.0, bot=3500.0))
+        H, ϵ, CFL, nt = 0.0, 1.0e-5, 0.95 / math.sqrt(2), 20
+        kwargs = dict(iterMax=1.0e3, nout=10, verbose=False)
+
+    def ratios(coords, hat):
+        """fraction of phase 2 around every node: uniform sub-samples of the cell (centres) or hat-weighted over ±d (face nodes)"""
+        off = (np.arange(nsub) + 0.5) / nsub - 0.5
+        if hat:
+            off = off * 2.0
+        acc = np.zeros(tuple(c.size for c in coords))
+        wsum = 0.0
+        for idx in np.ndindex(*(nsub,) * nd):
+            o = [off[i] for i in idx]
+            w = float(np.prod([1.0 - abs(v) for v in o])) if hat else 1.0
+            X = mesh([c + o[q] * di[q] for q, c in enumerate(coords)])
+            acc += w * inside(*X)
+            wsum += w
+        f2 = acc / wsum
+        return _onehot([1.0 - f2, f2])
+
+    xvi = grid.xvi
+    locs = dict(center=xci)
+    for a, nm in enumerate(("Vx", "Vy", "Vz")[:nd]):
+        locs[nm] = tuple(xvi[q] if q == a else xci[q] for q in range(nd))
+    phase = {nm: np.asfortranarray(ratios(c, nm != "center")) for nm, c in locs.items()}
+    rows = [dict(rho_kind=1, has_Hr=1, rho0=3.0e3, alpha=1.5e-5, beta=0.0, T0=0.0, P0=0.0, Cp=1.2e3, k=3.0, Hr=1.0e-6),
+            dict(rho_kind=1, has_Hr=1, rho0=3.3e3, alpha=1.5e-5, beta=0.0, T0=0.0, P0=0.0, Cp=1.2e3, k=3.0, Hr=1.0e-7)]
+    ρCp = np.full(ni, 1.2e3 * 3.3e3, order="F")
+    K = np.full(ni, 3.0, order="F")
+    pt = pt_thermal_coeffs_arrays(K, ρCp, dt, di, li, ϵ=ϵ, CFL=CFL)
+    return SimpleNamespace(ni=ni, li=li, di=di, grid=grid, dt=dt, nt=nt, T=T, bc=bc, pt=pt, perturbation=pert, δT=100.0, phase=phase, phases=rows,
+                           H=np.full(ni, H, order="F"), P=np.zeros(ni, order="F"), kwargs=kwargs, thermal_bcs_first=(nd == 2))

@@ -107,8 +107,59 @@ def main():
     assert np.allclose(out.err_evo1, [h[1] for h in hist], rtol=1e-9, atol=0), (out.err_evo1[-3:], hist[-3:])
     worst = max(max_rel_diff(to_host(st.slots()[nm]), blocks[rank][nm]) for nm in names[:10])
     assert worst <= 1e-8, ("converged fields", worst)
+    # ---- 5. 3D-VC (multiphase visco-elasto-plastic), fixed number of iterations: ητ, τ-shear and V halos every iteration -----
+    from justrelax_jl_b200 import PhaseRatios, rheology as R
+    from justrelax_jl_b200.stokes3d_vc import iterate3d_VC_
+    niv = (14, 12, 11)
+    iggv_ng = mrank.n_g(niv, dims)
+    blocks, vcs, sets = [], [], []
+    for r in range(world):
+        sv = setups.random_vc3d(niv, seed=900 + r)
+        sets.append(sv)
+        d = po.alloc_stokes(niv, sv.fields)
+        d["Pargs"] = d["P"]
+        blocks.append(d)
+        vcs.append(po.vc_inputs(R.lower_stokes(sv.rheology), R.gravity_of(sv.rheology), sv.ratios))
+    sv = sets[rank]
+    flags = dict(free_slip=[1] * 6, no_slip=[0] * 6, periodic=[0] * 6)
+    optsv = po.make_opts(sv.pt_stokes, sv.grid._di.center, sv.dt, flags, iggv_ng, iterMax=100, nout=100, viscosity_relaxation=0.3,
+                         viscosity_cutoff=sv.kwargs["viscosity_cutoff"])
+    stv, extrav = device_stokes(niv, blocks[rank])
+    mrank.vc_iterate(po, blocks, optsv, vcs, dims, niv, 5, finish=True)
+    prv = PhaseRatios.from_arrays(B200Backend, **sv.ratios)
+    iggv = type(igg)(me=rank, dims=dims, nprocs=world, coords=coords_all[rank])
+    ρgv = (extrav["rhogx"], extrav["rhogy"], extrav["rhogz"])
+    iterate3d_VC_(stv, sv.pt_stokes, sv.grid, bcs, ρgv, prv, sv.rheology, dict(T=extrav["T"], P=stv.P), sv.dt, 5, iggv, finish=True,
+                  kwargs=dict(viscosity_relaxation=0.3, viscosity_cutoff=sv.kwargs["viscosity_cutoff"]))
+    vnames = ["Vx", "Vy", "Vz", "P", "txx", "tyy", "tzz", "tyz", "txz", "txy", "tyz_c", "txz_c", "txy_c", "eta", "etatau", "lam", "Rx", "Ry", "Rz", "RP",
+              "pyz", "pxz", "pxy", "tII", "EII_pl", "txy_o"]
+    worst_vc = max(max_rel_diff(to_host(stv.slots()[nm]), blocks[rank][nm]) for nm in vnames)
+    assert worst_vc <= 1e-12, ("3D-VC iterate", rank, worst_vc, {nm: max_rel_diff(to_host(stv.slots()[nm]), blocks[rank][nm]) for nm in vnames})
+
+    # ---- 6. heatdiffusion_PT! 3D with phase ratios, fixed number of iterations: T halo every iteration ------------------------------
+    from justrelax_jl_b200 import thermal as jth
+    from justrelax_jl_b200.types import Geometry
+    import test_gpu_thermal as tg
+    nit = (13, 12, 10)
+    li = (1.0e5, 1.1e5, 1.2e5)
+    gridt = Geometry(nit, li)
+    bct = tg.bc_variants(3)[0]
+    tblocks = [po.alloc_thermal(nit, tg.random_thermal(nit, 40 + r, 3)) for r in range(world)]
+    ptt = type("PT", (), {})()
+    ptt.ϵ, ptt.max_lxyz, ptt.Vpdτ = 1e-8, max(li), min(gridt.di.center) * 0.5
+    ot = po.thermal_opts(_di=gridt._di.center, dt=1.0e11, eps=1e-8, iterMax=10, nout=4, max_lxyz=ptt.max_lxyz, Vpdtau=ptt.Vpdτ, form=1,
+                         phases=tg.PHASES, bc=bct)
+    tht, extrat = tg.to_device(nit, tblocks[rank])
+    mrank.thermal_iterate(po, tblocks, ot, dims, nit, 4)
+    ptt.θr_dτ, ptt.dτ_ρ = extrat["theta_r_dtau"], extrat["dtau_rho"]
+    pht = tg._Phase()
+    pht.center, pht.Vx, pht.Vy, pht.Vz = extrat["phase_c"], extrat["phase_x"], extrat["phase_y"], extrat["phase_z"]
+    jth.thermal_iterate_(tht, ptt, bct, tg.rheology_of(tg.PHASES), dict(P=extrat["P"], T=tht.T), 1.0e11, gridt, 4,
+                         kwargs=dict(verbose=False, phase=pht, igg=iggv))
+    tg.compare(tht, tblocks[rank], ["T", "qTx", "qTy", "qTz", "qTx2", "qTy2", "qTz2", "ResT"], f"thermal 3D multi-rank rank {rank}")
+
     dist.barrier()
-    print(f"MGPU_OK rank {rank}/{world} dims {dims}: halo, all-reduce, 3D-VA iterate (fused+unfused), solve iter={out.iter} worst={worst:.2e}", flush=True)
+    print(f"MGPU_OK rank {rank}/{world} dims {dims}: halo, all-reduce, 3D-VA iterate (fused+unfused), solve iter={out.iter} worst={worst:.2e}, 3D-VC worst={worst_vc:.2e}, thermal OK", flush=True)
     comm.finalize_global_grid()
     dist.destroy_process_group()
 

@@ -93,3 +93,33 @@ def va_solve(po, ranks, opts, dims, ni):
             hist.append((it, err, nrm))
             err_it1 = max(hist[0][2])
     return it, hist
+
+
+# ---------------------------------------------------------------------------------------------------------
+# multi-rank 3D-VC oracle: the loop body in the three pieces the reference separates with update_halo! (Stokes3D.jl:515 ητ,
+# :578-580 τyz/τxz/τxy, :596 V)
+def vc_iterate(po, ranks, opts, vcs, dims, ni, niter, finish=False):
+    import ctypes as C
+    L = po.lib()
+    fss = [po.make_fields(d, ni) for d in ranks]
+    hs = [C.c_void_p(L.orc_vc3_begin(C.byref(fs), C.byref(opts), C.byref(vc))) for fs, vc in zip(fss, vcs)]
+    for _ in range(niter):
+        for piece, names in ((0, ("etatau",)), (1, ("tyz", "txz", "txy")), (2, ("Vx", "Vy", "Vz"))):
+            for fs, vc, h in zip(fss, vcs, hs):
+                L.orc_vc3_step(C.byref(fs), C.byref(opts), C.byref(vc), h, piece)
+            for nm in names:
+                update_halo([d[nm] for d in ranks], dims, ni)
+    for fs, h in zip(fss, hs):
+        L.orc_vc3_end(C.byref(fs), C.byref(opts), h, int(finish))
+
+
+# multi-rank heatdiffusion_PT! iterations: update_halo!(thermal.T) after thermal_bcs! (DiffusionPT_solver.jl:110, 261)
+def thermal_iterate(po, ranks, opts, dims, ni, niter):
+    import ctypes as C
+    fss = [po.thermal_fields(d, ni) for d in ranks]
+    for _ in range(niter):
+        for fs in fss:
+            po.lib().orc_thermal_iterate_once(C.byref(fs), C.byref(opts))
+        update_halo([d["T"] for d in ranks], dims, ni)
+    for fs in fss:
+        po.lib().orc_thermal_check_res(C.byref(fs), C.byref(opts))

@@ -87,7 +87,7 @@ def test_shearband3d_solve_matches_oracle(oracle):
     jst.compute_viscosity_(st, pr, args, s.rheology, (-math.inf, math.inf))
     jst.flow_bcs_(st, s.flow_bcs)
     ρg = (extra["rhogx"], extra["rhogy"], extra["rhogz"])
-    for step in range(5):
+    for step in range(8):
         ref = oracle.solve3d_VC(d, s.ni, opts, vc)
         out = jst.solve_(st, s.pt_stokes, s.grid, s.flow_bcs, ρg, pr, s.rheology, args, s.dt, s.igg, kwargs=s.kwargs)
         assert abs(out.iter - ref["iter"]) <= max(0.01 * ref["iter"], 1), (step, out.iter, ref["iter"])

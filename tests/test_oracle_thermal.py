@@ -1,6 +1,8 @@
 """CPU oracle of heatdiffusion_PT! pinned on the reference's own goldens (no GPU).
 
  - test/test_diffusion2D.jl:127-135 (config 1): T[18,18] ≈ 1817.9448461176817, T[17,17] ≈ 1827.4674313638786 (atol 0.1)
+ - test/test_diffusion2D_multiphase.jl:185-195: two phases, T[18,18] ≈ 1814.029, T[17,17] ≈ 1823.548 (atol 0.1)
+ - test/test_diffusion3D_multiphase.jl:207-215: two phases in 3D, T[16,16,16] ≈ 1816.8262937737384, interior[16,16,16] ≈ 1834.4197141500213 (rtol 1e-3)
  - thermal_bcs! ghost identities of test/test_boundary_conditions2D.jl (constant value / no flux / periodic)
 """
 import numpy as np
@@ -77,3 +79,40 @@ def test_array_form_matches_rheology_form_with_constant_density(oracle):
         res.append((f["T"].copy(), out["iter"]))
     assert res[0][1] == res[1][1]
     assert np.allclose(res[0][0], res[1][0], rtol=1e-13, atol=0)
+
+
+def run_diffusion_multiphase(oracle, s):
+    import ctypes as C
+
+    nd = len(s.ni)
+    init = dict(T=s.T, H=s.H, P=s.P, theta_r_dtau=s.pt.θr_dτ, dtau_rho=s.pt.dτ_ρ, phase_c=s.phase["center"], phase_x=s.phase["Vx"], phase_y=s.phase["Vy"])
+    if nd == 3:
+        init["phase_z"] = s.phase["Vz"]
+    f = oracle.alloc_thermal(s.ni, init)
+    o = oracle.thermal_opts(_di=s.grid._di.center, dt=s.dt, eps=s.pt.ϵ, iterMax=s.kwargs["iterMax"], nout=s.kwargs["nout"], max_lxyz=s.pt.max_lxyz,
+                            Vpdtau=s.pt.Vpdτ, form=1, phases=s.phases, bc=s.bc)
+    fs = oracle.thermal_fields(f, s.ni)
+    if s.thermal_bcs_first:
+        oracle.lib().orc_thermal_bcs(C.byref(fs), C.byref(o))
+    f["T"][(slice(1, -1),) * nd][s.perturbation] += s.δT
+    outs = [oracle.heatdiffusion_PT(f, s.ni, o) for _ in range(s.nt)]
+    return f, outs
+
+
+def test_diffusion2d_multiphase_reference_golden(oracle):
+    s = setups.diffusion_multiphase(2)
+    f, outs = run_diffusion_multiphase(oracle, s)
+    T = f["T"]
+    # Julia (1-based): T[nx_T >>> 1 + 1, ny_T >>> 1 + 1] = T[18, 18], T[(nx >>> 1) + 1, (ny >>> 1) + 1] = T[17, 17]
+    assert abs(T[17, 17] - 1814.029) < 1.0e-1
+    assert abs(T[16, 16] - 1823.548) < 1.0e-1
+
+
+def test_diffusion3d_multiphase_reference_golden(oracle):
+    s = setups.diffusion_multiphase(3)
+    f, outs = run_diffusion_multiphase(oracle, s)
+    T = f["T"]
+    # Julia (1-based): T[16, 16, 16] on the ghosted array and on the interior view
+    assert abs(T[15, 15, 15] / 1816.8262937737384 - 1) < 1.0e-3
+    assert abs(T[1:-1, 1:-1, 1:-1][15, 15, 15] / 1834.4197141500213 - 1) < 1.0e-3
+    assert all(o["err"] <= 1e-8 for o in outs)
