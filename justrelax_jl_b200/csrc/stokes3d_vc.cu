@@ -99,44 +99,124 @@ __global__ void __launch_bounds__(256) k_vc3_prep(const __grid_constant__ V3 a, 
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------------
-struct EdgeIn { double eta, P, e[6], t[6], to[6]; };
-
-// one edge family of update_stresses_center_vertex_ps!  StressKernels.jl:716-778 (yz), :781-849 (xz), :852-921 (xy)
-template <int SLOT, bool DIAG>
-__device__ __forceinline__ void vc3_edge(const V3 &a, const jr_phase_tab &pt, const double *__restrict__ ph, size_t stride, size_t v, const EdgeIn &in,
-                                         double *__restrict__ lamv, double *__restrict__ tau_out, double *__restrict__ epl)
-{
+// phase mixture at one staggered node: the ratios are loaded ONCE into registers and every phase-weighted quantity the stress kernel
+// needs is formed from them with the reference's operation order (fn_ratio phases.jl:5-16, plastic_params_phase StressUpdate.jl:153-176,
+// compute_yieldfunction_phase :384-452, compute_plastic_gradients_phase :463-550).  NP = compile-time bound on the number of phases.
+template <int NP>
+struct Mix {
+    double r[NP];
+    double G, Kb, eta_reg;
     bool is_pl;
-    double eta_reg;
-    jr_plastic_params(pt, ph, stride, v, is_pl, eta_reg);
-    const double _Gdt = jr_inv(jr_ratio_G(pt, ph, stride, v) * a.dt), Kv = jr_ratio_Kb(pt, ph, stride, v);
-    const double etav = in.eta, dtr = jr_inv(a.th + etav * _Gdt + 1.0);
-    double d[6], trial[6];
+};
+template <int NP>
+__device__ __forceinline__ void mix_load(const jr_phase_tab &pt, const double *__restrict__ ph, size_t stride, size_t q, Mix<NP> &m)
+{
+    m.G = 0.0; m.Kb = 0.0; m.eta_reg = 0.0; m.is_pl = false;
+#pragma unroll
+    for (int p = 0; p < NP; p++) {
+        if (p < pt.n) {
+            const double r = __ldg(ph + (size_t)p * stride + q);
+            m.r[p] = r;
+            m.G += (r == 0.0) ? 0.0 : pt.G[p] * r;
+            m.Kb += (r == 0.0) ? 0.0 : pt.Kb[p] * r;
+            const bool pl = (r != 0.0) && pt.has_pl[p];
+            if (pl) m.is_pl = true;
+            m.eta_reg += (pl ? pt.eta_vp[p] : 0.0) * r;
+        } else
+            m.r[p] = 0.0;
+    }
+}
+template <int NP>
+__device__ __forceinline__ double mix_yield_F(const jr_phase_tab &pt, const Mix<NP> &m, double P, double tII)
+{
+    double acc = 0.0;
+#pragma unroll
+    for (int p = 0; p < NP; p++) {
+        if (p < pt.n) {
+            const double r = m.r[p];
+            double v = 0.0;
+            if (r != 0.0) {
+                const double Fp = pt.has_pl[p] ? (tII - pt.cosphi[p] * pt.C[p] - pt.sinphi[p] * (P - 0.0)) - 2 * pt.eta_vp[p] * (0.0 * 0.5) : tII;
+                v = r * Fp;
+            }
+            acc = p == 0 ? v : acc + v;
+        }
+    }
+    return acc;
+}
+template <int NP>
+__device__ __forceinline__ void mix_dP(const jr_phase_tab &pt, const Mix<NP> &m, double &dQdP, double &dFdP)
+{
+    dQdP = 0.0; dFdP = 0.0;
+#pragma unroll
+    for (int p = 0; p < NP; p++) {
+        if (p < pt.n) {
+            const double r = m.r[p];
+            if (r != 0.0) {
+                dQdP = fma(r, pt.has_pl[p] ? -pt.sinpsi[p] : 0.0, dQdP);
+                dFdP = fma(r, pt.has_pl[p] ? -pt.sinphi[p] : 0.0, dFdP);
+            }
+        }
+    }
+}
+// one component of ∂Q/∂τ (tensor convention, shear slots halved) at the trial stress t with second invariant tII — evaluated lazily,
+// only where the node yields (the value is the one compute_plastic_gradients_phase returns: same operations, same order)
+template <int NP, bool SHEAR>
+__device__ __forceinline__ double mix_dQdt(const jr_phase_tab &pt, const Mix<NP> &m, double t, double tII)
+{
+    double acc = 0.0;
+#pragma unroll
+    for (int p = 0; p < NP; p++) {
+        if (p < pt.n) {
+            const double r = m.r[p];
+            if (r != 0.0) {
+                const double g = pt.has_pl[p] ? (SHEAR ? 0.5 * (t / tII) : 0.5 * t / tII) : 0.0;
+                acc = fma(r, g, acc);
+            }
+        }
+    }
+    return acc;
+}
+
+// one edge family of update_stresses_center_vertex_ps!  StressKernels.jl:716-778 (yz), :781-849 (xz), :852-921 (xy).
+// t/to/e: the six Voigt components (xx, yy, zz, yz, xz, xy) interpolated to the edge; SLOT = the component that lives on this edge.
+template <int SLOT, bool DIAG, int NP>
+__device__ __forceinline__ void vc3_edge(const V3 &a, const jr_phase_tab &pt, const double *__restrict__ ph, size_t stride, size_t v, double etav, double Pv,
+                                         const double (&t)[6], const double (&to)[6], const double (&e)[6], double *__restrict__ lamv,
+                                         double *__restrict__ tau_out, double *__restrict__ epl)
+{
+    Mix<NP> m;
+    mix_load<NP>(pt, ph, stride, v, m);
+    const double _Gdt = jr_inv(m.G * a.dt);
+    const double dtr = jr_inv(a.th + etav * _Gdt + 1.0);
+    double trial[6], dS = 0.0;
 #pragma unroll
     for (int q = 0; q < 6; q++) {
-        d[q] = jr_stress_increment(in.t[q], in.to[q], etav, in.e[q], _Gdt, dtr);
-        trial[q] = in.t[q] + d[q];
+        const double d = jr_stress_increment(t[q], to[q], etav, e[q], _Gdt, dtr);
+        trial[q] = t[q] + d;
+        if (q == SLOT) dS = d;
     }
     const double tII = jr_second_invariant<6>(trial);
-    double dQ[6], dQdP, dFdP;
-    jr_plastic_grads<6>(pt, ph, stride, v, trial, dQ, dQdP, dFdP);
-    const double volume = isinf(Kv) ? 0.0 : Kv * a.dt * dFdP * dQdP;
-    const double Fv = jr_yield_F(pt, ph, stride, v, in.P, tII);
-    double tn, ep;
-    if (is_pl && tII != 0.0 && Fv > 0) {
-        const double l = (1.0 - a.rel) * lamv[v] + a.rel * (fmax(Fv, 0.0) / (etav * dtr + eta_reg + volume));
-        lamv[v] = l;
-        ep = l * dQ[SLOT];
-        tn = in.t[SLOT] + fma(-2.0, etav * ep * dtr, d[SLOT]);
-    } else {
-        tn = in.t[SLOT] + d[SLOT];
-        ep = 0.0;
+    double tn = t[SLOT] + dS, ep = 0.0;
+    if (m.is_pl && tII != 0.0) {
+        const double Fv = mix_yield_F<NP>(pt, m, Pv, tII);
+        if (Fv > 0) {
+            double dQdP, dFdP;
+            mix_dP<NP>(pt, m, dQdP, dFdP);
+            const double volume = isinf(m.Kb) ? 0.0 : m.Kb * a.dt * dFdP * dQdP;
+            const double l = (1.0 - a.rel) * lamv[v] + a.rel * (fmax(Fv, 0.0) / (etav * dtr + m.eta_reg + volume));
+            lamv[v] = l;
+            ep = l * mix_dQdt<NP, true>(pt, m, trial[SLOT], tII);
+            tn = t[SLOT] + fma(-2.0, etav * ep * dtr, dS);
+        }
     }
     tau_out[v] = tn;
     if (DIAG) epl[v] = ep;
 }
 
-template <bool DIAG>
+// Node (i,j,k) of the (nx+1, ny+1, nz+1) lattice updates its yz, xz, xy edges and its cell centre.  All neighbour addresses are a family
+// base index (cell / yz / xz / xy array shapes) plus small precomputed offsets (clamped: 0 or ± one stride).
+template <bool DIAG, int NP>
 __global__ void __launch_bounds__(256) k_vc3_stress(const __grid_constant__ V3 a, const __grid_constant__ jr_phase_tab pt)
 {
     const int nx = a.nx, ny = a.ny, nz = a.nz;
@@ -147,71 +227,66 @@ __global__ void __launch_bounds__(256) k_vc3_stress(const __grid_constant__ V3 a
     const int i0 = jr_clamp(i - 1, 1, nx), ic = jr_clamp(i, 1, nx), i1 = jr_clamp(i + 1, 1, nx);
     const int j0 = jr_clamp(j - 1, 1, ny), jc = jr_clamp(j, 1, ny), j1 = jr_clamp(j + 1, 1, ny);
     const int k0 = jr_clamp(k - 1, 1, nz), kc = jr_clamp(k, 1, nz), k1 = jr_clamp(k + 1, 1, nz);
-    const double *eta = a.eta_o;  // the relaxed viscosity of this iteration
+    // family bases at (ic, jc, kc) and offsets
+    const int csy = nx, csz = nx * ny;                    // cell arrays (nx, ny, nz)
+    const int ysy = nx, ysz = nx * (ny + 1);              // yz arrays   (nx, ny+1, nz+1)
+    const int zsy = nx + 1, zsz = (nx + 1) * ny;          // xz arrays   (nx+1, ny, nz+1)
+    const int xsy = nx + 1, xsz = (nx + 1) * (ny + 1);    // xy arrays   (nx+1, ny+1, nz)
+    const size_t cb = IX3(nx, ny, ic, jc, kc), yb = IX3(nx, ny + 1, ic, jc, kc), zb = IX3(nx + 1, ny, ic, jc, kc), xb = IX3(nx + 1, ny + 1, ic, jc, kc);
+    const int di0 = i0 - ic, di1 = i1 - ic, dj0 = j0 - jc, dj1 = j1 - jc, dk0 = k0 - kc, dk1 = k1 - kc;
+    const int ci0 = di0, cj0 = dj0 * csy, ck0 = dk0 * csz;
+    const double *__restrict__ eta = a.eta_o;  // the relaxed viscosity of this iteration
+#define LC(A, o) __ldg((A) + cb + (o))
+#define LY(A, o) __ldg((A) + yb + (o))
+#define LZ(A, o) __ldg((A) + zb + (o))
+#define LX(A, o) __ldg((A) + xb + (o))
     // clamped averages  StressKernels.jl:620-669 (argument order = summation order)
-#define AV_YZ(A) (0.25 * (CC(A, ic, j0, k0) + CC(A, ic, jc, k0) + CC(A, ic, j0, kc) + CC(A, ic, jc, kc)))
-#define AV_XZ(A) (0.25 * (CC(A, i0, jc, k0) + CC(A, ic, jc, k0) + CC(A, i0, jc, kc) + CC(A, ic, jc, kc)))
-#define AV_XY(A) (0.25 * (CC(A, i0, j0, kc) + CC(A, ic, j0, kc) + CC(A, i0, jc, kc) + CC(A, ic, jc, kc)))
-#define HARM_YZ(A) (4 / (1 / CC(A, ic, j0, k0) + 1 / CC(A, ic, jc, k0) + 1 / CC(A, ic, j0, kc) + 1 / CC(A, ic, jc, kc)))
-#define HARM_XZ(A) (4 / (1 / CC(A, i0, jc, k0) + 1 / CC(A, ic, jc, k0) + 1 / CC(A, i0, jc, kc) + 1 / CC(A, ic, jc, kc)))
-#define HARM_XY(A) (4 / (1 / CC(A, i0, j0, kc) + 1 / CC(A, ic, j0, kc) + 1 / CC(A, i0, jc, kc) + 1 / CC(A, ic, jc, kc)))
-#define AV_YZ_Z(A) (0.25 * (XY(A, ic, jc, k0) + XY(A, i1, jc, k0) + XY(A, ic, jc, kc) + XY(A, i1, jc, kc)))
-#define AV_YZ_Y(A) (0.25 * (XZ(A, ic, j0, kc) + XZ(A, i1, j0, kc) + XZ(A, ic, jc, kc) + XZ(A, i1, jc, kc)))
-#define AV_XZ_Z(A) (0.25 * (XY(A, ic, jc, k0) + XY(A, ic, j1, k0) + XY(A, ic, jc, kc) + XY(A, ic, j1, kc)))
-#define AV_XZ_X(A) (0.25 * (YZ(A, i0, jc, kc) + YZ(A, ic, jc, kc) + YZ(A, ic, j1, kc) + YZ(A, i0, j1, kc)))
-#define AV_XY_Y(A) (0.25 * (XZ(A, ic, j0, kc) + XZ(A, ic, jc, kc) + XZ(A, ic, j0, k1) + XZ(A, ic, jc, k1)))
-#define AV_XY_X(A) (0.25 * (YZ(A, i0, jc, kc) + YZ(A, ic, jc, kc) + YZ(A, i0, jc, k1) + YZ(A, ic, jc, k1)))
+#define AV_YZ(A) (0.25 * (LC(A, cj0 + ck0) + LC(A, ck0) + LC(A, cj0) + LC(A, 0)))
+#define AV_XZ(A) (0.25 * (LC(A, ci0 + ck0) + LC(A, ck0) + LC(A, ci0) + LC(A, 0)))
+#define AV_XY(A) (0.25 * (LC(A, ci0 + cj0) + LC(A, cj0) + LC(A, ci0) + LC(A, 0)))
+#define HARM_YZ(A) (4 / (1 / LC(A, cj0 + ck0) + 1 / LC(A, ck0) + 1 / LC(A, cj0) + 1 / LC(A, 0)))
+#define HARM_XZ(A) (4 / (1 / LC(A, ci0 + ck0) + 1 / LC(A, ck0) + 1 / LC(A, ci0) + 1 / LC(A, 0)))
+#define HARM_XY(A) (4 / (1 / LC(A, ci0 + cj0) + 1 / LC(A, cj0) + 1 / LC(A, ci0) + 1 / LC(A, 0)))
+#define AV_YZ_Z(A) (0.25 * (LX(A, dk0 * xsz) + LX(A, di1 + dk0 * xsz) + LX(A, 0) + LX(A, di1)))                       /* xy arrays */
+#define AV_YZ_Y(A) (0.25 * (LZ(A, dj0 * zsy) + LZ(A, di1 + dj0 * zsy) + LZ(A, 0) + LZ(A, di1)))                       /* xz arrays */
+#define AV_XZ_Z(A) (0.25 * (LX(A, dk0 * xsz) + LX(A, dj1 * xsy + dk0 * xsz) + LX(A, 0) + LX(A, dj1 * xsy)))           /* xy arrays */
+#define AV_XZ_X(A) (0.25 * (LY(A, di0) + LY(A, 0) + LY(A, dj1 * ysy) + LY(A, di0 + dj1 * ysy)))                       /* yz arrays */
+#define AV_XY_Y(A) (0.25 * (LZ(A, dj0 * zsy) + LZ(A, 0) + LZ(A, dj0 * zsy + dk1 * zsz) + LZ(A, dk1 * zsz)))           /* xz arrays */
+#define AV_XY_X(A) (0.25 * (LY(A, di0) + LY(A, 0) + LY(A, di0 + dk1 * ysz) + LY(A, dk1 * ysz)))                       /* yz arrays */
     if (i <= nx && j <= ny + 1 && k <= nz + 1) {  // ---- yz edge
         const size_t v = IX3(nx, ny + 1, i, j, k);
-        EdgeIn in;
-        in.eta = HARM_YZ(eta); in.P = AV_YZ(a.theta);
-        in.e[0] = AV_YZ(a.exx); in.e[1] = AV_YZ(a.eyy); in.e[2] = AV_YZ(a.ezz);
-        in.e[3] = a.eyz[v]; in.e[4] = AV_YZ_Y(a.exz); in.e[5] = AV_YZ_Z(a.exy);
-        in.t[0] = AV_YZ(a.txx_i); in.t[1] = AV_YZ(a.tyy_i); in.t[2] = AV_YZ(a.tzz_i);
-        in.t[3] = a.tyz_i[v]; in.t[4] = AV_YZ_Y(a.txz_i); in.t[5] = AV_YZ_Z(a.txy_i);
-        in.to[0] = AV_YZ(a.oxx); in.to[1] = AV_YZ(a.oyy); in.to[2] = AV_YZ(a.ozz);
-        in.to[3] = a.oyz[v]; in.to[4] = AV_YZ_Y(a.oxz); in.to[5] = AV_YZ_Z(a.oxy);
-        vc3_edge<3, DIAG>(a, pt, a.ph_yz, nyz, v, in, a.lamyz, a.tyz_o, a.pyz);
+        const double t[6] = {AV_YZ(a.txx_i), AV_YZ(a.tyy_i), AV_YZ(a.tzz_i), __ldg(a.tyz_i + v), AV_YZ_Y(a.txz_i), AV_YZ_Z(a.txy_i)};
+        const double to[6] = {AV_YZ(a.oxx), AV_YZ(a.oyy), AV_YZ(a.ozz), __ldg(a.oyz + v), AV_YZ_Y(a.oxz), AV_YZ_Z(a.oxy)};
+        const double e[6] = {AV_YZ(a.exx), AV_YZ(a.eyy), AV_YZ(a.ezz), __ldg(a.eyz + v), AV_YZ_Y(a.exz), AV_YZ_Z(a.exy)};
+        vc3_edge<3, DIAG, NP>(a, pt, a.ph_yz, nyz, v, HARM_YZ(eta), AV_YZ(a.theta), t, to, e, a.lamyz, a.tyz_o, a.pyz);
     }
     if (i <= nx + 1 && j <= ny && k <= nz + 1) {  // ---- xz edge
         const size_t v = IX3(nx + 1, ny, i, j, k);
-        EdgeIn in;
-        in.eta = HARM_XZ(eta); in.P = AV_XZ(a.theta);
-        in.e[0] = AV_XZ(a.exx); in.e[1] = AV_XZ(a.eyy); in.e[2] = AV_XZ(a.ezz);
-        in.e[3] = AV_XZ_X(a.eyz); in.e[4] = a.exz[v]; in.e[5] = AV_XZ_Z(a.exy);
-        in.t[0] = AV_XZ(a.txx_i); in.t[1] = AV_XZ(a.tyy_i); in.t[2] = AV_XZ(a.tzz_i);
-        in.t[3] = AV_XZ_X(a.tyz_i); in.t[4] = a.txz_i[v]; in.t[5] = AV_XZ_Z(a.txy_i);
-        in.to[0] = AV_XZ(a.oxx); in.to[1] = AV_XZ(a.oyy); in.to[2] = AV_XZ(a.ozz);
-        in.to[3] = AV_XZ_X(a.oyz); in.to[4] = a.oxz[v]; in.to[5] = AV_XZ_Z(a.oxy);
-        vc3_edge<4, DIAG>(a, pt, a.ph_xz, nxz, v, in, a.lamxz, a.txz_o, a.pxz);
+        const double t[6] = {AV_XZ(a.txx_i), AV_XZ(a.tyy_i), AV_XZ(a.tzz_i), AV_XZ_X(a.tyz_i), __ldg(a.txz_i + v), AV_XZ_Z(a.txy_i)};
+        const double to[6] = {AV_XZ(a.oxx), AV_XZ(a.oyy), AV_XZ(a.ozz), AV_XZ_X(a.oyz), __ldg(a.oxz + v), AV_XZ_Z(a.oxy)};
+        const double e[6] = {AV_XZ(a.exx), AV_XZ(a.eyy), AV_XZ(a.ezz), AV_XZ_X(a.eyz), __ldg(a.exz + v), AV_XZ_Z(a.exy)};
+        vc3_edge<4, DIAG, NP>(a, pt, a.ph_xz, nxz, v, HARM_XZ(eta), AV_XZ(a.theta), t, to, e, a.lamxz, a.txz_o, a.pxz);
     }
     if (i <= nx + 1 && j <= ny + 1 && k <= nz) {  // ---- xy edge
         const size_t v = IX3(nx + 1, ny + 1, i, j, k);
-        EdgeIn in;
-        in.eta = HARM_XY(eta); in.P = AV_XY(a.theta);
-        in.e[0] = AV_XY(a.exx); in.e[1] = AV_XY(a.eyy); in.e[2] = AV_XY(a.ezz);
-        in.e[3] = AV_XY_X(a.eyz); in.e[4] = AV_XY_Y(a.exz); in.e[5] = a.exy[v];
-        in.t[0] = AV_XY(a.txx_i); in.t[1] = AV_XY(a.tyy_i); in.t[2] = AV_XY(a.tzz_i);
-        in.t[3] = AV_XY_X(a.tyz_i); in.t[4] = AV_XY_Y(a.txz_i); in.t[5] = a.txy_i[v];
-        in.to[0] = AV_XY(a.oxx); in.to[1] = AV_XY(a.oyy); in.to[2] = AV_XY(a.ozz);
-        in.to[3] = AV_XY_X(a.oyz); in.to[4] = AV_XY_Y(a.oxz); in.to[5] = a.oxy[v];
-        vc3_edge<5, DIAG>(a, pt, a.ph_xy, nxy, v, in, a.lamxy, a.txy_o, a.pxy);
+        const double t[6] = {AV_XY(a.txx_i), AV_XY(a.tyy_i), AV_XY(a.tzz_i), AV_XY_X(a.tyz_i), AV_XY_Y(a.txz_i), __ldg(a.txy_i + v)};
+        const double to[6] = {AV_XY(a.oxx), AV_XY(a.oyy), AV_XY(a.ozz), AV_XY_X(a.oyz), AV_XY_Y(a.oxz), __ldg(a.oxy + v)};
+        const double e[6] = {AV_XY(a.exx), AV_XY(a.eyy), AV_XY(a.ezz), AV_XY_X(a.eyz), AV_XY_Y(a.exz), __ldg(a.exy + v)};
+        vc3_edge<5, DIAG, NP>(a, pt, a.ph_xy, nxy, v, HARM_XY(eta), AV_XY(a.theta), t, to, e, a.lamxy, a.txy_o, a.pxy);
     }
     if (i <= nx && j <= ny && k <= nz) {  // ---- centre  StressKernels.jl:923-986 (plain products and sums: no @muladd there)
-        const size_t c = IX3(nx, ny, i, j, k);
-        const double _Gdt = jr_inv(jr_ratio_G(pt, a.ph_c, nc, c) * a.dt);
-        bool is_pl;
-        double eta_reg;
-        jr_plastic_params(pt, a.ph_c, nc, c, is_pl, eta_reg);
-        const double K = jr_ratio_Kb(pt, a.ph_c, nc, c), et = eta[c];
+        const size_t c = cb;
+        Mix<NP> m;
+        mix_load<NP>(pt, a.ph_c, nc, c, m);
+        const double _Gdt = jr_inv(m.G * a.dt), K = m.Kb, et = __ldg(eta + c);
         const double dtr = jr_inv(a.th + et * _Gdt + 1.0);
         // cache_tensors  StressUpdate.jl:248-301 (_av_yz/_av_xz/_av_xy: mysum order k → j → i starting from 0.0, quirk Q15)
-        const double eij[6] = {a.exx[c], a.eyy[c], a.ezz[c],
-                               0.25 * ((((0.0 + YZ(a.eyz, i, j, k)) + YZ(a.eyz, i, j + 1, k)) + YZ(a.eyz, i, j, k + 1)) + YZ(a.eyz, i, j + 1, k + 1)),
-                               0.25 * ((((0.0 + XZ(a.exz, i, j, k)) + XZ(a.exz, i + 1, j, k)) + XZ(a.exz, i, j, k + 1)) + XZ(a.exz, i + 1, j, k + 1)),
-                               0.25 * ((((0.0 + XY(a.exy, i, j, k)) + XY(a.exy, i + 1, j, k)) + XY(a.exy, i, j + 1, k)) + XY(a.exy, i + 1, j + 1, k))};
-        double tij[6] = {a.txx_i[c], a.tyy_i[c], a.tzz_i[c], a.tyzc[c], a.txzc[c], a.txyc[c]};
-        const double tijo[6] = {a.oxx[c], a.oyy[c], a.ozz[c], a.oyzc[c], a.oxzc[c], a.oxyc[c]};
+        const double eij[6] = {__ldg(a.exx + c), __ldg(a.eyy + c), __ldg(a.ezz + c),
+                               0.25 * ((((0.0 + LY(a.eyz, 0)) + LY(a.eyz, ysy)) + LY(a.eyz, ysz)) + LY(a.eyz, ysy + ysz)),
+                               0.25 * ((((0.0 + LZ(a.exz, 0)) + LZ(a.exz, 1)) + LZ(a.exz, zsz)) + LZ(a.exz, 1 + zsz)),
+                               0.25 * ((((0.0 + LX(a.exy, 0)) + LX(a.exy, 1)) + LX(a.exy, xsy)) + LX(a.exy, 1 + xsy))};
+        double tij[6] = {__ldg(a.txx_i + c), __ldg(a.tyy_i + c), __ldg(a.tzz_i + c), a.tyzc[c], a.txzc[c], a.txyc[c]};
+        const double tijo[6] = {__ldg(a.oxx + c), __ldg(a.oyy + c), __ldg(a.ozz + c), __ldg(a.oyzc + c), __ldg(a.oxzc + c), __ldg(a.oxyc + c)};
         double d[6], trial[6];
 #pragma unroll
         for (int q = 0; q < 6; q++) {
@@ -219,18 +294,21 @@ __global__ void __launch_bounds__(256) k_vc3_stress(const __grid_constant__ V3 a
             trial[q] = tij[q] + d[q];
         }
         double tII = jr_second_invariant<6>(trial);
-        double dQ[6], dQdP, dFdP;
+        double dQdP, dFdP;
         const double Pr = a.theta[c];
-        jr_plastic_grads<6>(pt, a.ph_c, nc, c, trial, dQ, dQdP, dFdP);
-        const double volume = isinf(K) ? 0.0 : K * a.dt * dFdP * dQdP;
-        const double Fc = jr_yield_F(pt, a.ph_c, nc, c, Pr, tII);
+        mix_dP<NP>(pt, m, dQdP, dFdP);
         double lam = a.lam[c], evol = 0.0, epl[3] = {0.0, 0.0, 0.0};
-        if (is_pl && tII != 0.0 && Fc > 0) {
-            lam = (1.0 - a.rel) * lam + a.rel * (fmax(Fc, 0.0) / (et * dtr + eta_reg + volume));
+        bool yielding = false;
+        if (m.is_pl && tII != 0.0) yielding = mix_yield_F<NP>(pt, m, Pr, tII) > 0;
+        if (yielding) {
+            const double Fc = mix_yield_F<NP>(pt, m, Pr, tII);
+            const double volume = isinf(K) ? 0.0 : K * a.dt * dFdP * dQdP;
+            lam = (1.0 - a.rel) * lam + a.rel * (fmax(Fc, 0.0) / (et * dtr + m.eta_reg + volume));
             a.lam[c] = lam;
+            const double tIIt = tII;
 #pragma unroll
             for (int q = 0; q < 6; q++) {
-                const double e = lam * dQ[q];
+                const double e = lam * (q < 3 ? mix_dQdt<NP, false>(pt, m, trial[q], tIIt) : mix_dQdt<NP, true>(pt, m, trial[q], tIIt));
                 if (q < 3) epl[q] = e;
                 d[q] = d[q] - 2.0 * et * e * dtr;
                 tij[q] = d[q] + tij[q];
@@ -456,6 +534,21 @@ static int pre_VC3(jr_context *ctx, const jr_fields *s, const jr_stokes_opts *o,
     return JR_OK;
 }
 
+template <int NP>
+static void launch_stress_np(bool diag, dim3 grd, cudaStream_t st, const V3 &k, const jr_phase_tab &pt)
+{
+    if (diag) k_vc3_stress<true, NP><<<grd, BLK3, 0, st>>>(k, pt);
+    else k_vc3_stress<false, NP><<<grd, BLK3, 0, st>>>(k, pt);
+}
+static void launch_stress(bool diag, int nphase, dim3 grd, cudaStream_t st, const V3 &k, const jr_phase_tab &pt)
+{
+    if (nphase <= 1) launch_stress_np<1>(diag, grd, st, k, pt);
+    else if (nphase == 2) launch_stress_np<2>(diag, grd, st, k, pt);
+    else if (nphase == 3) launch_stress_np<3>(diag, grd, st, k, pt);
+    else if (nphase == 4) launch_stress_np<4>(diag, grd, st, k, pt);
+    else launch_stress_np<JR_MAX_PHASES>(diag, grd, st, k, pt);
+}
+
 // one PT iteration: τ set (it & 1) → set ((it + 1) & 1), η likewise
 static int plan3_iter(jr_context *ctx, Plan3 *p, int64_t it, bool diag, const jr_fields *s, const jr_stokes_opts *o)
 {
@@ -478,8 +571,7 @@ static int plan3_iter(jr_context *ctx, Plan3 *p, int64_t it, bool diag, const jr
         if (diag) k_vc3_prep<true, true><<<grid3(nx, ny, nz), BLK3, 0, st>>>(k, p->pt);
         else k_vc3_prep<false, true><<<grid3(nx, ny, nz), BLK3, 0, st>>>(k, p->pt);
     }
-    if (diag) k_vc3_stress<true><<<grid3(nx + 1, ny + 1, nz + 1), BLK3, 0, st>>>(k, p->pt);
-    else k_vc3_stress<false><<<grid3(nx + 1, ny + 1, nz + 1), BLK3, 0, st>>>(k, p->pt);
+    launch_stress(diag, p->pt.n, grid3(nx + 1, ny + 1, nz + 1), st, k, p->pt);
     ctx->launches += 2;
     JR_CHECK_LAUNCH();
     if (p->multi) {  // update_halo!(τyz); update_halo!(τxz); update_halo!(τxy)  :578-580

@@ -286,6 +286,9 @@ def convection3d(nx=32, ny=32, nz=32, *, igg: IGG | None = None, plastic=True):
     213-300: three phases — crust (LinearViscous + ConstantElasticity + DruckerPrager_regularised, PT_Density),
     a hot low-density blob (LinearViscous + ConstantElasticity, PT_Density) and a weak top layer (LinearViscous, ConstantDensity) —
     ConstantHeatCapacity / ConstantConductivity per phase, free slip, T fixed at top and bottom, no flux on the sides.
+    The conductivities differ only mildly between phases and the thermal PT CFL is 0.8/√3.1: the reference's PT scheme sizes dτ_ρ from the
+    cell conductivity but fluxes with the 2-cell average, so a conductivity jump ≥ 1.15 at CFL = 0.95/√3.1 exceeds the 3D stability bound
+    (observed: the oracle itself diverges at 64³ with k = 1 | 0.5 | 5).
     Deviations from the miniapp (stated in DESIGN.md): non-dimensional O(1) parameters instead of GEO_units scaling, no
     NonLinearSoftening / latent heat / shear heating, phases sampled on the staggered grid instead of from particles.
     Returns Stokes (3D-VC) and thermal (rheology form with phase ratios) inputs for one coupled time step."""
@@ -306,10 +309,10 @@ def convection3d(nx=32, ny=32, nz=32, *, igg: IGG | None = None, plastic=True):
                             Conductivity=R.ConstantConductivity(k=1.0), CompositeRheology=R.CompositeRheology(crust),
                             Gravity=R.ConstantGravity(g=10.0), Elasticity=el),
         R.SetMaterialParams(Phase=2, Density=R.PT_Density(ρ0=0.9, α=3.0e-2, β=1.0e-3, T0=0.0, P0=0.0), HeatCapacity=R.ConstantHeatCapacity(Cp=1.0),
-                            Conductivity=R.ConstantConductivity(k=0.5), CompositeRheology=R.CompositeRheology((R.LinearViscous(η=0.1), el_blob)),
+                            Conductivity=R.ConstantConductivity(k=0.9), CompositeRheology=R.CompositeRheology((R.LinearViscous(η=0.1), el_blob)),
                             Gravity=R.ConstantGravity(g=10.0), Elasticity=el_blob),
-        R.SetMaterialParams(Phase=3, Density=R.ConstantDensity(ρ=0.01), HeatCapacity=R.ConstantHeatCapacity(Cp=1.0),
-                            Conductivity=R.ConstantConductivity(k=5.0), CompositeRheology=R.CompositeRheology((R.LinearViscous(η=0.01),)),
+        R.SetMaterialParams(Phase=3, Density=R.ConstantDensity(ρ=0.8), HeatCapacity=R.ConstantHeatCapacity(Cp=1.0),
+                            Conductivity=R.ConstantConductivity(k=1.1), CompositeRheology=R.CompositeRheology((R.LinearViscous(η=0.01),)),
                             Gravity=R.ConstantGravity(g=10.0)),
     )
 
@@ -336,7 +339,7 @@ def convection3d(nx=32, ny=32, nz=32, *, igg: IGG | None = None, plastic=True):
     return SimpleNamespace(ni=ni, li=li, di=di, grid=grid, igg=igg, pt_stokes=pt, flow_bcs=flow_bcs, thermal_bc=thermal_bc, dt=0.05, fields=fields,
                            rheology=rheology, ratios=ratios, T=T,
                            kwargs=dict(verbose=False, iterMax=150.0e3, nout=1.0e3, viscosity_cutoff=(1.0e-3, 1.0e3)),
-                           thermal_kwargs=dict(iterMax=150.0e3, nout=1.0e3, verbose=False))
+                           thermal_kwargs=dict(iterMax=150.0e3, nout=1.0e3, verbose=False), thermal_CFL=0.8 / math.sqrt(3.1))
 
 
 def random_vc3d(ni, nphase=3, seed=20261017, *, dt=0.4, mixed=True):

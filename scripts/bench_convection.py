@@ -4,7 +4,7 @@
 (overlap 2; 8 GPUs → 2×2×2, local 257³ = global 512³).  One JSON line (rank 0): Stokes and thermal PT iterations/s, T_eff per GPU with the
 A_eff of SURVEY.md §8d (512 and 200 B/cell at N = 3 phases), max over ranks of the device-timed regions.
 
-Usage: python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 scripts/bench_convection.py [--n 257]
+Usage: python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 scripts/bench_convection.py [--size 257]
        (or plain `python scripts/bench_convection.py` on one GPU)
 """
 import argparse
@@ -19,7 +19,7 @@ sys.path.insert(0, ROOT)
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=257)
+    ap.add_argument("--size", type=int, default=257)
     ap.add_argument("--stokes-iters", type=int, default=100)
     ap.add_argument("--thermal-iters", type=int, default=100)
     ap.add_argument("--steps", type=int, default=2, help="coupled time steps timed (after one warm-up step)")
@@ -38,7 +38,7 @@ def main():
     from justrelax_jl_b200.stokes3d_vc import iterate3d_VC_
     from justrelax_jl_b200.types import IGG, ThermalArrays
 
-    n = args.n
+    n = args.size
     igg = comm.init_global_grid(n, n, n) if world > 1 else IGG()
     s = setups.convection3d(n, n, n, igg=igg)
     dev = lambda a: PTArray(B200Backend)(a)
@@ -50,7 +50,7 @@ def main():
     z = lambda: dev(np.zeros(s.ni, order="F"))
     ρg = (z(), z(), z())
     jst.flow_bcs_(st, s.flow_bcs)
-    pt_th = jth.PTThermalCoeffs(B200Backend, s.rheology, pr, a, s.dt, s.ni, s.di, s.li, ϵ=1e-5, CFL=0.95 / math.sqrt(3.1))
+    pt_th = jth.PTThermalCoeffs(B200Backend, s.rheology, pr, a, s.dt, s.ni, s.di, s.li, ϵ=1e-5, CFL=s.thermal_CFL)
     kw_s = dict(viscosity_cutoff=s.kwargs["viscosity_cutoff"])
     kw_t = dict(phase=pr, verbose=False, igg=igg)
 

@@ -88,7 +88,7 @@ def main():
                 pr = PhaseRatios.from_arrays(B200Backend, **{k: v for k, v in s.ratios.items() if k in ("center", "Vx", "Vy", "Vz")})
                 P = dev(np.zeros(s.ni, order="F"))
                 a = dict(T=th.T, P=P)
-                pt = jth.PTThermalCoeffs(B200Backend, s.rheology, pr, a, s.dt, s.ni, s.di, s.li, ϵ=1e-5, CFL=0.95 / math.sqrt(3.1))
+                pt = jth.PTThermalCoeffs(B200Backend, s.rheology, pr, a, s.dt, s.ni, s.di, s.li, ϵ=1e-5, CFL=s.thermal_CFL)
                 kw = dict(phase=pr, verbose=False)
                 run = lambda k: jth.thermal_iterate_(th, pt, s.thermal_bc, s.rheology, a, s.dt, s.grid, k, kwargs=kw)
                 run(args.warmup)
