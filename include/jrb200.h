@@ -209,6 +209,13 @@ int jr_tensor_invariant3d(jr_context *ctx, double *II, const double *xx, const d
 /* shear2center!(A::SymmetricTensor) 3D  src/ext/CUDA/3D.jl:319-327 → src/Interpolations.jl:313-323 */
 int jr_shear2center3d(jr_context *ctx, double *yz_c, double *xz_c, double *xy_c, const double *yz, const double *xz, const double *xy, const int32_t n[3]);
 
+/* update_phase_ratios_{2,3}D!(phase_ratios, phase_arrays, xci, xvi) — grid-based phases (config 5)  src/ext/CUDA/3D.jl:519-539 →
+ * src/phases/PhaseRatios.jl:21-78.  phase_arrays: nphase DEVICE arrays (nx, ny[, nz]); xci/xvi: HOST coordinate vectors per dimension;
+ * outputs: DEVICE ratio arrays laid out [phase][node] at centres, vertices, velocity faces and (3D) edge midpoints; NULL = skip. */
+int jr_phase_ratios_from_arrays(jr_context *ctx, int32_t ndim, const int32_t n[3], int32_t nphase, const double *const *phase_arrays,
+                                const double *const *xci_host, const double *const *xvi_host, double *center, double *vertex, double *Vx,
+                                double *Vy, double *Vz, double *xy, double *yz, double *xz);
+
 /* --- stand-alone kernels the reference exposes outside the loops ----------- */
 /* flow_bcs!(stokes, bcs)  src/ext/CUDA/3D.jl:195-218 → BoundaryConditions.jl:65-100 */
 int jr_flow_bcs3d(jr_context *ctx, double *Ax, double *Ay, double *Az, const int32_t n[3],

@@ -178,6 +178,7 @@ def _declare(L):
     L.jr_compute_rhog3d.argtypes = [vp, vp, vc]
     L.jr_tensor_invariant3d.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32p]
     L.jr_shear2center3d.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32p]
+    L.jr_phase_ratios_from_arrays.argtypes = [vp, C.c_int32, i32p, C.c_int32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), vp, vp, vp, vp, vp, vp, vp, vp]
     L.jr_heatdiffusion_PT.argtypes = [vp, C.POINTER(ThermalFields), C.POINTER(ThermalOpts), vp, vp, C.POINTER(ThermalResult)]
     L.jr_thermal_iterate.argtypes = [vp, C.POINTER(ThermalFields), C.POINTER(ThermalOpts), C.c_int64, C.POINTER(ThermalResult)]
     L.jr_thermal_bcs.argtypes = [vp, vp, C.c_int32, i32p, C.POINTER(ThermalOpts)]

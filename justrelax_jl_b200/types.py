@@ -480,3 +480,30 @@ class PhaseRatios:
             if a is not None:
                 pr.nphases = int(a.shape[-1])
         return pr
+
+
+def update_phase_ratios_(phase_ratios: PhaseRatios, phase_arrays, xci, xvi):
+    """update_phase_ratios_2D!/update_phase_ratios_3D!(phase_ratios, phase_arrays, xci, xvi) — src/phases/PhaseRatios.jl:21-78 (GPU method
+    src/ext/CUDA/3D.jl:519-539): fills every allocated location of `phase_ratios` from N phase arrays (B200 arrays with values in [0, 1])."""
+    import ctypes as C
+
+    from . import _abi
+    from .stokes import context
+
+    nd = phase_arrays[0].dim()
+    ni = tuple(int(v) for v in phase_arrays[0].shape)
+    for a in phase_arrays:
+        if not is_device_array(a) or tuple(a.shape) != ni:
+            raise ValueError("update_phase_ratios_: phase arrays must be B200 arrays of identical shape")
+    if len(phase_arrays) != phase_ratios.nphases:
+        raise ValueError(f"{len(phase_arrays)} phase arrays for PhaseRatios with {phase_ratios.nphases} phases")
+    vp3 = lambda ptrs: (C.c_void_p * max(len(ptrs), 3))(*ptrs)
+    xc = [np.ascontiguousarray(np.asarray(x, dtype=np.float64)) for x in xci]
+    xv = [np.ascontiguousarray(np.asarray(x, dtype=np.float64)) for x in xvi]
+    out = [getattr(phase_ratios, nm) for nm in ("center", "vertex", "Vx", "Vy", "Vz", "xy", "yz", "xz")]
+    _abi.check(_abi.lib().jr_phase_ratios_from_arrays(context(), nd, _abi.i32x(list(ni) + [1] * (3 - nd)), len(phase_arrays),
+                                                        vp3([data_ptr(a) for a in phase_arrays]), vp3([x.ctypes.data for x in xc]),
+                                                        vp3([x.ctypes.data for x in xv]), *[None if a is None else data_ptr(a) for a in out]))
+
+
+update_phase_ratios_2D_ = update_phase_ratios_3D_ = update_phase_ratios_

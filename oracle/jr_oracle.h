@@ -158,6 +158,10 @@ void *orc_vc3_begin(const orc_fields *s, const orc_stokes_opts *o, const orc_vc_
 void orc_vc3_step(const orc_fields *s, const orc_stokes_opts *o, const orc_vc_inputs *vc, void *h, int piece);
 void orc_vc3_end(const orc_fields *s, const orc_stokes_opts *o, void *h, int finish);
 
+/* ---- grid-based phase ratios (oracle/phase_ratios.c): update_phase_ratios_{2,3}D!  src/phases/PhaseRatios.jl:21-78 ---- */
+void orc_phase_ratios_from_arrays(int nd, const int32_t n[3], int N, const double *const *ph, const double *const *xc, const double *const *xv,
+                                  double *center, double *vertex, double *Vx, double *Vy, double *Vz, double *xy, double *yz, double *xz);
+
 /* norms (src/Utils.jl:698-701), interior slice 2:end-1 in every dim when interior!=0 */
 double orc_sumsq_interior(const double *A, int n1, int n2, int n3, int interior);
 

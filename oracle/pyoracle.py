@@ -392,3 +392,25 @@ def tensor_invariant2d(xx, yy, xy):
     II = np.zeros(xx.shape, order="F")
     lib().orc_tensor_invariant2d(_dp(II), _dp(xx), _dp(yy), _dp(xy), C.c_int(xx.shape[0]), C.c_int(xx.shape[1]))
     return II
+
+
+def phase_ratios_from_arrays(phase_arrays, xci, xvi):
+    """update_phase_ratios_{2,3}D!(phase_ratios, phase_arrays, xci, xvi) → dict of (nodes..., nphase) column-major arrays"""
+    ni = phase_arrays[0].shape
+    nd, N = len(ni), len(phase_arrays)
+    n3 = (C.c_int32 * 3)(*[int(ni[d]) if d < nd else 1 for d in range(3)])
+    ph = [np.asfortranarray(a, dtype=np.float64) for a in phase_arrays]
+    xc = [np.ascontiguousarray(x, dtype=np.float64) for x in xci]
+    xv = [np.ascontiguousarray(x, dtype=np.float64) for x in xvi]
+    pp = lambda arrs: (C.POINTER(C.c_double) * max(len(arrs), 3))(*[_dp(a) for a in arrs])
+    shp = dict(center=ni, vertex=tuple(n + 1 for n in ni))
+    for a, nm in enumerate(("Vx", "Vy", "Vz")[:nd]):
+        shp[nm] = tuple(n + (1 if b == a else 0) for b, n in enumerate(ni))
+    if nd == 3:
+        nx, ny, nz = ni
+        shp.update(xy=(nx + 1, ny + 1, nz), yz=(nx, ny + 1, nz + 1), xz=(nx + 1, ny, nz + 1))
+    out = {k: np.zeros(v + (N,), order="F") for k, v in shp.items()}
+    g = lambda k: _dp(out[k]) if k in out else None
+    lib().orc_phase_ratios_from_arrays(C.c_int(nd), n3, C.c_int(N), pp(ph), pp(xc), pp(xv), g("center"), g("vertex"), g("Vx"), g("Vy"), g("Vz"),
+                                       g("xy"), g("yz"), g("xz"))
+    return out
