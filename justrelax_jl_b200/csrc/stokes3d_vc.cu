@@ -45,36 +45,55 @@ struct V3 {
 #define VZ(i, j, k) a.Vz[IX3(nx + 2, ny + 2, i, j, k)]
 
 // ---------------------------------------------------------------------------------------------------------------------------------
-// MAXLOC: compute ητ here (single rank); otherwise ητ was computed by k_maxloc3 and halo-exchanged before this launch
-template <bool DIAG, bool MAXLOC>
+// MAXLOC: compute ητ here (single rank); otherwise ητ was computed by k_maxloc3 and halo-exchanged before this launch.
+// NP = compile-time bound on the number of phases: the centre ratios are loaded once and reused for K, G, ρ and η.
+template <bool DIAG, bool MAXLOC, int NP>
 __global__ void __launch_bounds__(256) k_vc3_prep(const __grid_constant__ V3 a, const __grid_constant__ jr_phase_tab pt)
 {
     const int nx = a.nx, ny = a.ny, nz = a.nz;
     const int i = blockIdx.x * blockDim.x + threadIdx.x + 1, j = blockIdx.y * blockDim.y + threadIdx.y + 1, k = blockIdx.z + 1;
     if (i > nx || j > ny || k > nz) return;
     const size_t nc = (size_t)nx * ny * nz, c = IX3(nx, ny, i, j, k);
-    const double eta = a.eta_i[c];
+    const double eta = __ldg(a.eta_i + c);
     double ett;
-    if (MAXLOC) {  // compute_maxloc!(ητ, η)  Stokes3D.jl:514 ; Utils.jl:409-461
+    if (MAXLOC) {  // compute_maxloc!(ητ, η)  Stokes3D.jl:514 ; Utils.jl:409-461 (window clamped to the array)
+        const int sy = nx, sz = nx * ny;
+        const int oi[3] = {jr_clamp(i - 1, 1, nx) - i, 0, jr_clamp(i + 1, 1, nx) - i};
+        const int oj[3] = {(jr_clamp(j - 1, 1, ny) - j) * sy, 0, (jr_clamp(j + 1, 1, ny) - j) * sy};
+        const int ok[3] = {(jr_clamp(k - 1, 1, nz) - k) * sz, 0, (jr_clamp(k + 1, 1, nz) - k) * sz};
         double x = -INFINITY;
-        for (int kk = k - 1; kk <= k + 1; kk++)
-            for (int jj = j - 1; jj <= j + 1; jj++)
-                for (int ii = i - 1; ii <= i + 1; ii++) {
-                    const double e = a.eta_i[IX3(nx, ny, jr_clamp(ii, 1, nx), jr_clamp(jj, 1, ny), jr_clamp(kk, 1, nz))];
+#pragma unroll
+        for (int kk = 0; kk < 3; kk++)
+#pragma unroll
+            for (int jj = 0; jj < 3; jj++)
+#pragma unroll
+                for (int ii = 0; ii < 3; ii++) {
+                    const double e = __ldg(a.eta_i + c + (oi[ii] + oj[jj] + ok[kk]));
                     if (e > x) x = e;
                 }
         ett = x;
         a.etatau[c] = ett;
     } else
         ett = a.etatau[c];
-    // compute_∇V!  VelocityKernels.jl:3-6
-    const double vx0 = VX(i, j + 1, k + 1), vy0 = VY(i + 1, j, k + 1), vz0 = VZ(i + 1, j + 1, k);
-    const double dVx = (-vx0 + VX(i + 1, j + 1, k + 1)) * a._dx;
-    const double dVy = (-vy0 + VY(i + 1, j + 1, k + 1)) * a._dy;
-    const double dVz = (-vz0 + VZ(i + 1, j + 1, k + 1)) * a._dz;
+    // compute_∇V!  VelocityKernels.jl:3-6   (Vx (nx+1, ny+2, nz+2), Vy (nx+2, ny+1, nz+2), Vz (nx+2, ny+2, nz+1))
+    const int xsy = nx + 1, xsz = (nx + 1) * (ny + 2), ysy = nx + 2, ysz = (nx + 2) * (ny + 1), zsy = nx + 2, zsz = (nx + 2) * (ny + 2);
+    const double *__restrict__ pVx = a.Vx + IX3(nx + 1, ny + 2, i, j + 1, k + 1);
+    const double *__restrict__ pVy = a.Vy + IX3(nx + 2, ny + 1, i + 1, j, k + 1);
+    const double *__restrict__ pVz = a.Vz + IX3(nx + 2, ny + 2, i + 1, j + 1, k);
+    const double vx0 = pVx[0], vy0 = pVy[0], vz0 = pVz[0];
+    const double dVx = (-vx0 + pVx[1]) * a._dx;
+    const double dVy = (-vy0 + pVy[ysy]) * a._dy;
+    const double dVz = (-vz0 + pVz[zsz]) * a._dz;
     const double divV = dVx + dVy + dVz;
+    // phase ratios at the centre, loaded once
+    double r[NP];
+#pragma unroll
+    for (int p = 0; p < NP; p++) r[p] = p < pt.n ? __ldg(a.ph_c + (size_t)p * nc + c) : 0.0;
     // compute_P!(θ, P0, RP, ∇V, Q, ητ, rheology, phase_ratios, …)  Stokes3D.jl:518-531 ; PressureKernels.jl:87-102,186-195
-    const double Kc = jr_ratio_Kb(pt, a.ph_c, nc, c), Gc = jr_ratio_G(pt, a.ph_c, nc, c);
+    double Kc = 0.0, Gc = 0.0;
+#pragma unroll
+    for (int p = 0; p < NP; p++)
+        if (p < pt.n) { Kc += (r[p] == 0.0) ? 0.0 : pt.Kb[p] * r[p]; Gc += (r[p] == 0.0) ? 0.0 : pt.G[p] * r[p]; }
     double RP, th = a.theta[c];
     jr_compute_P_point(RP, th, a.P0[c], divV, a.Q[c], ett, Kc, Gc, a.dt, a.r, a.th);
     a.theta[c] = th;
@@ -83,18 +102,37 @@ __global__ void __launch_bounds__(256) k_vc3_prep(const __grid_constant__ V3 a, 
     a.exx[c] = dVx - d3;
     a.eyy[c] = dVy - d3;
     a.ezz[c] = dVz - d3;
-    YZ(a.eyz, i, j, k) = 0.5 * (a._dz * (vy0 - VY(i + 1, j, k)) + a._dy * (vz0 - VZ(i + 1, j, k)));
-    XZ(a.exz, i, j, k) = 0.5 * (a._dz * (vx0 - VX(i, j + 1, k)) + a._dx * (vz0 - VZ(i, j + 1, k)));
-    XY(a.exy, i, j, k) = 0.5 * (a._dy * (vx0 - VX(i, j, k + 1)) + a._dx * (vy0 - VY(i, j, k + 1)));
-    // update_ρg!  Stokes3D.jl:538 ; BuoyancyForces.jl:38-60 (args.T sampled at I+1, quirk Q17)
+    YZ(a.eyz, i, j, k) = 0.5 * (a._dz * (vy0 - pVy[-ysz]) + a._dy * (vz0 - pVz[-zsy]));
+    XZ(a.exz, i, j, k) = 0.5 * (a._dz * (vx0 - pVx[-xsz]) + a._dx * (vz0 - pVz[-1]));
+    XY(a.exy, i, j, k) = 0.5 * (a._dy * (vx0 - pVx[-xsy]) + a._dx * (vy0 - pVy[-1]));
+    // update_ρg!  Stokes3D.jl:538 ; BuoyancyForces.jl:38-60 (args.T sampled at I+1, quirk Q17); fn_ratio with args: a ratio == 1 returns that phase
     if (!pt.rho_const) {
         const double Tc = a.T ? a.T[IX3(nx + 2, ny + 2, i + 1, j + 1, k + 1)] : 0.0, Pc = a.Pargs ? a.Pargs[c] : 0.0;
-        const double rho = jr_ratio_density(pt, a.ph_c, nc, c, Tc, Pc);
+        double rho = 0.0;
+        bool done = false;
+#pragma unroll
+        for (int p = 0; p < NP; p++)
+            if (p < pt.n && !done) {
+                if (r[p] == 1.0) { rho = jr_density(pt, p, Tc, Pc) * r[p]; done = true; }
+                else rho += (r[p] == 0.0) ? 0.0 : jr_density(pt, p, Tc, Pc) * r[p];
+            }
         if (!pt.g_scalar) { a.rgx[c] = rho * pt.g[0]; a.rgy[c] = rho * pt.g[1]; }
         a.rgz[c] = rho * pt.g[2];
     }
-    // update_viscosity_τII! BEFORE the stress kernel (quirk Q13)  Stokes3D.jl:541-548 ; Viscosity.jl:454-504
-    a.eta_o[c] = jr_clampd((1 - a.nu) * eta + a.nu * jr_phase_viscosity(pt, a.ph_c, nc, c), a.cut_lo, a.cut_hi);
+    // update_viscosity_τII! BEFORE the stress kernel (quirk Q13)  Stokes3D.jl:541-548 ; Viscosity.jl:454-504,599-619
+    double eph = 0.0;
+    bool single = false;
+#pragma unroll
+    for (int p = 0; p < NP; p++)
+        if (p < pt.n && !single && r[p] > 0.999) { eph = jr_inv(jr_inv(pt.eta[p]) + jr_inv(pt.G[p] * INFINITY)); single = true; }
+    if (!single) {
+        double e = 0.0;
+#pragma unroll
+        for (int p = 0; p < NP; p++)
+            if (p < pt.n && r[p] != 0.0) e += jr_inv(jr_inv(jr_inv(pt.eta[p]) + jr_inv(pt.G[p] * INFINITY))) * r[p];
+        eph = jr_inv(e);
+    }
+    a.eta_o[c] = jr_clampd((1 - a.nu) * eta + a.nu * eph, a.cut_lo, a.cut_hi);
     if (DIAG) { a.divV[c] = divV; a.RP[c] = RP; }
 }
 
@@ -535,6 +573,21 @@ static int pre_VC3(jr_context *ctx, const jr_fields *s, const jr_stokes_opts *o,
 }
 
 template <int NP>
+static void launch_prep_np(bool diag, bool maxloc, dim3 grd, cudaStream_t st, const V3 &k, const jr_phase_tab &pt)
+{
+    if (diag) { if (maxloc) k_vc3_prep<true, true, NP><<<grd, BLK3, 0, st>>>(k, pt); else k_vc3_prep<true, false, NP><<<grd, BLK3, 0, st>>>(k, pt); }
+    else { if (maxloc) k_vc3_prep<false, true, NP><<<grd, BLK3, 0, st>>>(k, pt); else k_vc3_prep<false, false, NP><<<grd, BLK3, 0, st>>>(k, pt); }
+}
+static void launch_prep(bool diag, bool maxloc, int nphase, dim3 grd, cudaStream_t st, const V3 &k, const jr_phase_tab &pt)
+{
+    if (nphase <= 1) launch_prep_np<1>(diag, maxloc, grd, st, k, pt);
+    else if (nphase == 2) launch_prep_np<2>(diag, maxloc, grd, st, k, pt);
+    else if (nphase == 3) launch_prep_np<3>(diag, maxloc, grd, st, k, pt);
+    else if (nphase == 4) launch_prep_np<4>(diag, maxloc, grd, st, k, pt);
+    else launch_prep_np<JR_MAX_PHASES>(diag, maxloc, grd, st, k, pt);
+}
+
+template <int NP>
 static void launch_stress_np(bool diag, dim3 grd, cudaStream_t st, const V3 &k, const jr_phase_tab &pt)
 {
     if (diag) k_vc3_stress<true, NP><<<grd, BLK3, 0, st>>>(k, pt);
@@ -565,12 +618,8 @@ static int plan3_iter(jr_context *ctx, Plan3 *p, int64_t it, bool diag, const jr
         if ((rc = jr_launch_maxloc3d(ctx, k.etatau, k.eta_i, p->n, w3))) return rc;
         const jr_harr H = jr_harr_dense(k.etatau, p->n, p->n);
         if ((rc = jr_comm_halo(ctx, &H, 1))) return rc;
-        if (diag) k_vc3_prep<true, false><<<grid3(nx, ny, nz), BLK3, 0, st>>>(k, p->pt);
-        else k_vc3_prep<false, false><<<grid3(nx, ny, nz), BLK3, 0, st>>>(k, p->pt);
-    } else {
-        if (diag) k_vc3_prep<true, true><<<grid3(nx, ny, nz), BLK3, 0, st>>>(k, p->pt);
-        else k_vc3_prep<false, true><<<grid3(nx, ny, nz), BLK3, 0, st>>>(k, p->pt);
     }
+    launch_prep(diag, !p->multi, p->pt.n, grid3(nx, ny, nz), st, k, p->pt);
     launch_stress(diag, p->pt.n, grid3(nx + 1, ny + 1, nz + 1), st, k, p->pt);
     ctx->launches += 2;
     JR_CHECK_LAUNCH();

@@ -38,7 +38,7 @@ struct ThArgs {
     int form;
     int cf_lo[3], cf_hi[3];
     double cfv_lo[3], cfv_hi[3];
-    int write_q2, write_res;
+    int write_q2, write_res, next_pt;   // next_pt: k_th_update also writes θr_dτ, dτ_ρ of the NEXT iteration (update_pt_thermal_arrays! fused)
     double *res_part;  // per-block partial sums of ResT²
 };
 
@@ -199,6 +199,15 @@ __global__ void __launch_bounds__(256) k_th_update(const __grid_constant__ ThArg
                          a.f.adiabatic[c] * Tc) + Tc) / (1.0 + dtr * rhoCp * a._dt);
         }
         a.f.T[t] = Tn;
+        if (a.next_pt) {
+            // update_pt_thermal_arrays! of the next iteration (solver.jl:233-234; DiffusionPT_coefficients.jl:105-151): it reads interior T only,
+            // which neither thermal_bcs! nor update_halo!(T) touches, so evaluating it here from Tn is the same arithmetic on the same inputs
+            const double rc = th_rhoCp(a.tab, a.f.phase_c, nc, c, Tn, a.f.P ? a.f.P[c] : 0.0);
+            const double _K = 1.0 / th_K(a.tab, a.f.phase_c, nc, c);
+            const double _Re = 1.0 / (TH_PI + sqrt(TH_PI * TH_PI + rc * (a.L * a.L) * _K * a._dt));
+            a.f.theta_r_dtau[c] = a.L / a.Vpdtau * _Re;
+            a.f.dtau_rho[c] = a.Vpdtau * a.L * _K * _Re;
+        }
         if (a.write_res) {
             double R = 0.0;
             if (!dir) {
@@ -368,13 +377,17 @@ static int th_halo(jr_context *ctx, const ThArgs &a)
 }
 
 // one PT iteration; `sample` = this iteration's residual is read (iter % nout == 0)
-static int th_iter(jr_context *ctx, ThArgs &a, const jr_thermal_opts *o, bool sample, double *d_sum)
+// have_pt: θr_dτ, dτ_ρ of this iteration were already written by the previous k_th_update; write_next: this iteration's k_th_update writes the
+// next iteration's (never on an iteration the loop can end on, so the arrays the caller sees are the reference's)
+static int th_iter(jr_context *ctx, ThArgs &a, const jr_thermal_opts *o, bool sample, double *d_sum, bool have_pt, bool write_next)
 {
     const ThDims &d = a.d;
     dim3 blk(32, 8, 1);
     dim3 g0((d.nx + 31) / 32, (d.ny + 7) / 8, d.nz), g1((d.nx + 32) / 32, (d.ny + 8) / 8, d.nd == 3 ? d.nz + 1 : 1);
-    if (a.form == 1 && a.f.phase_c) {
-        k_th_pt<<<g0, blk, 0, ctx->stream>>>(a);  // update_pt_thermal_arrays!  solver.jl:233-234
+    const bool pt_dyn = a.form == 1 && a.f.phase_c;
+    a.next_pt = (pt_dyn && write_next) ? 1 : 0;
+    if (pt_dyn && !have_pt) {
+        k_th_pt<<<g0, blk, 0, ctx->stream>>>(a);  // update_pt_thermal_arrays!  solver.jl:233-234 (later iterations: fused into k_th_update)
         ctx->launches++;
     }
     a.write_q2 = sample; a.write_res = sample;
@@ -444,7 +457,7 @@ int jr_thermal_iterate(jr_context *ctx, const jr_thermal_fields *f, const jr_the
     ctx->launches = 0;
     JR_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
     for (int64_t it = 0; it < niter; it++)
-        if ((st = th_iter(ctx, a, o, it == niter - 1, (double *)slot))) return st;
+        if ((st = th_iter(ctx, a, o, it == niter - 1, (double *)slot, it > 0, it < niter - 1))) return st;
     JR_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
     JR_CUDA(cudaMemcpyAsync(ctx->h_pinned, slot, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     JR_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -481,9 +494,12 @@ int jr_heatdiffusion_PT(jr_context *ctx, const jr_thermal_fields *f, const jr_th
     }
     int64_t iter = 0, cont = 0;
     double err = 2 * o->eps;
+    bool have_pt = false;
     while (err > o->eps && iter < o->iterMax) {
         const bool sample = (iter + 1) % o->nout == 0;
-        if ((st = th_iter(ctx, a, o, sample, (double *)slot))) return st;
+        const bool write_next = !(sample || iter + 1 >= o->iterMax);
+        if ((st = th_iter(ctx, a, o, sample, (double *)slot, have_pt, write_next))) return st;
+        have_pt = write_next;
         iter += 1;
         if (sample) {
             // err = norm(ResT)/√(prod(ni)): rank-local in the reference (quirk Q8); with a communicator the squared norm is
