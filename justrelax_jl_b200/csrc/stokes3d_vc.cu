@@ -255,7 +255,7 @@ __device__ __forceinline__ void vc3_edge(const V3 &a, const jr_phase_tab &pt, co
 // Node (i,j,k) of the (nx+1, ny+1, nz+1) lattice updates its yz, xz, xy edges and its cell centre.  All neighbour addresses are a family
 // base index (cell / yz / xz / xy array shapes) plus small precomputed offsets (clamped: 0 or ± one stride).
 template <bool DIAG, int NP>
-__global__ void __launch_bounds__(256) k_vc3_stress(const __grid_constant__ V3 a, const __grid_constant__ jr_phase_tab pt)
+__device__ __forceinline__ void vc3_stress_body(const V3 &a, const jr_phase_tab &pt)
 {
     const int nx = a.nx, ny = a.ny, nz = a.nz;
     const int i = blockIdx.x * blockDim.x + threadIdx.x + 1, j = blockIdx.y * blockDim.y + threadIdx.y + 1, k = blockIdx.z + 1;
@@ -368,6 +368,11 @@ __global__ void __launch_bounds__(256) k_vc3_stress(const __grid_constant__ V3 a
         }
     }
 }
+
+// 3 CTAs of 256 threads per SM (≤ 80 registers, a few spilled doubles): the kernel is bound by the latency of its ~280 loads per node, and
+// measured time falls with occupancy up to 24 warps/SM (5.75 ms per iteration at 128 registers → 5.15 ms at 80; no gain beyond)
+template <bool DIAG, int NP>
+__global__ void __launch_bounds__(256, 3) k_vc3_stress(const __grid_constant__ V3 a, const __grid_constant__ jr_phase_tab pt) { vc3_stress_body<DIAG, NP>(a, pt); }
 
 // ---------------------------------------------------------------------------------------------------------------------------------
 // compute_V! 3D  VelocityKernels.jl:182-242 (reads the NEW stresses, P = Pr_c, ητ)
