@@ -219,12 +219,10 @@ __device__ __forceinline__ double mix_dQdt(const jr_phase_tab &pt, const Mix<NP>
 // one edge family of update_stresses_center_vertex_ps!  StressKernels.jl:716-778 (yz), :781-849 (xz), :852-921 (xy).
 // t/to/e: the six Voigt components (xx, yy, zz, yz, xz, xy) interpolated to the edge; SLOT = the component that lives on this edge.
 template <int SLOT, bool DIAG, int NP>
-__device__ __forceinline__ void vc3_edge(const V3 &a, const jr_phase_tab &pt, const double *__restrict__ ph, size_t stride, size_t v, double etav, double Pv,
-                                         const double (&t)[6], const double (&to)[6], const double (&e)[6], double *__restrict__ lamv,
-                                         double *__restrict__ tau_out, double *__restrict__ epl)
+__device__ __forceinline__ void vc3_edge_mix(const V3 &a, const jr_phase_tab &pt, const Mix<NP> &m, size_t v, double etav, double Pv, const double (&t)[6],
+                                             const double (&to)[6], const double (&e)[6], double *__restrict__ lamv, double *__restrict__ tau_out,
+                                             double *__restrict__ epl)
 {
-    Mix<NP> m;
-    mix_load<NP>(pt, ph, stride, v, m);
     const double _Gdt = jr_inv(m.G * a.dt);
     const double dtr = jr_inv(a.th + etav * _Gdt + 1.0);
     double trial[6], dS = 0.0;
@@ -250,6 +248,64 @@ __device__ __forceinline__ void vc3_edge(const V3 &a, const jr_phase_tab &pt, co
     }
     tau_out[v] = tn;
     if (DIAG) epl[v] = ep;
+}
+template <int SLOT, bool DIAG, int NP>
+__device__ __forceinline__ void vc3_edge(const V3 &a, const jr_phase_tab &pt, const double *__restrict__ ph, size_t stride, size_t v, double etav, double Pv,
+                                         const double (&t)[6], const double (&to)[6], const double (&e)[6], double *__restrict__ lamv,
+                                         double *__restrict__ tau_out, double *__restrict__ epl)
+{
+    Mix<NP> m;
+    mix_load<NP>(pt, ph, stride, v, m);
+    vc3_edge_mix<SLOT, DIAG, NP>(a, pt, m, v, etav, Pv, t, to, e, lamv, tau_out, epl);
+}
+
+// the cell-centre part of update_stresses_center_vertex_ps!  StressKernels.jl:923-986 (plain products and sums: no @muladd there);
+// eij / tij / tijo: strain rate, stress, old stress at the centre in Voigt order (shear: 4-edge averages / centre copies)
+template <bool DIAG, int NP>
+__device__ __forceinline__ void vc3_centre(const V3 &a, const jr_phase_tab &pt, const Mix<NP> &m, size_t c, double et, double Pr, const double (&eij)[6],
+                                           double (&tij)[6], const double (&tijo)[6])
+{
+    const double _Gdt = jr_inv(m.G * a.dt), K = m.Kb;
+    const double dtr = jr_inv(a.th + et * _Gdt + 1.0);
+    double d[6], trial[6];
+#pragma unroll
+    for (int q = 0; q < 6; q++) {
+        d[q] = (-(tij[q] - tijo[q]) * et * _Gdt - tij[q] + 2.0 * et * eij[q]) * dtr;
+        trial[q] = tij[q] + d[q];
+    }
+    double tII = jr_second_invariant<6>(trial);
+    double dQdP, dFdP;
+    mix_dP<NP>(pt, m, dQdP, dFdP);
+    double lam = a.lam[c], evol = 0.0, epl[3] = {0.0, 0.0, 0.0};
+    double Fc = 0.0;
+    if (m.is_pl && tII != 0.0) Fc = mix_yield_F<NP>(pt, m, Pr, tII);
+    if (m.is_pl && tII != 0.0 && Fc > 0) {
+        const double volume = isinf(K) ? 0.0 : K * a.dt * dFdP * dQdP;
+        lam = (1.0 - a.rel) * lam + a.rel * (fmax(Fc, 0.0) / (et * dtr + m.eta_reg + volume));
+        a.lam[c] = lam;
+        const double tIIt = tII;
+#pragma unroll
+        for (int q = 0; q < 6; q++) {
+            const double e = lam * (q < 3 ? mix_dQdt<NP, false>(pt, m, trial[q], tIIt) : mix_dQdt<NP, true>(pt, m, trial[q], tIIt));
+            if (q < 3) epl[q] = e;
+            d[q] = d[q] - 2.0 * et * e * dtr;
+            tij[q] = d[q] + tij[q];
+        }
+        evol = -lam * dQdP;
+        tII = jr_second_invariant<6>(tij);
+    } else {
+#pragma unroll
+        for (int q = 0; q < 6; q++) tij[q] = d[q] + tij[q];
+    }
+    a.txx_o[c] = tij[0]; a.tyy_o[c] = tij[1]; a.tzz_o[c] = tij[2];
+    a.tyzc[c] = tij[3]; a.txzc[c] = tij[4]; a.txyc[c] = tij[5];
+    a.P[c] = Pr - (isinf(K) ? 0.0 : K * a.dt * lam * dQdP);
+    if (DIAG) {
+        a.pxx[c] = epl[0]; a.pyy[c] = epl[1]; a.pzz[c] = epl[2];
+        a.e_vol_pl[c] = evol;
+        a.tII[c] = tII;
+        a.eta_vep[c] = tII * 0.5 * jr_inv(jr_second_invariant<6>(eij));
+    }
 }
 
 // Node (i,j,k) of the (nx+1, ny+1, nz+1) lattice updates its yz, xz, xy edges and its cell centre.  All neighbour addresses are a family
@@ -313,64 +369,135 @@ __device__ __forceinline__ void vc3_stress_body(const V3 &a, const jr_phase_tab 
         vc3_edge<5, DIAG, NP>(a, pt, a.ph_xy, nxy, v, HARM_XY(eta), AV_XY(a.theta), t, to, e, a.lamxy, a.txy_o, a.pxy);
     }
     if (i <= nx && j <= ny && k <= nz) {  // ---- centre  StressKernels.jl:923-986 (plain products and sums: no @muladd there)
-        const size_t c = cb;
-        Mix<NP> m;
-        mix_load<NP>(pt, a.ph_c, nc, c, m);
-        const double _Gdt = jr_inv(m.G * a.dt), K = m.Kb, et = __ldg(eta + c);
-        const double dtr = jr_inv(a.th + et * _Gdt + 1.0);
         // cache_tensors  StressUpdate.jl:248-301 (_av_yz/_av_xz/_av_xy: mysum order k → j → i starting from 0.0, quirk Q15)
+        const size_t c = cb;
         const double eij[6] = {__ldg(a.exx + c), __ldg(a.eyy + c), __ldg(a.ezz + c),
                                0.25 * ((((0.0 + LY(a.eyz, 0)) + LY(a.eyz, ysy)) + LY(a.eyz, ysz)) + LY(a.eyz, ysy + ysz)),
                                0.25 * ((((0.0 + LZ(a.exz, 0)) + LZ(a.exz, 1)) + LZ(a.exz, zsz)) + LZ(a.exz, 1 + zsz)),
                                0.25 * ((((0.0 + LX(a.exy, 0)) + LX(a.exy, 1)) + LX(a.exy, xsy)) + LX(a.exy, 1 + xsy))};
         double tij[6] = {__ldg(a.txx_i + c), __ldg(a.tyy_i + c), __ldg(a.tzz_i + c), a.tyzc[c], a.txzc[c], a.txyc[c]};
         const double tijo[6] = {__ldg(a.oxx + c), __ldg(a.oyy + c), __ldg(a.ozz + c), __ldg(a.oyzc + c), __ldg(a.oxzc + c), __ldg(a.oxyc + c)};
-        double d[6], trial[6];
-#pragma unroll
-        for (int q = 0; q < 6; q++) {
-            d[q] = (-(tij[q] - tijo[q]) * et * _Gdt - tij[q] + 2.0 * et * eij[q]) * dtr;
-            trial[q] = tij[q] + d[q];
-        }
-        double tII = jr_second_invariant<6>(trial);
-        double dQdP, dFdP;
-        const double Pr = a.theta[c];
-        mix_dP<NP>(pt, m, dQdP, dFdP);
-        double lam = a.lam[c], evol = 0.0, epl[3] = {0.0, 0.0, 0.0};
-        bool yielding = false;
-        if (m.is_pl && tII != 0.0) yielding = mix_yield_F<NP>(pt, m, Pr, tII) > 0;
-        if (yielding) {
-            const double Fc = mix_yield_F<NP>(pt, m, Pr, tII);
-            const double volume = isinf(K) ? 0.0 : K * a.dt * dFdP * dQdP;
-            lam = (1.0 - a.rel) * lam + a.rel * (fmax(Fc, 0.0) / (et * dtr + m.eta_reg + volume));
-            a.lam[c] = lam;
-            const double tIIt = tII;
-#pragma unroll
-            for (int q = 0; q < 6; q++) {
-                const double e = lam * (q < 3 ? mix_dQdt<NP, false>(pt, m, trial[q], tIIt) : mix_dQdt<NP, true>(pt, m, trial[q], tIIt));
-                if (q < 3) epl[q] = e;
-                d[q] = d[q] - 2.0 * et * e * dtr;
-                tij[q] = d[q] + tij[q];
-            }
-            evol = -lam * dQdP;
-            tII = jr_second_invariant<6>(tij);
-        } else {
-#pragma unroll
-            for (int q = 0; q < 6; q++) tij[q] = d[q] + tij[q];
-        }
-        a.txx_o[c] = tij[0]; a.tyy_o[c] = tij[1]; a.tzz_o[c] = tij[2];
-        a.tyzc[c] = tij[3]; a.txzc[c] = tij[4]; a.txyc[c] = tij[5];
-        a.P[c] = Pr - (isinf(K) ? 0.0 : K * a.dt * lam * dQdP);
-        if (DIAG) {
-            a.pxx[c] = epl[0]; a.pyy[c] = epl[1]; a.pzz[c] = epl[2];
-            a.e_vol_pl[c] = evol;
-            a.tII[c] = tII;
-            a.eta_vep[c] = tII * 0.5 * jr_inv(jr_second_invariant<6>(eij));
-        }
+        Mix<NP> m;
+        mix_load<NP>(pt, a.ph_c, nc, c, m);
+        vc3_centre<DIAG, NP>(a, pt, m, c, __ldg(eta + c), a.theta[c], eij, tij, tijo);
     }
 }
 
-// 3 CTAs of 256 threads per SM (≤ 80 registers, a few spilled doubles): the kernel is bound by the latency of its ~280 loads per node, and
-// measured time falls with occupancy up to 24 warps/SM (5.75 ms per iteration at 128 registers → 5.15 ms at 80; no gain beyond)
+// ---- shared-memory staged variant ----------------------------------------------------------------------------------------------------
+// A CTA of 32 × TYS nodes of plane k first copies the tiles of the 20 neighbour-read arrays it needs (2 planes × (TYS+1) rows × 33
+// columns each; four tile origins: cell, yz, xz, xy families) global → shared with cp.async — ≈ 46 independent 8-byte copies in flight per
+// thread and no registers held — then every node computes from shared memory with clamp-free indices.  CTAs that touch the high-side
+// boundary planes (where the clamped and the raw indices of the reference differ between families) take the global-memory body above.
+// The z-neighbour CTA re-reads one of the two planes: L2 serves it (CTAs are scheduled plane by plane).
+#define TYS 8
+#define SROW 33
+#define SPLANE (SROW * (TYS + 1))
+#define STILE (2 * SPLANE)
+enum { SL_eta, SL_theta, SL_txx, SL_tyy, SL_tzz, SL_oxx, SL_oyy, SL_ozz, SL_exx, SL_eyy, SL_ezz,   // cell family
+       SL_tyz, SL_oyz, SL_eyz,                                                                       // yz family
+       SL_txz, SL_oxz, SL_exz,                                                                       // xz family
+       SL_txy, SL_oxy, SL_exy, SL_COUNT };
+
+__device__ __forceinline__ void cp_async8(double *dst_smem, const double *src)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src) : "memory");
+}
+
+template <bool DIAG, int NP>
+__global__ void __launch_bounds__(32 * TYS, 2) k_vc3_stress_sm(const __grid_constant__ V3 a, const __grid_constant__ jr_phase_tab pt)
+{
+    extern __shared__ double sm[];
+    const int nx = a.nx, ny = a.ny, nz = a.nz;
+    const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 32 + tx;
+    const int ib = blockIdx.x * 32 + 1, jb = blockIdx.y * TYS + 1, k = blockIdx.z + 1;   // first node of the CTA (1-based)
+    // fast CTAs: every node has i+1 ≤ nx, j+1 ≤ ny, k+1 ≤ nz (no high-side clamp is active)
+    if (!(ib + 31 <= nx - 1 && jb + TYS - 1 <= ny - 1 && k <= nz - 1)) {
+        vc3_stress_body<DIAG, NP>(a, pt);
+        return;
+    }
+    const int i = ib + tx, j = jb + ty;
+    {   // ---- stage the tiles
+        const double *src[SL_COUNT] = {a.eta_o, a.theta, a.txx_i, a.tyy_i, a.tzz_i, a.oxx, a.oyy, a.ozz, a.exx, a.eyy, a.ezz,
+                                       a.tyz_i, a.oyz, a.eyz, a.txz_i, a.oxz, a.exz, a.txy_i, a.oxy, a.exy};
+#pragma unroll
+        for (int it = 0; it < (STILE + 32 * TYS - 1) / (32 * TYS); it++) {
+            const int e = tid + it * 32 * TYS;
+            if (e < STILE) {
+                const int p = e / SPLANE, r = (e - p * SPLANE) / SROW, c = e - p * SPLANE - r * SROW;
+                // tile origins (low-side clamp to index 1): cell (i−1, j−1, k−1); yz (i−1, j, k); xz (i, j−1, k); xy (i, j, k−1)
+                const int im = max(ib - 1 + c, 1), jm = max(jb - 1 + r, 1), km = max(k - 1 + p, 1), ip = ib + c, jp = jb + r, kp = k + p;
+                const size_t oc = IX3(nx, ny, im, jm, km), oy = IX3(nx, ny + 1, im, jp, kp), oz = IX3(nx + 1, ny, ip, jm, kp),
+                             ox = IX3(nx + 1, ny + 1, ip, jp, km);
+#pragma unroll
+                for (int s = 0; s < SL_COUNT; s++) {
+                    const size_t o = s < SL_tyz ? oc : (s < SL_txz ? oy : (s < SL_txy ? oz : ox));
+                    cp_async8(sm + s * STILE + e, src[s] + o);
+                }
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    // global reads that do not go through the tiles are issued while the copies are in flight
+    const size_t nc = (size_t)nx * ny * nz, nyz = (size_t)nx * (ny + 1) * (nz + 1), nxz = (size_t)(nx + 1) * ny * (nz + 1),
+                 nxy = (size_t)(nx + 1) * (ny + 1) * nz;
+    const size_t c = IX3(nx, ny, i, j, k), vyz = IX3(nx, ny + 1, i, j, k), vxz = IX3(nx + 1, ny, i, j, k), vxy = IX3(nx + 1, ny + 1, i, j, k);
+    Mix<NP> myz, mxz, mxy, mc;
+    mix_load<NP>(pt, a.ph_yz, nyz, vyz, myz);
+    mix_load<NP>(pt, a.ph_xz, nxz, vxz, mxz);
+    mix_load<NP>(pt, a.ph_xy, nxy, vxy, mxy);
+    mix_load<NP>(pt, a.ph_c, nc, c, mc);
+    double tij[6] = {0.0, 0.0, 0.0, a.tyzc[c], a.txzc[c], a.txyc[c]};
+    double tijo[6] = {0.0, 0.0, 0.0, __ldg(a.oyzc + c), __ldg(a.oxzc + c), __ldg(a.oxyc + c)};
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    // S(slot, I, J, K): tile entry at column tx+I, row ty+J, plane K — per family: cell (i0|ic, j0|jc, k0|kc); yz (i0|ic, j|j+1, k|k+1);
+    // xz (i|i+1, j0|jc, k|k+1); xy (i|i+1, j|j+1, k0|kc)
+#define S(s, I, J, K) sm[(s) * STILE + (K) * SPLANE + (ty + (J)) * SROW + tx + (I)]
+#define SAV_YZ(s) (0.25 * (S(s, 1, 0, 0) + S(s, 1, 1, 0) + S(s, 1, 0, 1) + S(s, 1, 1, 1)))
+#define SAV_XZ(s) (0.25 * (S(s, 0, 1, 0) + S(s, 1, 1, 0) + S(s, 0, 1, 1) + S(s, 1, 1, 1)))
+#define SAV_XY(s) (0.25 * (S(s, 0, 0, 1) + S(s, 1, 0, 1) + S(s, 0, 1, 1) + S(s, 1, 1, 1)))
+#define SHARM_YZ(s) (4 / (1 / S(s, 1, 0, 0) + 1 / S(s, 1, 1, 0) + 1 / S(s, 1, 0, 1) + 1 / S(s, 1, 1, 1)))
+#define SHARM_XZ(s) (4 / (1 / S(s, 0, 1, 0) + 1 / S(s, 1, 1, 0) + 1 / S(s, 0, 1, 1) + 1 / S(s, 1, 1, 1)))
+#define SHARM_XY(s) (4 / (1 / S(s, 0, 0, 1) + 1 / S(s, 1, 0, 1) + 1 / S(s, 0, 1, 1) + 1 / S(s, 1, 1, 1)))
+#define SAV_YZ_Y(s) (0.25 * (S(s, 0, 0, 0) + S(s, 1, 0, 0) + S(s, 0, 1, 0) + S(s, 1, 1, 0)))   /* xz family: (ic,j0,kc),(i1,j0,kc),(ic,jc,kc),(i1,jc,kc) */
+#define SAV_YZ_Z(s) (0.25 * (S(s, 0, 0, 0) + S(s, 1, 0, 0) + S(s, 0, 0, 1) + S(s, 1, 0, 1)))   /* xy family: (ic,jc,k0),(i1,jc,k0),(ic,jc,kc),(i1,jc,kc) */
+#define SAV_XZ_X(s) (0.25 * (S(s, 0, 0, 0) + S(s, 1, 0, 0) + S(s, 1, 1, 0) + S(s, 0, 1, 0)))   /* yz family: (i0,jc,kc),(ic,jc,kc),(ic,j1,kc),(i0,j1,kc) */
+#define SAV_XZ_Z(s) (0.25 * (S(s, 0, 0, 0) + S(s, 0, 1, 0) + S(s, 0, 0, 1) + S(s, 0, 1, 1)))   /* xy family: (ic,jc,k0),(ic,j1,k0),(ic,jc,kc),(ic,j1,kc) */
+#define SAV_XY_X(s) (0.25 * (S(s, 0, 0, 0) + S(s, 1, 0, 0) + S(s, 0, 0, 1) + S(s, 1, 0, 1)))   /* yz family: (i0,jc,kc),(ic,jc,kc),(i0,jc,k1),(ic,jc,k1) */
+#define SAV_XY_Y(s) (0.25 * (S(s, 0, 0, 0) + S(s, 0, 1, 0) + S(s, 0, 0, 1) + S(s, 0, 1, 1)))   /* xz family: (ic,j0,kc),(ic,jc,kc),(ic,j0,k1),(ic,jc,k1) */
+    {   // ---- yz edge (own entry: yz family (ic, j, k) = S(·, 1, 0, 0))
+        const double t[6] = {SAV_YZ(SL_txx), SAV_YZ(SL_tyy), SAV_YZ(SL_tzz), S(SL_tyz, 1, 0, 0), SAV_YZ_Y(SL_txz), SAV_YZ_Z(SL_txy)};
+        const double to[6] = {SAV_YZ(SL_oxx), SAV_YZ(SL_oyy), SAV_YZ(SL_ozz), S(SL_oyz, 1, 0, 0), SAV_YZ_Y(SL_oxz), SAV_YZ_Z(SL_oxy)};
+        const double e[6] = {SAV_YZ(SL_exx), SAV_YZ(SL_eyy), SAV_YZ(SL_ezz), S(SL_eyz, 1, 0, 0), SAV_YZ_Y(SL_exz), SAV_YZ_Z(SL_exy)};
+        vc3_edge_mix<3, DIAG, NP>(a, pt, myz, vyz, SHARM_YZ(SL_eta), SAV_YZ(SL_theta), t, to, e, a.lamyz, a.tyz_o, a.pyz);
+    }
+    {   // ---- xz edge (own entry: xz family (i, jc, k) = S(·, 0, 1, 0))
+        const double t[6] = {SAV_XZ(SL_txx), SAV_XZ(SL_tyy), SAV_XZ(SL_tzz), SAV_XZ_X(SL_tyz), S(SL_txz, 0, 1, 0), SAV_XZ_Z(SL_txy)};
+        const double to[6] = {SAV_XZ(SL_oxx), SAV_XZ(SL_oyy), SAV_XZ(SL_ozz), SAV_XZ_X(SL_oyz), S(SL_oxz, 0, 1, 0), SAV_XZ_Z(SL_oxy)};
+        const double e[6] = {SAV_XZ(SL_exx), SAV_XZ(SL_eyy), SAV_XZ(SL_ezz), SAV_XZ_X(SL_eyz), S(SL_exz, 0, 1, 0), SAV_XZ_Z(SL_exy)};
+        vc3_edge_mix<4, DIAG, NP>(a, pt, mxz, vxz, SHARM_XZ(SL_eta), SAV_XZ(SL_theta), t, to, e, a.lamxz, a.txz_o, a.pxz);
+    }
+    {   // ---- xy edge (own entry: xy family (i, j, kc) = S(·, 0, 0, 1))
+        const double t[6] = {SAV_XY(SL_txx), SAV_XY(SL_tyy), SAV_XY(SL_tzz), SAV_XY_X(SL_tyz), SAV_XY_Y(SL_txz), S(SL_txy, 0, 0, 1)};
+        const double to[6] = {SAV_XY(SL_oxx), SAV_XY(SL_oyy), SAV_XY(SL_ozz), SAV_XY_X(SL_oyz), SAV_XY_Y(SL_oxz), S(SL_oxy, 0, 0, 1)};
+        const double e[6] = {SAV_XY(SL_exx), SAV_XY(SL_eyy), SAV_XY(SL_ezz), SAV_XY_X(SL_eyz), SAV_XY_Y(SL_exz), S(SL_exy, 0, 0, 1)};
+        vc3_edge_mix<5, DIAG, NP>(a, pt, mxy, vxy, SHARM_XY(SL_eta), SAV_XY(SL_theta), t, to, e, a.lamxy, a.txy_o, a.pxy);
+    }
+    {   // ---- centre: cell (i, j, k) = S(·, 1, 1, 1); edge gathers in mysum order (quirk Q15)
+        const double eij[6] = {S(SL_exx, 1, 1, 1), S(SL_eyy, 1, 1, 1), S(SL_ezz, 1, 1, 1),
+                               0.25 * ((((0.0 + S(SL_eyz, 1, 0, 0)) + S(SL_eyz, 1, 1, 0)) + S(SL_eyz, 1, 0, 1)) + S(SL_eyz, 1, 1, 1)),
+                               0.25 * ((((0.0 + S(SL_exz, 0, 1, 0)) + S(SL_exz, 1, 1, 0)) + S(SL_exz, 0, 1, 1)) + S(SL_exz, 1, 1, 1)),
+                               0.25 * ((((0.0 + S(SL_exy, 0, 0, 1)) + S(SL_exy, 1, 0, 1)) + S(SL_exy, 0, 1, 1)) + S(SL_exy, 1, 1, 1))};
+        tij[0] = S(SL_txx, 1, 1, 1); tij[1] = S(SL_tyy, 1, 1, 1); tij[2] = S(SL_tzz, 1, 1, 1);
+        tijo[0] = S(SL_oxx, 1, 1, 1); tijo[1] = S(SL_oyy, 1, 1, 1); tijo[2] = S(SL_ozz, 1, 1, 1);
+        vc3_centre<DIAG, NP>(a, pt, mc, c, S(SL_eta, 1, 1, 1), S(SL_theta, 1, 1, 1), eij, tij, tijo);
+    }
+#undef S
+}
+
+// global-memory variant: 3 CTAs of 256 threads per SM (≤ 80 registers, a few spilled doubles) — bound by the latency of its ≈ 280 loads per
+// node; measured time falls with occupancy up to 24 warps/SM (5.75 ms per iteration at 128 registers → 5.15 ms at 80; no gain beyond)
 template <bool DIAG, int NP>
 __global__ void __launch_bounds__(256, 3) k_vc3_stress(const __grid_constant__ V3 a, const __grid_constant__ jr_phase_tab pt) { vc3_stress_body<DIAG, NP>(a, pt); }
 
@@ -595,6 +722,20 @@ static void launch_prep(bool diag, bool maxloc, int nphase, dim3 grd, cudaStream
 template <int NP>
 static void launch_stress_np(bool diag, dim3 grd, cudaStream_t st, const V3 &k, const jr_phase_tab &pt)
 {
+    static const bool use_sm = !(getenv("JRB200_VC_STRESS_GLOBAL") && atoi(getenv("JRB200_VC_STRESS_GLOBAL")));
+    if (use_sm) {
+        const size_t smem = (size_t)SL_COUNT * STILE * sizeof(double);
+        static bool attr = false;   // per instantiation
+        if (!attr) {
+            cudaFuncSetAttribute(k_vc3_stress_sm<true, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(k_vc3_stress_sm<false, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            attr = true;
+        }
+        const dim3 blk(32, TYS, 1), g2(grd.x, (grd.y * 8 + TYS - 1) / TYS, grd.z);
+        if (diag) k_vc3_stress_sm<true, NP><<<g2, blk, smem, st>>>(k, pt);
+        else k_vc3_stress_sm<false, NP><<<g2, blk, smem, st>>>(k, pt);
+        return;
+    }
     if (diag) k_vc3_stress<true, NP><<<grd, BLK3, 0, st>>>(k, pt);
     else k_vc3_stress<false, NP><<<grd, BLK3, 0, st>>>(k, pt);
 }
