@@ -383,6 +383,45 @@ __device__ __forceinline__ void vc3_stress_body(const V3 &a, const jr_phase_tab 
     }
 }
 
+// State of one edge family while the six Voigt components stream through: visco-elastic factors, the running sum of the second invariant of
+// the trial stress (reference order sqrt(0.5 (T0² + T1² + T2²) + T3² + T4² + T5²)) and the own component.  Lets the three edges of a node
+// advance as independent instruction streams (ILP) before the rarely taken plastic branches.
+struct EdgeAcc {
+    double etav, Pv, _Gdt, dtr, acc, t_own, d_own, trial_own;
+};
+template <int Q, bool OWN>
+__device__ __forceinline__ void edge_comp(EdgeAcc &E, double t, double to, double e)
+{
+    const double d = jr_stress_increment(t, to, E.etav, e, E._Gdt, E.dtr);
+    const double T = t + d;
+    if (Q == 0) E.acc = T * T;
+    else if (Q < 3) E.acc = E.acc + T * T;
+    else if (Q == 3) E.acc = 0.5 * E.acc + T * T;
+    else E.acc = E.acc + T * T;
+    if (OWN) { E.t_own = t; E.d_own = d; E.trial_own = T; }
+}
+template <bool DIAG, int NP>
+__device__ __forceinline__ void edge_finish(const V3 &a, const jr_phase_tab &pt, const Mix<NP> &m, const EdgeAcc &E, size_t v, double *__restrict__ lamv,
+                                            double *__restrict__ tau_out, double *__restrict__ epl)
+{
+    const double tII = sqrt(E.acc);
+    double tn = E.t_own + E.d_own, ep = 0.0;
+    if (m.is_pl && tII != 0.0) {
+        const double Fv = mix_yield_F<NP>(pt, m, E.Pv, tII);
+        if (Fv > 0) {
+            double dQdP, dFdP;
+            mix_dP<NP>(pt, m, dQdP, dFdP);
+            const double volume = isinf(m.Kb) ? 0.0 : m.Kb * a.dt * dFdP * dQdP;
+            const double l = (1.0 - a.rel) * lamv[v] + a.rel * (fmax(Fv, 0.0) / (E.etav * E.dtr + m.eta_reg + volume));
+            lamv[v] = l;
+            ep = l * mix_dQdt<NP, true>(pt, m, E.trial_own, tII);
+            tn = E.t_own + fma(-2.0, E.etav * ep * E.dtr, E.d_own);
+        }
+    }
+    tau_out[v] = tn;
+    if (DIAG) epl[v] = ep;
+}
+
 // ---- shared-memory staged variant ----------------------------------------------------------------------------------------------------
 // A CTA of 32 × TYS nodes of plane k first copies the tiles of the 20 neighbour-read arrays it needs (2 planes × (TYS+1) rows × 33
 // columns each; four tile origins: cell, yz, xz, xy families) global → shared with cp.async — ≈ 46 independent 8-byte copies in flight per
@@ -405,6 +444,32 @@ __device__ __forceinline__ void cp_async8(double *dst_smem, const double *src)
 }
 
 template <bool DIAG, int NP>
+__device__ __noinline__ void vc3_stress_body_call(const V3 &a, const jr_phase_tab &pt) { vc3_stress_body<DIAG, NP>(a, pt); }
+
+template <int NP>
+__device__ __forceinline__ void ratios_load(const jr_phase_tab &pt, const double *__restrict__ ph, size_t stride, size_t q, double (&r)[NP])
+{
+#pragma unroll
+    for (int p = 0; p < NP; p++) r[p] = p < pt.n ? __ldg(ph + (size_t)p * stride + q) : 0.0;
+}
+template <int NP>
+__device__ __forceinline__ void mix_from(const jr_phase_tab &pt, const double (&r)[NP], Mix<NP> &m)
+{
+    m.G = 0.0; m.Kb = 0.0; m.eta_reg = 0.0; m.is_pl = false;
+#pragma unroll
+    for (int p = 0; p < NP; p++) {
+        m.r[p] = r[p];
+        if (p < pt.n) {
+            m.G += (r[p] == 0.0) ? 0.0 : pt.G[p] * r[p];
+            m.Kb += (r[p] == 0.0) ? 0.0 : pt.Kb[p] * r[p];
+            const bool pl = (r[p] != 0.0) && pt.has_pl[p];
+            if (pl) m.is_pl = true;
+            m.eta_reg += (pl ? pt.eta_vp[p] : 0.0) * r[p];
+        }
+    }
+}
+
+template <bool DIAG, int NP>
 __global__ void __launch_bounds__(32 * TYS, 2) k_vc3_stress_sm(const __grid_constant__ V3 a, const __grid_constant__ jr_phase_tab pt)
 {
     extern __shared__ double sm[];
@@ -413,7 +478,7 @@ __global__ void __launch_bounds__(32 * TYS, 2) k_vc3_stress_sm(const __grid_cons
     const int ib = blockIdx.x * 32 + 1, jb = blockIdx.y * TYS + 1, k = blockIdx.z + 1;   // first node of the CTA (1-based)
     // fast CTAs: every node has i+1 ≤ nx, j+1 ≤ ny, k+1 ≤ nz (no high-side clamp is active)
     if (!(ib + 31 <= nx - 1 && jb + TYS - 1 <= ny - 1 && k <= nz - 1)) {
-        vc3_stress_body<DIAG, NP>(a, pt);
+        vc3_stress_body_call<DIAG, NP>(a, pt);
         return;
     }
     const int i = ib + tx, j = jb + ty;
@@ -442,13 +507,10 @@ __global__ void __launch_bounds__(32 * TYS, 2) k_vc3_stress_sm(const __grid_cons
     const size_t nc = (size_t)nx * ny * nz, nyz = (size_t)nx * (ny + 1) * (nz + 1), nxz = (size_t)(nx + 1) * ny * (nz + 1),
                  nxy = (size_t)(nx + 1) * (ny + 1) * nz;
     const size_t c = IX3(nx, ny, i, j, k), vyz = IX3(nx, ny + 1, i, j, k), vxz = IX3(nx + 1, ny, i, j, k), vxy = IX3(nx + 1, ny + 1, i, j, k);
-    Mix<NP> myz, mxz, mxy, mc;
-    mix_load<NP>(pt, a.ph_yz, nyz, vyz, myz);
-    mix_load<NP>(pt, a.ph_xz, nxz, vxz, mxz);
-    mix_load<NP>(pt, a.ph_xy, nxy, vxy, mxy);
-    mix_load<NP>(pt, a.ph_c, nc, c, mc);
-    double tij[6] = {0.0, 0.0, 0.0, a.tyzc[c], a.txzc[c], a.txyc[c]};
-    double tijo[6] = {0.0, 0.0, 0.0, __ldg(a.oyzc + c), __ldg(a.oxzc + c), __ldg(a.oxyc + c)};
+    double ryz[NP], rxz[NP], rxy[NP];
+    ratios_load<NP>(pt, a.ph_yz, nyz, vyz, ryz);
+    ratios_load<NP>(pt, a.ph_xz, nxz, vxz, rxz);
+    ratios_load<NP>(pt, a.ph_xy, nxy, vxy, rxy);
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
     // S(slot, I, J, K): tile entry at column tx+I, row ty+J, plane K — per family: cell (i0|ic, j0|jc, k0|kc); yz (i0|ic, j|j+1, k|k+1);
@@ -466,31 +528,50 @@ __global__ void __launch_bounds__(32 * TYS, 2) k_vc3_stress_sm(const __grid_cons
 #define SAV_XZ_Z(s) (0.25 * (S(s, 0, 0, 0) + S(s, 0, 1, 0) + S(s, 0, 0, 1) + S(s, 0, 1, 1)))   /* xy family: (ic,jc,k0),(ic,j1,k0),(ic,jc,kc),(ic,j1,kc) */
 #define SAV_XY_X(s) (0.25 * (S(s, 0, 0, 0) + S(s, 1, 0, 0) + S(s, 0, 0, 1) + S(s, 1, 0, 1)))   /* yz family: (i0,jc,kc),(ic,jc,kc),(i0,jc,k1),(ic,jc,k1) */
 #define SAV_XY_Y(s) (0.25 * (S(s, 0, 0, 0) + S(s, 0, 1, 0) + S(s, 0, 0, 1) + S(s, 0, 1, 1)))   /* xz family: (ic,j0,kc),(ic,jc,kc),(ic,j0,k1),(ic,jc,k1) */
-    {   // ---- yz edge (own entry: yz family (ic, j, k) = S(·, 1, 0, 0))
-        const double t[6] = {SAV_YZ(SL_txx), SAV_YZ(SL_tyy), SAV_YZ(SL_tzz), S(SL_tyz, 1, 0, 0), SAV_YZ_Y(SL_txz), SAV_YZ_Z(SL_txy)};
-        const double to[6] = {SAV_YZ(SL_oxx), SAV_YZ(SL_oyy), SAV_YZ(SL_ozz), S(SL_oyz, 1, 0, 0), SAV_YZ_Y(SL_oxz), SAV_YZ_Z(SL_oxy)};
-        const double e[6] = {SAV_YZ(SL_exx), SAV_YZ(SL_eyy), SAV_YZ(SL_ezz), S(SL_eyz, 1, 0, 0), SAV_YZ_Y(SL_exz), SAV_YZ_Z(SL_exy)};
-        vc3_edge_mix<3, DIAG, NP>(a, pt, myz, vyz, SHARM_YZ(SL_eta), SAV_YZ(SL_theta), t, to, e, a.lamyz, a.tyz_o, a.pyz);
-    }
-    {   // ---- xz edge (own entry: xz family (i, jc, k) = S(·, 0, 1, 0))
-        const double t[6] = {SAV_XZ(SL_txx), SAV_XZ(SL_tyy), SAV_XZ(SL_tzz), SAV_XZ_X(SL_tyz), S(SL_txz, 0, 1, 0), SAV_XZ_Z(SL_txy)};
-        const double to[6] = {SAV_XZ(SL_oxx), SAV_XZ(SL_oyy), SAV_XZ(SL_ozz), SAV_XZ_X(SL_oyz), S(SL_oxz, 0, 1, 0), SAV_XZ_Z(SL_oxy)};
-        const double e[6] = {SAV_XZ(SL_exx), SAV_XZ(SL_eyy), SAV_XZ(SL_ezz), SAV_XZ_X(SL_eyz), S(SL_exz, 0, 1, 0), SAV_XZ_Z(SL_exy)};
-        vc3_edge_mix<4, DIAG, NP>(a, pt, mxz, vxz, SHARM_XZ(SL_eta), SAV_XZ(SL_theta), t, to, e, a.lamxz, a.txz_o, a.pxz);
-    }
-    {   // ---- xy edge (own entry: xy family (i, j, kc) = S(·, 0, 0, 1))
-        const double t[6] = {SAV_XY(SL_txx), SAV_XY(SL_tyy), SAV_XY(SL_tzz), SAV_XY_X(SL_tyz), SAV_XY_Y(SL_txz), S(SL_txy, 0, 0, 1)};
-        const double to[6] = {SAV_XY(SL_oxx), SAV_XY(SL_oyy), SAV_XY(SL_ozz), SAV_XY_X(SL_oyz), SAV_XY_Y(SL_oxz), S(SL_oxy, 0, 0, 1)};
-        const double e[6] = {SAV_XY(SL_exx), SAV_XY(SL_eyy), SAV_XY(SL_ezz), SAV_XY_X(SL_eyz), SAV_XY_Y(SL_exz), S(SL_exy, 0, 0, 1)};
-        vc3_edge_mix<5, DIAG, NP>(a, pt, mxy, vxy, SHARM_XY(SL_eta), SAV_XY(SL_theta), t, to, e, a.lamxy, a.txy_o, a.pxy);
-    }
+    // ---- the three edges advance together (straight-line code: three independent dependency chains), then the plastic branches
+    Mix<NP> myz, mxz, mxy;
+    mix_from<NP>(pt, ryz, myz);
+    mix_from<NP>(pt, rxz, mxz);
+    mix_from<NP>(pt, rxy, mxy);
+    EdgeAcc Eyz, Exz, Exy;
+    Eyz.etav = SHARM_YZ(SL_eta); Exz.etav = SHARM_XZ(SL_eta); Exy.etav = SHARM_XY(SL_eta);
+    Eyz.Pv = SAV_YZ(SL_theta); Exz.Pv = SAV_XZ(SL_theta); Exy.Pv = SAV_XY(SL_theta);
+    Eyz._Gdt = jr_inv(myz.G * a.dt); Exz._Gdt = jr_inv(mxz.G * a.dt); Exy._Gdt = jr_inv(mxy.G * a.dt);
+    Eyz.dtr = jr_inv(a.th + Eyz.etav * Eyz._Gdt + 1.0);
+    Exz.dtr = jr_inv(a.th + Exz.etav * Exz._Gdt + 1.0);
+    Exy.dtr = jr_inv(a.th + Exy.etav * Exy._Gdt + 1.0);
+#define COMP(Q, OYZ, OXZ, OXY, TYZ, TXZ, TXY, OLDYZ, OLDXZ, OLDXY, EPYZ, EPXZ, EPXY)                                                   \
+    edge_comp<Q, OYZ>(Eyz, TYZ, OLDYZ, EPYZ);                                                                                          \
+    edge_comp<Q, OXZ>(Exz, TXZ, OLDXZ, EPXZ);                                                                                          \
+    edge_comp<Q, OXY>(Exy, TXY, OLDXY, EPXY);
+    COMP(0, false, false, false, SAV_YZ(SL_txx), SAV_XZ(SL_txx), SAV_XY(SL_txx), SAV_YZ(SL_oxx), SAV_XZ(SL_oxx), SAV_XY(SL_oxx), SAV_YZ(SL_exx),
+         SAV_XZ(SL_exx), SAV_XY(SL_exx))
+    COMP(1, false, false, false, SAV_YZ(SL_tyy), SAV_XZ(SL_tyy), SAV_XY(SL_tyy), SAV_YZ(SL_oyy), SAV_XZ(SL_oyy), SAV_XY(SL_oyy), SAV_YZ(SL_eyy),
+         SAV_XZ(SL_eyy), SAV_XY(SL_eyy))
+    COMP(2, false, false, false, SAV_YZ(SL_tzz), SAV_XZ(SL_tzz), SAV_XY(SL_tzz), SAV_YZ(SL_ozz), SAV_XZ(SL_ozz), SAV_XY(SL_ozz), SAV_YZ(SL_ezz),
+         SAV_XZ(SL_ezz), SAV_XY(SL_ezz))
+    // yz component: own on the yz edge (yz family (ic, j, k) = S(·, 1, 0, 0)); av_clamped_xz_x, av_clamped_xy_x elsewhere
+    COMP(3, true, false, false, S(SL_tyz, 1, 0, 0), SAV_XZ_X(SL_tyz), SAV_XY_X(SL_tyz), S(SL_oyz, 1, 0, 0), SAV_XZ_X(SL_oyz), SAV_XY_X(SL_oyz),
+         S(SL_eyz, 1, 0, 0), SAV_XZ_X(SL_eyz), SAV_XY_X(SL_eyz))
+    // xz component: own on the xz edge (xz family (i, jc, k) = S(·, 0, 1, 0))
+    COMP(4, false, true, false, SAV_YZ_Y(SL_txz), S(SL_txz, 0, 1, 0), SAV_XY_Y(SL_txz), SAV_YZ_Y(SL_oxz), S(SL_oxz, 0, 1, 0), SAV_XY_Y(SL_oxz),
+         SAV_YZ_Y(SL_exz), S(SL_exz, 0, 1, 0), SAV_XY_Y(SL_exz))
+    // xy component: own on the xy edge (xy family (i, j, kc) = S(·, 0, 0, 1))
+    COMP(5, false, false, true, SAV_YZ_Z(SL_txy), SAV_XZ_Z(SL_txy), S(SL_txy, 0, 0, 1), SAV_YZ_Z(SL_oxy), SAV_XZ_Z(SL_oxy), S(SL_oxy, 0, 0, 1),
+         SAV_YZ_Z(SL_exy), SAV_XZ_Z(SL_exy), S(SL_exy, 0, 0, 1))
+#undef COMP
+    edge_finish<DIAG, NP>(a, pt, myz, Eyz, vyz, a.lamyz, a.tyz_o, a.pyz);
+    edge_finish<DIAG, NP>(a, pt, mxz, Exz, vxz, a.lamxz, a.txz_o, a.pxz);
+    edge_finish<DIAG, NP>(a, pt, mxy, Exy, vxy, a.lamxy, a.txy_o, a.pxy);
     {   // ---- centre: cell (i, j, k) = S(·, 1, 1, 1); edge gathers in mysum order (quirk Q15)
         const double eij[6] = {S(SL_exx, 1, 1, 1), S(SL_eyy, 1, 1, 1), S(SL_ezz, 1, 1, 1),
                                0.25 * ((((0.0 + S(SL_eyz, 1, 0, 0)) + S(SL_eyz, 1, 1, 0)) + S(SL_eyz, 1, 0, 1)) + S(SL_eyz, 1, 1, 1)),
                                0.25 * ((((0.0 + S(SL_exz, 0, 1, 0)) + S(SL_exz, 1, 1, 0)) + S(SL_exz, 0, 1, 1)) + S(SL_exz, 1, 1, 1)),
                                0.25 * ((((0.0 + S(SL_exy, 0, 0, 1)) + S(SL_exy, 1, 0, 1)) + S(SL_exy, 0, 1, 1)) + S(SL_exy, 1, 1, 1))};
-        tij[0] = S(SL_txx, 1, 1, 1); tij[1] = S(SL_tyy, 1, 1, 1); tij[2] = S(SL_tzz, 1, 1, 1);
-        tijo[0] = S(SL_oxx, 1, 1, 1); tijo[1] = S(SL_oyy, 1, 1, 1); tijo[2] = S(SL_ozz, 1, 1, 1);
+        double tij[6] = {S(SL_txx, 1, 1, 1), S(SL_tyy, 1, 1, 1), S(SL_tzz, 1, 1, 1), a.tyzc[c], a.txzc[c], a.txyc[c]};
+        const double tijo[6] = {S(SL_oxx, 1, 1, 1), S(SL_oyy, 1, 1, 1), S(SL_ozz, 1, 1, 1), __ldg(a.oyzc + c), __ldg(a.oxzc + c), __ldg(a.oxyc + c)};
+        Mix<NP> mc;
+        mix_load<NP>(pt, a.ph_c, nc, c, mc);
         vc3_centre<DIAG, NP>(a, pt, mc, c, S(SL_eta, 1, 1, 1), S(SL_theta, 1, 1, 1), eij, tij, tijo);
     }
 #undef S
