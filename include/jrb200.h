@@ -217,6 +217,14 @@ int jr_phase_ratios_from_arrays(jr_context *ctx, int32_t ndim, const int32_t n[3
                                 double *Vy, double *Vz, double *xy, double *yz, double *xz);
 
 /* --- stand-alone kernels the reference exposes outside the loops ----------- */
+/* accumulate_tensor!(II, A::SymmetricTensor, dt): II += second_invariant_staggered(A) * dt  src/ext/CUDA/3D.jl:274-279 → src/stokes/StressKernels.jl:364-408 */
+int jr_accumulate_tensor2d(jr_context *ctx, double *II, const double *xx, const double *yy, const double *xy, const int32_t n[3], double dt);
+int jr_accumulate_tensor3d(jr_context *ctx, double *II, const double *xx, const double *yy, const double *zz, const double *yz, const double *xz,
+                           const double *xy, const int32_t n[3], double dt);
+/* accumulate_vol!(EVol_pl, ε_vol_pl, dt): EVol_pl += dt * ε_vol_pl  src/ext/CUDA/3D.jl:281-284 → src/stokes/StressKernels.jl:422-438 */
+int jr_accumulate_vol(jr_context *ctx, double *EVol_pl, const double *e_vol_pl, size_t count, double dt);
+/* maximum(abs.(A)) (allreduce != 0: maximum_mpi over the communicator) — the reduction of compute_dt  src/ext/CUDA/3D.jl:388-390 → src/Utils.jl:492-519 */
+int jr_absmax(jr_context *ctx, const double *A, size_t count, int allreduce, double *out_host);
 /* flow_bcs!(stokes, bcs)  src/ext/CUDA/3D.jl:195-218 → BoundaryConditions.jl:65-100 */
 int jr_flow_bcs3d(jr_context *ctx, double *Ax, double *Ay, double *Az, const int32_t n[3],
                   const int32_t free_slip[6], const int32_t no_slip[6], const int32_t periodic[6]);

@@ -179,6 +179,10 @@ def _declare(L):
     L.jr_tensor_invariant3d.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32p]
     L.jr_shear2center3d.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32p]
     L.jr_phase_ratios_from_arrays.argtypes = [vp, C.c_int32, i32p, C.c_int32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), vp, vp, vp, vp, vp, vp, vp, vp]
+    L.jr_accumulate_tensor2d.argtypes = [vp, vp, vp, vp, vp, i32p, C.c_double]
+    L.jr_accumulate_tensor3d.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32p, C.c_double]
+    L.jr_accumulate_vol.argtypes = [vp, vp, vp, C.c_size_t, C.c_double]
+    L.jr_absmax.argtypes = [vp, vp, C.c_size_t, C.c_int, C.POINTER(C.c_double)]
     L.jr_heatdiffusion_PT.argtypes = [vp, C.POINTER(ThermalFields), C.POINTER(ThermalOpts), vp, vp, C.POINTER(ThermalResult)]
     L.jr_thermal_iterate.argtypes = [vp, C.POINTER(ThermalFields), C.POINTER(ThermalOpts), C.c_int64, C.POINTER(ThermalResult)]
     L.jr_thermal_bcs.argtypes = [vp, vp, C.c_int32, i32p, C.POINTER(ThermalOpts)]

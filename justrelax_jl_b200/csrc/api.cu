@@ -1,5 +1,6 @@
 // api.cu — context, memory helpers, error reporting, reductions of libjrb200 (sm_100a).
 #include "common.cuh"
+#include "comm.cuh"
 #include <cstdarg>
 
 static thread_local char g_err[1024] = "";
@@ -178,6 +179,41 @@ __global__ void k_sumsq_stage2(const double *__restrict__ part, int nparts, doub
     if (threadIdx.x == 0) *out = s;
 }
 
+
+// maximum(abs.(A)) — the reduction behind compute_dt (src/Utils.jl:492-519); NaN propagates like Julia's maximum
+__global__ void k_absmax_stage1(const double *__restrict__ A, size_t n, double *__restrict__ part)
+{
+    __shared__ double sm[32];
+    double m = 0.0;
+    bool nan = false;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const double v = fabs(A[i]);
+        if (v != v) nan = true;
+        m = fmax(m, v);
+    }
+    if (nan) m = NAN;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double w = __shfl_down_sync(0xffffffffu, m, o);
+        m = (m != m || w != w) ? NAN : fmax(m, w);
+    }
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double r = sm[0];
+        for (int w = 1; w < (int)(blockDim.x >> 5); w++) r = (r != r || sm[w] != sm[w]) ? NAN : fmax(r, sm[w]);
+        part[blockIdx.x] = r;
+    }
+}
+__global__ void k_absmax_stage2(const double *__restrict__ part, int nparts, double *__restrict__ out)
+{
+    if (threadIdx.x == 0) {
+        double r = part[0];
+        for (int b = 1; b < nparts; b++) r = (r != r || part[b] != part[b]) ? NAN : fmax(r, part[b]);
+        *out = r;
+    }
+}
+
 int jr_launch_sumsq(jr_context *ctx, const double *A, const int32_t n[3], int interior, double *d_out_slot)
 {
     const int o = interior ? 1 : 0;
@@ -232,6 +268,27 @@ int jr_sumsq(jr_context *ctx, const double *A, const int32_t n[3], int interior,
     st = jr_launch_sumsq(ctx, A, n, interior, (double *)slot);
     if (st) return st;
     JR_CUDA(cudaMemcpyAsync(ctx->h_pinned, slot, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    JR_CUDA(cudaStreamSynchronize(ctx->stream));
+    *out_host = ctx->h_pinned[0];
+    return JR_OK;
+}
+
+
+int jr_absmax(jr_context *ctx, const double *A, size_t count, int allreduce, double *out_host)
+{
+    JR_REQUIRE(ctx && A && out_host && count > 0, JR_ERR_ARG, "jr_absmax: null argument");
+    JR_CUDA(cudaSetDevice(ctx->device));
+    void *buf = nullptr;
+    const int nb = 512;
+    int st = jr_ctx_scratch(ctx, "absmax_part", (nb + 16) * sizeof(double), &buf);
+    if (st) return st;
+    double *part = (double *)buf, *out = part + nb;
+    k_absmax_stage1<<<nb, 256, 0, ctx->stream>>>(A, count, part);
+    k_absmax_stage2<<<1, 32, 0, ctx->stream>>>(part, nb, out);
+    ctx->launches += 2;
+    JR_CHECK_LAUNCH();
+    if (allreduce && (st = jr_comm_allreduce_dev(ctx, out, 1, 1))) return st;   // maximum_mpi
+    JR_CUDA(cudaMemcpyAsync(ctx->h_pinned, out, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     JR_CUDA(cudaStreamSynchronize(ctx->stream));
     *out_host = ctx->h_pinned[0];
     return JR_OK;

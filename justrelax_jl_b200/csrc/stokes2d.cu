@@ -861,4 +861,14 @@ int jr_tensor_invariant2d(jr_context *ctx, double *II, const double *xx, const d
     return JR_OK;
 }
 
+int jr_accumulate_tensor2d(jr_context *ctx, double *II, const double *xx, const double *yy, const double *xy, const int32_t n[3], double dt)
+{
+    JR_REQUIRE(ctx && II && xx && yy && xy && n, JR_ERR_ARG, "jr_accumulate_tensor2d: null argument");
+    k_inv_stag2d<<<grid2(n[0], n[1]), dim3(32, 8), 0, ctx->stream>>>(n[0], n[1], II, xx, yy, xy, 1, dt);
+    ctx->launches++;
+    JR_CHECK_LAUNCH();
+    JR_CUDA(cudaStreamSynchronize(ctx->stream));
+    return JR_OK;
+}
+
 }  // extern "C"

@@ -1057,4 +1057,25 @@ int jr_shear2center3d(jr_context *ctx, double *yz_c, double *xz_c, double *xy_c,
     return JR_OK;
 }
 
+int jr_accumulate_tensor3d(jr_context *ctx, double *II, const double *xx, const double *yy, const double *zz, const double *yz, const double *xz,
+                           const double *xy, const int32_t n[3], double dt)
+{
+    JR_REQUIRE(ctx && II && xx && yy && zz && yz && xz && xy && n, JR_ERR_ARG, "jr_accumulate_tensor3d: null argument");
+    k_inv_stag3d<<<grid3(n[0], n[1], n[2]), BLK3, 0, ctx->stream>>>(n[0], n[1], n[2], II, xx, yy, zz, yz, xz, xy, 1, dt);
+    ctx->launches++;
+    JR_CHECK_LAUNCH();
+    JR_CUDA(cudaStreamSynchronize(ctx->stream));
+    return JR_OK;
+}
+
+int jr_accumulate_vol(jr_context *ctx, double *EVol_pl, const double *e_vol_pl, size_t count, double dt)
+{
+    JR_REQUIRE(ctx && EVol_pl && e_vol_pl, JR_ERR_ARG, "jr_accumulate_vol: null argument");
+    k_axpy3<<<(unsigned)((count + 255) / 256), 256, 0, ctx->stream>>>(count, EVol_pl, e_vol_pl, dt);
+    ctx->launches++;
+    JR_CHECK_LAUNCH();
+    JR_CUDA(cudaStreamSynchronize(ctx->stream));
+    return JR_OK;
+}
+
 }  // extern "C"

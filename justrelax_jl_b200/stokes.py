@@ -429,3 +429,33 @@ def tensor_invariant_(T, ni):
         return tensor_invariant3d_(T, ni)
     _abi.check(_abi.lib().jr_tensor_invariant2d(context(), data_ptr(T.II), data_ptr(T.xx), data_ptr(T.yy), data_ptr(T.xy),
                                                  _abi.i32x(list(ni) + [1])))
+
+
+def accumulate_tensor_(II, A, dt, ni):
+    """accumulate_tensor!(II, A::SymmetricTensor, dt) — src/stokes/StressKernels.jl:364-408 (II += second_invariant_staggered(A) · dt)."""
+    n3 = _abi.i32x(list(ni) + [1] * (3 - len(ni)))
+    if len(ni) == 2:
+        _abi.check(_abi.lib().jr_accumulate_tensor2d(context(), data_ptr(II), data_ptr(A.xx), data_ptr(A.yy), data_ptr(A.xy), n3, float(dt)))
+    else:
+        _abi.check(_abi.lib().jr_accumulate_tensor3d(context(), data_ptr(II), data_ptr(A.xx), data_ptr(A.yy), data_ptr(A.zz), data_ptr(A.yz),
+                                                      data_ptr(A.xz), data_ptr(A.xy), n3, float(dt)))
+
+
+def accumulate_vol_(EVol_pl, ε_vol_pl, dt):
+    """accumulate_vol!(EVol_pl, ε_vol_pl, dt) — src/stokes/StressKernels.jl:422-438."""
+    _abi.check(_abi.lib().jr_accumulate_vol(context(), data_ptr(EVol_pl), data_ptr(ε_vol_pl), int(np.prod(EVol_pl.shape)), float(dt)))
+
+
+def compute_dt_(stokes, di, dt_diff=math.inf, igg: Optional[IGG] = None):
+    """compute_dt(stokes, di[, dt_diff][, igg]) — src/Utils.jl:492-519: min(dt_diff, 0.9 · min_d(di[d] · inv(maximum(abs.(V_d))))), with
+    maximum_mpi when an IGG is given."""
+    best = math.inf
+    for d, v in zip(di, stokes.V):
+        if v is None:
+            continue
+        out = C.c_double()
+        _abi.check(_abi.lib().jr_absmax(context(), data_ptr(v), int(np.prod(v.shape)), int(igg is not None and igg.nprocs > 1), C.byref(out)))
+        m = out.value
+        x = float(d) * (math.inf if m == 0.0 else 1.0 / m)
+        best = x if math.isnan(x) else min(best, x)   # mapreduce(min): NaN propagates
+    return min(float(dt_diff), best * 0.9)

@@ -144,3 +144,52 @@ def test_standalone_3d_kernels(oracle):
     jst.compute_ρg_(ρg, pr, s.rheology, args, st)
     for a, nm in zip(ρg, ("rhogx", "rhogy", "rhogz")):
         assert max_rel_diff(to_host(a), d[nm]) <= 1e-15, nm
+
+
+def test_compute_dt_and_accumulate_entry_points(oracle):
+    """compute_dt (src/Utils.jl:492-519), accumulate_tensor! / accumulate_vol! (src/stokes/StressKernels.jl:364-438), flow_bcs! and
+    displacement2velocity! with DisplacementBoundaryConditions (src/types/displacement.jl:33-70) through the public API"""
+    from justrelax_jl_b200 import B200Backend, PTArray, StokesArrays, stokes as jst, to_host
+    from justrelax_jl_b200.types import DisplacementBoundaryConditions
+
+    rng = np.random.default_rng(12)
+    ni = (10, 9, 8)
+    st = StokesArrays(B200Backend, *ni)
+    host = {}
+    for nm, a in (("Vx", st.V.Vx), ("Vy", st.V.Vy), ("Vz", st.V.Vz), ("Ux", st.U.Ux), ("Uy", st.U.Uy), ("Uz", st.U.Uz)):
+        host[nm] = np.asfortranarray(rng.uniform(-2, 2, size=tuple(a.shape)))
+        a.copy_(PTArray(B200Backend)(host[nm]))
+    di = (0.1, 0.2, 0.3)
+    want = min(0.5, 0.9 * min(d * (1.0 / np.abs(host[k]).max()) for d, k in zip(di, ("Vx", "Vy", "Vz"))))
+    assert jst.compute_dt_(st, di, 0.5) == want
+    assert jst.compute_dt_(st, di) == 0.9 * min(d * (1.0 / np.abs(host[k]).max()) for d, k in zip(di, ("Vx", "Vy", "Vz")))
+    # accumulate_tensor! 3D: II += second_invariant_staggered(ε_pl) dt
+    T = st.ε_pl
+    h = {}
+    for nm in ("xx", "yy", "zz", "yz", "xz", "xy"):
+        a = getattr(T, nm)
+        h[nm] = np.asfortranarray(rng.uniform(-1, 1, size=tuple(a.shape)))
+        a.copy_(PTArray(B200Backend)(h[nm]))
+    E0 = np.asfortranarray(rng.uniform(0, 1, size=ni))
+    st.EII_pl.copy_(PTArray(B200Backend)(E0))
+    jst.accumulate_tensor_(st.EII_pl, T, 0.37, ni)
+    g = lambda A, ax: sum(np.take(A, range(o[0], o[0] + A.shape[ax[0]] - 1), ax[0]).take(range(o[1], o[1] + A.shape[ax[1]] - 1), ax[1]) ** 2
+                          for o in ((0, 0), (1, 0), (0, 1), (1, 1))) / 4
+    II = np.sqrt(0.5 * (h["xx"] ** 2 + h["yy"] ** 2 + h["zz"] ** 2) + g(h["yz"], (1, 2)) + g(h["xz"], (0, 2)) + g(h["xy"], (0, 1)))
+    assert max_rel_diff(to_host(st.EII_pl), E0 + II * 0.37) <= 1e-14
+    ev = np.asfortranarray(rng.uniform(-1, 1, size=ni))
+    st.ε_vol_pl.copy_(PTArray(B200Backend)(ev))
+    jst.accumulate_vol_(st.EVol_pl, st.ε_vol_pl, 0.37)
+    assert max_rel_diff(to_host(st.EVol_pl), 0.37 * ev) <= 1e-15
+    # DisplacementBoundaryConditions: flow_bcs! acts on U; displacement2velocity!: V = U · inv(dt)
+    bcs = DisplacementBoundaryConditions(free_slip=dict(left=True, right=True, front=True, back=True, top=True, bot=True))
+    jst.flow_bcs_(st, bcs)
+    d = oracle.alloc_stokes(ni, dict(Vx=host["Ux"], Vy=host["Uy"], Vz=host["Uz"]))
+    opts = oracle.make_opts(type("pt", (), dict(r=1, θ_dτ=1, ηdτ=1, ϵ_rel=1, ϵ_abs=1)), (1, 1, 1), 1.0, dict(free_slip=[1] * 6), ni, iterMax=1, nout=1)
+    fs = oracle.make_fields(d, ni)
+    oracle.lib().orc_flow_bcs3(C.byref(fs), C.byref(opts), 0)
+    for u, v in (("Ux", "Vx"), ("Uy", "Vy"), ("Uz", "Vz")):
+        assert np.array_equal(to_host(getattr(st.U, u)), d[v]), u
+    assert np.array_equal(to_host(st.V.Vx), host["Vx"])
+    jst.displacement2velocity_(st, 0.25)
+    assert np.array_equal(to_host(st.V.Vz), d["Vz"] * (1.0 / 0.25))
