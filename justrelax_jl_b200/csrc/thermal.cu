@@ -40,6 +40,7 @@ struct ThArgs {
     double cfv_lo[3], cfv_hi[3];
     int write_q2, write_res, next_pt;   // next_pt: k_th_update also writes θr_dτ, dτ_ρ of the NEXT iteration (update_pt_thermal_arrays! fused)
     double *res_part;  // per-block partial sums of ResT²
+    double *Kf[3];     // rheology form: face conductivities K̄ (static for the ConstantConductivity subset), computed once per call
 };
 
 // ---- GeoParams subset (restated from the published definitions; same operation order as oracle/thermal.c) ----
@@ -95,6 +96,48 @@ __device__ __forceinline__ double th_alpha(const ThTable &t, const double *ph, s
     return x;
 }
 
+
+// the same phase-weighted evaluations from a register copy of the ratios (loaded once per cell); identical operation order
+struct ThRatios { double r[TH_MAX_PHASES]; };
+__device__ __forceinline__ void th_load_ratios(const ThTable &t, const double *__restrict__ ph, size_t stride, size_t idx, ThRatios &R)
+{
+#pragma unroll
+    for (int q = 0; q < TH_MAX_PHASES; q++) R.r[q] = q < t.nphase ? ph[(size_t)q * stride + idx] : 0.0;
+}
+__device__ __forceinline__ double th_rhoCp_r(const ThTable &t, const ThRatios &R, double T, double P)
+{
+    double x = 0.0, out = 0.0;
+    bool done = false;
+#pragma unroll
+    for (int q = 0; q < TH_MAX_PHASES; q++)
+        if (q < t.nphase && !done) {
+            const double v = t.p[q].Cp * th_density(t.p[q], T, P);
+            if (R.r[q] == 1.0) { out = v * R.r[q]; done = true; }
+            else x += (R.r[q] == 0.0) ? 0.0 : v * R.r[q];
+        }
+    return done ? out : x;
+}
+__device__ __forceinline__ double th_K_r(const ThTable &t, const ThRatios &R)
+{
+    double x = 0.0, out = 0.0;
+    bool done = false;
+#pragma unroll
+    for (int q = 0; q < TH_MAX_PHASES; q++)
+        if (q < t.nphase && !done) {
+            if (R.r[q] == 1.0) { out = t.p[q].k * R.r[q]; done = true; }
+            else x += (R.r[q] == 0.0) ? 0.0 : t.p[q].k * R.r[q];
+        }
+    return done ? out : x;
+}
+__device__ __forceinline__ double th_Hr_r(const ThTable &t, const ThRatios &R)
+{
+    double x = 0.0;
+#pragma unroll
+    for (int q = 0; q < TH_MAX_PHASES; q++)
+        if (q < t.nphase) x += (R.r[q] == 0.0) ? 0.0 : t.p[q].Hr * R.r[q];
+    return x;
+}
+
 #define TH_PI 3.141592653589793
 
 // compute_pt_thermal_arrays!  DiffusionPT_coefficients.jl:105-151
@@ -138,15 +181,45 @@ __device__ __forceinline__ void th_flux_dim(const ThArgs &a, int i, int j, int k
     if (a.form == 0) K = (a.f.K[cL] + a.f.K[cR]) * 0.5;
     else {
         // face phase ratios indexed with the clamped CENTRE indices (quirk Q9)
-        const double *phf = DIM == 0 ? a.f.phase_x : DIM == 1 ? a.f.phase_y : a.f.phase_z;
-        const size_t ps = (size_t)e[0] * e[1] * e[2];
-        const size_t pL = ((size_t)L[2] * e[1] + L[1]) * e[0] + L[0], pR = ((size_t)R[2] * e[1] + R[1]) * e[0] + R[0];
-        K = (th_K(a.tab, phf, ps, pL) + th_K(a.tab, phf, ps, pR)) * 0.5;
+        if (a.Kf[DIM]) K = a.Kf[DIM][qi];
+        else {
+            const double *phf = DIM == 0 ? a.f.phase_x : DIM == 1 ? a.f.phase_y : a.f.phase_z;
+            const size_t ps = (size_t)e[0] * e[1] * e[2];
+            const size_t pL = ((size_t)L[2] * e[1] + L[1]) * e[0] + L[0], pR = ((size_t)R[2] * e[1] + R[1]) * e[0] + R[0];
+            K = (th_K(a.tab, phf, ps, pL) + th_K(a.tab, phf, ps, pR)) * 0.5;
+        }
     }
     const double th_ = (a.f.theta_r_dtau[cL] + a.f.theta_r_dtau[cR]) * 0.5;
     const double qx = -K * (Th - Tl) * a._di[DIM];
     if (a.write_q2) q2[qi] = qx;
     q[qi] = (q[qi] * th_ + qx) / (1.0 + th_);
+}
+
+// K̄ at the faces of dimension DIM: (K(cL) + K(cR)) / 2 with the face phase ratios indexed by the clamped centre indices (quirk Q9) — the
+// expression compute_flux! evaluates every iteration; for ConstantConductivity it does not change during a solve
+template <int DIM>
+__device__ __forceinline__ void th_kface_dim(const ThArgs &a, int i, int j, int k)
+{
+    const ThDims &d = a.d;
+    const int nc3[3] = {d.nx, d.ny, d.nz};
+    int e[3] = {d.nx, d.ny, d.nz};
+    e[DIM] += 1;
+    const int I[3] = {i, j, k};
+    if (i >= e[0] || j >= e[1] || k >= e[2]) return;
+    int L[3] = {i, j, k}, R[3] = {i, j, k};
+    L[DIM] = jr_clamp(I[DIM] - 1, 0, nc3[DIM] - 1);
+    R[DIM] = jr_clamp(I[DIM], 0, nc3[DIM] - 1);
+    const double *phf = DIM == 0 ? a.f.phase_x : DIM == 1 ? a.f.phase_y : a.f.phase_z;
+    const size_t ps = (size_t)e[0] * e[1] * e[2];
+    const size_t pL = ((size_t)L[2] * e[1] + L[1]) * e[0] + L[0], pR = ((size_t)R[2] * e[1] + R[1]) * e[0] + R[0];
+    a.Kf[DIM][((size_t)k * e[1] + j) * e[0] + i] = (th_K(a.tab, phf, ps, pL) + th_K(a.tab, phf, ps, pR)) * 0.5;
+}
+__global__ void __launch_bounds__(256) k_th_kface(const __grid_constant__ ThArgs a)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y, k = blockIdx.z;
+    th_kface_dim<0>(a, i, j, k);
+    th_kface_dim<1>(a, i, j, k);
+    if (a.d.nd == 3) th_kface_dim<2>(a, i, j, k);
 }
 
 __global__ void __launch_bounds__(256) k_th_flux(const __grid_constant__ ThArgs a)
@@ -182,7 +255,10 @@ __global__ void __launch_bounds__(256) k_th_update(const __grid_constant__ ThArg
         const bool dir = a.f.dir_mask && a.f.dir_mask[t] != 0.0;
         double Tn;
         const double Tc = a.f.T[t], Told = a.f.Told[t];
-        double rhoCp = 0.0, src = 0.0;
+        double rhoCp = 0.0, src = 0.0, Hr = 0.0;
+        ThRatios R;
+        const bool hasR = a.form == 1 && a.f.phase_c;
+        if (hasR) th_load_ratios(a.tab, a.f.phase_c, nc, c, R);
         if (dir) {
             // apply_mask!: A = inv(m)·A + m·B  (src/mask/mask.jl:51-52)
             const double m = a.f.dir_mask[t], B = a.f.dir_value ? a.f.dir_value[t] : a.dir_const;
@@ -193,33 +269,33 @@ __global__ void __launch_bounds__(256) k_th_update(const __grid_constant__ ThArg
             Tn = (dtr * (-(th_div(a, i, j, k, false)) + Told * rhoCp * a._dt + a.f.H[c] + a.f.shear_heating[c]) + Tc) / (1.0 + dtr * rhoCp * a._dt);
         } else {
             const double P = a.f.P ? a.f.P[c] : 0.0;
-            rhoCp = th_rhoCp(a.tab, a.f.phase_c, nc, c, Tc, P);
+            if (hasR) { rhoCp = th_rhoCp_r(a.tab, R, Tc, P); Hr = th_Hr_r(a.tab, R); }
+            else { rhoCp = th_rhoCp(a.tab, a.f.phase_c, nc, c, Tc, P); Hr = th_Hr(a.tab, a.f.phase_c, nc, c); }
             const double dtr = a.f.dtau_rho[c];
-            Tn = (dtr * (-(th_div(a, i, j, k, false)) + Told * rhoCp * a._dt + th_Hr(a.tab, a.f.phase_c, nc, c) + a.f.H[c] + a.f.shear_heating[c] +
+            Tn = (dtr * (-(th_div(a, i, j, k, false)) + Told * rhoCp * a._dt + Hr + a.f.H[c] + a.f.shear_heating[c] +
                          a.f.adiabatic[c] * Tc) + Tc) / (1.0 + dtr * rhoCp * a._dt);
         }
         a.f.T[t] = Tn;
         if (a.next_pt) {
             // update_pt_thermal_arrays! of the next iteration (solver.jl:233-234; DiffusionPT_coefficients.jl:105-151): it reads interior T only,
             // which neither thermal_bcs! nor update_halo!(T) touches, so evaluating it here from Tn is the same arithmetic on the same inputs
-            const double rc = th_rhoCp(a.tab, a.f.phase_c, nc, c, Tn, a.f.P ? a.f.P[c] : 0.0);
-            const double _K = 1.0 / th_K(a.tab, a.f.phase_c, nc, c);
+            const double rc = th_rhoCp_r(a.tab, R, Tn, a.f.P ? a.f.P[c] : 0.0);
+            const double _K = 1.0 / th_K_r(a.tab, R);
             const double _Re = 1.0 / (TH_PI + sqrt(TH_PI * TH_PI + rc * (a.L * a.L) * _K * a._dt));
             a.f.theta_r_dtau[c] = a.L / a.Vpdtau * _Re;
             a.f.dtau_rho[c] = a.Vpdtau * a.L * _K * _Re;
         }
         if (a.write_res) {
-            double R = 0.0;
+            double Rr = 0.0;
             if (!dir) {
-                if (a.form == 0) R = -rhoCp * (Tn - Told) * a._dt - th_div(a, i, j, k, true) + a.f.H[c] + a.f.shear_heating[c];
+                if (a.form == 0) Rr = -rhoCp * (Tn - Told) * a._dt - th_div(a, i, j, k, true) + a.f.H[c] + a.f.shear_heating[c];
                 else {
-                    const double rc2 = th_rhoCp(a.tab, a.f.phase_c, nc, c, Tn, a.f.P ? a.f.P[c] : 0.0);
-                    R = -rc2 * (Tn - Told) * a._dt - th_div(a, i, j, k, true) + th_Hr(a.tab, a.f.phase_c, nc, c) + a.f.H[c] + a.f.shear_heating[c] +
-                        a.f.adiabatic[c] * Tn;
+                    const double rc2 = hasR ? th_rhoCp_r(a.tab, R, Tn, a.f.P ? a.f.P[c] : 0.0) : th_rhoCp(a.tab, a.f.phase_c, nc, c, Tn, a.f.P ? a.f.P[c] : 0.0);
+                    Rr = -rc2 * (Tn - Told) * a._dt - th_div(a, i, j, k, true) + Hr + a.f.H[c] + a.f.shear_heating[c] + a.f.adiabatic[c] * Tn;
                 }
             }
-            a.f.ResT[c] = R;
-            r2 = R * R;
+            a.f.ResT[c] = Rr;
+            r2 = Rr * Rr;
         }
     }
     if (a.write_res) {
@@ -335,6 +411,7 @@ static int th_check(const jr_thermal_fields *f, const jr_thermal_opts *o, ThArgs
         a.cfv_lo[q] = on ? o->cf_value[lo[q]] : 0.0; a.cfv_hi[q] = on ? o->cf_value[hi[q]] : 0.0;
     }
     a.write_q2 = 0; a.write_res = 0; a.res_part = nullptr;
+    a.Kf[0] = a.Kf[1] = a.Kf[2] = nullptr;
     return JR_OK;
 }
 
@@ -374,6 +451,25 @@ static int th_halo(jr_context *ctx, const ThArgs &a)
     const int32_t ext[3] = {a.d.gx, a.d.gy, a.d.gz}, nc[3] = {a.d.nx, a.d.ny, a.d.nz};
     const jr_harr H = jr_harr_dense(a.f.T, ext, nc);
     return jr_comm_halo(ctx, &H, 1);  // update_halo!(thermal.T)  DiffusionPT_solver.jl:110,261
+}
+
+// rheology form with phase ratios: face conductivities once per call (scratch owned by the context)
+static int th_prepare_kface(jr_context *ctx, ThArgs &a)
+{
+    if (!(a.form == 1 && a.f.phase_c)) return JR_OK;
+    const ThDims &d = a.d;
+    const size_t nfx = (size_t)(d.nx + 1) * d.ny * d.nz, nfy = (size_t)d.nx * (d.ny + 1) * d.nz, nfz = d.nd == 3 ? (size_t)d.nx * d.ny * (d.nz + 1) : 0;
+    void *buf = nullptr;
+    int st = jr_ctx_scratch(ctx, "th_kface", (nfx + nfy + nfz) * sizeof(double), &buf);
+    if (st) return st;
+    ThArgs b = a;
+    b.Kf[0] = (double *)buf; b.Kf[1] = b.Kf[0] + nfx; b.Kf[2] = d.nd == 3 ? b.Kf[1] + nfy : nullptr;
+    dim3 blk(32, 8, 1), g1((d.nx + 32) / 32, (d.ny + 8) / 8, d.nd == 3 ? d.nz + 1 : 1);
+    k_th_kface<<<g1, blk, 0, ctx->stream>>>(b);
+    ctx->launches++;
+    JR_CHECK_LAUNCH();
+    a.Kf[0] = b.Kf[0]; a.Kf[1] = b.Kf[1]; a.Kf[2] = b.Kf[2];
+    return JR_OK;
 }
 
 // one PT iteration; `sample` = this iteration's residual is read (iter % nout == 0)
@@ -456,6 +552,7 @@ int jr_thermal_iterate(jr_context *ctx, const jr_thermal_fields *f, const jr_the
     if ((st = jr_ctx_scratch(ctx, "th_sum", 16 * sizeof(double), &slot))) return st;
     ctx->launches = 0;
     JR_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    if ((st = th_prepare_kface(ctx, a))) return st;
     for (int64_t it = 0; it < niter; it++)
         if ((st = th_iter(ctx, a, o, it == niter - 1, (double *)slot, it > 0, it < niter - 1))) return st;
     JR_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
@@ -492,6 +589,7 @@ int jr_heatdiffusion_PT(jr_context *ctx, const jr_thermal_fields *f, const jr_th
         k_th_adiabatic<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(a, stokes_P, stokes_P0, nc);
         ctx->launches++;
     }
+    if ((st = th_prepare_kface(ctx, a))) return st;
     int64_t iter = 0, cont = 0;
     double err = 2 * o->eps;
     bool have_pt = false;
