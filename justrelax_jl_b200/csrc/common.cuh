@@ -119,6 +119,8 @@ int jr_launch_maxloc3d(jr_context *ctx, double *B, const double *A, const int32_
 int jr_launch_sumsq(jr_context *ctx, const double *A, const int32_t n[3], int interior, double *d_out_slot);
 int jr_stokes3d_VA_unfused_iter(jr_context *ctx, const jr_fields *s, const jr_stokes_opts *o);
 int jr_stokes3d_VA_fused_iter(jr_context *ctx, const jr_fields *s, const jr_stokes_opts *o, int write_diag, int parity);
+int jr_stokes3d_VA_fused_multi_max(jr_context *ctx, const jr_stokes_opts *o);
+int jr_stokes3d_VA_fused_multi(jr_context *ctx, const jr_fields *s, const jr_stokes_opts *o, int niter, int parity);
 int jr_stokes3d_VA_fused_supported(const jr_fields *s, const jr_stokes_opts *o);
 int jr_stokes3d_VA_fused_begin(jr_context *ctx, const jr_fields *s, const jr_stokes_opts *o);
 int jr_stokes3d_VA_fused_finish(jr_context *ctx, const jr_fields *s, int64_t niter);

@@ -6,6 +6,7 @@
 // JR_FLAG_UNFUSED, the reference-structured kernel sequence (stokes3d_unfused.cu).
 #include "common.cuh"
 #include "comm.cuh"
+#include <algorithm>
 
 #define F(name) (s->f[JR_F_##name])
 
@@ -75,9 +76,18 @@ int jr_stokes3d_iterate_VA(jr_context *ctx, const jr_fields *s, const jr_stokes_
     // the timed region includes packing the dense arrays into the TMA box layout and unpacking them again
     JR_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
     if (fused && (st = jr_stokes3d_VA_fused_begin(ctx, s, o))) return st;
-    for (int64_t it = 0; it < niter; it++) {
+    // iterations whose diagnostics nobody reads run several per launch (the kernel applies flow_bcs! itself)
+    const int64_t multi = (fused && !(ctx->flags & JR_FLAG_DIAG_EVERY_ITER)) ? jr_stokes3d_VA_fused_multi_max(ctx, o) : 0;
+    for (int64_t it = 0; it < niter;) {
+        const int64_t nb = std::min<int64_t>(niter - 1 - it, multi);
+        if (nb >= 1 && multi >= 1) {
+            if ((st = jr_stokes3d_VA_fused_multi(ctx, s, o, (int)nb, (int)(it & 1)))) return st;
+            it += nb;
+            continue;
+        }
         const int diag = (ctx->flags & JR_FLAG_DIAG_EVERY_ITER) ? 1 : (it == niter - 1);
         if ((st = one_iter_VA(ctx, s, o, fused, diag, it))) return st;
+        it++;
     }
     if (fused && (st = jr_stokes3d_VA_fused_finish(ctx, s, niter))) return st;
     JR_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
@@ -116,7 +126,18 @@ int jr_stokes3d_solve_VA(jr_context *ctx, const jr_fields *s, const jr_stokes_op
     if ((st = pre_VA(ctx, s))) return st;
     JR_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
     if (fused && (st = jr_stokes3d_VA_fused_begin(ctx, s, o))) return st;
+    const int64_t multi = (fused && !(ctx->flags & JR_FLAG_DIAG_EVERY_ITER)) ? jr_stokes3d_VA_fused_multi_max(ctx, o) : 0;
     while (iter < 2 || (((err / err_it1) > o->eps_rel && err > o->eps_abs) && iter <= o->iterMax)) {
+        // the iterations up to the next sample (or iterMax) whose diagnostics nobody reads: one launch.  The loop
+        // condition cannot change in between (err is only updated at samples; iter stays ≤ iterMax).
+        if (multi >= 1 && iter >= 1) {
+            const int64_t nb = std::min<int64_t>(std::min<int64_t>(o->nout - 1 - (iter % o->nout), o->iterMax - iter), multi);
+            if (nb >= 1) {
+                if ((st = jr_stokes3d_VA_fused_multi(ctx, s, o, (int)nb, (int)(iter & 1)))) return st;
+                iter += nb;
+                continue;
+            }
+        }
         // diagnostics (∇V, ε, R, U) are only read at `nout` samples and after the loop; the loop can only
         // end right after a sample or once iter > iterMax, so writing them on those iterations reproduces
         // the reference's final state exactly.

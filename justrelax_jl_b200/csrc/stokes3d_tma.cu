@@ -61,6 +61,15 @@ struct alignas(64) VaArgs {
     int pol_ld, pol_st;  // L2 eviction policy of the TMA loads / output stores (0 normal, 1 evict_first, 2 evict_last)
     double _dx, _dy, _dz, dt, r, theta_dtau, eta_dtau;
     double fxc, fyc, fzc;  // constant body force (RHOG = false)
+    // ---- MULTI (several PT iterations in one launch, boundary conditions applied by the kernel itself) ----
+    CUtensorMap mS5b;                  // the other state set (in-set of odd iterations of this launch)
+    double *out2;                      // out-set of odd iterations (= the set mS5 describes)
+    unsigned long long *gbar;          // grid barrier counter between iterations
+    unsigned long long gbar_base;      // its value at launch
+    int niter;                         // iterations of this launch
+    int dbg_nobc, dbg_nobar;           // timing experiments only (results are wrong): skip the in-kernel BCs / the grid barrier
+    int bc_nsn[6];                     // x-lo, x-hi, y-lo, y-hi, z-lo, z-hi: boundary-normal face is zeroed (no_slip!)
+    double bc_sg[6];                   // same sides: tangential ghost = bc_sg · interior (+1 free slip, −1 no slip)
 };
 
 #define TXW 30  // owned columns per tile
@@ -81,7 +90,10 @@ __device__ __forceinline__ bool jr_elect_one()
 //       progress counter, polled before the barrier so the L2 round trip is hidden): neighbouring tiles then load
 //       their shared halo rows within a few steps of each other and the second reader hits L2 instead of HBM.
 //   all warps: wait on the slot's full mbarrier, update, ONE __syncthreads per step, store.
-template <int BY, bool FINITE_DT, bool DIAG, int NST, bool RHOG>
+//   MULTI: the launch runs a.niter iterations (ping-pong S_in ↔ S_out, a grid-wide barrier with generic→async proxy
+//       fences between them) and applies flow_bcs! itself: every thread that holds the source of a ghost / boundary
+//       value (no_slip! → free_slip! as complete sweeps, same gather as k_bc_box3) also stores its images.
+template <int BY, bool FINITE_DT, bool DIAG, int NST, bool RHOG, bool MULTI>
 __global__ void __launch_bounds__(32 * BY, (BY <= 10 ? 2 : 1)) k_va_tma(const __grid_constant__ VaArgs a)
 {
     using M = SlotMap<FINITE_DT, RHOG>;
@@ -110,13 +122,14 @@ __global__ void __launch_bounds__(32 * BY, (BY <= 10 ? 2 : 1)) k_va_tma(const __
 
     // ---- producer state (CTA-uniform): the next z-step to load ----
     int p_g = 0, p_r = 0, p_l = 0, p_slot = 0, p_x0 = 0, p_y0 = 0, p_kb = 0;
+    const CUtensorMap *mS = &a.mS5;                // in-set of the current iteration
+    unsigned long long pbase = a.progress_base;    // progress counter value at the start of the current iteration
     auto p_decode = [&]() {
         const int item = p_r * G + cta;
         const int chunk = item / ntile, t = item - chunk * ntile;
         const int by = t / a.ntx, bx = t - by * a.ntx;
         p_x0 = bx * TXW; p_y0 = by * TY; p_kb = chunk * a.kchunk;
     };
-    p_decode();
     // loads of step p_g (one elected lane).  Step 0 of an item only needs V, η[, G] of plane kb−1 (queue fill).
     auto p_issue = [&]() {
         const uint64_t pld = jr_l2_policy(a.pol_ld);
@@ -128,11 +141,11 @@ __global__ void __launch_bounds__(32 * BY, (BY <= 10 ? 2 : 1)) k_va_tma(const __
         uint32_t bytes = (5 + 1 + (FINITE_DT ? 1 : 0)) * TILE_BYTES;
         if (full) bytes = NARR * TILE_BYTES;
         jr_mbar_arrive_expect_tx(bar, bytes);
-        jr_tma_load_4d_hint(d + T_Vx * TILE, &a.mS5, p_x0, p_y0, S_Vx, za, bar, pld);
+        jr_tma_load_4d_hint(d + T_Vx * TILE, mS, p_x0, p_y0, S_Vx, za, bar, pld);
         jr_tma_load_4d_hint(d + T_eta * TILE, &a.mC1, p_x0, p_y0, C_eta, za, bar, pld);
         if (FINITE_DT) jr_tma_load_4d_hint(d + M::G * TILE, &a.mD1, p_x0, p_y0, D_G, za, bar, pld);
         if (full) {
-            jr_tma_load_4d_hint(d + T_tzz * TILE, &a.mS5, p_x0, p_y0, S_tzz, zc, bar, pld);
+            jr_tma_load_4d_hint(d + T_tzz * TILE, mS, p_x0, p_y0, S_tzz, zc, bar, pld);
             if (FINITE_DT) {
                 jr_tma_load_4d_hint(d + M::oyz * TILE, &a.mD2, p_x0, p_y0, D_oyz, za, bar, pld);
                 jr_tma_load_4d_hint(d + M::K * TILE, &a.mD7, p_x0, p_y0, D_K, zc, bar, pld);
@@ -154,26 +167,8 @@ __global__ void __launch_bounds__(32 * BY, (BY <= 10 ? 2 : 1)) k_va_tma(const __
     auto p_target = [&](int gt) -> unsigned long long {
         const int rr = gt / nstep, ll = gt - rr * nstep;
         const int act = min(G, nitem - rr * G);
-        return a.progress_base + (unsigned long long)G * nstep * rr + (unsigned long long)act * (ll + 1);
+        return pbase + (unsigned long long)G * nstep * rr + (unsigned long long)act * (ll + 1);
     };
-    // prologue: the first DEPTH steps
-#pragma unroll
-    for (int d = 0; d < DEPTH; d++) {
-        if (p_g < my_steps) {
-            if (ty == 0) {
-                if (jr_elect_one()) {
-                    if (d == 0) {
-                        jr_tma_prefetch_desc(&a.mS5);
-                        jr_tma_prefetch_desc(&a.mC1);
-                        jr_tma_prefetch_desc(&a.mC4);
-                    }
-                    p_issue();
-                }
-            }
-            p_advance();
-        }
-    }
-
     const double _dx = a._dx, _dy = a._dy, _dz = a._dz, th = a.theta_dtau;
     const double inv3 = jr_inv(3.0);
     const double dtr_inf = jr_inv(th + 1.0);  // compute_dτ_r with 1/(G dt) = 0: fma(η, 0, 1) = 1
@@ -211,8 +206,49 @@ __global__ void __launch_bounds__(32 * BY, (BY <= 10 ? 2 : 1)) k_va_tma(const __
         }                                                                                                 \
     } while (0)
 
-    int slot = 0, g = 0;
+    // boundary conditions of the in-kernel flow_bcs! (MULTI): ghost-image directions of this thread (−1 low side,
+    // +1 high side, 0 none) for sources on the first / last interior row; per item (x, y) and per step (z)
+#define JR_GHOSTS(q, v, z, ma, sa, ea, mb, sb, eb)                                                            \
+    do {                                                                                                      \
+        if ((ma) | (mb)) {                                                                                    \
+            const double ga_ = (z) ? 1.0 : ((ma) > 0 ? a.bc_sg[2 * (ea) + 1] : a.bc_sg[2 * (ea)]);                \
+            const double gb_ = (z) ? 1.0 : ((mb) > 0 ? a.bc_sg[2 * (eb) + 1] : a.bc_sg[2 * (eb)]);                \
+            if (ma) jr_st_hint((q) + (ma) * (ptrdiff_t)(sa), ga_ * (v), pst);                                 \
+            if (mb) jr_st_hint((q) + (mb) * (ptrdiff_t)(sb), gb_ * (v), pst);                                 \
+            if ((ma) && (mb)) jr_st_hint((q) + (ma) * (ptrdiff_t)(sa) + (mb) * (ptrdiff_t)(sb), (ga_ * gb_) * (v), pst); \
+        }                                                                                                     \
+    } while (0)
+
+    int slot = 0;
     uint32_t parity = 0;
+    const int niter = MULTI ? a.niter : 1;
+    for (int it = 0; it < niter; ++it) {
+    double *const outset = (MULTI && (it & 1)) ? a.out2 : a.out;
+    if (MULTI) {
+        mS = (it & 1) ? &a.mS5b : &a.mS5;
+        pbase = a.progress_base + (unsigned long long)it * (unsigned long long)nitem * (unsigned long long)nstep;
+        p_g = 0; p_r = 0; p_l = 0;
+    }
+    p_decode();
+    // prologue: the first DEPTH steps
+#pragma unroll
+    for (int d = 0; d < DEPTH; d++) {
+        if (p_g < my_steps) {
+            if (ty == 0) {
+                if (jr_elect_one()) {
+                    if (d == 0 && it == 0) {
+                        jr_tma_prefetch_desc(&a.mS5);
+                        jr_tma_prefetch_desc(&a.mC1);
+                        jr_tma_prefetch_desc(&a.mC4);
+                        if (MULTI) jr_tma_prefetch_desc(&a.mS5b);
+                    }
+                    p_issue();
+                }
+            }
+            p_advance();
+        }
+    }
+    int g = 0;
     for (int r = 0; r < my_rounds; ++r) {
         const int item = r * G + cta;
         const int chunk = item / ntile, t = item - chunk * ntile;
@@ -226,8 +262,10 @@ __global__ void __launch_bounds__(32 * BY, (BY <= 10 ? 2 : 1)) k_va_tma(const __
         const bool vxz = own && gi <= nx && gj < ny;   // xz edge exists
         const bool vyz = own && gi < nx && gj <= ny;   // yz edge exists
         const bool stVx = cell && gi >= 1, stVy = cell && gj >= 1;
+        // MULTI: this thread holds sources of boundary / ghost values in x or y (first / last interior row, boundary faces)
+        const bool bxy = MULTI && own && (gi == 0 || gi >= nx - 1 || gj == 0 || gj >= ny - 1);
         // out-set pointer of (X, Y) in plane group Z = k+1: ((Z·10 + a)·PY + Y)·PX + X; starts at Z = kb (step k = kb−1)
-        double *po = a.out + ((size_t)kb * S_N) * pxy + (size_t)Y * a.PX + X;
+        double *po = outset + ((size_t)kb * S_N) * pxy + (size_t)Y * a.PX + X;
 
         for (int l = 0; l < nstep; ++l) {
             const int k = kb - 2 + l;
@@ -318,6 +356,12 @@ __global__ void __launch_bounds__(32 * BY, (BY <= 10 ? 2 : 1)) k_va_tma(const __
                 const double c_fz = RHOG ? p[M::fz * TILE] : a.fzc, c_ett = p[M::ett * TILE];
                 const double sRz_next = _dx * (p[T_txz * TILE + 1] - txz_n) + _dy * (p[T_tyz * TILE + 32] - tyz_n);
                 const bool kin = k >= kb && k < ke;  // this chunk owns plane k (k = kb−1 is the warm-up plane)
+                // MULTI: flow_bcs! inside the kernel.  mz: CTA-uniform z ghost-image direction of this plane; bz: this thread
+                // holds the source of some boundary / ghost value at this step (rare) — the only test on the common path
+                const int mz = !MULTI ? 0 : (k == 0 ? -1 : (k == nz - 1 ? 1 : 0));
+                const bool bz = MULTI && (bxy || mz != 0) && !a.dbg_nobc;
+#define JR_MX (gi == 0 ? -1 : (gi == nx - 1 ? 1 : 0))
+#define JR_MY (gj == 0 ? -1 : (gj == ny - 1 ? 1 : 0))
                 if (kin) {
                     if (cell) {
                         jr_st_hint(&po[S_P * pxy], P_n, pst); jr_st_hint(&po[S_txx * pxy], txx_n, pst);
@@ -342,6 +386,13 @@ __global__ void __launch_bounds__(32 * BY, (BY <= 10 ? 2 : 1)) k_va_tma(const __
                             a.Rx[((size_t)k * ny + gj) * (nx - 1) + (gi - 1)] = R;
                             a.Ux[((size_t)(k + 1) * (ny + 2) + gj + 1) * (nx + 1) + gi] = vn * a.dt;
                         }
+                        if (MULTI && bz) JR_GHOSTS(&po[S_Vx * pxy], vn, false, JR_MY, a.PX, 1, mz, S_N * pxy, 2);
+                    } else if (MULTI && bz && vxz && (gi == 0 || gi == nx)) {
+                        // boundary-normal face: kept (free slip) or zeroed (no slip), and its tangential ghosts
+                        const bool z = (gi == 0 ? a.bc_nsn[0] : a.bc_nsn[1]) != 0;
+                        const double v = z ? 0.0 : vx0;
+                        jr_st_hint(&po[S_Vx * pxy], v, pst);
+                        JR_GHOSTS(&po[S_Vx * pxy], v, z, JR_MY, a.PX, 1, mz, S_N * pxy, 2);
                     }
                     // y-momentum: face gj between cells gj−1 (S) and gj
                     if (stVy) {
@@ -354,6 +405,12 @@ __global__ void __launch_bounds__(32 * BY, (BY <= 10 ? 2 : 1)) k_va_tma(const __
                             a.Ry[((size_t)k * (ny - 1) + (gj - 1)) * nx + gi] = R;
                             a.Uy[((size_t)(k + 1) * (ny + 1) + gj) * (nx + 2) + gi + 1] = vn * a.dt;
                         }
+                        if (MULTI && bz) JR_GHOSTS(&po[S_Vy * pxy], vn, false, JR_MX, 1, 0, mz, S_N * pxy, 2);
+                    } else if (MULTI && bz && vyz && (gj == 0 || gj == ny)) {
+                        const bool z = (gj == 0 ? a.bc_nsn[2] : a.bc_nsn[3]) != 0;
+                        const double v = z ? 0.0 : vy0;
+                        jr_st_hint(&po[S_Vy * pxy], v, pst);
+                        JR_GHOSTS(&po[S_Vy * pxy], v, z, JR_MX, 1, 0, mz, S_N * pxy, 2);
                     }
                     // z-momentum: face k between planes k−1 and k
                     if (cell && k >= 1) {
@@ -364,6 +421,16 @@ __global__ void __launch_bounds__(32 * BY, (BY <= 10 ? 2 : 1)) k_va_tma(const __
                             a.Rz[((size_t)(k - 1) * ny + gj) * nx + gi] = R;
                             a.Uz[((size_t)k * (ny + 2) + gj + 1) * (nx + 2) + gi + 1] = vn * a.dt;
                         }
+                        if (MULTI && bz) JR_GHOSTS(&po[S_Vz * pxy], vn, false, JR_MX, 1, 0, JR_MY, a.PX, 1);
+                    }
+                    if (MULTI && mz != 0 && cell && !a.dbg_nobc) {
+                        // z-normal boundary faces: Vz(K = 0) from the queue (k = 0), Vz(K = nz) from the arrival plane
+                        // (k = nz − 1); nz ≥ 3 on this path, so never both
+                        const bool z = (mz < 0 ? a.bc_nsn[4] : a.bc_nsn[5]) != 0;
+                        const double v = z ? 0.0 : (mz < 0 ? vz0 : p[T_Vz * TILE]);
+                        double *const q = (mz < 0 ? po : po + S_N * pxy) + S_Vz * pxy;
+                        jr_st_hint(q, v, pst);
+                        JR_GHOSTS(q, v, z, JR_MX, 1, 0, JR_MY, a.PX, 1);
                     }
                 }
                 // top edges (kz = k+1) belong to the chunk that owns plane k; the kz = 0 edges to chunk 0's warm-up
@@ -387,7 +454,29 @@ __global__ void __launch_bounds__(32 * BY, (BY <= 10 ? 2 : 1)) k_va_tma(const __
             if (++slot == NST) { slot = 0; parity ^= 1u; }
         }
     }
+    if (MULTI && it + 1 < niter && !a.dbg_nobar) {
+        // grid-wide barrier between iterations: every store of this iteration (generic proxy) must be visible to
+        // the TMA loads (async proxy) of every other CTA, and nobody may overwrite a set others still read
+        asm volatile("fence.proxy.async.global;" ::: "memory");
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(a.gbar), "l"(1ull) : "memory");
+            const unsigned long long target = a.gbar_base + (unsigned long long)(it + 1) * (unsigned long long)G;
+            unsigned long long seen = 0;
+            do {
+                asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(a.gbar) : "memory");
+            } while (seen < target);
+            __threadfence();
+            asm volatile("fence.proxy.async.global;" ::: "memory");
+        }
+        __syncthreads();
+    }
+    }  // iterations
 #undef JR_FILL_QUEUE
+#undef JR_GHOSTS
+#undef JR_MX
+#undef JR_MY
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -583,7 +672,7 @@ struct VaPlan {
     CUtensorMap mS5[2], mC1, mC4, mD1, mD2, mD7;
     int BY = 0, nchunk = 1;
     int pol_ld = 2, pol_st = 1, l2promo = 3, slack = 1;
-    unsigned long long *progress = nullptr, progress_base = 0;
+    unsigned long long *progress = nullptr, progress_base = 0, gbar_base = 0;
     bool rhog_const = false;  // ρg arrays are spatially constant: not streamed
     double fc[3] = {0, 0, 0};
 };
@@ -680,10 +769,11 @@ int jr_stokes3d_VA_fused_begin(jr_context *ctx, const jr_fields *s, const jr_sto
             P.nchunk = (nz + kch - 1) / kch;
         }
     }
-    if ((st = jr_ctx_scratch(ctx, "va_progress", 64, &p))) return st;
+    if ((st = jr_ctx_scratch(ctx, "va_progress", 256, &p))) return st;
     P.progress = (unsigned long long *)p;
     P.progress_base = 0;
-    JR_CUDA(cudaMemsetAsync(p, 0, 64, ctx->stream));
+    P.gbar_base = 0;
+    JR_CUDA(cudaMemsetAsync(p, 0, 256, ctx->stream));
     // constant body force?  (one pass over ρg per solve; ρg ≡ 0 in SolVi / Taylor-Green / Burstedde-type benchmarks)
     {
         void *part = nullptr, *mm = nullptr;
@@ -751,18 +841,18 @@ int jr_stokes3d_VA_fused_begin(jr_context *ctx, const jr_fields *s, const jr_sto
     return JR_OK;
 }
 
-template <int BY, bool FIN, bool DG, int NSTv, bool RHOG>
+template <int BY, bool FIN, bool DG, int NSTv, bool RHOG, bool MULTI = false>
 static int launch_one(jr_context *ctx, VaPlan &P, VaArgs &a)
 {
     constexpr int TY = BY - 2;
     constexpr int smem = NSTv * SlotMap<FIN, RHOG>::NARR * 32 * BY * 8;
     static int cta_per_sm = 0;
     if (!cta_per_sm) {
-        JR_CUDA(cudaFuncSetAttribute(k_va_tma<BY, FIN, DG, NSTv, RHOG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        JR_CUDA(cudaFuncSetAttribute(k_va_tma<BY, FIN, DG, NSTv, RHOG>, cudaFuncAttributePreferredSharedMemoryCarveout,
+        JR_CUDA(cudaFuncSetAttribute(k_va_tma<BY, FIN, DG, NSTv, RHOG, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        JR_CUDA(cudaFuncSetAttribute(k_va_tma<BY, FIN, DG, NSTv, RHOG, MULTI>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                      cudaSharedmemCarveoutMaxShared));
         int nb = 0;
-        JR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_va_tma<BY, FIN, DG, NSTv, RHOG>, 32 * BY, smem));
+        JR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_va_tma<BY, FIN, DG, NSTv, RHOG, MULTI>, 32 * BY, smem));
         JR_REQUIRE(nb >= 1, JR_ERR_CUDA, "k_va_tma<%d> does not fit on an SM (%d B shared memory)", BY, smem);
         cta_per_sm = nb;
         if (getenv("JRB200_VERBOSE"))
@@ -778,10 +868,14 @@ static int launch_one(jr_context *ctx, VaPlan &P, VaArgs &a)
     a.progress = P.progress;
     a.progress_base = P.progress_base;
     a.slack = P.slack;
-    P.progress_base += (unsigned long long)items * (a.kchunk + 2);  // every item posts kchunk+2 steps
+    const int nit = MULTI ? a.niter : 1;
+    P.progress_base += (unsigned long long)nit * items * (a.kchunk + 2);  // every item posts kchunk+2 steps per iteration
+    a.gbar = P.progress + 16;  // its own 128-B line
+    a.gbar_base = P.gbar_base;
+    if (!a.dbg_nobar) P.gbar_base += (unsigned long long)(nit - 1) * G;
     void *args[1] = {(void *)&a};
     // cooperative launch: the soft lock-step spins on other CTAs, so all G CTAs must be resident
-    JR_CUDA(cudaLaunchCooperativeKernel((const void *)k_va_tma<BY, FIN, DG, NSTv, RHOG>, dim3(G, 1, 1), dim3(32, BY, 1), args, smem,
+    JR_CUDA(cudaLaunchCooperativeKernel((const void *)k_va_tma<BY, FIN, DG, NSTv, RHOG, MULTI>, dim3(G, 1, 1), dim3(32, BY, 1), args, smem,
                                         ctx->stream));
     return JR_OK;
 }
@@ -801,6 +895,92 @@ static int launch_va(jr_context *ctx, VaPlan &P, VaArgs &a, int diag)
 {
     return P.rhog_const ? launch_va_t<false>(ctx, P, a, diag) : launch_va_t<true>(ctx, P, a, diag);
 }
+// several iterations per launch, boundary conditions inside the kernel (never with diagnostics)
+template <bool RHOG>
+static int launch_va_multi_t(jr_context *ctx, VaPlan &P, VaArgs &a)
+{
+    if (P.finite_dt) return launch_one<8, true, false, 2, RHOG, true>(ctx, P, a);
+    switch (P.BY) {
+    case 8: return launch_one<8, false, false, 3, RHOG, true>(ctx, P, a);
+    case 10: return launch_one<10, false, false, 3, RHOG, true>(ctx, P, a);
+    default: return launch_one<16, false, false, 3, RHOG, true>(ctx, P, a);
+    }
+}
+
+static void fill_args(VaArgs &a, const VaPlan &P, const jr_fields *s, const jr_stokes_opts *o, int parity)
+{
+    const int nx = P.nx, ny = P.ny, nz = P.nz;
+    a.mS5 = P.mS5[parity ? 1 : 0]; a.mC1 = P.mC1; a.mC4 = P.mC4;
+    if (P.finite_dt) { a.mD1 = P.mD1; a.mD2 = P.mD2; a.mD7 = P.mD7; }
+    else { a.mD1 = P.mC1; a.mD2 = P.mC1; a.mD7 = P.mC1; }
+    a.out = P.S[parity ? 0 : 1];
+    a.mS5b = P.mS5[parity ? 0 : 1];
+    a.out2 = P.S[parity ? 1 : 0];
+    a.niter = 1;
+    a.gbar = nullptr; a.gbar_base = 0;
+    a.dbg_nobc = getenv("JRB200_VA_DBG_NOBC") ? 1 : 0;
+    a.dbg_nobar = getenv("JRB200_VA_DBG_NOBAR") ? 1 : 0;
+    a.divV = F(divV); a.RP = F(RP); a.exx = F(exx); a.eyy = F(eyy); a.ezz = F(ezz); a.eyz = F(eyz); a.exz = F(exz); a.exy = F(exy);
+    a.Rx = F(Rx); a.Ry = F(Ry); a.Rz = F(Rz); a.Ux = F(Ux); a.Uy = F(Uy); a.Uz = F(Uz);
+    a.nx = nx; a.ny = ny; a.nz = nz; a.PX = P.PX; a.PY = P.PY;
+    a.kchunk = (nz + P.nchunk - 1) / P.nchunk;
+    a.pol_ld = P.pol_ld; a.pol_st = P.pol_st;
+    a.fxc = P.fc[0]; a.fyc = P.fc[1]; a.fzc = P.fc[2];
+    a._dx = o->_di[0]; a._dy = o->_di[1]; a._dz = o->_di[2]; a.dt = o->dt; a.r = o->r; a.theta_dtau = o->theta_dtau;
+    a.eta_dtau = o->eta_dtau;
+    // flags: left,right,front,back,top,bot.  no_slip: bot → z lo, top → z hi; free_slip (Q2): top → z lo, bot → z hi
+    const int32_t *fs = o->free_slip, *ns = o->no_slip;
+    const int fsl[6] = {fs[0], fs[1], fs[2], fs[3], fs[4], fs[5]};
+    const int nsl[6] = {ns[0], ns[1], ns[2], ns[3], ns[5], ns[4]};
+    for (int q = 0; q < 6; q++) {
+        a.bc_nsn[q] = nsl[q] ? 1 : 0;
+        a.bc_sg[q] = fsl[q] ? 1.0 : -1.0;
+    }
+}
+
+// can the kernel apply flow_bcs! itself?  every side needs a free-slip or no-slip flag (tangential ghosts are then
+// images of interior values); single rank only (the halo exchange sits between iterations)
+static bool multi_supported(const jr_context *ctx, const jr_stokes_opts *o)
+{
+    if (ctx->comm) return false;
+    // opt-in (JRB200_VA_MULTI=1).  Measured on the pool's B200s (profiles/r01_va_multi_experiment.md): the kernel runs at the
+    // 1000 W board power cap, so the launch gaps this removes are not on the critical path (the SM clock recovers in
+    // them), and the in-kernel boundary code costs the lock-stepped grid more than the separate 16 µs BC kernel.
+    const char *e = getenv("JRB200_VA_MULTI");
+    if (!e || atoi(e) == 0) return false;
+    const int32_t *fs = o->free_slip, *ns = o->no_slip;
+    const int fsl[6] = {fs[0], fs[1], fs[2], fs[3], fs[4], fs[5]};
+    const int nsl[6] = {ns[0], ns[1], ns[2], ns[3], ns[5], ns[4]};
+    for (int q = 0; q < 6; q++)
+        if (!fsl[q] && !nsl[q]) return false;
+    return true;
+}
+
+// how many iterations one launch may run (0: not supported here, use jr_stokes3d_VA_fused_iter)
+int jr_stokes3d_VA_fused_multi_max(jr_context *ctx, const jr_stokes_opts *o)
+{
+    if (!multi_supported(ctx, o)) return 0;
+    int cap = 256;
+    if (const char *e = getenv("JRB200_VA_MULTI_MAX")) cap = atoi(e);
+    return cap < 1 ? 0 : cap;
+}
+
+// `niter` iterations without diagnostics in ONE launch, starting from set `parity` (0: S0 holds the state)
+int jr_stokes3d_VA_fused_multi(jr_context *ctx, const jr_fields *s, const jr_stokes_opts *o, int niter, int parity)
+{
+    auto it = g_plans.find(ctx);
+    JR_REQUIRE(it != g_plans.end() && it->second.S[0], JR_ERR_ARG, "fused iteration without jr_stokes3d_VA_fused_begin");
+    JR_REQUIRE(niter >= 1 && multi_supported(ctx, o), JR_ERR_ARG, "multi-iteration launch not supported for this setup");
+    VaPlan &P = it->second;
+    VaArgs a;
+    fill_args(a, P, s, o, parity);
+    a.niter = niter;
+    int st = P.rhog_const ? launch_va_multi_t<false>(ctx, P, a) : launch_va_multi_t<true>(ctx, P, a);
+    if (st) return st;
+    ctx->launches += 1;
+    JR_CHECK_LAUNCH();
+    return JR_OK;
+}
 
 // `parity` 0: set S0 → S1, 1: S1 → S0.
 int jr_stokes3d_VA_fused_iter(jr_context *ctx, const jr_fields *s, const jr_stokes_opts *o, int diag, int parity)
@@ -812,18 +992,7 @@ int jr_stokes3d_VA_fused_iter(jr_context *ctx, const jr_fields *s, const jr_stok
     double *in = P.S[parity ? 1 : 0], *out = P.S[parity ? 0 : 1];
 
     VaArgs a;
-    a.mS5 = P.mS5[parity ? 1 : 0]; a.mC1 = P.mC1; a.mC4 = P.mC4;
-    if (P.finite_dt) { a.mD1 = P.mD1; a.mD2 = P.mD2; a.mD7 = P.mD7; }
-    else { a.mD1 = P.mC1; a.mD2 = P.mC1; a.mD7 = P.mC1; }
-    a.out = out;
-    a.divV = F(divV); a.RP = F(RP); a.exx = F(exx); a.eyy = F(eyy); a.ezz = F(ezz); a.eyz = F(eyz); a.exz = F(exz); a.exy = F(exy);
-    a.Rx = F(Rx); a.Ry = F(Ry); a.Rz = F(Rz); a.Ux = F(Ux); a.Uy = F(Uy); a.Uz = F(Uz);
-    a.nx = nx; a.ny = ny; a.nz = nz; a.PX = P.PX; a.PY = P.PY;
-    a.kchunk = (nz + P.nchunk - 1) / P.nchunk;
-    a.pol_ld = P.pol_ld; a.pol_st = P.pol_st;
-    a.fxc = P.fc[0]; a.fyc = P.fc[1]; a.fzc = P.fc[2];
-    a._dx = o->_di[0]; a._dy = o->_di[1]; a._dz = o->_di[2]; a.dt = o->dt; a.r = o->r; a.theta_dtau = o->theta_dtau;
-    a.eta_dtau = o->eta_dtau;
+    fill_args(a, P, s, o, parity);
     int st = launch_va(ctx, P, a, diag);
     if (st) return st;
 

@@ -36,6 +36,7 @@ def _run_both(oracle, s, niter, flags, unfused):
     finally:
         jst.set_flags(0)
     assert r.kernel_launches > 0
+    st.last_result = r
     return st, d
 
 
@@ -88,6 +89,50 @@ def test_mixed_boundary_flags(oracle, unfused):
     flags = dict(free_slip=[1, 0, 1, 0, 0, 1], no_slip=[0, 1, 0, 0, 1, 0], periodic=[0] * 6)
     st, d = _run_both(oracle, s, 3, flags, unfused)
     compare_slots(st.slots(), d, FIELDS_STATE + FIELDS_DIAG, TOL, "mixed BC")
+
+
+ALL_FLAGGED = {
+    "free_slip": dict(free_slip=[1] * 6, no_slip=[0] * 6, periodic=[0] * 6),
+    "no_slip": dict(free_slip=[0] * 6, no_slip=[1] * 6, periodic=[0] * 6),
+    # every side carries exactly one flag (both on one side is rejected by check_flow_bcs, types.jl:167-186)
+    # (quirk Q2 maps free_slip top/bot → z lo/hi but no_slip bot/top → z lo/hi: z needs the same kind on both sides)
+    "mixed": dict(free_slip=[1, 0, 0, 1, 1, 1], no_slip=[0, 1, 1, 0, 0, 0], periodic=[0] * 6),
+    "mixed_z": dict(free_slip=[0, 1, 1, 0, 0, 0], no_slip=[1, 0, 0, 1, 1, 1], periodic=[0] * 6),
+}
+
+
+@pytest.mark.parametrize("bc", list(ALL_FLAGGED))
+@pytest.mark.parametrize("BY,nchunk", [(8, 2), (10, 1), (16, 3)])
+@pytest.mark.parametrize("dt,finite_K", [(0.7, True), (np.inf, False)])
+def test_multi_iteration_launch(oracle, monkeypatch, bc, BY, nchunk, dt, finite_K):
+    """opt-in (JRB200_VA_MULTI=1): several PT iterations per launch with flow_bcs! applied inside the kernel (grid barrier
+    between iterations): same result as the oracle, fewer launches than one kernel + one BC kernel per iteration"""
+    from justrelax_jl_b200 import setups
+
+    monkeypatch.setenv("JRB200_VA_BY", str(BY))
+    monkeypatch.setenv("JRB200_VA_NCHUNK", str(nchunk))
+    ni = (64, 33, 29)
+    s = setups.random_stokes3d(ni, seed=4242, dt=dt, finite_K=finite_K)
+    flags = ALL_FLAGGED[bc]
+    launches = {}
+    for multi in ("1", "0"):
+        monkeypatch.setenv("JRB200_VA_MULTI", multi)
+        for niter in (3, 8):
+            st, d = _run_both(oracle, s, niter, flags, False)
+            compare_slots(st.slots(), d, FIELDS_STATE + FIELDS_DIAG, TOL, f"multi={multi} bc={bc} BY={BY} nchunk={nchunk} niter={niter}")
+        launches[multi] = st.last_result.kernel_launches
+    assert launches["1"] == launches["0"] - 2 * 7 + 1, launches
+
+
+def test_multi_iteration_capped_batches(oracle, monkeypatch):
+    """a cap on the iterations per launch splits the run into several multi-iteration launches (odd and even parity)"""
+    from justrelax_jl_b200 import setups
+
+    monkeypatch.setenv("JRB200_VA_MULTI", "1")
+    monkeypatch.setenv("JRB200_VA_MULTI_MAX", "3")
+    s = setups.random_stokes3d((35, 31, 17), seed=7, const_rhog=(0.0, 0.0, -1.0))
+    st, d = _run_both(oracle, s, 12, ALL_FLAGGED["mixed"], False)
+    compare_slots(st.slots(), d, FIELDS_STATE + FIELDS_DIAG, TOL, "capped multi")
 
 
 @pytest.mark.parametrize("unfused", [True, False], ids=["unfused", "fused"])
