@@ -36,6 +36,13 @@ A_EFF_BYTES_PER_CELL = 192  # (2*D_u + D_k)*8 with D_u=10 (V×3,P,τ×6), D_k=4 
 A_EFF_CONST_RHOG = 168      # the same with D_k=1: the library does not stream spatially constant ρg (SolVi: ρg ≡ 0)
 
 
+# DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) of ONE launch of the dominant kernel from the committed `ncu --set full`
+# capture of this same workload (profiles/r01_va_tma_ncu_full.txt: k_va_tma<10,0,0,3,0> at 255^3, constant body force: 1.674083 GB
+# read + 1.293379 GB written).  bench.py cannot run ncu itself (a number taken under a profiler is never a bench value), so the
+# figure is quoted for the configuration it was captured on and null for anything else.
+NCU_TRAFFIC_BYTES = {(255, True): 2_967_462_000}
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -299,7 +306,8 @@ def run_ours(args):
                           "T_eff_frac_of_8TBs": achieved_streamed / 8000.0,
                           "note": "same run with JRB200_VA_STREAM_RHOG=1: the three (zero) body-force arrays are read every iteration"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_kind": peak_kind, "kernel": "k_va_tma (TMA-staged fused 3D-VA iteration)",
+                     "traffic": NCU_TRAFFIC_BYTES.get((n, bool(info["rhog_const"]))),
+                     "traffic_source": "profiles/r01_va_tma_ncu_full.txt (ncu --set full, one launch)", "peak_kind": peak_kind, "kernel": "k_va_tma (TMA-staged fused 3D-VA iteration)",
                      "algorithmic_bytes_per_launch": a_eff * cells},
         "e2e": {"value": e2e_ips, "unit": "iters/s", "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": d2h / args.steps,
                 "note": f"one solve of {args.steps} PT iterations incl. upload of 12 input arrays and download of V,P,τ"},

@@ -17,6 +17,7 @@
 // q×3,T,Told,H,Hs,ρCp,dτ_ρ + writes T = 10 passes → 152 B/cell against A_eff = (2·4 + 7)·8 = 120 B/cell.
 #include "common.cuh"
 #include "comm.cuh"
+#include "tma.cuh"
 
 struct ThDims {
     int nd, nx, ny, nz, gx, gy, gz;
@@ -209,10 +210,15 @@ __device__ __forceinline__ void th_kface_dim(const ThArgs &a, int i, int j, int 
     int L[3] = {i, j, k}, R[3] = {i, j, k};
     L[DIM] = jr_clamp(I[DIM] - 1, 0, nc3[DIM] - 1);
     R[DIM] = jr_clamp(I[DIM], 0, nc3[DIM] - 1);
-    const double *phf = DIM == 0 ? a.f.phase_x : DIM == 1 ? a.f.phase_y : a.f.phase_z;
+    const size_t qi = ((size_t)k * e[1] + j) * e[0] + i;
+    if (a.form == 0) {  // array form: K at the two (clamped) cells
+        a.Kf[DIM][qi] = (a.f.K[th_ci(d, L[0], L[1], L[2])] + a.f.K[th_ci(d, R[0], R[1], R[2])]) * 0.5;
+        return;
+    }
+    const double *phf = !a.f.phase_c ? nullptr : DIM == 0 ? a.f.phase_x : DIM == 1 ? a.f.phase_y : a.f.phase_z;
     const size_t ps = (size_t)e[0] * e[1] * e[2];
     const size_t pL = ((size_t)L[2] * e[1] + L[1]) * e[0] + L[0], pR = ((size_t)R[2] * e[1] + R[1]) * e[0] + R[0];
-    a.Kf[DIM][((size_t)k * e[1] + j) * e[0] + i] = (th_K(a.tab, phf, ps, pL) + th_K(a.tab, phf, ps, pR)) * 0.5;
+    a.Kf[DIM][qi] = (th_K(a.tab, phf, ps, pL) + th_K(a.tab, phf, ps, pR)) * 0.5;
 }
 __global__ void __launch_bounds__(256) k_th_kface(const __grid_constant__ ThArgs a)
 {
@@ -302,6 +308,158 @@ __global__ void __launch_bounds__(256) k_th_update(const __grid_constant__ ThArg
         __shared__ double sm[32];
         const double s = jr_block_sum(r2, sm);
         if (threadIdx.x == 0 && threadIdx.y == 0) a.res_part[(size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = s;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Fused compute_flux! + update_T! (+ update_pt_thermal_arrays! of the next iteration) for 3D, one launch per PT iteration.
+// Jacobi-exact = the two-kernel sequence: every flux is formed from T_in, θ_in, q_in (ping-pong sets A ↔ B, so no thread reads what
+// another one writes in this launch) with the expressions of th_flux_dim, every temperature from the new fluxes with the
+// expressions of k_th_update — operation for operation, so the results are bit-identical to k_th_flux → k_th_update.
+// A thread owns the column (i, j) of a z-chunk and marches in z: T, θ of the planes k−1, k, k+1 and the z-flux of the lower face
+// roll through registers; the four lateral fluxes of a cell are formed by the cell itself (the x-high / y-high ones redundantly
+// with the neighbour: 5 instead of 3 flux evaluations per cell, no shared memory, no barrier).  Index arithmetic is
+// incremental (one pointer bump per array and plane).
+// HBM traffic per cell (rheology form, N phases): reads T, K̄×3, θ, q×3, Told, dτ_ρ, H, H_s, A, P, ratios×N; writes q×3, T, θ, dτ_ρ
+// = 19 + N passes against 24 + N of the two-kernel path (q is not re-read, T and θ are read once).
+// phase-weighted evaluations from a register copy of the ratios with a COMPILE-TIME phase bound NP (same operation order as
+// th_rhoCp_r / th_K_r / th_Hr_r: phases in table order, a ratio equal to one returns that phase alone)
+template <int NP> struct ThRatiosN { double r[NP]; };
+template <int NP>
+__device__ __forceinline__ double th_rhoCp_n(const ThTable &t, const ThRatiosN<NP> &R, double T, double P)
+{
+    double x = 0.0, out = 0.0;
+    bool done = false;
+#pragma unroll
+    for (int q = 0; q < NP; q++)
+        if (q < t.nphase && !done) {
+            const double v = t.p[q].Cp * th_density(t.p[q], T, P);
+            if (R.r[q] == 1.0) { out = v * R.r[q]; done = true; }
+            else x += (R.r[q] == 0.0) ? 0.0 : v * R.r[q];
+        }
+    return done ? out : x;
+}
+template <int NP>
+__device__ __forceinline__ double th_K_n(const ThTable &t, const ThRatiosN<NP> &R)
+{
+    double x = 0.0, out = 0.0;
+    bool done = false;
+#pragma unroll
+    for (int q = 0; q < NP; q++)
+        if (q < t.nphase && !done) {
+            if (R.r[q] == 1.0) { out = t.p[q].k * R.r[q]; done = true; }
+            else x += (R.r[q] == 0.0) ? 0.0 : t.p[q].k * R.r[q];
+        }
+    return done ? out : x;
+}
+template <int NP>
+__device__ __forceinline__ double th_Hr_n(const ThTable &t, const ThRatiosN<NP> &R)
+{
+    double x = 0.0;
+#pragma unroll
+    for (int q = 0; q < NP; q++)
+        if (q < t.nphase) x += (R.r[q] == 0.0) ? 0.0 : t.p[q].Hr * R.r[q];
+    return x;
+}
+struct ThPP {
+    const double *T_in, *th_in, *q_in[3];
+    double *T_out, *th_out, *q_out[3];
+    int kchunk;
+};
+// the flux expression of th_flux_dim (compute_flux!, DiffusionPT_kernels.jl:6-158)
+__device__ __forceinline__ double th_flux_pt(double q_old, double K, double Tl, double Th, double thL, double thR, double _d)
+{
+    const double th_ = (thL + thR) * 0.5;
+    const double qx = -K * (Th - Tl) * _d;
+    return jr_div_nr(q_old * th_ + qx, 1.0 + th_);  // IEEE-exact quotient (denominator ≥ 1), no slow-path call
+}
+template <int FORM, int NP>  // NP = 0: no phase ratios; else compile-time bound on the number of phases
+__global__ void __launch_bounds__(256, 2) k_th_fused3(const __grid_constant__ ThArgs a, const __grid_constant__ ThPP pp)
+{
+    const ThDims &d = a.d;
+    const int nx = d.nx, ny = d.ny, nz = d.nz;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= nx || j >= ny) return;
+    const int k0 = blockIdx.z * pp.kchunk, k1 = min(k0 + pp.kchunk, nz);
+    if (k0 >= k1) return;
+    const size_t nc = (size_t)nx * ny * nz;
+    const size_t sT = (size_t)d.gx * d.gy, sC = (size_t)nx * ny, sX = (size_t)(nx + 1) * ny, sY = (size_t)nx * (ny + 1);
+    // clamped lateral neighbours of the cell (θ is indexed with clamped CENTRE indices)
+    const int oxm = i > 0 ? -1 : 0, oxp = i < nx - 1 ? 1 : 0, oym = j > 0 ? -nx : 0, oyp = j < ny - 1 ? nx : 0;
+    const double _dx = a._di[0], _dy = a._di[1], _dz = a._di[2], _dt = a._dt;
+    // running indices of plane k
+    size_t t = th_ti(d, i + 1, j + 1, k0 + 1), c = th_ci(d, i, j, k0);
+    size_t fx = ((size_t)k0 * ny + j) * (nx + 1) + i, fy = ((size_t)k0 * (ny + 1) + j) * nx + i;  // x-low / y-low face of the cell
+    const double *__restrict__ T = pp.T_in, *__restrict__ TH = pp.th_in;
+    const double *__restrict__ qxi = pp.q_in[0], *__restrict__ qyi = pp.q_in[1], *__restrict__ qzi = pp.q_in[2];
+    const double *__restrict__ Kx = a.Kf[0], *__restrict__ Ky = a.Kf[1], *__restrict__ Kz = a.Kf[2];
+    // z carry: T(k−1), T(k); θ at the clamped cells k−1, k; the new flux through the lower z-face k
+    double Tm = __ldg(T + t - sT), Tc = __ldg(T + t);
+    double thc = __ldg(TH + c), thm = k0 > 0 ? __ldg(TH + c - sC) : thc;
+    double qz_lo = th_flux_pt(__ldg(qzi + c), __ldg(Kz + c), Tm, Tc, thm, thc, _dz);  // z-face k has the index of cell k
+    const double L_V = a.L / a.Vpdtau, VL = a.Vpdtau * a.L;
+    constexpr bool HASR = NP > 0;
+    constexpr int NR = NP > 0 ? NP : 1;
+    for (int k = k0; k < k1; ++k) {
+        // ---- loads of this plane (independent: issued back to back) ----
+        const double Tp = __ldg(T + t + sT);
+        const double thp = k < nz - 1 ? __ldg(TH + c + sC) : thc;
+        const double Txm = __ldg(T + t - 1), Txp = __ldg(T + t + 1), Tym = __ldg(T + t - d.gx), Typ = __ldg(T + t + d.gx);
+        const double thxm = __ldg(TH + c + oxm), thxp = __ldg(TH + c + oxp), thym = __ldg(TH + c + oym), thyp = __ldg(TH + c + oyp);
+        const double qxl_o = __ldg(qxi + fx), qxh_o = __ldg(qxi + fx + 1), qyl_o = __ldg(qyi + fy), qyh_o = __ldg(qyi + fy + nx);
+        const double qzh_o = __ldg(qzi + c + sC);
+        const double Kxl = __ldg(Kx + fx), Kxh = __ldg(Kx + fx + 1), Kyl = __ldg(Ky + fy), Kyh = __ldg(Ky + fy + nx), Kzh = __ldg(Kz + c + sC);
+        const double Told = __ldg(a.f.Told + t), dtr = a.f.dtau_rho[c], Hc = __ldg(a.f.H + c), Hs = __ldg(a.f.shear_heating + c);
+        double rhoCp_a = 0.0, adi = 0.0, P = 0.0;
+        ThRatiosN<NR> R;
+        if (FORM == 0) rhoCp_a = __ldg(a.f.rhoCp + c);
+        else {
+            adi = __ldg(a.f.adiabatic + c);
+            P = a.f.P ? __ldg(a.f.P + c) : 0.0;
+            if (HASR) {
+#pragma unroll
+                for (int q = 0; q < NR; q++) R.r[q] = q < a.tab.nphase ? __ldg(a.f.phase_c + (size_t)q * nc + c) : 0.0;
+            }
+        }
+        // every load of this plane is in flight before the first use (the compiler otherwise sinks them into dependent batches)
+        asm volatile("" ::: "memory");
+        // ---- fluxes (x-low, x-high, y-low, y-high, z-high) ----
+        const double qx_lo = th_flux_pt(qxl_o, Kxl, Txm, Tc, thxm, thc, _dx);
+        const double qx_hi = th_flux_pt(qxh_o, Kxh, Tc, Txp, thc, thxp, _dx);
+        const double qy_lo = th_flux_pt(qyl_o, Kyl, Tym, Tc, thym, thc, _dy);
+        const double qy_hi = th_flux_pt(qyh_o, Kyh, Tc, Typ, thc, thyp, _dy);
+        const double qz_hi = th_flux_pt(qzh_o, Kzh, Tc, Tp, thc, thp, _dz);
+        pp.q_out[0][fx] = qx_lo;
+        if (i == nx - 1) pp.q_out[0][fx + 1] = qx_hi;
+        pp.q_out[1][fy] = qy_lo;
+        if (j == ny - 1) pp.q_out[1][fy + nx] = qy_hi;
+        pp.q_out[2][c] = qz_lo;
+        if (k == nz - 1) pp.q_out[2][c + sC] = qz_hi;
+        // ---- update_T!  (th_div: ((∂x qx) + (∂y qy)) + (∂z qz)) ----
+        double div = (qx_hi - qx_lo) * _dx + (qy_hi - qy_lo) * _dy;
+        div = div + (qz_hi - qz_lo) * _dz;
+        double Tn;
+        if (FORM == 0) {
+            const double rhoCp = rhoCp_a;
+            Tn = jr_div_nr(dtr * (-(div) + Told * rhoCp * _dt + Hc + Hs) + Tc, 1.0 + dtr * rhoCp * _dt);
+        } else {
+            double rhoCp, Hr;
+            if (HASR) { rhoCp = th_rhoCp_n<NR>(a.tab, R, Tc, P); Hr = th_Hr_n<NR>(a.tab, R); }
+            else { rhoCp = th_rhoCp(a.tab, nullptr, nc, c, Tc, P); Hr = th_Hr(a.tab, nullptr, nc, c); }
+            Tn = jr_div_nr(dtr * (-(div) + Told * rhoCp * _dt + Hr + Hc + Hs + adi * Tc) + Tc, 1.0 + dtr * rhoCp * _dt);
+            if (HASR) {
+                // update_pt_thermal_arrays! of the next iteration from the new interior T (as k_th_update with next_pt)
+                const double rc = th_rhoCp_n<NR>(a.tab, R, Tn, P);
+                const double _K = jr_inv_nr(th_K_n<NR>(a.tab, R));
+                const double _Re = jr_inv_nr(TH_PI + sqrt(TH_PI * TH_PI + rc * (a.L * a.L) * _K * _dt));
+                pp.th_out[c] = L_V * _Re;
+                a.f.dtau_rho[c] = VL * _K * _Re;
+            }
+        }
+        pp.T_out[t] = Tn;
+        // ---- roll ----
+        Tm = Tc; Tc = Tp; thm = thc; thc = thp; qz_lo = qz_hi;
+        t += sT; c += sC; fx += sX; fy += sY;
     }
 }
 
@@ -445,18 +603,19 @@ static int th_launch_bc(jr_context *ctx, double *T, const ThDims &d, const jr_th
     return JR_OK;
 }
 
-static int th_halo(jr_context *ctx, const ThArgs &a)
+static int th_halo_of(jr_context *ctx, const ThArgs &a, double *T)
 {
     if (!ctx->comm) return JR_OK;
     const int32_t ext[3] = {a.d.gx, a.d.gy, a.d.gz}, nc[3] = {a.d.nx, a.d.ny, a.d.nz};
-    const jr_harr H = jr_harr_dense(a.f.T, ext, nc);
+    const jr_harr H = jr_harr_dense(T, ext, nc);
     return jr_comm_halo(ctx, &H, 1);  // update_halo!(thermal.T)  DiffusionPT_solver.jl:110,261
 }
+static int th_halo(jr_context *ctx, const ThArgs &a) { return th_halo_of(ctx, a, a.f.T); }
 
 // rheology form with phase ratios: face conductivities once per call (scratch owned by the context)
-static int th_prepare_kface(jr_context *ctx, ThArgs &a)
+static int th_prepare_kface(jr_context *ctx, ThArgs &a, bool all_forms = false)
 {
-    if (!(a.form == 1 && a.f.phase_c)) return JR_OK;
+    if (!(a.form == 1 && a.f.phase_c) && !all_forms) return JR_OK;
     const ThDims &d = a.d;
     const size_t nfx = (size_t)(d.nx + 1) * d.ny * d.nz, nfy = (size_t)d.nx * (d.ny + 1) * d.nz, nfz = d.nd == 3 ? (size_t)d.nx * d.ny * (d.nz + 1) : 0;
     void *buf = nullptr;
@@ -509,6 +668,71 @@ static int th_iter(jr_context *ctx, ThArgs &a, const jr_thermal_opts *o, bool sa
     return JR_OK;
 }
 
+// ---- fused path (3D): set A = the caller's T, θr_dτ, qT arrays, set B = scratch owned by the context; iterations run in PAIRS
+// (A → B, B → A) so the state is back in the caller's arrays whenever anything else (sampled iteration, exit) looks at it.
+struct ThFused {
+    bool ok = false, pt_dyn = false;
+    double *Tb = nullptr, *thb = nullptr, *qb[3] = {nullptr, nullptr, nullptr};
+    int kchunk = 32;
+};
+static int th_fused_prepare(jr_context *ctx, ThArgs &a, ThFused &F)
+{
+    const ThDims &d = a.d;
+    F.ok = d.nd == 3 && !a.f.dir_mask;
+    for (int q = 0; q < 3; q++) F.ok = F.ok && !a.cf_lo[q] && !a.cf_hi[q];
+    if (const char *e = getenv("JRB200_TH_FUSED")) F.ok = F.ok && atoi(e) != 0;
+    if (!F.ok) return th_prepare_kface(ctx, a);
+    F.pt_dyn = a.form == 1 && a.f.phase_c;
+    if (const char *e = getenv("JRB200_TH_KCHUNK")) F.kchunk = atoi(e) > 0 ? atoi(e) : F.kchunk;
+    const size_t nc = (size_t)d.nx * d.ny * d.nz, ng = (size_t)d.gx * d.gy * d.gz;
+    const size_t nfx = (size_t)(d.nx + 1) * d.ny * d.nz, nfy = (size_t)d.nx * (d.ny + 1) * d.nz, nfz = (size_t)d.nx * d.ny * (d.nz + 1);
+    void *p = nullptr;
+    int st;
+    if ((st = jr_ctx_scratch(ctx, "th_fused_T", ng * sizeof(double), &p))) return st;
+    F.Tb = (double *)p;
+    if ((st = jr_ctx_scratch(ctx, "th_fused_q", (nfx + nfy + nfz) * sizeof(double), &p))) return st;
+    F.qb[0] = (double *)p; F.qb[1] = F.qb[0] + nfx; F.qb[2] = F.qb[1] + nfy;
+    if (F.pt_dyn) {
+        if ((st = jr_ctx_scratch(ctx, "th_fused_th", nc * sizeof(double), &p))) return st;
+        F.thb = (double *)p;
+    }
+    // ghost elements no boundary condition touches keep their value in the reference: seed set B with them
+    JR_CUDA(cudaMemcpyAsync(F.Tb, a.f.T, ng * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    return th_prepare_kface(ctx, a, true);
+}
+static int th_fused_launch(jr_context *ctx, const ThArgs &a, const ThFused &F, bool a_to_b)
+{
+    const ThDims &d = a.d;
+    ThPP pp;
+    double *qA[3] = {a.f.qTx, a.f.qTy, a.f.qTz};
+    pp.T_in = a_to_b ? a.f.T : F.Tb; pp.T_out = a_to_b ? F.Tb : a.f.T;
+    for (int q = 0; q < 3; q++) { pp.q_in[q] = a_to_b ? qA[q] : F.qb[q]; pp.q_out[q] = a_to_b ? F.qb[q] : qA[q]; }
+    if (F.pt_dyn) { pp.th_in = a_to_b ? a.f.theta_r_dtau : F.thb; pp.th_out = a_to_b ? F.thb : a.f.theta_r_dtau; }
+    else { pp.th_in = a.f.theta_r_dtau; pp.th_out = a.f.theta_r_dtau; }
+    pp.kchunk = F.kchunk;
+    dim3 blk(32, 8, 1), grid((d.nx + 31) / 32, (d.ny + 7) / 8, (d.nz + F.kchunk - 1) / F.kchunk);
+    if (a.form == 0) k_th_fused3<0, 0><<<grid, blk, 0, ctx->stream>>>(a, pp);
+    else if (!F.pt_dyn) k_th_fused3<1, 0><<<grid, blk, 0, ctx->stream>>>(a, pp);
+    else if (a.tab.nphase <= 2) k_th_fused3<1, 2><<<grid, blk, 0, ctx->stream>>>(a, pp);
+    else if (a.tab.nphase <= 3) k_th_fused3<1, 3><<<grid, blk, 0, ctx->stream>>>(a, pp);
+    else if (a.tab.nphase <= 4) k_th_fused3<1, 4><<<grid, blk, 0, ctx->stream>>>(a, pp);
+    else k_th_fused3<1, TH_MAX_PHASES><<<grid, blk, 0, ctx->stream>>>(a, pp);
+    ctx->launches++;
+    JR_CHECK_LAUNCH();
+    return JR_OK;
+}
+// two PT iterations whose residual nobody samples: A → B, thermal_bcs!(B), halo(B), B → A, thermal_bcs!(A), halo(A)
+static int th_fused_pair(jr_context *ctx, const ThArgs &a, const jr_thermal_opts *o, const ThFused &F)
+{
+    int st;
+    if ((st = th_fused_launch(ctx, a, F, true))) return st;
+    if ((st = th_launch_bc(ctx, F.Tb, a.d, o))) return st;
+    if ((st = th_halo_of(ctx, a, F.Tb))) return st;
+    if ((st = th_fused_launch(ctx, a, F, false))) return st;
+    if ((st = th_launch_bc(ctx, a.f.T, a.d, o))) return st;
+    return th_halo_of(ctx, a, a.f.T);
+}
+
 extern "C" {
 
 int jr_thermal_bcs(jr_context *ctx, double *T, int32_t ndim, const int32_t n[3], const jr_thermal_opts *o)
@@ -552,9 +776,18 @@ int jr_thermal_iterate(jr_context *ctx, const jr_thermal_fields *f, const jr_the
     if ((st = jr_ctx_scratch(ctx, "th_sum", 16 * sizeof(double), &slot))) return st;
     ctx->launches = 0;
     JR_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
-    if ((st = th_prepare_kface(ctx, a))) return st;
-    for (int64_t it = 0; it < niter; it++)
+    ThFused F;
+    if ((st = th_fused_prepare(ctx, a, F))) return st;
+    for (int64_t it = 0; it < niter;) {
+        // pairs of iterations that are neither the first (PT coefficients still to be formed) nor the last (sampled)
+        if (F.ok && (it > 0 || !F.pt_dyn) && it + 2 <= niter - 1) {
+            if ((st = th_fused_pair(ctx, a, o, F))) return st;
+            it += 2;
+            continue;
+        }
         if ((st = th_iter(ctx, a, o, it == niter - 1, (double *)slot, it > 0, it < niter - 1))) return st;
+        it++;
+    }
     JR_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
     JR_CUDA(cudaMemcpyAsync(ctx->h_pinned, slot, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     JR_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -589,11 +822,19 @@ int jr_heatdiffusion_PT(jr_context *ctx, const jr_thermal_fields *f, const jr_th
         k_th_adiabatic<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(a, stokes_P, stokes_P0, nc);
         ctx->launches++;
     }
-    if ((st = th_prepare_kface(ctx, a))) return st;
+    ThFused F;
+    if ((st = th_fused_prepare(ctx, a, F))) return st;
     int64_t iter = 0, cont = 0;
     double err = 2 * o->eps;
     bool have_pt = false;
     while (err > o->eps && iter < o->iterMax) {
+        // two iterations in a row that are not sampled and not the last the loop can run (the condition cannot change in
+        // between: err is only updated at samples): the fused kernel, set A → B → A
+        if (F.ok && (have_pt || !F.pt_dyn) && (iter + 1) % o->nout != 0 && (iter + 2) % o->nout != 0 && iter + 2 < o->iterMax) {
+            if ((st = th_fused_pair(ctx, a, o, F))) return st;
+            iter += 2;
+            continue;
+        }
         const bool sample = (iter + 1) % o->nout == 0;
         const bool write_next = !(sample || iter + 1 >= o->iterMax);
         if ((st = th_iter(ctx, a, o, sample, (double *)slot, have_pt, write_next))) return st;

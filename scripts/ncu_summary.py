@@ -31,8 +31,17 @@ def main(path):
             if k in d:
                 print(f"   {k:75s} {d[k][1]:>16s} {d[k][0]}")
         try:
-            rd, wr = float(d["dram__bytes_read.sum"][1]), float(d["dram__bytes_write.sum"][1])
-            print(f"   {'dram traffic (read+write)':75s} {rd + wr:16.6f} {d['dram__bytes_read.sum'][0]}")
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+            rd = float(d["dram__bytes_read.sum"][1]) * scale[d["dram__bytes_read.sum"][0]]
+            wr = float(d["dram__bytes_write.sum"][1]) * scale[d["dram__bytes_write.sum"][0]]
+            print(f"   {'dram traffic (read+write)':75s} {(rd + wr) / 1e9:16.6f} Gbyte")
+            # stall reasons from the warp-state sampler (share of all samples)
+            st = {k[len("smsp__pcsamp_warps_issue_stalled_"):]: float(v[1]) for k, v in d.items()
+                  if k.startswith("smsp__pcsamp_warps_issue_stalled_") and not k.endswith("_not_issued") and v[1] not in ("", "n/a")}
+            tot = sum(st.values())
+            if tot > 0:
+                top = sorted(st.items(), key=lambda kv: -kv[1])[:6]
+                print("   warp-state samples: " + ", ".join(f"{k} {100 * v / tot:.0f}%" for k, v in top))
         except Exception:
             pass
 

@@ -113,53 +113,76 @@ class _Phase:
     pass
 
 
-@pytest.mark.parametrize("ni", [(17, 12), (33, 40), (9, 8, 7), (34, 17, 21)])
-@pytest.mark.parametrize("form,nphase", [(0, 0), (1, 1), (1, 3)])
-def test_fixed_iterations_random_state(oracle, ni, form, nphase):
+def _run_case(oracle, ni, form, nphase, vb, bc, niter, seed_shift=0):
+    """`niter` PT iterations (the last one sampled) from a random state on the B200 and in the oracle; returns the result"""
     from justrelax_jl_b200 import thermal as jth
     from justrelax_jl_b200.types import Geometry
 
     li = tuple(1.0e5 * (1 + 0.1 * d) for d in range(len(ni)))
     grid = Geometry(ni, li)
     rows = PHASES[:max(nphase, 1)]
+    host = random_thermal(ni, 77 + ni[0] + vb + seed_shift, nphase if nphase > 1 else 0)
+    if vb == 1:  # Dirichlet mask on a block of nodes
+        m = np.zeros(tuple(n + 2 for n in ni), order="F")
+        m[(slice(2, 5),) * len(ni)] = 1.0
+        host["dir_mask"] = m
+        bc.dirichlet = (1234.5, m)
+    full = oracle.alloc_thermal(ni, host)
+    pt = type("PT", (), {})()
+    pt.ϵ, pt.max_lxyz, pt.Vpdτ = 1e-8, max(li), min(grid.di.center) * 0.5
+    dt = 1.0e11
+    o = oracle.thermal_opts(_di=grid._di.center, dt=dt, eps=1e-8, iterMax=10, nout=niter, max_lxyz=pt.max_lxyz, Vpdtau=pt.Vpdτ,
+                            form=form, phases=rows, bc=bc, dir_const=1234.5)
+    th, extra = to_device(ni, full)
+    fs = oracle.thermal_fields(full, ni)
+    for _ in range(niter):
+        oracle.lib().orc_thermal_iterate_once(C.byref(fs), C.byref(o))
+    oracle.lib().orc_thermal_check_res(C.byref(fs), C.byref(o))
+    pt.θr_dτ, pt.dτ_ρ = extra["theta_r_dtau"], extra["dtau_rho"]
+    kw = dict(verbose=False)
+    if nphase > 1:
+        ph = _Phase()
+        ph.center, ph.Vx, ph.Vy = extra["phase_c"], extra["phase_x"], extra["phase_y"]
+        ph.Vz = extra.get("phase_z")
+        kw["phase"] = ph
+    if form == 0:
+        r = jth.thermal_iterate_(th, pt, bc, extra["K"], extra["rhoCp"], dt, grid, niter, kwargs=kw)
+    else:
+        rheo = rheology_of(rows)
+        r = jth.thermal_iterate_(th, pt, bc, rheo if nphase > 1 else rheo[0], dict(P=extra["P"], T=th.T), dt, grid, niter, kwargs=kw)
+    assert r.kernel_launches > 0
+    names = ["T", "qTx", "qTy", "qTx2", "qTy2", "ResT"] + (["qTz", "qTz2"] if len(ni) == 3 else [])
+    compare(th, full, names, f"ni={ni} form={form} nphase={nphase} bc={vb} niter={niter}")
+    from justrelax_jl_b200 import to_host
+    if nphase > 1:
+        assert max_rel_diff(to_host(pt.θr_dτ), full["theta_r_dtau"]) <= TOL and max_rel_diff(to_host(pt.dτ_ρ), full["dtau_rho"]) <= TOL
+    bc.dirichlet = None
+    return r
+
+
+@pytest.mark.parametrize("ni", [(17, 12), (33, 40), (9, 8, 7), (34, 17, 21)])
+@pytest.mark.parametrize("form,nphase", [(0, 0), (1, 1), (1, 3)])
+def test_fixed_iterations_random_state(oracle, ni, form, nphase):
     for vb, bc in enumerate(bc_variants(len(ni))):
         for niter in (1, 3):
-            host = random_thermal(ni, 77 + ni[0] + vb, nphase if nphase > 1 else 0)
-            if vb == 1:  # Dirichlet mask on a block of nodes
-                m = np.zeros(tuple(n + 2 for n in ni), order="F")
-                m[(slice(2, 5),) * len(ni)] = 1.0
-                host["dir_mask"] = m
-                bc.dirichlet = (1234.5, m)
-            full = oracle.alloc_thermal(ni, host)
-            pt = type("PT", (), {})()
-            pt.ϵ, pt.max_lxyz, pt.Vpdτ = 1e-8, max(li), min(grid.di.center) * 0.5
-            dt = 1.0e11
-            o = oracle.thermal_opts(_di=grid._di.center, dt=dt, eps=1e-8, iterMax=10, nout=niter, max_lxyz=pt.max_lxyz, Vpdtau=pt.Vpdτ,
-                                    form=form, phases=rows, bc=bc, dir_const=1234.5)
-            th, extra = to_device(ni, full)
-            fs = oracle.thermal_fields(full, ni)
-            for _ in range(niter):
-                oracle.lib().orc_thermal_iterate_once(C.byref(fs), C.byref(o))
-            oracle.lib().orc_thermal_check_res(C.byref(fs), C.byref(o))
-            pt.θr_dτ, pt.dτ_ρ = extra["theta_r_dtau"], extra["dtau_rho"]
-            kw = dict(verbose=False)
-            if nphase > 1:
-                ph = _Phase()
-                ph.center, ph.Vx, ph.Vy = extra["phase_c"], extra["phase_x"], extra["phase_y"]
-                ph.Vz = extra.get("phase_z")
-                kw["phase"] = ph
-            if form == 0:
-                r = jth.thermal_iterate_(th, pt, bc, extra["K"], extra["rhoCp"], dt, grid, niter, kwargs=kw)
-            else:
-                rheo = rheology_of(rows)
-                r = jth.thermal_iterate_(th, pt, bc, rheo if nphase > 1 else rheo[0], dict(P=extra["P"], T=th.T), dt, grid, niter, kwargs=kw)
-            assert r.kernel_launches > 0
-            names = ["T", "qTx", "qTy", "qTx2", "qTy2", "ResT"] + (["qTz", "qTz2"] if len(ni) == 3 else [])
-            compare(th, full, names, f"ni={ni} form={form} nphase={nphase} bc={vb} niter={niter}")
-            from justrelax_jl_b200 import to_host
-            if nphase > 1:
-                assert max_rel_diff(to_host(pt.θr_dτ), full["theta_r_dtau"]) <= TOL and max_rel_diff(to_host(pt.dτ_ρ), full["dtau_rho"]) <= TOL
-            bc.dirichlet = None
+            _run_case(oracle, ni, form, nphase, vb, bc, niter)
+
+
+@pytest.mark.parametrize("ni", [(9, 8, 7), (34, 17, 21), (40, 70, 37)])
+@pytest.mark.parametrize("form,nphase", [(0, 0), (1, 1), (1, 3)])
+@pytest.mark.parametrize("kchunk", [32, 5])
+def test_fused_flux_update_3d(oracle, monkeypatch, ni, form, nphase, kchunk):
+    """3D, no Dirichlet mask / constant-flux face: pairs of unsampled iterations run the fused flux + update kernel on ping-pong
+    sets (z-marching, chunk seams at kchunk): same fields as the oracle, fewer launches than the two-kernel path"""
+    monkeypatch.setenv("JRB200_TH_KCHUNK", str(kchunk))
+    bc = bc_variants(3)[0]
+    launches = {}
+    for fused in ("1", "0"):
+        monkeypatch.setenv("JRB200_TH_FUSED", fused)
+        for niter in (4, 7, 8):
+            r = _run_case(oracle, ni, form, nphase, 0, bc, niter, seed_shift=niter)
+        launches[fused] = r.kernel_launches
+    assert launches["1"] < launches["0"], launches
 
 
 def test_config1_diffusion2d_golden_and_parity(oracle):
