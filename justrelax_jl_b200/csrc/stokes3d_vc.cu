@@ -34,7 +34,9 @@ struct V3 {
     double *rgx, *rgy, *rgz;
     const double *T, *Pargs, *ph_c, *ph_xy, *ph_yz, *ph_xz;
     double *divV, *RP, *pxx, *pyy, *pzz, *pyz, *pxz, *pxy, *tII, *eta_vep, *e_vol_pl, *Rx, *Ry, *Rz;
+    int pf_next;   // L2 prefetch of the next plane's operands (JRB200_VC3_PREFETCH, default on)
 };
+__device__ __forceinline__ void jr_prefetch_l2(const double *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 #define CC(A, i, j, k) (A)[IX3(nx, ny, i, j, k)]
 #define YZ(A, i, j, k) (A)[IX3(nx, ny + 1, i, j, k)]
@@ -54,6 +56,20 @@ __global__ void __launch_bounds__(256) k_vc3_prep(const __grid_constant__ V3 a, 
     const int i = blockIdx.x * blockDim.x + threadIdx.x + 1, j = blockIdx.y * blockDim.y + threadIdx.y + 1, k = blockIdx.z + 1;
     if (i > nx || j > ny || k > nz) return;
     const size_t nc = (size_t)nx * ny * nz, c = IX3(nx, ny, i, j, k);
+    if (a.pf_next && k + 2 <= nz) {
+        // L2 prefetch of this thread's operands two planes up (the CTAs of that plane start about one wave later)
+        const size_t c2 = c + 2 * (size_t)nx * ny;
+        jr_prefetch_l2(a.eta_i + c2); jr_prefetch_l2(a.theta + c2); jr_prefetch_l2(a.P0 + c2); jr_prefetch_l2(a.Q + c2);
+        jr_prefetch_l2(a.Vx + IX3(nx + 1, ny + 2, i, j + 1, k + 3)); jr_prefetch_l2(a.Vy + IX3(nx + 2, ny + 1, i + 1, j, k + 3));
+        jr_prefetch_l2(a.Vz + IX3(nx + 2, ny + 2, i + 1, j + 1, k + 3));
+#pragma unroll
+        for (int p = 0; p < NP; p++)
+            if (p < pt.n) jr_prefetch_l2(a.ph_c + (size_t)p * nc + c2);
+        if (!pt.rho_const) {
+            if (a.T) jr_prefetch_l2(a.T + IX3(nx + 2, ny + 2, i + 1, j + 1, k + 3));
+            if (a.Pargs) jr_prefetch_l2(a.Pargs + c2);
+        }
+    }
     const double eta = __ldg(a.eta_i + c);
     double ett;
     if (MAXLOC) {  // compute_maxloc!(ητ, η)  Stokes3D.jl:514 ; Utils.jl:409-461 (window clamped to the array)
@@ -507,6 +523,37 @@ __global__ void __launch_bounds__(32 * TYS, 2) k_vc3_stress_sm(const __grid_cons
     const size_t nc = (size_t)nx * ny * nz, nyz = (size_t)nx * (ny + 1) * (nz + 1), nxz = (size_t)(nx + 1) * ny * (nz + 1),
                  nxy = (size_t)(nx + 1) * (ny + 1) * nz;
     const size_t c = IX3(nx, ny, i, j, k), vyz = IX3(nx, ny + 1, i, j, k), vxz = IX3(nx + 1, ny, i, j, k), vxy = IX3(nx + 1, ny + 1, i, j, k);
+    // L2 prefetch for the CTA of the same tile on plane k + 1 (CTAs are scheduled plane by plane, one plane ≈ one wave): the one new
+    // plane of each family it will stage, and its own-position operands.  No registers held; its cp.async / loads then hit L2.
+    if (a.pf_next && k + 1 <= nz - 1) {
+        const double *src[SL_COUNT] = {a.eta_o, a.theta, a.txx_i, a.tyy_i, a.tzz_i, a.oxx, a.oyy, a.ozz, a.exx, a.eyy, a.ezz,
+                                       a.tyz_i, a.oyz, a.eyz, a.txz_i, a.oxz, a.exz, a.txy_i, a.oxy, a.exy};
+#pragma unroll
+        for (int it = 0; it < (SPLANE + 32 * TYS - 1) / (32 * TYS); it++) {
+            const int e = tid + it * 32 * TYS;
+            if (e < SPLANE) {
+                const int r = e / SROW, cc = e - r * SROW;
+                const int im = max(ib - 1 + cc, 1), jm = max(jb - 1 + r, 1), ip = ib + cc, jp = jb + r;
+                const size_t oc = IX3(nx, ny, im, jm, k + 1), oy = IX3(nx, ny + 1, im, jp, k + 2), oz = IX3(nx + 1, ny, ip, jm, k + 2),
+                             ox = IX3(nx + 1, ny + 1, ip, jp, k + 1);
+#pragma unroll
+                for (int s = 0; s < SL_COUNT; s++) {
+                    const size_t o = s < SL_tyz ? oc : (s < SL_txz ? oy : (s < SL_txy ? oz : ox));
+                    jr_prefetch_l2(src[s] + o);
+                }
+            }
+        }
+        const size_t sc = (size_t)nx * ny, syz = (size_t)nx * (ny + 1), sxz = (size_t)(nx + 1) * ny, sxy = (size_t)(nx + 1) * (ny + 1);
+#pragma unroll
+        for (int p = 0; p < NP; p++)
+            if (p < pt.n) {
+                jr_prefetch_l2(a.ph_yz + (size_t)p * nyz + vyz + syz); jr_prefetch_l2(a.ph_xz + (size_t)p * nxz + vxz + sxz);
+                jr_prefetch_l2(a.ph_xy + (size_t)p * nxy + vxy + sxy); jr_prefetch_l2(a.ph_c + (size_t)p * nc + c + sc);
+            }
+        jr_prefetch_l2(a.tyzc + c + sc); jr_prefetch_l2(a.txzc + c + sc); jr_prefetch_l2(a.txyc + c + sc);
+        jr_prefetch_l2(a.oyzc + c + sc); jr_prefetch_l2(a.oxzc + c + sc); jr_prefetch_l2(a.oxyc + c + sc);
+        jr_prefetch_l2(a.lam + c + sc); jr_prefetch_l2(a.lamyz + vyz + syz); jr_prefetch_l2(a.lamxz + vxz + sxz); jr_prefetch_l2(a.lamxy + vxy + sxy);
+    }
     double ryz[NP], rxz[NP], rxy[NP];
     ratios_load<NP>(pt, a.ph_yz, nyz, vyz, ryz);
     ratios_load<NP>(pt, a.ph_xz, nxz, vxz, rxz);
@@ -591,6 +638,14 @@ __global__ void __launch_bounds__(256) k_vc3_vel(const __grid_constant__ V3 a)
     const int i = blockIdx.x * blockDim.x + threadIdx.x + 1, j = blockIdx.y * blockDim.y + threadIdx.y + 1, k = blockIdx.z + 1;
     if (i > nx || j > ny || k > nz) return;
     const double *P = a.P, *ett = a.etatau, *txx = a.txx_o, *tyy = a.tyy_o, *tzz = a.tzz_o, *tyz = a.tyz_o, *txz = a.txz_o, *txy = a.txy_o;
+    if (a.pf_next && k + 2 <= nz) {
+        // L2 prefetch of this thread's operands two planes up
+        const size_t c2 = IX3(nx, ny, i, j, k + 2);
+        jr_prefetch_l2(P + c2); jr_prefetch_l2(ett + c2); jr_prefetch_l2(txx + c2); jr_prefetch_l2(tyy + c2); jr_prefetch_l2(tzz + c2);
+        jr_prefetch_l2(a.rgx + c2); jr_prefetch_l2(a.rgy + c2); jr_prefetch_l2(a.rgz + c2);
+        jr_prefetch_l2(&XY(txy, i + 1, j + 1, k + 2)); jr_prefetch_l2(&XZ(txz, i + 1, j, k + 3)); jr_prefetch_l2(&YZ(tyz, i, j + 1, k + 3));
+        jr_prefetch_l2(&VX(i + 1, j + 1, k + 3)); jr_prefetch_l2(&VY(i + 1, j + 1, k + 3)); jr_prefetch_l2(&VZ(i + 1, j + 1, k + 3));
+    }
     const double Pc = CC(P, i, j, k), ec = CC(ett, i, j, k);
     const double xy11 = XY(txy, i + 1, j + 1, k), xz11 = XZ(txz, i + 1, j, k + 1), yz11 = YZ(tyz, i, j + 1, k + 1);
     if (i <= nx - 1) {
@@ -752,6 +807,10 @@ static int plan3_begin(jr_context *ctx, const jr_fields *s, const jr_stokes_opts
     k.nx = nx; k.ny = ny; k.nz = nz;
     k._dx = o->_di[0]; k._dy = o->_di[1]; k._dz = o->_di[2]; k.dt = o->dt; k.r = o->r; k.th = o->theta_dtau; k.edt = o->eta_dtau;
     k.rel = o->lambda_relaxation; k.nu = o->viscosity_relaxation; k.cut_lo = o->visc_cutoff_lo; k.cut_hi = o->visc_cutoff_hi;
+    {
+        const char *e = getenv("JRB200_VC3_PREFETCH");
+        k.pf_next = (e && atoi(e) == 0) ? 0 : 1;
+    }
     k.Vx = F(Vx); k.Vy = F(Vy); k.Vz = F(Vz); k.theta = (double *)(B + o_th); k.P = F(P); k.P0 = F(P0); k.Q = F(Q); k.etatau = F(etatau);
     k.exx = F(exx); k.eyy = F(eyy); k.ezz = F(ezz); k.eyz = F(eyz); k.exz = F(exz); k.exy = F(exy);
     k.tyzc = F(tyz_c); k.txzc = F(txz_c); k.txyc = F(txy_c);

@@ -373,7 +373,8 @@ __device__ __forceinline__ double th_flux_pt(double q_old, double K, double Tl, 
     const double qx = -K * (Th - Tl) * _d;
     return jr_div_nr(q_old * th_ + qx, 1.0 + th_);  // IEEE-exact quotient (denominator ≥ 1), no slow-path call
 }
-template <int FORM, int NP>  // NP = 0: no phase ratios; else compile-time bound on the number of phases
+__device__ __forceinline__ void th_pf(const double *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+template <int FORM, int NP, bool PF>  // NP = 0: no phase ratios; else compile-time bound on the number of phases; PF: L2 prefetch
 __global__ void __launch_bounds__(256, 2) k_th_fused3(const __grid_constant__ ThArgs a, const __grid_constant__ ThPP pp)
 {
     const ThDims &d = a.d;
@@ -401,6 +402,24 @@ __global__ void __launch_bounds__(256, 2) k_th_fused3(const __grid_constant__ Th
     constexpr bool HASR = NP > 0;
     constexpr int NR = NP > 0 ? NP : 1;
     for (int k = k0; k < k1; ++k) {
+        // ---- L2 prefetch of the NEXT plane's operands (no registers held; the loads of the next step then hit L2) ----
+        if (PF && k + 1 < k1) {
+            th_pf(T + t + 2 * sT); th_pf(a.f.Told + t + sT);
+            if (k + 2 < nz) th_pf(TH + c + 2 * sC);
+            th_pf(qxi + fx + sX); th_pf(qyi + fy + sY); th_pf(qzi + c + 2 * sC);
+            th_pf(Kx + fx + sX); th_pf(Ky + fy + sY); th_pf(Kz + c + 2 * sC);
+            th_pf(a.f.dtau_rho + c + sC); th_pf(a.f.H + c + sC); th_pf(a.f.shear_heating + c + sC);
+            if (FORM == 0) th_pf(a.f.rhoCp + c + sC);
+            else {
+                th_pf(a.f.adiabatic + c + sC);
+                if (a.f.P) th_pf(a.f.P + c + sC);
+                if (HASR) {
+#pragma unroll
+                    for (int q = 0; q < NR; q++)
+                        if (q < a.tab.nphase) th_pf(a.f.phase_c + (size_t)q * nc + c + sC);
+                }
+            }
+        }
         // ---- loads of this plane (independent: issued back to back) ----
         const double Tp = __ldg(T + t + sT);
         const double thp = k < nz - 1 ? __ldg(TH + c + sC) : thc;
@@ -673,7 +692,8 @@ static int th_iter(jr_context *ctx, ThArgs &a, const jr_thermal_opts *o, bool sa
 struct ThFused {
     bool ok = false, pt_dyn = false;
     double *Tb = nullptr, *thb = nullptr, *qb[3] = {nullptr, nullptr, nullptr};
-    int kchunk = 32;
+    int kchunk = 16;
+    bool prefetch = true;
 };
 static int th_fused_prepare(jr_context *ctx, ThArgs &a, ThFused &F)
 {
@@ -684,6 +704,7 @@ static int th_fused_prepare(jr_context *ctx, ThArgs &a, ThFused &F)
     if (!F.ok) return th_prepare_kface(ctx, a);
     F.pt_dyn = a.form == 1 && a.f.phase_c;
     if (const char *e = getenv("JRB200_TH_KCHUNK")) F.kchunk = atoi(e) > 0 ? atoi(e) : F.kchunk;
+    if (const char *e = getenv("JRB200_TH_PREFETCH")) F.prefetch = atoi(e) != 0;
     const size_t nc = (size_t)d.nx * d.ny * d.nz, ng = (size_t)d.gx * d.gy * d.gz;
     const size_t nfx = (size_t)(d.nx + 1) * d.ny * d.nz, nfy = (size_t)d.nx * (d.ny + 1) * d.nz, nfz = (size_t)d.nx * d.ny * (d.nz + 1);
     void *p = nullptr;
@@ -711,12 +732,19 @@ static int th_fused_launch(jr_context *ctx, const ThArgs &a, const ThFused &F, b
     else { pp.th_in = a.f.theta_r_dtau; pp.th_out = a.f.theta_r_dtau; }
     pp.kchunk = F.kchunk;
     dim3 blk(32, 8, 1), grid((d.nx + 31) / 32, (d.ny + 7) / 8, (d.nz + F.kchunk - 1) / F.kchunk);
-    if (a.form == 0) k_th_fused3<0, 0><<<grid, blk, 0, ctx->stream>>>(a, pp);
-    else if (!F.pt_dyn) k_th_fused3<1, 0><<<grid, blk, 0, ctx->stream>>>(a, pp);
-    else if (a.tab.nphase <= 2) k_th_fused3<1, 2><<<grid, blk, 0, ctx->stream>>>(a, pp);
-    else if (a.tab.nphase <= 3) k_th_fused3<1, 3><<<grid, blk, 0, ctx->stream>>>(a, pp);
-    else if (a.tab.nphase <= 4) k_th_fused3<1, 4><<<grid, blk, 0, ctx->stream>>>(a, pp);
-    else k_th_fused3<1, TH_MAX_PHASES><<<grid, blk, 0, ctx->stream>>>(a, pp);
+    const bool pf = F.prefetch;
+#define TH_LAUNCH(FORM_, NP_)                                                                 \
+    do {                                                                                      \
+        if (pf) k_th_fused3<FORM_, NP_, true><<<grid, blk, 0, ctx->stream>>>(a, pp);          \
+        else k_th_fused3<FORM_, NP_, false><<<grid, blk, 0, ctx->stream>>>(a, pp);            \
+    } while (0)
+    if (a.form == 0) TH_LAUNCH(0, 0);
+    else if (!F.pt_dyn) TH_LAUNCH(1, 0);
+    else if (a.tab.nphase <= 2) TH_LAUNCH(1, 2);
+    else if (a.tab.nphase <= 3) TH_LAUNCH(1, 3);
+    else if (a.tab.nphase <= 4) TH_LAUNCH(1, 4);
+    else TH_LAUNCH(1, TH_MAX_PHASES);
+#undef TH_LAUNCH
     ctx->launches++;
     JR_CHECK_LAUNCH();
     return JR_OK;
