@@ -145,6 +145,12 @@ def solve_(stokes: StokesArrays, pt_stokes, grid, flow_bcs, ρg, *rest, kwargs=N
         from .stokes3d_vc import solve3d_VC_
 
         return solve3d_VC_(stokes, pt_stokes, grid, flow_bcs, ρg, *rest, kwargs=kwargs)
+    from .rheology import MaterialParams
+
+    if rest and isinstance(rest[0], MaterialParams):
+        # legacy single-phase VEP variant 2D-V3 (Stokes2D.jl:345-557): not built, deliberately — fail loudly
+        raise NotImplementedError("solve!(stokes, pt, grid, bcs, ρg, rheology::MaterialParams, args, dt, igg) — the legacy single-phase "
+                                  "variant is outside the B200 backend; pass PhaseRatios with one phase and a 1-tuple rheology (2D-VC)")
     if len(stokes.ni) == 2:
         return _solve2d_V2(stokes, pt_stokes, grid, flow_bcs, ρg, *rest, kwargs=kwargs)
     return _solve3d_VA(stokes, pt_stokes, grid, flow_bcs, ρg, *rest, kwargs=kwargs)

@@ -50,3 +50,18 @@ def test_no_gpu_fails_loudly():
     st = _abi.lib().jr_context_create(0, None, C.byref(h))
     assert st == _abi.JR_ERR_CUDA
     assert b"no CPU fallback" in _abi.lib().jr_last_error()
+
+
+def test_legacy_single_phase_variant_fails_loudly():
+    """2D-V3 (Stokes2D.jl:345-557, solve! with a single MaterialParams) is deliberately outside the backend"""
+    import pytest
+
+    from justrelax_jl_b200 import rheology as R, stokes as jst
+
+    class _S:
+        ni = (8, 8)
+
+    rheo = R.SetMaterialParams(Phase=1, Density=R.ConstantDensity(ρ=1.0),
+                               CompositeRheology=R.CompositeRheology((R.LinearViscous(η=1.0), R.ConstantElasticity(G=1.0, ν=0.45))))
+    with pytest.raises(NotImplementedError, match="legacy single-phase"):
+        jst.solve_(_S(), None, None, None, None, rheo, {}, 0.1, None)
