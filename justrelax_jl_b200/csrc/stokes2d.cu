@@ -13,6 +13,7 @@
 // Diagnostics nobody reads inside the loop (∇V, ε, ε_pl, RP, τII, η_vep, U, ρg) are only stored on the iterations whose
 // result can be observed (every `nout`, and the last).
 #include "rheo.cuh"
+#include "tma.cuh"
 
 #define F(name) (s->f[JR_F_##name])
 #define TX 32
@@ -132,8 +133,9 @@ __global__ void __launch_bounds__(NT) k_stokes2d(const __grid_constant__ K2 a, c
             double eta_reg;
             jr_plastic_params(pt, a.ph_v, nv, v, is_pl, eta_reg);
             const double _Gdt = jr_inv(jr_ratio_G(pt, a.ph_v, nv, v) * a.dt), Kv = jr_ratio_Kb(pt, a.ph_v, nv, v);
-            const double etav = 4 / (1 / s_eta[q00] + 1 / s_eta[qcc] + 1 / s_eta[q0c] + 1 / s_eta[qc0]);
-            const double dtr = jr_inv(a.th + etav * _Gdt + 1.0);
+            // harmonic mean of η (> 0, normal range) and 1/(θ_dτ + η/(G dt) + 1) (operand ≥ 1): branch-free IEEE-exact sequences
+            const double etav = jr_div_nr(4.0, jr_inv_nr(s_eta[q00]) + jr_inv_nr(s_eta[qcc]) + jr_inv_nr(s_eta[q0c]) + jr_inv_nr(s_eta[qc0]));
+            const double dtr = jr_inv_nr(a.th + etav * _Gdt + 1.0);
             const double txyv = a.txy_i[v];
             const double dxx = jr_stress_increment(txxv, txxov, etav, exxv, _Gdt, dtr), dyy = jr_stress_increment(tyyv, tyyov, etav, eyyv, _Gdt, dtr);
             const double dxy = jr_stress_increment(txyv, a.txyo[v], etav, exy, _Gdt, dtr);

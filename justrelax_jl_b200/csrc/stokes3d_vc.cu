@@ -50,8 +50,11 @@ __device__ __forceinline__ void jr_prefetch_l2(const double *p) { asm volatile("
 // ---------------------------------------------------------------------------------------------------------------------------------
 // MAXLOC: compute ητ here (single rank); otherwise ητ was computed by k_maxloc3 and halo-exchanged before this launch.
 // NP = compile-time bound on the number of phases: the centre ratios are loaded once and reused for K, G, ρ and η.
+#ifndef JR_PREP_MINB
+#define JR_PREP_MINB 4
+#endif
 template <bool DIAG, bool MAXLOC, int NP>
-__global__ void __launch_bounds__(256) k_vc3_prep(const __grid_constant__ V3 a, const __grid_constant__ jr_phase_tab pt)
+__global__ void __launch_bounds__(256, JR_PREP_MINB) k_vc3_prep(const __grid_constant__ V3 a, const __grid_constant__ jr_phase_tab pt)
 {
     const int nx = a.nx, ny = a.ny, nz = a.nz;
     const int i = blockIdx.x * blockDim.x + threadIdx.x + 1, j = blockIdx.y * blockDim.y + threadIdx.y + 1, k = blockIdx.z + 1;
@@ -627,133 +630,6 @@ __global__ void __launch_bounds__(32 * TYS, 2) k_vc3_stress_sm(const __grid_cons
 #undef S
 }
 
-// ---- role-split variant ---------------------------------------------------------------------------------------------------------------
-// The staged kernel above runs ≈ 2000 dependent FP64-heavy instructions per node at 16 warps/SM (128 registers): bound by instruction
-// latency.  Here the four updates of a node — yz, xz, xy edge and the cell centre — are taken by four different WARPS (threadIdx.z =
-// role, warp-uniform: no divergence) that share the same staged tiles: four times the threads with a quarter of the work and less than
-// half the live state each (≤ 64 registers), so 32 warps/SM are resident.  Same tiles, same expressions, same operation order per
-// update ⇒ bit-identical results.  TYR = rows of nodes per CTA (8: one CTA of 1024 threads per SM; 4: two CTAs of 512).
-template <bool DIAG, int NP, int TYR>
-__global__ void __launch_bounds__(128 * TYR, (TYR == 4 ? 2 : 1)) k_vc3_stress_rs(const __grid_constant__ V3 a, const __grid_constant__ jr_phase_tab pt)
-{
-    constexpr int RPLANE = SROW * (TYR + 1), RTILE = 2 * RPLANE, NTH = 128 * TYR;
-    extern __shared__ double sm[];
-    const int nx = a.nx, ny = a.ny, nz = a.nz;
-    const int tx = threadIdx.x, ty = threadIdx.y, role = threadIdx.z, tid = (role * TYR + ty) * 32 + tx;
-    const int ib = blockIdx.x * 32 + 1, jb = blockIdx.y * TYR + 1, k = blockIdx.z + 1;   // first node of the CTA (1-based)
-    // fast CTAs: every node has i+1 ≤ nx, j+1 ≤ ny, k+1 ≤ nz (no high-side clamp is active); the others take the global-memory body
-    if (!(ib + 31 <= nx - 1 && jb + TYR - 1 <= ny - 1 && k <= nz - 1)) {
-        if (role == 0) vc3_stress_body_call<DIAG, NP>(a, pt);
-        return;
-    }
-    const int i = ib + tx, j = jb + ty;
-    const double *src[SL_COUNT] = {a.eta_o, a.theta, a.txx_i, a.tyy_i, a.tzz_i, a.oxx, a.oyy, a.ozz, a.exx, a.eyy, a.ezz,
-                                   a.tyz_i, a.oyz, a.eyz, a.txz_i, a.oxz, a.exz, a.txy_i, a.oxy, a.exy};
-    // ---- stage the tiles (all four roles copy)
-#pragma unroll
-    for (int it = 0; it < (RTILE + NTH - 1) / NTH; it++) {
-        const int e = tid + it * NTH;
-        if (e < RTILE) {
-            const int p = e / RPLANE, r = (e - p * RPLANE) / SROW, c = e - p * RPLANE - r * SROW;
-            const int im = max(ib - 1 + c, 1), jm = max(jb - 1 + r, 1), km = max(k - 1 + p, 1), ip = ib + c, jp = jb + r, kp = k + p;
-            const size_t oc = IX3(nx, ny, im, jm, km), oy = IX3(nx, ny + 1, im, jp, kp), oz = IX3(nx + 1, ny, ip, jm, kp),
-                         ox = IX3(nx + 1, ny + 1, ip, jp, km);
-#pragma unroll
-            for (int q = 0; q < SL_COUNT; q++) {
-                const size_t o = q < SL_tyz ? oc : (q < SL_txz ? oy : (q < SL_txy ? oz : ox));
-                cp_async8(sm + q * RTILE + e, src[q] + o);
-            }
-        }
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    const size_t nc = (size_t)nx * ny * nz, nyz = (size_t)nx * (ny + 1) * (nz + 1), nxz = (size_t)(nx + 1) * ny * (nz + 1),
-                 nxy = (size_t)(nx + 1) * (ny + 1) * nz;
-    const size_t c = IX3(nx, ny, i, j, k), vyz = IX3(nx, ny + 1, i, j, k), vxz = IX3(nx + 1, ny, i, j, k), vxy = IX3(nx + 1, ny + 1, i, j, k);
-    // L2 prefetch for the CTA of the same tile on plane k + 1 (see k_vc3_stress_sm)
-    if (a.pf_next && k + 1 <= nz - 1) {
-        if (tid < RPLANE) {
-            const int r = tid / SROW, cc = tid - r * SROW;
-            const int im = max(ib - 1 + cc, 1), jm = max(jb - 1 + r, 1), ip = ib + cc, jp = jb + r;
-            const size_t oc = IX3(nx, ny, im, jm, k + 1), oy = IX3(nx, ny + 1, im, jp, k + 2), oz = IX3(nx + 1, ny, ip, jm, k + 2),
-                         ox = IX3(nx + 1, ny + 1, ip, jp, k + 1);
-#pragma unroll
-            for (int q = 0; q < SL_COUNT; q++) {
-                const size_t o = q < SL_tyz ? oc : (q < SL_txz ? oy : (q < SL_txy ? oz : ox));
-                jr_prefetch_l2(src[q] + o);
-            }
-        }
-        const size_t sc = (size_t)nx * ny, syz = (size_t)nx * (ny + 1), sxz = (size_t)(nx + 1) * ny, sxy = (size_t)(nx + 1) * (ny + 1);
-        const double *phr = role == 0 ? a.ph_yz : role == 1 ? a.ph_xz : role == 2 ? a.ph_xy : a.ph_c;
-        const size_t nst = role == 0 ? nyz : role == 1 ? nxz : role == 2 ? nxy : nc;
-        const size_t vn = role == 0 ? vyz + syz : role == 1 ? vxz + sxz : role == 2 ? vxy + sxy : c + sc;
-#pragma unroll
-        for (int p = 0; p < NP; p++)
-            if (p < pt.n) jr_prefetch_l2(phr + (size_t)p * nst + vn);
-        if (role == 0) jr_prefetch_l2(a.lamyz + vn);
-        else if (role == 1) jr_prefetch_l2(a.lamxz + vn);
-        else if (role == 2) jr_prefetch_l2(a.lamxy + vn);
-        else {
-            jr_prefetch_l2(a.tyzc + vn); jr_prefetch_l2(a.txzc + vn); jr_prefetch_l2(a.txyc + vn);
-            jr_prefetch_l2(a.oyzc + vn); jr_prefetch_l2(a.oxzc + vn); jr_prefetch_l2(a.oxyc + vn); jr_prefetch_l2(a.lam + vn);
-        }
-    }
-    // this role's phase ratios, issued while the copies are in flight
-    double rr[NP];
-    if (role == 0) ratios_load<NP>(pt, a.ph_yz, nyz, vyz, rr);
-    else if (role == 1) ratios_load<NP>(pt, a.ph_xz, nxz, vxz, rr);
-    else if (role == 2) ratios_load<NP>(pt, a.ph_xy, nxy, vxy, rr);
-    else ratios_load<NP>(pt, a.ph_c, nc, c, rr);
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();
-#define S(s, I, J, K) sm[(s) * RTILE + (K) * RPLANE + (ty + (J)) * SROW + tx + (I)]
-    Mix<NP> m;
-    mix_from<NP>(pt, rr, m);
-    if (role < 3) {
-        EdgeAcc E;
-        E._Gdt = jr_inv(m.G * a.dt);
-        if (role == 0) {  // yz edge  StressKernels.jl:716-778
-            E.etav = SHARM_YZ(SL_eta); E.Pv = SAV_YZ(SL_theta);
-            E.dtr = jr_inv_nr(a.th + E.etav * E._Gdt + 1.0);
-            edge_comp<0, false>(E, SAV_YZ(SL_txx), SAV_YZ(SL_oxx), SAV_YZ(SL_exx));
-            edge_comp<1, false>(E, SAV_YZ(SL_tyy), SAV_YZ(SL_oyy), SAV_YZ(SL_eyy));
-            edge_comp<2, false>(E, SAV_YZ(SL_tzz), SAV_YZ(SL_ozz), SAV_YZ(SL_ezz));
-            edge_comp<3, true>(E, S(SL_tyz, 1, 0, 0), S(SL_oyz, 1, 0, 0), S(SL_eyz, 1, 0, 0));
-            edge_comp<4, false>(E, SAV_YZ_Y(SL_txz), SAV_YZ_Y(SL_oxz), SAV_YZ_Y(SL_exz));
-            edge_comp<5, false>(E, SAV_YZ_Z(SL_txy), SAV_YZ_Z(SL_oxy), SAV_YZ_Z(SL_exy));
-            edge_finish<DIAG, NP>(a, pt, m, E, vyz, a.lamyz, a.tyz_o, a.pyz);
-        } else if (role == 1) {  // xz edge  :781-849
-            E.etav = SHARM_XZ(SL_eta); E.Pv = SAV_XZ(SL_theta);
-            E.dtr = jr_inv_nr(a.th + E.etav * E._Gdt + 1.0);
-            edge_comp<0, false>(E, SAV_XZ(SL_txx), SAV_XZ(SL_oxx), SAV_XZ(SL_exx));
-            edge_comp<1, false>(E, SAV_XZ(SL_tyy), SAV_XZ(SL_oyy), SAV_XZ(SL_eyy));
-            edge_comp<2, false>(E, SAV_XZ(SL_tzz), SAV_XZ(SL_ozz), SAV_XZ(SL_ezz));
-            edge_comp<3, false>(E, SAV_XZ_X(SL_tyz), SAV_XZ_X(SL_oyz), SAV_XZ_X(SL_eyz));
-            edge_comp<4, true>(E, S(SL_txz, 0, 1, 0), S(SL_oxz, 0, 1, 0), S(SL_exz, 0, 1, 0));
-            edge_comp<5, false>(E, SAV_XZ_Z(SL_txy), SAV_XZ_Z(SL_oxy), SAV_XZ_Z(SL_exy));
-            edge_finish<DIAG, NP>(a, pt, m, E, vxz, a.lamxz, a.txz_o, a.pxz);
-        } else {  // xy edge  :852-921
-            E.etav = SHARM_XY(SL_eta); E.Pv = SAV_XY(SL_theta);
-            E.dtr = jr_inv_nr(a.th + E.etav * E._Gdt + 1.0);
-            edge_comp<0, false>(E, SAV_XY(SL_txx), SAV_XY(SL_oxx), SAV_XY(SL_exx));
-            edge_comp<1, false>(E, SAV_XY(SL_tyy), SAV_XY(SL_oyy), SAV_XY(SL_eyy));
-            edge_comp<2, false>(E, SAV_XY(SL_tzz), SAV_XY(SL_ozz), SAV_XY(SL_ezz));
-            edge_comp<3, false>(E, SAV_XY_X(SL_tyz), SAV_XY_X(SL_oyz), SAV_XY_X(SL_eyz));
-            edge_comp<4, false>(E, SAV_XY_Y(SL_txz), SAV_XY_Y(SL_oxz), SAV_XY_Y(SL_exz));
-            edge_comp<5, true>(E, S(SL_txy, 0, 0, 1), S(SL_oxy, 0, 0, 1), S(SL_exy, 0, 0, 1));
-            edge_finish<DIAG, NP>(a, pt, m, E, vxy, a.lamxy, a.txy_o, a.pxy);
-        }
-    } else {  // centre: cell (i, j, k) = S(·, 1, 1, 1); edge gathers in mysum order (quirk Q15)  :923-986
-        const double eij[6] = {S(SL_exx, 1, 1, 1), S(SL_eyy, 1, 1, 1), S(SL_ezz, 1, 1, 1),
-                               0.25 * ((((0.0 + S(SL_eyz, 1, 0, 0)) + S(SL_eyz, 1, 1, 0)) + S(SL_eyz, 1, 0, 1)) + S(SL_eyz, 1, 1, 1)),
-                               0.25 * ((((0.0 + S(SL_exz, 0, 1, 0)) + S(SL_exz, 1, 1, 0)) + S(SL_exz, 0, 1, 1)) + S(SL_exz, 1, 1, 1)),
-                               0.25 * ((((0.0 + S(SL_exy, 0, 0, 1)) + S(SL_exy, 1, 0, 1)) + S(SL_exy, 0, 1, 1)) + S(SL_exy, 1, 1, 1))};
-        double tij[6] = {S(SL_txx, 1, 1, 1), S(SL_tyy, 1, 1, 1), S(SL_tzz, 1, 1, 1), a.tyzc[c], a.txzc[c], a.txyc[c]};
-        const double tijo[6] = {S(SL_oxx, 1, 1, 1), S(SL_oyy, 1, 1, 1), S(SL_ozz, 1, 1, 1), __ldg(a.oyzc + c), __ldg(a.oxzc + c), __ldg(a.oxyc + c)};
-        vc3_centre<DIAG, NP>(a, pt, m, c, S(SL_eta, 1, 1, 1), S(SL_theta, 1, 1, 1), eij, tij, tijo);
-    }
-#undef S
-}
-
 // global-memory variant: 3 CTAs of 256 threads per SM (≤ 80 registers, a few spilled doubles) — bound by the latency of its ≈ 280 loads per
 // node; measured time falls with occupancy up to 24 warps/SM (5.75 ms per iteration at 128 registers → 5.15 ms at 80; no gain beyond)
 template <bool DIAG, int NP>
@@ -989,31 +865,10 @@ static void launch_prep(bool diag, bool maxloc, int nphase, dim3 grd, cudaStream
     else launch_prep_np<JR_MAX_PHASES>(diag, maxloc, grd, st, k, pt);
 }
 
-template <int NP, int TYR>
-static void launch_stress_rs(bool diag, dim3 grd, cudaStream_t st, const V3 &k, const jr_phase_tab &pt)
-{
-    const size_t smem = (size_t)SL_COUNT * 2 * SROW * (TYR + 1) * sizeof(double);
-    static bool attr = false;   // per instantiation
-    if (!attr) {
-        cudaFuncSetAttribute(k_vc3_stress_rs<true, NP, TYR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(k_vc3_stress_rs<false, NP, TYR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr = true;
-    }
-    const dim3 blk(32, TYR, 4), g2(grd.x, (grd.y * 8 + TYR - 1) / TYR, grd.z);
-    if (diag) k_vc3_stress_rs<true, NP, TYR><<<g2, blk, smem, st>>>(k, pt);
-    else k_vc3_stress_rs<false, NP, TYR><<<g2, blk, smem, st>>>(k, pt);
-}
 template <int NP>
 static void launch_stress_np(bool diag, dim3 grd, cudaStream_t st, const V3 &k, const jr_phase_tab &pt)
 {
     static const bool use_sm = !(getenv("JRB200_VC_STRESS_GLOBAL") && atoi(getenv("JRB200_VC_STRESS_GLOBAL")));
-    // role-split variant: JRB200_VC3_ROLES = 8 | 4 (rows of nodes per CTA), 0 = off
-    static const int roles = getenv("JRB200_VC3_ROLES") ? atoi(getenv("JRB200_VC3_ROLES")) : 0;
-    if (use_sm && (roles == 8 || roles == 4)) {
-        if (roles == 8) launch_stress_rs<NP, 8>(diag, grd, st, k, pt);
-        else launch_stress_rs<NP, 4>(diag, grd, st, k, pt);
-        return;
-    }
     if (use_sm) {
         const size_t smem = (size_t)SL_COUNT * STILE * sizeof(double);
         static bool attr = false;   // per instantiation

@@ -374,8 +374,8 @@ __device__ __forceinline__ double th_flux_pt(double q_old, double K, double Tl, 
     return jr_div_nr(q_old * th_ + qx, 1.0 + th_);  // IEEE-exact quotient (denominator ≥ 1), no slow-path call
 }
 __device__ __forceinline__ void th_pf(const double *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-template <int FORM, int NP, bool PF>  // NP = 0: no phase ratios; else compile-time bound on the number of phases; PF: L2 prefetch
-__global__ void __launch_bounds__(256, 2) k_th_fused3(const __grid_constant__ ThArgs a, const __grid_constant__ ThPP pp)
+template <int FORM, int NP, bool PF, int MINB>  // NP = 0: no phase ratios; else compile-time phase bound; PF: L2 prefetch; MINB: CTAs/SM
+__global__ void __launch_bounds__(256, MINB) k_th_fused3(const __grid_constant__ ThArgs a, const __grid_constant__ ThPP pp)
 {
     const ThDims &d = a.d;
     const int nx = d.nx, ny = d.ny, nz = d.nz;
@@ -692,8 +692,9 @@ static int th_iter(jr_context *ctx, ThArgs &a, const jr_thermal_opts *o, bool sa
 struct ThFused {
     bool ok = false, pt_dyn = false;
     double *Tb = nullptr, *thb = nullptr, *qb[3] = {nullptr, nullptr, nullptr};
-    int kchunk = 16;
+    int kchunk = 12;
     bool prefetch = true;
+    int minb = 4;   // resident CTAs per SM the kernel is compiled for (2: 115 registers, 3: 78, 4: 64 — still no spills —, 5: 48 with spills)
 };
 static int th_fused_prepare(jr_context *ctx, ThArgs &a, ThFused &F)
 {
@@ -705,6 +706,7 @@ static int th_fused_prepare(jr_context *ctx, ThArgs &a, ThFused &F)
     F.pt_dyn = a.form == 1 && a.f.phase_c;
     if (const char *e = getenv("JRB200_TH_KCHUNK")) F.kchunk = atoi(e) > 0 ? atoi(e) : F.kchunk;
     if (const char *e = getenv("JRB200_TH_PREFETCH")) F.prefetch = atoi(e) != 0;
+    if (const char *e = getenv("JRB200_TH_MINB")) F.minb = (atoi(e) >= 2 && atoi(e) <= 5) ? atoi(e) : F.minb;
     const size_t nc = (size_t)d.nx * d.ny * d.nz, ng = (size_t)d.gx * d.gy * d.gz;
     const size_t nfx = (size_t)(d.nx + 1) * d.ny * d.nz, nfy = (size_t)d.nx * (d.ny + 1) * d.nz, nfz = (size_t)d.nx * d.ny * (d.nz + 1);
     void *p = nullptr;
@@ -733,10 +735,17 @@ static int th_fused_launch(jr_context *ctx, const ThArgs &a, const ThFused &F, b
     pp.kchunk = F.kchunk;
     dim3 blk(32, 8, 1), grid((d.nx + 31) / 32, (d.ny + 7) / 8, (d.nz + F.kchunk - 1) / F.kchunk);
     const bool pf = F.prefetch;
-#define TH_LAUNCH(FORM_, NP_)                                                                 \
-    do {                                                                                      \
-        if (pf) k_th_fused3<FORM_, NP_, true><<<grid, blk, 0, ctx->stream>>>(a, pp);          \
-        else k_th_fused3<FORM_, NP_, false><<<grid, blk, 0, ctx->stream>>>(a, pp);            \
+#define TH_LAUNCH_B(FORM_, NP_, B_)                                                                 \
+    do {                                                                                            \
+        if (pf) k_th_fused3<FORM_, NP_, true, B_><<<grid, blk, 0, ctx->stream>>>(a, pp);            \
+        else k_th_fused3<FORM_, NP_, false, B_><<<grid, blk, 0, ctx->stream>>>(a, pp);              \
+    } while (0)
+#define TH_LAUNCH(FORM_, NP_)                                                                       \
+    do {                                                                                            \
+        if (F.minb == 2) TH_LAUNCH_B(FORM_, NP_, 2);                                                \
+        else if (F.minb == 3) TH_LAUNCH_B(FORM_, NP_, 3);                                           \
+        else if (F.minb == 5) TH_LAUNCH_B(FORM_, NP_, 5);                                           \
+        else TH_LAUNCH_B(FORM_, NP_, 4);                                                            \
     } while (0)
     if (a.form == 0) TH_LAUNCH(0, 0);
     else if (!F.pt_dyn) TH_LAUNCH(1, 0);
@@ -745,6 +754,7 @@ static int th_fused_launch(jr_context *ctx, const ThArgs &a, const ThFused &F, b
     else if (a.tab.nphase <= 4) TH_LAUNCH(1, 4);
     else TH_LAUNCH(1, TH_MAX_PHASES);
 #undef TH_LAUNCH
+#undef TH_LAUNCH_B
     ctx->launches++;
     JR_CHECK_LAUNCH();
     return JR_OK;
