@@ -448,7 +448,9 @@ __device__ __forceinline__ void edge_finish(const V3 &a, const jr_phase_tab &pt,
 // thread and no registers held — then every node computes from shared memory with clamp-free indices.  CTAs that touch the high-side
 // boundary planes (where the clamped and the raw indices of the reference differ between families) take the global-memory body above.
 // The z-neighbour CTA re-reads one of the two planes: L2 serves it (CTAs are scheduled plane by plane).
+#ifndef TYS
 #define TYS 8
+#endif
 #define SROW 33
 #define SPLANE (SROW * (TYS + 1))
 #define STILE (2 * SPLANE)
@@ -490,7 +492,7 @@ __device__ __forceinline__ void mix_from(const jr_phase_tab &pt, const double (&
 }
 
 template <bool DIAG, int NP>
-__global__ void __launch_bounds__(32 * TYS, 2) k_vc3_stress_sm(const __grid_constant__ V3 a, const __grid_constant__ jr_phase_tab pt)
+__global__ void __launch_bounds__(32 * TYS, 16 / TYS) k_vc3_stress_sm(const __grid_constant__ V3 a, const __grid_constant__ jr_phase_tab pt)
 {
     extern __shared__ double sm[];
     const int nx = a.nx, ny = a.ny, nz = a.nz;
