@@ -212,6 +212,36 @@ def test_config1_diffusion2d_golden_and_parity(oracle):
     compare(th, f, ["T", "Told", "dT", "qTx", "qTy", "ResT"], "config 1 after 20 steps")
 
 
+def test_diffusion3d_multiphase_solve_parity(oracle):
+    """test/test_diffusion3D_multiphase.jl through the public API (heatdiffusion_PT!, rheology form, two phases with ratios, nout = 100):
+    the solve loop runs the fused flux + update kernel in pairs between the samples.  Same PT iteration counts as the oracle and the same
+    fields (≤ 1e-12; the arithmetic is the oracle's), and the reference's golden temperatures (rtol 1e-3) after all 10 steps."""
+    from justrelax_jl_b200 import B200Backend, PTArray, setups, thermal as jth, to_host
+    from test_oracle_thermal import run_diffusion_multiphase
+
+    s = setups.diffusion_multiphase(3)
+    f, outs = run_diffusion_multiphase(oracle, s)
+    init = dict(T=s.T.copy(order="F"), H=s.H, P=s.P, theta_r_dtau=s.pt.θr_dτ, dtau_rho=s.pt.dτ_ρ)
+    th, extra = to_device(s.ni, oracle.alloc_thermal(s.ni, init))
+    Tin = th.T[1:-1, 1:-1, 1:-1]
+    Tin += PTArray(B200Backend)(s.perturbation.astype(np.float64) * s.δT)
+    pt = type("PT", (), {})()
+    pt.ϵ, pt.max_lxyz, pt.Vpdτ = s.pt.ϵ, s.pt.max_lxyz, s.pt.Vpdτ
+    pt.θr_dτ, pt.dτ_ρ = extra["theta_r_dtau"], extra["dtau_rho"]
+    ph = _Phase()
+    ph.center, ph.Vx, ph.Vy, ph.Vz = (PTArray(B200Backend)(s.phase[k]) for k in ("center", "Vx", "Vy", "Vz"))
+    rheo = rheology_of(s.phases)
+    iters = []
+    for _ in range(s.nt):
+        out = jth.heatdiffusion_PT_(th, pt, s.bc, rheo, dict(P=extra["P"], T=th.T), s.dt, s.grid, kwargs=dict(s.kwargs, phase=ph))
+        iters.append(int(out.iter_count[-1]))
+    assert iters == [int(o["iter_count"][-1]) for o in outs]
+    T = to_host(th.T)
+    assert abs(T[15, 15, 15] / 1816.8262937737384 - 1) < 1.0e-3
+    assert abs(T[1:-1, 1:-1, 1:-1][15, 15, 15] / 1834.4197141500213 - 1) < 1.0e-3
+    compare(th, f, ["T", "Told", "dT", "qTx", "qTy", "qTz", "ResT"], "3D multiphase diffusion after 10 steps")
+
+
 @pytest.mark.parametrize("ni", [(12, 9), (10, 9, 8)])
 def test_thermal_bcs_standalone(oracle, ni):
     from justrelax_jl_b200 import B200Backend, PTArray, thermal as jth, to_host
