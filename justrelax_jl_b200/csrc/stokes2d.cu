@@ -17,7 +17,7 @@
 
 #define F(name) (s->f[JR_F_##name])
 #define TX 32
-#define TY 16
+#define TY 16            /* default tile height (threads in y) */
 #define NT (TX * TY)
 
 struct K2 {
@@ -35,22 +35,24 @@ struct K2 {
 
 __device__ __forceinline__ double inv2(double xx, double yy, double xy) { return sqrt(0.5 * (xx * xx + yy * yy) + xy * xy); }
 
-template <bool VC, bool DIAG>
-__global__ void __launch_bounds__(NT) k_stokes2d(const __grid_constant__ K2 a, const __grid_constant__ jr_phase_tab pt)
+// TYT = threads in y (tile height incl. the one-node rim): chosen per grid so that the CTA count fills whole waves (plan2_tile)
+template <bool VC, bool DIAG, int TYT>
+__global__ void __launch_bounds__(TX * TYT) k_stokes2d(const __grid_constant__ K2 a, const __grid_constant__ jr_phase_tab pt)
 {
+    constexpr int NTT = TX * TYT;
     extern __shared__ double sm[];
     const int tx = threadIdx.x, ty = threadIdx.y, t = ty * TX + tx;
-    const int i = blockIdx.x * (TX - 2) + tx, j = blockIdx.y * (TY - 2) + ty;  // 1-based node index; 0 = idle rim thread
+    const int i = blockIdx.x * (TX - 2) + tx, j = blockIdx.y * (TYT - 2) + ty;  // 1-based node index; 0 = idle rim thread
     const int nx = a.nx, ny = a.ny;
     const bool vert = i >= 1 && j >= 1 && i <= nx + 1 && j <= ny + 1;
     const bool cell = vert && i <= nx && j <= ny;
-    const bool own = tx >= 1 && tx <= TX - 2 && ty >= 1 && ty <= TY - 2;
+    const bool own = tx >= 1 && tx <= TX - 2 && ty >= 1 && ty <= TYT - 2;
     const size_t nc = (size_t)nx * ny, nv = (size_t)(nx + 1) * (ny + 1);
     const size_t c = cell ? IX2(nx, i, j) : 0, v = vert ? IX2(nx + 1, i, j) : 0;
 
-    double *s_th = sm, *s_exx = sm + NT, *s_eyy = sm + 2 * NT, *s_exy = sm + 3 * NT, *s_ett = sm + 4 * NT, *s_rgx = sm + 5 * NT,
-           *s_rgy = sm + 6 * NT, *s_txxn = sm + 7 * NT, *s_tyyn = sm + 8 * NT, *s_txyn = sm + 9 * NT, *s_Pn = sm + 10 * NT,
-           *s_txx = sm + 11 * NT, *s_tyy = sm + 12 * NT, *s_txxo = sm + 13 * NT, *s_tyyo = sm + 14 * NT, *s_eta = sm + 15 * NT;
+    double *s_th = sm, *s_exx = sm + NTT, *s_eyy = sm + 2 * NTT, *s_exy = sm + 3 * NTT, *s_ett = sm + 4 * NTT, *s_rgx = sm + 5 * NTT,
+           *s_rgy = sm + 6 * NTT, *s_txxn = sm + 7 * NTT, *s_tyyn = sm + 8 * NTT, *s_txyn = sm + 9 * NTT, *s_Pn = sm + 10 * NTT,
+           *s_txx = sm + 11 * NTT, *s_tyy = sm + 12 * NTT, *s_txxo = sm + 13 * NTT, *s_tyyo = sm + 14 * NTT, *s_eta = sm + 15 * NTT;
 
     // ---------------- stage 1: ητ, ∇V, P|θ, ε (centres) and εxy (vertices) ------------------------------------------------------
     double divV = 0.0, RP = 0.0, thn = 0.0, exx = 0.0, eyy = 0.0, exy = 0.0, ett = 0.0, eta = 0.0, rgx = 0.0, rgy = 0.0;
@@ -156,7 +158,7 @@ __global__ void __launch_bounds__(NT) k_stokes2d(const __grid_constant__ K2 a, c
             }
         }
         __syncthreads();  // (no data hazard: keeps the vertex and centre register live ranges apart)
-        if (cell && tx <= TX - 2 && ty <= TY - 2) {
+        if (cell && tx <= TX - 2 && ty <= TYT - 2) {
             const double _Gdt = jr_inv(Gc * a.dt);
             bool is_pl;
             double eta_reg;
@@ -456,7 +458,58 @@ struct Plan2 {
     jr_phase_tab pt;
     bool periodic;
     int32_t fs[6], ns[6], pe[6];
+    int ty;   // tile height (threads in y) of k_stokes2d for this grid
 };
+
+// ---- tile height ----------------------------------------------------------------------------------------------------------------
+// The kernel is latency-bound per CTA (load tile → three dependent stages with two barriers → store), so a partial last wave costs
+// almost a full one: 511² with 16-row tiles is 666 CTAs on 296 slots = 2.25 → 3 waves, with 18-row tiles 576 CTAs = 2 waves.
+// Candidates are instantiated at compile time; the choice minimises waves × (fixed latency + resident rows per SM).
+template <bool VC, bool DIAG, int TYT>
+static int k2_attr(int *nb)
+{
+    const int smem = (VC ? 16 : 11) * TX * TYT * 8;
+    JR_CUDA(cudaFuncSetAttribute(k_stokes2d<VC, DIAG, TYT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    if (nb) JR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(nb, k_stokes2d<VC, DIAG, TYT>, TX * TYT, smem));
+    return JR_OK;
+}
+template <bool VC, int TYT>
+static int k2_attr_both(int *nb)
+{
+    int st = k2_attr<VC, true, TYT>(nullptr);
+    return st ? st : k2_attr<VC, false, TYT>(nb);
+}
+#define K2_TILES(X) X(12) X(14) X(16) X(18) X(20)
+static int plan2_tile(jr_context *ctx, Plan2 *p)
+{
+    static int nb_cache[2][32] = {};   // [vc][ty] resident CTAs per SM (0 = not queried yet, −1 = does not fit)
+    int best_ty = TY;
+    double best = 1e300;
+    int forced = 0;
+    if (const char *e = getenv("JRB200_2D_TY")) forced = atoi(e);
+#define X(T_)                                                                                                              \
+    {                                                                                                                      \
+        int &nb = nb_cache[p->vc ? 1 : 0][T_];                                                                             \
+        if (nb == 0) {                                                                                                     \
+            int q = 0;                                                                                                     \
+            const int st = p->vc ? k2_attr_both<true, T_>(&q) : k2_attr_both<false, T_>(&q);                               \
+            if (st) return st;                                                                                             \
+            nb = q > 0 ? q : -1;                                                                                           \
+        }                                                                                                                  \
+        if (nb > 0) {                                                                                                      \
+            const long ctas = (long)((p->nx + 1 + TX - 3) / (TX - 2)) * ((p->ny + 1 + T_ - 3) / (T_ - 2));                 \
+            const long slots = (long)nb * ctx->sm_count;                                                                   \
+            const long waves = (ctas + slots - 1) / slots;                                                                 \
+            const double est = (double)waves * (16.0 + (double)nb * T_);                                                   \
+            if (forced == T_ || (!forced && est < best * 0.999)) { best = forced == T_ ? -1.0 : est; best_ty = T_; }       \
+        }                                                                                                                  \
+    }
+    K2_TILES(X)
+#undef X
+    p->ty = best_ty;
+    if (getenv("JRB200_VERBOSE")) fprintf(stderr, "[jrb200] k_stokes2d<vc=%d>: %d x %d grid, tile height %d\n", (int)p->vc, p->nx, p->ny, p->ty);
+    return JR_OK;
+}
 
 static int check2d(const jr_fields *s, const jr_stokes_opts *o, bool vc, const jr_vc_inputs *in)
 {
@@ -521,14 +574,7 @@ static int plan2_begin(jr_context *ctx, const jr_fields *s, const jr_stokes_opts
         if ((st = jr_make_phase_tab(in, &p->pt))) return st;
         k.ph_c = in->ph_center; k.ph_v = in->ph_vertex;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
-        JR_CUDA(cudaFuncSetAttribute(k_stokes2d<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * NT * 8));
-        JR_CUDA(cudaFuncSetAttribute(k_stokes2d<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * NT * 8));
-        JR_CUDA(cudaFuncSetAttribute(k_stokes2d<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * NT * 8));
-        JR_CUDA(cudaFuncSetAttribute(k_stokes2d<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * NT * 8));
-        attr_set = true;
-    }
+    if ((st = plan2_tile(ctx, p))) return st;
     return JR_OK;
 }
 
@@ -542,15 +588,21 @@ static int plan2_iter(jr_context *ctx, Plan2 *p, int64_t it, bool diag)
     k.Vx_o = O[S_Vx]; k.Vy_o = O[S_Vy]; k.P_o = O[S_P]; k.txx_o = O[S_txx]; k.tyy_o = O[S_tyy]; k.txy_o = O[S_txy]; k.th_o = O[S_th];
     k.txyc_o = O[S_txyc]; k.lam_o = O[S_lam]; k.lamv_o = O[S_lamv]; k.eta_o = O[S_eta]; k.etav_o = O[S_etav];
     if (p->vc && k.Pargs == p->set[0][S_P]) k.Pargs = I[S_P];  // args.P aliases stokes.P in the reference's scripts
-    dim3 blk(TX, TY), grd((p->nx + 1 + TX - 3) / (TX - 2), (p->ny + 1 + TY - 3) / (TY - 2));
-    const size_t smem = (p->vc ? 16 : 11) * NT * 8;
-    if (p->vc) {
-        if (diag) k_stokes2d<true, true><<<grd, blk, smem, ctx->stream>>>(k, p->pt);
-        else k_stokes2d<true, false><<<grd, blk, smem, ctx->stream>>>(k, p->pt);
-    } else {
-        if (diag) k_stokes2d<false, true><<<grd, blk, smem, ctx->stream>>>(k, p->pt);
-        else k_stokes2d<false, false><<<grd, blk, smem, ctx->stream>>>(k, p->pt);
+    const int ty = p->ty;
+    dim3 blk(TX, ty), grd((p->nx + 1 + TX - 3) / (TX - 2), (p->ny + 1 + ty - 3) / (ty - 2));
+    const size_t smem = (size_t)(p->vc ? 16 : 11) * TX * ty * 8;
+#define X(T_)                                                                                              \
+    if (ty == T_) {                                                                                        \
+        if (p->vc) {                                                                                       \
+            if (diag) k_stokes2d<true, true, T_><<<grd, blk, smem, ctx->stream>>>(k, p->pt);               \
+            else k_stokes2d<true, false, T_><<<grd, blk, smem, ctx->stream>>>(k, p->pt);                   \
+        } else {                                                                                           \
+            if (diag) k_stokes2d<false, true, T_><<<grd, blk, smem, ctx->stream>>>(k, p->pt);              \
+            else k_stokes2d<false, false, T_><<<grd, blk, smem, ctx->stream>>>(k, p->pt);                  \
+        }                                                                                                  \
     }
+    K2_TILES(X)
+#undef X
     ctx->launches++;
     JR_CHECK_LAUNCH();
     if (p->periodic) {
