@@ -36,7 +36,19 @@ struct V3 {
     const double *T, *Pargs, *ph_c, *ph_xy, *ph_yz, *ph_xz;
     double *divV, *RP, *pxx, *pyy, *pzz, *pyz, *pxz, *pxy, *tII, *eta_vep, *e_vol_pl, *Rx, *Ry, *Rz;
     int pf_next;   // L2 prefetch of the next plane's operands (JRB200_VC3_PREFETCH, default on)
+    int xfull_c, xfull_n;   // block columns with full 32-wide tiles for the cell (nx) and node (nx+1) lattices; a further block
+                            // column, if launched, packs the few remainder columns densely (nx = 257: 1 cell / 2 node columns)
 };
+// thread → 1-based (i, j): block columns < xfull are ordinary 32 × 8 tiles, block column xfull packs the n0 − 32·xfull remainder columns
+__device__ __forceinline__ void vc3_map_ij(int n0, int xfull, int &i, int &j)
+{
+    if ((int)blockIdx.x < xfull) {
+        i = blockIdx.x * 32 + threadIdx.x + 1; j = blockIdx.y * 8 + threadIdx.y + 1;
+    } else {
+        const int rem = n0 - xfull * 32, lin = blockIdx.y * 256 + threadIdx.y * 32 + threadIdx.x, jj = lin / rem;
+        i = xfull * 32 + (lin - jj * rem) + 1; j = jj + 1;
+    }
+}
 __device__ __forceinline__ void jr_prefetch_l2(const double *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 #define CC(A, i, j, k) (A)[IX3(nx, ny, i, j, k)]
@@ -57,7 +69,9 @@ template <bool DIAG, bool MAXLOC, int NP>
 __global__ void __launch_bounds__(256, JR_PREP_MINB) k_vc3_prep(const __grid_constant__ V3 a, const __grid_constant__ jr_phase_tab pt)
 {
     const int nx = a.nx, ny = a.ny, nz = a.nz;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x + 1, j = blockIdx.y * blockDim.y + threadIdx.y + 1, k = blockIdx.z + 1;
+    int i, j;
+    vc3_map_ij(nx, a.xfull_c, i, j);
+    const int k = blockIdx.z + 1;
     if (i > nx || j > ny || k > nz) return;
     const size_t nc = (size_t)nx * ny * nz, c = IX3(nx, ny, i, j, k);
     if (a.pf_next && k + 2 <= nz) {
@@ -334,7 +348,9 @@ template <bool DIAG, int NP>
 __device__ __forceinline__ void vc3_stress_body(const V3 &a, const jr_phase_tab &pt)
 {
     const int nx = a.nx, ny = a.ny, nz = a.nz;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x + 1, j = blockIdx.y * blockDim.y + threadIdx.y + 1, k = blockIdx.z + 1;
+    int i, j;
+    vc3_map_ij(nx + 1, a.xfull_n, i, j);
+    const int k = blockIdx.z + 1;
     if (i > nx + 1 || j > ny + 1 || k > nz + 1) return;
     const size_t nc = (size_t)nx * ny * nz, nyz = (size_t)nx * (ny + 1) * (nz + 1), nxz = (size_t)(nx + 1) * ny * (nz + 1),
                  nxy = (size_t)(nx + 1) * (ny + 1) * nz;
@@ -643,7 +659,9 @@ template <bool DIAG>
 __global__ void __launch_bounds__(256) k_vc3_vel(const __grid_constant__ V3 a)
 {
     const int nx = a.nx, ny = a.ny, nz = a.nz;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x + 1, j = blockIdx.y * blockDim.y + threadIdx.y + 1, k = blockIdx.z + 1;
+    int i, j;
+    vc3_map_ij(nx, a.xfull_c, i, j);
+    const int k = blockIdx.z + 1;
     if (i > nx || j > ny || k > nz) return;
     const double *P = a.P, *ett = a.etatau, *txx = a.txx_o, *tyy = a.tyy_o, *tzz = a.tzz_o, *tyz = a.tyz_o, *txz = a.txz_o, *txy = a.txy_o;
     if (a.pf_next && k + 2 <= nz) {
@@ -784,6 +802,14 @@ static int check3d_vc(const jr_fields *s, const jr_stokes_opts *o, const jr_vc_i
 }
 
 static inline dim3 grid3(int nx, int ny, int nz) { return dim3((nx + 31) / 32, (ny + 7) / 8, nz); }
+// remainder-column packing (vc3_map_ij): few (≤ 8) columns beyond the last full 32-wide tile are packed densely into one extra block column
+static inline int xfull_of(int n0)
+{
+    static const bool on = !(getenv("JRB200_VC3_PACK") && atoi(getenv("JRB200_VC3_PACK")) == 0);
+    const int rem = n0 % 32;
+    return (on && rem > 0 && rem <= 8 && n0 >= 32) ? n0 / 32 : (n0 + 31) / 32;
+}
+static inline dim3 grid3p(int n0, int n1, int n2, int xfull) { return dim3(xfull * 32 < n0 ? xfull + 1 : xfull, (n1 + 7) / 8, n2); }
 static const dim3 BLK3(32, 8, 1);
 
 static int plan3_begin(jr_context *ctx, const jr_fields *s, const jr_stokes_opts *o, const jr_vc_inputs *in, Plan3 *p)
@@ -819,6 +845,7 @@ static int plan3_begin(jr_context *ctx, const jr_fields *s, const jr_stokes_opts
         const char *e = getenv("JRB200_VC3_PREFETCH");
         k.pf_next = (e && atoi(e) == 0) ? 0 : 1;
     }
+    k.xfull_c = xfull_of(k.nx); k.xfull_n = xfull_of(k.nx + 1);
     k.Vx = F(Vx); k.Vy = F(Vy); k.Vz = F(Vz); k.theta = (double *)(B + o_th); k.P = F(P); k.P0 = F(P0); k.Q = F(Q); k.etatau = F(etatau);
     k.exx = F(exx); k.eyy = F(eyy); k.ezz = F(ezz); k.eyz = F(eyz); k.exz = F(exz); k.exy = F(exy);
     k.tyzc = F(tyz_c); k.txzc = F(txz_c); k.txyc = F(txy_c);
@@ -913,8 +940,8 @@ static int plan3_iter(jr_context *ctx, Plan3 *p, int64_t it, bool diag, const jr
         const jr_harr H = jr_harr_dense(k.etatau, p->n, p->n);
         if ((rc = jr_comm_halo(ctx, &H, 1))) return rc;
     }
-    launch_prep(diag, !p->multi, p->pt.n, grid3(nx, ny, nz), st, k, p->pt);
-    launch_stress(diag, p->pt.n, grid3(nx + 1, ny + 1, nz + 1), st, k, p->pt);
+    launch_prep(diag, !p->multi, p->pt.n, grid3p(nx, ny, nz, k.xfull_c), st, k, p->pt);
+    launch_stress(diag, p->pt.n, grid3p(nx + 1, ny + 1, nz + 1, k.xfull_n), st, k, p->pt);
     ctx->launches += 2;
     JR_CHECK_LAUNCH();
     if (p->multi) {  // update_halo!(τyz); update_halo!(τxz); update_halo!(τxy)  :578-580
@@ -922,8 +949,8 @@ static int plan3_iter(jr_context *ctx, Plan3 *p, int64_t it, bool diag, const jr
         const jr_harr H[3] = {jr_harr_dense(k.tyz_o, eyz, p->n), jr_harr_dense(k.txz_o, exz, p->n), jr_harr_dense(k.txy_o, exy, p->n)};
         if ((rc = jr_comm_halo(ctx, H, 3))) return rc;
     }
-    if (diag) k_vc3_vel<true><<<grid3(nx, ny, nz), BLK3, 0, st>>>(k);
-    else k_vc3_vel<false><<<grid3(nx, ny, nz), BLK3, 0, st>>>(k);
+    if (diag) k_vc3_vel<true><<<grid3p(nx, ny, nz, k.xfull_c), BLK3, 0, st>>>(k);
+    else k_vc3_vel<false><<<grid3p(nx, ny, nz, k.xfull_c), BLK3, 0, st>>>(k);
     ctx->launches++;
     const size_t nVx = (size_t)(nx + 1) * (ny + 2) * (nz + 2), nVy = (size_t)(nx + 2) * (ny + 1) * (nz + 2), nVz = (size_t)(nx + 2) * (ny + 2) * (nz + 1);
     if (diag && F(Ux) && F(Uy) && F(Uz)) {  // velocity2displacement!(stokes, dt) BEFORE flow_bcs!  :594

@@ -365,6 +365,7 @@ struct ThPP {
     const double *T_in, *th_in, *q_in[3];
     double *T_out, *th_out, *q_out[3];
     int kchunk;
+    int xfull;   // block columns that hold full 32-column tiles; block column xfull (if any) packs the nx mod 32 remainder columns
 };
 // the flux expression of th_flux_dim (compute_flux!, DiffusionPT_kernels.jl:6-158)
 __device__ __forceinline__ double th_flux_pt(double q_old, double K, double Tl, double Th, double thL, double thR, double _d)
@@ -379,7 +380,16 @@ __global__ void __launch_bounds__(256, MINB) k_th_fused3(const __grid_constant__
 {
     const ThDims &d = a.d;
     const int nx = d.nx, ny = d.ny, nz = d.nz;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y;
+    // thread → column (i, j).  Full 32-column tiles: a warp = one x-row of the tile.  The nx mod 32 remainder columns (nx = 257: ONE
+    // column, which would otherwise cost a ninth of the CTAs at 1/32 lane use) are packed densely into the CTAs of block column
+    // `pp.xfull` — uncoalesced, but rem/nx of the cells.
+    int i, j;
+    if ((int)blockIdx.x < pp.xfull) {
+        i = blockIdx.x * 32 + threadIdx.x; j = blockIdx.y * 8 + threadIdx.y;
+    } else {
+        const int rem = nx - pp.xfull * 32, lin = blockIdx.y * 256 + threadIdx.y * 32 + threadIdx.x;
+        j = lin / rem; i = pp.xfull * 32 + (lin - j * rem);
+    }
     if (i >= nx || j >= ny) return;
     const int k0 = blockIdx.z * pp.kchunk, k1 = min(k0 + pp.kchunk, nz);
     if (k0 >= k1) return;
@@ -694,6 +704,9 @@ struct ThFused {
     double *Tb = nullptr, *thb = nullptr, *qb[3] = {nullptr, nullptr, nullptr};
     int kchunk = 12;
     bool prefetch = true;
+    bool pack_rem = false;  // pack the nx mod 32 remainder columns (JRB200_TH_PACK=1).  Measured at 257³: 0.653 ms against 0.602 ms plain —
+                            // the packed column's z-marching CTAs run uncoalesced for their whole chunk and become the tail; the same
+                            // packing pays in the one-plane-per-CTA 3D-VC kernels
     int minb = 4;   // resident CTAs per SM the kernel is compiled for (2: 115 registers, 3: 78, 4: 64 — still no spills —, 5: 48 with spills)
 };
 static int th_fused_prepare(jr_context *ctx, ThArgs &a, ThFused &F)
@@ -706,6 +719,7 @@ static int th_fused_prepare(jr_context *ctx, ThArgs &a, ThFused &F)
     F.pt_dyn = a.form == 1 && a.f.phase_c;
     if (const char *e = getenv("JRB200_TH_KCHUNK")) F.kchunk = atoi(e) > 0 ? atoi(e) : F.kchunk;
     if (const char *e = getenv("JRB200_TH_PREFETCH")) F.prefetch = atoi(e) != 0;
+    if (const char *e = getenv("JRB200_TH_PACK")) F.pack_rem = atoi(e) != 0;
     if (const char *e = getenv("JRB200_TH_MINB")) F.minb = (atoi(e) >= 2 && atoi(e) <= 5) ? atoi(e) : F.minb;
     const size_t nc = (size_t)d.nx * d.ny * d.nz, ng = (size_t)d.gx * d.gy * d.gz;
     const size_t nfx = (size_t)(d.nx + 1) * d.ny * d.nz, nfy = (size_t)d.nx * (d.ny + 1) * d.nz, nfz = (size_t)d.nx * d.ny * (d.nz + 1);
@@ -733,7 +747,11 @@ static int th_fused_launch(jr_context *ctx, const ThArgs &a, const ThFused &F, b
     if (F.pt_dyn) { pp.th_in = a_to_b ? a.f.theta_r_dtau : F.thb; pp.th_out = a_to_b ? F.thb : a.f.theta_r_dtau; }
     else { pp.th_in = a.f.theta_r_dtau; pp.th_out = a.f.theta_r_dtau; }
     pp.kchunk = F.kchunk;
-    dim3 blk(32, 8, 1), grid((d.nx + 31) / 32, (d.ny + 7) / 8, (d.nz + F.kchunk - 1) / F.kchunk);
+    // remainder columns are packed when they are few (else the last block column is an ordinary, partly filled tile)
+    const int rem = d.nx % 32;
+    const bool pack = F.pack_rem && rem > 0 && rem <= 8 && d.nx >= 32;
+    pp.xfull = pack ? d.nx / 32 : (d.nx + 31) / 32;
+    dim3 blk(32, 8, 1), grid(pack ? pp.xfull + 1 : pp.xfull, (d.ny + 7) / 8, (d.nz + F.kchunk - 1) / F.kchunk);
     const bool pf = F.prefetch;
 #define TH_LAUNCH_B(FORM_, NP_, B_)                                                                 \
     do {                                                                                            \
