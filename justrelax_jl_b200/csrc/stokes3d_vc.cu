@@ -576,7 +576,12 @@ __global__ void __launch_bounds__(32 * TYS, 16 / TYS) k_vc3_stress_sm(const __gr
         jr_prefetch_l2(a.oyzc + c + sc); jr_prefetch_l2(a.oxzc + c + sc); jr_prefetch_l2(a.oxyc + c + sc);
         jr_prefetch_l2(a.lam + c + sc); jr_prefetch_l2(a.lamyz + vyz + syz); jr_prefetch_l2(a.lamxz + vxz + sxz); jr_prefetch_l2(a.lamxy + vxy + sxy);
     }
-    double ryz[NP], rxz[NP], rxy[NP];
+    double ryz[NP], rxz[NP], rxy[NP], rc[NP];
+    ratios_load<NP>(pt, a.ph_c, nc, c, rc);
+    // the centre's own-position operands, also in flight behind the copies (the centre is updated FIRST below, so they are consumed
+    // before the three edges need the registers)
+    const double c_tyz = a.tyzc[c], c_txz = a.txzc[c], c_txy = a.txyc[c];
+    const double c_oyz = __ldg(a.oyzc + c), c_oxz = __ldg(a.oxzc + c), c_oxy = __ldg(a.oxyc + c);
     ratios_load<NP>(pt, a.ph_yz, nyz, vyz, ryz);
     ratios_load<NP>(pt, a.ph_xz, nxz, vxz, rxz);
     ratios_load<NP>(pt, a.ph_xy, nxy, vxy, rxy);
@@ -599,6 +604,17 @@ __global__ void __launch_bounds__(32 * TYS, 16 / TYS) k_vc3_stress_sm(const __gr
 #define SAV_XZ_Z(s) (0.25 * (S(s, 0, 0, 0) + S(s, 0, 1, 0) + S(s, 0, 0, 1) + S(s, 0, 1, 1)))   /* xy family: (ic,jc,k0),(ic,j1,k0),(ic,jc,kc),(ic,j1,kc) */
 #define SAV_XY_X(s) (0.25 * (S(s, 0, 0, 0) + S(s, 1, 0, 0) + S(s, 0, 0, 1) + S(s, 1, 0, 1)))   /* yz family: (i0,jc,kc),(ic,jc,kc),(i0,jc,k1),(ic,jc,k1) */
 #define SAV_XY_Y(s) (0.25 * (S(s, 0, 0, 0) + S(s, 0, 1, 0) + S(s, 0, 0, 1) + S(s, 0, 1, 1)))   /* xz family: (ic,j0,kc),(ic,jc,kc),(ic,j0,k1),(ic,jc,k1) */
+    {   // ---- centre: cell (i, j, k) = S(·, 1, 1, 1); edge gathers in mysum order (quirk Q15)
+        const double eij[6] = {S(SL_exx, 1, 1, 1), S(SL_eyy, 1, 1, 1), S(SL_ezz, 1, 1, 1),
+                               0.25 * ((((0.0 + S(SL_eyz, 1, 0, 0)) + S(SL_eyz, 1, 1, 0)) + S(SL_eyz, 1, 0, 1)) + S(SL_eyz, 1, 1, 1)),
+                               0.25 * ((((0.0 + S(SL_exz, 0, 1, 0)) + S(SL_exz, 1, 1, 0)) + S(SL_exz, 0, 1, 1)) + S(SL_exz, 1, 1, 1)),
+                               0.25 * ((((0.0 + S(SL_exy, 0, 0, 1)) + S(SL_exy, 1, 0, 1)) + S(SL_exy, 0, 1, 1)) + S(SL_exy, 1, 1, 1))};
+        double tij[6] = {S(SL_txx, 1, 1, 1), S(SL_tyy, 1, 1, 1), S(SL_tzz, 1, 1, 1), c_tyz, c_txz, c_txy};
+        const double tijo[6] = {S(SL_oxx, 1, 1, 1), S(SL_oyy, 1, 1, 1), S(SL_ozz, 1, 1, 1), c_oyz, c_oxz, c_oxy};
+        Mix<NP> mc;
+        mix_from<NP>(pt, rc, mc);
+        vc3_centre<DIAG, NP>(a, pt, mc, c, S(SL_eta, 1, 1, 1), S(SL_theta, 1, 1, 1), eij, tij, tijo);
+    }
     // ---- the three edges advance together (straight-line code: three independent dependency chains), then the plastic branches
     Mix<NP> myz, mxz, mxy;
     mix_from<NP>(pt, ryz, myz);
@@ -634,17 +650,6 @@ __global__ void __launch_bounds__(32 * TYS, 16 / TYS) k_vc3_stress_sm(const __gr
     edge_finish<DIAG, NP>(a, pt, myz, Eyz, vyz, a.lamyz, a.tyz_o, a.pyz);
     edge_finish<DIAG, NP>(a, pt, mxz, Exz, vxz, a.lamxz, a.txz_o, a.pxz);
     edge_finish<DIAG, NP>(a, pt, mxy, Exy, vxy, a.lamxy, a.txy_o, a.pxy);
-    {   // ---- centre: cell (i, j, k) = S(·, 1, 1, 1); edge gathers in mysum order (quirk Q15)
-        const double eij[6] = {S(SL_exx, 1, 1, 1), S(SL_eyy, 1, 1, 1), S(SL_ezz, 1, 1, 1),
-                               0.25 * ((((0.0 + S(SL_eyz, 1, 0, 0)) + S(SL_eyz, 1, 1, 0)) + S(SL_eyz, 1, 0, 1)) + S(SL_eyz, 1, 1, 1)),
-                               0.25 * ((((0.0 + S(SL_exz, 0, 1, 0)) + S(SL_exz, 1, 1, 0)) + S(SL_exz, 0, 1, 1)) + S(SL_exz, 1, 1, 1)),
-                               0.25 * ((((0.0 + S(SL_exy, 0, 0, 1)) + S(SL_exy, 1, 0, 1)) + S(SL_exy, 0, 1, 1)) + S(SL_exy, 1, 1, 1))};
-        double tij[6] = {S(SL_txx, 1, 1, 1), S(SL_tyy, 1, 1, 1), S(SL_tzz, 1, 1, 1), a.tyzc[c], a.txzc[c], a.txyc[c]};
-        const double tijo[6] = {S(SL_oxx, 1, 1, 1), S(SL_oyy, 1, 1, 1), S(SL_ozz, 1, 1, 1), __ldg(a.oyzc + c), __ldg(a.oxzc + c), __ldg(a.oxyc + c)};
-        Mix<NP> mc;
-        mix_load<NP>(pt, a.ph_c, nc, c, mc);
-        vc3_centre<DIAG, NP>(a, pt, mc, c, S(SL_eta, 1, 1, 1), S(SL_theta, 1, 1, 1), eij, tij, tijo);
-    }
 #undef S
 }
 
