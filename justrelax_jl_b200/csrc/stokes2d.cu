@@ -34,6 +34,7 @@ struct K2 {
 };
 
 __device__ __forceinline__ double inv2(double xx, double yy, double xy) { return sqrt(0.5 * (xx * xx + yy * yy) + xy * xy); }
+__device__ __forceinline__ void jr_prefetch_l1(const double *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // TYT = threads in y (tile height incl. the one-node rim): chosen per grid so that the CTA count fills whole waves (plan2_tile)
 template <bool VC, bool DIAG, int TYT>
@@ -55,6 +56,15 @@ __global__ void __launch_bounds__(TX * TYT) k_stokes2d(const __grid_constant__ K
            *s_txx = sm + 11 * NTT, *s_tyy = sm + 12 * NTT, *s_txxo = sm + 13 * NTT, *s_tyyo = sm + 14 * NTT, *s_eta = sm + 15 * NTT;
 
     // ---------------- stage 1: ητ, ∇V, P|θ, ε (centres) and εxy (vertices) ------------------------------------------------------
+    if (VC) {
+        // operands that are only read in stage 2 (after the first barrier): pull their lines into L1 now, so those loads do not expose
+        // a DRAM round trip in the middle of the CTA (no registers held)
+        if (vert) {
+            jr_prefetch_l1(a.txy_i + v); jr_prefetch_l1(a.txyo + v); jr_prefetch_l1(a.lamv_i + v);
+            for (int p = 0; p < pt.n; p++) jr_prefetch_l1(a.ph_v + (size_t)p * nv + v);
+        }
+        if (cell) { jr_prefetch_l1(a.txyc_i + c); jr_prefetch_l1(a.txyco + c); jr_prefetch_l1(a.lam_i + c); }
+    }
     double divV = 0.0, RP = 0.0, thn = 0.0, exx = 0.0, eyy = 0.0, exy = 0.0, ett = 0.0, eta = 0.0, rgx = 0.0, rgy = 0.0;
     double txx = 0.0, tyy = 0.0, txxo = 0.0, tyyo = 0.0, Kc = 0.0, Gc = 0.0;
     if (cell) {

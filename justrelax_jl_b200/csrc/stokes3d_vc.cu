@@ -89,6 +89,11 @@ __global__ void __launch_bounds__(256, JR_PREP_MINB) k_vc3_prep(const __grid_con
         }
     }
     const double eta = __ldg(a.eta_i + c);
+    // every operand is requested before the first store (V, P0, Q, T, P are read-only here: ld.global.nc lets the compiler hoist them;
+    // θ is read-modify-write by this thread only)
+    const double th_in = a.theta[c], P0c = __ldg(a.P0 + c), Qc = __ldg(a.Q + c);
+    const double Targ = (!pt.rho_const && a.T) ? __ldg(a.T + IX3(nx + 2, ny + 2, i + 1, j + 1, k + 1)) : 0.0;
+    const double Parg = (!pt.rho_const && a.Pargs) ? __ldg(a.Pargs + c) : 0.0;
     double ett;
     if (MAXLOC) {  // compute_maxloc!(ητ, η)  Stokes3D.jl:514 ; Utils.jl:409-461 (window clamped to the array)
         const int sy = nx, sz = nx * ny;
@@ -114,10 +119,11 @@ __global__ void __launch_bounds__(256, JR_PREP_MINB) k_vc3_prep(const __grid_con
     const double *__restrict__ pVx = a.Vx + IX3(nx + 1, ny + 2, i, j + 1, k + 1);
     const double *__restrict__ pVy = a.Vy + IX3(nx + 2, ny + 1, i + 1, j, k + 1);
     const double *__restrict__ pVz = a.Vz + IX3(nx + 2, ny + 2, i + 1, j + 1, k);
-    const double vx0 = pVx[0], vy0 = pVy[0], vz0 = pVz[0];
-    const double dVx = (-vx0 + pVx[1]) * a._dx;
-    const double dVy = (-vy0 + pVy[ysy]) * a._dy;
-    const double dVz = (-vz0 + pVz[zsz]) * a._dz;
+    const double vx0 = __ldg(pVx), vy0 = __ldg(pVy), vz0 = __ldg(pVz);
+    const double dVx = (-vx0 + __ldg(pVx + 1)) * a._dx;
+    const double dVy = (-vy0 + __ldg(pVy + ysy)) * a._dy;
+    const double dVz = (-vz0 + __ldg(pVz + zsz)) * a._dz;
+    const double vyB = __ldg(pVy - ysz), vzS = __ldg(pVz - zsy), vxB = __ldg(pVx - xsz), vzW = __ldg(pVz - 1), vxS = __ldg(pVx - xsy), vyW = __ldg(pVy - 1);
     const double divV = dVx + dVy + dVz;
     // phase ratios at the centre, loaded once
     double r[NP];
@@ -128,20 +134,20 @@ __global__ void __launch_bounds__(256, JR_PREP_MINB) k_vc3_prep(const __grid_con
 #pragma unroll
     for (int p = 0; p < NP; p++)
         if (p < pt.n) { Kc += (r[p] == 0.0) ? 0.0 : pt.Kb[p] * r[p]; Gc += (r[p] == 0.0) ? 0.0 : pt.G[p] * r[p]; }
-    double RP, th = a.theta[c];
-    jr_compute_P_point(RP, th, a.P0[c], divV, a.Q[c], ett, Kc, Gc, a.dt, a.r, a.th);
+    double RP, th = th_in;
+    jr_compute_P_point(RP, th, P0c, divV, Qc, ett, Kc, Gc, a.dt, a.r, a.th);
     a.theta[c] = th;
     // compute_strain_rate! over ni (quirk Q20)  Stokes3D.jl:533-535 ; VelocityKernels.jl:59-104
     const double d3 = divV * jr_inv(3.0);
     a.exx[c] = dVx - d3;
     a.eyy[c] = dVy - d3;
     a.ezz[c] = dVz - d3;
-    YZ(a.eyz, i, j, k) = 0.5 * (a._dz * (vy0 - pVy[-ysz]) + a._dy * (vz0 - pVz[-zsy]));
-    XZ(a.exz, i, j, k) = 0.5 * (a._dz * (vx0 - pVx[-xsz]) + a._dx * (vz0 - pVz[-1]));
-    XY(a.exy, i, j, k) = 0.5 * (a._dy * (vx0 - pVx[-xsy]) + a._dx * (vy0 - pVy[-1]));
+    YZ(a.eyz, i, j, k) = 0.5 * (a._dz * (vy0 - vyB) + a._dy * (vz0 - vzS));
+    XZ(a.exz, i, j, k) = 0.5 * (a._dz * (vx0 - vxB) + a._dx * (vz0 - vzW));
+    XY(a.exy, i, j, k) = 0.5 * (a._dy * (vx0 - vxS) + a._dx * (vy0 - vyW));
     // update_ρg!  Stokes3D.jl:538 ; BuoyancyForces.jl:38-60 (args.T sampled at I+1, quirk Q17); fn_ratio with args: a ratio == 1 returns that phase
     if (!pt.rho_const) {
-        const double Tc = a.T ? a.T[IX3(nx + 2, ny + 2, i + 1, j + 1, k + 1)] : 0.0, Pc = a.Pargs ? a.Pargs[c] : 0.0;
+        const double Tc = Targ, Pc = Parg;
         double rho = 0.0;
         bool done = false;
 #pragma unroll
@@ -297,7 +303,7 @@ __device__ __forceinline__ void vc3_edge(const V3 &a, const jr_phase_tab &pt, co
 // eij / tij / tijo: strain rate, stress, old stress at the centre in Voigt order (shear: 4-edge averages / centre copies)
 template <bool DIAG, int NP>
 __device__ __forceinline__ void vc3_centre(const V3 &a, const jr_phase_tab &pt, const Mix<NP> &m, size_t c, double et, double Pr, const double (&eij)[6],
-                                           double (&tij)[6], const double (&tijo)[6])
+                                           double (&tij)[6], const double (&tijo)[6], double lam_in)
 {
     const double _Gdt = jr_inv(m.G * a.dt), K = m.Kb;
     const double dtr = jr_inv(a.th + et * _Gdt + 1.0);
@@ -310,7 +316,7 @@ __device__ __forceinline__ void vc3_centre(const V3 &a, const jr_phase_tab &pt, 
     double tII = jr_second_invariant<6>(trial);
     double dQdP, dFdP;
     mix_dP<NP>(pt, m, dQdP, dFdP);
-    double lam = a.lam[c], evol = 0.0, epl[3] = {0.0, 0.0, 0.0};
+    double lam = lam_in, evol = 0.0, epl[3] = {0.0, 0.0, 0.0};   // lam_in = a.lam[c], loaded by the caller (early in the staged kernel)
     double Fc = 0.0;
     if (m.is_pl && tII != 0.0) Fc = mix_yield_F<NP>(pt, m, Pr, tII);
     if (m.is_pl && tII != 0.0 && Fc > 0) {
@@ -415,7 +421,7 @@ __device__ __forceinline__ void vc3_stress_body(const V3 &a, const jr_phase_tab 
         const double tijo[6] = {__ldg(a.oxx + c), __ldg(a.oyy + c), __ldg(a.ozz + c), __ldg(a.oyzc + c), __ldg(a.oxzc + c), __ldg(a.oxyc + c)};
         Mix<NP> m;
         mix_load<NP>(pt, a.ph_c, nc, c, m);
-        vc3_centre<DIAG, NP>(a, pt, m, c, __ldg(eta + c), a.theta[c], eij, tij, tijo);
+        vc3_centre<DIAG, NP>(a, pt, m, c, __ldg(eta + c), a.theta[c], eij, tij, tijo, a.lam[c]);
     }
 }
 
@@ -581,7 +587,7 @@ __global__ void __launch_bounds__(32 * TYS, 16 / TYS) k_vc3_stress_sm(const __gr
     // the centre's own-position operands, also in flight behind the copies (the centre is updated FIRST below, so they are consumed
     // before the three edges need the registers)
     const double c_tyz = a.tyzc[c], c_txz = a.txzc[c], c_txy = a.txyc[c];
-    const double c_oyz = __ldg(a.oyzc + c), c_oxz = __ldg(a.oxzc + c), c_oxy = __ldg(a.oxyc + c);
+    const double c_oyz = __ldg(a.oyzc + c), c_oxz = __ldg(a.oxzc + c), c_oxy = __ldg(a.oxyc + c), c_lam = a.lam[c];
     ratios_load<NP>(pt, a.ph_yz, nyz, vyz, ryz);
     ratios_load<NP>(pt, a.ph_xz, nxz, vxz, rxz);
     ratios_load<NP>(pt, a.ph_xy, nxy, vxy, rxy);
@@ -613,7 +619,7 @@ __global__ void __launch_bounds__(32 * TYS, 16 / TYS) k_vc3_stress_sm(const __gr
         const double tijo[6] = {S(SL_oxx, 1, 1, 1), S(SL_oyy, 1, 1, 1), S(SL_ozz, 1, 1, 1), c_oyz, c_oxz, c_oxy};
         Mix<NP> mc;
         mix_from<NP>(pt, rc, mc);
-        vc3_centre<DIAG, NP>(a, pt, mc, c, S(SL_eta, 1, 1, 1), S(SL_theta, 1, 1, 1), eij, tij, tijo);
+        vc3_centre<DIAG, NP>(a, pt, mc, c, S(SL_eta, 1, 1, 1), S(SL_theta, 1, 1, 1), eij, tij, tijo, c_lam);
     }
     // ---- the three edges advance together (straight-line code: three independent dependency chains), then the plastic branches
     Mix<NP> myz, mxz, mxy;
@@ -677,26 +683,32 @@ __global__ void __launch_bounds__(256) k_vc3_vel(const __grid_constant__ V3 a)
         jr_prefetch_l2(&XY(txy, i + 1, j + 1, k + 2)); jr_prefetch_l2(&XZ(txz, i + 1, j, k + 3)); jr_prefetch_l2(&YZ(tyz, i, j + 1, k + 3));
         jr_prefetch_l2(&VX(i + 1, j + 1, k + 3)); jr_prefetch_l2(&VY(i + 1, j + 1, k + 3)); jr_prefetch_l2(&VZ(i + 1, j + 1, k + 3));
     }
-    const double Pc = CC(P, i, j, k), ec = CC(ett, i, j, k);
-    const double xy11 = XY(txy, i + 1, j + 1, k), xz11 = XZ(txz, i + 1, j, k + 1), yz11 = YZ(tyz, i, j + 1, k + 1);
+    // read-only operands go through ld.global.nc (LD(...)): the compiler may then issue all of them before the first V store
+#define LD(x) __ldg(&(x))
+    const double Pc = LD(CC(P, i, j, k)), ec = LD(CC(ett, i, j, k));
+    const double xy11 = LD(XY(txy, i + 1, j + 1, k)), xz11 = LD(XZ(txz, i + 1, j, k + 1)), yz11 = LD(YZ(tyz, i, j + 1, k + 1));
     if (i <= nx - 1) {
-        const double R = (-CC(txx, i, j, k) + CC(txx, i + 1, j, k)) * a._dx + a._dy * (xy11 - XY(txy, i + 1, j, k)) + a._dz * (xz11 - XZ(txz, i + 1, j, k)) -
-                         (-Pc + CC(P, i + 1, j, k)) * a._dx - 0.5 * (CC(a.rgx, i, j, k) + CC(a.rgx, i + 1, j, k));
+        const double R = (-LD(CC(txx, i, j, k)) + LD(CC(txx, i + 1, j, k))) * a._dx + a._dy * (xy11 - LD(XY(txy, i + 1, j, k))) +
+                         a._dz * (xz11 - LD(XZ(txz, i + 1, j, k))) - (-Pc + LD(CC(P, i + 1, j, k))) * a._dx -
+                         0.5 * (LD(CC(a.rgx, i, j, k)) + LD(CC(a.rgx, i + 1, j, k)));
         if (DIAG) a.Rx[IX3(nx - 1, ny, i, j, k)] = R;
-        VX(i + 1, j + 1, k + 1) += R * a.edt / (0.5 * (ec + CC(ett, i + 1, j, k)));
+        VX(i + 1, j + 1, k + 1) += R * a.edt / (0.5 * (ec + LD(CC(ett, i + 1, j, k))));
     }
     if (j <= ny - 1) {
-        const double R = a._dx * (xy11 - XY(txy, i, j + 1, k)) + a._dy * (CC(tyy, i, j + 1, k) - CC(tyy, i, j, k)) + a._dz * (yz11 - YZ(tyz, i, j + 1, k)) -
-                         (-Pc + CC(P, i, j + 1, k)) * a._dy - 0.5 * (CC(a.rgy, i, j, k) + CC(a.rgy, i, j + 1, k));
+        const double R = a._dx * (xy11 - LD(XY(txy, i, j + 1, k))) + a._dy * (LD(CC(tyy, i, j + 1, k)) - LD(CC(tyy, i, j, k))) +
+                         a._dz * (yz11 - LD(YZ(tyz, i, j + 1, k))) - (-Pc + LD(CC(P, i, j + 1, k))) * a._dy -
+                         0.5 * (LD(CC(a.rgy, i, j, k)) + LD(CC(a.rgy, i, j + 1, k)));
         if (DIAG) a.Ry[IX3(nx, ny - 1, i, j, k)] = R;
-        VY(i + 1, j + 1, k + 1) += R * a.edt / (0.5 * (ec + CC(ett, i, j + 1, k)));
+        VY(i + 1, j + 1, k + 1) += R * a.edt / (0.5 * (ec + LD(CC(ett, i, j + 1, k))));
     }
     if (k <= nz - 1) {
-        const double R = a._dx * (xz11 - XZ(txz, i, j, k + 1)) + a._dy * (yz11 - YZ(tyz, i, j, k + 1)) + (-CC(tzz, i, j, k) + CC(tzz, i, j, k + 1)) * a._dz -
-                         (-Pc + CC(P, i, j, k + 1)) * a._dz - 0.5 * (CC(a.rgz, i, j, k) + CC(a.rgz, i, j, k + 1));
+        const double R = a._dx * (xz11 - LD(XZ(txz, i, j, k + 1))) + a._dy * (yz11 - LD(YZ(tyz, i, j, k + 1))) +
+                         (-LD(CC(tzz, i, j, k)) + LD(CC(tzz, i, j, k + 1))) * a._dz - (-Pc + LD(CC(P, i, j, k + 1))) * a._dz -
+                         0.5 * (LD(CC(a.rgz, i, j, k)) + LD(CC(a.rgz, i, j, k + 1)));
         if (DIAG) a.Rz[IX3(nx, ny, i, j, k)] = R;
-        VZ(i + 1, j + 1, k + 1) += R * a.edt / (0.5 * (ec + CC(ett, i, j, k + 1)));
+        VZ(i + 1, j + 1, k + 1) += R * a.edt / (0.5 * (ec + LD(CC(ett, i, j, k + 1))));
     }
+#undef LD
 }
 
 // compute_ρg! 3D stand-alone  BuoyancyForces.jl:38-60
