@@ -56,11 +56,12 @@ __global__ void __launch_bounds__(TX * TYT) k_stokes2d(const __grid_constant__ K
            *s_txx = sm + 11 * NTT, *s_tyy = sm + 12 * NTT, *s_txxo = sm + 13 * NTT, *s_tyyo = sm + 14 * NTT, *s_eta = sm + 15 * NTT;
 
     // ---------------- stage 1: ητ, ∇V, P|θ, ε (centres) and εxy (vertices) ------------------------------------------------------
+    // operands that are only read in stage 2 (after the first barrier): pull their lines into L1 now, so those loads do not expose
+    // a DRAM / L2 round trip in the middle of the CTA (no registers held)
+    if (vert) { jr_prefetch_l1(a.txy_i + v); jr_prefetch_l1(a.txyo + v); }
     if (VC) {
-        // operands that are only read in stage 2 (after the first barrier): pull their lines into L1 now, so those loads do not expose
-        // a DRAM round trip in the middle of the CTA (no registers held)
         if (vert) {
-            jr_prefetch_l1(a.txy_i + v); jr_prefetch_l1(a.txyo + v); jr_prefetch_l1(a.lamv_i + v);
+            jr_prefetch_l1(a.lamv_i + v);
             for (int p = 0; p < pt.n; p++) jr_prefetch_l1(a.ph_v + (size_t)p * nv + v);
         }
         if (cell) { jr_prefetch_l1(a.txyc_i + c); jr_prefetch_l1(a.txyco + c); jr_prefetch_l1(a.lam_i + c); }
