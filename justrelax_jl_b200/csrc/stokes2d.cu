@@ -62,6 +62,7 @@ __global__ void __launch_bounds__(TX * TYT) k_stokes2d(const __grid_constant__ K
     if (VC) {
         if (vert) {
             jr_prefetch_l1(a.lamv_i + v);
+            if (a.etav_o) jr_prefetch_l1(a.etav_i + v);
             for (int p = 0; p < pt.n; p++) jr_prefetch_l1(a.ph_v + (size_t)p * nv + v);
         }
         if (cell) { jr_prefetch_l1(a.txyc_i + c); jr_prefetch_l1(a.txyco + c); jr_prefetch_l1(a.lam_i + c); }

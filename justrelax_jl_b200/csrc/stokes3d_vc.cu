@@ -685,6 +685,10 @@ __global__ void __launch_bounds__(256) k_vc3_vel(const __grid_constant__ V3 a)
     }
     // read-only operands go through ld.global.nc (LD(...)): the compiler may then issue all of them before the first V store
 #define LD(x) __ldg(&(x))
+    // the three velocities this thread updates are read BEFORE its first store (a later read-modify-write could not be hoisted above an
+    // earlier store it might alias: three dependent DRAM round trips otherwise)
+    const double vx_old = i <= nx - 1 ? VX(i + 1, j + 1, k + 1) : 0.0, vy_old = j <= ny - 1 ? VY(i + 1, j + 1, k + 1) : 0.0,
+                 vz_old = k <= nz - 1 ? VZ(i + 1, j + 1, k + 1) : 0.0;
     const double Pc = LD(CC(P, i, j, k)), ec = LD(CC(ett, i, j, k));
     const double xy11 = LD(XY(txy, i + 1, j + 1, k)), xz11 = LD(XZ(txz, i + 1, j, k + 1)), yz11 = LD(YZ(tyz, i, j + 1, k + 1));
     if (i <= nx - 1) {
@@ -692,21 +696,21 @@ __global__ void __launch_bounds__(256) k_vc3_vel(const __grid_constant__ V3 a)
                          a._dz * (xz11 - LD(XZ(txz, i + 1, j, k))) - (-Pc + LD(CC(P, i + 1, j, k))) * a._dx -
                          0.5 * (LD(CC(a.rgx, i, j, k)) + LD(CC(a.rgx, i + 1, j, k)));
         if (DIAG) a.Rx[IX3(nx - 1, ny, i, j, k)] = R;
-        VX(i + 1, j + 1, k + 1) += R * a.edt / (0.5 * (ec + LD(CC(ett, i + 1, j, k))));
+        VX(i + 1, j + 1, k + 1) = vx_old + R * a.edt / (0.5 * (ec + LD(CC(ett, i + 1, j, k))));
     }
     if (j <= ny - 1) {
         const double R = a._dx * (xy11 - LD(XY(txy, i, j + 1, k))) + a._dy * (LD(CC(tyy, i, j + 1, k)) - LD(CC(tyy, i, j, k))) +
                          a._dz * (yz11 - LD(YZ(tyz, i, j + 1, k))) - (-Pc + LD(CC(P, i, j + 1, k))) * a._dy -
                          0.5 * (LD(CC(a.rgy, i, j, k)) + LD(CC(a.rgy, i, j + 1, k)));
         if (DIAG) a.Ry[IX3(nx, ny - 1, i, j, k)] = R;
-        VY(i + 1, j + 1, k + 1) += R * a.edt / (0.5 * (ec + LD(CC(ett, i, j + 1, k))));
+        VY(i + 1, j + 1, k + 1) = vy_old + R * a.edt / (0.5 * (ec + LD(CC(ett, i, j + 1, k))));
     }
     if (k <= nz - 1) {
         const double R = a._dx * (xz11 - LD(XZ(txz, i, j, k + 1))) + a._dy * (yz11 - LD(YZ(tyz, i, j, k + 1))) +
                          (-LD(CC(tzz, i, j, k)) + LD(CC(tzz, i, j, k + 1))) * a._dz - (-Pc + LD(CC(P, i, j, k + 1))) * a._dz -
                          0.5 * (LD(CC(a.rgz, i, j, k)) + LD(CC(a.rgz, i, j, k + 1)));
         if (DIAG) a.Rz[IX3(nx, ny, i, j, k)] = R;
-        VZ(i + 1, j + 1, k + 1) += R * a.edt / (0.5 * (ec + LD(CC(ett, i, j, k + 1))));
+        VZ(i + 1, j + 1, k + 1) = vz_old + R * a.edt / (0.5 * (ec + LD(CC(ett, i, j, k + 1))));
     }
 #undef LD
 }
