@@ -230,6 +230,52 @@ def shearband2d(n=32):
                            ratios=ratios, nt=10, kwargs=dict(verbose=False, iterMax=50.0e3, nout=1.0e2, viscosity_cutoff=(-math.inf, math.inf)))
 
 
+def sinking_block2d(n=32, *, nsub=8):
+    """test/test_sinking_block.jl:93-200 (variant 2D-VC with buoyancy, SI units): 500 km square, mantle (LinearViscous η = 1e21,
+    ConstantDensity 3200) with a 100 km square block (η = 1e23, ρ = 3300) centred at x = 250 km, depth 100 km; no elasticity (G = Kb = Inf),
+    g = 9.81, lithostatic initial pressure, free slip, dt = 1, PTStokesCoeffs(li, di; ϵ_rel = 1e-5, CFL = 0.95/√2.1),
+    kwargs = (iterMax = 150e3, nout = 1e3).  The reference builds the phase ratios from JustPIC particles (20–40 per cell); here they are
+    the volume fractions of nsub² sub-samples per cell (hat-weighted at the vertices)."""
+    from . import rheology as R
+
+    ly = 500.0e3
+    ni, li = (n, n), (ly, ly)
+    grid = Geometry(ni, li, origin=(0.0, -ly))
+    di = grid.di.center
+    rheology = (R.SetMaterialParams(Phase=1, Density=R.ConstantDensity(ρ=3.2e3), Gravity=R.ConstantGravity(g=9.81),
+                                    CompositeRheology=R.CompositeRheology((R.LinearViscous(η=1.0e21),))),
+                R.SetMaterialParams(Phase=2, Density=R.ConstantDensity(ρ=3.3e3), Gravity=R.ConstantGravity(g=9.81),
+                                    CompositeRheology=R.CompositeRheology((R.LinearViscous(η=1.0e23),))))
+    xc_a, depth_a, r_a = 250.0e3, 100.0e3, 50.0e3
+    inside = lambda X, Y: ((X - xc_a) ** 2 <= r_a ** 2) & ((-Y - depth_a) ** 2 <= r_a ** 2)
+
+    def ratios(x, y, hat):
+        off = (np.arange(nsub) + 0.5) / nsub - 0.5
+        if hat:
+            off = off * 2.0
+        acc, wsum = np.zeros((x.size, y.size)), 0.0
+        for ox in off:
+            for oy in off:
+                w = (1.0 - abs(ox)) * (1.0 - abs(oy)) if hat else 1.0
+                X, Y = np.meshgrid(x + ox * di[0], y + oy * di[1], indexing="ij")
+                acc += w * inside(X, Y)
+                wsum += w
+        f2 = acc / wsum
+        return _onehot([1.0 - f2, f2])
+
+    (xc, yc), (xv, yv) = grid.xci, grid.xvi
+    rat = dict(center=np.asfortranarray(ratios(xc, yc, False)), vertex=np.asfortranarray(ratios(xv, yv, True)))
+    rho = rat["center"][..., 0] * 3.2e3 + rat["center"][..., 1] * 3.3e3
+    rhogy = np.asfortranarray(rho * 9.81)                                   # compute_ρg!(ρg[2], phase_ratios, rheology, args)
+    P = np.asfortranarray(rhogy * np.abs(yc)[None, :])                      # init_P!: P = ρg·|z|
+    pt = PTStokesCoeffs(li, di, ϵ_rel=1.0e-5, CFL=0.95 / math.sqrt(2.1))
+    flow_bcs = VelocityBoundaryConditions(free_slip=dict(left=True, right=True, top=True, bot=True),
+                                          no_slip=dict(left=False, right=False, top=False, bot=False))
+    fields = dict(P=P, rhogy=rhogy, T=np.ones((n + 2, n + 2), order="F"))
+    return SimpleNamespace(ni=ni, li=li, di=di, grid=grid, igg=IGG(), pt_stokes=pt, flow_bcs=flow_bcs, dt=1.0, fields=fields, rheology=rheology,
+                           ratios=rat, kwargs=dict(verbose=False, iterMax=150.0e3, nout=1.0e3, viscosity_cutoff=(-math.inf, math.inf)))
+
+
 # ------------------------------------------------------------------------------------------------------------
 def _onehot(mask_list):
     """stack boolean masks into a ratio array (nodes..., nphases), column-major"""

@@ -202,6 +202,28 @@ def test_shearband2d_reference_golden_on_gpu(oracle):
     compare_slots(st.slots(), d, ["Vx", "Vy", "P", "txx", "tyy", "txy", "EII_pl"], 1.0e-6, "shear band final fields")
 
 
+def test_sinking_block_reference_golden_on_gpu(oracle):
+    """test/test_sinking_block.jl through the public API: 2D-VC with buoyancy in SI units (η = 1e21 | 1e23, G = Kb = Inf, P ~ 1e10):
+    the oracle's iteration count and fields, and the reference's golden maximum velocity."""
+    from justrelax_jl_b200 import B200Backend, PhaseRatios, setups, stokes as jst, to_host
+    from test_oracle_stokes2d import run_sinking_block, vertex_speed
+
+    s = setups.sinking_block2d(32)
+    d, out_o = run_sinking_block(oracle, s)
+    d0 = oracle.alloc_stokes(s.ni, s.fields)
+    st, extra = device_stokes(s.ni, d0)
+    pr = PhaseRatios.from_arrays(B200Backend, **s.ratios)
+    args = dict(T=extra["T"], P=st.P)
+    jst.compute_viscosity_(st, pr, args, s.rheology, (-math.inf, math.inf))
+    jst.flow_bcs_(st, s.flow_bcs)
+    out = jst.solve_(st, s.pt_stokes, s.grid, s.flow_bcs, (extra["rhogx"], extra["rhogy"]), pr, s.rheology, args, s.dt, s.igg, kwargs=s.kwargs)
+    assert out.err_evo1[-1] < 1.0e-5
+    assert out.iter == out_o["iter"]
+    vmax = vertex_speed(to_host(st.V.Vx), to_host(st.V.Vy)).max()
+    assert abs(vmax - 4.841885609356093e-10) < 1.0e-6 and abs(vmax / 4.841885609356093e-10 - 1) < 0.1
+    compare_slots(st.slots(), d, ["Vx", "Vy", "P", "txx", "tyy", "txy"], 1.0e-8, "sinking block converged fields")
+
+
 def test_standalone_2d_kernels(oracle):
     from justrelax_jl_b200 import B200Backend, PTArray, StokesArrays, stokes as jst, to_host
 

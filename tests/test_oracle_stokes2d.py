@@ -44,6 +44,40 @@ def test_shearband2d_reference_golden(oracle):
     assert d["EII_pl"].max() > 0 and d["lam"].max() > 0
 
 
+def run_sinking_block(oracle, s):
+    d = oracle.alloc_stokes(s.ni, s.fields)
+    rows = R.lower_stokes(s.rheology)
+    vc = oracle.vc_inputs(rows, R.gravity_of(s.rheology), s.ratios)
+    kw = s.kwargs
+    opts = oracle.make_opts(s.pt_stokes, s.grid._di.center, s.dt, bc_flags(s.flow_bcs), s.ni, iterMax=kw["iterMax"], nout=kw["nout"],
+                            viscosity_cutoff=kw["viscosity_cutoff"])
+    fs = oracle.make_fields(d, s.ni)
+    oracle.lib().orc_viscosity2d(C.byref(fs), C.byref(opts), C.byref(vc), C.c_double(1.0))   # compute_viscosity!  test_sinking_block.jl:158
+    oracle.lib().orc_flow_bcs2(C.byref(fs), C.byref(opts), 0)
+    out = oracle.solve2d_VC(d, s.ni, opts, vc)
+    return d, out
+
+
+def vertex_speed(Vx, Vy):
+    """velocity2vertex! (2D) + √(Vx_v² + Vy_v²)  test_sinking_block.jl:192-195"""
+    Vx_v = 0.5 * (Vx[:, :-1] + Vx[:, 1:])
+    Vy_v = 0.5 * (Vy[:-1, :] + Vy[1:, :])
+    return np.sqrt(Vx_v ** 2 + Vy_v ** 2)
+
+
+def test_sinking_block_reference_golden(oracle):
+    """test/test_sinking_block.jl:202-208: 2D-VC with buoyancy in SI units, no elasticity (G = Kb = Inf): converges below 1e-5 and
+    maximum(velocity) ≈ 4.841885609356093e-10 (atol 1e-6 in the reference; the restatement lands within a few per cent)"""
+    s = setups.sinking_block2d(32)
+    d, out = run_sinking_block(oracle, s)
+    assert out["status"] == 0 and out["err_evo1"][-1] < 1.0e-5 and out["iter"] < s.kwargs["iterMax"]
+    vmax = vertex_speed(d["Vx"], d["Vy"]).max()
+    assert abs(vmax - 4.841885609356093e-10) < 1.0e-6
+    assert abs(vmax / 4.841885609356093e-10 - 1) < 0.1, vmax
+    # the block sinks: Vy < 0 at the block centre (x = 250 km, depth = 100 km)
+    assert d["Vy"][17, 26] < 0
+
+
 def test_solcx_reference_golden(oracle):
     s = setups.solcx2d(32, 32)
     d = oracle.alloc_stokes(s.ni, s.fields)
