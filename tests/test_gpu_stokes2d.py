@@ -224,6 +224,17 @@ def test_sinking_block_reference_golden_on_gpu(oracle):
     compare_slots(st.slots(), d, ["Vx", "Vy", "P", "txx", "tyy", "txy"], 1.0e-8, "sinking block converged fields")
 
 
+def test_compute_dt_reference_kat():
+    """test/test_Utils.jl:146-148: ni = (4, 4), di = (0.25, 0.25), Vx = 0, Vy = 10 → compute_dt === 0.022500000000000003"""
+    from justrelax_jl_b200 import B200Backend, StokesArrays, stokes as jst
+
+    st = StokesArrays(B200Backend, 4, 4)
+    st.V.Vy.fill_(10.0)
+    di = (0.25, 0.25)
+    assert jst.compute_dt_(st, di, 0.1) == 0.022500000000000003
+    assert jst.compute_dt_(st, di) == 0.022500000000000003
+
+
 def test_standalone_2d_kernels(oracle):
     from justrelax_jl_b200 import B200Backend, PTArray, StokesArrays, stokes as jst, to_host
 

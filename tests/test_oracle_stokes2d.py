@@ -78,6 +78,21 @@ def test_sinking_block_reference_golden(oracle):
     assert d["Vy"][17, 26] < 0
 
 
+def test_continuation_linear_kat(oracle):
+    """test/test_Utils.jl:150: continuation_linear(1.0, 0.8, 0.05) === 0.81 — the viscosity relaxation of update_viscosity_τII!
+    (Viscosity.jl:382-418: η ← clamp((1 − ν)·η + ν·η_GP)) with η = 0.8, a single LinearViscous phase of η = 1, ν = 0.05"""
+    ni = (4, 4)
+    rheo = (R.SetMaterialParams(Phase=1, Density=R.ConstantDensity(ρ=1.0), CompositeRheology=R.CompositeRheology((R.LinearViscous(η=1.0),))),)
+    ratios = dict(center=np.ones(ni + (1,), order="F"), vertex=np.ones((5, 5, 1), order="F"))
+    d = oracle.alloc_stokes(ni, dict(eta=np.full(ni, 0.8, order="F")))
+    vc = oracle.vc_inputs(R.lower_stokes(rheo), R.gravity_of(rheo), ratios)
+    pt = setups.PTStokesCoeffs((1.0, 1.0), (0.25, 0.25))
+    opts = oracle.make_opts(pt, (4.0, 4.0), 1.0, dict(free_slip=[1] * 6), ni, iterMax=1, nout=1)
+    fs = oracle.make_fields(d, ni)
+    oracle.lib().orc_viscosity2d(C.byref(fs), C.byref(opts), C.byref(vc), C.c_double(0.05))
+    assert np.all(d["eta"] == 0.81)
+
+
 def test_solcx_reference_golden(oracle):
     s = setups.solcx2d(32, 32)
     d = oracle.alloc_stokes(s.ni, s.fields)
