@@ -189,6 +189,31 @@ def solcx2d(nx=64, ny=64, *, Δη=1.0e6, lx=1.0, ly=1.0):
                            kwargs=dict(iterMax=500e3, nout=5e3, verbose=False))
 
 
+def elastic_buildup2d(n=32, *, lx=100.0e3, ly=100.0e3, endtime=10, η0=1.0e21, εbg=1.0e-14, G=10.0e9):
+    """test/test_stokes_elastic_buildup.jl:24-53 + miniapps/benchmarks/stokes2D/elastic_buildup/Elastic_BuildUp.jl:19-108 (variant 2D-V2 with
+    finite G and dt, K = Inf): uniform η0, pure shear εbg (pureshear_bc!, src/boundaryconditions/pure_shear.jl:1-9), free slip, no gravity,
+    PTStokesCoeffs(li, di; ϵ_abs = ϵ_rel = 1e-6, CFL = 1/√2.1), kwargs = (iterMax = 150e3, nout = 1000); time steps of 0.05 kyr below
+    10 kyr (1 kyr above).  Analytic stress: τ(t) = 2 εbg η0 (1 − exp(−G t / η0)); the reference test wants the mean relative error of
+    max|τyy| over the steps ≤ 5e-3."""
+    ni, li = (n, n), (lx, ly)
+    grid = Geometry(ni, li, origin=(0.0, 0.0))
+    di = grid.di.center
+    pt = PTStokesCoeffs(li, di, ϵ_abs=1.0e-6, ϵ_rel=1.0e-6, CFL=1 / math.sqrt(2.1))
+    (xc, yc), (xv, yv) = grid.xci, grid.xvi
+    Vx = np.zeros((n + 1, n + 2), order="F")
+    Vy = np.zeros((n + 2, n + 1), order="F")
+    Vx[:, 1:-1] = (εbg * xv)[:, None] * np.ones((1, n))
+    Vy[1:-1, :] = np.ones((n, 1)) * (-εbg * yv)[None, :]
+    kyr = 1.0e3 * 365.25 * 3600 * 24
+    flow_bcs = VelocityBoundaryConditions(free_slip=dict(left=True, right=True, top=True, bot=True))
+    fields = dict(Vx=Vx, Vy=Vy, eta=np.full(ni, η0, order="F"), rhogx=np.zeros(ni, order="F"), rhogy=np.zeros(ni, order="F"),
+                  G=np.full(ni, G, order="F"), K=np.full(ni, np.inf, order="F"))
+    dt_of = lambda t: 0.05 * kyr if t < 10 * kyr else 1.0 * kyr
+    solution = lambda t: 2 * εbg * η0 * (1 - math.exp(-G * t / η0))
+    return SimpleNamespace(ni=ni, li=li, di=di, grid=grid, igg=IGG(), pt_stokes=pt, flow_bcs=flow_bcs, fields=fields, ttot=endtime * kyr,
+                           dt_of=dt_of, solution=solution, kwargs=dict(iterMax=150.0e3, nout=1000, verbose=False))
+
+
 def shearband2d(n=32):
     """Config 3 — test/test_shearband2D.jl:61-192 (variant 2D-VC): unit square, two phases (matrix G = 1, inclusion r = 0.1 with
     G = 0.5, Kb = 4), η = 1, DruckerPrager_regularised(C = 1.6/cosd(30), ϕ = 30, η_vp = 8e-3, Ψ = 0), dt = 0.25, pure shear

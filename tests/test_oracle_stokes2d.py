@@ -78,6 +78,32 @@ def test_sinking_block_reference_golden(oracle):
     assert d["Vy"][17, 26] < 0
 
 
+def run_elastic_buildup(oracle, s, solve=None):
+    """the time loop of Elastic_BuildUp.jl:74-103 on the oracle; returns (fields, max|τyy| per step, analytic values, iterations per step)"""
+    d = oracle.alloc_stokes(s.ni, s.fields)
+    opts0 = oracle.make_opts(s.pt_stokes, s.grid._di.center, 1.0, bc_flags(s.flow_bcs), s.ni, iterMax=s.kwargs["iterMax"], nout=s.kwargs["nout"])
+    fs = oracle.make_fields(d, s.ni)
+    oracle.lib().orc_flow_bcs2(C.byref(fs), C.byref(opts0), 0)
+    t, av, sol, iters = 0.0, [], [], []
+    while t < s.ttot:
+        dt = s.dt_of(t)
+        opts = oracle.make_opts(s.pt_stokes, s.grid._di.center, dt, bc_flags(s.flow_bcs), s.ni, iterMax=s.kwargs["iterMax"], nout=s.kwargs["nout"])
+        out = oracle.solve2d_V2(d, s.ni, opts)
+        assert out["status"] == 0
+        t += dt
+        av.append(np.abs(d["tyy"]).max()); sol.append(s.solution(t)); iters.append(out["iter"])
+    return d, np.array(av), np.array(sol), iters
+
+
+def test_elastic_buildup_reference_criterion(oracle):
+    """test/test_stokes_elastic_buildup.jl:24-53: visco-elastic stress build-up under pure shear (2D-V2 with finite G and dt): the mean
+    relative error of max|τyy| against 2 εbg η0 (1 − exp(−G t/η0)) over the 200 steps is ≤ 5e-3"""
+    s = setups.elastic_buildup2d(32)
+    d, av, sol, iters = run_elastic_buildup(oracle, s)
+    err = np.mean(np.abs(np.abs(av) - sol) / sol)
+    assert len(av) == 200 and err <= 5.0e-3, err
+
+
 def test_continuation_linear_kat(oracle):
     """test/test_Utils.jl:150: continuation_linear(1.0, 0.8, 0.05) === 0.81 — the viscosity relaxation of update_viscosity_τII!
     (Viscosity.jl:382-418: η ← clamp((1 − ν)·η + ν·η_GP)) with η = 0.8, a single LinearViscous phase of η = 1, ν = 0.05"""
