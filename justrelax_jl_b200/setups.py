@@ -88,6 +88,73 @@ def solvi3d(nx=31, ny=31, nz=31, *, Δη=1.0e-3, lx=1.0e1, ly=1.0e1, lz=1.0e1, r
                            fields=fields, kwargs=dict(iterMax=5000, nout=100, verbose=False))
 
 
+def burstedde3d(n=16, *, β=10.0):
+    """test/test_stokes_burstedde.jl:28-40 + miniapps/benchmarks/stokes3D/burstedde/Burstedde.jl (variant 3D-VA, dt = Inf, G = K = Inf):
+    the manufactured solution of Burstedde et al. (2013) on the unit cube — η = exp(1 − β(x(1−x) + y(1−y) + z(1−z))), body force from the
+    analytical velocity / pressure, the analytical velocity prescribed on every face and ghost layer (no face is free-slip or no-slip, so
+    flow_bcs! leaves them untouched), net boundary flux removed, PTStokesCoeffs(li, di; CFL = 1/√3), kwargs = (iterMax = 100e3, nout = 1e3)."""
+    ni, li = (n, n, n), (1.0, 1.0, 1.0)
+    grid = Geometry(ni, li, origin=(0.0, 0.0, 0.0))
+    di = grid.di.center
+    (xc, yc, zc), (xv, yv, zv) = grid.xci, grid.xvi
+    X, Y, Z = np.meshgrid(xc, yc, zc, indexing="ij")
+    η = np.exp(1 - β * (X * (1 - X) + Y * (1 - Y) + Z * (1 - Z)))
+    dηdx, dηdy, dηdz = -β * (1 - 2 * X) * η, -β * (1 - 2 * Y) * η, -β * (1 - 2 * Z) * η
+    fx = ((Y * Z + 3 * X ** 2 * Y ** 3 * Z) - η * (2 + 6 * X * Y)) - dηdx * (2 + 4 * X + 2 * Y + 6 * X ** 2 * Y) \
+        - dηdy * (X + X ** 3 + Y + 2 * X * Y ** 2) - dηdz * (-3 * Z - 10 * X * Y * Z)
+    fy = ((X * Z + 3 * X ** 3 * Y ** 2 * Z) - η * (2 + 2 * X ** 2 + 2 * Y ** 2)) - dηdx * (X + X ** 3 + Y + 2 * X * Y ** 2) \
+        - dηdy * (2 + 2 * X + 4 * Y + 4 * X ** 2 * Y) - dηdz * (-3 * Z - 5 * X ** 2 * Z)
+    fz = ((X * Y + X ** 3 * Y ** 3) - η * (-10 * Y * Z)) - dηdx * (-3 * Z - 10 * X * Y * Z) - dηdy * (-3 * Z - 5 * X ** 2 * Z) \
+        - dηdz * (-4 - 6 * X - 6 * Y - 10 * X ** 2 * Y)
+    vx = lambda x, y: x + x ** 2 + x * y + x ** 3 * y
+    vy = lambda x, y: y + x * y + y ** 2 + x ** 2 * y ** 2
+    vz = lambda x, y, z: -2 * z - 3 * x * z - 3 * y * z - 5 * x ** 2 * y * z
+    # ghosted centre coordinates: LinRange(xci[1] − d, xci[end] + d, n + 2)   Burstedde.jl:44-48
+    gc = [np.linspace(c[0] - d, c[-1] + d, c.size + 2) for c, d in zip((xc, yc, zc), di)]
+
+    def shell(shape, values):
+        A = np.zeros(shape, order="F")
+        m = np.zeros(shape, dtype=bool)
+        for ax in range(3):
+            idx = [slice(None)] * 3
+            for side in (0, -1):
+                idx[ax] = side
+                m[tuple(idx)] = True
+        A[m] = values[m]
+        return A
+
+    Vx = shell((n + 1, n + 2, n + 2), vx(xv[:, None, None], gc[1][None, :, None]) * np.ones((1, 1, n + 2)))
+    Vy = shell((n + 2, n + 1, n + 2), vy(gc[0][:, None, None], yv[None, :, None]) * np.ones((1, 1, n + 2)))
+    Vz = shell((n + 2, n + 2, n + 1), vz(gc[0][:, None, None], gc[1][None, :, None], zv[None, None, :]))
+    # remove_net_flux!  Burstedde.jl:100-122
+    dx, dy, dz = di
+    Ax, Ay, Az = dy * dz, dx * dz, dx * dy
+    flux = ((Vx[-1, 1:-1, 1:-1].sum() - Vx[0, 1:-1, 1:-1].sum()) * Ax + (Vy[1:-1, -1, 1:-1].sum() - Vy[1:-1, 0, 1:-1].sum()) * Ay
+            + (Vz[1:-1, 1:-1, -1].sum() - Vz[1:-1, 1:-1, 0].sum()) * Az)
+    δ = flux / (2 * (n * n * Ax + n * n * Ay + n * n * Az))
+    Vx[0, :, :] += δ; Vx[-1, :, :] -= δ
+    Vy[:, 0, :] += δ; Vy[:, -1, :] -= δ
+    Vz[:, :, 0] += δ; Vz[:, :, -1] -= δ
+    none = dict(left=False, right=False, top=False, bot=False, back=False, front=False)
+    flow_bcs = VelocityBoundaryConditions(free_slip=dict(none), no_slip=dict(none))
+    F = np.asfortranarray
+    fields = dict(Vx=Vx, Vy=Vy, Vz=Vz, eta=F(η), G=np.full(ni, np.inf, order="F"), K=np.full(ni, np.inf, order="F"),
+                  rhogx=F(-fx), rhogy=F(-fy), rhogz=F(-fz))
+
+    def error_norms(Vx_, Vy_, Vz_, P_):
+        """vizBurstedde.jl error_norms: √(Σ e² ΔV) against the analytical fields, pressures with their mean removed"""
+        dV = dx * dy * dz
+        L2 = lambda e: math.sqrt(float(np.sum(e * e)) * dV)
+        ax_ = vx(xv[:, None, None], yc[None, :, None]) * np.ones((1, 1, n))
+        ay_ = vy(xc[:, None, None], yv[None, :, None]) * np.ones((1, 1, n))
+        az_ = vz(xc[:, None, None], yc[None, :, None], zv[None, None, :])
+        p = X * Y * Z + X ** 3 * Y ** 3 * Z - 5 / 32
+        return (L2((P_ - P_.mean()) - (p - p.mean())), L2(Vx_[:, 1:-1, 1:-1] - ax_), L2(Vy_[1:-1, :, 1:-1] - ay_), L2(Vz_[1:-1, 1:-1, :] - az_))
+
+    return SimpleNamespace(ni=ni, li=li, di=di, grid=grid, igg=IGG(), pt_stokes=PTStokesCoeffs(li, di, CFL=1 / math.sqrt(3)), flow_bcs=flow_bcs,
+                           dt=math.inf, fields=fields, error_norms=error_norms, kwargs=dict(iterMax=100.0e3, nout=1.0e3, verbose=False))
+
+
 def random_stokes3d(ni, seed=20261017, *, dt=0.7, finite_K=True, const_rhog=None):
     """Seeded random state for kernel-level parity fuzzing of variant 3D-VA:
     V, τ ~ U(−1,1), P ~ U(0,1), η ~ 10^U(−3,0), G ~ U(0.5,2), K ~ U(1,4) (or Inf), ρg ~ U(−1,1)."""

@@ -34,6 +34,31 @@ def test_solvi3d_reference_golden(oracle):
         assert np.array_equal(d["t" + c], d["t" + c + "_o"])
 
 
+def run_burstedde(oracle, n):
+    s = setups.burstedde3d(n)
+    d = oracle.alloc_stokes(s.ni, s.fields)
+    opts = oracle.make_opts(s.pt_stokes, s.grid._di.center, s.dt, bc_flags(s.flow_bcs), s.ni, iterMax=s.kwargs["iterMax"], nout=s.kwargs["nout"])
+    fs = oracle.make_fields(d, s.ni)
+    oracle.lib().orc_flow_bcs3(C.byref(fs), C.byref(opts), 0)  # flow_bcs! with no active face: leaves the prescribed values  Burstedde.jl:166
+    out = oracle.solve3d_VA(d, s.ni, opts)
+    return s, d, out
+
+
+def test_burstedde_reference_criteria(oracle):
+    """test/test_stokes_burstedde.jl:28-40: the manufactured solution of Burstedde et al. at 8³ and 16³ (3D-VA, variable η over 2.8 decades,
+    spatially varying body force, velocity prescribed on every face): PT converges below 1e-8, velocity errors converge with order > 1.4,
+    max L2 velocity error < 3e-2 and L2 pressure error < 2e-1 at 16³"""
+    errs = []
+    for n in (8, 16):
+        s, d, out = run_burstedde(oracle, n)
+        assert out["status"] == 0 and out["err_evo1"][-1] < 1.0e-8, (n, out["err_evo1"][-1])
+        errs.append(s.error_norms(d["Vx"], d["Vy"], d["Vz"], d["P"]))
+    order = np.log2(np.array(errs[0]) / np.array(errs[1]))
+    L2_p, L2_vx, L2_vy, L2_vz = errs[1]
+    assert np.all(order[1:] > 1.4), order
+    assert max(L2_vx, L2_vy, L2_vz) < 3.0e-2 and L2_p < 2.0e-1, errs[1]
+
+
 def test_maxloc_hotspot(oracle):
     # test_Utils.jl:387-397 analogue in 3D: a single hotspot spreads to its 3x3x3 neighbourhood
     A = np.ones((5, 5, 5), order="F")
