@@ -155,6 +155,56 @@ def burstedde3d(n=16, *, β=10.0):
                            dt=math.inf, fields=fields, error_norms=error_norms, kwargs=dict(iterMax=100.0e3, nout=1.0e3, verbose=False))
 
 
+def taylor_green3d(n=16):
+    """test/test_stokes_taylor_green.jl:29-40 + miniapps/benchmarks/stokes3D/taylor_green/TaylorGreen.jl (variant 3D-VA, η = 1, dt = Inf,
+    G = K = Inf): the FVCA8 Taylor-Green Stokes solution on the unit cube — V = (−2 cos2πx sin2πy sin2πz, sin2πx cos2πy sin2πz,
+    sin2πx sin2πy cos2πz), P = −6π sin2πx sin2πy sin2πz, ρg_x = 36π² cos2πx sin2πy sin2πz; the analytical velocity is prescribed on every
+    face and ghost layer (no free-slip / no-slip face), PTStokesCoeffs(li, di; CFL = 1/√3), kwargs = (iterMax = 100e3, nout = 1e3)."""
+    ni, li = (n, n, n), (1.0, 1.0, 1.0)
+    grid = Geometry(ni, li, origin=(0.0, 0.0, 0.0))
+    di = grid.di.center
+    (xc, yc, zc), (xv, yv, zv) = grid.xci, grid.xvi
+    tp = 2 * math.pi
+    X, Y, Z = np.meshgrid(xc, yc, zc, indexing="ij")
+    vx = lambda x, y, z: -2 * np.cos(tp * x) * np.sin(tp * y) * np.sin(tp * z)
+    vy = lambda x, y, z: np.sin(tp * x) * np.cos(tp * y) * np.sin(tp * z)
+    vz = lambda x, y, z: np.sin(tp * x) * np.sin(tp * y) * np.cos(tp * z)
+    gc = [np.linspace(c[0] - d, c[-1] + d, c.size + 2) for c, d in zip((xc, yc, zc), di)]
+
+    def shell(values):
+        A = np.zeros(values.shape, order="F")
+        m = np.zeros(values.shape, dtype=bool)
+        for ax in range(3):
+            idx = [slice(None)] * 3
+            for side in (0, -1):
+                idx[ax] = side
+                m[tuple(idx)] = True
+        A[m] = values[m]
+        return A
+
+    Vx = shell(vx(xv[:, None, None], gc[1][None, :, None], gc[2][None, None, :]))
+    Vy = shell(vy(gc[0][:, None, None], yv[None, :, None], gc[2][None, None, :]))
+    Vz = shell(vz(gc[0][:, None, None], gc[1][None, :, None], zv[None, None, :]))
+    none = dict(left=False, right=False, top=False, bot=False, back=False, front=False)
+    flow_bcs = VelocityBoundaryConditions(free_slip=dict(none), no_slip=dict(none))
+    F = np.asfortranarray
+    fx = 36 * math.pi ** 2 * np.cos(tp * X) * np.sin(tp * Y) * np.sin(tp * Z)
+    fields = dict(Vx=Vx, Vy=Vy, Vz=Vz, eta=np.ones(ni, order="F"), G=np.full(ni, np.inf, order="F"), K=np.full(ni, np.inf, order="F"),
+                  rhogx=F(fx), rhogy=np.zeros(ni, order="F"), rhogz=np.zeros(ni, order="F"))
+    dx, dy, dz = di
+
+    def error_norms(Vx_, Vy_, Vz_, P_):
+        dV = dx * dy * dz
+        L2 = lambda e: math.sqrt(float(np.sum(e * e)) * dV)
+        p = -6 * math.pi * np.sin(tp * X) * np.sin(tp * Y) * np.sin(tp * Z)
+        return (L2((P_ - P_.mean()) - (p - p.mean())), L2(Vx_[:, 1:-1, 1:-1] - vx(xv[:, None, None], yc[None, :, None], zc[None, None, :])),
+                L2(Vy_[1:-1, :, 1:-1] - vy(xc[:, None, None], yv[None, :, None], zc[None, None, :])),
+                L2(Vz_[1:-1, 1:-1, :] - vz(xc[:, None, None], yc[None, :, None], zv[None, None, :])))
+
+    return SimpleNamespace(ni=ni, li=li, di=di, grid=grid, igg=IGG(), pt_stokes=PTStokesCoeffs(li, di, CFL=1 / math.sqrt(3)), flow_bcs=flow_bcs,
+                           dt=math.inf, fields=fields, error_norms=error_norms, kwargs=dict(iterMax=100.0e3, nout=1.0e3, verbose=False))
+
+
 def random_stokes3d(ni, seed=20261017, *, dt=0.7, finite_K=True, const_rhog=None):
     """Seeded random state for kernel-level parity fuzzing of variant 3D-VA:
     V, τ ~ U(−1,1), P ~ U(0,1), η ~ 10^U(−3,0), G ~ U(0.5,2), K ~ U(1,4) (or Inf), ρg ~ U(−1,1)."""

@@ -34,8 +34,8 @@ def test_solvi3d_reference_golden(oracle):
         assert np.array_equal(d["t" + c], d["t" + c + "_o"])
 
 
-def run_burstedde(oracle, n):
-    s = setups.burstedde3d(n)
+def run_burstedde(oracle, n, setup=None):
+    s = (setup or setups.burstedde3d)(n)
     d = oracle.alloc_stokes(s.ni, s.fields)
     opts = oracle.make_opts(s.pt_stokes, s.grid._di.center, s.dt, bc_flags(s.flow_bcs), s.ni, iterMax=s.kwargs["iterMax"], nout=s.kwargs["nout"])
     fs = oracle.make_fields(d, s.ni)
@@ -57,6 +57,20 @@ def test_burstedde_reference_criteria(oracle):
     L2_p, L2_vx, L2_vy, L2_vz = errs[1]
     assert np.all(order[1:] > 1.4), order
     assert max(L2_vx, L2_vy, L2_vz) < 3.0e-2 and L2_p < 2.0e-1, errs[1]
+
+
+def test_taylor_green_reference_criteria(oracle):
+    """test/test_stokes_taylor_green.jl:29-40: the FVCA8 Taylor-Green Stokes solution at 8³ and 16³ (3D-VA, η = 1, body force in x only):
+    PT converges below 1e-8, all four errors converge with order > 1.7, max L2 velocity error < 5e-3 and L2 pressure error < 1.5e-1 at 16³"""
+    errs = []
+    for n in (8, 16):
+        s, d, out = run_burstedde(oracle, n, setups.taylor_green3d)
+        assert out["status"] == 0 and out["err_evo1"][-1] < 1.0e-8, (n, out["err_evo1"][-1])
+        errs.append(s.error_norms(d["Vx"], d["Vy"], d["Vz"], d["P"]))
+    order = np.log2(np.array(errs[0]) / np.array(errs[1]))
+    L2_p, L2_vx, L2_vy, L2_vz = errs[1]
+    assert np.all(order > 1.7), order
+    assert max(L2_vx, L2_vy, L2_vz) < 5.0e-3 and L2_p < 1.5e-1, errs[1]
 
 
 def test_maxloc_hotspot(oracle):
