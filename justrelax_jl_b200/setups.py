@@ -306,6 +306,22 @@ def solcx2d(nx=64, ny=64, *, Δη=1.0e6, lx=1.0, ly=1.0):
                            kwargs=dict(iterMax=500e3, nout=5e3, verbose=False))
 
 
+def solkz2d(nx=32, ny=32, *, Δη=1.0e6):
+    """test/test_stokes_solkz.jl:26-37 + miniapps/benchmarks/stokes2D/solkz/SolKz.jl:4-101 (variant 2D-V2): η = exp(ln(Δη)·y) (six decades
+    bottom to top), ρg_y = −sin(2y) cos(3πx), G = K = Inf, dt = 0.1, free slip, PTStokesCoeffs(li, di; Re = 5π, CFL = 1/√2.1),
+    kwargs = (iterMax = 150e3, nout = 1e3); the reference test wants err_evo1[end] < 1e-8."""
+    ni, li = (nx, ny), (1.0, 1.0)
+    grid = Geometry(ni, li, origin=(0.0, 0.0))
+    di = grid.di.center
+    xc, yc = grid.xci
+    η = np.asfortranarray(np.exp(math.log(Δη) * yc)[None, :] * np.ones((nx, 1)))
+    ρ = np.asfortranarray(-np.sin(2 * yc)[None, :] * np.cos(3 * math.pi * xc)[:, None])
+    flow_bcs = VelocityBoundaryConditions(free_slip=dict(left=True, right=True, top=True, bot=True))
+    fields = dict(eta=η, rhogx=np.zeros(ni, order="F"), rhogy=ρ * 1.0, G=np.full(ni, np.inf, order="F"), K=np.full(ni, np.inf, order="F"))
+    return SimpleNamespace(ni=ni, li=li, di=di, grid=grid, igg=IGG(), pt_stokes=PTStokesCoeffs(li, di, Re=5 * math.pi, CFL=1 / math.sqrt(2.1)),
+                           flow_bcs=flow_bcs, dt=0.1, fields=fields, kwargs=dict(iterMax=150.0e3, nout=1.0e3, verbose=False))
+
+
 def elastic_buildup2d(n=32, *, lx=100.0e3, ly=100.0e3, endtime=10, η0=1.0e21, εbg=1.0e-14, G=10.0e9):
     """test/test_stokes_elastic_buildup.jl:24-53 + miniapps/benchmarks/stokes2D/elastic_buildup/Elastic_BuildUp.jl:19-108 (variant 2D-V2 with
     finite G and dt, K = Inf): uniform η0, pure shear εbg (pureshear_bc!, src/boundaryconditions/pure_shear.jl:1-9), free slip, no gravity,

@@ -60,3 +60,18 @@ def test_manufactured_solutions_on_gpu(oracle, case):
     else:
         assert np.all(order > 1.7), order
         assert max(L2_vx, L2_vy, L2_vz) < 5.0e-3 and L2_p < 1.5e-1
+
+
+def test_solkz_on_gpu(oracle):
+    """test/test_stokes_solkz.jl:26-37 through the public API (2D-V2, η over six decades, Re = 5π): converges below 1e-8 with the oracle's
+    iteration count and fields"""
+    from justrelax_jl_b200 import setups, stokes as jst
+    from test_oracle_stokes2d import run_solkz
+
+    s = setups.solkz2d(32, 32)
+    d, ref = run_solkz(oracle, s)
+    st, extra = device_stokes(s.ni, oracle.alloc_stokes(s.ni, s.fields))
+    jst.flow_bcs_(st, s.flow_bcs)
+    out = jst.solve_(st, s.pt_stokes, s.grid, s.flow_bcs, (extra["rhogx"], extra["rhogy"]), extra["G"], extra["K"], s.dt, s.igg, kwargs=s.kwargs)
+    assert out.err_evo1[-1] < 1.0e-8 and out.iter == ref["iter"]
+    compare_slots(st.slots(), d, V2_STATE, 1.0e-8, "solkz converged fields")

@@ -133,6 +133,21 @@ def test_solcx_reference_golden(oracle):
         assert np.array_equal(d["t" + c], d["t" + c + "_o"])
 
 
+def run_solkz(oracle, s):
+    d = oracle.alloc_stokes(s.ni, s.fields)
+    opts = oracle.make_opts(s.pt_stokes, s.grid._di.center, s.dt, bc_flags(s.flow_bcs), s.ni, iterMax=s.kwargs["iterMax"], nout=s.kwargs["nout"])
+    fs = oracle.make_fields(d, s.ni)
+    oracle.lib().orc_flow_bcs2(C.byref(fs), C.byref(opts), 0)
+    return d, oracle.solve2d_V2(d, s.ni, opts)
+
+
+def test_solkz_reference_criterion(oracle):
+    """test/test_stokes_solkz.jl:26-37 (2D-V2, viscosity exp(B·y) over six decades, Re = 5π): err_evo1[end] < 1e-8"""
+    s = setups.solkz2d(32, 32)
+    d, out = run_solkz(oracle, s)
+    assert out["status"] == 0 and out["err_evo1"][-1] < 1.0e-8 and out["iter"] < s.kwargs["iterMax"]
+
+
 def test_v2_iteration_matches_numpy_restatement(oracle):
     """independent cross-check of the C oracle: one 2D-V2 iteration written with numpy slices"""
     rng = np.random.default_rng(4)
