@@ -67,7 +67,6 @@ struct alignas(64) VaArgs {
     unsigned long long *gbar;          // grid barrier counter between iterations
     unsigned long long gbar_base;      // its value at launch
     int niter;                         // iterations of this launch
-    int dbg_nobc, dbg_nobar;           // timing experiments only (results are wrong): skip the in-kernel BCs / the grid barrier
     int bc_nsn[6];                     // x-lo, x-hi, y-lo, y-hi, z-lo, z-hi: boundary-normal face is zeroed (no_slip!)
     double bc_sg[6];                   // same sides: tangential ghost = bc_sg · interior (+1 free slip, −1 no slip)
 };
@@ -359,7 +358,7 @@ __global__ void __launch_bounds__(32 * BY, (BY <= 10 ? 2 : 1)) k_va_tma(const __
                 // MULTI: flow_bcs! inside the kernel.  mz: CTA-uniform z ghost-image direction of this plane; bz: this thread
                 // holds the source of some boundary / ghost value at this step (rare) — the only test on the common path
                 const int mz = !MULTI ? 0 : (k == 0 ? -1 : (k == nz - 1 ? 1 : 0));
-                const bool bz = MULTI && (bxy || mz != 0) && !a.dbg_nobc;
+                const bool bz = MULTI && (bxy || mz != 0);
 #define JR_MX (gi == 0 ? -1 : (gi == nx - 1 ? 1 : 0))
 #define JR_MY (gj == 0 ? -1 : (gj == ny - 1 ? 1 : 0))
                 if (kin) {
@@ -423,7 +422,7 @@ __global__ void __launch_bounds__(32 * BY, (BY <= 10 ? 2 : 1)) k_va_tma(const __
                         }
                         if (MULTI && bz) JR_GHOSTS(&po[S_Vz * pxy], vn, false, JR_MX, 1, 0, JR_MY, a.PX, 1);
                     }
-                    if (MULTI && mz != 0 && cell && !a.dbg_nobc) {
+                    if (MULTI && mz != 0 && cell) {
                         // z-normal boundary faces: Vz(K = 0) from the queue (k = 0), Vz(K = nz) from the arrival plane
                         // (k = nz − 1); nz ≥ 3 on this path, so never both
                         const bool z = (mz < 0 ? a.bc_nsn[4] : a.bc_nsn[5]) != 0;
@@ -454,7 +453,7 @@ __global__ void __launch_bounds__(32 * BY, (BY <= 10 ? 2 : 1)) k_va_tma(const __
             if (++slot == NST) { slot = 0; parity ^= 1u; }
         }
     }
-    if (MULTI && it + 1 < niter && !a.dbg_nobar) {
+    if (MULTI && it + 1 < niter) {
         // grid-wide barrier between iterations: every store of this iteration (generic proxy) must be visible to
         // the TMA loads (async proxy) of every other CTA, and nobody may overwrite a set others still read
         asm volatile("fence.proxy.async.global;" ::: "memory");
@@ -872,7 +871,7 @@ static int launch_one(jr_context *ctx, VaPlan &P, VaArgs &a)
     P.progress_base += (unsigned long long)nit * items * (a.kchunk + 2);  // every item posts kchunk+2 steps per iteration
     a.gbar = P.progress + 16;  // its own 128-B line
     a.gbar_base = P.gbar_base;
-    if (!a.dbg_nobar) P.gbar_base += (unsigned long long)(nit - 1) * G;
+    P.gbar_base += (unsigned long long)(nit - 1) * G;
     void *args[1] = {(void *)&a};
     // cooperative launch: the soft lock-step spins on other CTAs, so all G CTAs must be resident
     JR_CUDA(cudaLaunchCooperativeKernel((const void *)k_va_tma<BY, FIN, DG, NSTv, RHOG, MULTI>, dim3(G, 1, 1), dim3(32, BY, 1), args, smem,
@@ -918,8 +917,6 @@ static void fill_args(VaArgs &a, const VaPlan &P, const jr_fields *s, const jr_s
     a.out2 = P.S[parity ? 1 : 0];
     a.niter = 1;
     a.gbar = nullptr; a.gbar_base = 0;
-    a.dbg_nobc = getenv("JRB200_VA_DBG_NOBC") ? 1 : 0;
-    a.dbg_nobar = getenv("JRB200_VA_DBG_NOBAR") ? 1 : 0;
     a.divV = F(divV); a.RP = F(RP); a.exx = F(exx); a.eyy = F(eyy); a.ezz = F(ezz); a.eyz = F(eyz); a.exz = F(exz); a.exy = F(exy);
     a.Rx = F(Rx); a.Ry = F(Ry); a.Rz = F(Rz); a.Ux = F(Ux); a.Uy = F(Uy); a.Uz = F(Uz);
     a.nx = nx; a.ny = ny; a.nz = nz; a.PX = P.PX; a.PY = P.PY;
