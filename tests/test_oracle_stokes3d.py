@@ -73,6 +73,15 @@ def test_taylor_green_reference_criteria(oracle):
     assert max(L2_vx, L2_vy, L2_vz) < 5.0e-3 and L2_p < 1.5e-1, errs[1]
 
 
+def test_norm_mpi_kats(oracle):
+    """test/test_Utils.jl:172,237: norm_mpi(η) === 4.0 for η = ones(4, 4) and === 8.0 for ones(4, 4, 4) — the single-rank value of the
+    residual-norm reduction (Utils.jl:698-701: √(Σ A²))"""
+    assert np.sqrt(oracle.sumsq(np.ones((4, 4), order="F"), False)) == 4.0
+    assert np.sqrt(oracle.sumsq(np.ones((4, 4, 4), order="F"), False)) == 8.0
+    # the solvers' view A[2:end-1, …] (interior = true)
+    assert oracle.sumsq(np.ones((6, 6, 6), order="F"), True) == 64.0
+
+
 def test_maxloc_hotspot(oracle):
     # test_Utils.jl:387-397 analogue in 3D: a single hotspot spreads to its 3x3x3 neighbourhood
     A = np.ones((5, 5, 5), order="F")
