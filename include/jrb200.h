@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define JRB200_ABI_VERSION 1
+#define JRB200_ABI_VERSION 2
 
 typedef enum {
     JR_OK = 0,
@@ -48,7 +48,9 @@ typedef enum {
  * Naming: t=τ, e=ε, p=ε_pl, d=Δε, w=ω, `_o` = τ_o, `_c` = shear @ centres,
  * `_v` = normal @ vertices (2D), lam=λ, lamv=λv, etatau=ητ, divV=∇V, divU=∇U,
  * rhog*=ρg tuple, K/G = bulk/shear modulus arrays (VA/V2 variants),
- * T/Pargs = args.T (ghosted, ni.+2) and args.P (ni).
+ * T/Pargs = args.T (ghosted, ni.+2) and args.P (ni); dTargs = args.ΔT (ni): when
+ * non-NULL the VC solves use the thermal-stress form of compute_P!
+ * (src/stokes/PressureKernels.jl:128-149,197-206).
  * ------------------------------------------------------------------------- */
 #define JR_STOKES_FIELDS(X)                                                    \
     X(P) X(P0) X(divV) X(Q)                                                    \
@@ -66,7 +68,8 @@ typedef enum {
     X(divU) X(lam) X(lamv) X(dPpsi)                                            \
     X(rhogx) X(rhogy) X(rhogz)                                                 \
     X(K) X(G) X(T) X(Pargs)                                                    \
-    X(txx_v) X(tyy_v) X(txx_o_v) X(tyy_o_v)
+    X(txx_v) X(tyy_v) X(txx_o_v) X(tyy_o_v)                                    \
+    X(dTargs)
 
 typedef enum {
 #define X(n) JR_F_##n,
@@ -140,6 +143,17 @@ int jr_stokes3d_solve_VA(jr_context *ctx, const jr_fields *s, const jr_stokes_op
 /* exactly `niter` PT iterations, no convergence test (benchmark / fixed-iteration parity). */
 int jr_stokes3d_iterate_VA(jr_context *ctx, const jr_fields *s, const jr_stokes_opts *o, int64_t niter,
                            jr_stokes_result *res);
+
+/* iteration session: what the body of the reference's `while` loop (src/stokes/Stokes3D.jl:76-122) is to a host that
+ * keeps its own convergence logic.  begin = the pre-loop work of _solve! (:43-57: ητ = maxloc(η) + halo) and the entry
+ * into the library's TMA box layout; step = `niter` PT iterations (res->time_s = device time of exactly these
+ * iterations, CUDA events on the context's stream); with observe_last the last iteration also writes everything the
+ * reference's iteration leaves in the user's arrays (∇V, ε, R, RP, U and the state V, P, τ), otherwise the dense arrays
+ * are stale until the next observable iteration or end; end = leave the layout (the dense state is made current).
+ * One open session per context; fields/opts are copied at begin, the arrays must stay allocated until end. */
+int jr_stokes3d_VA_begin(jr_context *ctx, const jr_fields *s, const jr_stokes_opts *o);
+int jr_stokes3d_VA_step(jr_context *ctx, int64_t niter, int observe_last, jr_stokes_result *res);
+int jr_stokes3d_VA_end(jr_context *ctx);
 
 /* facts about the fused plan the last VA solve on this context used:
  * info = {tile rows BY, z-chunks, 1 if the body-force arrays were constant and not streamed, finite dt,

@@ -163,6 +163,9 @@ def _declare(L):
     L.jr_stokes3d_solve_VA.argtypes = [vp, vp, C.POINTER(StokesOpts), C.POINTER(StokesResult)]
     L.jr_stokes3d_iterate_VA.argtypes = [vp, vp, C.POINTER(StokesOpts), C.c_int64, C.POINTER(StokesResult)]
     L.jr_stokes3d_VA_plan_info.argtypes = [vp, i32p]
+    L.jr_stokes3d_VA_begin.argtypes = [vp, vp, C.POINTER(StokesOpts)]
+    L.jr_stokes3d_VA_step.argtypes = [vp, C.c_int64, C.c_int, C.POINTER(StokesResult)]
+    L.jr_stokes3d_VA_end.argtypes = [vp]
     so, sr, vc = C.POINTER(StokesOpts), C.POINTER(StokesResult), C.POINTER(VcInputs)
     L.jr_stokes2d_solve_V2.argtypes = [vp, vp, so, sr]
     L.jr_stokes2d_iterate_V2.argtypes = [vp, vp, so, C.c_int64, sr]

@@ -94,7 +94,7 @@ def init_global_grid(nx: int, ny: int, nz: int = 1, *, dims: Sequence[int] = (0,
     ndims = 3 if nz > 1 else 2
     dims = dims_create(world, ndims, dims)
     coords = cart_coords(rank, dims)
-    igg = IGG(me=rank, dims=dims, nprocs=world, coords=coords, comm_cart=None)
+    igg = IGG(me=rank, dims=dims, nprocs=world, coords=coords, comm_cart=None, nxyz=(int(nx), int(ny), int(nz)))
     ctx = context()
     cb = _make_allgather_cb() if world > 1 else _abi.ALLGATHER_FN()
     h = C.c_void_p()
@@ -115,8 +115,8 @@ def finalize_global_grid():
 
 
 def update_halo_(*arrays, ni: Optional[Sequence[int]] = None):
-    """update_halo!(A...) on dense B200 arrays.  `ni` = local cell counts (nx, ny, nz); default: the igg's grid size
-    is taken to be the smallest extent per dimension over the arrays given (IGG needs it to compute each array's overlap)."""
+    """update_halo!(A...) on dense B200 arrays.  `ni` = local cell counts (nx, ny, nz); default: the (nx, ny, nz) given to
+    init_global_grid, as in ImplicitGlobalGrid (which derives each array's overlap from size(A) − nxyz)."""
     from .stokes import context
 
     if not arrays:
@@ -129,7 +129,9 @@ def update_halo_(*arrays, ni: Optional[Sequence[int]] = None):
         shp = list(a.shape) + [1] * (3 - a.dim())
         ext += shp
     if ni is None:
-        ni = [min(ext[3 * q + d] for q in range(len(arrays))) for d in range(3)]
+        if _state["igg"] is None or _state["igg"].nxyz is None:
+            raise RuntimeError("update_halo_: no global grid (call init_global_grid first) and no `ni` given")
+        ni = _state["igg"].nxyz
     ni = list(ni) + [1] * (3 - len(ni))
     ptrs = (C.c_void_p * len(arrays))(*[data_ptr(a) for a in arrays])
     _abi.check(_abi.lib().jr_update_halo3d(context(), len(arrays), ptrs, _abi.i32x(ext), _abi.i32x(ni)))

@@ -341,6 +341,13 @@ int jr_comm_destroy(jr_comm *cm)
 {
     if (!cm) return JR_OK;
     cudaDeviceSynchronize();
+    // a slower peer's last pull / all-reduce may still be reading this rank's exported buffers: every rank drains its own
+    // device first, then one host token round makes sure ALL ranks have done so before anybody unmaps or frees
+    if (cm->nranks > 1 && cm->allgather) {
+        char tok = 1;
+        std::vector<char> all((size_t)cm->nranks);
+        cm->allgather(&tok, all.data(), 1, cm->user);
+    }
     for (auto &kv : cm->ipc_open) cudaIpcCloseMemHandle(kv.second);
     for (void *p : cm->retired) cudaFree(p);
     for (int b = 0; b < 2; b++)

@@ -112,6 +112,19 @@ __device__ __forceinline__ void jr_compute_P_point(double &RP, double &P, double
     P = ((fma(P0, _Kdt, (-divV + (Q * _dt)))) * psi + Pc) / (1 + _Kdt * psi);
 }
 
+// _compute_P! with thermal stresses  src/stokes/PressureKernels.jl:197-206 (Kiss et al. 2023)
+__device__ __forceinline__ void jr_compute_P_point_dT(double &RP, double &P, double P0, double divV, double Q, double dT, double alpha,
+                                                      double eta, double K, double G, double dt, double r, double theta_dtau)
+{
+    const double _Kdt = jr_inv(K * dt);
+    const double _Gdt = jr_inv(G * dt);
+    const double _dt = jr_inv(dt);
+    const double Pc = P;
+    RP = fma(-(Pc - P0), _Kdt, (-divV + (alpha * (dT * _dt)) + (Q * _dt)));
+    const double psi = jr_inv(jr_inv(eta) + _Gdt) * r / theta_dtau;
+    P = ((fma(P0, _Kdt, (-divV + (alpha * (dT * _dt)) + (Q * _dt)))) * psi + Pc) / (1 + _Kdt * psi);
+}
+
 // internal entry points shared between translation units
 int jr_launch_flow_bcs3d(jr_context *ctx, double *Ax, double *Ay, double *Az, const int32_t n[3],
                          const int32_t free_slip[6], const int32_t no_slip[6], const int32_t periodic[6]);

@@ -43,6 +43,16 @@ __device__ __forceinline__ double jr_ratio_Kb(const jr_phase_tab &pt, const doub
     }
     return x;
 }
+// fn_ratio(get_thermal_expansion, rheology, ratio)  src/rheology/GeoParams.jl:17 (α of the density law; 0 for ConstantDensity)
+__device__ __forceinline__ double jr_ratio_alpha(const jr_phase_tab &pt, const double *__restrict__ ph, size_t stride, size_t q)
+{
+    double x = 0.0;
+    for (int p = 0; p < pt.n; p++) {
+        const double r = ph[(size_t)p * stride + q];
+        x += (r == 0.0) ? 0.0 : (pt.rho_kind[p] == 0 ? 0.0 : pt.alpha[p]) * r;
+    }
+    return x;
+}
 __device__ __forceinline__ void jr_plastic_params(const jr_phase_tab &pt, const double *__restrict__ ph, size_t stride, size_t q, bool &is_pl,
                                                   double &eta_reg)
 {

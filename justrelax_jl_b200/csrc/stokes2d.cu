@@ -14,6 +14,7 @@
 // result can be observed (every `nout`, and the last).
 #include "rheo.cuh"
 #include "tma.cuh"
+#include "comm.cuh"
 
 #define F(name) (s->f[JR_F_##name])
 #define TX 32
@@ -28,7 +29,7 @@ struct K2 {
     const double *Vx_i, *Vy_i, *P_i, *txx_i, *tyy_i, *txy_i, *th_i, *txyc_i, *lam_i, *lamv_i, *eta_i, *etav_i;
     double *Vx_o, *Vy_o, *P_o, *txx_o, *tyy_o, *txy_o, *th_o, *txyc_o, *lam_o, *lamv_o, *eta_o, *etav_o;
     // read-only inputs
-    const double *P0, *Q, *K, *G, *etatau, *txxo, *tyyo, *txyo, *txyco, *rhogx, *rhogy, *T, *Pargs, *ph_c, *ph_v;
+    const double *P0, *Q, *K, *G, *etatau, *txxo, *tyyo, *txyo, *txyco, *rhogx, *rhogy, *T, *Pargs, *dTargs, *ph_c, *ph_v;
     // diagnostics (written when DIAG)
     double *divV, *RP, *exx, *eyy, *exy, *pxx, *pyy, *pxy, *tII, *eta_vep, *e_vol_pl, *Ux, *Uy, *rhogx_w, *rhogy_w, *etatau_w;
 };
@@ -94,7 +95,10 @@ __global__ void __launch_bounds__(TX * TYT) k_stokes2d(const __grid_constant__ K
             thn = a.P_i[c];
         }
         // compute_P! with ητ (quirk Q5)  Stokes2D.jl:231-233, 664-677; PressureKernels.jl:186-195
-        jr_compute_P_point(RP, thn, a.P0[c], divV, a.Q[c], ett, Kc, Gc, a.dt, a.r, a.th);
+        if (VC && a.dTargs)  // args.ΔT given: thermal-stress form  PressureKernels.jl:128-149,197-206
+            jr_compute_P_point_dT(RP, thn, a.P0[c], divV, a.Q[c], a.dTargs[c], jr_ratio_alpha(pt, a.ph_c, nc, c), ett, Kc, Gc, a.dt, a.r, a.th);
+        else
+            jr_compute_P_point(RP, thn, a.P0[c], divV, a.Q[c], ett, Kc, Gc, a.dt, a.r, a.th);
         const double dV = divV * jr_inv(3.0);
         exx = dVx - dV;  // compute_strain_rate!  VelocityKernels.jl:10-44
         eyy = dVy - dV;
@@ -523,6 +527,16 @@ static int plan2_tile(jr_context *ctx, Plan2 *p)
     return JR_OK;
 }
 
+// the 2D solvers are single-rank: the fused iteration has no halo exchange (the reference cuts it at update_halo!(ητ),
+// update_halo!(τxy), update_halo!(V): Stokes2D.jl:655,757,784) and the norms are not all-reduced — refuse loudly instead
+// of returning rank-local answers
+static int single_rank2d(const jr_context *ctx)
+{
+    JR_REQUIRE(!(ctx->comm && ctx->comm->nranks > 1), JR_ERR_UNSUPPORTED,
+               "the 2D Stokes solvers run on one rank only (a communicator with %d ranks is attached to this context)", ctx->comm->nranks);
+    return JR_OK;
+}
+
 static int check2d(const jr_fields *s, const jr_stokes_opts *o, bool vc, const jr_vc_inputs *in)
 {
     JR_REQUIRE(s && o, JR_ERR_ARG, "null fields/opts");
@@ -578,7 +592,7 @@ static int plan2_begin(jr_context *ctx, const jr_fields *s, const jr_stokes_opts
     k.ns_l = o->no_slip[0]; k.ns_r = o->no_slip[1]; k.ns_t = o->no_slip[4]; k.ns_b = o->no_slip[5];
     k.P0 = F(P0); k.Q = F(Q); k.K = F(K); k.G = F(G); k.etatau = F(etatau);
     k.txxo = F(txx_o); k.tyyo = F(tyy_o); k.txyo = F(txy_o); k.txyco = F(txy_o_c);
-    k.rhogx = F(rhogx); k.rhogy = F(rhogy); k.T = F(T); k.Pargs = F(Pargs);
+    k.rhogx = F(rhogx); k.rhogy = F(rhogy); k.T = F(T); k.Pargs = F(Pargs); k.dTargs = F(dTargs);
     k.divV = F(divV); k.RP = F(RP); k.exx = F(exx); k.eyy = F(eyy); k.exy = F(exy); k.pxx = F(pxx); k.pyy = F(pyy); k.pxy = F(pxy);
     k.tII = F(tII); k.eta_vep = F(eta_vep); k.e_vol_pl = F(e_vol_pl); k.Ux = F(Ux); k.Uy = F(Uy); k.rhogx_w = F(rhogx); k.rhogy_w = F(rhogy);
     k.etatau_w = F(etatau);
@@ -747,6 +761,7 @@ int jr_stokes2d_iterate_V2(jr_context *ctx, const jr_fields *s, const jr_stokes_
     JR_REQUIRE(ctx, JR_ERR_ARG, "null context");
     int st = check2d(s, o, false, nullptr);
     if (st) return st;
+    if ((st = single_rank2d(ctx))) return st;
     JR_CUDA(cudaSetDevice(ctx->device));
     Plan2 p;
     ctx->launches = 0;
@@ -768,6 +783,7 @@ int jr_stokes2d_solve_V2(jr_context *ctx, const jr_fields *s, const jr_stokes_op
     JR_REQUIRE(ctx && res, JR_ERR_ARG, "null context/result");
     int st = check2d(s, o, false, nullptr);
     if (st) return st;
+    if ((st = single_rank2d(ctx))) return st;
     JR_REQUIRE(res->err_evo1 && res->err_evo2 && res->norm_Rx && res->norm_Ry && res->norm_divV, JR_ERR_ARG, "result history arrays must be provided");
     JR_CUDA(cudaSetDevice(ctx->device));
     Plan2 p;
@@ -791,13 +807,8 @@ int jr_stokes2d_solve_V2(jr_context *ctx, const jr_fields *s, const jr_stokes_op
             res->err_evo1[cont] = err; res->err_evo2[cont] = iter;
             cont += 1;
             err_it1 = fmax(fmax(res->norm_Rx[0], res->norm_Ry[0]), res->norm_divV[0]);
-            if (std::isnan(err)) {
-                plan2_finish(ctx, s, &p, iter);
-                cudaStreamSynchronize(ctx->stream);
-                res->iter = iter; res->nhist = cont; res->err = err;
-                jr_set_error("NaN(s)");
-                return JR_ERR_NAN;
-            }
+            // no isnan test in this variant (Stokes2D.jl:222-311): a NaN error fails the loop condition, the loop ends quietly,
+            // multi_copy! runs and the history (with the NaN) is returned
         }
     }
     if ((st = plan2_finish(ctx, s, &p, iter))) return st;
@@ -814,6 +825,7 @@ int jr_stokes2d_iterate_VC(jr_context *ctx, const jr_fields *s, const jr_stokes_
     JR_REQUIRE(ctx, JR_ERR_ARG, "null context");
     int st = check2d(s, o, true, vc);
     if (st) return st;
+    if ((st = single_rank2d(ctx))) return st;
     JR_CUDA(cudaSetDevice(ctx->device));
     Plan2 p;
     ctx->launches = 0;
@@ -836,6 +848,7 @@ int jr_stokes2d_solve_VC(jr_context *ctx, const jr_fields *s, const jr_stokes_op
     JR_REQUIRE(ctx && res, JR_ERR_ARG, "null context/result");
     int st = check2d(s, o, true, vc);
     if (st) return st;
+    if ((st = single_rank2d(ctx))) return st;
     JR_REQUIRE(res->err_evo1 && res->err_evo2 && res->norm_Rx && res->norm_Ry && res->norm_divV, JR_ERR_ARG, "result history arrays must be provided");
     JR_CUDA(cudaSetDevice(ctx->device));
     Plan2 p;

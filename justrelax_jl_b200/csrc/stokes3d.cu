@@ -62,46 +62,125 @@ static int post_VA(jr_context *ctx, const jr_fields *s)
 
 extern "C" {
 
-int jr_stokes3d_iterate_VA(jr_context *ctx, const jr_fields *s, const jr_stokes_opts *o, int64_t niter, jr_stokes_result *res)
+// ---- iteration session: the state lives in the library's layout between calls ------------------------------------
+struct VaSession {
+    bool active = false, fused = false;
+    jr_fields f;
+    jr_stokes_opts o;
+    int64_t iter = 0;
+};
+static std::map<jr_context *, VaSession> g_sessions;
+
+// `niter` iterations of the open session; the last one observable (diagnostics + dense state written) when observe_last
+static int session_run(jr_context *ctx, VaSession &S, int64_t niter, int observe_last)
+{
+    const jr_fields *s = &S.f;
+    const jr_stokes_opts *o = &S.o;
+    int st;
+    // iterations whose diagnostics nobody reads may run several per launch (the kernel applies flow_bcs! itself)
+    const int64_t multi = (S.fused && !(ctx->flags & JR_FLAG_DIAG_EVERY_ITER)) ? jr_stokes3d_VA_fused_multi_max(ctx, o) : 0;
+    for (int64_t it = 0; it < niter;) {
+        const int64_t nb = std::min<int64_t>(niter - (observe_last ? 1 : 0) - it, multi);
+        if (nb >= 1 && multi >= 1) {
+            if ((st = jr_stokes3d_VA_fused_multi(ctx, s, o, (int)nb, (int)(S.iter & 1)))) return st;
+            it += nb; S.iter += nb;
+            continue;
+        }
+        const int diag = (ctx->flags & JR_FLAG_DIAG_EVERY_ITER) ? 1 : (observe_last && it == niter - 1);
+        if ((st = one_iter_VA(ctx, s, o, S.fused, diag, S.iter))) return st;
+        it++; S.iter++;
+    }
+    return JR_OK;
+}
+
+int jr_stokes3d_VA_begin(jr_context *ctx, const jr_fields *s, const jr_stokes_opts *o)
 {
     JR_REQUIRE(ctx, JR_ERR_ARG, "null context");
     int st = check_fields_VA(s, o);
     if (st) return st;
     JR_CUDA(cudaSetDevice(ctx->device));
+    VaSession &S = g_sessions[ctx];
+    JR_REQUIRE(!S.active, JR_ERR_ARG, "jr_stokes3d_VA_begin: a session is already open on this context (call jr_stokes3d_VA_end)");
     // both paths are CUDA paths of this library; the fused kernel covers uniform grids with
     // free-slip/no-slip faces, everything else runs the reference-structured kernel sequence.
-    const bool fused = !(ctx->flags & JR_FLAG_UNFUSED) && jr_stokes3d_VA_fused_supported(s, o) == JR_OK;
+    S.fused = !(ctx->flags & JR_FLAG_UNFUSED) && jr_stokes3d_VA_fused_supported(s, o) == JR_OK;
+    S.f = *s; S.o = *o; S.iter = 0;
     ctx->launches = 0;
     if ((st = pre_VA(ctx, s))) return st;
-    // the timed region includes packing the dense arrays into the TMA box layout and unpacking them again
+    if (S.fused && (st = jr_stokes3d_VA_fused_begin(ctx, s, o))) return st;
+    S.active = true;
+    return JR_OK;
+}
+
+int jr_stokes3d_VA_step(jr_context *ctx, int64_t niter, int observe_last, jr_stokes_result *res)
+{
+    JR_REQUIRE(ctx, JR_ERR_ARG, "null context");
+    auto it = g_sessions.find(ctx);
+    JR_REQUIRE(it != g_sessions.end() && it->second.active, JR_ERR_ARG, "jr_stokes3d_VA_step without jr_stokes3d_VA_begin");
+    JR_REQUIRE(niter >= 0, JR_ERR_ARG, "niter must be >= 0");
+    JR_CUDA(cudaSetDevice(ctx->device));
+    const int64_t l0 = ctx->launches;
     JR_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
-    if (fused && (st = jr_stokes3d_VA_fused_begin(ctx, s, o))) return st;
-    // iterations whose diagnostics nobody reads run several per launch (the kernel applies flow_bcs! itself)
-    const int64_t multi = (fused && !(ctx->flags & JR_FLAG_DIAG_EVERY_ITER)) ? jr_stokes3d_VA_fused_multi_max(ctx, o) : 0;
-    for (int64_t it = 0; it < niter;) {
-        const int64_t nb = std::min<int64_t>(niter - 1 - it, multi);
-        if (nb >= 1 && multi >= 1) {
-            if ((st = jr_stokes3d_VA_fused_multi(ctx, s, o, (int)nb, (int)(it & 1)))) return st;
-            it += nb;
-            continue;
-        }
-        const int diag = (ctx->flags & JR_FLAG_DIAG_EVERY_ITER) ? 1 : (it == niter - 1);
-        if ((st = one_iter_VA(ctx, s, o, fused, diag, it))) return st;
-        it++;
-    }
-    if (fused && (st = jr_stokes3d_VA_fused_finish(ctx, s, niter))) return st;
+    int st = session_run(ctx, it->second, niter, observe_last);
+    if (st) return st;
     JR_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
     JR_CUDA(cudaStreamSynchronize(ctx->stream));
     if (res) {
         float ms = 0.f;
         JR_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
-        res->iter = niter;
+        res->iter = it->second.iter;
         res->nhist = 0;
         res->err = NAN;
         res->time_s = ms * 1e-3;
-        res->kernel_launches = ctx->launches;
+        res->kernel_launches = ctx->launches - l0;
     }
     return JR_OK;
+}
+
+int jr_stokes3d_VA_end(jr_context *ctx)
+{
+    JR_REQUIRE(ctx, JR_ERR_ARG, "null context");
+    auto it = g_sessions.find(ctx);
+    JR_REQUIRE(it != g_sessions.end() && it->second.active, JR_ERR_ARG, "jr_stokes3d_VA_end without jr_stokes3d_VA_begin");
+    VaSession &S = it->second;
+    S.active = false;
+    int st;
+    if (S.fused && (st = jr_stokes3d_VA_fused_finish(ctx, &S.f, S.iter))) return st;
+    JR_CUDA(cudaStreamSynchronize(ctx->stream));
+    return JR_OK;
+}
+
+int jr_stokes3d_iterate_VA(jr_context *ctx, const jr_fields *s, const jr_stokes_opts *o, int64_t niter, jr_stokes_result *res)
+{
+    JR_REQUIRE(ctx, JR_ERR_ARG, "null context");
+    JR_CUDA(cudaSetDevice(ctx->device));
+    // the timed region of this call includes entering and leaving the TMA box layout (jr_stokes3d_VA_step times iterations only)
+    cudaEvent_t e0, e1;
+    JR_CUDA(cudaEventCreate(&e0));
+    JR_CUDA(cudaEventCreate(&e1));
+    JR_CUDA(cudaEventRecord(e0, ctx->stream));
+    int st = jr_stokes3d_VA_begin(ctx, s, o);
+    if (!st) {
+        st = session_run(ctx, g_sessions[ctx], niter, 1);
+        const int st2 = jr_stokes3d_VA_end(ctx);
+        if (!st) st = st2;
+    }
+    if (!st) {
+        cudaEventRecord(e1, ctx->stream);
+        cudaStreamSynchronize(ctx->stream);
+        if (res) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, e0, e1);
+            res->iter = niter;
+            res->nhist = 0;
+            res->err = NAN;
+            res->time_s = ms * 1e-3;
+            res->kernel_launches = ctx->launches;
+        }
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return st;
 }
 
 int jr_stokes3d_solve_VA(jr_context *ctx, const jr_fields *s, const jr_stokes_opts *o, jr_stokes_result *res)

@@ -53,6 +53,8 @@ struct alignas(64) VaArgs {
     CUtensorMap mS5, mC1, mC4, mD1, mD2, mD7;  // in-state set (5-array boxes), const set, finite-dt set
     double *out;                               // out-state set base
     double *divV, *RP, *exx, *eyy, *ezz, *eyz, *exz, *exy, *Rx, *Ry, *Rz, *Ux, *Uy, *Uz;  // dense user arrays (DIAG)
+    double *dVx, *dVy, *dVz, *dP, *dtxx, *dtyy, *dtzz, *dtyz, *dtxz, *dtxy;  // dense state (DIAG: an observable iteration leaves
+                                                                            // the user's arrays current, no unpack pass)
     unsigned long long *progress;              // grid-wide step counter (soft lock-step of the resident CTAs)
     unsigned long long progress_base;          // counter value at launch
     int nx, ny, nz, PX, PY, kchunk;
@@ -368,11 +370,15 @@ __global__ void __launch_bounds__(32 * BY, (BY <= 10 ? 2 : 1)) k_va_tma(const __
                         if (DIAG) {
                             const size_t c = ((size_t)k * ny + gj) * nx + gi;
                             a.divV[c] = divV; a.RP[c] = RP; a.exx[c] = exx; a.eyy[c] = eyy; a.ezz[c] = ezz;
+                            a.dP[c] = P_n; a.dtxx[c] = txx_n; a.dtyy[c] = tyy_n; a.dtzz[c] = tzz_n;
                         }
                     }
                     if (vxy) {
                         jr_st_hint(&po[S_txy * pxy], txy_n, pst);
-                        if (DIAG) a.exy[((size_t)k * (ny + 1) + gj) * (nx + 1) + gi] = exy0;
+                        if (DIAG) {
+                            const size_t c = ((size_t)k * (ny + 1) + gj) * (nx + 1) + gi;
+                            a.exy[c] = exy0; a.dtxy[c] = txy_n;
+                        }
                     }
                     // x-momentum: face gi between cells gi−1 (W) and gi
                     if (stVx) {
@@ -383,7 +389,8 @@ __global__ void __launch_bounds__(32 * BY, (BY <= 10 ? 2 : 1)) k_va_tma(const __
                         jr_st_hint(&po[S_Vx * pxy], vn, pst);
                         if (DIAG) {
                             a.Rx[((size_t)k * ny + gj) * (nx - 1) + (gi - 1)] = R;
-                            a.Ux[((size_t)(k + 1) * (ny + 2) + gj + 1) * (nx + 1) + gi] = vn * a.dt;
+                            const size_t c = ((size_t)(k + 1) * (ny + 2) + gj + 1) * (nx + 1) + gi;
+                            a.Ux[c] = vn * a.dt; a.dVx[c] = vn;
                         }
                         if (MULTI && bz) JR_GHOSTS(&po[S_Vx * pxy], vn, false, JR_MY, a.PX, 1, mz, S_N * pxy, 2);
                     } else if (MULTI && bz && vxz && (gi == 0 || gi == nx)) {
@@ -402,7 +409,8 @@ __global__ void __launch_bounds__(32 * BY, (BY <= 10 ? 2 : 1)) k_va_tma(const __
                         jr_st_hint(&po[S_Vy * pxy], vn, pst);
                         if (DIAG) {
                             a.Ry[((size_t)k * (ny - 1) + (gj - 1)) * nx + gi] = R;
-                            a.Uy[((size_t)(k + 1) * (ny + 1) + gj) * (nx + 2) + gi + 1] = vn * a.dt;
+                            const size_t c = ((size_t)(k + 1) * (ny + 1) + gj) * (nx + 2) + gi + 1;
+                            a.Uy[c] = vn * a.dt; a.dVy[c] = vn;
                         }
                         if (MULTI && bz) JR_GHOSTS(&po[S_Vy * pxy], vn, false, JR_MX, 1, 0, mz, S_N * pxy, 2);
                     } else if (MULTI && bz && vyz && (gj == 0 || gj == ny)) {
@@ -418,7 +426,8 @@ __global__ void __launch_bounds__(32 * BY, (BY <= 10 ? 2 : 1)) k_va_tma(const __
                         jr_st_hint(&po[S_Vz * pxy], vn, pst);
                         if (DIAG) {
                             a.Rz[((size_t)(k - 1) * ny + gj) * nx + gi] = R;
-                            a.Uz[((size_t)k * (ny + 2) + gj + 1) * (nx + 2) + gi + 1] = vn * a.dt;
+                            const size_t c = ((size_t)k * (ny + 2) + gj + 1) * (nx + 2) + gi + 1;
+                            a.Uz[c] = vn * a.dt; a.dVz[c] = vn;
                         }
                         if (MULTI && bz) JR_GHOSTS(&po[S_Vz * pxy], vn, false, JR_MX, 1, 0, JR_MY, a.PX, 1);
                     }
@@ -437,11 +446,17 @@ __global__ void __launch_bounds__(32 * BY, (BY <= 10 ? 2 : 1)) k_va_tma(const __
                     double *const pe = po + S_N * pxy;
                     if (vxz) {
                         jr_st_hint(&pe[S_txz * pxy], txz_n, pst);
-                        if (DIAG) a.exz[((size_t)(k + 1) * ny + gj) * (nx + 1) + gi] = exz_t;
+                        if (DIAG) {
+                            const size_t c = ((size_t)(k + 1) * ny + gj) * (nx + 1) + gi;
+                            a.exz[c] = exz_t; a.dtxz[c] = txz_n;
+                        }
                     }
                     if (vyz) {
                         jr_st_hint(&pe[S_tyz * pxy], tyz_n, pst);
-                        if (DIAG) a.eyz[((size_t)(k + 1) * (ny + 1) + gj) * nx + gi] = eyz_t;
+                        if (DIAG) {
+                            const size_t c = ((size_t)(k + 1) * (ny + 1) + gj) * nx + gi;
+                            a.eyz[c] = eyz_t; a.dtyz[c] = tyz_n;
+                        }
                     }
                 }
                 tzz_p = tzz_n; P_p = P_n; fz_p = c_fz; ett_p = c_ett;
@@ -532,6 +547,7 @@ __global__ void k_box_pack(const __grid_constant__ PackArgs pa)
 struct BcArrB {
     BoxArr in, out;
     double *U;   // dense
+    double *Vd;  // dense V of the user (written together with U on observable iterations)
     int n[3];    // dense extents of this velocity component
     int o[3];    // dense → box offset
     int normal;  // normal dimension of this component
@@ -582,7 +598,11 @@ __global__ void k_bc_box3(const __grid_constant__ BcArgsB b)
     if (zero) val = 0.0;
     else val = sign * (computed ? A.out.p[is] : A.in.p[is]);
     A.out.p[ic] = val;
-    if (b.diag) A.U[((size_t)c[2] * A.n[1] + c[1]) * A.n[0] + c[0]] = A.in.p[ic] * b.dt;
+    if (b.diag) {
+        const size_t dc = ((size_t)c[2] * A.n[1] + c[1]) * A.n[0] + c[0];
+        A.U[dc] = A.in.p[ic] * b.dt;
+        A.Vd[dc] = val;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -674,6 +694,11 @@ struct VaPlan {
     unsigned long long *progress = nullptr, progress_base = 0, gbar_base = 0;
     bool rhog_const = false;  // ρg arrays are spatially constant: not streamed
     double fc[3] = {0, 0, 0};
+    // box sets are zeroed when they are (re)allocated or re-shaped only: no kernel ever writes outside an array's own extent,
+    // so the zero padding the stencils rely on survives from one solve to the next
+    void *zeroed[4] = {nullptr, nullptr, nullptr, nullptr};
+    int zdims[4] = {0, 0, 0, 0};  // nx, ny, nz, finite_dt of the zeroed layout
+    bool last_diag = false;       // the last iteration was an observable one: the user's dense arrays are current
 };
 static std::map<jr_context *, VaPlan> g_plans;
 
@@ -753,8 +778,12 @@ int jr_stokes3d_VA_fused_begin(jr_context *ctx, const jr_fields *s, const jr_sto
         const size_t bytes = plane * NA[q] * P.PZ;
         if ((st = jr_ctx_scratch(ctx, names[q], bytes, &p))) return st;
         *dst[q] = (double *)p;
-        JR_CUDA(cudaMemsetAsync(p, 0, bytes, ctx->stream));
+        const bool same = P.zeroed[q] == p && P.zdims[0] == nx && P.zdims[1] == ny && P.zdims[2] == nz;
+        if (!same) JR_CUDA(cudaMemsetAsync(p, 0, bytes, ctx->stream));
+        P.zeroed[q] = p;
     }
+    P.zdims[0] = nx; P.zdims[1] = ny; P.zdims[2] = nz; P.zdims[3] = fin;
+    P.last_diag = false;
     choose_tiling(P, ctx->sm_count);
     // test / tuning overrides of the tiling heuristic
     if (const char *fb = getenv("JRB200_VA_BY")) {
@@ -919,6 +948,8 @@ static void fill_args(VaArgs &a, const VaPlan &P, const jr_fields *s, const jr_s
     a.gbar = nullptr; a.gbar_base = 0;
     a.divV = F(divV); a.RP = F(RP); a.exx = F(exx); a.eyy = F(eyy); a.ezz = F(ezz); a.eyz = F(eyz); a.exz = F(exz); a.exy = F(exy);
     a.Rx = F(Rx); a.Ry = F(Ry); a.Rz = F(Rz); a.Ux = F(Ux); a.Uy = F(Uy); a.Uz = F(Uz);
+    a.dVx = F(Vx); a.dVy = F(Vy); a.dVz = F(Vz); a.dP = F(P); a.dtxx = F(txx); a.dtyy = F(tyy); a.dtzz = F(tzz);
+    a.dtyz = F(tyz); a.dtxz = F(txz); a.dtxy = F(txy);
     a.nx = nx; a.ny = ny; a.nz = nz; a.PX = P.PX; a.PY = P.PY;
     a.kchunk = (nz + P.nchunk - 1) / P.nchunk;
     a.pol_ld = P.pol_ld; a.pol_st = P.pol_st;
@@ -974,6 +1005,7 @@ int jr_stokes3d_VA_fused_multi(jr_context *ctx, const jr_fields *s, const jr_sto
     a.niter = niter;
     int st = P.rhog_const ? launch_va_multi_t<false>(ctx, P, a) : launch_va_multi_t<true>(ctx, P, a);
     if (st) return st;
+    P.last_diag = false;
     ctx->launches += 1;
     JR_CHECK_LAUNCH();
     return JR_OK;
@@ -992,11 +1024,12 @@ int jr_stokes3d_VA_fused_iter(jr_context *ctx, const jr_fields *s, const jr_stok
     fill_args(a, P, s, o, parity);
     int st = launch_va(ctx, P, a, diag);
     if (st) return st;
+    P.last_diag = diag != 0;
 
     BcArgsB b;
-    b.A[0] = BcArrB{box_arr(in, S_Vx, S_N, P), box_arr(out, S_Vx, S_N, P), F(Ux), {nx + 1, ny + 2, nz + 2}, {1, 0, 0}, 0};
-    b.A[1] = BcArrB{box_arr(in, S_Vy, S_N, P), box_arr(out, S_Vy, S_N, P), F(Uy), {nx + 2, ny + 1, nz + 2}, {0, 1, 0}, 1};
-    b.A[2] = BcArrB{box_arr(in, S_Vz, S_N, P), box_arr(out, S_Vz, S_N, P), F(Uz), {nx + 2, ny + 2, nz + 1}, {0, 0, 1}, 2};
+    b.A[0] = BcArrB{box_arr(in, S_Vx, S_N, P), box_arr(out, S_Vx, S_N, P), F(Ux), F(Vx), {nx + 1, ny + 2, nz + 2}, {1, 0, 0}, 0};
+    b.A[1] = BcArrB{box_arr(in, S_Vy, S_N, P), box_arr(out, S_Vy, S_N, P), F(Uy), F(Vy), {nx + 2, ny + 1, nz + 2}, {0, 1, 0}, 1};
+    b.A[2] = BcArrB{box_arr(in, S_Vz, S_N, P), box_arr(out, S_Vz, S_N, P), F(Uz), F(Vz), {nx + 2, ny + 2, nz + 1}, {0, 0, 1}, 2};
     // flags: left,right,front,back,top,bot.  no_slip: bot → z lo, top → z hi; free_slip (Q2): top → z lo, bot → z hi
     const int32_t *fs = o->free_slip, *ns = o->no_slip;
     b.lo_fs[0] = fs[0]; b.hi_fs[0] = fs[1]; b.lo_ns[0] = ns[0]; b.hi_ns[0] = ns[1];
@@ -1023,7 +1056,10 @@ int jr_stokes3d_VA_fused_iter(jr_context *ctx, const jr_fields *s, const jr_stok
     return JR_OK;
 }
 
-// unpack the current state set into the user's dense arrays; `niter` = iterations done since begin
+// make the user's dense arrays current; `niter` = iterations done since begin.  An observable (DIAG) iteration has
+// already written the whole state to the dense arrays (kernel + BC kernel), so after a solve — whose loop can only end
+// on such an iteration — there is nothing to unpack; with a communicator attached the halo planes of V were exchanged
+// on the box set afterwards, so V is still unpacked.
 int jr_stokes3d_VA_fused_finish(jr_context *ctx, const jr_fields *s, int64_t niter)
 {
     auto it = g_plans.find(ctx);
@@ -1031,9 +1067,12 @@ int jr_stokes3d_VA_fused_finish(jr_context *ctx, const jr_fields *s, int64_t nit
     const VaPlan &P = it->second;
     const int nx = P.nx, ny = P.ny, nz = P.nz;
     double *cur = P.S[niter & 1];
+    if (P.last_diag && !ctx->comm && niter > 0) return JR_OK;
+    const bool v_only = P.last_diag && niter > 0;
     PackArgs pa;
     pa.njobs = 0;
     auto add = [&](double *dense, int a, int n0, int n1, int n2, int o0, int o1, int o2) {
+        if (v_only && a != S_Vx && a != S_Vy && a != S_Vz) return;
         PackJob &J = pa.j[pa.njobs++];
         J.dense = dense; J.box = box_arr(cur, a, S_N, P);
         J.n[0] = n0; J.n[1] = n1; J.n[2] = n2; J.o[0] = o0; J.o[1] = o1; J.o[2] = o2; J.mode = 1;

@@ -36,8 +36,10 @@ def context(device: Optional[int] = None):
     dev = torch.cuda.current_device() if device is None else int(device)
     if dev not in _ctx_cache:
         h = C.c_void_p()
+        # torch's default stream has handle 0 = the legacy default stream; pass it as cudaStreamLegacy (0x1) so the library's
+        # launches are ordered with torch's fills / copies of the same arrays (handle 0 would ask for an own stream)
         stream = torch.cuda.current_stream(dev).cuda_stream
-        _abi.check(_abi.lib().jr_context_create(dev, C.c_void_p(stream) if stream else None, C.byref(h)))
+        _abi.check(_abi.lib().jr_context_create(dev, C.c_void_p(stream if stream else 1), C.byref(h)))
         _ctx_cache[dev] = h
     return _ctx_cache[dev]
 
@@ -206,6 +208,40 @@ def iterate_(stokes: StokesArrays, pt_stokes, grid, flow_bcs, ρg, K, G, dt, nit
     return SimpleNamespace(iter=int(res.iter), time=float(res.time_s), kernel_launches=int(res.kernel_launches))
 
 
+class IterationSession:
+    """3D-VA PT iterations with the state resident in the library's TMA box layout between calls (jr_stokes3d_VA_begin /
+    _step / _end): the body of the reference's `while` loop (Stokes3D.jl:76-122) for a host that keeps its own convergence
+    logic.  `step(n)` returns the device time of exactly those n iterations.
+
+        with IterationSession(stokes, pt, grid, bcs, ρg, K, G, dt, igg) as it:
+            it.step(10); r = it.step(200)       # r.time: CUDA-event seconds of the 200 iterations
+    """
+
+    def __init__(self, stokes: StokesArrays, pt_stokes, grid, flow_bcs, ρg, K, G, dt, igg: Optional[IGG] = None, *, nout=10 ** 9):
+        igg = igg or IGG()
+        grid = _grid_of(stokes, grid, igg)
+        self._opts = build_opts(pt_stokes, grid._di.center, dt, flow_bcs, igg.n_g(stokes.ni), iterMax=10 ** 9, nout=nout)
+        self._keep = va_slots(stokes, ρg, K, G)
+        self._fs = build_fields(self._keep, stokes.ni)
+        self._open = False
+
+    def __enter__(self):
+        _abi.check(_abi.lib().jr_stokes3d_VA_begin(context(), C.byref(self._fs), C.byref(self._opts)))
+        self._open = True
+        return self
+
+    def step(self, niter: int, observe_last: bool = False):
+        res = _abi.StokesResult()
+        _abi.check(_abi.lib().jr_stokes3d_VA_step(context(), int(niter), int(bool(observe_last)), C.byref(res)))
+        return SimpleNamespace(iter=int(res.iter), time=float(res.time_s), kernel_launches=int(res.kernel_launches))
+
+    def __exit__(self, *exc):
+        if self._open:
+            self._open = False
+            _abi.check(_abi.lib().jr_stokes3d_VA_end(context()))
+        return False
+
+
 def plan_info():
     """Facts about the fused plan of the last 3D-VA solve on this device (tile rows, z-chunks, constant-ρg elision …)."""
     info = (C.c_int32 * 8)()
@@ -263,6 +299,19 @@ def sumsq_interior(A, interior: bool = True) -> float:
     return out.value
 
 
+def residual_norms3d_(stokes, igg: Optional[IGG] = None):
+    """the four residual norms the 3D loops sample every `nout` iterations (Stokes3D.jl:125-142): ‖R‖₂ of the interior of Rx, Ry, Rz
+    and of RP (norm_mpi: all-reduced sums of squares), divided by the reference's normalisers (quirk Q4)"""
+    ss = [sumsq_interior(stokes.R.Rx), sumsq_interior(stokes.R.Ry), sumsq_interior(stokes.R.Rz), sumsq_interior(stokes.R.RP, False)]
+    if igg is not None and igg.nprocs > 1:
+        from .comm import _allreduce
+
+        ss = _allreduce(ss, 0)
+    gx, gy, gz = (igg or IGG()).n_g(stokes.ni)
+    den = ((gx - 2) * (gy - 1) * (gz - 1), (gx - 1) * (gy - 2) * (gz - 1), (gx - 1) * (gy - 1) * (gz - 2), gx * gy * gz)
+    return tuple(math.sqrt(v) / d for v, d in zip(ss, den))
+
+
 def norm_interior(A, interior: bool = True) -> float:
     return math.sqrt(sumsq_interior(A, interior))
 
@@ -282,6 +331,13 @@ def _common_checks(stokes, flow_bcs, arrays):
             raise ValueError("array arguments must be B200 arrays (use PTArray(B200Backend)(x))")
 
 
+def _single_rank2d(igg):
+    """the 2D solvers have no halo exchange / all-reduced norms (libjrb200 returns JR_ERR_UNSUPPORTED too): refuse loudly
+    instead of returning rank-local answers"""
+    if igg is not None and igg.nprocs > 1:
+        raise NotImplementedError(f"the 2D Stokes solvers of the B200 backend run on one rank only (igg.nprocs = {igg.nprocs})")
+
+
 def _print_hist2(out, igg, verbose):
     if verbose and igg.me == 0:
         for c in range(len(out.err_evo1)):
@@ -295,6 +351,7 @@ def _solve2d_V2(stokes, pt_stokes, di, flow_bcs, ρg, G, K, dt, igg: Optional[IG
     kw.update(kwargs or {})
     _common_checks(stokes, flow_bcs, (*ρg, G, K))
     igg = igg or IGG()
+    _single_rank2d(igg)
     grid = _grid_of(stokes, di, igg)
     opts = build_opts(pt_stokes, grid._di.center, dt, flow_bcs, igg.n_g(stokes.ni), iterMax=kw["iterMax"], nout=kw["nout"])
     fs = build_fields(va_slots(stokes, ρg, K, G), stokes.ni)
@@ -311,6 +368,7 @@ def _solve2d_V2(stokes, pt_stokes, di, flow_bcs, ρg, G, K, dt, igg: Optional[IG
 def iterate2d_V2_(stokes, pt_stokes, di, flow_bcs, ρg, G, K, dt, niter: int, igg: Optional[IGG] = None):
     """exactly `niter` PT iterations of variant 2D-V2 (benchmark / fixed-iteration parity)"""
     igg = igg or IGG()
+    _single_rank2d(igg)
     grid = _grid_of(stokes, di, igg)
     opts = build_opts(pt_stokes, grid._di.center, dt, flow_bcs, igg.n_g(stokes.ni), iterMax=niter, nout=max(niter, 1))
     fs = build_fields(va_slots(stokes, ρg, K, G), stokes.ni)
@@ -345,16 +403,41 @@ def vc_inputs(rheology, phase_ratios: PhaseRatios, *, free_surface: float = 0.0)
     return vc
 
 
+def _args_items(args) -> dict:
+    if args is None:
+        return {}
+    if isinstance(args, dict):
+        return dict(args)
+    if hasattr(args, "_asdict"):
+        return dict(args._asdict())
+    return dict(vars(args))
+
+
 def vc_slots(stokes, ρg, args) -> dict:
+    """field slots of a VC solve.  `args` is the reference's NamedTuple (Stokes2D.jl:577-599, Stokes3D.jl:447-466): T (ni.+2, cell
+    centres with one ghost layer) and P feed the density / viscosity laws, ΔT (ni) switches compute_P! to the thermal-stress form
+    (PressureKernels.jl:128-149,197-206), dt is carried by the miniapps but never read by the lowered laws.  Every other key —
+    melt_fraction (PressureKernels.jl:151-176), perturbation_C (StressUpdate.jl:146-176), … — selects behaviour this backend does
+    not have: it raises instead of being dropped."""
     d = stokes.slots()
     d["rhogx"], d["rhogy"] = ρg[0], ρg[1]
     if len(ρg) > 2:
         d["rhogz"] = ρg[2]
-    T, P = (args.get("T"), args.get("P")) if isinstance(args, dict) else (getattr(args, "T", None), getattr(args, "P", None))
-    if T is not None:
-        d["T"] = T
-    if P is not None:
-        d["Pargs"] = P
+    items = _args_items(args)
+    known = {"T": "T", "P": "Pargs", "ΔT": "dTargs", "dT": "dTargs"}
+    for k, v in items.items():
+        if k == "dt":
+            continue
+        if k not in known:
+            raise NotImplementedError(f"args.{k} is not supported by the B200 backend (supported keys: T, P, ΔT, dt); "
+                                      "refusing to ignore it")
+        if v is None:
+            continue
+        if not is_device_array(v):
+            raise ValueError(f"args.{k} must be a B200 array (use PTArray(B200Backend)(x))")
+        d[known[k]] = v
+    if "dTargs" in d and tuple(d["dTargs"].shape) != tuple(stokes.ni):
+        raise ValueError(f"args.ΔT must live at the cell centres, size {tuple(stokes.ni)} (got {tuple(d['dTargs'].shape)})")
     return d
 
 
@@ -373,6 +456,7 @@ def _solve2d_VC(stokes, pt_stokes, di, flow_bcs, ρg, phase_ratios, rheology, ar
         raise NotImplementedError("strain_increment = true (Δε form) is outside the supported subset (SURVEY §8f-3)")
     _common_checks(stokes, flow_bcs, ρg)
     igg = igg or IGG()
+    _single_rank2d(igg)
     grid = _grid_of(stokes, di, igg)
     opts = _vc_opts(stokes, pt_stokes, grid, flow_bcs, dt, igg, kw)
     vc = vc_inputs(rheology, phase_ratios, free_surface=float(dt) * float(kw["free_surface"]) if kw["free_surface"] else 0.0)
@@ -394,6 +478,7 @@ def iterate2d_VC_(stokes, pt_stokes, di, flow_bcs, ρg, phase_ratios, rheology, 
               viscosity_cutoff=(-math.inf, math.inf))
     kw.update(kwargs or {})
     igg = igg or IGG()
+    _single_rank2d(igg)
     grid = _grid_of(stokes, di, igg)
     opts = _vc_opts(stokes, pt_stokes, grid, flow_bcs, dt, igg, kw)
     vc = vc_inputs(rheology, phase_ratios, free_surface=float(dt) * float(kw["free_surface"]) if kw["free_surface"] else 0.0)

@@ -371,6 +371,7 @@ class IGG:
     coords: Sequence[int] = (0, 0, 0)
     comm_cart: object = None
     overlaps: Sequence[int] = (2, 2, 2)
+    nxyz: Optional[Sequence[int]] = None   # local cell counts given to init_global_grid (IGG keeps them as nxyz)
 
     def n_g(self, ni: Sequence[int]):
         """nx_g(), ny_g(), nz_g(): dims·(n − overlap) + overlap  (ImplicitGlobalGrid)."""

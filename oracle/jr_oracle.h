@@ -52,7 +52,8 @@ extern "C" {
     X(divU) X(lam) X(lamv) X(dPpsi)                                            \
     X(rhogx) X(rhogy) X(rhogz)                                                 \
     X(K) X(G) X(T) X(Pargs)                                                    \
-    X(txx_v) X(tyy_v) X(txx_o_v) X(tyy_o_v)
+    X(txx_v) X(tyy_v) X(txx_o_v) X(tyy_o_v)                                    \
+    X(dTargs)
 
 enum orc_field {
 #define X(n) ORC_F_##n,

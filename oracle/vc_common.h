@@ -25,6 +25,25 @@ static inline double ratio_Kb(const orc_vc_inputs *vc, const double *ph, size_t 
     for (int p = 0; p < vc->nphase; p++) { const double r = ph[(size_t)p * stride + idx]; x += (r == 0.0) ? 0.0 : vc->phases[p].Kb * r; }
     return x;
 }
+/* fn_ratio(get_thermal_expansion, rheology, ratio)  rheology/GeoParams.jl:17: α of the density law, 0 for ConstantDensity */
+static inline double ratio_alpha(const orc_vc_inputs *vc, const double *ph, size_t stride, size_t idx)
+{
+    double x = 0.0;
+    for (int p = 0; p < vc->nphase; p++) {
+        const double r = ph[(size_t)p * stride + idx];
+        x += (r == 0.0) ? 0.0 : (vc->phases[p].rho_kind == 0 ? 0.0 : vc->phases[p].alpha) * r;
+    }
+    return x;
+}
+/* _compute_P! with thermal stresses  PressureKernels.jl:197-206 */
+static inline void P_point_dT(double *RP, double *P, double P0, double divV, double Q, double dT, double alpha, double eta, double K, double G,
+                              double dt, double r, double theta_dtau)
+{
+    const double _Kdt = orc_inv(K * dt), _Gdt = orc_inv(G * dt), _dt = orc_inv(dt), Pc = *P;
+    *RP = fma(-(Pc - P0), _Kdt, (-divV + (alpha * (dT * _dt)) + (Q * _dt)));
+    const double psi = orc_inv(orc_inv(eta) + _Gdt) * r / theta_dtau;
+    *P = ((fma(P0, _Kdt, (-divV + (alpha * (dT * _dt)) + (Q * _dt)))) * psi + Pc) / (1 + _Kdt * psi);
+}
 /* plastic_params_phase  StressUpdate.jl:153-176: is_pl if any phase with non-zero ratio is plastic; η_reg = Σ η_vp·ratio */
 static inline void plastic_params(const orc_vc_inputs *vc, const double *ph, size_t stride, size_t idx, int *is_pl, double *eta_reg)
 {

@@ -135,12 +135,14 @@ def random_vc2d(ni, seed, nphase=3, plastic=True, rho_var=False):
     return f, grid, pt, dt, rat, tuple(rheo)
 
 
-def _run_vc(oracle, ni, f, grid, pt, dt, rat, rheo, flags, niter, finish, free_surface=False, alias_P=False):
+def _run_vc(oracle, ni, f, grid, pt, dt, rat, rheo, flags, niter, finish, free_surface=False, alias_P=False, dT=None):
     from justrelax_jl_b200 import B200Backend, PhaseRatios, rheology as R, stokes as jst
 
     d = oracle.alloc_stokes(ni, f)
     if alias_P:
         d["Pargs"] = d["P"]
+    if dT is not None:
+        d["dTargs"] = dT
     st, extra = device_stokes(ni, d)
     rows = R.lower_stokes(rheo)
     vc = oracle.vc_inputs(rows, R.gravity_of(rheo), rat, free_surface=dt if free_surface else 0.0)
@@ -148,6 +150,8 @@ def _run_vc(oracle, ni, f, grid, pt, dt, rat, rheo, flags, niter, finish, free_s
     oracle.iterate2d_VC(d, ni, opts, vc, niter, finish=finish)
     pr = PhaseRatios.from_arrays(B200Backend, **rat)
     args = dict(T=extra["T"], P=st.P if alias_P else extra["Pargs"])
+    if dT is not None:
+        args["ΔT"] = extra["dTargs"]
     jst.iterate2d_VC_(st, pt, grid, _bcs(flags), (extra["rhogx"], extra["rhogy"]), pr, rheo, args, dt, niter, finish=finish,
                       kwargs=dict(viscosity_relaxation=0.3, free_surface=free_surface))
     return {**st.slots(), "rhogx": extra["rhogx"], "rhogy": extra["rhogy"]}, d
@@ -162,6 +166,21 @@ def test_vc_fixed_iterations_random_state(oracle, ni, rho_var):
         st, d = _run_vc(oracle, ni, f, grid, pt, dt, rat, rheo, flags, niter, False, alias_P=rho_var)
         assert d["lam"].max() > 0 and d["lamv"].max() > 0, "the random state must yield somewhere"
         compare_slots(st, d, VC_STATE + VC_DIAG, TOL, f"VC ni={ni} niter={niter}")
+
+
+def test_vc_thermal_stress_pressure_form(oracle):
+    """args.ΔT given: thermal-stress form of compute_P! (PressureKernels.jl:128-149,197-206) in the fused 2D kernel"""
+    from justrelax_jl_b200 import to_host
+
+    ni = (45, 38)
+    f, grid, pt, dt, rat, rheo = random_vc2d(ni, 12, rho_var=True)
+    flags = dict(free_slip=[1, 1, 0, 0, 1, 1], no_slip=[0] * 6, periodic=[0] * 6)
+    dT = np.asfortranarray(np.random.default_rng(6).uniform(-2.0e3, 2.0e3, size=ni))
+    for niter in (1, 4):
+        st, d = _run_vc(oracle, ni, f, grid, pt, dt, rat, rheo, flags, niter, False, alias_P=True, dT=dT)
+        compare_slots(st, d, VC_STATE + VC_DIAG, TOL, f"2D-VC with ΔT niter={niter}")
+    st0, d0 = _run_vc(oracle, ni, f, grid, pt, dt, rat, rheo, flags, 4, False, alias_P=True)
+    assert max_rel_diff(to_host(st["P"]), d0["P"]) > 1e-4, "ΔT must change the pressure"
 
 
 def test_vc_exit_kernels_free_surface_and_mixed_bcs(oracle):

@@ -27,7 +27,7 @@ def _bcs(flags):
     return VelocityBoundaryConditions(free_slip=pick("free_slip"), no_slip=pick("no_slip"), periodic=pick("periodic"))
 
 
-def _run(oracle, s, flags, niter, finish, *, alias_P=True, kw=None):
+def _run(oracle, s, flags, niter, finish, *, alias_P=True, kw=None, dT=None):
     from justrelax_jl_b200 import B200Backend, PhaseRatios, rheology as R
     from justrelax_jl_b200.stokes3d_vc import iterate3d_VC_
 
@@ -35,13 +35,17 @@ def _run(oracle, s, flags, niter, finish, *, alias_P=True, kw=None):
     d = oracle.alloc_stokes(s.ni, s.fields)
     if alias_P:
         d["Pargs"] = d["P"]
+    if dT is not None:
+        d["dTargs"] = dT
     st, extra = device_stokes(s.ni, d)
     vc = oracle.vc_inputs(R.lower_stokes(s.rheology), R.gravity_of(s.rheology), s.ratios)
     opts = oracle.make_opts(s.pt_stokes, s.grid._di.center, s.dt, flags, s.ni, iterMax=niter, nout=niter, viscosity_relaxation=kw["viscosity_relaxation"],
                             lambda_relaxation=kw["λ_relaxation"], viscosity_cutoff=kw["viscosity_cutoff"])
     oracle.iterate3d_VC(d, s.ni, opts, vc, niter, finish=finish)
     pr = PhaseRatios.from_arrays(B200Backend, **s.ratios)
-    args = dict(T=extra["T"], P=st.P if alias_P else extra["Pargs"])
+    args = dict(T=extra["T"], P=st.P if alias_P else extra["Pargs"], dt=s.dt)
+    if dT is not None:
+        args["ΔT"] = extra["dTargs"]
     ρg = (extra["rhogx"], extra["rhogy"], extra["rhogz"])
     r = iterate3d_VC_(st, s.pt_stokes, s.grid, _bcs(flags), ρg, pr, s.rheology, args, s.dt, niter, finish=finish, kwargs=kw)
     assert r.kernel_launches >= 3 * niter
@@ -58,6 +62,22 @@ def test_vc3_fixed_iterations_random_state(oracle, ni):
         st, d = _run(oracle, s, flags, niter, False)
         assert d["lam"].max() > 0 and np.abs(d["pyz"]).max() > 0, "the random state must yield somewhere"
         compare_slots(st, d, STATE + DIAG, TOL, f"3D-VC ni={ni} niter={niter}")
+
+
+def test_vc3_thermal_stress_pressure_form(oracle):
+    """args.ΔT given: compute_P! takes the thermal-stress form (PressureKernels.jl:128-149,197-206) with α = fn_ratio(get_thermal_expansion, …);
+    parity with the oracle, and the pressure really differs from the run without ΔT"""
+    from justrelax_jl_b200 import setups, to_host
+
+    ni = (21, 18, 13)
+    s = setups.random_vc3d(ni, seed=31)
+    flags = dict(free_slip=[1] * 6, no_slip=[0] * 6, periodic=[0] * 6)
+    dT = np.asfortranarray(np.random.default_rng(5).uniform(-50.0, 50.0, size=ni))
+    for niter in (1, 3):
+        st, d = _run(oracle, s, flags, niter, False, dT=dT)
+        compare_slots(st, d, STATE + DIAG, TOL, f"3D-VC with ΔT niter={niter}")
+    st0, d0 = _run(oracle, s, flags, 3, False)
+    assert max_rel_diff(to_host(st["P"]), d0["P"]) > 1e-3, "ΔT must change the pressure"
 
 
 def test_vc3_exit_kernels_mixed_bcs_one_hot_phases(oracle):

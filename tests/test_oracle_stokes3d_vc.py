@@ -184,3 +184,44 @@ def test_vc_iteration_matches_independent_restatement(oracle):
     assert np.allclose(d["tyz"][nonpl], (ref["tyz"] + dtyz)[nonpl], rtol=0, atol=1e-13)
     assert np.all(d["pyz"][nonpl] == 0)
     assert np.abs(d["pyz"]).max() > 0                      # some edges yielded
+
+
+def test_thermal_stress_pressure_form_identity(oracle):
+    """compute_P_kernel! with ΔT (PressureKernels.jl:128-149,197-206): RP gains exactly α·ΔT/dt with α = Σ ratio·α_phase (the α of the
+    density law, 0 for ConstantDensity: test/test_rheology.jl:57-116), and with ΔT ≡ 0 the result is the plain form's bit for bit"""
+    import ctypes as C
+
+    from justrelax_jl_b200 import rheology as R, setups
+
+    ni = (9, 8, 7)
+    s = setups.random_vc3d(ni, seed=3)
+    flags = dict(free_slip=[1] * 6, no_slip=[0] * 6, periodic=[0] * 6)
+    vc = oracle.vc_inputs(R.lower_stokes(s.rheology), R.gravity_of(s.rheology), s.ratios)
+    opts = oracle.make_opts(s.pt_stokes, s.grid._di.center, s.dt, flags, s.ni, iterMax=1, nout=1, viscosity_cutoff=s.kwargs["viscosity_cutoff"])
+    dT = np.asfortranarray(np.random.default_rng(1).uniform(-30.0, 30.0, size=ni))
+    out = {}
+    for tag, arr in (("none", None), ("zero", np.zeros(ni, order="F")), ("dT", dT)):
+        d = oracle.alloc_stokes(s.ni, s.fields)
+        d["Pargs"] = d["P"]
+        if arr is not None:
+            d["dTargs"] = arr
+        oracle.iterate3d_VC(d, s.ni, opts, vc, 1, finish=False)
+        out[tag] = d
+    assert np.array_equal(out["none"]["RP"], out["zero"]["RP"]) and np.array_equal(out["none"]["P"], out["zero"]["P"])
+    alpha = s.ratios["center"][..., 0] * 3.0e-2     # only phase 1 carries a T-dependent density (α = 3e-2)
+    assert np.allclose(out["dT"]["RP"] - out["none"]["RP"], alpha * dT / s.dt, rtol=1e-9, atol=1e-12)
+    assert np.abs(out["dT"]["P"] - out["none"]["P"]).max() > 1e-3
+
+
+def test_unknown_args_key_fails_loudly():
+    """args keys the backend does not consume (melt_fraction: PressureKernels.jl:151-176; perturbation_C: StressUpdate.jl:146-176) raise"""
+    import pytest
+
+    from justrelax_jl_b200 import CPUBackend, StokesArrays
+    from justrelax_jl_b200.stokes import vc_slots
+
+    st = StokesArrays(CPUBackend, 4, 4, 4)
+    for bad in ("melt_fraction", "perturbation_C", "ϕ"):
+        with pytest.raises(NotImplementedError, match="refusing to ignore"):
+            vc_slots(st, (st.P, st.P, st.P), {bad: st.P})
+    assert "dTargs" not in vc_slots(st, (st.P, st.P, st.P), dict(dt=0.1))
