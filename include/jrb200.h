@@ -249,6 +249,26 @@ int jr_scale_copy(jr_context *ctx, double *dst, const double *src, double factor
 /* Σ A[2:end-1,…]^2 (interior != 0) or Σ A^2 — the local part of norm_mpi, src/Utils.jl:698-701 */
 int jr_sumsq(jr_context *ctx, const double *A, const int32_t n[3], int interior, double *out_host);
 
+/* --- per-time-step kernels between the Stokes and the thermal loops (a coupled time step stays on the GPU) ----------------
+ * velocity2vertex!(Vx_v, Vy_v[, Vz_v], Vx, Vy[, Vz]) / velocity2center!(Vx_c, Vy_c[, Vz_c], Vx, Vy[, Vz])
+ * (src/ext/CUDA/3D.jl:344-356 → src/Interpolations.jl:212-289): n = local cells, out_ext = size of the output arrays (the
+ * reference launches over size(Vx_v) / size(Vx_c)). */
+int jr_velocity2vertex(jr_context *ctx, int32_t ndim, const int32_t n[3], const int32_t out_ext[3], double *Vx_v, double *Vy_v, double *Vz_v,
+                       const double *Vx, const double *Vy, const double *Vz);
+int jr_velocity2center(jr_context *ctx, int32_t ndim, const int32_t n[3], const int32_t out_ext[3], double *Vx_c, double *Vy_c, double *Vz_c,
+                       const double *Vx, const double *Vy, const double *Vz);
+/* compute_lithostatic_pressure!(P, ρg, dz[, igg]) (src/Utils.jl:541-617): P[j] = Σ_{k>j} ρg[k] dz[k] + ρg[j] dz[j] / 2 along the last
+ * dimension; n = size(P); dz_cells = DEVICE vector of cell heights or NULL (then the scalar dz); across_ranks != 0 = the four-argument
+ * method: the weight of the cells held by the ranks stacked above is gathered over peer memory (replaces MPI.Allgather on the vertical
+ * sub-communicator), ncell_vertical = the local cell count given to init_global_grid in the vertical direction (IGG's nxyz[N]).
+ * Without across_ranks the call fails (like the reference) when the vertical direction is split across ranks. */
+int jr_lithostatic_pressure(jr_context *ctx, int32_t ndim, const int32_t n[3], double *P, const double *rhog, double dz, const double *dz_cells,
+                            int across_ranks, int32_t ncell_vertical);
+/* compute_shear_heating!(thermal, stokes, [phase_ratios,] rheology, dt) (src/thermal_diffusion/ShearHeating.jl:14-72):
+ * shear_heating = max(0, Χ τij (εij − εij_el)), εij_el = ½(τij − τij_o)/(G dt); Χ per phase in chi_host[nphase] (GeoParams
+ * ConstantShearheating); vc->ph_center NULL = the single-MaterialParams method. */
+int jr_compute_shear_heating(jr_context *ctx, const jr_fields *s, const jr_vc_inputs *vc, const double *chi_host, double dt, double *shear_heating);
+
 /* --- thermal diffusion: heatdiffusion_PT! ------------------------------------------------------------------------
  * replaces JR{2,3}D.heatdiffusion_PT!(::CUDABackendTrait, thermal, args...; kwargs) (src/ext/CUDA/3D.jl:383-385 →
  * src/thermal_diffusion/DiffusionPT_solver.jl:34-149 [K, ρCp arrays] and :181-305 [rheology]).

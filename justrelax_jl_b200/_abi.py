@@ -186,6 +186,10 @@ def _declare(L):
     L.jr_accumulate_tensor3d.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32p, C.c_double]
     L.jr_accumulate_vol.argtypes = [vp, vp, vp, C.c_size_t, C.c_double]
     L.jr_absmax.argtypes = [vp, vp, C.c_size_t, C.c_int, C.POINTER(C.c_double)]
+    L.jr_velocity2vertex.argtypes = [vp, C.c_int32, i32p, i32p, vp, vp, vp, vp, vp, vp]
+    L.jr_velocity2center.argtypes = [vp, C.c_int32, i32p, i32p, vp, vp, vp, vp, vp, vp]
+    L.jr_lithostatic_pressure.argtypes = [vp, C.c_int32, i32p, vp, vp, C.c_double, vp, C.c_int, C.c_int32]
+    L.jr_compute_shear_heating.argtypes = [vp, vp, vc, C.POINTER(C.c_double), C.c_double, vp]
     L.jr_heatdiffusion_PT.argtypes = [vp, C.POINTER(ThermalFields), C.POINTER(ThermalOpts), vp, vp, C.POINTER(ThermalResult)]
     L.jr_thermal_iterate.argtypes = [vp, C.POINTER(ThermalFields), C.POINTER(ThermalOpts), C.c_int64, C.POINTER(ThermalResult)]
     L.jr_thermal_bcs.argtypes = [vp, vp, C.c_int32, i32p, C.POINTER(ThermalOpts)]

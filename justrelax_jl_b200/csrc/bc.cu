@@ -168,8 +168,40 @@ __global__ void k_maxloc3(double *__restrict__ B, const double *__restrict__ A, 
     B[IX3(nx, ny, I, J, K)] = x;
 }
 
+// window (1,1,1), the one the solvers use: z-marching, the clamped 3×3 in-plane maxima of planes k−1, k, k+1 roll through registers
+// (9 loads per cell instead of 27; the max of maxima is the same value as the reference's 27-point scan: max is exact)
+#define MAXLOC_KCH 32
+__global__ void __launch_bounds__(256) k_maxloc3_w1(double *__restrict__ B, const double *__restrict__ A, int nx, int ny, int nz)
+{
+    const int I = blockIdx.x * blockDim.x + threadIdx.x + 1, J = blockIdx.y * blockDim.y + threadIdx.y + 1;
+    if (I > nx || J > ny) return;
+    const int k0 = blockIdx.z * MAXLOC_KCH + 1, k1 = min(k0 + MAXLOC_KCH - 1, nz);
+    const int i0 = jr_clamp(I - 1, 1, nx), i1 = jr_clamp(I + 1, 1, nx), j0 = jr_clamp(J - 1, 1, ny), j1 = jr_clamp(J + 1, 1, ny);
+    auto plane_max = [&](int k) {
+        const int kk = jr_clamp(k, 1, nz);
+        const double *p = A + (size_t)(kk - 1) * nx * ny;
+        const double a0 = p[(size_t)(j0 - 1) * nx + i0 - 1], a1 = p[(size_t)(j0 - 1) * nx + I - 1], a2 = p[(size_t)(j0 - 1) * nx + i1 - 1];
+        const double b0 = p[(size_t)(J - 1) * nx + i0 - 1], b1 = p[(size_t)(J - 1) * nx + I - 1], b2 = p[(size_t)(J - 1) * nx + i1 - 1];
+        const double c0 = p[(size_t)(j1 - 1) * nx + i0 - 1], c1 = p[(size_t)(j1 - 1) * nx + I - 1], c2 = p[(size_t)(j1 - 1) * nx + i1 - 1];
+        return fmax(fmax(fmax(a0, a1), fmax(a2, b0)), fmax(fmax(b1, b2), fmax(fmax(c0, c1), c2)));
+    };
+    double lo = plane_max(k0 - 1), mid = plane_max(k0);
+    for (int k = k0; k <= k1; k++) {
+        const double hi = plane_max(k + 1);
+        B[IX3(nx, ny, I, J, k)] = fmax(fmax(lo, mid), hi);
+        lo = mid; mid = hi;
+    }
+}
+
 int jr_launch_maxloc3d(jr_context *ctx, double *B, const double *A, const int32_t n[3], const int32_t w[3])
 {
+    if (w[0] == 1 && w[1] == 1 && w[2] == 1) {
+        dim3 blk1(32, 8, 1), grd1((n[0] + 31) / 32, (n[1] + 7) / 8, (n[2] + MAXLOC_KCH - 1) / MAXLOC_KCH);
+        k_maxloc3_w1<<<grd1, blk1, 0, ctx->stream>>>(B, A, n[0], n[1], n[2]);
+        ctx->launches++;
+        JR_CHECK_LAUNCH();
+        return JR_OK;
+    }
     dim3 blk(32, 8, 1), grd((n[0] + 31) / 32, (n[1] + 7) / 8, n[2]);
     k_maxloc3<<<grd, blk, 0, ctx->stream>>>(B, A, n[0], n[1], n[2], w[0], w[1], w[2]);
     ctx->launches++;

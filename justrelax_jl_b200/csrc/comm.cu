@@ -64,26 +64,6 @@ __host__ __device__ inline long jr_stage_elem(const int n[3], int d, const int s
 }
 static long stage_array_size(const int n[3]) { return 2 * (jr_stage_plane_size(n, 0) + jr_stage_plane_size(n, 1) + jr_stage_plane_size(n, 2)); }
 
-// ---------------------------------------------------------------------------------------------------------------
-// device-side barrier over all ranks of the communicator (called by every block of a kernel; block 0 signals)
-__device__ __forceinline__ void jr_comm_barrier_dev(const jr_comm_dev &cd, unsigned long long epoch)
-{
-    const int t = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
-    if (t < cd.nranks && t != cd.rank) {
-        if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
-            __threadfence_system();
-            unsigned long long *f = &cd.sig[t]->flags[cd.rank];
-            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(epoch) : "memory");
-        }
-        const unsigned long long *mine = &cd.sig[cd.rank]->flags[t];
-        unsigned long long v;
-        do {
-            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
-        } while (v < epoch);
-    }
-    __syncthreads();
-}
-
 __global__ void k_comm_barrier(const __grid_constant__ jr_comm_dev cd, unsigned long long epoch) { jr_comm_barrier_dev(cd, epoch); }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -215,6 +195,13 @@ static int comm_ensure_stage(jr_context *ctx, jr_comm *cm, size_t doubles)
     }
     cm->stage_cap = cap;
     return JR_OK;
+}
+
+int jr_comm_reserve_stage(jr_context *ctx, size_t doubles)
+{
+    jr_comm *cm = ctx->comm;
+    JR_REQUIRE(cm && cm->nranks > 1, JR_ERR_ARG, "no multi-rank communicator attached to this context");
+    return comm_ensure_stage(ctx, cm, doubles);
 }
 
 int jr_comm_halo(jr_context *ctx, const jr_harr *arrs, int narr)

@@ -54,3 +54,28 @@ int jr_comm_halo(jr_context *ctx, const jr_harr *arrs, int narr);
 size_t jr_comm_halo_bytes(const jr_comm *cm, const jr_harr *arrs, int narr);
 // in-place all-reduce of n ≤ 16 device doubles (op 0 sum, 1 max, 2 min); asynchronous on ctx->stream
 int jr_comm_allreduce_dev(jr_context *ctx, double *d_vals, int n, int op);
+// make sure every rank's staging buffers hold at least `doubles` elements (collective: all ranks call it with the same size)
+int jr_comm_reserve_stage(jr_context *ctx, size_t doubles);
+
+#ifdef __CUDACC__
+// ---------------------------------------------------------------------------------------------------------------
+// device-side barrier over all ranks of the communicator (called by every block of a kernel; block 0 signals)
+__device__ __forceinline__ void jr_comm_barrier_dev(const jr_comm_dev &cd, unsigned long long epoch)
+{
+    const int t = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
+    if (t < cd.nranks && t != cd.rank) {
+        if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+            __threadfence_system();
+            unsigned long long *f = &cd.sig[t]->flags[cd.rank];
+            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(epoch) : "memory");
+        }
+        const unsigned long long *mine = &cd.sig[cd.rank]->flags[t];
+        unsigned long long v;
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
+        } while (v < epoch);
+    }
+    __syncthreads();
+}
+
+#endif

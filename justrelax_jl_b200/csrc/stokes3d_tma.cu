@@ -60,6 +60,8 @@ struct alignas(64) VaArgs {
     int nx, ny, nz, PX, PY, kchunk;
     int ntx, nty, nchunk;                      // work items: ntx · nty column tiles × nchunk z-chunks
     int slack;                                 // a CTA may run at most DEPTH + slack z-steps ahead of the slowest one
+    int stagger_ns;                            // >= 0: the compute-plane half of a step's loads is issued by the northern halo warp
+                                               // this many ns after the barrier (smooths the lock-stepped request bursts); < 0: off
     int pol_ld, pol_st;  // L2 eviction policy of the TMA loads / output stores (0 normal, 1 evict_first, 2 evict_last)
     double _dx, _dy, _dz, dt, r, theta_dtau, eta_dtau;
     double fxc, fyc, fzc;  // constant body force (RHOG = false)
@@ -74,6 +76,9 @@ struct alignas(64) VaArgs {
 };
 
 #define TXW 30  // owned columns per tile
+#ifndef JR_VA_MINB8
+#define JR_VA_MINB8 3  // dt = Inf, 8-row tiles: 80 registers, three CTAs per SM (12 tiles x 2 KB x 3 stages = 72 KB each)
+#endif
 
 __device__ __forceinline__ bool jr_elect_one()
 {
@@ -95,7 +100,7 @@ __device__ __forceinline__ bool jr_elect_one()
 //       fences between them) and applies flow_bcs! itself: every thread that holds the source of a ghost / boundary
 //       value (no_slip! → free_slip! as complete sweeps, same gather as k_bc_box3) also stores its images.
 template <int BY, bool FINITE_DT, bool DIAG, int NST, bool RHOG, bool MULTI>
-__global__ void __launch_bounds__(32 * BY, (BY <= 10 ? 2 : 1)) k_va_tma(const __grid_constant__ VaArgs a)
+__global__ void __launch_bounds__(32 * BY, (BY <= 8 ? (FINITE_DT ? 2 : JR_VA_MINB8) : BY <= 10 ? 2 : 1)) k_va_tma(const __grid_constant__ VaArgs a)
 {
     using M = SlotMap<FINITE_DT, RHOG>;
     constexpr int TY = BY - 2, TILE = 32 * BY;
@@ -132,20 +137,23 @@ __global__ void __launch_bounds__(32 * BY, (BY <= 10 ? 2 : 1)) k_va_tma(const __
         p_x0 = bx * TXW; p_y0 = by * TY; p_kb = chunk * a.kchunk;
     };
     // loads of step p_g (one elected lane).  Step 0 of an item only needs V, η[, G] of plane kb−1 (queue fill).
-    auto p_issue = [&]() {
+    // part 0: everything; 1: the arrival-plane boxes (+ the expect_tx of the whole step); 2: the compute-plane boxes only
+    auto p_issue = [&](int part) {
         const uint64_t pld = jr_l2_policy(a.pol_ld);
         const int k = p_kb - 2 + p_l;
         const bool full = p_l > 0;
         uint64_t *bar = &full_bar[p_slot];
         double *d = sm + (size_t)p_slot * SLOT;
         const int za = k + 2, zc = k + 1;  // arrival plane (V, η, top edges) / compute plane
-        uint32_t bytes = (5 + 1 + (FINITE_DT ? 1 : 0)) * TILE_BYTES;
-        if (full) bytes = NARR * TILE_BYTES;
-        jr_mbar_arrive_expect_tx(bar, bytes);
-        jr_tma_load_4d_hint(d + T_Vx * TILE, mS, p_x0, p_y0, S_Vx, za, bar, pld);
-        jr_tma_load_4d_hint(d + T_eta * TILE, &a.mC1, p_x0, p_y0, C_eta, za, bar, pld);
-        if (FINITE_DT) jr_tma_load_4d_hint(d + M::G * TILE, &a.mD1, p_x0, p_y0, D_G, za, bar, pld);
-        if (full) {
+        if (part != 2) {
+            uint32_t bytes = (5 + 1 + (FINITE_DT ? 1 : 0)) * TILE_BYTES;
+            if (full) bytes = NARR * TILE_BYTES;
+            jr_mbar_arrive_expect_tx(bar, bytes);
+            jr_tma_load_4d_hint(d + T_Vx * TILE, mS, p_x0, p_y0, S_Vx, za, bar, pld);
+            jr_tma_load_4d_hint(d + T_eta * TILE, &a.mC1, p_x0, p_y0, C_eta, za, bar, pld);
+            if (FINITE_DT) jr_tma_load_4d_hint(d + M::G * TILE, &a.mD1, p_x0, p_y0, D_G, za, bar, pld);
+        }
+        if (full && part != 1) {
             jr_tma_load_4d_hint(d + T_tzz * TILE, mS, p_x0, p_y0, S_tzz, zc, bar, pld);
             if (FINITE_DT) {
                 jr_tma_load_4d_hint(d + M::oyz * TILE, &a.mD2, p_x0, p_y0, D_oyz, za, bar, pld);
@@ -243,7 +251,7 @@ __global__ void __launch_bounds__(32 * BY, (BY <= 10 ? 2 : 1)) k_va_tma(const __
                         jr_tma_prefetch_desc(&a.mC4);
                         if (MULTI) jr_tma_prefetch_desc(&a.mS5b);
                     }
-                    p_issue();
+                    p_issue(0);
                 }
             }
             p_advance();
@@ -344,7 +352,18 @@ __global__ void __launch_bounds__(32 * BY, (BY <= 10 ? 2 : 1)) k_va_tma(const __
                             while (seen < target) asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(a.progress) : "memory");
                         }
                         jr_fence_proxy_async();
-                        p_issue();
+                        p_issue(a.stagger_ns >= 0 ? 1 : 0);
+                    }
+                }
+                __syncwarp();
+            } else if (ty == BY - 1 && a.stagger_ns >= 0) {
+                // second half of the step's loads, from the northern halo warp (it has no store work either), a little later:
+                // the grid runs in lock-step, so issuing everything at the barrier makes the whole GPU's requests arrive in bursts
+                if (p_g < my_steps && p_l > 0) {
+                    if (jr_elect_one()) {
+                        if (a.stagger_ns > 0) __nanosleep(a.stagger_ns);
+                        jr_fence_proxy_async();
+                        p_issue(2);
                     }
                 }
                 __syncwarp();
@@ -559,49 +578,65 @@ struct BcArgsB {
     double dt;
 };
 
-__global__ void k_bc_box3(const __grid_constant__ BcArgsB b)
+#define BC_ROWS 4   // rows per thread: the four gathers are independent and issued back to back (the kernel is pure latency)
+__global__ void __launch_bounds__(256) k_bc_box3(const __grid_constant__ BcArgsB b)
 {
     const int which = blockIdx.z / 6, plane = blockIdx.z % 6;  // component, (dim, lo/hi)
     const BcArrB &A = b.A[which];
     const int d = plane >> 1, hi = plane & 1;
-    const int p = blockIdx.x * blockDim.x + threadIdx.x, q = blockIdx.y * blockDim.y + threadIdx.y;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
     // fastest-varying free coordinate on threadIdx.x: for d = 0 planes use (dim1, dim2), else dim0 first
-    int c[3];
     const int u = (d == 0) ? 1 : 0, v = (d == 2) ? 1 : 2;
-    if (p >= A.n[u] || q >= A.n[v]) return;
-    c[d] = hi ? A.n[d] - 1 : 0;
-    c[u] = p;
-    c[v] = q;
-    int s[3] = {c[0], c[1], c[2]};
-    double sign = 1.0;
-    bool zero = false;
+    if (p >= A.n[u]) return;
+    size_t ic[BC_ROWS], dc[BC_ROWS];
+    double val[BC_ROWS], vin[BC_ROWS];
+    bool ok[BC_ROWS];
 #pragma unroll
-    for (int e = 0; e < 3; e++) {
-        const bool lo_e = c[e] == 0, hi_e = c[e] == A.n[e] - 1;
-        if (!lo_e && !hi_e) continue;
-        // no_slip! runs before free_slip! (BoundaryConditions.jl:86-99): on a side that carries both
-        // (possible through quirk Q2) the free-slip copy wins for the tangential ghosts, the normal face stays 0
-        const bool fsl = lo_e ? b.lo_fs[e] : b.hi_fs[e], nsl = lo_e ? b.lo_ns[e] : b.hi_ns[e];
-        if (e == A.normal) {
-            if (nsl) zero = true;
-        } else if (fsl || nsl) {
-            s[e] = lo_e ? 1 : A.n[e] - 2;
-            if (!fsl) sign = -sign;
+    for (int r = 0; r < BC_ROWS; r++) {
+        const int q = (blockIdx.y * BC_ROWS + r) * blockDim.y + threadIdx.y;
+        ok[r] = q < A.n[v];
+        val[r] = 0.0; vin[r] = 0.0; ic[r] = 0; dc[r] = 0;
+        if (!ok[r]) continue;
+        int c[3];
+        c[d] = hi ? A.n[d] - 1 : 0;
+        c[u] = p;
+        c[v] = q;
+        int s[3] = {c[0], c[1], c[2]};
+        double sign = 1.0;
+        bool zero = false;
+#pragma unroll
+        for (int e = 0; e < 3; e++) {
+            const bool lo_e = c[e] == 0, hi_e = c[e] == A.n[e] - 1;
+            if (!lo_e && !hi_e) continue;
+            // no_slip! runs before free_slip! (BoundaryConditions.jl:86-99): on a side that carries both
+            // (possible through quirk Q2) the free-slip copy wins for the tangential ghosts, the normal face stays 0
+            const bool fsl = lo_e ? b.lo_fs[e] : b.hi_fs[e], nsl = lo_e ? b.lo_ns[e] : b.hi_ns[e];
+            if (e == A.normal) {
+                if (nsl) zero = true;
+            } else if (fsl || nsl) {
+                s[e] = lo_e ? 1 : A.n[e] - 2;
+                if (!fsl) sign = -sign;
+            }
+        }
+        ic[r] = box_idx(A.out, c[0] + A.o[0], c[1] + A.o[1], c[2] + A.o[2]);
+        const size_t is = box_idx(A.out, s[0] + A.o[0], s[1] + A.o[1], s[2] + A.o[2]);
+        bool computed = true;
+#pragma unroll
+        for (int e = 0; e < 3; e++) computed = computed && s[e] >= 1 && s[e] <= A.n[e] - 2;
+        val[r] = zero ? 0.0 : sign * (computed ? A.out.p[is] : A.in.p[is]);
+        if (b.diag) {
+            dc[r] = ((size_t)c[2] * A.n[1] + c[1]) * A.n[0] + c[0];
+            vin[r] = A.in.p[ic[r]];
         }
     }
-    const size_t ic = box_idx(A.out, c[0] + A.o[0], c[1] + A.o[1], c[2] + A.o[2]);
-    const size_t is = box_idx(A.out, s[0] + A.o[0], s[1] + A.o[1], s[2] + A.o[2]);
-    bool computed = true;
 #pragma unroll
-    for (int e = 0; e < 3; e++) computed = computed && s[e] >= 1 && s[e] <= A.n[e] - 2;
-    double val;
-    if (zero) val = 0.0;
-    else val = sign * (computed ? A.out.p[is] : A.in.p[is]);
-    A.out.p[ic] = val;
-    if (b.diag) {
-        const size_t dc = ((size_t)c[2] * A.n[1] + c[1]) * A.n[0] + c[0];
-        A.U[dc] = A.in.p[ic] * b.dt;
-        A.Vd[dc] = val;
+    for (int r = 0; r < BC_ROWS; r++) {
+        if (!ok[r]) continue;
+        A.out.p[ic[r]] = val[r];
+        if (b.diag) {
+            A.U[dc[r]] = vin[r] * b.dt;
+            A.Vd[dc[r]] = val[r];
+        }
     }
 }
 
@@ -635,13 +670,26 @@ __global__ void k_minmax3(const double *a0, const double *a1, const double *a2, 
         part[blockIdx.x * 6 + threadIdx.x] = v;
     }
 }
+// one warp per quantity (6 warps): lane-strided scan of the block partials, then a shuffle reduction
 __global__ void k_minmax3_final(const double *part, int nparts, double *out)
 {
-    if (threadIdx.x < 6) {
-        double v = part[threadIdx.x];
-        for (int b = 1; b < nparts; b++) v = (threadIdx.x & 1) ? fmax(v, part[b * 6 + threadIdx.x]) : fmin(v, part[b * 6 + threadIdx.x]);
-        out[threadIdx.x] = v;
+    const int q = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (q >= 6) return;
+    const bool is_max = q & 1;
+    double v = is_max ? -INFINITY : INFINITY;
+    bool nan = false;
+    for (int b = lane; b < nparts; b += 32) {
+        const double x = part[b * 6 + q];
+        if (x != x) nan = true;
+        v = is_max ? fmax(v, x) : fmin(v, x);
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double w = __shfl_down_sync(0xffffffffu, v, o);
+        v = is_max ? fmax(v, w) : fmin(v, w);
+    }
+    nan = __any_sync(0xffffffffu, nan);
+    if (lane == 0) out[q] = nan ? NAN : v;
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -690,7 +738,7 @@ struct VaPlan {
     double *S[2] = {nullptr, nullptr}, *C = nullptr, *D = nullptr;
     CUtensorMap mS5[2], mC1, mC4, mD1, mD2, mD7;
     int BY = 0, nchunk = 1;
-    int pol_ld = 2, pol_st = 1, l2promo = 3, slack = 1;
+    int pol_ld = 2, pol_st = 1, l2promo = 3, slack = 1, stagger_ns = -1;
     unsigned long long *progress = nullptr, progress_base = 0, gbar_base = 0;
     bool rhog_const = false;  // ρg arrays are spatially constant: not streamed
     double fc[3] = {0, 0, 0};
@@ -808,7 +856,7 @@ int jr_stokes3d_VA_fused_begin(jr_context *ctx, const jr_fields *s, const jr_sto
         if ((st = jr_ctx_scratch(ctx, "minmax_part", (MINMAX_BLOCKS * 6 + 8) * sizeof(double), &part))) return st;
         mm = (double *)part + MINMAX_BLOCKS * 6;
         k_minmax3<<<MINMAX_BLOCKS, 256, 0, ctx->stream>>>(F(rhogx), F(rhogy), F(rhogz), (size_t)nx * ny * nz, (double *)part);
-        k_minmax3_final<<<1, 32, 0, ctx->stream>>>((const double *)part, MINMAX_BLOCKS, (double *)mm);
+        k_minmax3_final<<<1, 192, 0, ctx->stream>>>((const double *)part, MINMAX_BLOCKS, (double *)mm);
         ctx->launches += 2;
         JR_CUDA(cudaMemcpyAsync(ctx->h_pinned, mm, 6 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         JR_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -816,7 +864,10 @@ int jr_stokes3d_VA_fused_begin(jr_context *ctx, const jr_fields *s, const jr_sto
         P.rhog_const = h[0] == h[1] && h[2] == h[3] && h[4] == h[5] && !getenv("JRB200_VA_STREAM_RHOG");
         P.fc[0] = h[0]; P.fc[1] = h[2]; P.fc[2] = h[4];
     }
+    P.slack = 1; P.pol_ld = 2; P.pol_st = 1; P.l2promo = 3;   // defaults (the knobs below are read at every solve entry)
     if (const char *e = getenv("JRB200_VA_SLACK")) P.slack = atoi(e);
+    P.stagger_ns = -1;
+    if (const char *e = getenv("JRB200_VA_STAGGER_NS")) P.stagger_ns = atoi(e);
     if (const char *e = getenv("JRB200_VA_POL_LD")) P.pol_ld = atoi(e);
     if (const char *e = getenv("JRB200_VA_POL_ST")) P.pol_st = atoi(e);
     if (const char *e = getenv("JRB200_VA_L2PROMO")) P.l2promo = atoi(e);
@@ -896,6 +947,7 @@ static int launch_one(jr_context *ctx, VaPlan &P, VaArgs &a)
     a.progress = P.progress;
     a.progress_base = P.progress_base;
     a.slack = P.slack;
+    a.stagger_ns = P.stagger_ns;
     const int nit = MULTI ? a.niter : 1;
     P.progress_base += (unsigned long long)nit * items * (a.kchunk + 2);  // every item posts kchunk+2 steps per iteration
     a.gbar = P.progress + 16;  // its own 128-B line
@@ -1038,7 +1090,7 @@ int jr_stokes3d_VA_fused_iter(jr_context *ctx, const jr_fields *s, const jr_stok
     b.diag = diag; b.dt = o->dt;
     int m = nx > ny ? nx : ny;
     m = (m > nz ? m : nz) + 2;
-    dim3 bgrid((m + 31) / 32, (m + 7) / 8, 18), bblock(32, 8, 1);
+    dim3 bgrid((m + 31) / 32, (m + 8 * BC_ROWS - 1) / (8 * BC_ROWS), 18), bblock(32, 8, 1);
     k_bc_box3<<<bgrid, bblock, 0, ctx->stream>>>(b);
     ctx->launches += 2;
     JR_CHECK_LAUNCH();

@@ -59,6 +59,12 @@ class ConstantRadioactiveHeat:
 
 
 @dataclass
+class ConstantShearheating:
+    """GeoParams ConstantShearheating(Χ): H_s = Χ·τij(εij − εij_el)"""
+    Χ: float = 0.0
+
+
+@dataclass
 class ConstantGravity:
     g: float = 9.81
 
@@ -125,6 +131,7 @@ class MaterialParams:
     HeatCapacity: object = None
     Conductivity: object = None
     RadioactiveHeat: object = None
+    ShearHeat: object = None
     CompositeRheology: object = None
     Gravity: object = field(default_factory=ConstantGravity)
     Elasticity: object = None
@@ -225,3 +232,17 @@ def gravity_of(rheology):
     g = _as_tuple(rheology)[0].Gravity
     gv = g.g if g is not None else 0.0
     return (0.0, 0.0, float(gv))
+
+
+def shear_heating_coefficients(rheology):
+    """Χ per phase (ShearHeat = ConstantShearheating(Χ); absent → 0, like GeoParams' empty ShearHeat tuple)"""
+    out = []
+    for p in _as_tuple(rheology):
+        sh = p.ShearHeat
+        if sh is None:
+            out.append(0.0)
+        elif isinstance(sh, ConstantShearheating):
+            out.append(float(sh.Χ))
+        else:
+            raise UnsupportedRheology(f"shear-heating law {type(sh).__name__} is outside the supported subset")
+    return out

@@ -550,3 +550,69 @@ def compute_dt_(stokes, di, dt_diff=math.inf, igg: Optional[IGG] = None):
         x = float(d) * (math.inf if m == 0.0 else 1.0 / m)
         best = x if math.isnan(x) else min(best, x)   # mapreduce(min): NaN propagates
     return min(float(dt_diff), best * 0.9)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# per-time-step kernels between the Stokes and the thermal loops
+def _n3(ni):
+    return _abi.i32x(list(ni) + [1] * (3 - len(ni)))
+
+
+def velocity2vertex_(Vv, V, ni):
+    """velocity2vertex!(Vx_v, Vy_v[, Vz_v], Vx, Vy[, Vz]) — src/Interpolations.jl:212-248; Vv / V: sequences of B200 arrays"""
+    nd = len(ni)
+    z = lambda seq, q: data_ptr(seq[q]) if nd == 3 else None
+    _abi.check(_abi.lib().jr_velocity2vertex(context(), nd, _n3(ni), _n3(Vv[0].shape), data_ptr(Vv[0]), data_ptr(Vv[1]), z(Vv, 2),
+                                              data_ptr(V[0]), data_ptr(V[1]), z(V, 2)))
+
+
+def velocity2center_(Vc, V, ni):
+    """velocity2center!(Vx_c, Vy_c[, Vz_c], Vx, Vy[, Vz]) — src/Interpolations.jl:257-289"""
+    nd = len(ni)
+    z = lambda seq, q: data_ptr(seq[q]) if nd == 3 else None
+    _abi.check(_abi.lib().jr_velocity2center(context(), nd, _n3(ni), _n3(Vc[0].shape), data_ptr(Vc[0]), data_ptr(Vc[1]), z(Vc, 2),
+                                              data_ptr(V[0]), data_ptr(V[1]), z(V, 2)))
+
+
+def compute_lithostatic_pressure_(P, ρg, dz, igg: Optional[IGG] = None):
+    """compute_lithostatic_pressure!(P, ρg, dz[, igg]) — src/Utils.jl:541-617.  dz: a number or a B200 vector of cell heights."""
+    if tuple(P.shape) != tuple(ρg.shape):
+        raise ValueError(f"`P` and `ρg` must span the same cells, got axes {tuple(P.shape)} and {tuple(ρg.shape)}")   # DimensionMismatch
+    nd = P.dim()
+    dzv = None
+    if not isinstance(dz, (int, float)):
+        if int(np.prod(dz.shape)) != P.shape[-1]:
+            raise ValueError(f"`dz` must hold one height per cell, got {int(np.prod(dz.shape))} heights for {P.shape[-1]} cells")
+        dzv = data_ptr(dz)
+    across = igg is not None
+    nvert = int(igg.nxyz[nd - 1]) if (across and igg.nxyz is not None) else int(P.shape[-1])
+    st = _abi.lib().jr_lithostatic_pressure(context(), nd, _n3(P.shape), data_ptr(P), data_ptr(ρg), 0.0 if dzv else float(dz), dzv, int(across), nvert)
+    if st == _abi.JR_ERR_ARG:
+        raise ValueError(_abi.lib().jr_last_error().decode())   # ArgumentError("the vertical direction is split across MPI ranks; …")
+    _abi.check(st)
+    _abi.check(_abi.lib().jr_context_synchronize(context()))
+    return P
+
+
+def compute_shear_heating_(thermal, stokes, *rest):
+    """compute_shear_heating!(thermal, stokes, rheology, dt) / (thermal, stokes, phase_ratios, rheology, dt)
+    — src/thermal_diffusion/ShearHeating.jl:14-72"""
+    if len(rest) == 3:
+        phase_ratios, rheology, dt = rest
+    else:
+        (rheology, dt), phase_ratios = rest, None
+    rh = tuple(rheology) if isinstance(rheology, (tuple, list)) else (rheology,)
+    if phase_ratios is None and len(rh) != 1:
+        raise ValueError("a multi-phase rheology needs the phase ratios")
+    rows = _rheology.lower_stokes(rh)
+    arr = (_abi.StokesPhase * len(rows))()
+    for i, r in enumerate(rows):
+        for k, v in r.items():
+            setattr(arr[i], k, v)
+    vc = _abi.VcInputs()
+    vc.nphase, vc.g_scalar, vc.phases = len(rows), 1, arr
+    if phase_ratios is not None:
+        vc.ph_center = data_ptr(phase_ratios.center)
+    chi = (C.c_double * len(rows))(*_rheology.shear_heating_coefficients(rh))
+    fs = build_fields(stokes.slots(), stokes.ni)
+    _abi.check(_abi.lib().jr_compute_shear_heating(context(), C.byref(fs), C.byref(vc), chi, float(dt), data_ptr(thermal.shear_heating)))

@@ -163,6 +163,12 @@ void orc_vc3_end(const orc_fields *s, const orc_stokes_opts *o, void *h, int fin
 void orc_phase_ratios_from_arrays(int nd, const int32_t n[3], int N, const double *const *ph, const double *const *xc, const double *const *xv,
                                   double *center, double *vertex, double *Vx, double *Vy, double *Vz, double *xy, double *yz, double *xz);
 
+/* ---- per-time-step kernels around the loops (oracle/aux.c) ---- */
+void orc_velocity2vertex(int nd, const int32_t n[3], const int32_t e[3], double *Xv, double *Yv, double *Zv, const double *Vx, const double *Vy, const double *Vz);
+void orc_velocity2center(int nd, const int32_t n[3], const int32_t e[3], double *Xc, double *Yc, double *Zc, const double *Vx, const double *Vy, const double *Vz);
+void orc_lithostatic_pressure(int nd, const int32_t n[3], double *P, const double *rhog, double dz, const double *dzv, const double *above);
+void orc_shear_heating(const orc_fields *s, const orc_vc_inputs *vc, const double *chi, double dt, double *out);
+
 /* norms (src/Utils.jl:698-701), interior slice 2:end-1 in every dim when interior!=0 */
 double orc_sumsq_interior(const double *A, int n1, int n2, int n3, int interior);
 

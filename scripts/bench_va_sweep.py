@@ -25,7 +25,16 @@ def main():
         st.slots()[k].copy_(dev[k])
     jst.flow_bcs_(st, s.flow_bcs)
     ρg = (dev["rhogx"], dev["rhogy"], dev["rhogz"])
-    run = lambda k: jst.iterate_(st, s.pt_stokes, s.grid, s.flow_bcs, ρg, dev["K"], dev["G"], s.dt, k)
+    class _R:
+        pass
+
+    def run(k):
+        # steady state: k iterations inside a running loop (after 5 warm-up iterations of the same session)
+        with jst.IterationSession(st, s.pt_stokes, s.grid, s.flow_bcs, ρg, dev["K"], dev["G"], s.dt) as it:
+            it.step(5)
+            return it.step(k)
+
+    sleep_s = float(os.environ.get("SWEEP_SLEEP", "0"))
     settings = [dict(kv.split("=") for kv in item.split(",") if kv) for item in sys.argv[1:]] or [{}]
     # SWEEP_REPEAT > 1 cycles through the settings several times (A/B/A/B …): sustained load moves the SM clock under the
     # power cap, so only interleaved repeats compare fairly
@@ -52,6 +61,8 @@ def main():
         th = threading.Thread(target=sample, daemon=True)
         th.start()
         for _ in range(3):
+            if sleep_s:
+                time.sleep(sleep_s)   # let the board's power average (and the SM clock) recover: the short-run regime of the driver's bench
             r = run(steps)
             best = r.time if best is None else min(best, r.time)
         torch.cuda.synchronize()

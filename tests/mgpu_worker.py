@@ -158,6 +158,29 @@ def main():
                          kwargs=dict(verbose=False, phase=pht, igg=iggv))
     tg.compare(tht, tblocks[rank], ["T", "qTx", "qTy", "qTz", "qTx2", "qTy2", "qTz2", "ResT"], f"thermal 3D multi-rank rank {rank}")
 
+    # ---- 7. compute_lithostatic_pressure!(P, ρg, dz, igg) with the vertical direction split across ALL ranks ---------------------------
+    comm.finalize_global_grid()
+    nl = (9, 8, 12)
+    iggz = comm.init_global_grid(*nl, dims=(1, 1, world))
+    nzg = world * (nl[2] - 2) + 2
+    rg_glob = np.asfortranarray(np.random.default_rng(77).uniform(1.0, 3.0, size=(nl[0], nl[1], nzg)))
+    dzl = 0.37
+    import ctypes as C2
+    P_glob = np.zeros_like(rg_glob, order="F")
+    dp = lambda a: a.ctypes.data_as(C2.POINTER(C2.c_double))
+    po.lib().orc_lithostatic_pressure(3, (C2.c_int32 * 3)(nl[0], nl[1], nzg), dp(P_glob), dp(rg_glob), C2.c_double(dzl), None, None)
+    k0 = iggz.coords[2] * (nl[2] - 2)
+    rg_loc = np.asfortranarray(rg_glob[:, :, k0:k0 + nl[2]])
+    from justrelax_jl_b200 import zeros
+    P_loc = zeros(B200Backend, *nl)
+    jst.compute_lithostatic_pressure_(P_loc, PTArray(B200Backend)(rg_loc), dzl, iggz)
+    assert np.allclose(to_host(P_loc), P_glob[:, :, k0:k0 + nl[2]], rtol=1e-13, atol=0), ("lithostatic pressure across ranks", rank)
+    try:   # the three-argument method must refuse a split vertical direction (test/test_lithostatic_pressure3D_MPI.jl:95)
+        jst.compute_lithostatic_pressure_(P_loc, PTArray(B200Backend)(rg_loc), dzl)
+        raise AssertionError("expected the split-column error")
+    except ValueError as e:
+        assert "split across MPI ranks" in str(e)
+
     dist.barrier()
     print(f"MGPU_OK rank {rank}/{world} dims {dims}: halo, all-reduce, 3D-VA iterate (fused+unfused), solve iter={out.iter} worst={worst:.2e}, 3D-VC worst={worst_vc:.2e}, thermal OK", flush=True)
     comm.finalize_global_grid()
