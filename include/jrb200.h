@@ -98,6 +98,10 @@ typedef struct {
     double viscosity_relaxation, lambda_relaxation, visc_cutoff_lo, visc_cutoff_hi;
     int64_t iterMin;
     int32_t strain_rate_ni_only;
+    int32_t strain_increment;       /* 2D-VC kwarg strain_increment = true: Δε form (Stokes2D.jl:659-730, StressKernels.jl:1147-1302) */
+    int32_t displacement_bcs;       /* flow_bcs isa DisplacementBoundaryConditions (src/types/displacement.jl:62-70): V = U/dt before the
+                                     * loop, flow_bcs! applied to U instead of V (2D-VC) */
+    int32_t _pad;
 } jr_stokes_opts;
 
 typedef struct {

@@ -72,6 +72,9 @@ struct StokesOpts
     visc_cutoff_hi::Cdouble
     iterMin::Int64
     strain_rate_ni_only::Int32
+    strain_increment::Int32          # 2D-VC kwarg strain_increment (Δε form)
+    displacement_bcs::Int32          # flow_bcs isa DisplacementBoundaryConditions
+    _pad::Int32
 end
 
 # ---- jr_stokes_result (history arrays are HOST pointers) --------------------------------------------------------------
@@ -215,7 +218,7 @@ end
 
 "layout check against the sizes the C compiler produces for include/jrb200.h (same numbers as tests/test_abi.py)"
 function selfcheck()
-    @assert sizeof(StokesOpts) == 5 * 8 + 3 * 8 + 8 + 16 + 12 + 3 * 24 + 4 + 4 * 8 + 8 + 8
+    @assert sizeof(StokesOpts) == 5 * 8 + 3 * 8 + 8 + 16 + 12 + 3 * 24 + 4 + 4 * 8 + 8 + 16
     @assert sizeof(StokesResult) == 11 * 8
     @assert sizeof(StokesPhase) == 14 * 8                  # 13 doubles + two int32 sharing one 8-byte slot
     @assert sizeof(VcInputs) == 8 + 8 + 24 + 5 * 8 + 8

@@ -145,19 +145,20 @@ function global_size(ni::NTuple{N}) where {N}
 end
 
 function stokes_opts(pt::JustRelax.PTStokesCoeffs, grid, dt, bcs, ni; iterMax = 10.0e3, nout = 500, viscosity_relaxation = 1.0e-2,
-                     λ_relaxation = 0.2, viscosity_cutoff = (-Inf, Inf), iterMin = 0, kw...)
+                     λ_relaxation = 0.2, viscosity_cutoff = (-Inf, Inf), iterMin = 0, strain_increment = false, kw...)
     _require_uniform(grid)
     return API.StokesOpts(
         pt.r, pt.θ_dτ, pt.ηdτ, pt.ϵ_rel, pt.ϵ_abs, API.tuple3(_inv_spacing(grid), 0.0), Float64(dt), Int64(floor(iterMax)), Int64(floor(nout)),
         global_size(ni), API.flags6(bcs.free_slip), API.flags6(bcs.no_slip), API.flags6(bcs.periodic),
         Float64(viscosity_relaxation), Float64(λ_relaxation), Float64(viscosity_cutoff[1]), Float64(viscosity_cutoff[2]), Int64(floor(iterMin)), Int32(0),
+        Int32(strain_increment === true), Int32(bcs isa JustRelax.DisplacementBoundaryConditions), Int32(0),
     )
 end
 
-function check_flow_bcs_type(bcs)
+function check_flow_bcs_type(bcs; allow_displacement = false)
     bcs isa JustRelax.AbstractFlowBoundaryConditions || throw(ArgumentError("Unknown boundary conditions type: $(typeof(bcs))"))   # types/displacement.jl:68-70
-    bcs isa JustRelax.DisplacementBoundaryConditions &&
-        throw(ArgumentError("DisplacementBoundaryConditions are outside the B200 backend's supported subset"))
+    (bcs isa JustRelax.DisplacementBoundaryConditions && !allow_displacement) &&
+        throw(ArgumentError("DisplacementBoundaryConditions are supported by the multiphase 2D solve (2D-VC) only"))
     return bcs
 end
 
@@ -312,9 +313,8 @@ function solve_phases!(stokes, pt_stokes, grid, flow_bcs, ρg, phase_ratios, rhe
         (; iterMax = 50.0e3, iterMin = 1.0e2, viscosity_relaxation = 1.0e-2, λ_relaxation = 0.2, free_surface = false, nout = 500,
          b_width = (4, 4, 0), verbose = true, viscosity_cutoff = (-Inf, Inf), strain_increment = false)
     kw = merge(defaults, values(kwargs))
-    check_flow_bcs_type(flow_bcs)
+    check_flow_bcs_type(flow_bcs; allow_displacement = ND == 2)
     ensure_comm!(igg)
-    (ND == 2 && kw.strain_increment) && throw(ArgumentError("strain_increment = true is outside the B200 backend's supported subset"))
     ni = size(stokes.P)
     d = add_args!(add_ρg!(stokes_slots(stokes), ρg), args)
     f = API.Fields(ni, d)
@@ -379,7 +379,7 @@ function compute_viscosity_b200!(stokes, ν, phase_ratios, args, rheology::NTupl
     dummy = ND == 3 ? (stokes.P, stokes.P, stokes.P) : (stokes.P, stokes.P)
     f = API.Fields(ni, add_args!(add_ρg!(stokes_slots(stokes), dummy), args))
     opt = Ref(API.StokesOpts(0, 0, 0, 0, 0, (0.0, 0.0, 0.0), Inf, 0, 1, global_size(ni), ntuple(_ -> Int32(0), 6), ntuple(_ -> Int32(0), 6),
-                             ntuple(_ -> Int32(0), 6), 0.0, 0.0, Float64(cutoff[1]), Float64(cutoff[2]), 0, Int32(0)))
+                             ntuple(_ -> Int32(0), 6), 0.0, 0.0, Float64(cutoff[1]), Float64(cutoff[2]), 0, Int32(0), Int32(0), Int32(0), Int32(0)))
     vc, keep = vc_inputs(rheology, phase_ratios)
     fn = ND == 3 ? :jr_compute_viscosity3d : :jr_compute_viscosity2d
     GC.@preserve f keep LIB.check(ccall(jrsym(fn), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ref{API.StokesOpts}, Ref{API.VcInputs}, Cdouble), ctx(), pointer(f), opt, vc, Float64(ν)))

@@ -99,6 +99,11 @@ __device__ __forceinline__ double jr_stress_increment(double t, double t_o, doub
 {
     return dtr * fma(2.0 * eta, e, fma(-(t - t_o) * eta, _Gdt, -t));
 }
+// compute_stress_increment, strain-increment form  src/stokes/StressKernels.jl:19-22
+__device__ __forceinline__ double jr_stress_increment_d(double t, double t_o, double eta, double de, double _G, double dtr, double dt)
+{
+    return dtr * fma(2.0 * eta, de, fma(-(t - t_o) * eta, _G, -t * dt));
+}
 // _compute_P!  src/stokes/PressureKernels.jl:186-195
 __device__ __forceinline__ void jr_compute_P_point(double &RP, double &P, double P0, double divV, double Q, double eta,
                                                    double K, double G, double dt, double r, double theta_dtau)

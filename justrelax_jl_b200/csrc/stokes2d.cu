@@ -25,6 +25,10 @@ struct K2 {
     int nx, ny;
     double _dx, _dy, dt, r, th, edt, rel, nu, cut_lo, cut_hi;
     int fs_l, fs_r, fs_t, fs_b, ns_l, ns_r, ns_t, ns_b;
+    int dbc;   // flow_bcs isa DisplacementBoundaryConditions: flow_bcs! acts on U = V·dt, V keeps its ghosts / boundary faces
+    // strain-increment form (INC): the displacement is part of the ping-pong state (Δε of the next iteration reads it at neighbours)
+    const double *Ux_i, *Uy_i;
+    double *Ux_o, *Uy_o, *dxx, *dyy, *dxy, *divU;
     // ping-pong state
     const double *Vx_i, *Vy_i, *P_i, *txx_i, *tyy_i, *txy_i, *th_i, *txyc_i, *lam_i, *lamv_i, *eta_i, *etav_i;
     double *Vx_o, *Vy_o, *P_o, *txx_o, *tyy_o, *txy_o, *th_o, *txyc_o, *lam_o, *lamv_o, *eta_o, *etav_o;
@@ -38,7 +42,9 @@ __device__ __forceinline__ double inv2(double xx, double yy, double xy) { return
 __device__ __forceinline__ void jr_prefetch_l1(const double *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // TYT = threads in y (tile height incl. the one-node rim): chosen per grid so that the CTA count fills whole waves (plan2_tile)
-template <bool VC, bool DIAG, int TYT>
+// INC (VC only): strain-increment form (kwarg strain_increment = true, Stokes2D.jl:659-730; StressKernels.jl:1147-1302): Δε from the
+// displacement U, ε = Δε/dt, stress increments from Δε; the planes s_exx / s_eyy / s_exy then hold Δε and readers scale by 1/dt.
+template <bool VC, bool DIAG, int TYT, bool INC = false>
 __global__ void __launch_bounds__(TX * TYT) k_stokes2d(const __grid_constant__ K2 a, const __grid_constant__ jr_phase_tab pt)
 {
     constexpr int NTT = TX * TYT;
@@ -69,7 +75,8 @@ __global__ void __launch_bounds__(TX * TYT) k_stokes2d(const __grid_constant__ K
         if (cell) { jr_prefetch_l1(a.txyc_i + c); jr_prefetch_l1(a.txyco + c); jr_prefetch_l1(a.lam_i + c); }
     }
     double divV = 0.0, RP = 0.0, thn = 0.0, exx = 0.0, eyy = 0.0, exy = 0.0, ett = 0.0, eta = 0.0, rgx = 0.0, rgy = 0.0;
-    double txx = 0.0, tyy = 0.0, txxo = 0.0, tyyo = 0.0, Kc = 0.0, Gc = 0.0;
+    double txx = 0.0, tyy = 0.0, txxo = 0.0, tyyo = 0.0, Kc = 0.0, Gc = 0.0, divU = 0.0;
+    const double _dt = jr_inv(a.dt);
     if (cell) {
         eta = a.eta_i[c];
         if (VC) {  // compute_maxloc!(ητ, η; window = (1,1))  Stokes2D.jl:654, Utils.jl:409-461
@@ -99,9 +106,18 @@ __global__ void __launch_bounds__(TX * TYT) k_stokes2d(const __grid_constant__ K
             jr_compute_P_point_dT(RP, thn, a.P0[c], divV, a.Q[c], a.dTargs[c], jr_ratio_alpha(pt, a.ph_c, nc, c), ett, Kc, Gc, a.dt, a.r, a.th);
         else
             jr_compute_P_point(RP, thn, a.P0[c], divV, a.Q[c], ett, Kc, Gc, a.dt, a.r, a.th);
-        const double dV = divV * jr_inv(3.0);
-        exx = dVx - dV;  // compute_strain_rate!  VelocityKernels.jl:10-44
-        eyy = dVy - dV;
+        if (INC) {  // compute_∇V!(∇U, U) + compute_strain_rate!(Δε, ∇U, U)  Stokes2D.jl:660-662, 681-689
+            const double dUx = (-a.Ux_i[IX2(nx + 1, i, j + 1)] + a.Ux_i[IX2(nx + 1, i + 1, j + 1)]) * a._dx;
+            const double dUy = (-a.Uy_i[IX2(nx + 2, i + 1, j)] + a.Uy_i[IX2(nx + 2, i + 1, j + 1)]) * a._dy;
+            divU = dUx + dUy;
+            const double dU = divU * jr_inv(3.0);
+            exx = dUx - dU;
+            eyy = dUy - dU;
+        } else {
+            const double dV = divV * jr_inv(3.0);
+            exx = dVx - dV;  // compute_strain_rate!  VelocityKernels.jl:10-44
+            eyy = dVy - dV;
+        }
         txx = a.txx_i[c];
         tyy = a.tyy_i[c];
         txxo = a.txxo[c];
@@ -116,8 +132,10 @@ __global__ void __launch_bounds__(TX * TYT) k_stokes2d(const __grid_constant__ K
             rgy = a.rhogy[c];
         }
     }
-    if (vert)
-        exy = 0.5 * (a._dy * (a.Vx_i[IX2(nx + 1, i, j + 1)] - a.Vx_i[IX2(nx + 1, i, j)]) + a._dx * (a.Vy_i[IX2(nx + 2, i + 1, j)] - a.Vy_i[IX2(nx + 2, i, j)]));
+    if (vert) {
+        const double *Ax = INC ? a.Ux_i : a.Vx_i, *Ay = INC ? a.Uy_i : a.Vy_i;
+        exy = 0.5 * (a._dy * (Ax[IX2(nx + 1, i, j + 1)] - Ax[IX2(nx + 1, i, j)]) + a._dx * (Ay[IX2(nx + 2, i + 1, j)] - Ay[IX2(nx + 2, i, j)]));
+    }
     s_th[t] = thn; s_exx[t] = exx; s_eyy[t] = eyy; s_exy[t] = exy; s_ett[t] = ett; s_rgx[t] = rgx; s_rgy[t] = rgy;
     if (VC) { s_txx[t] = txx; s_tyy[t] = tyy; s_txxo[t] = txxo; s_tyyo[t] = tyyo; s_eta[t] = eta; }
     __syncthreads();
@@ -150,13 +168,22 @@ __global__ void __launch_bounds__(TX * TYT) k_stokes2d(const __grid_constant__ K
             bool is_pl;
             double eta_reg;
             jr_plastic_params(pt, a.ph_v, nv, v, is_pl, eta_reg);
-            const double _Gdt = jr_inv(jr_ratio_G(pt, a.ph_v, nv, v) * a.dt), Kv = jr_ratio_Kb(pt, a.ph_v, nv, v);
+            const double Gv = jr_ratio_G(pt, a.ph_v, nv, v);
+            const double _Gdt = jr_inv(Gv * a.dt), _G = jr_inv(Gv), Kv = jr_ratio_Kb(pt, a.ph_v, nv, v);
             // harmonic mean of η (> 0, normal range) and 1/(θ_dτ + η/(G dt) + 1) (operand ≥ 1): branch-free IEEE-exact sequences
             const double etav = jr_div_nr(4.0, jr_inv_nr(s_eta[q00]) + jr_inv_nr(s_eta[qcc]) + jr_inv_nr(s_eta[q0c]) + jr_inv_nr(s_eta[qc0]));
-            const double dtr = jr_inv_nr(a.th + etav * _Gdt + 1.0);
+            const double dtr = INC ? jr_inv(a.th * a.dt + etav * _G + a.dt) : jr_inv_nr(a.th + etav * _Gdt + 1.0);
             const double txyv = a.txy_i[v];
-            const double dxx = jr_stress_increment(txxv, txxov, etav, exxv, _Gdt, dtr), dyy = jr_stress_increment(tyyv, tyyov, etav, eyyv, _Gdt, dtr);
-            const double dxy = jr_stress_increment(txyv, a.txyo[v], etav, exy, _Gdt, dtr);
+            double dxx, dyy, dxy;
+            if (INC) {  // compute_stress_increment(τ, τ_o, η, Δε, 1/G, dτ_r, dt)  StressKernels.jl:19-22
+                dxx = jr_stress_increment_d(txxv, txxov, etav, exxv, _G, dtr, a.dt);
+                dyy = jr_stress_increment_d(tyyv, tyyov, etav, eyyv, _G, dtr, a.dt);
+                dxy = jr_stress_increment_d(txyv, a.txyo[v], etav, exy, _G, dtr, a.dt);
+            } else {
+                dxx = jr_stress_increment(txxv, txxov, etav, exxv, _Gdt, dtr);
+                dyy = jr_stress_increment(tyyv, tyyov, etav, eyyv, _Gdt, dtr);
+                dxy = jr_stress_increment(txyv, a.txyo[v], etav, exy, _Gdt, dtr);
+            }
             const double trial[3] = {txxv + dxx, tyyv + dyy, txyv + dxy};
             const double tIIv = inv2(dxx + txxv, dyy + tyyv, dxy + txyv);
             double dQ[3], dQdP, dFdP;
@@ -165,9 +192,9 @@ __global__ void __launch_bounds__(TX * TYT) k_stokes2d(const __grid_constant__ K
             const double Fv = jr_yield_F(pt, a.ph_v, nv, v, Pv, tIIv);
             lamv = a.lamv_i[v];
             if (is_pl && tIIv != 0.0 && Fv > 0) {
-                lamv = fma(a.rel, fmax(Fv, 0.0) / (etav * dtr + eta_reg + volume), (1.0 - a.rel) * lamv);
+                lamv = fma(a.rel, fmax(Fv, 0.0) / ((INC ? etav * dtr * a.dt : etav * dtr) + eta_reg + volume), (1.0 - a.rel) * lamv);
                 pxy = lamv * dQ[2];
-                txyn = txyv + fma(-2.0, etav * pxy * dtr, dxy);
+                txyn = txyv + (INC ? fma(-2.0, etav * a.dt * pxy * dtr, dxy) : fma(-2.0, etav * pxy * dtr, dxy));
             } else {
                 txyn = txyv + dxy;
                 pxy = 0.0;
@@ -179,13 +206,23 @@ __global__ void __launch_bounds__(TX * TYT) k_stokes2d(const __grid_constant__ K
             bool is_pl;
             double eta_reg;
             jr_plastic_params(pt, a.ph_c, nc, c, is_pl, eta_reg);
-            const double dtr = 1.0 / (a.th + eta * _Gdt + 1.0);
-            const double eij[3] = {exx, eyy, (((s_exy[t] + s_exy[t + 1]) + s_exy[t + TX]) + s_exy[t + TX + 1]) / 4};
+            const double _G = jr_inv(Gc);
+            const double dtr = INC ? 1.0 / (a.th * a.dt + eta * _G + a.dt) : 1.0 / (a.th + eta * _Gdt + 1.0);
+            // strain rate at the centre (INC: ε = Δε·(1/dt) element by element, then the same four-vertex average)
+            const double eij[3] = {INC ? exx * _dt : exx, INC ? eyy * _dt : eyy,
+                                   INC ? (((s_exy[t] * _dt + s_exy[t + 1] * _dt) + s_exy[t + TX] * _dt) + s_exy[t + TX + 1] * _dt) / 4
+                                       : (((s_exy[t] + s_exy[t + 1]) + s_exy[t + TX]) + s_exy[t + TX + 1]) / 4};
             double tij[3] = {txx, tyy, a.txyc_i[c]};
             const double tijo[3] = {txxo, tyyo, a.txyco[c]};
             double dt_[3];
+            if (INC) {
+                const double dij[3] = {exx, eyy, (((s_exy[t] + s_exy[t + 1]) + s_exy[t + TX]) + s_exy[t + TX + 1]) / 4};
 #pragma unroll
-            for (int q = 0; q < 3; q++) dt_[q] = jr_stress_increment(tij[q], tijo[q], eta, eij[q], _Gdt, dtr);
+                for (int q = 0; q < 3; q++) dt_[q] = jr_stress_increment_d(tij[q], tijo[q], eta, dij[q], _G, dtr, a.dt);
+            } else {
+#pragma unroll
+                for (int q = 0; q < 3; q++) dt_[q] = jr_stress_increment(tij[q], tijo[q], eta, eij[q], _Gdt, dtr);
+            }
             tII = inv2(dt_[0] + tij[0], dt_[1] + tij[1], dt_[2] + tij[2]);
             const double trial[3] = {tij[0] + dt_[0], tij[1] + dt_[1], tij[2] + dt_[2]};
             double dQ[3], dQdP, dFdP;
@@ -194,12 +231,12 @@ __global__ void __launch_bounds__(TX * TYT) k_stokes2d(const __grid_constant__ K
             const double Fc = jr_yield_F(pt, a.ph_c, nc, c, thn, tII);
             lam = a.lam_i[c];
             if (is_pl && tII != 0.0 && Fc > 0) {
-                lam = fma(a.rel, fmax(Fc, 0.0) / (eta * dtr + eta_reg + volume), (1.0 - a.rel) * lam);
+                lam = fma(a.rel, fmax(Fc, 0.0) / ((INC ? eta * dtr * a.dt : eta * dtr) + eta_reg + volume), (1.0 - a.rel) * lam);
                 double epl[3];
 #pragma unroll
                 for (int q = 0; q < 3; q++) {
                     epl[q] = lam * dQ[q];
-                    dt_[q] = fma(-2.0, eta * epl[q] * dtr, dt_[q]);
+                    dt_[q] = INC ? fma(-2.0, eta * a.dt * epl[q] * dtr, dt_[q]) : fma(-2.0, eta * epl[q] * dtr, dt_[q]);
                     tij[q] = dt_[q] + tij[q];
                 }
                 evol = -lam * dQdP;
@@ -232,7 +269,8 @@ __global__ void __launch_bounds__(TX * TYT) k_stokes2d(const __grid_constant__ K
             a.eta_o[c] = jr_clampd((1 - a.nu) * eta + a.nu * jr_phase_viscosity(pt, a.ph_c, nc, c), a.cut_lo, a.cut_hi);
         }
         if (DIAG) {
-            a.divV[c] = divV; a.RP[c] = RP; a.exx[c] = exx; a.eyy[c] = eyy;
+            a.divV[c] = divV; a.RP[c] = RP; a.exx[c] = INC ? exx * _dt : exx; a.eyy[c] = INC ? eyy * _dt : eyy;
+            if (INC) { a.dxx[c] = exx; a.dyy[c] = eyy; a.divU[c] = divU; }
             if (VC) {
                 a.pxx[c] = pxx; a.pyy[c] = pyy; a.tII[c] = tII; a.eta_vep[c] = etavep; a.e_vol_pl[c] = evol; a.etatau_w[c] = ett;
                 if (!pt.rho_const) { if (!pt.g_scalar) a.rhogx_w[c] = rgx; a.rhogy_w[c] = rgy; }
@@ -245,7 +283,7 @@ __global__ void __launch_bounds__(TX * TYT) k_stokes2d(const __grid_constant__ K
             a.lamv_o[v] = lamv;
             if (a.etav_o) a.etav_o[v] = jr_clampd((1 - a.nu) * a.etav_i[v] + a.nu * jr_phase_viscosity(pt, a.ph_v, nv, v), a.cut_lo, a.cut_hi);
         }
-        if (DIAG) { a.exy[v] = exy; if (VC) a.pxy[v] = pxy; }
+        if (DIAG) { a.exy[v] = INC ? exy * _dt : exy; if (INC) a.dxy[v] = exy; if (VC) a.pxy[v] = pxy; }
     }
     // compute_V! VelocityKernels.jl:108-131 (V2) / :134-180 (VC, free-surface form) + flow_bcs! (no_slip! → free_slip!) as a gather
     if (vert && j <= ny) {  // Vx[i, j+1]
@@ -256,20 +294,32 @@ __global__ void __launch_bounds__(TX * TYT) k_stokes2d(const __grid_constant__ K
             const double dt_xy = (-s_txyn[t] + s_txyn[t + TX]) * a._dy, avf = (s_rgx[t - 1] + s_rgx[t]) * 0.5, ave = (s_ett[t - 1] + s_ett[t]) * 0.5;
             vx = a.Vx_i[e] + (-dP + dt_xx + dt_xy - avf) * a.edt / ave;
         } else
-            vx = ((i == 1) ? a.ns_l : a.ns_r) ? 0.0 : a.Vx_i[e];
+            vx = (!a.dbc && ((i == 1) ? a.ns_l : a.ns_r)) ? 0.0 : a.Vx_i[e];
         a.Vx_o[e] = vx;
-        if (DIAG && a.Ux) a.Ux[e] = ((i >= 2 && i <= nx) ? vx : a.Vx_i[e]) * a.dt;  // velocity2displacement! runs BEFORE flow_bcs!
+        // velocity2displacement! runs BEFORE flow_bcs!; with DisplacementBoundaryConditions flow_bcs! then acts on U (V untouched)
+        double *const Uxw = INC ? a.Ux_o : ((DIAG && a.Ux) ? a.Ux : nullptr);
+        const bool nzero = (i == 1 && a.ns_l) || (i == nx + 1 && a.ns_r);   // no_slip! zeroes the boundary-normal face (all rows)
+        const double ux = (a.dbc && nzero) ? 0.0 : ((i >= 2 && i <= nx) ? vx : a.Vx_i[e]) * a.dt;
+        if (Uxw) Uxw[e] = ux;
         if (j == 1) {
             const size_t g = IX2(nx + 1, i, 1);
-            const double gv = a.fs_b ? vx : (a.ns_b ? -vx : (((i == 1 && a.ns_l) || (i == nx + 1 && a.ns_r)) ? 0.0 : a.Vx_i[g]));
-            a.Vx_o[g] = gv;
-            if (DIAG && a.Ux) a.Ux[g] = a.Vx_i[g] * a.dt;
+            if (!a.dbc) {
+                a.Vx_o[g] = a.fs_b ? vx : (a.ns_b ? -vx : (nzero ? 0.0 : a.Vx_i[g]));
+                if (Uxw) Uxw[g] = a.Vx_i[g] * a.dt;
+            } else {
+                a.Vx_o[g] = a.Vx_i[g];
+                if (Uxw) Uxw[g] = a.fs_b ? ux : (a.ns_b ? -ux : (nzero ? 0.0 : a.Vx_i[g] * a.dt));
+            }
         }
         if (j == ny) {
             const size_t g = IX2(nx + 1, i, ny + 2);
-            const double gv = a.fs_t ? vx : (a.ns_t ? -vx : (((i == 1 && a.ns_l) || (i == nx + 1 && a.ns_r)) ? 0.0 : a.Vx_i[g]));
-            a.Vx_o[g] = gv;
-            if (DIAG && a.Ux) a.Ux[g] = a.Vx_i[g] * a.dt;
+            if (!a.dbc) {
+                a.Vx_o[g] = a.fs_t ? vx : (a.ns_t ? -vx : (nzero ? 0.0 : a.Vx_i[g]));
+                if (Uxw) Uxw[g] = a.Vx_i[g] * a.dt;
+            } else {
+                a.Vx_o[g] = a.Vx_i[g];
+                if (Uxw) Uxw[g] = a.fs_t ? ux : (a.ns_t ? -ux : (nzero ? 0.0 : a.Vx_i[g] * a.dt));
+            }
         }
     }
     if (vert && i <= nx) {  // Vy[i+1, j]
@@ -286,20 +336,31 @@ __global__ void __launch_bounds__(TX * TYT) k_stokes2d(const __grid_constant__ K
             } else
                 vy = Vy0 + (-dP + dt_yy + dt_xy - avf) * a.edt / ave;
         } else
-            vy = ((j == 1) ? a.ns_b : a.ns_t) ? 0.0 : a.Vy_i[e];
+            vy = (!a.dbc && ((j == 1) ? a.ns_b : a.ns_t)) ? 0.0 : a.Vy_i[e];
         a.Vy_o[e] = vy;
-        if (DIAG && a.Uy) a.Uy[e] = ((j >= 2 && j <= ny) ? vy : a.Vy_i[e]) * a.dt;
+        double *const Uyw = INC ? a.Uy_o : ((DIAG && a.Uy) ? a.Uy : nullptr);
+        const bool nzero = (j == 1 && a.ns_b) || (j == ny + 1 && a.ns_t);
+        const double uy = (a.dbc && nzero) ? 0.0 : ((j >= 2 && j <= ny) ? vy : a.Vy_i[e]) * a.dt;
+        if (Uyw) Uyw[e] = uy;
         if (i == 1) {
             const size_t g = IX2(nx + 2, 1, j);
-            const double gv = a.fs_l ? vy : (a.ns_l ? -vy : (((j == 1 && a.ns_b) || (j == ny + 1 && a.ns_t)) ? 0.0 : a.Vy_i[g]));
-            a.Vy_o[g] = gv;
-            if (DIAG && a.Uy) a.Uy[g] = a.Vy_i[g] * a.dt;
+            if (!a.dbc) {
+                a.Vy_o[g] = a.fs_l ? vy : (a.ns_l ? -vy : (nzero ? 0.0 : a.Vy_i[g]));
+                if (Uyw) Uyw[g] = a.Vy_i[g] * a.dt;
+            } else {
+                a.Vy_o[g] = a.Vy_i[g];
+                if (Uyw) Uyw[g] = a.fs_l ? uy : (a.ns_l ? -uy : (nzero ? 0.0 : a.Vy_i[g] * a.dt));
+            }
         }
         if (i == nx) {
             const size_t g = IX2(nx + 2, nx + 2, j);
-            const double gv = a.fs_r ? vy : (a.ns_r ? -vy : (((j == 1 && a.ns_b) || (j == ny + 1 && a.ns_t)) ? 0.0 : a.Vy_i[g]));
-            a.Vy_o[g] = gv;
-            if (DIAG && a.Uy) a.Uy[g] = a.Vy_i[g] * a.dt;
+            if (!a.dbc) {
+                a.Vy_o[g] = a.fs_r ? vy : (a.ns_r ? -vy : (nzero ? 0.0 : a.Vy_i[g]));
+                if (Uyw) Uyw[g] = a.Vy_i[g] * a.dt;
+            } else {
+                a.Vy_o[g] = a.Vy_i[g];
+                if (Uyw) Uyw[g] = a.fs_r ? uy : (a.ns_r ? -uy : (nzero ? 0.0 : a.Vy_i[g] * a.dt));
+            }
         }
     }
 }
@@ -464,9 +525,9 @@ int jr_make_phase_tab(const jr_vc_inputs *vc, jr_phase_tab *out)
 
 // ------------------------------------------------------------------------------------------------------------------------------
 // host drivers
-enum { S_Vx, S_Vy, S_P, S_txx, S_tyy, S_txy, S_th, S_txyc, S_lam, S_lamv, S_eta, S_etav, S_COUNT };
+enum { S_Vx, S_Vy, S_P, S_txx, S_tyy, S_txy, S_th, S_txyc, S_lam, S_lamv, S_eta, S_etav, S_Ux, S_Uy, S_COUNT };
 struct Plan2 {
-    bool vc;
+    bool vc, inc;   // inc: strain-increment form (the displacement joins the ping-pong state)
     int nx, ny;
     size_t bytes[S_COUNT];
     double *set[2][S_COUNT];
@@ -493,6 +554,11 @@ template <bool VC, int TYT>
 static int k2_attr_both(int *nb)
 {
     int st = k2_attr<VC, true, TYT>(nullptr);
+    if (!st && VC) {   // the strain-increment instantiations share the tile choice of the ε form
+        constexpr int smem = 16 * TX * TYT * 8;
+        JR_CUDA(cudaFuncSetAttribute(k_stokes2d<true, true, TYT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        JR_CUDA(cudaFuncSetAttribute(k_stokes2d<true, false, TYT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    }
     return st ? st : k2_attr<VC, false, TYT>(nb);
 }
 #define K2_TILES(X) X(12) X(14) X(16) X(18) X(20)
@@ -548,10 +614,20 @@ static int check2d(const jr_fields *s, const jr_stokes_opts *o, bool vc, const j
     for (int q : req_common) JR_REQUIRE(s->f[q] != nullptr, JR_ERR_SHAPE, "required field '%s' is NULL", jr_field_name(q));
     if (!vc) {
         JR_REQUIRE(F(K) && F(G), JR_ERR_SHAPE, "2D-V2 needs the K and G arrays");
+        JR_REQUIRE(!o->strain_increment && !o->displacement_bcs, JR_ERR_UNSUPPORTED,
+                   "strain_increment / DisplacementBoundaryConditions are supported by the multiphase 2D solve (2D-VC) only");
     } else {
         static const int req_vc[] = {JR_F_txy_c, JR_F_txy_o_c, JR_F_pxx, JR_F_pyy, JR_F_pxy, JR_F_tII, JR_F_eta_vep, JR_F_e_vol_pl, JR_F_EII_pl, JR_F_EVol_pl};
         for (int q : req_vc) JR_REQUIRE(s->f[q] != nullptr, JR_ERR_SHAPE, "required field '%s' is NULL", jr_field_name(q));
         JR_REQUIRE(in && in->ph_center && in->ph_vertex, JR_ERR_SHAPE, "2D-VC needs phase ratios at centres and vertices");
+        if (o->strain_increment || o->displacement_bcs) {
+            JR_REQUIRE(F(Ux) && F(Uy), JR_ERR_SHAPE, "strain_increment / DisplacementBoundaryConditions need the displacement arrays U");
+        }
+        if (o->strain_increment) {
+            JR_REQUIRE(F(dxx) && F(dyy) && F(dxy) && F(divU), JR_ERR_SHAPE, "strain_increment needs the Δε tensor and ∇U");
+        }
+        if (o->displacement_bcs) JR_REQUIRE(!(o->periodic[0] | o->periodic[1] | o->periodic[4] | o->periodic[5]), JR_ERR_UNSUPPORTED,
+                       "periodic DisplacementBoundaryConditions are outside the supported subset");
     }
     return JR_OK;
 }
@@ -562,7 +638,9 @@ static int plan2_begin(jr_context *ctx, const jr_fields *s, const jr_stokes_opts
     p->vc = vc;
     const int nx = p->nx = s->n[0], ny = p->ny = s->n[1];
     const size_t nc = (size_t)nx * ny * 8, nv = (size_t)(nx + 1) * (ny + 1) * 8;
-    const size_t b[S_COUNT] = {(size_t)(nx + 1) * (ny + 2) * 8, (size_t)(nx + 2) * (ny + 1) * 8, nc, nc, nc, nv, nc, nc, nc, nv, nc, nv};
+    p->inc = vc && o->strain_increment;
+    const size_t nVx = (size_t)(nx + 1) * (ny + 2) * 8, nVy = (size_t)(nx + 2) * (ny + 1) * 8;
+    const size_t b[S_COUNT] = {nVx, nVy, nc, nc, nc, nv, nc, nc, nc, nv, nc, nv, p->inc ? nVx : 0, p->inc ? nVy : 0};
     size_t off[S_COUNT + 1], tot = 0;
     for (int q = 0; q < S_COUNT; q++) { p->bytes[q] = b[q]; off[q] = tot; tot += (b[q] + 255) & ~(size_t)255; }
     off[S_COUNT] = tot;
@@ -576,6 +654,7 @@ static int plan2_begin(jr_context *ctx, const jr_fields *s, const jr_stokes_opts
     // set 0 aliases the caller's arrays where they exist (no packing); θ, λ, λv are solver-local (Stokes2D.jl:635-637)
     p->set[0][S_Vx] = F(Vx); p->set[0][S_Vy] = F(Vy); p->set[0][S_P] = F(P); p->set[0][S_txx] = F(txx); p->set[0][S_tyy] = F(tyy); p->set[0][S_txy] = F(txy);
     p->set[0][S_eta] = F(eta);
+    if (p->inc) { p->set[0][S_Ux] = F(Ux); p->set[0][S_Uy] = F(Uy); }
     if (vc) {
         p->set[0][S_txyc] = F(txy_c);
         if (F(etav)) p->set[0][S_etav] = F(etav);
@@ -590,6 +669,8 @@ static int plan2_begin(jr_context *ctx, const jr_fields *s, const jr_stokes_opts
     k.rel = o->lambda_relaxation; k.nu = o->viscosity_relaxation; k.cut_lo = o->visc_cutoff_lo; k.cut_hi = o->visc_cutoff_hi;
     k.fs_l = o->free_slip[0]; k.fs_r = o->free_slip[1]; k.fs_t = o->free_slip[4]; k.fs_b = o->free_slip[5];
     k.ns_l = o->no_slip[0]; k.ns_r = o->no_slip[1]; k.ns_t = o->no_slip[4]; k.ns_b = o->no_slip[5];
+    k.dbc = vc && o->displacement_bcs;
+    k.dxx = F(dxx); k.dyy = F(dyy); k.dxy = F(dxy); k.divU = F(divU);
     k.P0 = F(P0); k.Q = F(Q); k.K = F(K); k.G = F(G); k.etatau = F(etatau);
     k.txxo = F(txx_o); k.tyyo = F(tyy_o); k.txyo = F(txy_o); k.txyco = F(txy_o_c);
     k.rhogx = F(rhogx); k.rhogy = F(rhogy); k.T = F(T); k.Pargs = F(Pargs); k.dTargs = F(dTargs);
@@ -613,13 +694,17 @@ static int plan2_iter(jr_context *ctx, Plan2 *p, int64_t it, bool diag)
     k.txyc_i = I[S_txyc]; k.lam_i = I[S_lam]; k.lamv_i = I[S_lamv]; k.eta_i = I[S_eta]; k.etav_i = I[S_etav];
     k.Vx_o = O[S_Vx]; k.Vy_o = O[S_Vy]; k.P_o = O[S_P]; k.txx_o = O[S_txx]; k.tyy_o = O[S_tyy]; k.txy_o = O[S_txy]; k.th_o = O[S_th];
     k.txyc_o = O[S_txyc]; k.lam_o = O[S_lam]; k.lamv_o = O[S_lamv]; k.eta_o = O[S_eta]; k.etav_o = O[S_etav];
+    k.Ux_i = I[S_Ux]; k.Uy_i = I[S_Uy]; k.Ux_o = O[S_Ux]; k.Uy_o = O[S_Uy];
     if (p->vc && k.Pargs == p->set[0][S_P]) k.Pargs = I[S_P];  // args.P aliases stokes.P in the reference's scripts
     const int ty = p->ty;
     dim3 blk(TX, ty), grd((p->nx + 1 + TX - 3) / (TX - 2), (p->ny + 1 + ty - 3) / (ty - 2));
     const size_t smem = (size_t)(p->vc ? 16 : 11) * TX * ty * 8;
 #define X(T_)                                                                                              \
     if (ty == T_) {                                                                                        \
-        if (p->vc) {                                                                                       \
+        if (p->inc) {                                                                                      \
+            if (diag) k_stokes2d<true, true, T_, true><<<grd, blk, smem, ctx->stream>>>(k, p->pt);         \
+            else k_stokes2d<true, false, T_, true><<<grd, blk, smem, ctx->stream>>>(k, p->pt);             \
+        } else if (p->vc) {                                                                                \
             if (diag) k_stokes2d<true, true, T_><<<grd, blk, smem, ctx->stream>>>(k, p->pt);               \
             else k_stokes2d<true, false, T_><<<grd, blk, smem, ctx->stream>>>(k, p->pt);                   \
         } else {                                                                                           \
@@ -646,7 +731,7 @@ static int plan2_finish(jr_context *ctx, const jr_fields *s, Plan2 *p, int64_t n
     cudaStream_t st = ctx->stream;
     if (niter & 1) {
         double *user[S_COUNT] = {F(Vx), F(Vy), F(P), F(txx), F(tyy), F(txy), nullptr, p->vc ? F(txy_c) : nullptr, nullptr, nullptr,
-                                 p->vc ? F(eta) : nullptr, p->vc ? F(etav) : nullptr};
+                                 p->vc ? F(eta) : nullptr, p->vc ? F(etav) : nullptr, p->inc ? F(Ux) : nullptr, p->inc ? F(Uy) : nullptr};
         for (int q = 0; q < S_COUNT; q++)
             if (user[q] && user[q] != Fin[q]) JR_CUDA(cudaMemcpyAsync(user[q], Fin[q], p->bytes[q], cudaMemcpyDeviceToDevice, st));
     }
@@ -709,10 +794,23 @@ static int pre_V2(jr_context *ctx, const jr_fields *s)
     return jr_launch_maxloc3d(ctx, F(etatau), F(eta), n, w);  // ητ = deepcopy(η); compute_maxloc!  Stokes2D.jl:214-216
 }
 
+static inline double jr_inv_host(double x) { return 1.0 / x; }
+__global__ void k_scale2(size_t n, double *__restrict__ dst, const double *__restrict__ src, double f)
+{
+    const size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (q < n) dst[q] = src[q] * f;
+}
+
 static int pre_VC(jr_context *ctx, const jr_fields *s, Plan2 *p)
 {
     const size_t nc = p->bytes[S_P], nv = p->bytes[S_txy];
     cudaStream_t st = ctx->stream;
+    if (p->k.dbc) {   // displacement2velocity!(stokes, dt, flow_bcs::DisplacementBoundaryConditions)  Stokes2D.jl:647 ; types/displacement.jl:33-70
+        const size_t nVx = p->bytes[S_Vx] / 8, nVy = p->bytes[S_Vy] / 8;
+        k_scale2<<<(unsigned)((nVx + 255) / 256), 256, 0, st>>>(nVx, F(Vx), F(Ux), jr_inv_host(p->k.dt));
+        k_scale2<<<(unsigned)((nVy + 255) / 256), 256, 0, st>>>(nVy, F(Vy), F(Uy), jr_inv_host(p->k.dt));
+        ctx->launches += 2;
+    }
     JR_CUDA(cudaMemcpyAsync(F(P0), F(P), nc, cudaMemcpyDeviceToDevice, st));              // @copy stokes.P0 stokes.P   :609
     JR_CUDA(cudaMemcpyAsync(p->set[0][S_th], F(P), nc, cudaMemcpyDeviceToDevice, st));    // θ = deepcopy(stokes.P)     :635
     JR_CUDA(cudaMemsetAsync(p->set[0][S_lam], 0, nc, st));                                 // λ, λv = 0                  :636-637

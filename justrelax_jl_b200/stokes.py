@@ -66,7 +66,7 @@ def build_fields(slots: dict, ni):
 
 
 def build_opts(pt_stokes, _di, dt, flow_bcs, n_g, *, iterMax, nout, OptsType=_abi.StokesOpts, viscosity_relaxation=1e-2,
-               λ_relaxation=0.2, viscosity_cutoff=(-math.inf, math.inf), iterMin=100, strain_rate_ni_only=0):
+               λ_relaxation=0.2, viscosity_cutoff=(-math.inf, math.inf), iterMin=100, strain_rate_ni_only=0, strain_increment=False):
     o = OptsType()
     o.r, o.theta_dtau, o.eta_dtau = pt_stokes.r, pt_stokes.θ_dτ, pt_stokes.ηdτ
     o.eps_rel, o.eps_abs = pt_stokes.ϵ_rel, pt_stokes.ϵ_abs
@@ -84,6 +84,8 @@ def build_opts(pt_stokes, _di, dt, flow_bcs, n_g, *, iterMax, nout, OptsType=_ab
     o.visc_cutoff_lo, o.visc_cutoff_hi = float(viscosity_cutoff[0]), float(viscosity_cutoff[1])
     o.iterMin = int(iterMin)
     o.strain_rate_ni_only = int(strain_rate_ni_only)
+    o.strain_increment = int(bool(strain_increment))
+    o.displacement_bcs = int(isinstance(flow_bcs, DisplacementBoundaryConditions))
     return o
 
 
@@ -318,14 +320,14 @@ def norm_interior(A, interior: bool = True) -> float:
 
 # ------------------------------------------------------------------------------------------------------------------
 # 2D variants
-def _common_checks(stokes, flow_bcs, arrays):
+def _common_checks(stokes, flow_bcs, arrays, *, allow_displacement=False):
     if isinstance(backend(stokes), CPUBackendTrait):
         raise RuntimeError("solve_: StokesArrays live on the host (CPUBackend). This package only provides the B200 "
                            "backend; the CPU solver is JustRelax.jl's own. No CPU fallback.")
     if not isinstance(flow_bcs, AbstractFlowBoundaryConditions):
         raise TypeError(f"Unknown boundary conditions type: {type(flow_bcs)}")
-    if isinstance(flow_bcs, DisplacementBoundaryConditions):
-        raise NotImplementedError("DisplacementBoundaryConditions are outside the supported subset (SURVEY §8f-3)")
+    if isinstance(flow_bcs, DisplacementBoundaryConditions) and not allow_displacement:
+        raise NotImplementedError("DisplacementBoundaryConditions are supported by the multiphase 2D solve (2D-VC) only")
     for a in arrays:
         if a is not None and not is_device_array(a):
             raise ValueError("array arguments must be B200 arrays (use PTArray(B200Backend)(x))")
@@ -444,7 +446,7 @@ def vc_slots(stokes, ρg, args) -> dict:
 def _vc_opts(stokes, pt_stokes, grid, flow_bcs, dt, igg, kw):
     return build_opts(pt_stokes, grid._di.center, dt, flow_bcs, igg.n_g(stokes.ni), iterMax=kw["iterMax"], nout=kw["nout"],
                       viscosity_relaxation=kw["viscosity_relaxation"], λ_relaxation=kw["λ_relaxation"],
-                      viscosity_cutoff=kw["viscosity_cutoff"], iterMin=kw["iterMin"])
+                      viscosity_cutoff=kw["viscosity_cutoff"], iterMin=kw["iterMin"], strain_increment=kw.get("strain_increment", False))
 
 
 def _solve2d_VC(stokes, pt_stokes, di, flow_bcs, ρg, phase_ratios, rheology, args, dt, igg: Optional[IGG] = None, *, kwargs=None):
@@ -452,9 +454,7 @@ def _solve2d_VC(stokes, pt_stokes, di, flow_bcs, ρg, phase_ratios, rheology, ar
     kw = dict(iterMax=50e3, iterMin=1e2, viscosity_relaxation=1e-2, λ_relaxation=0.2, free_surface=False, nout=500, b_width=(4, 4, 0),
               verbose=True, viscosity_cutoff=(-math.inf, math.inf), strain_increment=False)
     kw.update(kwargs or {})
-    if kw["strain_increment"]:
-        raise NotImplementedError("strain_increment = true (Δε form) is outside the supported subset (SURVEY §8f-3)")
-    _common_checks(stokes, flow_bcs, ρg)
+    _common_checks(stokes, flow_bcs, ρg, allow_displacement=True)
     igg = igg or IGG()
     _single_rank2d(igg)
     grid = _grid_of(stokes, di, igg)
@@ -475,7 +475,7 @@ def iterate2d_VC_(stokes, pt_stokes, di, flow_bcs, ρg, phase_ratios, rheology, 
                   kwargs=None):
     """pre-loop initialisation + exactly `niter` iterations of variant 2D-VC (+ the exit kernels when finish)"""
     kw = dict(iterMax=niter, iterMin=0, viscosity_relaxation=1e-2, λ_relaxation=0.2, free_surface=False, nout=max(niter, 1),
-              viscosity_cutoff=(-math.inf, math.inf))
+              viscosity_cutoff=(-math.inf, math.inf), strain_increment=False)
     kw.update(kwargs or {})
     igg = igg or IGG()
     _single_rank2d(igg)

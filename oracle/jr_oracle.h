@@ -82,6 +82,9 @@ typedef struct {
     double viscosity_relaxation, lambda_relaxation, visc_cutoff_lo, visc_cutoff_hi;
     int64_t iterMin;
     int32_t strain_rate_ni_only;  /* Q20: 3D-VC launches strain rate over ni */
+    int32_t strain_increment;     /* 2D-VC kwarg strain_increment: Δε form (Stokes2D.jl:659-730, StressKernels.jl:1147-1302) */
+    int32_t displacement_bcs;     /* flow_bcs isa DisplacementBoundaryConditions: V = U/dt before the loop, BCs applied to U */
+    int32_t _pad;
 } orc_stokes_opts;
 
 typedef struct {

@@ -57,20 +57,23 @@ static inline void compute_P_point(double *RP, double *P, double P0, double divV
     *P = ((fma(P0, _Kdt, (-divV + (Q * _dt)))) * psi + Pc) / (1 + _Kdt * psi);
 }
 
-static void strain_rate2(const orc_fields *s, const double _di[3])
+/* compute_strain_rate! 2D  VelocityKernels.jl:10-44 — on (V, ∇V) → ε, or on (U, ∇U) → Δε (strain-increment form, Stokes2D.jl:681-689) */
+static void strain_rate2_of(const orc_fields *s, const double _di[3], const double *Ax, const double *Ay, const double *div, double *exx, double *eyy,
+                            double *exy)
 {
     const int nx = s->n[0], ny = s->n[1];
-    const arr ax = mk2(F(Vx), nx + 1, ny + 2), ay = mk2(F(Vy), nx + 2, ny + 1);
+    const arr ax = mk2((double *)Ax, nx + 1, ny + 2), ay = mk2((double *)Ay, nx + 2, ny + 1);
     for (int j = 1; j <= ny + 1; j++)
         for (int i = 1; i <= nx + 1; i++) {
             if (i <= nx && j <= ny) {
-                const double dV = A2(F(divV), nx, i, j) * orc_inv(3.0);
-                A2(F(exx), nx, i, j) = d_xi2(ax, _di[0], i, j) - dV;
-                A2(F(eyy), nx, i, j) = d_yi2(ay, _di[1], i, j) - dV;
+                const double dV = A2(div, nx, i, j) * orc_inv(3.0);
+                A2(exx, nx, i, j) = d_xi2(ax, _di[0], i, j) - dV;
+                A2(eyy, nx, i, j) = d_yi2(ay, _di[1], i, j) - dV;
             }
-            A2(F(exy), nx + 1, i, j) = 0.5 * (_di[1] * (AT2(ax, i, j + 1) - AT2(ax, i, j)) + _di[0] * (AT2(ay, i + 1, j) - AT2(ay, i, j)));
+            A2(exy, nx + 1, i, j) = 0.5 * (_di[1] * (AT2(ax, i, j + 1) - AT2(ax, i, j)) + _di[0] * (AT2(ay, i + 1, j) - AT2(ay, i, j)));
         }
 }
+static void strain_rate2(const orc_fields *s, const double _di[3]) { strain_rate2_of(s, _di, F(Vx), F(Vy), F(divV), F(exx), F(eyy), F(exy)); }
 
 static inline double dtau_r(double th, double eta, double _Gdt) { return orc_inv(th + fma(eta, _Gdt, 1.0)); }
 static inline double stress_inc(double t, double to, double eta, double e, double _Gdt, double dtr)
@@ -290,9 +293,17 @@ void orc_viscosity2d(const orc_fields *s, const orc_stokes_opts *o, const orc_vc
         }
 }
 
-/* update_stresses_center_vertex_ps! 2D  StressKernels.jl:992-1144, Jacobi schedule */
+/* compute_stress_increment, strain-increment form  StressKernels.jl:19-22 */
+static inline double stress_inc_d(double t, double to, double eta, double de, double _G, double dtr, double dt)
+{
+    return dtr * fma(2.0 * eta, de, fma(-(t - to) * eta, _G, -t * dt));
+}
+
+/* update_stresses_center_vertex_ps! 2D  StressKernels.jl:992-1144 (ε form) and :1147-1302 (Δε form, inc != 0), Jacobi schedule.
+ * Δε form: dτ_r = 1/(θ_dτ·dt + η/G + dt), increments from Δε with 1/G and −τ·dt, plastic terms carry the extra dt. */
 static void stress_vep2(const orc_fields *s, const orc_stokes_opts *o, const orc_vc_inputs *vc, const double *theta, double *lam, double *lamv)
 {
+    const int inc = o->strain_increment;
     const int nx = s->n[0], ny = s->n[1];
     const size_t nc = (size_t)nx * ny, nv = (size_t)(nx + 1) * (ny + 1);
     const double dt = o->dt, th = o->theta_dtau, rel = o->lambda_relaxation;
@@ -305,17 +316,19 @@ static void stress_vep2(const orc_fields *s, const orc_stokes_opts *o, const orc
             const size_t v = IX2(nx + 1, i, j);
             /* ---- vertex ---- */
             {
-                const double Pv = AVC(theta), exxv = AVC(F(exx)), eyyv = AVC(F(eyy)), txxv = AVC(txx0), tyyv = AVC(tyy0);
+                const double Pv = AVC(theta), exxv = inc ? AVC(F(dxx)) : AVC(F(exx)), eyyv = inc ? AVC(F(dyy)) : AVC(F(eyy)), txxv = AVC(txx0), tyyv = AVC(tyy0);
                 const double txxov = AVC(F(txx_o)), tyyov = AVC(F(tyy_o)), EIIv = AVC(F(EII_pl));
                 (void)EIIv;
                 int is_pl; double eta_reg;
                 plastic_params(vc, vc->ph_vertex, nv, v, &is_pl, &eta_reg);
                 const double _Gdt = orc_inv(ratio_G(vc, vc->ph_vertex, nv, v) * dt), Kv = ratio_Kb(vc, vc->ph_vertex, nv, v);
+                const double _G = orc_inv(ratio_G(vc, vc->ph_vertex, nv, v));
                 const double etav = 4 / (1 / A2(F(eta), nx, i0, j0) + 1 / A2(F(eta), nx, ic, jc) + 1 / A2(F(eta), nx, i0, jc) + 1 / A2(F(eta), nx, ic, j0));
-                const double dtr = orc_inv(th + etav * _Gdt + 1.0);
+                const double dtr = inc ? orc_inv(th * dt + etav * _G + dt) : orc_inv(th + etav * _Gdt + 1.0);
                 const double txyv = F(txy)[v];
-                const double dxx = stress_inc(txxv, txxov, etav, exxv, _Gdt, dtr), dyy = stress_inc(tyyv, tyyov, etav, eyyv, _Gdt, dtr);
-                const double dxy = stress_inc(txyv, F(txy_o)[v], etav, F(exy)[v], _Gdt, dtr);
+                const double dxx = inc ? stress_inc_d(txxv, txxov, etav, exxv, _G, dtr, dt) : stress_inc(txxv, txxov, etav, exxv, _Gdt, dtr);
+                const double dyy = inc ? stress_inc_d(tyyv, tyyov, etav, eyyv, _G, dtr, dt) : stress_inc(tyyv, tyyov, etav, eyyv, _Gdt, dtr);
+                const double dxy = inc ? stress_inc_d(txyv, F(txy_o)[v], etav, F(dxy)[v], _G, dtr, dt) : stress_inc(txyv, F(txy_o)[v], etav, F(exy)[v], _Gdt, dtr);
                 const double trial[3] = {txxv + dxx, tyyv + dyy, txyv + dxy};
                 const double tII = second_invariant3(dxx + txxv, dyy + tyyv, dxy + txyv);
                 double dQ[3], dQdP, dFdP;
@@ -323,9 +336,9 @@ static void stress_vep2(const orc_fields *s, const orc_stokes_opts *o, const orc
                 const double volume = isinf(Kv) ? 0.0 : Kv * dt * dFdP * dQdP;
                 const double Fv = yield_F(vc, vc->ph_vertex, nv, v, Pv, tII);
                 if (is_pl && tII != 0.0 && Fv > 0) {
-                    lamv[v] = fma(rel, fmax(Fv, 0.0) / (etav * dtr + eta_reg + volume), (1.0 - rel) * lamv[v]);
+                    lamv[v] = fma(rel, fmax(Fv, 0.0) / ((inc ? etav * dtr * dt : etav * dtr) + eta_reg + volume), (1.0 - rel) * lamv[v]);
                     const double epl = lamv[v] * dQ[2];
-                    F(txy)[v] += fma(-2.0, etav * epl * dtr, dxy);
+                    F(txy)[v] += inc ? fma(-2.0, etav * dt * epl * dtr, dxy) : fma(-2.0, etav * epl * dtr, dxy);
                     F(pxy)[v] = epl;
                 } else {
                     F(txy)[v] += dxy;
@@ -339,14 +352,20 @@ static void stress_vep2(const orc_fields *s, const orc_stokes_opts *o, const orc
                 int is_pl; double eta_reg;
                 plastic_params(vc, vc->ph_center, nc, c, &is_pl, &eta_reg);
                 const double K = ratio_Kb(vc, vc->ph_center, nc, c), eta = F(eta)[c];
-                const double dtr = 1.0 / (th + eta * _Gdt + 1.0);
+                const double _G = orc_inv(ratio_G(vc, vc->ph_center, nc, c));
+                const double dtr = inc ? 1.0 / (th * dt + eta * _G + dt) : 1.0 / (th + eta * _Gdt + 1.0);
                 const arr exyv = mk2(F(exy), nx + 1, ny + 1);
                 const double eij[3] = {F(exx)[c], F(eyy)[c],
                                        (((AT2(exyv, i, j) + AT2(exyv, i + 1, j)) + AT2(exyv, i, j + 1)) + AT2(exyv, i + 1, j + 1)) / 4};
                 double tij[3] = {F(txx)[c], F(tyy)[c], F(txy_c)[c]};
                 const double tijo[3] = {F(txx_o)[c], F(tyy_o)[c], F(txy_o_c)[c]};
                 double dt_[3];
-                for (int q = 0; q < 3; q++) dt_[q] = stress_inc(tij[q], tijo[q], eta, eij[q], _Gdt, dtr);
+                if (inc) {
+                    const arr dxyv = mk2(F(dxy), nx + 1, ny + 1);
+                    const double dij[3] = {F(dxx)[c], F(dyy)[c], (((AT2(dxyv, i, j) + AT2(dxyv, i + 1, j)) + AT2(dxyv, i, j + 1)) + AT2(dxyv, i + 1, j + 1)) / 4};
+                    for (int q = 0; q < 3; q++) dt_[q] = stress_inc_d(tij[q], tijo[q], eta, dij[q], _G, dtr, dt);
+                } else
+                    for (int q = 0; q < 3; q++) dt_[q] = stress_inc(tij[q], tijo[q], eta, eij[q], _Gdt, dtr);
                 double tII = second_invariant3(dt_[0] + tij[0], dt_[1] + tij[1], dt_[2] + tij[2]);
                 const double trial[3] = {tij[0] + dt_[0], tij[1] + dt_[1], tij[2] + dt_[2]};
                 double dQ[3], dQdP, dFdP;
@@ -355,11 +374,11 @@ static void stress_vep2(const orc_fields *s, const orc_stokes_opts *o, const orc
                 const double volume = isinf(K) ? 0.0 : K * dt * dFdP * dQdP;
                 const double Fc = yield_F(vc, vc->ph_center, nc, c, Pr, tII);
                 if (is_pl && tII != 0.0 && Fc > 0) {
-                    lam[c] = fma(rel, fmax(Fc, 0.0) / (eta * dtr + eta_reg + volume), (1.0 - rel) * lam[c]);
+                    lam[c] = fma(rel, fmax(Fc, 0.0) / ((inc ? eta * dtr * dt : eta * dtr) + eta_reg + volume), (1.0 - rel) * lam[c]);
                     double epl[3];
                     for (int q = 0; q < 3; q++) {
                         epl[q] = lam[c] * dQ[q];
-                        dt_[q] = fma(-2.0, eta * epl[q] * dtr, dt_[q]);
+                        dt_[q] = inc ? fma(-2.0, eta * dt * epl[q] * dtr, dt_[q]) : fma(-2.0, eta * epl[q] * dtr, dt_[q]);
                         tij[q] = dt_[q] + tij[q];
                     }
                     F(e_vol_pl)[c] = -lam[c] * dQdP;
@@ -402,7 +421,7 @@ static void shear2center2(double *c, const double *v, int nx, int ny)
 
 typedef struct { double *theta, *lam, *lamv; } vc_scratch;
 
-static void pre_VC(const orc_fields *s, const orc_vc_inputs *vc, vc_scratch *w)
+static void pre_VC(const orc_fields *s, const orc_stokes_opts *o, const orc_vc_inputs *vc, vc_scratch *w)
 {
     const int nx = s->n[0], ny = s->n[1];
     const size_t nc = (size_t)nx * ny, nv = (size_t)(nx + 1) * (ny + 1);
@@ -413,6 +432,12 @@ static void pre_VC(const orc_fields *s, const orc_vc_inputs *vc, vc_scratch *w)
     memset(F(pxx), 0, nc * 8); memset(F(pyy), 0, nc * 8);          /* @tensor_center(ε_pl) .= 0           :641-643 */
     if (F(pxy_c)) memset(F(pxy_c), 0, nc * 8);
     orc_rhog2d(s, vc);                                             /* compute_ρg!                         :646 */
+    if (o->displacement_bcs) {                                     /* displacement2velocity!(stokes, dt, flow_bcs) :647 ; types/displacement.jl:33-70 */
+        const size_t nVx = (size_t)(nx + 1) * (ny + 2), nVy = (size_t)(nx + 2) * (ny + 1);
+        const double _dt = orc_inv(o->dt);
+        for (size_t q = 0; q < nVx; q++) F(Vx)[q] = F(Ux)[q] * _dt;
+        for (size_t q = 0; q < nVy; q++) F(Vy)[q] = F(Uy)[q] * _dt;
+    }
 }
 
 static void iter_VC(const orc_fields *s, const orc_stokes_opts *o, const orc_vc_inputs *vc, vc_scratch *w)
@@ -430,12 +455,20 @@ static void iter_VC(const orc_fields *s, const orc_stokes_opts *o, const orc_vc_
             compute_P_point(&F(RP)[c], &w->theta[c], F(P0)[c], F(divV)[c], F(Q)[c], F(etatau)[c], K, G, o->dt, o->r, o->theta_dtau);
     }
     if (!density_is_constant(vc)) orc_rhog2d(s, vc);               /* update_ρg!                           :679 */
-    strain_rate2(s, o->_di);
+    if (o->strain_increment) {                                     /* :660-662, 681-695 */
+        const size_t nv = (size_t)(nx + 1) * (ny + 1);
+        const double _dt = orc_inv(o->dt);
+        divV2(s, o->_di, F(Ux), F(Uy), F(divU));                   /* compute_∇V!(stokes.∇U, @displacement(stokes), …) */
+        strain_rate2_of(s, o->_di, F(Ux), F(Uy), F(divU), F(dxx), F(dyy), F(dxy));   /* Δε from U */
+        for (size_t c = 0; c < nc; c++) { F(exx)[c] = F(dxx)[c] * _dt; F(eyy)[c] = F(dyy)[c] * _dt; }   /* compute_strain_rate_from_increment! */
+        for (size_t v = 0; v < nv; v++) F(exy)[v] = F(dxy)[v] * _dt;
+    } else
+        strain_rate2(s, o->_di);
     stress_vep2(s, o, vc, w->theta, w->lam, w->lamv);
     orc_viscosity2d(s, o, vc, o->viscosity_relaxation);            /* update_viscosity_τII! AFTER the stress kernel (quirk Q13) */
     V2(s, o, 1, vc->free_surface);
     v2u2(s, o->dt);
-    orc_flow_bcs2(s, o, 0);
+    orc_flow_bcs2(s, o, o->displacement_bcs);                      /* flow_bcs!(stokes, flow_bcs): on U for DisplacementBoundaryConditions */
 }
 
 static void post_VC(const orc_fields *s, const orc_stokes_opts *o, vc_scratch *w)
@@ -463,7 +496,7 @@ static void post_VC(const orc_fields *s, const orc_stokes_opts *o, vc_scratch *w
 int orc_iterate2d_VC(const orc_fields *s, const orc_stokes_opts *o, const orc_vc_inputs *vc, int64_t niter, int finish)
 {
     vc_scratch w;
-    pre_VC(s, vc, &w);
+    pre_VC(s, o, vc, &w);
     for (int64_t it = 0; it < niter; it++) iter_VC(s, o, vc, &w);
     Res2(s, o, 1, vc->free_surface);
     if (F(lam)) memcpy(F(lam), w.lam, (size_t)s->n[0] * s->n[1] * 8);      /* expose the solver-local λ, λv for parity checks */
@@ -479,7 +512,7 @@ int orc_solve2d_VC(const orc_fields *s, const orc_stokes_opts *o, const orc_vc_i
     double err_it1 = 1.0, err = 1.0;
     int64_t iter = 0, cont = 0;
     int status = 0;
-    pre_VC(s, vc, &w);
+    pre_VC(s, o, vc, &w);
     while (iter <= o->iterMax) {
         if (o->iterMin < iter && ((err / err_it1) < o->eps_rel || err < o->eps_abs)) break;
         iter_VC(s, o, vc, &w);

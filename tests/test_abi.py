@@ -36,7 +36,7 @@ def test_struct_sizes_match_header():
 
     n = len(_abi.field_names())
     assert C.sizeof(_abi.make_fields_struct(n)) == 16 + 8 * n
-    assert C.sizeof(_abi.StokesOpts) == 5 * 8 + 3 * 8 + 8 + 16 + 12 + 3 * 24 + 4 + 4 * 8 + 8 + 8
+    assert C.sizeof(_abi.StokesOpts) == 5 * 8 + 3 * 8 + 8 + 16 + 12 + 3 * 24 + 4 + 4 * 8 + 8 + 16
 
 
 def test_no_gpu_fails_loudly():

@@ -20,11 +20,12 @@ VC_DIAG = V2_DIAG + ["pxx", "pyy", "pxy", "tII", "eta_vep", "e_vol_pl", "P0", "r
 NAMES6 = ("left", "right", "front", "back", "top", "bot")
 
 
-def _bcs(flags):
-    from justrelax_jl_b200.types import VelocityBoundaryConditions
+def _bcs(flags, displacement=False):
+    from justrelax_jl_b200.types import DisplacementBoundaryConditions, VelocityBoundaryConditions
 
     pick = lambda nm: {k: bool(v) for k, v in zip(NAMES6, flags[nm]) if k in ("left", "right", "top", "bot")}
-    return VelocityBoundaryConditions(free_slip=pick("free_slip"), no_slip=pick("no_slip"), periodic=pick("periodic"))
+    T = DisplacementBoundaryConditions if displacement else VelocityBoundaryConditions
+    return T(free_slip=pick("free_slip"), no_slip=pick("no_slip"), periodic=pick("periodic"))
 
 
 def random_stokes2d(ni, seed, *, dt=0.6, finite=True):
@@ -135,7 +136,7 @@ def random_vc2d(ni, seed, nphase=3, plastic=True, rho_var=False):
     return f, grid, pt, dt, rat, tuple(rheo)
 
 
-def _run_vc(oracle, ni, f, grid, pt, dt, rat, rheo, flags, niter, finish, free_surface=False, alias_P=False, dT=None):
+def _run_vc(oracle, ni, f, grid, pt, dt, rat, rheo, flags, niter, finish, free_surface=False, alias_P=False, dT=None, inc=False, dbc=False):
     from justrelax_jl_b200 import B200Backend, PhaseRatios, rheology as R, stokes as jst
 
     d = oracle.alloc_stokes(ni, f)
@@ -146,14 +147,15 @@ def _run_vc(oracle, ni, f, grid, pt, dt, rat, rheo, flags, niter, finish, free_s
     st, extra = device_stokes(ni, d)
     rows = R.lower_stokes(rheo)
     vc = oracle.vc_inputs(rows, R.gravity_of(rheo), rat, free_surface=dt if free_surface else 0.0)
-    opts = oracle.make_opts(pt, grid._di.center, dt, flags, ni, iterMax=niter, nout=niter, viscosity_relaxation=0.3, lambda_relaxation=0.2)
+    opts = oracle.make_opts(pt, grid._di.center, dt, flags, ni, iterMax=niter, nout=niter, viscosity_relaxation=0.3, lambda_relaxation=0.2,
+                            strain_increment=int(inc), displacement_bcs=int(dbc))
     oracle.iterate2d_VC(d, ni, opts, vc, niter, finish=finish)
     pr = PhaseRatios.from_arrays(B200Backend, **rat)
     args = dict(T=extra["T"], P=st.P if alias_P else extra["Pargs"])
     if dT is not None:
         args["ΔT"] = extra["dTargs"]
-    jst.iterate2d_VC_(st, pt, grid, _bcs(flags), (extra["rhogx"], extra["rhogy"]), pr, rheo, args, dt, niter, finish=finish,
-                      kwargs=dict(viscosity_relaxation=0.3, free_surface=free_surface))
+    jst.iterate2d_VC_(st, pt, grid, _bcs(flags, dbc), (extra["rhogx"], extra["rhogy"]), pr, rheo, args, dt, niter, finish=finish,
+                      kwargs=dict(viscosity_relaxation=0.3, free_surface=free_surface, strain_increment=inc))
     return {**st.slots(), "rhogx": extra["rhogx"], "rhogy": extra["rhogy"]}, d
 
 
@@ -181,6 +183,25 @@ def test_vc_thermal_stress_pressure_form(oracle):
         compare_slots(st, d, VC_STATE + VC_DIAG, TOL, f"2D-VC with ΔT niter={niter}")
     st0, d0 = _run_vc(oracle, ni, f, grid, pt, dt, rat, rheo, flags, 4, False, alias_P=True)
     assert max_rel_diff(to_host(st["P"]), d0["P"]) > 1e-4, "ΔT must change the pressure"
+
+
+@pytest.mark.parametrize("inc,dbc", [(True, False), (True, True), (False, True)])
+@pytest.mark.parametrize("ni", [(9, 7), (64, 47), (95, 130)])
+def test_vc_strain_increment_and_displacement_bcs(oracle, ni, inc, dbc):
+    """kwarg strain_increment = true (Δε form, Stokes2D.jl:659-730, StressKernels.jl:1147-1302) and DisplacementBoundaryConditions
+    (flow_bcs! on U, V = U/dt before the loop: types/displacement.jl:33-70) in the fused kernel, free-slip / no-slip mixes"""
+    f, grid, pt, dt, rat, rheo = random_vc2d(ni, 300 + ni[0], rho_var=False)
+    rng = np.random.default_rng(ni[1])
+    f["Ux"] = np.asfortranarray(rng.uniform(-1, 1, size=f["Vx"].shape)) * dt
+    f["Uy"] = np.asfortranarray(rng.uniform(-1, 1, size=f["Vy"].shape)) * dt
+    extra_names = ["Ux", "Uy"] + (["dxx", "dyy", "dxy", "divU"] if inc else [])
+    for flags in (dict(free_slip=[1, 1, 0, 0, 1, 1], no_slip=[0] * 6, periodic=[0] * 6),
+                  dict(free_slip=[1, 0, 0, 0, 0, 1], no_slip=[0, 1, 0, 0, 1, 0], periodic=[0] * 6)):
+        for niter, finish in ((1, False), (4, False), (5, True)):
+            st, d = _run_vc(oracle, ni, f, grid, pt, dt, rat, rheo, flags, niter, finish, inc=inc, dbc=dbc)
+            assert d["lam"].max() > 0 and d["lamv"].max() > 0
+            names = VC_STATE + VC_DIAG + extra_names + (["dxy_c", "exy_c", "txx_o"] if finish else [])
+            compare_slots(st, d, names, TOL, f"VC inc={inc} dbc={dbc} ni={ni} niter={niter} flags={flags}")
 
 
 def test_vc_exit_kernels_free_surface_and_mixed_bcs(oracle):

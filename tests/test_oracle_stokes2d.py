@@ -13,17 +13,20 @@ from justrelax_jl_b200 import rheology as R, setups
 from util import bc_flags
 
 
-def run_shearband(oracle, s):
+def run_shearband(oracle, s, *, strain_increment=0, displacement_bcs=0):
     d = oracle.alloc_stokes(s.ni, s.fields)
     rows = R.lower_stokes(s.rheology)
     vc = oracle.vc_inputs(rows, R.gravity_of(s.rheology), s.ratios)
     kw = s.kwargs
     opts = oracle.make_opts(s.pt_stokes, s.grid._di.center, s.dt, bc_flags(s.flow_bcs), s.ni, iterMax=kw["iterMax"], nout=kw["nout"],
-                            viscosity_cutoff=kw["viscosity_cutoff"])
+                            viscosity_cutoff=kw["viscosity_cutoff"], strain_increment=strain_increment, displacement_bcs=displacement_bcs)
+    if displacement_bcs:   # the displacement form prescribes U = V·dt (pureshear_bc! on the displacement, then flow_bcs! on U)
+        d["Ux"][...] = d["Vx"] * s.dt
+        d["Uy"][...] = d["Vy"] * s.dt
     fs = oracle.make_fields(d, s.ni)
     # compute_viscosity!(stokes, phase_ratios, args, rheology, (-Inf, Inf)) with relaxation 1   test_shearband2D.jl:133-135
     oracle.lib().orc_viscosity2d(C.byref(fs), C.byref(opts), C.byref(vc), C.c_double(1.0))
-    oracle.lib().orc_flow_bcs2(C.byref(fs), C.byref(opts), 0)
+    oracle.lib().orc_flow_bcs2(C.byref(fs), C.byref(opts), displacement_bcs)
     outs, txx_max = [], []
     for _ in range(s.nt):
         outs.append(oracle.solve2d_VC(d, s.ni, opts, vc))
@@ -42,6 +45,23 @@ def test_shearband2d_reference_golden(oracle):
     assert abs(txx_max[-1] - 1.6376258215356436) < 1.0e-4
     # plasticity was active
     assert d["EII_pl"].max() > 0 and d["lam"].max() > 0
+
+
+def test_shearband2d_strain_increment_form_reproduces_golden(oracle):
+    """kwarg strain_increment = true (Δε form: Stokes2D.jl:659-730, StressKernels.jl:1147-1302), with velocity and with displacement
+    boundary conditions (types/displacement.jl:62-70): the same physics, so the reference's shear-band golden
+    (test/test_shearband2D.jl:197-201) must be reproduced to its own tolerances"""
+    s = setups.shearband2d(32)
+    for dbc in (0, 1):
+        d, outs, txx_max = run_shearband(oracle, s, strain_increment=1, displacement_bcs=dbc)
+        assert all(o["status"] == 0 for o in outs) and outs[-1]["err_evo1"][-1] < 1.0e-6
+        tII = oracle.tensor_invariant2d(d["txx"], d["tyy"], d["txy"])
+        assert abs(tII.min() - 1.5128689768248313) < 1.0e-3, (dbc, tII.min())
+        assert abs(tII.max() - 1.6415759440014273) < 1.0e-3, (dbc, tII.max())
+        assert abs(txx_max[-1] - 1.6376258215356436) < 1.0e-4, (dbc, txx_max[-1])
+        assert d["EII_pl"].max() > 0
+        # Δε / dt is the strain rate
+        assert np.allclose(d["dxx"] / s.dt, d["exx"], rtol=1e-12, atol=0) and np.abs(d["dxx"]).max() > 0
 
 
 def run_sinking_block(oracle, s):
