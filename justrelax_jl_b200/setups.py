@@ -388,7 +388,7 @@ def shearband2d(n=32):
                            ratios=ratios, nt=10, kwargs=dict(verbose=False, iterMax=50.0e3, nout=1.0e2, viscosity_cutoff=(-math.inf, math.inf)))
 
 
-def sinking_block2d(n=32, *, nsub=8):
+def sinking_block2d(n=32, *, nsub=8, center_weights="uniform"):
     """test/test_sinking_block.jl:93-200 (variant 2D-VC with buoyancy, SI units): 500 km square, mantle (LinearViscous η = 1e21,
     ConstantDensity 3200) with a 100 km square block (η = 1e23, ρ = 3300) centred at x = 250 km, depth 100 km; no elasticity (G = Kb = Inf),
     g = 9.81, lithostatic initial pressure, free slip, dt = 1, PTStokesCoeffs(li, di; ϵ_rel = 1e-5, CFL = 0.95/√2.1),
@@ -414,7 +414,9 @@ def sinking_block2d(n=32, *, nsub=8):
         acc, wsum = np.zeros((x.size, y.size)), 0.0
         for ox in off:
             for oy in off:
-                w = (1.0 - abs(ox)) * (1.0 - abs(oy)) if hat else 1.0
+                # JustPIC weights every particle of a cell with the bilinear shape function of the node it contributes to — at the
+                # centres too (weights 1 … ½ per dimension): center_weights = "bilinear" emulates that, "uniform" is the volume fraction
+                w = (1.0 - abs(ox)) * (1.0 - abs(oy)) if (hat or center_weights == "bilinear") else 1.0
                 X, Y = np.meshgrid(x + ox * di[0], y + oy * di[1], indexing="ij")
                 acc += w * inside(X, Y)
                 wsum += w
@@ -483,6 +485,32 @@ def shearband3d(n=16):
     fields = dict(Vx=Vx, Vz=Vz, T=np.zeros((n + 2,) * 3, order="F"))
     return SimpleNamespace(ni=ni, li=li, di=di, grid=grid, igg=IGG(), pt_stokes=pt, flow_bcs=flow_bcs, dt=dt, fields=fields, rheology=rheology,
                            ratios=ratios, nt=3, kwargs=dict(verbose=False, iterMax=150.0e3, nout=1.0e3, viscosity_cutoff=(-math.inf, math.inf)))
+
+
+def shearband3d_extruded(n=32, ny=4):
+    """The reference's 2D shear-band test (test/test_shearband2D.jl:61-192, see shearband2d) extruded along y and run through the 3D
+    multiphase solver (variant 3D-VC): 2D (x, y) ↦ 3D (x, z), ny cubic cells deep, cylindrical inclusion, free slip on every face,
+    Vx = x εbg, Vz = −z εbg, Vy = 0, the 2D test's rheology (Kb = 4, η_vp = 8e-3), dt and tolerance.  Plane strain in 3D carries the
+    out-of-plane deviatoric stress τyy the 2D kernels do not have, so the 2D golden is reproduced up to that term (≈ 1 %)."""
+    from . import rheology as R
+
+    ni, li = (n, ny, n), (1.0, ny / n, 1.0)
+    grid = Geometry(ni, li, origin=(0.0, 0.0, 0.0))
+    di = grid.di.center
+    s2 = shearband2d(n)
+    ratios = {}
+    for nm, (x, y, z) in _stag_coords3(grid).items():
+        out = np.broadcast_to((((x[:, None, None] - 0.5) ** 2 + (z[None, None, :] - 0.5) ** 2) > 0.1 ** 2), (len(x), len(y), len(z)))
+        ratios[nm] = _onehot([out, ~out])
+    pt = PTStokesCoeffs((1.0, 1.0, 1.0), di, ϵ_rel=1.0e-6, CFL=0.75 / math.sqrt(3.1))
+    xv, yv, zv = grid.xvi
+    Vx = np.asfortranarray(np.broadcast_to((xv * 1.0)[:, None, None], (n + 1, ny + 2, n + 2)).copy())
+    Vz = np.asfortranarray(np.broadcast_to((-zv * 1.0)[None, None, :], (n + 2, ny + 2, n + 1)).copy())
+    flow_bcs = VelocityBoundaryConditions(free_slip=dict(left=True, right=True, top=True, bot=True, back=True, front=True),
+                                          no_slip=dict(left=False, right=False, top=False, bot=False, back=False, front=False))
+    fields = dict(Vx=Vx, Vz=Vz, T=np.zeros((n + 2, ny + 2, n + 2), order="F"))
+    return SimpleNamespace(ni=ni, li=li, di=di, grid=grid, igg=IGG(), pt_stokes=pt, flow_bcs=flow_bcs, dt=s2.dt, fields=fields, rheology=s2.rheology,
+                           ratios=ratios, nt=10, kwargs=dict(verbose=False, iterMax=50.0e3, nout=1.0e2, viscosity_cutoff=(-math.inf, math.inf)))
 
 
 def convection3d(nx=32, ny=32, nz=32, *, igg: IGG | None = None, plastic=True):

@@ -118,6 +118,31 @@ def test_shearband3d_solve_matches_oracle(oracle):
     assert np.isfinite(to_host(st.ε.II)).all() and to_host(st.ε.II).max() > 0
 
 
+def test_extruded_shearband_2d_reference_golden_through_3d_vc_on_gpu(oracle):
+    """the external pin of 3D-VC (tests/test_oracle_stokes3d_vc.py) on the device: the reference's 2D shear-band test extruded along y,
+    ten solve! calls through the public API, lands on the 2D golden of test/test_shearband2D.jl:197-201 to its own tolerances"""
+    from justrelax_jl_b200 import B200Backend, PhaseRatios, setups, stokes as jst, to_host
+    from test_oracle_stokes3d_vc import in_plane_invariant
+
+    s = setups.shearband3d_extruded(32, 4)
+    d = oracle.alloc_stokes(s.ni, s.fields)
+    st, extra = device_stokes(s.ni, d)
+    pr = PhaseRatios.from_arrays(B200Backend, **s.ratios)
+    args = dict(T=extra["T"], P=st.P)
+    jst.compute_viscosity_(st, pr, args, s.rheology, (-math.inf, math.inf))
+    jst.flow_bcs_(st, s.flow_bcs)
+    ρg = (extra["rhogx"], extra["rhogy"], extra["rhogz"])
+    txx_max = []
+    for _ in range(s.nt):
+        out = jst.solve_(st, s.pt_stokes, s.grid, s.flow_bcs, ρg, pr, s.rheology, args, s.dt, s.igg, kwargs=s.kwargs)
+        assert out.err_evo1[-1] < 1.0e-6
+        txx_max.append(float(to_host(st.τ.xx).max()))
+    tII = in_plane_invariant(oracle, to_host(st.τ.xx), to_host(st.τ.zz), to_host(st.τ.xz))
+    assert abs(tII.min() - 1.5128689768248313) < 1.0e-3 and abs(tII.max() - 1.6415759440014273) < 1.0e-3, (tII.min(), tII.max())
+    assert abs(txx_max[-1] - 1.6376258215356436) < 1.0e-4, txx_max[-1]
+    assert float(to_host(st.EII_pl).max()) > 0
+
+
 def test_convection3d_stokes_solve(oracle):
     """config 5's Stokes half at 16³: three phases (plastic crust, blob, weak layer), PT_Density with args.P aliasing stokes.P,
     gravity — solve to tolerance, compare with the oracle"""

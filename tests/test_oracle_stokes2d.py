@@ -209,3 +209,47 @@ def test_v2_iteration_matches_numpy_restatement(oracle):
     assert np.allclose(d["Rx"], Rx, rtol=0, atol=tol(Rx))
     Vxn = ref["Vx"][1:-1, 1:-1] + Rx * pt.ηdτ / (0.5 * (ett[1:] + ett[:-1]))
     assert np.allclose(d["Vx"][1:-1, 1:-1], Vxn, rtol=0, atol=tol(Vxn))
+
+
+def particle_equivalent_ratios(s, seed, nxcell=20):
+    """JustPIC-style phase ratios for the sinking block: nxcell particles per cell at uniformly random positions inside 5–95 % of the cell
+    (init_particles), phase by position (test_sinking_block.jl:60-79), ratios = bilinear-weighted particle fractions at the centres (own
+    cell) and at the vertices (the four surrounding cells) — phase_ratio_weights / bilinear_weight of JustPIC (third party, not vendored)"""
+    rng = np.random.default_rng(seed)
+    n = s.ni[0]
+    dx, dy = s.di
+    (xc, yc), (xv, yv) = s.grid.xci, s.grid.xvi
+    px = xv[:-1, None, None] + dx * (rng.random((n, n, nxcell)) * 0.9 + 0.05)
+    py = yv[None, :-1, None] + dy * (rng.random((n, n, nxcell)) * 0.9 + 0.05)
+    ph2 = (((px - 250e3) ** 2 <= 50e3 ** 2) & ((-py - 100e3) ** 2 <= 50e3 ** 2)).astype(float)
+    w = (1 - np.abs(px - xc[:, None, None]) / dx) * (1 - np.abs(py - yc[None, :, None]) / dy)
+    f2c = (w * ph2).sum(-1) / w.sum(-1)
+    num, den = np.zeros((n + 1, n + 1)), np.zeros((n + 1, n + 1))
+    for a in (0, 1):
+        for b in (0, 1):
+            wv = (1 - np.abs(px - xv[a:n + a, None, None]) / dx) * (1 - np.abs(py - yv[None, b:n + b, None]) / dy)
+            num[a:n + a, b:n + b] += (wv * ph2).sum(-1)
+            den[a:n + a, b:n + b] += wv.sum(-1)
+    oh = lambda f: np.asfortranarray(np.stack([1 - f, f], axis=-1))
+    return dict(center=oh(f2c), vertex=oh(num / den))
+
+
+def test_sinking_block_particle_equivalent_phase_ratios(oracle):
+    """What the 5.6 % between the restatement (5.11e-10, grid-sampled ratios) and the reference's golden (4.84e-10, JustPIC particles,
+    unseeded RNG, atol 1e-6) can and cannot be: (a) NOT the PT tolerance — the maximum vertex speed is converged to 1e-9 relative after
+    2000 of the 3000 iterations; (b) NOT the sampling noise of 20 random particles per cell — particle-equivalent ratios (two seeds here,
+    six in the analysis of DESIGN.md) move the result by ≈ ±1 %: 4.97e-10 … 5.12e-10; the remaining ≈ 4 % is systematic and sits in the
+    unpinned JustPIC particle / phase-ratio kernels (or GeoParams' phase-mixed viscosity), which only a Julia run can pin."""
+    base = None
+    for seed in (0, 5):
+        s = setups.sinking_block2d(32)
+        s.ratios = particle_equivalent_ratios(s, seed)
+        rho = s.ratios["center"][..., 0] * 3.2e3 + s.ratios["center"][..., 1] * 3.3e3
+        s.fields["rhogy"] = np.asfortranarray(rho * 9.81)
+        s.fields["P"] = np.asfortranarray(s.fields["rhogy"] * np.abs(s.grid.xci[1])[None, :])
+        d, out = run_sinking_block(oracle, s)
+        assert out["status"] == 0 and out["err_evo1"][-1] < 1.0e-5
+        v = vertex_speed(d["Vx"], d["Vy"]).max()
+        assert abs(v / 5.1146e-10 - 1) < 0.04, (seed, v)          # within particle noise of the grid-sampled restatement
+        assert abs(v / 4.841885609356093e-10 - 1) < 0.07, (seed, v)   # and within 7 % of the reference's golden
+        base = v if base is None else base

@@ -225,3 +225,33 @@ def test_unknown_args_key_fails_loudly():
         with pytest.raises(NotImplementedError, match="refusing to ignore"):
             vc_slots(st, (st.P, st.P, st.P), {bad: st.P})
     assert "dTargs" not in vc_slots(st, (st.P, st.P, st.P), dict(dt=0.1))
+
+
+def in_plane_invariant(oracle, txx, tzz, txz, j=1):
+    """tensor_invariant!(stokes.τ) of the 2D test on the (x, z) plane y = j of the 3D fields"""
+    return oracle.tensor_invariant2d(np.asfortranarray(txx[:, j, :]), np.asfortranarray(tzz[:, j, :]), np.asfortranarray(txz[:, j, :]))
+
+
+def test_extruded_shearband_pins_3d_vc_on_the_2d_reference_golden(oracle):
+    """EXTERNAL PIN of the 3D-VC restatement: the reference's 2D shear-band test (test/test_shearband2D.jl, Drucker-Prager + elasticity +
+    two phases) extruded along y and solved with the 3D multiphase solver must land on the 2D golden values
+    (test/test_shearband2D.jl:197-201: extrema(τII) ≈ (1.5128689768248313, 1.6415759440014273) atol 1e-3, maximum(τxx) ≈ 1.6376258215356436
+    atol 1e-4) — plane strain differs from the 2D kernels only by the out-of-plane deviatoric stress (|τyy| ≤ 0.02 here)."""
+    s = setups.shearband3d_extruded(32, 4)
+    d = oracle.alloc_stokes(s.ni, s.fields)
+    vc = oracle.vc_inputs(R.lower_stokes(s.rheology), R.gravity_of(s.rheology), s.ratios)
+    opts = oracle.make_opts(s.pt_stokes, s.grid._di.center, s.dt, bc_flags(s.flow_bcs), s.ni, iterMax=s.kwargs["iterMax"], nout=s.kwargs["nout"])
+    fs = oracle.make_fields(d, s.ni)
+    oracle.lib().orc_viscosity3d(C.byref(fs), C.byref(opts), C.byref(vc), C.c_double(1.0))
+    oracle.lib().orc_flow_bcs3(C.byref(fs), C.byref(opts), 0)
+    txx_max = []
+    for _ in range(s.nt):
+        out = oracle.solve3d_VC(d, s.ni, opts, vc)
+        assert out["status"] == 0 and out["err_evo1"][-1] < 1.0e-6
+        txx_max.append(d["txx"].max())
+    tII = in_plane_invariant(oracle, d["txx"], d["tzz"], d["txz"])
+    assert abs(tII.min() - 1.5128689768248313) < 1.0e-3, tII.min()
+    assert abs(tII.max() - 1.6415759440014273) < 1.0e-3, tII.max()
+    assert abs(txx_max[-1] - 1.6376258215356436) < 1.0e-4, txx_max[-1]
+    assert d["EII_pl"].max() > 0 and d["lam"].max() > 0
+    assert np.abs(d["txx"] - d["txx"][:, :1, :]).max() == 0.0 and np.abs(d["tyy"]).max() < 0.03      # y-invariant; small out-of-plane stress
