@@ -197,6 +197,17 @@ static int comm_ensure_stage(jr_context *ctx, jr_comm *cm, size_t doubles)
     return JR_OK;
 }
 
+int jr_comm_share(jr_context *ctx, void *mine, void **out)
+{
+    jr_comm *cm = ctx->comm;
+    JR_REQUIRE(cm && cm->nranks > 1, JR_ERR_ARG, "no multi-rank communicator attached to this context");
+    std::vector<void *> peers;
+    int st = comm_share(cm, mine, peers);
+    if (st) return st;
+    for (int r = 0; r < cm->nranks; r++) out[r] = peers[r];
+    return JR_OK;
+}
+
 int jr_comm_reserve_stage(jr_context *ctx, size_t doubles)
 {
     jr_comm *cm = ctx->comm;

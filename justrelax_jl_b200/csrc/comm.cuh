@@ -13,6 +13,8 @@
 // one per rank, in device memory, CUDA-IPC mapped by every other rank
 struct jr_comm_sig {
     unsigned long long flags[JR_COMM_MAX_RANKS];                // flags[r] = last epoch rank r has reached (written by r)
+    unsigned long long push_flags[JR_COMM_MAX_RANKS];           // push protocol of the fused 3D-VA kernel: push_flags[r] = r has finished
+                                                                // (kernel + BC pushes) every iteration before its launch number …
     double red[2][JR_COMM_MAX_RANKS][JR_COMM_RED_SLOTS];        // all-reduce slots, double-buffered
 };
 
@@ -33,7 +35,7 @@ struct jr_comm {
     jr_comm_sig *sig_mine = nullptr;
     void *stage_mine[2] = {nullptr, nullptr};
     size_t stage_cap = 0;                         // doubles per staging buffer
-    unsigned long long epoch = 0, red_count = 0;
+    unsigned long long epoch = 0, red_count = 0, push_epoch = 0;
     size_t halo_bytes = 0;
     std::map<std::string, void *> ipc_open;       // opened peer handles (handle bytes + rank → mapped pointer)
     std::vector<void *> retired;                  // outgrown staging buffers (freed at destroy)
@@ -54,6 +56,9 @@ int jr_comm_halo(jr_context *ctx, const jr_harr *arrs, int narr);
 size_t jr_comm_halo_bytes(const jr_comm *cm, const jr_harr *arrs, int narr);
 // in-place all-reduce of n ≤ 16 device doubles (op 0 sum, 1 max, 2 min); asynchronous on ctx->stream
 int jr_comm_allreduce_dev(jr_context *ctx, double *d_vals, int n, int op);
+// CUDA-IPC share `mine` (a cudaMalloc base pointer) with every rank: out[r] = rank r's buffer mapped here (out[rank] = mine).
+// Collective (one host all-gather); mappings are cached per handle.
+int jr_comm_share(jr_context *ctx, void *mine, void **out);
 // make sure every rank's staging buffers hold at least `doubles` elements (collective: all ranks call it with the same size)
 int jr_comm_reserve_stage(jr_context *ctx, size_t doubles);
 

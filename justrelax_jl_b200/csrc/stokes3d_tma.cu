@@ -49,6 +49,36 @@ template <bool FIN, bool RHOG> struct SlotMap {
     static constexpr int ett = FIN ? G + 10 : T_NEXT, fx = ett + 1, fy = ett + 2, fz = ett + 3, NARR = ett + (RHOG ? 4 : 1);
 };
 
+// push protocol (see comm.cuh: push_flags).  Offsets index the 27 neighbour directions [(dz+1)·9 + (dy+1)·3 + dx+1].
+struct PushArgs {
+    double *peer_out[27];              // neighbours' out-set base (the set with the same parity as ours); nullptr = no such neighbour
+    jr_comm_sig *sig_peer[27];         // their signal pages (nullptr = none) and ours
+    jr_comm_sig *sig_mine;
+    int nbr_rank[27];
+    int rank;
+    int has_lo[3], has_hi[3];
+    long delta[3];                     // (n_d − 2) · stride_d in elements: own element + Σ −f_d·delta_d = its ghost image on the neighbour
+    unsigned long long epoch;          // launch number of this iteration (monotonic over the communicator's life)
+};
+
+// store v, produced at out-set offset `off` of a V component whose normal dimension is `nrm`, into every neighbour whose ghost planes
+// hold it: g = (gi, gj, k) cell / face indices; send planes are index 2 on the low side and n − 2 (normal) / n − 3 (tangential) on
+// the high side — IGG's planes ol and size − ol + 1 of the staggered array (overlap 2)
+__device__ __forceinline__ void jr_push_v(const PushArgs &pu, int nrm, int gi, int gj, int k, int nx, int ny, int nz, size_t off, double v)
+{
+    const int f0 = (gi == 2 && pu.has_lo[0]) ? -1 : ((gi == (nrm == 0 ? nx - 2 : nx - 3) && pu.has_hi[0]) ? 1 : 0);
+    const int f1 = (gj == 2 && pu.has_lo[1]) ? -1 : ((gj == (nrm == 1 ? ny - 2 : ny - 3) && pu.has_hi[1]) ? 1 : 0);
+    const int f2 = (k == 2 && pu.has_lo[2]) ? -1 : ((k == (nrm == 2 ? nz - 2 : nz - 3) && pu.has_hi[2]) ? 1 : 0);
+    if (!(f0 | f1 | f2)) return;
+#pragma unroll
+    for (int m = 1; m < 8; m++) {
+        const int d0 = (m & 1) ? f0 : 0, d1 = (m & 2) ? f1 : 0, d2 = (m & 4) ? f2 : 0;
+        if (((m & 1) && !f0) || ((m & 2) && !f1) || ((m & 4) && !f2)) continue;
+        double *base = pu.peer_out[(d2 + 1) * 9 + (d1 + 1) * 3 + d0 + 1];
+        if (base) base[(long)off - d0 * pu.delta[0] - d1 * pu.delta[1] - d2 * pu.delta[2]] = v;
+    }
+}
+
 struct alignas(64) VaArgs {
     CUtensorMap mS5, mC1, mC4, mD1, mD2, mD7;  // in-state set (5-array boxes), const set, finite-dt set
     double *out;                               // out-state set base
@@ -73,6 +103,10 @@ struct alignas(64) VaArgs {
     int niter;                         // iterations of this launch
     int bc_nsn[6];                     // x-lo, x-hi, y-lo, y-hi, z-lo, z-hi: boundary-normal face is zeroed (no_slip!)
     double bc_sg[6];                   // same sides: tangential ghost = bc_sg · interior (+1 free slip, −1 no slip)
+    // ---- PUSH (multi-GPU): the halo exchange of update_halo!(Vx, Vy, Vz) (Stokes3D.jl:120) inside the iteration.  Every V element
+    // on one of this rank's send planes is stored a second (… eighth) time straight into the ghost planes of the neighbours'
+    // out-sets over the CUDA-IPC mapping, as it is produced — the transfer rides on NVLink under the z-march.
+    PushArgs push;
 };
 
 #define TXW 30  // owned columns per tile
@@ -99,7 +133,7 @@ __device__ __forceinline__ bool jr_elect_one()
 //   MULTI: the launch runs a.niter iterations (ping-pong S_in ↔ S_out, a grid-wide barrier with generic→async proxy
 //       fences between them) and applies flow_bcs! itself: every thread that holds the source of a ghost / boundary
 //       value (no_slip! → free_slip! as complete sweeps, same gather as k_bc_box3) also stores its images.
-template <int BY, bool FINITE_DT, bool DIAG, int NST, bool RHOG, bool MULTI>
+template <int BY, bool FINITE_DT, bool DIAG, int NST, bool RHOG, bool MULTI, bool PUSH = false>
 __global__ void __launch_bounds__(32 * BY, (BY <= 8 ? (FINITE_DT ? 2 : JR_VA_MINB8) : BY <= 10 ? 2 : 1)) k_va_tma(const __grid_constant__ VaArgs a)
 {
     using M = SlotMap<FINITE_DT, RHOG>;
@@ -125,6 +159,27 @@ __global__ void __launch_bounds__(32 * BY, (BY <= 8 ? (FINITE_DT ? 2 : JR_VA_MIN
         jr_fence_mbar_init();
     }
     __syncthreads();
+    if (PUSH) {
+        // everything this rank launched before this kernel (previous iteration + its BC kernel, or the layout entry) is complete:
+        // tell the neighbours, then wait until they say the same — their pushes into our in-set are then visible, and they no longer
+        // read the set our pushes of THIS iteration go to
+        if (tid < 27) {
+            jr_comm_sig *pe = a.push.sig_peer[tid];
+            if (pe) {
+                if (cta == 0) {
+                    __threadfence_system();
+                    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(&pe->push_flags[a.push.rank]), "l"(a.push.epoch) : "memory");
+                }
+                const unsigned long long *mine = &a.push.sig_mine->push_flags[a.push.nbr_rank[tid]];
+                unsigned long long v;
+                do {
+                    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
+                } while (v < a.push.epoch);
+            }
+        }
+        __syncthreads();
+        asm volatile("fence.proxy.async.global;" ::: "memory");
+    }
 
     // ---- producer state (CTA-uniform): the next z-step to load ----
     int p_g = 0, p_r = 0, p_l = 0, p_slot = 0, p_x0 = 0, p_y0 = 0, p_kb = 0;
@@ -406,6 +461,7 @@ __global__ void __launch_bounds__(32 * BY, (BY <= 8 ? (FINITE_DT ? 2 : JR_VA_MIN
                                          0.5 * (RHOG ? (p[M::fx * TILE - 1] + p[M::fx * TILE]) : (a.fxc + a.fxc));
                         const double vn = vx0 + jr_div_nr(R * a.eta_dtau, 0.5 * (p[M::ett * TILE - 1] + c_ett));
                         jr_st_hint(&po[S_Vx * pxy], vn, pst);
+                        if (PUSH) jr_push_v(a.push, 0, gi, gj, k, nx, ny, nz, (size_t)(&po[S_Vx * pxy] - outset), vn);
                         if (DIAG) {
                             a.Rx[((size_t)k * ny + gj) * (nx - 1) + (gi - 1)] = R;
                             const size_t c = ((size_t)(k + 1) * (ny + 2) + gj + 1) * (nx + 1) + gi;
@@ -426,6 +482,7 @@ __global__ void __launch_bounds__(32 * BY, (BY <= 8 ? (FINITE_DT ? 2 : JR_VA_MIN
                                          0.5 * (RHOG ? (p[M::fy * TILE - 32] + p[M::fy * TILE]) : (a.fyc + a.fyc));
                         const double vn = vy0 + jr_div_nr(R * a.eta_dtau, 0.5 * (p[M::ett * TILE - 32] + c_ett));
                         jr_st_hint(&po[S_Vy * pxy], vn, pst);
+                        if (PUSH) jr_push_v(a.push, 1, gi, gj, k, nx, ny, nz, (size_t)(&po[S_Vy * pxy] - outset), vn);
                         if (DIAG) {
                             a.Ry[((size_t)k * (ny - 1) + (gj - 1)) * nx + gi] = R;
                             const size_t c = ((size_t)(k + 1) * (ny + 1) + gj) * (nx + 2) + gi + 1;
@@ -443,6 +500,7 @@ __global__ void __launch_bounds__(32 * BY, (BY <= 8 ? (FINITE_DT ? 2 : JR_VA_MIN
                         const double R = sRz + (-tzz_p + tzz_n) * _dz - (-P_p + P_n) * _dz - 0.5 * (fz_p + c_fz);
                         const double vn = vz0 + jr_div_nr(R * a.eta_dtau, 0.5 * (ett_p + c_ett));
                         jr_st_hint(&po[S_Vz * pxy], vn, pst);
+                        if (PUSH) jr_push_v(a.push, 2, gi, gj, k, nx, ny, nz, (size_t)(&po[S_Vz * pxy] - outset), vn);
                         if (DIAG) {
                             a.Rz[((size_t)(k - 1) * ny + gj) * nx + gi] = R;
                             const size_t c = ((size_t)k * (ny + 2) + gj + 1) * (nx + 2) + gi + 1;
@@ -570,13 +628,34 @@ struct BcArrB {
     int n[3];    // dense extents of this velocity component
     int o[3];    // dense → box offset
     int normal;  // normal dimension of this component
+    long set_off;  // out.p − base of the out-set (push exchange: offsets are relative to the set, which every rank lays out alike)
 };
 struct BcArgsB {
     BcArrB A[3];
     int lo_fs[3], hi_fs[3], lo_ns[3], hi_ns[3];  // per dimension and side: free-slip / no-slip active
     int diag;
     double dt;
+    int do_push, ncell[3];                       // multi-GPU push exchange: elements on a send plane also go to the neighbours' ghosts,
+    PushArgs push;                               // elements the neighbours push to us (halo planes) are left alone
 };
+
+// signal + wait of the push protocol outside the iteration kernel (solve exit: everybody's last pushes have landed)
+__global__ void k_push_sync(const __grid_constant__ PushArgs pu)
+{
+    const int tid = threadIdx.x;
+    if (tid < 27) {
+        jr_comm_sig *pe = pu.sig_peer[tid];
+        if (pe) {
+            __threadfence_system();
+            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(&pe->push_flags[pu.rank]), "l"(pu.epoch) : "memory");
+            const unsigned long long *mine = &pu.sig_mine->push_flags[pu.nbr_rank[tid]];
+            unsigned long long v;
+            do {
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
+            } while (v < pu.epoch);
+        }
+    }
+}
 
 #define BC_ROWS 4   // rows per thread: the four gathers are independent and issued back to back (the kernel is pure latency)
 __global__ void __launch_bounds__(256) k_bc_box3(const __grid_constant__ BcArgsB b)
@@ -590,12 +669,13 @@ __global__ void __launch_bounds__(256) k_bc_box3(const __grid_constant__ BcArgsB
     if (p >= A.n[u]) return;
     size_t ic[BC_ROWS], dc[BC_ROWS];
     double val[BC_ROWS], vin[BC_ROWS];
-    bool ok[BC_ROWS];
+    bool ok[BC_ROWS], rcv[BC_ROWS];
+    int pf[BC_ROWS][3];
 #pragma unroll
     for (int r = 0; r < BC_ROWS; r++) {
         const int q = (blockIdx.y * BC_ROWS + r) * blockDim.y + threadIdx.y;
         ok[r] = q < A.n[v];
-        val[r] = 0.0; vin[r] = 0.0; ic[r] = 0; dc[r] = 0;
+        val[r] = 0.0; vin[r] = 0.0; ic[r] = 0; dc[r] = 0; rcv[r] = false; pf[r][0] = pf[r][1] = pf[r][2] = 0;
         if (!ok[r]) continue;
         int c[3];
         c[d] = hi ? A.n[d] - 1 : 0;
@@ -618,6 +698,19 @@ __global__ void __launch_bounds__(256) k_bc_box3(const __grid_constant__ BcArgsB
                 if (!fsl) sign = -sign;
             }
         }
+        if (b.do_push) {
+            // halo planes towards a neighbour are written by that neighbour's pushes: leave them alone (box set), but keep the
+            // dense diagnostics below
+            bool recv = false;
+#pragma unroll
+            for (int e = 0; e < 3; e++) recv = recv || (c[e] == 0 && b.push.has_lo[e]) || (c[e] == A.n[e] - 1 && b.push.has_hi[e]);
+            rcv[r] = recv;
+#pragma unroll
+            for (int e = 0; e < 3; e++) {
+                const int ol = 2 + A.n[e] - b.ncell[e];
+                pf[r][e] = (c[e] == ol - 1 && b.push.has_lo[e]) ? -1 : ((c[e] == A.n[e] - ol && b.push.has_hi[e]) ? 1 : 0);
+            }
+        }
         ic[r] = box_idx(A.out, c[0] + A.o[0], c[1] + A.o[1], c[2] + A.o[2]);
         const size_t is = box_idx(A.out, s[0] + A.o[0], s[1] + A.o[1], s[2] + A.o[2]);
         bool computed = true;
@@ -632,7 +725,19 @@ __global__ void __launch_bounds__(256) k_bc_box3(const __grid_constant__ BcArgsB
 #pragma unroll
     for (int r = 0; r < BC_ROWS; r++) {
         if (!ok[r]) continue;
-        A.out.p[ic[r]] = val[r];
+        if (!rcv[r]) {
+            A.out.p[ic[r]] = val[r];
+            if (b.do_push && (pf[r][0] | pf[r][1] | pf[r][2])) {
+                const long off = A.set_off + (long)ic[r];
+#pragma unroll
+                for (int m = 1; m < 8; m++) {
+                    if (((m & 1) && !pf[r][0]) || ((m & 2) && !pf[r][1]) || ((m & 4) && !pf[r][2])) continue;
+                    const int d0 = (m & 1) ? pf[r][0] : 0, d1 = (m & 2) ? pf[r][1] : 0, d2 = (m & 4) ? pf[r][2] : 0;
+                    double *base = b.push.peer_out[(d2 + 1) * 9 + (d1 + 1) * 3 + d0 + 1];
+                    if (base) base[off - d0 * b.push.delta[0] - d1 * b.push.delta[1] - d2 * b.push.delta[2]] = val[r];
+                }
+            }
+        }
         if (b.diag) {
             A.U[dc[r]] = vin[r] * b.dt;
             A.Vd[dc[r]] = val[r];
@@ -747,6 +852,10 @@ struct VaPlan {
     void *zeroed[4] = {nullptr, nullptr, nullptr, nullptr};
     int zdims[4] = {0, 0, 0, 0};  // nx, ny, nz, finite_dt of the zeroed layout
     bool last_diag = false;       // the last iteration was an observable one: the user's dense arrays are current
+    // multi-GPU push exchange (see PushArgs): the state sets of every rank are CUDA-IPC mapped here
+    bool push = false;
+    void *shared_ptr[2] = {nullptr, nullptr};   // the S pointers the mappings below belong to
+    std::vector<void *> peerS[2];
 };
 static std::map<jr_context *, VaPlan> g_plans;
 
@@ -871,6 +980,21 @@ int jr_stokes3d_VA_fused_begin(jr_context *ctx, const jr_fields *s, const jr_sto
     if (const char *e = getenv("JRB200_VA_POL_LD")) P.pol_ld = atoi(e);
     if (const char *e = getenv("JRB200_VA_POL_ST")) P.pol_st = atoi(e);
     if (const char *e = getenv("JRB200_VA_L2PROMO")) P.l2promo = atoi(e);
+    // multi-GPU: in-iteration push exchange (opt-in, JRB200_VA_PUSH=1; every dimension must be large enough for the send planes —
+    // index 2 / n − 3 — to be interior).  Bit-exact (tests/mgpu_worker.py) but measured SLOWER than pack + pull on 2 B200s
+    // (0.688 vs 0.582 ms per iteration at 255^3, profiles/r02_push_exchange.md): the x-face planes are columns of the box layout, i.e.
+    // ≈ 2·10^5 scattered 8-byte NVLink stores per face and iteration issued from the CTAs that pace the lock-stepped grid.
+    P.push = false;
+    if (ctx->comm && ctx->comm->nranks > 1 && nx >= 8 && ny >= 8 && nz >= 8 && getenv("JRB200_VA_PUSH") && atoi(getenv("JRB200_VA_PUSH")) == 1) {
+        for (int q = 0; q < 2; q++) {
+            if (P.shared_ptr[q] != (void *)P.S[q] || (int)P.peerS[q].size() != ctx->comm->nranks) {
+                P.peerS[q].assign(ctx->comm->nranks, nullptr);
+                if ((st = jr_comm_share(ctx, P.S[q], P.peerS[q].data()))) return st;
+                P.shared_ptr[q] = (void *)P.S[q];
+            }
+        }
+        P.push = true;
+    }
     if ((st = set_tma_map(&P.mS5[0], P.S[0], P, S_N, 5))) return st;
     if ((st = set_tma_map(&P.mS5[1], P.S[1], P, S_N, 5))) return st;
     if ((st = set_tma_map(&P.mC1, P.C, P, C_N, 1))) return st;
@@ -920,18 +1044,18 @@ int jr_stokes3d_VA_fused_begin(jr_context *ctx, const jr_fields *s, const jr_sto
     return JR_OK;
 }
 
-template <int BY, bool FIN, bool DG, int NSTv, bool RHOG, bool MULTI = false>
+template <int BY, bool FIN, bool DG, int NSTv, bool RHOG, bool MULTI = false, bool PUSH = false>
 static int launch_one(jr_context *ctx, VaPlan &P, VaArgs &a)
 {
     constexpr int TY = BY - 2;
     constexpr int smem = NSTv * SlotMap<FIN, RHOG>::NARR * 32 * BY * 8;
     static int cta_per_sm = 0;
     if (!cta_per_sm) {
-        JR_CUDA(cudaFuncSetAttribute(k_va_tma<BY, FIN, DG, NSTv, RHOG, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        JR_CUDA(cudaFuncSetAttribute(k_va_tma<BY, FIN, DG, NSTv, RHOG, MULTI>, cudaFuncAttributePreferredSharedMemoryCarveout,
+        JR_CUDA(cudaFuncSetAttribute(k_va_tma<BY, FIN, DG, NSTv, RHOG, MULTI, PUSH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        JR_CUDA(cudaFuncSetAttribute(k_va_tma<BY, FIN, DG, NSTv, RHOG, MULTI, PUSH>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                      cudaSharedmemCarveoutMaxShared));
         int nb = 0;
-        JR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_va_tma<BY, FIN, DG, NSTv, RHOG, MULTI>, 32 * BY, smem));
+        JR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_va_tma<BY, FIN, DG, NSTv, RHOG, MULTI, PUSH>, 32 * BY, smem));
         JR_REQUIRE(nb >= 1, JR_ERR_CUDA, "k_va_tma<%d> does not fit on an SM (%d B shared memory)", BY, smem);
         cta_per_sm = nb;
         if (getenv("JRB200_VERBOSE"))
@@ -955,25 +1079,26 @@ static int launch_one(jr_context *ctx, VaPlan &P, VaArgs &a)
     P.gbar_base += (unsigned long long)(nit - 1) * G;
     void *args[1] = {(void *)&a};
     // cooperative launch: the soft lock-step spins on other CTAs, so all G CTAs must be resident
-    JR_CUDA(cudaLaunchCooperativeKernel((const void *)k_va_tma<BY, FIN, DG, NSTv, RHOG, MULTI>, dim3(G, 1, 1), dim3(32, BY, 1), args, smem,
+    JR_CUDA(cudaLaunchCooperativeKernel((const void *)k_va_tma<BY, FIN, DG, NSTv, RHOG, MULTI, PUSH>, dim3(G, 1, 1), dim3(32, BY, 1), args, smem,
                                         ctx->stream));
     return JR_OK;
 }
 
-template <bool RHOG>
+template <bool RHOG, bool PUSH>
 static int launch_va_t(jr_context *ctx, VaPlan &P, VaArgs &a, int diag)
 {
     if (P.finite_dt)
-        return diag ? launch_one<8, true, true, 2, RHOG>(ctx, P, a) : launch_one<8, true, false, 2, RHOG>(ctx, P, a);
+        return diag ? launch_one<8, true, true, 2, RHOG, false, PUSH>(ctx, P, a) : launch_one<8, true, false, 2, RHOG, false, PUSH>(ctx, P, a);
     switch (P.BY) {
-    case 8: return diag ? launch_one<8, false, true, 3, RHOG>(ctx, P, a) : launch_one<8, false, false, 3, RHOG>(ctx, P, a);
-    case 10: return diag ? launch_one<10, false, true, 3, RHOG>(ctx, P, a) : launch_one<10, false, false, 3, RHOG>(ctx, P, a);
-    default: return diag ? launch_one<16, false, true, 3, RHOG>(ctx, P, a) : launch_one<16, false, false, 3, RHOG>(ctx, P, a);
+    case 8: return diag ? launch_one<8, false, true, 3, RHOG, false, PUSH>(ctx, P, a) : launch_one<8, false, false, 3, RHOG, false, PUSH>(ctx, P, a);
+    case 10: return diag ? launch_one<10, false, true, 3, RHOG, false, PUSH>(ctx, P, a) : launch_one<10, false, false, 3, RHOG, false, PUSH>(ctx, P, a);
+    default: return diag ? launch_one<16, false, true, 3, RHOG, false, PUSH>(ctx, P, a) : launch_one<16, false, false, 3, RHOG, false, PUSH>(ctx, P, a);
     }
 }
 static int launch_va(jr_context *ctx, VaPlan &P, VaArgs &a, int diag)
 {
-    return P.rhog_const ? launch_va_t<false>(ctx, P, a, diag) : launch_va_t<true>(ctx, P, a, diag);
+    if (P.push) return P.rhog_const ? launch_va_t<false, true>(ctx, P, a, diag) : launch_va_t<true, true>(ctx, P, a, diag);
+    return P.rhog_const ? launch_va_t<false, false>(ctx, P, a, diag) : launch_va_t<true, false>(ctx, P, a, diag);
 }
 // several iterations per launch, boundary conditions inside the kernel (never with diagnostics)
 template <bool RHOG>
@@ -1016,6 +1141,28 @@ static void fill_args(VaArgs &a, const VaPlan &P, const jr_fields *s, const jr_s
         a.bc_nsn[q] = nsl[q] ? 1 : 0;
         a.bc_sg[q] = fsl[q] ? 1.0 : -1.0;
     }
+    memset(&a.push, 0, sizeof(a.push));
+}
+
+// neighbour tables of the push exchange for the iteration that writes set `outq`
+static void fill_push(PushArgs &pu, const jr_context *ctx, const VaPlan &P, int outq)
+{
+    const jr_comm *cm = ctx->comm;
+    memset(&pu, 0, sizeof(pu));
+    pu.rank = cm->rank;
+    pu.sig_mine = cm->dev.sig[cm->rank];
+    for (int t = 0; t < 27; t++) {
+        const int nb = cm->dev.nbr[t];
+        pu.nbr_rank[t] = nb;
+        if (nb >= 0 && nb != cm->rank) {
+            pu.peer_out[t] = (double *)P.peerS[outq][nb];
+            pu.sig_peer[t] = cm->dev.sig[nb];
+        }
+    }
+    for (int d = 0; d < 3; d++) { pu.has_lo[d] = cm->coords[d] > 0; pu.has_hi[d] = cm->coords[d] < cm->dims[d] - 1; }
+    pu.delta[0] = (long)(P.nx - 2);
+    pu.delta[1] = (long)(P.ny - 2) * P.PX;
+    pu.delta[2] = (long)(P.nz - 2) * S_N * (long)P.pxy;
 }
 
 // can the kernel apply flow_bcs! itself?  every side needs a free-slip or no-slip flag (tangential ghosts are then
@@ -1074,28 +1221,36 @@ int jr_stokes3d_VA_fused_iter(jr_context *ctx, const jr_fields *s, const jr_stok
 
     VaArgs a;
     fill_args(a, P, s, o, parity);
+    if (P.push) {
+        fill_push(a.push, ctx, P, parity ? 0 : 1);
+        a.push.epoch = ++ctx->comm->push_epoch;
+    }
     int st = launch_va(ctx, P, a, diag);
     if (st) return st;
     P.last_diag = diag != 0;
 
     BcArgsB b;
-    b.A[0] = BcArrB{box_arr(in, S_Vx, S_N, P), box_arr(out, S_Vx, S_N, P), F(Ux), F(Vx), {nx + 1, ny + 2, nz + 2}, {1, 0, 0}, 0};
-    b.A[1] = BcArrB{box_arr(in, S_Vy, S_N, P), box_arr(out, S_Vy, S_N, P), F(Uy), F(Vy), {nx + 2, ny + 1, nz + 2}, {0, 1, 0}, 1};
-    b.A[2] = BcArrB{box_arr(in, S_Vz, S_N, P), box_arr(out, S_Vz, S_N, P), F(Uz), F(Vz), {nx + 2, ny + 2, nz + 1}, {0, 0, 1}, 2};
+    b.A[0] = BcArrB{box_arr(in, S_Vx, S_N, P), box_arr(out, S_Vx, S_N, P), F(Ux), F(Vx), {nx + 1, ny + 2, nz + 2}, {1, 0, 0}, 0, (long)S_Vx * (long)P.pxy};
+    b.A[1] = BcArrB{box_arr(in, S_Vy, S_N, P), box_arr(out, S_Vy, S_N, P), F(Uy), F(Vy), {nx + 2, ny + 1, nz + 2}, {0, 1, 0}, 1, (long)S_Vy * (long)P.pxy};
+    b.A[2] = BcArrB{box_arr(in, S_Vz, S_N, P), box_arr(out, S_Vz, S_N, P), F(Uz), F(Vz), {nx + 2, ny + 2, nz + 1}, {0, 0, 1}, 2, (long)S_Vz * (long)P.pxy};
     // flags: left,right,front,back,top,bot.  no_slip: bot → z lo, top → z hi; free_slip (Q2): top → z lo, bot → z hi
     const int32_t *fs = o->free_slip, *ns = o->no_slip;
     b.lo_fs[0] = fs[0]; b.hi_fs[0] = fs[1]; b.lo_ns[0] = ns[0]; b.hi_ns[0] = ns[1];
     b.lo_fs[1] = fs[2]; b.hi_fs[1] = fs[3]; b.lo_ns[1] = ns[2]; b.hi_ns[1] = ns[3];
     b.lo_fs[2] = fs[4]; b.hi_fs[2] = fs[5]; b.lo_ns[2] = ns[5]; b.hi_ns[2] = ns[4];
     b.diag = diag; b.dt = o->dt;
+    b.do_push = P.push ? 1 : 0;
+    if (P.push) b.push = a.push;
+    else memset(&b.push, 0, sizeof(b.push));
+    b.ncell[0] = nx; b.ncell[1] = ny; b.ncell[2] = nz;
     int m = nx > ny ? nx : ny;
     m = (m > nz ? m : nz) + 2;
     dim3 bgrid((m + 31) / 32, (m + 8 * BC_ROWS - 1) / (8 * BC_ROWS), 18), bblock(32, 8, 1);
     k_bc_box3<<<bgrid, bblock, 0, ctx->stream>>>(b);
     ctx->launches += 2;
     JR_CHECK_LAUNCH();
-    // update_halo!(Vx, Vy, Vz)  Stokes3D.jl:120 — straight on the box set the next iteration reads
-    if (ctx->comm) {
+    // update_halo!(Vx, Vy, Vz)  Stokes3D.jl:120 — pushed by the two kernels above (P.push), else pack + pull on the box set
+    if (ctx->comm && !P.push) {
         jr_harr H[3];
         for (int q = 0; q < 3; q++) {
             const BcArrB &A = b.A[q];
@@ -1120,6 +1275,15 @@ int jr_stokes3d_VA_fused_finish(jr_context *ctx, const jr_fields *s, int64_t nit
     const int nx = P.nx, ny = P.ny, nz = P.nz;
     double *cur = P.S[niter & 1];
     if (P.last_diag && !ctx->comm && niter > 0) return JR_OK;
+    if (P.push && niter > 0) {
+        // the neighbours' pushes of the last iteration must have landed before the halo planes are read back
+        PushArgs pu;
+        fill_push(pu, ctx, P, 0);
+        pu.epoch = ++ctx->comm->push_epoch;
+        k_push_sync<<<1, 32, 0, ctx->stream>>>(pu);
+        ctx->launches++;
+        JR_CHECK_LAUNCH();
+    }
     const bool v_only = P.last_diag && niter > 0;
     PackArgs pa;
     pa.njobs = 0;

@@ -57,7 +57,10 @@ def main():
 
     # ---- 3. 3D-VA, fixed number of iterations -----------------------------------------------------------------
     names = ["Vx", "Vy", "Vz", "P", "txx", "tyy", "tzz", "tyz", "txz", "txy", "Rx", "Ry", "Rz", "RP", "etatau"]
-    for dt, finite_K, unfused in [(np.inf, False, False), (0.7, True, False), (0.7, True, True)]:
+    # (push: the in-iteration push exchange of the fused kernel, JRB200_VA_PUSH=1, besides the default pack + pull)
+    for dt, finite_K, unfused, push in [(np.inf, False, False, "0"), (0.7, True, False, "0"), (0.7, True, True, "0"), (np.inf, False, False, "1"),
+                                        (0.7, True, False, "1")]:
+        os.environ["JRB200_VA_PUSH"] = push
         blocks = []
         for r in range(world):
             s = setups.random_stokes3d(ni, seed=500 + r, dt=dt, finite_K=finite_K)
@@ -76,7 +79,8 @@ def main():
         jst.iterate_(st, s.pt_stokes, s.grid, bcs, (extra["rhogx"], extra["rhogy"], extra["rhogz"]), extra["K"], extra["G"], dt, niter, igg)
         jst.set_flags(0)
         worst = max(max_rel_diff(to_host(st.slots()[nm]), blocks[rank][nm]) for nm in names)
-        assert worst <= 1e-12, ("3D-VA iterate", dt, unfused, rank, worst)
+        assert worst <= 1e-12, ("3D-VA iterate", dt, unfused, push, rank, worst)
+    os.environ["JRB200_VA_PUSH"] = "0"
 
     # ---- 4. SolVi3D solve across ranks: iteration count + norms ----------------------------------------------
     # (divergence-free pure shear + inclusion placed by global coordinates: the loop ends on its tolerance, see setups.solvi3d)
