@@ -127,6 +127,9 @@ struct StokesPhase
     beta::Cdouble
     T0::Cdouble
     P0::Cdouble
+    soft_C_kind::Int32               # 0 none, 1 LinearSoftening, 2 NonLinearSoftening (cohesion, 2D solves)
+    _pad::Int32
+    soft_C::NTuple{6, Cdouble}
 end
 
 struct VcInputs
@@ -220,7 +223,7 @@ end
 function selfcheck()
     @assert sizeof(StokesOpts) == 5 * 8 + 3 * 8 + 8 + 16 + 12 + 3 * 24 + 4 + 4 * 8 + 8 + 16
     @assert sizeof(StokesResult) == 11 * 8
-    @assert sizeof(StokesPhase) == 14 * 8                  # 13 doubles + two int32 sharing one 8-byte slot
+    @assert sizeof(StokesPhase) == 21 * 8                  # 13 + 6 doubles + 2 × two int32 sharing one 8-byte slot
     @assert sizeof(VcInputs) == 8 + 8 + 24 + 5 * 8 + 8
     @assert sizeof(ThermalFields) == 16 + 24 * 8
     @assert sizeof(ThermalPhase) == 8 + 8 * 8

@@ -115,10 +115,10 @@ StressUpdate.jl:146-176, …) and throws instead of being dropped.
 """
 function add_args!(d, args::NamedTuple)
     for (k, v) in pairs(args)
-        k === :dt && continue
+        (k === :dt || k === :perturbation_C) && continue     # perturbation_C: unused by the reference's stress kernels of this version too
         v === nothing && continue
         slot = k === :T ? "T" : k === :P ? "Pargs" : k === :ΔT ? "dTargs" :
-            throw(ArgumentError("args.$k is not supported by the B200 backend (supported keys: T, P, ΔT, dt); refusing to ignore it"))
+            throw(ArgumentError("args.$k is not supported by the B200 backend (supported keys: T, P, ΔT, dt, perturbation_C); refusing to ignore it"))
         d[slot] = LIB.ondevice(v)
     end
     return d
@@ -192,15 +192,27 @@ function lower_phase(p::GeoParams.MaterialParams)
     Kb = _modulus(JustRelax.get_bulk_modulus(p))
     pls = filter(_is_plastic, collect(els))
     has_pl, C, sϕ, cϕ, sψ, ηvp = Int32(0), 0.0, 0.0, 0.0, 0.0, 0.0
+    skind, spar = Int32(0), (0.0, 0.0, 0.0, 0.0, 0.0, 0.0)
     if !isempty(pls)
         pl = first(pls)                                                                 # the FIRST plastic element wins: StressUpdate.jl:131-144
-        (pl.softening_C isa GeoParams.NoSoftening && pl.softening_ϕ isa GeoParams.NoSoftening) ||
-            throw(ArgumentError("strain softening is outside the B200 backend's supported subset"))
+        pl.softening_ϕ isa GeoParams.NoSoftening || throw(ArgumentError("friction-angle softening is outside the B200 backend's supported subset"))
+        sc = pl.softening_C
+        if sc isa GeoParams.LinearSoftening
+            ND == 2 || throw(ArgumentError("cohesion softening is supported by the 2D multiphase solve only"))
+            skind = Int32(1)
+            spar = (Float64(sc.lo), Float64(sc.hi), Float64(sc.max_value), Float64(sc.min_value), Float64(sc.slope), Float64(sc.ordinate))
+        elseif sc isa GeoParams.NonLinearSoftening
+            ND == 2 || throw(ArgumentError("cohesion softening is supported by the 2D multiphase solve only"))
+            skind = Int32(2)
+            spar = (Float64(sc.ξ₀), Float64(sc.Δ), Float64(sc.μ), Float64(sc.σ), 0.0, 0.0)
+        elseif !(sc isa GeoParams.NoSoftening)
+            throw(ArgumentError("softening law $(nameof(typeof(sc))) is outside the B200 backend's supported subset"))
+        end
         ηvp_val = pl isa GeoParams.DruckerPrager_regularised ? _val(pl.η_vp) : 0.0
         has_pl, C, sϕ, cϕ, sψ, ηvp = Int32(1), _val(pl.C), _val(pl.sinϕ), _val(pl.cosϕ), _val(pl.sinΨ), ηvp_val     # StressUpdate.jl:139
     end
     kind, ρ0, α, β, T0, P0 = lower_density(p)
-    return API.StokesPhase(_val(first(visc).η), G, Kb, has_pl, kind, C, sϕ, cϕ, sψ, ηvp, ρ0, α, β, T0, P0)
+    return API.StokesPhase(_val(first(visc).η), G, Kb, has_pl, kind, C, sϕ, cϕ, sψ, ηvp, ρ0, α, β, T0, P0, skind, Int32(0), spar)
 end
 
 function lower_thermal_phase(p::GeoParams.MaterialParams)

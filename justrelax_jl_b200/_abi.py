@@ -131,7 +131,8 @@ class StokesPhase(C.Structure):
     """jr_stokes_phase"""
     _fields_ = [("eta", C.c_double), ("G", C.c_double), ("Kb", C.c_double), ("has_pl", C.c_int32), ("rho_kind", C.c_int32),
                 ("C", C.c_double), ("sinphi", C.c_double), ("cosphi", C.c_double), ("sinpsi", C.c_double), ("eta_vp", C.c_double),
-                ("rho0", C.c_double), ("alpha", C.c_double), ("beta", C.c_double), ("T0", C.c_double), ("P0", C.c_double)]
+                ("rho0", C.c_double), ("alpha", C.c_double), ("beta", C.c_double), ("T0", C.c_double), ("P0", C.c_double),
+                ("soft_C_kind", C.c_int32), ("_pad", C.c_int32), ("soft_C", C.c_double * 6)]
 
 
 class VcInputs(C.Structure):

@@ -21,6 +21,8 @@ struct jr_phase_tab {
     double C[JR_MAX_PHASES], sinphi[JR_MAX_PHASES], cosphi[JR_MAX_PHASES], sinpsi[JR_MAX_PHASES], eta_vp[JR_MAX_PHASES];
     double rho0[JR_MAX_PHASES], alpha[JR_MAX_PHASES], beta[JR_MAX_PHASES], T0[JR_MAX_PHASES], P0[JR_MAX_PHASES];
     int has_pl[JR_MAX_PHASES], rho_kind[JR_MAX_PHASES];
+    int soft_kind[JR_MAX_PHASES], any_soft, _pad2;   // cohesion softening (2D solves)
+    double soft[JR_MAX_PHASES][6];
 };
 
 int jr_make_phase_tab(const jr_vc_inputs *vc, jr_phase_tab *out);
@@ -73,6 +75,31 @@ __device__ __forceinline__ double jr_yield_F(const jr_phase_tab &pt, const doubl
         double v = 0.0;
         if (r != 0.0) {
             const double Fp = pt.has_pl[p] ? (tII - pt.cosphi[p] * pt.C[p] - pt.sinphi[p] * (P - 0.0)) - 2 * pt.eta_vp[p] * (0.0 * 0.5) : tII;
+            v = r * Fp;
+        }
+        acc = p == 0 ? v : acc + v;
+    }
+    return acc;
+}
+// soften_cohesion  StressUpdate.jl:305-332 → GeoParams LinearSoftening / NonLinearSoftening
+__device__ __forceinline__ double jr_soften_C(const jr_phase_tab &pt, int p, double EII)
+{
+    if (pt.soft_kind[p] == 1) {
+        if (EII >= pt.soft[p][1]) return pt.soft[p][3];
+        if (EII <= pt.soft[p][0]) return pt.soft[p][2];
+        return EII * pt.soft[p][4] + pt.soft[p][5];
+    }
+    if (pt.soft_kind[p] == 2) return pt.soft[p][0] - 0.5 * pt.soft[p][1] * erfc(-(EII - pt.soft[p][2]) / pt.soft[p][3]);
+    return pt.C[p];
+}
+__device__ __forceinline__ double jr_yield_F_soft(const jr_phase_tab &pt, const double *__restrict__ ph, size_t stride, size_t q, double P, double tII, double EII)
+{
+    double acc = 0.0;
+    for (int p = 0; p < pt.n; p++) {
+        const double r = ph[(size_t)p * stride + q];
+        double v = 0.0;
+        if (r != 0.0) {
+            const double Fp = pt.has_pl[p] ? (tII - pt.cosphi[p] * jr_soften_C(pt, p, EII) - pt.sinphi[p] * (P - 0.0)) - 2 * pt.eta_vp[p] * (0.0 * 0.5) : tII;
             v = r * Fp;
         }
         acc = p == 0 ? v : acc + v;

@@ -33,7 +33,7 @@ struct K2 {
     const double *Vx_i, *Vy_i, *P_i, *txx_i, *tyy_i, *txy_i, *th_i, *txyc_i, *lam_i, *lamv_i, *eta_i, *etav_i;
     double *Vx_o, *Vy_o, *P_o, *txx_o, *tyy_o, *txy_o, *th_o, *txyc_o, *lam_o, *lamv_o, *eta_o, *etav_o;
     // read-only inputs
-    const double *P0, *Q, *K, *G, *etatau, *txxo, *tyyo, *txyo, *txyco, *rhogx, *rhogy, *T, *Pargs, *dTargs, *ph_c, *ph_v;
+    const double *P0, *Q, *K, *G, *etatau, *txxo, *tyyo, *txyo, *txyco, *rhogx, *rhogy, *T, *Pargs, *dTargs, *ph_c, *ph_v, *EII;
     // diagnostics (written when DIAG)
     double *divV, *RP, *exx, *eyy, *exy, *pxx, *pyy, *pxy, *tII, *eta_vep, *e_vol_pl, *Ux, *Uy, *rhogx_w, *rhogy_w, *etatau_w;
 };
@@ -189,7 +189,12 @@ __global__ void __launch_bounds__(TX * TYT) k_stokes2d(const __grid_constant__ K
             double dQ[3], dQdP, dFdP;
             jr_plastic_grads<3>(pt, a.ph_v, nv, v, trial, dQ, dQdP, dFdP);
             const double volume = isinf(Kv) ? 0.0 : Kv * a.dt * dFdP * dQdP;
-            const double Fv = jr_yield_F(pt, a.ph_v, nv, v, Pv, tIIv);
+            double Fv;
+            if (pt.any_soft) {  // cohesion softening: EII interpolated to the vertex (av_clamped, StressKernels.jl:1031)
+                const double EIIv = 0.25 * (a.EII[IX2(nx, i0, j0)] + a.EII[IX2(nx, ic, jc)] + a.EII[IX2(nx, i0, jc)] + a.EII[IX2(nx, ic, j0)]);
+                Fv = jr_yield_F_soft(pt, a.ph_v, nv, v, Pv, tIIv, EIIv);
+            } else
+                Fv = jr_yield_F(pt, a.ph_v, nv, v, Pv, tIIv);
             lamv = a.lamv_i[v];
             if (is_pl && tIIv != 0.0 && Fv > 0) {
                 lamv = fma(a.rel, fmax(Fv, 0.0) / ((INC ? etav * dtr * a.dt : etav * dtr) + eta_reg + volume), (1.0 - a.rel) * lamv);
@@ -228,7 +233,7 @@ __global__ void __launch_bounds__(TX * TYT) k_stokes2d(const __grid_constant__ K
             double dQ[3], dQdP, dFdP;
             jr_plastic_grads<3>(pt, a.ph_c, nc, c, trial, dQ, dQdP, dFdP);
             const double volume = isinf(Kc) ? 0.0 : Kc * a.dt * dFdP * dQdP;
-            const double Fc = jr_yield_F(pt, a.ph_c, nc, c, thn, tII);
+            const double Fc = pt.any_soft ? jr_yield_F_soft(pt, a.ph_c, nc, c, thn, tII, a.EII[c]) : jr_yield_F(pt, a.ph_c, nc, c, thn, tII);
             lam = a.lam_i[c];
             if (is_pl && tII != 0.0 && Fc > 0) {
                 lam = fma(a.rel, fmax(Fc, 0.0) / ((INC ? eta * dtr * a.dt : eta * dtr) + eta_reg + volume), (1.0 - a.rel) * lam);
@@ -519,6 +524,10 @@ int jr_make_phase_tab(const jr_vc_inputs *vc, jr_phase_tab *out)
         out->sinpsi[p] = q.sinpsi; out->eta_vp[p] = q.eta_vp; out->rho0[p] = q.rho0; out->alpha[p] = q.alpha; out->beta[p] = q.beta;
         out->T0[p] = q.T0; out->P0[p] = q.P0; out->has_pl[p] = q.has_pl; out->rho_kind[p] = q.rho_kind;
         if (q.rho_kind != 0) out->rho_const = 0;
+        JR_REQUIRE(q.soft_C_kind >= 0 && q.soft_C_kind <= 2, JR_ERR_UNSUPPORTED, "phase %d: softening law %d outside the supported subset", p, q.soft_C_kind);
+        out->soft_kind[p] = q.has_pl ? q.soft_C_kind : 0;
+        for (int e = 0; e < 6; e++) out->soft[p][e] = q.soft_C[e];
+        if (out->soft_kind[p]) out->any_soft = 1;
     }
     return JR_OK;
 }
@@ -673,7 +682,7 @@ static int plan2_begin(jr_context *ctx, const jr_fields *s, const jr_stokes_opts
     k.dxx = F(dxx); k.dyy = F(dyy); k.dxy = F(dxy); k.divU = F(divU);
     k.P0 = F(P0); k.Q = F(Q); k.K = F(K); k.G = F(G); k.etatau = F(etatau);
     k.txxo = F(txx_o); k.tyyo = F(tyy_o); k.txyo = F(txy_o); k.txyco = F(txy_o_c);
-    k.rhogx = F(rhogx); k.rhogy = F(rhogy); k.T = F(T); k.Pargs = F(Pargs); k.dTargs = F(dTargs);
+    k.rhogx = F(rhogx); k.rhogy = F(rhogy); k.T = F(T); k.Pargs = F(Pargs); k.dTargs = F(dTargs); k.EII = F(EII_pl);
     k.divV = F(divV); k.RP = F(RP); k.exx = F(exx); k.eyy = F(eyy); k.exy = F(exy); k.pxx = F(pxx); k.pyy = F(pyy); k.pxy = F(pxy);
     k.tII = F(tII); k.eta_vep = F(eta_vep); k.e_vol_pl = F(e_vol_pl); k.Ux = F(Ux); k.Uy = F(Uy); k.rhogx_w = F(rhogx); k.rhogy_w = F(rhogy);
     k.etatau_w = F(etatau);

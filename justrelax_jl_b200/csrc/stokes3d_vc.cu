@@ -865,6 +865,7 @@ static int plan3_begin(jr_context *ctx, const jr_fields *s, const jr_stokes_opts
     for (int q = 0; q < 6; q++) { p->fs[q] = o->free_slip[q]; p->ns[q] = o->no_slip[q]; p->pe[q] = o->periodic[q]; }
     p->multi = ctx->comm && ctx->comm->nranks > 1;
     if ((st = jr_make_phase_tab(in, &p->pt))) return st;
+    JR_REQUIRE(!p->pt.any_soft, JR_ERR_UNSUPPORTED, "cohesion softening is supported by the 2D multiphase solve only (the 3D-VC kernels do not carry EII to the edges)");
     V3 &k = p->k;
     k.nx = nx; k.ny = ny; k.nz = nz;
     k._dx = o->_di[0]; k._dy = o->_di[1]; k._dz = o->_di[2]; k.dt = o->dt; k.r = o->r; k.th = o->theta_dtau; k.edt = o->eta_dtau;

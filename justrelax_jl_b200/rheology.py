@@ -89,6 +89,31 @@ class ConstantElasticity:
 
 
 @dataclass
+class LinearSoftening:
+    """GeoParams LinearSoftening((min_value, max_value), (lo, hi)): max_value below lo, min_value above hi, linear in between"""
+    min_max_values: tuple = (0.0, 0.0)
+    lo_hi: tuple = (0.0, 1.0)
+
+    def params(self):
+        mn, mx = (float(v) for v in self.min_max_values)
+        lo, hi = (float(v) for v in self.lo_hi)
+        slope = (mx - mn) / (lo - hi)
+        return 1, [lo, hi, mx, mn, slope, mx - slope * lo]
+
+
+@dataclass
+class NonLinearSoftening:
+    """GeoParams NonLinearSoftening(ξ₀, Δ, μ = 1, σ = 0.5): ξ₀ − ½·Δ·erfc(−(x − μ)/σ)"""
+    ξ0: float = 0.0
+    Δ: float = 0.0
+    μ: float = 1.0
+    σ: float = 0.5
+
+    def params(self):
+        return 2, [float(self.ξ0), float(self.Δ), float(self.μ), float(self.σ), 0.0, 0.0]
+
+
+@dataclass
 class DruckerPrager_regularised:
     """F = τII − C cosϕ − P sinϕ; ϕ, Ψ in degrees; η_vp regularisation viscosity"""
     C: float = 10e6
@@ -189,10 +214,11 @@ def _modulus(x):
     return math.inf if (x is None or x != x or x == 0) else float(x)
 
 
-def lower_stokes(rheology):
-    """rows of jr_stokes_phase: dict(eta, G, Kb, has_pl, rho_kind, C, sinphi, cosphi, sinpsi, eta_vp, rho0, alpha, beta, T0, P0).
-    Supported: LinearViscous (exactly one creep element), ConstantElasticity, DruckerPrager[_regularised] without softening
-    (the FIRST plastic element wins, StressUpdate.jl:131-144), Constant/PT_/T_Density."""
+def lower_stokes(rheology, ndim: int = 2):
+    """rows of jr_stokes_phase: dict(eta, G, Kb, has_pl, rho_kind, C, sinphi, cosphi, sinpsi, eta_vp, rho0, alpha, beta, T0, P0, soft_C_kind,
+    soft_C).  Supported: LinearViscous (exactly one creep element), ConstantElasticity, DruckerPrager[_regularised] (the FIRST plastic element
+    wins, StressUpdate.jl:131-144) with cohesion softening (Linear/NonLinearSoftening of C with the accumulated plastic strain,
+    StressUpdate.jl:305-332 — 2D solves only), Constant/PT_/T_Density."""
     rows = []
     for p in _as_tuple(rheology):
         if p.CompositeRheology is None:
@@ -209,11 +235,18 @@ def lower_stokes(rheology):
         pls = [e for e in p.CompositeRheology.elements if isinstance(e, DruckerPrager_regularised)]
         if pls:
             pl = pls[0]
-            if pl.softening_C is not None or pl.softening_ϕ is not None:
-                raise UnsupportedRheology("strain softening is outside the supported subset (SURVEY §8f-1)")
-            row.update(has_pl=1, C=float(pl.C), sinphi=pl.sinϕ, cosphi=pl.cosϕ, sinpsi=pl.sinΨ, eta_vp=float(pl.η_vp))
+            if pl.softening_ϕ is not None:
+                raise UnsupportedRheology("friction-angle softening is outside the supported subset (SURVEY §8f-1)")
+            kind, par = 0, [0.0] * 6
+            if pl.softening_C is not None:
+                if not isinstance(pl.softening_C, (LinearSoftening, NonLinearSoftening)):
+                    raise UnsupportedRheology(f"softening law {type(pl.softening_C).__name__} is outside the supported subset")
+                if ndim != 2:
+                    raise UnsupportedRheology("cohesion softening is supported by the 2D multiphase solve only (SURVEY §8f-1)")
+                kind, par = pl.softening_C.params()
+            row.update(has_pl=1, C=float(pl.C), sinphi=pl.sinϕ, cosphi=pl.cosϕ, sinpsi=pl.sinΨ, eta_vp=float(pl.η_vp), soft_C_kind=kind, soft_C=par)
         else:
-            row.update(has_pl=0, C=0.0, sinphi=0.0, cosphi=0.0, sinpsi=0.0, eta_vp=0.0)
+            row.update(has_pl=0, C=0.0, sinphi=0.0, cosphi=0.0, sinpsi=0.0, eta_vp=0.0, soft_C_kind=0, soft_C=[0.0] * 6)
         ρ = p.Density
         if ρ is None or isinstance(ρ, ConstantDensity):
             row.update(rho_kind=0, rho0=(ρ.ρ if ρ else 0.0), alpha=0.0, beta=0.0, T0=0.0, P0=0.0)

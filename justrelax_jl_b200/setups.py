@@ -388,6 +388,27 @@ def shearband2d(n=32):
                            ratios=ratios, nt=10, kwargs=dict(verbose=False, iterMax=50.0e3, nout=1.0e2, viscosity_cutoff=(-math.inf, math.inf)))
 
 
+def shearband2d_softening(n=32):
+    """test/test_shearband2D_softening.jl:61-192: the shear-band setup with cohesion softening — DruckerPrager_regularised(C = 1.6/cosd(30),
+    ϕ = 30, η_vp = 8e-3, Ψ = 0, softening_C = NonLinearSoftening(ξ₀ = 1.6, Δ = 0.8)), dt = η0/G0/4/5 = 0.05, five time steps, args carry
+    ΔT = 0 (the thermal-stress form of compute_P! with α = 0)."""
+    from . import rheology as R
+
+    s = shearband2d(n)
+    cosd = math.cos(math.radians(30))
+    pl = R.DruckerPrager_regularised(C=1.6 / cosd, ϕ=30, η_vp=8.0e-3, Ψ=0, softening_C=R.NonLinearSoftening(ξ0=1.6, Δ=0.8))
+    mats = []
+    for m in s.rheology:
+        els = tuple(pl if isinstance(e, R.DruckerPrager_regularised) else e for e in m.CompositeRheology.elements)
+        mats.append(R.SetMaterialParams(Phase=m.Phase, Density=m.Density, Gravity=m.Gravity, CompositeRheology=R.CompositeRheology(els), Elasticity=m.Elasticity))
+    s.rheology = tuple(mats)
+    s.dt = s.dt / 5
+    s.nt = 5
+    s.fields["dTargs"] = np.zeros(s.ni, order="F")
+    s.solution = lambda t: 2.0 * 1.0 * 1.0 * (1.0 - math.exp(-1.0 * t / 1.0))   # solution(ε, t, G, η) of the test script
+    return s
+
+
 def sinking_block2d(n=32, *, nsub=8, center_weights="uniform"):
     """test/test_sinking_block.jl:93-200 (variant 2D-VC with buoyancy, SI units): 500 km square, mantle (LinearViscous η = 1e21,
     ConstantDensity 3200) with a 100 km square block (η = 1e23, ρ = 3300) centred at x = 250 km, depth 100 km; no elasticity (G = Kb = Inf),

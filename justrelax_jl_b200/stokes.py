@@ -379,14 +379,14 @@ def iterate2d_V2_(stokes, pt_stokes, di, flow_bcs, ρg, G, K, dt, niter: int, ig
     return SimpleNamespace(iter=int(res.iter), time=float(res.time_s), kernel_launches=int(res.kernel_launches))
 
 
-def vc_inputs(rheology, phase_ratios: PhaseRatios, *, free_surface: float = 0.0):
+def vc_inputs(rheology, phase_ratios: PhaseRatios, *, free_surface: float = 0.0, ndim: int = 2):
     """lower rheology::NTuple{N,MaterialParams} to the flat table (raises UnsupportedRheology outside the subset) and bind the
     phase-ratio arrays → jr_vc_inputs"""
-    rows = _rheology.lower_stokes(rheology)
+    rows = _rheology.lower_stokes(rheology, ndim)
     arr = (_abi.StokesPhase * len(rows))()
     for i, r in enumerate(rows):
         for k, v in r.items():
-            setattr(arr[i], k, v)
+            setattr(arr[i], k, (C.c_double * len(v))(*v) if isinstance(v, (list, tuple)) else v)
     vc = _abi.VcInputs()
     # compute_gravity(ConstantGravity) is a Number: only the last ρg component is filled (BuoyancyForces.jl:70-71)
     vc.nphase, vc.g_scalar, vc.phases, vc.free_surface = len(rows), 1, arr, float(free_surface)
@@ -418,9 +418,11 @@ def _args_items(args) -> dict:
 def vc_slots(stokes, ρg, args) -> dict:
     """field slots of a VC solve.  `args` is the reference's NamedTuple (Stokes2D.jl:577-599, Stokes3D.jl:447-466): T (ni.+2, cell
     centres with one ghost layer) and P feed the density / viscosity laws, ΔT (ni) switches compute_P! to the thermal-stress form
-    (PressureKernels.jl:128-149,197-206), dt is carried by the miniapps but never read by the lowered laws.  Every other key —
-    melt_fraction (PressureKernels.jl:151-176), perturbation_C (StressUpdate.jl:146-176), … — selects behaviour this backend does
-    not have: it raises instead of being dropped."""
+    (PressureKernels.jl:128-149,197-206), dt is carried by the miniapps but never read by the lowered laws, and perturbation_C is
+    accepted and unused exactly as in the reference (its only consumer, the keyword of plastic_params_phase StressUpdate.jl:146-176,
+    is never handed `args` by the stress kernels of this version: StressKernels.jl:1037,1084 call it without keywords).  Every other
+    key — melt_fraction (PressureKernels.jl:151-176), ϕ, … — selects behaviour this backend does not have: it raises instead of
+    being dropped."""
     d = stokes.slots()
     d["rhogx"], d["rhogy"] = ρg[0], ρg[1]
     if len(ρg) > 2:
@@ -428,10 +430,10 @@ def vc_slots(stokes, ρg, args) -> dict:
     items = _args_items(args)
     known = {"T": "T", "P": "Pargs", "ΔT": "dTargs", "dT": "dTargs"}
     for k, v in items.items():
-        if k == "dt":
+        if k in ("dt", "perturbation_C"):
             continue
         if k not in known:
-            raise NotImplementedError(f"args.{k} is not supported by the B200 backend (supported keys: T, P, ΔT, dt); "
+            raise NotImplementedError(f"args.{k} is not supported by the B200 backend (supported keys: T, P, ΔT, dt, perturbation_C); "
                                       "refusing to ignore it")
         if v is None:
             continue
@@ -608,7 +610,7 @@ def compute_shear_heating_(thermal, stokes, *rest):
     arr = (_abi.StokesPhase * len(rows))()
     for i, r in enumerate(rows):
         for k, v in r.items():
-            setattr(arr[i], k, v)
+            setattr(arr[i], k, (C.c_double * len(v))(*v) if isinstance(v, (list, tuple)) else v)
     vc = _abi.VcInputs()
     vc.nphase, vc.g_scalar, vc.phases = len(rows), 1, arr
     if phase_ratios is not None:

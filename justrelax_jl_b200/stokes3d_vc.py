@@ -26,7 +26,7 @@ def solve3d_VC_(stokes, pt_stokes, grid, flow_bcs, ρg, phase_ratios, rheology, 
     igg = igg or IGG()
     grid = _grid_of(stokes, grid, igg)
     opts = _vc_opts(stokes, pt_stokes, grid, flow_bcs, dt, igg, kw)
-    vc = vc_inputs(rheology, phase_ratios)
+    vc = vc_inputs(rheology, phase_ratios, ndim=3)
     fs = build_fields(vc_slots(stokes, ρg, args), stokes.ni)
     hist = _Hist(int(opts.iterMax // max(opts.nout, 1)) + 3, _abi.StokesResult)
     st = _abi.lib().jr_stokes3d_solve_VC(context(), C.byref(fs), C.byref(opts), C.byref(vc), C.byref(hist.res))
@@ -49,7 +49,7 @@ def iterate3d_VC_(stokes, pt_stokes, grid, flow_bcs, ρg, phase_ratios, rheology
     igg = igg or IGG()
     grid = _grid_of(stokes, grid, igg)
     opts = _vc_opts(stokes, pt_stokes, grid, flow_bcs, dt, igg, kw)
-    vc = vc_inputs(rheology, phase_ratios)
+    vc = vc_inputs(rheology, phase_ratios, ndim=3)
     fs = build_fields(vc_slots(stokes, ρg, args), stokes.ni)
     res = _abi.StokesResult()
     _abi.check(_abi.lib().jr_stokes3d_iterate_VC(context(), C.byref(fs), C.byref(opts), C.byref(vc), int(niter), int(finish), C.byref(res)))
@@ -57,7 +57,7 @@ def iterate3d_VC_(stokes, pt_stokes, grid, flow_bcs, ρg, phase_ratios, rheology
 
 
 def compute_viscosity3d_(stokes, phase_ratios, args, rheology, cutoff=(-math.inf, math.inf), *, relaxation=1.0):
-    vc = vc_inputs(rheology, phase_ratios)
+    vc = vc_inputs(rheology, phase_ratios, ndim=3)
     o = _abi.StokesOpts()
     o.visc_cutoff_lo, o.visc_cutoff_hi = float(cutoff[0]), float(cutoff[1])
     fs = build_fields(vc_slots(stokes, (stokes.P, stokes.P, stokes.P), args), stokes.ni)
@@ -65,7 +65,7 @@ def compute_viscosity3d_(stokes, phase_ratios, args, rheology, cutoff=(-math.inf
 
 
 def compute_rhog3d_(ρg, phase_ratios, rheology, args, stokes):
-    vc = vc_inputs(rheology, phase_ratios)
+    vc = vc_inputs(rheology, phase_ratios, ndim=3)
     fs = build_fields(vc_slots(stokes, ρg, args), stokes.ni)
     _abi.check(_abi.lib().jr_compute_rhog3d(context(), C.byref(fs), C.byref(vc)))
 

@@ -105,6 +105,10 @@ typedef struct {
     int32_t has_pl, rho_kind;          /* rho_kind: 0 ConstantDensity, 1 PT_Density, 2 T_Density */
     double C, sinphi, cosphi, sinpsi, eta_vp;
     double rho0, alpha, beta, T0, P0;
+    /* cohesion softening with the accumulated plastic strain EII (StressUpdate.jl:305-332): 0 none; 1 LinearSoftening
+     * {lo, hi, max, min, slope, ordinate}; 2 NonLinearSoftening {ξ₀, Δ, μ, σ}: C(EII) = ξ₀ − ½ Δ erfc(−(EII − μ)/σ).  2D solves only. */
+    int32_t soft_C_kind, _pad;
+    double soft_C[6];
 } orc_stokes_phase;
 
 /* extra inputs of the multiphase (VC) solves: rheology table, gravity of phase 1 (BuoyancyForces.jl:25,56),

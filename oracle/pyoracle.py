@@ -122,6 +122,8 @@ def alloc_stokes(ni, init: dict | None = None) -> dict:
             d[nm] = z(*v)
     d["T"] = z(*(n + 2 for n in ni))      # args.T (ghosted) and args.P of the VC variants
     d["Pargs"] = z(*c)
+    if init and "dTargs" in init:         # args.ΔT: only present when the caller passes it (NULL slot = the plain compute_P! form)
+        d["dTargs"] = z(*c)
     if init:
         for k, a in init.items():
             assert k in d, k
@@ -281,7 +283,7 @@ def thermal_opts(*, _di, dt, eps, iterMax, nout, max_lxyz, Vpdtau, form, phases=
     arr = (ThermalPhase * max(len(phases), 1))()
     for i, p in enumerate(phases):
         for k, v in p.items():
-            setattr(arr[i], k, v)
+            setattr(arr[i], k, (C.c_double * len(v))(*v) if isinstance(v, (list, tuple)) else v)
     o.nphase, o.phases = len(phases), arr
     o._keep = arr
     for q, f in enumerate(FACES):
@@ -315,7 +317,8 @@ def heatdiffusion_PT(slots, ni, opts, stokes_P=None, stokes_P0=None):
 class StokesPhase(C.Structure):
     _fields_ = [("eta", C.c_double), ("G", C.c_double), ("Kb", C.c_double), ("has_pl", C.c_int32), ("rho_kind", C.c_int32),
                 ("C", C.c_double), ("sinphi", C.c_double), ("cosphi", C.c_double), ("sinpsi", C.c_double), ("eta_vp", C.c_double),
-                ("rho0", C.c_double), ("alpha", C.c_double), ("beta", C.c_double), ("T0", C.c_double), ("P0", C.c_double)]
+                ("rho0", C.c_double), ("alpha", C.c_double), ("beta", C.c_double), ("T0", C.c_double), ("P0", C.c_double),
+                ("soft_C_kind", C.c_int32), ("_pad", C.c_int32), ("soft_C", C.c_double * 6)]
 
 
 class VcInputs(C.Structure):
@@ -329,7 +332,7 @@ def vc_inputs(rows, g, ratios: dict, *, g_scalar=True, free_surface=0.0, Phase=S
     arr = (Phase * len(rows))()
     for i, r in enumerate(rows):
         for k, v in r.items():
-            setattr(arr[i], k, v)
+            setattr(arr[i], k, (C.c_double * len(v))(*v) if isinstance(v, (list, tuple)) else v)
     vc = Inputs()
     vc.nphase, vc.g_scalar, vc.phases, vc.free_surface = len(rows), int(g_scalar), arr, float(free_surface)
     for q in range(3):

@@ -318,7 +318,7 @@ static void stress_vep2(const orc_fields *s, const orc_stokes_opts *o, const orc
             {
                 const double Pv = AVC(theta), exxv = inc ? AVC(F(dxx)) : AVC(F(exx)), eyyv = inc ? AVC(F(dyy)) : AVC(F(eyy)), txxv = AVC(txx0), tyyv = AVC(tyy0);
                 const double txxov = AVC(F(txx_o)), tyyov = AVC(F(tyy_o)), EIIv = AVC(F(EII_pl));
-                (void)EIIv;
+
                 int is_pl; double eta_reg;
                 plastic_params(vc, vc->ph_vertex, nv, v, &is_pl, &eta_reg);
                 const double _Gdt = orc_inv(ratio_G(vc, vc->ph_vertex, nv, v) * dt), Kv = ratio_Kb(vc, vc->ph_vertex, nv, v);
@@ -334,7 +334,7 @@ static void stress_vep2(const orc_fields *s, const orc_stokes_opts *o, const orc
                 double dQ[3], dQdP, dFdP;
                 plastic_grads(vc, vc->ph_vertex, nv, v, trial, dQ, &dQdP, &dFdP);
                 const double volume = isinf(Kv) ? 0.0 : Kv * dt * dFdP * dQdP;
-                const double Fv = yield_F(vc, vc->ph_vertex, nv, v, Pv, tII);
+                const double Fv = yield_F_soft(vc, vc->ph_vertex, nv, v, Pv, tII, EIIv);
                 if (is_pl && tII != 0.0 && Fv > 0) {
                     lamv[v] = fma(rel, fmax(Fv, 0.0) / ((inc ? etav * dtr * dt : etav * dtr) + eta_reg + volume), (1.0 - rel) * lamv[v]);
                     const double epl = lamv[v] * dQ[2];
@@ -372,7 +372,7 @@ static void stress_vep2(const orc_fields *s, const orc_stokes_opts *o, const orc
                 const double Pr = theta[c];
                 plastic_grads(vc, vc->ph_center, nc, c, trial, dQ, &dQdP, &dFdP);
                 const double volume = isinf(K) ? 0.0 : K * dt * dFdP * dQdP;
-                const double Fc = yield_F(vc, vc->ph_center, nc, c, Pr, tII);
+                const double Fc = yield_F_soft(vc, vc->ph_center, nc, c, Pr, tII, F(EII_pl)[c]);
                 if (is_pl && tII != 0.0 && Fc > 0) {
                     lam[c] = fma(rel, fmax(Fc, 0.0) / ((inc ? eta * dtr * dt : eta * dtr) + eta_reg + volume), (1.0 - rel) * lam[c]);
                     double epl[3];

@@ -56,6 +56,32 @@ static inline void plastic_params(const orc_vc_inputs *vc, const double *ph, siz
     }
 }
 /* compute_yieldfunction_phase  StressUpdate.jl:384-452: Σ r·F_phase (non-plastic phase: F = τII), zero ratios skipped */
+/* soften_cohesion  StressUpdate.jl:305-332 → GeoParams LinearSoftening / NonLinearSoftening (third party, restated) */
+static inline double soften_C(const orc_stokes_phase *q, double EII)
+{
+    if (q->soft_C_kind == 1) {
+        if (EII >= q->soft_C[1]) return q->soft_C[3];
+        if (EII <= q->soft_C[0]) return q->soft_C[2];
+        return EII * q->soft_C[4] + q->soft_C[5];
+    }
+    if (q->soft_C_kind == 2) return q->soft_C[0] - 0.5 * q->soft_C[1] * erfc(-(EII - q->soft_C[2]) / q->soft_C[3]);
+    return q->C;
+}
+static inline double yield_F_soft(const orc_vc_inputs *vc, const double *ph, size_t stride, size_t idx, double P, double tII, double EII)
+{
+    double acc = 0.0;
+    for (int p = 0; p < vc->nphase; p++) {
+        const double r = ph[(size_t)p * stride + idx];
+        double v = 0.0;
+        if (r != 0.0) {
+            const orc_stokes_phase *q = &vc->phases[p];
+            const double Fp = q->has_pl ? (tII - q->cosphi * soften_C(q, EII) - q->sinphi * (P - 0.0)) - 2 * q->eta_vp * (0.0 * 0.5) : tII;
+            v = r * Fp;
+        }
+        acc = p == 0 ? v : acc + v;
+    }
+    return acc;
+}
 static inline double yield_F(const orc_vc_inputs *vc, const double *ph, size_t stride, size_t idx, double P, double tII)
 {
     double acc = 0.0;

@@ -185,6 +185,43 @@ def test_vc_thermal_stress_pressure_form(oracle):
     assert max_rel_diff(to_host(st["P"]), d0["P"]) > 1e-4, "ΔT must change the pressure"
 
 
+def test_vc_cohesion_softening(oracle):
+    """cohesion softening with the accumulated plastic strain (StressUpdate.jl:305-332; Linear / NonLinearSoftening) in the fused kernel:
+    EII at the centres and interpolated to the vertices, both laws, engaged (random EII across the softening range)"""
+    from justrelax_jl_b200 import rheology as R
+
+    ni = (47, 38)
+    f, grid, pt, dt, rat, rheo = random_vc2d(ni, 21, rho_var=False)
+    f["EII_pl"] = np.asfortranarray(np.random.default_rng(2).uniform(0.0, 2.0, size=ni))
+    laws = [R.LinearSoftening((0.02, 0.3), (0.2, 1.5)), R.NonLinearSoftening(ξ0=0.25, Δ=0.2)]
+    mats = []
+    for m in rheo:
+        els = []
+        for e in m.CompositeRheology.elements:
+            if isinstance(e, R.DruckerPrager_regularised):
+                e = R.DruckerPrager_regularised(C=e.C, ϕ=e.ϕ, η_vp=e.η_vp, Ψ=e.Ψ, softening_C=laws[len(mats) % 2])
+            els.append(e)
+        mats.append(R.SetMaterialParams(Phase=m.Phase, Density=m.Density, Gravity=m.Gravity, CompositeRheology=R.CompositeRheology(tuple(els)),
+                                        Elasticity=m.Elasticity))
+    flags = dict(free_slip=[1, 1, 0, 0, 1, 1], no_slip=[0] * 6, periodic=[0] * 6)
+    for niter in (1, 4):
+        st, d = _run_vc(oracle, ni, f, grid, pt, dt, rat, tuple(mats), flags, niter, False)
+        assert d["lam"].max() > 0 and d["lamv"].max() > 0
+        compare_slots(st, d, VC_STATE + VC_DIAG, TOL, f"VC softening niter={niter}")
+    st0, d0 = _run_vc(oracle, ni, f, grid, pt, dt, rat, rheo, flags, 4, False)
+    assert max_rel_diff(d["lam"], d0["lam"]) > 1e-3, "softening must change the plastic multiplier"
+
+
+def test_softening_unsupported_in_3d():
+    from justrelax_jl_b200 import rheology as R
+
+    pl = R.DruckerPrager_regularised(C=1.0, ϕ=30, η_vp=1e-2, softening_C=R.NonLinearSoftening(ξ0=1.0, Δ=0.5))
+    m = (R.SetMaterialParams(Phase=1, Density=R.ConstantDensity(ρ=1.0), CompositeRheology=R.CompositeRheology((R.LinearViscous(η=1.0), pl))),)
+    assert R.lower_stokes(m, 2)[0]["soft_C_kind"] == 2
+    with pytest.raises(R.UnsupportedRheology, match="2D multiphase solve only"):
+        R.lower_stokes(m, 3)
+
+
 @pytest.mark.parametrize("inc,dbc", [(True, False), (True, True), (False, True)])
 @pytest.mark.parametrize("ni", [(9, 7), (64, 47), (95, 130)])
 def test_vc_strain_increment_and_displacement_bcs(oracle, ni, inc, dbc):

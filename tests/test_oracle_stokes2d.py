@@ -253,3 +253,40 @@ def test_sinking_block_particle_equivalent_phase_ratios(oracle):
         assert abs(v / 5.1146e-10 - 1) < 0.04, (seed, v)          # within particle noise of the grid-sampled restatement
         assert abs(v / 4.841885609356093e-10 - 1) < 0.07, (seed, v)   # and within 7 % of the reference's golden
         base = v if base is None else base
+
+
+def test_shearband2d_softening_reference_golden(oracle):
+    """test/test_shearband2D_softening.jl:197-204: cohesion softening law present, five steps of dt = 0.05: err < 1e-6, maximum(τxx) ≈ 0.466
+    (atol 1e-3) and the visco-elastic build-up 2 ε η (1 − exp(−G t/η)) ≈ 0.4423 (atol 1e-4)"""
+    s = setups.shearband2d_softening(32)
+    d, outs, txx_max = run_shearband(oracle, s)
+    assert all(o["status"] == 0 for o in outs) and outs[-1]["err_evo1"][-1] < 1.0e-6
+    assert abs(txx_max[-1] - 0.466) < 1.0e-3, txx_max[-1]
+    assert abs(s.solution(5 * s.dt) - 0.4423) < 1.0e-4
+
+
+def test_softening_laws(oracle):
+    """GeoParams LinearSoftening / NonLinearSoftening as lowered into the flat table: limits and mid-points; and softening that engages
+    (large accumulated plastic strain lowers the cohesion, so a stress state that is elastic with EII = 0 yields)"""
+    lo, hi, mx, mn = 0.1, 0.5, 2.0, 1.0
+    kind, p = R.LinearSoftening((mn, mx), (lo, hi)).params()
+    lin = lambda x: mn if x >= p[1] else (mx if x <= p[0] else x * p[4] + p[5])
+    assert kind == 1 and lin(0.0) == mx and lin(1.0) == mn and abs(lin(0.3) - 1.5) < 1e-15 and abs(lin(lo + 1e-12) - mx) < 1e-9
+    kind, q = R.NonLinearSoftening(ξ0=1.6, Δ=0.8).params()
+    nl = lambda x: q[0] - 0.5 * q[1] * math.erfc(-(x - q[2]) / q[3])
+    assert kind == 2 and abs(nl(0.0) - (1.6 - 0.4 * math.erfc(2.0))) < 1e-15 and abs(nl(1.0) - 1.2) < 1e-15 and abs(nl(10.0) - 0.8) < 1e-12
+    # engagement: one iteration from the same state with EII = 0 and EII = 3 (C: 1.6/cos30 → ≈ 0.8)
+    s = setups.shearband2d_softening(16)
+    res = {}
+    for EII in (0.0, 3.0):
+        d = oracle.alloc_stokes(s.ni, s.fields)
+        d["txx"][...] = 1.2
+        d["tyy"][...] = -1.2
+        d["txx_o"][...] = 1.2
+        d["tyy_o"][...] = -1.2
+        d["EII_pl"][...] = EII
+        vc = oracle.vc_inputs(R.lower_stokes(s.rheology), R.gravity_of(s.rheology), s.ratios)
+        opts = oracle.make_opts(s.pt_stokes, s.grid._di.center, s.dt, bc_flags(s.flow_bcs), s.ni, iterMax=1, nout=1)
+        oracle.iterate2d_VC(d, s.ni, opts, vc, 1)
+        res[EII] = d["lam"].max()
+    assert res[0.0] == 0.0 and res[3.0] > 0.0, res

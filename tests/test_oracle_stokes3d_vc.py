@@ -221,10 +221,10 @@ def test_unknown_args_key_fails_loudly():
     from justrelax_jl_b200.stokes import vc_slots
 
     st = StokesArrays(CPUBackend, 4, 4, 4)
-    for bad in ("melt_fraction", "perturbation_C", "ϕ"):
+    for bad in ("melt_fraction", "ϕ", "anything_else"):
         with pytest.raises(NotImplementedError, match="refusing to ignore"):
             vc_slots(st, (st.P, st.P, st.P), {bad: st.P})
-    assert "dTargs" not in vc_slots(st, (st.P, st.P, st.P), dict(dt=0.1))
+    assert "dTargs" not in vc_slots(st, (st.P, st.P, st.P), dict(dt=0.1, perturbation_C=st.P))   # accepted and unused, as in the reference
 
 
 def in_plane_invariant(oracle, txx, tzz, txz, j=1):
