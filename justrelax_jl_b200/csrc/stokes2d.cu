@@ -44,7 +44,9 @@ __device__ __forceinline__ void jr_prefetch_l1(const double *p) { asm volatile("
 // TYT = threads in y (tile height incl. the one-node rim): chosen per grid so that the CTA count fills whole waves (plan2_tile)
 // INC (VC only): strain-increment form (kwarg strain_increment = true, Stokes2D.jl:659-730; StressKernels.jl:1147-1302): Δε from the
 // displacement U, ε = Δε/dt, stress increments from Δε; the planes s_exx / s_eyy / s_exy then hold Δε and readers scale by 1/dt.
-template <bool VC, bool DIAG, int TYT, bool INC = false>
+// RARE (VC only): the seldom-used options — args.ΔT (thermal-stress pressure form), DisplacementBoundaryConditions, cohesion softening,
+// and INC — are compiled only into the RARE instantiations, so the common path keeps its register budget (no spills)
+template <bool VC, bool DIAG, int TYT, bool INC = false, bool RARE = false>
 __global__ void __launch_bounds__(TX * TYT) k_stokes2d(const __grid_constant__ K2 a, const __grid_constant__ jr_phase_tab pt)
 {
     constexpr int NTT = TX * TYT;
@@ -76,6 +78,7 @@ __global__ void __launch_bounds__(TX * TYT) k_stokes2d(const __grid_constant__ K
     }
     double divV = 0.0, RP = 0.0, thn = 0.0, exx = 0.0, eyy = 0.0, exy = 0.0, ett = 0.0, eta = 0.0, rgx = 0.0, rgy = 0.0;
     double txx = 0.0, tyy = 0.0, txxo = 0.0, tyyo = 0.0, Kc = 0.0, Gc = 0.0, divU = 0.0;
+    const bool dbc = RARE && a.dbc;
     const double _dt = jr_inv(a.dt);
     if (cell) {
         eta = a.eta_i[c];
@@ -102,7 +105,7 @@ __global__ void __launch_bounds__(TX * TYT) k_stokes2d(const __grid_constant__ K
             thn = a.P_i[c];
         }
         // compute_P! with ητ (quirk Q5)  Stokes2D.jl:231-233, 664-677; PressureKernels.jl:186-195
-        if (VC && a.dTargs)  // args.ΔT given: thermal-stress form  PressureKernels.jl:128-149,197-206
+        if (VC && RARE && a.dTargs)  // args.ΔT given: thermal-stress form  PressureKernels.jl:128-149,197-206
             jr_compute_P_point_dT(RP, thn, a.P0[c], divV, a.Q[c], a.dTargs[c], jr_ratio_alpha(pt, a.ph_c, nc, c), ett, Kc, Gc, a.dt, a.r, a.th);
         else
             jr_compute_P_point(RP, thn, a.P0[c], divV, a.Q[c], ett, Kc, Gc, a.dt, a.r, a.th);
@@ -190,7 +193,7 @@ __global__ void __launch_bounds__(TX * TYT) k_stokes2d(const __grid_constant__ K
             jr_plastic_grads<3>(pt, a.ph_v, nv, v, trial, dQ, dQdP, dFdP);
             const double volume = isinf(Kv) ? 0.0 : Kv * a.dt * dFdP * dQdP;
             double Fv;
-            if (pt.any_soft) {  // cohesion softening: EII interpolated to the vertex (av_clamped, StressKernels.jl:1031)
+            if (RARE && pt.any_soft) {  // cohesion softening: EII interpolated to the vertex (av_clamped, StressKernels.jl:1031)
                 const double EIIv = 0.25 * (a.EII[IX2(nx, i0, j0)] + a.EII[IX2(nx, ic, jc)] + a.EII[IX2(nx, i0, jc)] + a.EII[IX2(nx, ic, j0)]);
                 Fv = jr_yield_F_soft(pt, a.ph_v, nv, v, Pv, tIIv, EIIv);
             } else
@@ -233,7 +236,7 @@ __global__ void __launch_bounds__(TX * TYT) k_stokes2d(const __grid_constant__ K
             double dQ[3], dQdP, dFdP;
             jr_plastic_grads<3>(pt, a.ph_c, nc, c, trial, dQ, dQdP, dFdP);
             const double volume = isinf(Kc) ? 0.0 : Kc * a.dt * dFdP * dQdP;
-            const double Fc = pt.any_soft ? jr_yield_F_soft(pt, a.ph_c, nc, c, thn, tII, a.EII[c]) : jr_yield_F(pt, a.ph_c, nc, c, thn, tII);
+            const double Fc = (RARE && pt.any_soft) ? jr_yield_F_soft(pt, a.ph_c, nc, c, thn, tII, a.EII[c]) : jr_yield_F(pt, a.ph_c, nc, c, thn, tII);
             lam = a.lam_i[c];
             if (is_pl && tII != 0.0 && Fc > 0) {
                 lam = fma(a.rel, fmax(Fc, 0.0) / ((INC ? eta * dtr * a.dt : eta * dtr) + eta_reg + volume), (1.0 - a.rel) * lam);
@@ -299,16 +302,16 @@ __global__ void __launch_bounds__(TX * TYT) k_stokes2d(const __grid_constant__ K
             const double dt_xy = (-s_txyn[t] + s_txyn[t + TX]) * a._dy, avf = (s_rgx[t - 1] + s_rgx[t]) * 0.5, ave = (s_ett[t - 1] + s_ett[t]) * 0.5;
             vx = a.Vx_i[e] + (-dP + dt_xx + dt_xy - avf) * a.edt / ave;
         } else
-            vx = (!a.dbc && ((i == 1) ? a.ns_l : a.ns_r)) ? 0.0 : a.Vx_i[e];
+            vx = (!dbc && ((i == 1) ? a.ns_l : a.ns_r)) ? 0.0 : a.Vx_i[e];
         a.Vx_o[e] = vx;
         // velocity2displacement! runs BEFORE flow_bcs!; with DisplacementBoundaryConditions flow_bcs! then acts on U (V untouched)
         double *const Uxw = INC ? a.Ux_o : ((DIAG && a.Ux) ? a.Ux : nullptr);
         const bool nzero = (i == 1 && a.ns_l) || (i == nx + 1 && a.ns_r);   // no_slip! zeroes the boundary-normal face (all rows)
-        const double ux = (a.dbc && nzero) ? 0.0 : ((i >= 2 && i <= nx) ? vx : a.Vx_i[e]) * a.dt;
+        const double ux = (dbc && nzero) ? 0.0 : ((i >= 2 && i <= nx) ? vx : a.Vx_i[e]) * a.dt;
         if (Uxw) Uxw[e] = ux;
         if (j == 1) {
             const size_t g = IX2(nx + 1, i, 1);
-            if (!a.dbc) {
+            if (!dbc) {
                 a.Vx_o[g] = a.fs_b ? vx : (a.ns_b ? -vx : (nzero ? 0.0 : a.Vx_i[g]));
                 if (Uxw) Uxw[g] = a.Vx_i[g] * a.dt;
             } else {
@@ -318,7 +321,7 @@ __global__ void __launch_bounds__(TX * TYT) k_stokes2d(const __grid_constant__ K
         }
         if (j == ny) {
             const size_t g = IX2(nx + 1, i, ny + 2);
-            if (!a.dbc) {
+            if (!dbc) {
                 a.Vx_o[g] = a.fs_t ? vx : (a.ns_t ? -vx : (nzero ? 0.0 : a.Vx_i[g]));
                 if (Uxw) Uxw[g] = a.Vx_i[g] * a.dt;
             } else {
@@ -341,15 +344,15 @@ __global__ void __launch_bounds__(TX * TYT) k_stokes2d(const __grid_constant__ K
             } else
                 vy = Vy0 + (-dP + dt_yy + dt_xy - avf) * a.edt / ave;
         } else
-            vy = (!a.dbc && ((j == 1) ? a.ns_b : a.ns_t)) ? 0.0 : a.Vy_i[e];
+            vy = (!dbc && ((j == 1) ? a.ns_b : a.ns_t)) ? 0.0 : a.Vy_i[e];
         a.Vy_o[e] = vy;
         double *const Uyw = INC ? a.Uy_o : ((DIAG && a.Uy) ? a.Uy : nullptr);
         const bool nzero = (j == 1 && a.ns_b) || (j == ny + 1 && a.ns_t);
-        const double uy = (a.dbc && nzero) ? 0.0 : ((j >= 2 && j <= ny) ? vy : a.Vy_i[e]) * a.dt;
+        const double uy = (dbc && nzero) ? 0.0 : ((j >= 2 && j <= ny) ? vy : a.Vy_i[e]) * a.dt;
         if (Uyw) Uyw[e] = uy;
         if (i == 1) {
             const size_t g = IX2(nx + 2, 1, j);
-            if (!a.dbc) {
+            if (!dbc) {
                 a.Vy_o[g] = a.fs_l ? vy : (a.ns_l ? -vy : (nzero ? 0.0 : a.Vy_i[g]));
                 if (Uyw) Uyw[g] = a.Vy_i[g] * a.dt;
             } else {
@@ -359,7 +362,7 @@ __global__ void __launch_bounds__(TX * TYT) k_stokes2d(const __grid_constant__ K
         }
         if (i == nx) {
             const size_t g = IX2(nx + 2, nx + 2, j);
-            if (!a.dbc) {
+            if (!dbc) {
                 a.Vy_o[g] = a.fs_r ? vy : (a.ns_r ? -vy : (nzero ? 0.0 : a.Vy_i[g]));
                 if (Uyw) Uyw[g] = a.Vy_i[g] * a.dt;
             } else {
@@ -537,6 +540,7 @@ int jr_make_phase_tab(const jr_vc_inputs *vc, jr_phase_tab *out)
 enum { S_Vx, S_Vy, S_P, S_txx, S_tyy, S_txy, S_th, S_txyc, S_lam, S_lamv, S_eta, S_etav, S_Ux, S_Uy, S_COUNT };
 struct Plan2 {
     bool vc, inc;   // inc: strain-increment form (the displacement joins the ping-pong state)
+    bool rare;      // any of the seldom-used options is on: the RARE kernel instantiations
     int nx, ny;
     size_t bytes[S_COUNT];
     double *set[2][S_COUNT];
@@ -565,8 +569,10 @@ static int k2_attr_both(int *nb)
     int st = k2_attr<VC, true, TYT>(nullptr);
     if (!st && VC) {   // the strain-increment instantiations share the tile choice of the ε form
         constexpr int smem = 16 * TX * TYT * 8;
-        JR_CUDA(cudaFuncSetAttribute(k_stokes2d<true, true, TYT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        JR_CUDA(cudaFuncSetAttribute(k_stokes2d<true, false, TYT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        JR_CUDA(cudaFuncSetAttribute(k_stokes2d<true, true, TYT, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        JR_CUDA(cudaFuncSetAttribute(k_stokes2d<true, false, TYT, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        JR_CUDA(cudaFuncSetAttribute(k_stokes2d<true, true, TYT, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        JR_CUDA(cudaFuncSetAttribute(k_stokes2d<true, false, TYT, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     }
     return st ? st : k2_attr<VC, false, TYT>(nb);
 }
@@ -690,6 +696,7 @@ static int plan2_begin(jr_context *ctx, const jr_fields *s, const jr_stokes_opts
         if ((st = jr_make_phase_tab(in, &p->pt))) return st;
         k.ph_c = in->ph_center; k.ph_v = in->ph_vertex;
     }
+    p->rare = vc && (p->inc || k.dbc || k.dTargs != nullptr || p->pt.any_soft);
     if ((st = plan2_tile(ctx, p))) return st;
     return JR_OK;
 }
@@ -711,8 +718,11 @@ static int plan2_iter(jr_context *ctx, Plan2 *p, int64_t it, bool diag)
 #define X(T_)                                                                                              \
     if (ty == T_) {                                                                                        \
         if (p->inc) {                                                                                      \
-            if (diag) k_stokes2d<true, true, T_, true><<<grd, blk, smem, ctx->stream>>>(k, p->pt);         \
-            else k_stokes2d<true, false, T_, true><<<grd, blk, smem, ctx->stream>>>(k, p->pt);             \
+            if (diag) k_stokes2d<true, true, T_, true, true><<<grd, blk, smem, ctx->stream>>>(k, p->pt);   \
+            else k_stokes2d<true, false, T_, true, true><<<grd, blk, smem, ctx->stream>>>(k, p->pt);       \
+        } else if (p->vc && p->rare) {                                                                     \
+            if (diag) k_stokes2d<true, true, T_, false, true><<<grd, blk, smem, ctx->stream>>>(k, p->pt);  \
+            else k_stokes2d<true, false, T_, false, true><<<grd, blk, smem, ctx->stream>>>(k, p->pt);      \
         } else if (p->vc) {                                                                                \
             if (diag) k_stokes2d<true, true, T_><<<grd, blk, smem, ctx->stream>>>(k, p->pt);               \
             else k_stokes2d<true, false, T_><<<grd, blk, smem, ctx->stream>>>(k, p->pt);                   \
