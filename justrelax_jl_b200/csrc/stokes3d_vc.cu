@@ -65,7 +65,7 @@ __device__ __forceinline__ void jr_prefetch_l2(const double *p) { asm volatile("
 #ifndef JR_PREP_MINB
 #define JR_PREP_MINB 4
 #endif
-template <bool DIAG, bool MAXLOC, int NP>
+template <bool DIAG, bool MAXLOC, int NP, bool DTF = false>
 __global__ void __launch_bounds__(256, JR_PREP_MINB) k_vc3_prep(const __grid_constant__ V3 a, const __grid_constant__ jr_phase_tab pt)
 {
     const int nx = a.nx, ny = a.ny, nz = a.nz;
@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(256, JR_PREP_MINB) k_vc3_prep(const __grid_con
     for (int p = 0; p < NP; p++)
         if (p < pt.n) { Kc += (r[p] == 0.0) ? 0.0 : pt.Kb[p] * r[p]; Gc += (r[p] == 0.0) ? 0.0 : pt.G[p] * r[p]; }
     double RP, th = th_in;
-    if (a.dTargs) {  // args.ΔT given: thermal-stress form, α = fn_ratio(get_thermal_expansion, …)  PressureKernels.jl:128-149
+    if (DTF) {  // args.ΔT given (instantiated separately): thermal-stress form, α = fn_ratio(get_thermal_expansion, …)  PressureKernels.jl:128-149
         double al = 0.0;
 #pragma unroll
         for (int p = 0; p < NP; p++)
@@ -911,6 +911,11 @@ static int pre_VC3(jr_context *ctx, const jr_fields *s, const jr_stokes_opts *o,
 template <int NP>
 static void launch_prep_np(bool diag, bool maxloc, dim3 grd, cudaStream_t st, const V3 &k, const jr_phase_tab &pt)
 {
+    if (k.dTargs) {  // thermal-stress pressure form (args.ΔT): its own instantiations, the common path keeps its register budget
+        if (diag) { if (maxloc) k_vc3_prep<true, true, NP, true><<<grd, BLK3, 0, st>>>(k, pt); else k_vc3_prep<true, false, NP, true><<<grd, BLK3, 0, st>>>(k, pt); }
+        else { if (maxloc) k_vc3_prep<false, true, NP, true><<<grd, BLK3, 0, st>>>(k, pt); else k_vc3_prep<false, false, NP, true><<<grd, BLK3, 0, st>>>(k, pt); }
+        return;
+    }
     if (diag) { if (maxloc) k_vc3_prep<true, true, NP><<<grd, BLK3, 0, st>>>(k, pt); else k_vc3_prep<true, false, NP><<<grd, BLK3, 0, st>>>(k, pt); }
     else { if (maxloc) k_vc3_prep<false, true, NP><<<grd, BLK3, 0, st>>>(k, pt); else k_vc3_prep<false, false, NP><<<grd, BLK3, 0, st>>>(k, pt); }
 }
