@@ -101,7 +101,9 @@ typedef struct {
     int32_t strain_increment;       /* 2D-VC kwarg strain_increment = true: Δε form (Stokes2D.jl:659-730, StressKernels.jl:1147-1302) */
     int32_t displacement_bcs;       /* flow_bcs isa DisplacementBoundaryConditions (src/types/displacement.jl:62-70): V = U/dt before the
                                      * loop, flow_bcs! applied to U instead of V (2D-VC) */
-    int32_t _pad;
+    int32_t dT_ghosted;             /* args.ΔT has the extents ni.+2 (thermal.ΔT, as the reference's scripts pass it: test_thermalstresses.jl:321,
+                                     * Blob3D.jl:280) and is indexed ΔT[I...] WITHOUT an offset, exactly like compute_P_kernel! does
+                                     * (PressureKernels.jl:143-146: quirk — the low corner of the ghosted array); 0: extents ni */
 } jr_stokes_opts;
 
 typedef struct {

@@ -74,7 +74,7 @@ struct StokesOpts
     strain_rate_ni_only::Int32
     strain_increment::Int32          # 2D-VC kwarg strain_increment (Δε form)
     displacement_bcs::Int32          # flow_bcs isa DisplacementBoundaryConditions
-    _pad::Int32
+    dT_ghosted::Int32                # args.ΔT has extents ni.+2 (thermal.ΔT) and is indexed ΔT[I...] without offset, like the reference
 end
 
 # ---- jr_stokes_result (history arrays are HOST pointers) --------------------------------------------------------------

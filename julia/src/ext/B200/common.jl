@@ -145,13 +145,13 @@ function global_size(ni::NTuple{N}) where {N}
 end
 
 function stokes_opts(pt::JustRelax.PTStokesCoeffs, grid, dt, bcs, ni; iterMax = 10.0e3, nout = 500, viscosity_relaxation = 1.0e-2,
-                     λ_relaxation = 0.2, viscosity_cutoff = (-Inf, Inf), iterMin = 0, strain_increment = false, kw...)
+                     λ_relaxation = 0.2, viscosity_cutoff = (-Inf, Inf), iterMin = 0, strain_increment = false, dT_ghosted = false, kw...)
     _require_uniform(grid)
     return API.StokesOpts(
         pt.r, pt.θ_dτ, pt.ηdτ, pt.ϵ_rel, pt.ϵ_abs, API.tuple3(_inv_spacing(grid), 0.0), Float64(dt), Int64(floor(iterMax)), Int64(floor(nout)),
         global_size(ni), API.flags6(bcs.free_slip), API.flags6(bcs.no_slip), API.flags6(bcs.periodic),
         Float64(viscosity_relaxation), Float64(λ_relaxation), Float64(viscosity_cutoff[1]), Float64(viscosity_cutoff[2]), Int64(floor(iterMin)), Int32(0),
-        Int32(strain_increment === true), Int32(bcs isa JustRelax.DisplacementBoundaryConditions), Int32(0),
+        Int32(strain_increment === true), Int32(bcs isa JustRelax.DisplacementBoundaryConditions), Int32(dT_ghosted === true),
     )
 end
 
@@ -330,7 +330,10 @@ function solve_phases!(stokes, pt_stokes, grid, flow_bcs, ρg, phase_ratios, rhe
     ni = size(stokes.P)
     d = add_args!(add_ρg!(stokes_slots(stokes), ρg), args)
     f = API.Fields(ni, d)
-    opt = Ref(stokes_opts(pt_stokes, grid, dt, flow_bcs, ni; kw...))
+    ghosted = haskey(args, :ΔT) && args.ΔT !== nothing && size(args.ΔT) == ni .+ 2     # thermal.ΔT, as the reference's scripts pass it
+    (haskey(args, :ΔT) && args.ΔT !== nothing && !ghosted && size(args.ΔT) != ni) &&
+        throw(ArgumentError("args.ΔT must have the size of the cell grid $(ni) or of thermal.ΔT $(ni .+ 2)"))
+    opt = Ref(stokes_opts(pt_stokes, grid, dt, flow_bcs, ni; kw..., dT_ghosted = ghosted))
     fs = (ND == 2 && kw.free_surface !== false) ? Float64(dt) * Float64(kw.free_surface) : 0.0       # VelocityKernels.jl:134-180
     vc, keep = vc_inputs(rheology, phase_ratios; free_surface = fs)
     h = API.History(kw.iterMax, kw.nout)

@@ -81,7 +81,7 @@ class StokesOpts(C.Structure):
         ("viscosity_relaxation", C.c_double), ("lambda_relaxation", C.c_double),
         ("visc_cutoff_lo", C.c_double), ("visc_cutoff_hi", C.c_double),
         ("iterMin", C.c_int64),
-        ("strain_rate_ni_only", C.c_int32), ("strain_increment", C.c_int32), ("displacement_bcs", C.c_int32), ("_pad", C.c_int32),
+        ("strain_rate_ni_only", C.c_int32), ("strain_increment", C.c_int32), ("displacement_bcs", C.c_int32), ("dT_ghosted", C.c_int32),
     ]
 
 

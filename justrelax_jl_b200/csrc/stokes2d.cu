@@ -25,6 +25,7 @@ struct K2 {
     int nx, ny;
     double _dx, _dy, dt, r, th, edt, rel, nu, cut_lo, cut_hi;
     int fs_l, fs_r, fs_t, fs_b, ns_l, ns_r, ns_t, ns_b;
+    int dT_ghosted;   // args.ΔT is (ni.+2), indexed ΔT[i, j] without offset (the reference's compute_P_kernel!)
     int dbc;   // flow_bcs isa DisplacementBoundaryConditions: flow_bcs! acts on U = V·dt, V keeps its ghosts / boundary faces
     // strain-increment form (INC): the displacement is part of the ping-pong state (Δε of the next iteration reads it at neighbours)
     const double *Ux_i, *Uy_i;
@@ -106,7 +107,7 @@ __global__ void __launch_bounds__(TX * TYT) k_stokes2d(const __grid_constant__ K
         }
         // compute_P! with ητ (quirk Q5)  Stokes2D.jl:231-233, 664-677; PressureKernels.jl:186-195
         if (VC && RARE && a.dTargs)  // args.ΔT given: thermal-stress form  PressureKernels.jl:128-149,197-206
-            jr_compute_P_point_dT(RP, thn, a.P0[c], divV, a.Q[c], a.dTargs[c], jr_ratio_alpha(pt, a.ph_c, nc, c), ett, Kc, Gc, a.dt, a.r, a.th);
+            jr_compute_P_point_dT(RP, thn, a.P0[c], divV, a.Q[c], a.dTargs[a.dT_ghosted ? IX2(nx + 2, i, j) : c], jr_ratio_alpha(pt, a.ph_c, nc, c), ett, Kc, Gc, a.dt, a.r, a.th);
         else
             jr_compute_P_point(RP, thn, a.P0[c], divV, a.Q[c], ett, Kc, Gc, a.dt, a.r, a.th);
         if (INC) {  // compute_∇V!(∇U, U) + compute_strain_rate!(Δε, ∇U, U)  Stokes2D.jl:660-662, 681-689
@@ -685,6 +686,7 @@ static int plan2_begin(jr_context *ctx, const jr_fields *s, const jr_stokes_opts
     k.fs_l = o->free_slip[0]; k.fs_r = o->free_slip[1]; k.fs_t = o->free_slip[4]; k.fs_b = o->free_slip[5];
     k.ns_l = o->no_slip[0]; k.ns_r = o->no_slip[1]; k.ns_t = o->no_slip[4]; k.ns_b = o->no_slip[5];
     k.dbc = vc && o->displacement_bcs;
+    k.dT_ghosted = o->dT_ghosted;
     k.dxx = F(dxx); k.dyy = F(dyy); k.dxy = F(dxy); k.divU = F(divU);
     k.P0 = F(P0); k.Q = F(Q); k.K = F(K); k.G = F(G); k.etatau = F(etatau);
     k.txxo = F(txx_o); k.tyyo = F(tyy_o); k.txyo = F(txy_o); k.txyco = F(txy_o_c);

@@ -35,6 +35,7 @@ struct V3 {
     double *rgx, *rgy, *rgz;
     const double *T, *Pargs, *dTargs, *ph_c, *ph_xy, *ph_yz, *ph_xz;
     double *divV, *RP, *pxx, *pyy, *pzz, *pyz, *pxz, *pxy, *tII, *eta_vep, *e_vol_pl, *Rx, *Ry, *Rz;
+    int dT_ghosted;   // args.ΔT is (ni.+2), indexed ΔT[i, j, k] without offset (the reference's compute_P_kernel!)
     int pf_next;   // L2 prefetch of the next plane's operands (JRB200_VC3_PREFETCH, default on)
     int xfull_c, xfull_n;   // block columns with full 32-wide tiles for the cell (nx) and node (nx+1) lattices; a further block
                             // column, if launched, packs the few remainder columns densely (nx = 257: 1 cell / 2 node columns)
@@ -140,7 +141,7 @@ __global__ void __launch_bounds__(256, JR_PREP_MINB) k_vc3_prep(const __grid_con
 #pragma unroll
         for (int p = 0; p < NP; p++)
             if (p < pt.n) al += (r[p] == 0.0) ? 0.0 : (pt.rho_kind[p] == 0 ? 0.0 : pt.alpha[p]) * r[p];
-        jr_compute_P_point_dT(RP, th, P0c, divV, Qc, __ldg(a.dTargs + c), al, ett, Kc, Gc, a.dt, a.r, a.th);
+        jr_compute_P_point_dT(RP, th, P0c, divV, Qc, __ldg(a.dTargs + (a.dT_ghosted ? IX3(nx + 2, ny + 2, i, j, k) : c)), al, ett, Kc, Gc, a.dt, a.r, a.th);
     } else
         jr_compute_P_point(RP, th, P0c, divV, Qc, ett, Kc, Gc, a.dt, a.r, a.th);
     a.theta[c] = th;
@@ -881,7 +882,7 @@ static int plan3_begin(jr_context *ctx, const jr_fields *s, const jr_stokes_opts
     k.oxx = F(txx_o); k.oyy = F(tyy_o); k.ozz = F(tzz_o); k.oyz = F(tyz_o); k.oxz = F(txz_o); k.oxy = F(txy_o);
     k.oyzc = F(tyz_o_c); k.oxzc = F(txz_o_c); k.oxyc = F(txy_o_c);
     k.lam = (double *)(B + o_lam); k.lamyz = (double *)(B + o_lyz); k.lamxz = (double *)(B + o_lxz); k.lamxy = (double *)(B + o_lxy);
-    k.rgx = F(rhogx); k.rgy = F(rhogy); k.rgz = F(rhogz); k.T = F(T); k.Pargs = F(Pargs); k.dTargs = F(dTargs);
+    k.rgx = F(rhogx); k.rgy = F(rhogy); k.rgz = F(rhogz); k.T = F(T); k.Pargs = F(Pargs); k.dTargs = F(dTargs); k.dT_ghosted = o->dT_ghosted;
     k.ph_c = in->ph_center; k.ph_xy = in->ph_xy; k.ph_yz = in->ph_yz; k.ph_xz = in->ph_xz;
     k.divV = F(divV); k.RP = F(RP); k.pxx = F(pxx); k.pyy = F(pyy); k.pzz = F(pzz); k.pyz = F(pyz); k.pxz = F(pxz); k.pxy = F(pxy);
     k.tII = F(tII); k.eta_vep = F(eta_vep); k.e_vol_pl = F(e_vol_pl); k.Rx = F(Rx); k.Ry = F(Ry); k.Rz = F(Rz);

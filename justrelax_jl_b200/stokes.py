@@ -440,9 +440,16 @@ def vc_slots(stokes, ρg, args) -> dict:
         if not is_device_array(v):
             raise ValueError(f"args.{k} must be a B200 array (use PTArray(B200Backend)(x))")
         d[known[k]] = v
-    if "dTargs" in d and tuple(d["dTargs"].shape) != tuple(stokes.ni):
-        raise ValueError(f"args.ΔT must live at the cell centres, size {tuple(stokes.ni)} (got {tuple(d['dTargs'].shape)})")
+    if "dTargs" in d and tuple(d["dTargs"].shape) not in (tuple(stokes.ni), tuple(n + 2 for n in stokes.ni)):
+        raise ValueError(f"args.ΔT must have the size of the cell grid {tuple(stokes.ni)} or of thermal.ΔT (ni .+ 2), got {tuple(d['dTargs'].shape)}")
     return d
+
+
+def _dT_ghosted(stokes, slots) -> bool:
+    """args.ΔT given as thermal.ΔT (ni .+ 2), the way the reference's scripts pass it (test_thermalstresses.jl:321, Blob3D.jl:280): the kernel
+    then indexes it ΔT[I...] without an offset, exactly like compute_P_kernel! (PressureKernels.jl:143-146)"""
+    a = slots.get("dTargs")
+    return a is not None and tuple(a.shape) == tuple(n + 2 for n in stokes.ni)
 
 
 def _vc_opts(stokes, pt_stokes, grid, flow_bcs, dt, igg, kw):
@@ -462,7 +469,9 @@ def _solve2d_VC(stokes, pt_stokes, di, flow_bcs, ρg, phase_ratios, rheology, ar
     grid = _grid_of(stokes, di, igg)
     opts = _vc_opts(stokes, pt_stokes, grid, flow_bcs, dt, igg, kw)
     vc = vc_inputs(rheology, phase_ratios, free_surface=float(dt) * float(kw["free_surface"]) if kw["free_surface"] else 0.0)
-    fs = build_fields(vc_slots(stokes, ρg, args), stokes.ni)
+    slots = vc_slots(stokes, ρg, args)
+    opts.dT_ghosted = int(_dT_ghosted(stokes, slots))
+    fs = build_fields(slots, stokes.ni)
     hist = _Hist(int(opts.iterMax // max(opts.nout, 1)) + 3, _abi.StokesResult)
     st = _abi.lib().jr_stokes2d_solve_VC(context(), C.byref(fs), C.byref(opts), C.byref(vc), C.byref(hist.res))
     if st == _abi.JR_ERR_NAN:
@@ -484,7 +493,9 @@ def iterate2d_VC_(stokes, pt_stokes, di, flow_bcs, ρg, phase_ratios, rheology, 
     grid = _grid_of(stokes, di, igg)
     opts = _vc_opts(stokes, pt_stokes, grid, flow_bcs, dt, igg, kw)
     vc = vc_inputs(rheology, phase_ratios, free_surface=float(dt) * float(kw["free_surface"]) if kw["free_surface"] else 0.0)
-    fs = build_fields(vc_slots(stokes, ρg, args), stokes.ni)
+    slots = vc_slots(stokes, ρg, args)
+    opts.dT_ghosted = int(_dT_ghosted(stokes, slots))
+    fs = build_fields(slots, stokes.ni)
     res = _abi.StokesResult()
     _abi.check(_abi.lib().jr_stokes2d_iterate_VC(context(), C.byref(fs), C.byref(opts), C.byref(vc), int(niter), int(finish), C.byref(res)))
     return SimpleNamespace(iter=int(res.iter), time=float(res.time_s), kernel_launches=int(res.kernel_launches))

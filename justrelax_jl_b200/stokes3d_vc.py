@@ -13,7 +13,7 @@ from types import SimpleNamespace
 from typing import Optional
 
 from . import _abi
-from .stokes import (_Hist, _common_checks, _grid_of, _vc_opts, build_fields, context, vc_inputs, vc_slots)
+from .stokes import (_Hist, _common_checks, _dT_ghosted, _grid_of, _vc_opts, build_fields, context, vc_inputs, vc_slots)
 from .types import IGG, data_ptr
 
 
@@ -27,7 +27,9 @@ def solve3d_VC_(stokes, pt_stokes, grid, flow_bcs, ρg, phase_ratios, rheology, 
     grid = _grid_of(stokes, grid, igg)
     opts = _vc_opts(stokes, pt_stokes, grid, flow_bcs, dt, igg, kw)
     vc = vc_inputs(rheology, phase_ratios, ndim=3)
-    fs = build_fields(vc_slots(stokes, ρg, args), stokes.ni)
+    slots = vc_slots(stokes, ρg, args)
+    opts.dT_ghosted = int(_dT_ghosted(stokes, slots))
+    fs = build_fields(slots, stokes.ni)
     hist = _Hist(int(opts.iterMax // max(opts.nout, 1)) + 3, _abi.StokesResult)
     st = _abi.lib().jr_stokes3d_solve_VC(context(), C.byref(fs), C.byref(opts), C.byref(vc), C.byref(hist.res))
     if st == _abi.JR_ERR_NAN:
@@ -50,7 +52,9 @@ def iterate3d_VC_(stokes, pt_stokes, grid, flow_bcs, ρg, phase_ratios, rheology
     grid = _grid_of(stokes, grid, igg)
     opts = _vc_opts(stokes, pt_stokes, grid, flow_bcs, dt, igg, kw)
     vc = vc_inputs(rheology, phase_ratios, ndim=3)
-    fs = build_fields(vc_slots(stokes, ρg, args), stokes.ni)
+    slots = vc_slots(stokes, ρg, args)
+    opts.dT_ghosted = int(_dT_ghosted(stokes, slots))
+    fs = build_fields(slots, stokes.ni)
     res = _abi.StokesResult()
     _abi.check(_abi.lib().jr_stokes3d_iterate_VC(context(), C.byref(fs), C.byref(opts), C.byref(vc), int(niter), int(finish), C.byref(res)))
     return SimpleNamespace(iter=int(res.iter), time=float(res.time_s), kernel_launches=int(res.kernel_launches))

@@ -84,7 +84,7 @@ typedef struct {
     int32_t strain_rate_ni_only;  /* Q20: 3D-VC launches strain rate over ni */
     int32_t strain_increment;     /* 2D-VC kwarg strain_increment: Δε form (Stokes2D.jl:659-730, StressKernels.jl:1147-1302) */
     int32_t displacement_bcs;     /* flow_bcs isa DisplacementBoundaryConditions: V = U/dt before the loop, BCs applied to U */
-    int32_t _pad;
+    int32_t dT_ghosted;           /* args.ΔT is (ni.+2) and indexed ΔT[I...] without offset, as compute_P_kernel! does (quirk) */
 } orc_stokes_opts;
 
 typedef struct {

@@ -143,7 +143,7 @@ class StokesOpts(C.Structure):
         ("viscosity_relaxation", C.c_double), ("lambda_relaxation", C.c_double),
         ("visc_cutoff_lo", C.c_double), ("visc_cutoff_hi", C.c_double),
         ("iterMin", C.c_int64), ("strain_rate_ni_only", C.c_int32), ("strain_increment", C.c_int32), ("displacement_bcs", C.c_int32),
-        ("_pad", C.c_int32),
+        ("dT_ghosted", C.c_int32),
     ]
 
 
@@ -157,7 +157,7 @@ class StokesResult(C.Structure):
 
 
 def make_opts(pt, _di, dt, flags: dict, n_g, *, iterMax, nout, viscosity_relaxation=1e-2, lambda_relaxation=0.2,
-              viscosity_cutoff=(-np.inf, np.inf), iterMin=100, strain_rate_ni_only=0, strain_increment=0, displacement_bcs=0):
+              viscosity_cutoff=(-np.inf, np.inf), iterMin=100, strain_rate_ni_only=0, strain_increment=0, displacement_bcs=0, dT_ghosted=0):
     """pt: object with r, θ_dτ, ηdτ, ϵ_rel, ϵ_abs; flags: dict(free_slip=[6], no_slip=[6], periodic=[6])."""
     o = StokesOpts()
     o.r, o.theta_dtau, o.eta_dtau, o.eps_rel, o.eps_abs = pt.r, pt.θ_dτ, pt.ηdτ, pt.ϵ_rel, pt.ϵ_abs
@@ -173,7 +173,7 @@ def make_opts(pt, _di, dt, flags: dict, n_g, *, iterMax, nout, viscosity_relaxat
     o.viscosity_relaxation, o.lambda_relaxation = viscosity_relaxation, lambda_relaxation
     o.visc_cutoff_lo, o.visc_cutoff_hi = viscosity_cutoff
     o.iterMin, o.strain_rate_ni_only = int(iterMin), int(strain_rate_ni_only)
-    o.strain_increment, o.displacement_bcs = int(strain_increment), int(displacement_bcs)
+    o.strain_increment, o.displacement_bcs, o.dT_ghosted = int(strain_increment), int(displacement_bcs), int(dT_ghosted)
     return o
 
 

@@ -247,7 +247,7 @@ void orc_vc3_P(const orc_fields *s, const orc_stokes_opts *o, const orc_vc_input
     for (size_t c = 0; c < nc; c++) { /* compute_P!(θ, P0, RP, ∇V, Q, ητ, rheology, phase_ratios, …)  :518-531 */
         const double K = ratio_Kb(vc, vc->ph_center, nc, c), G = ratio_G(vc, vc->ph_center, nc, c);
         if (F(dTargs)) /* args.ΔT given: compute_P_kernel!(…, ΔT, ::Nothing)  PressureKernels.jl:128-149 */
-            P_point_dT(&F(RP)[c], &theta[c], F(P0)[c], F(divV)[c], F(Q)[c], F(dTargs)[c], ratio_alpha(vc, vc->ph_center, nc, c), F(etatau)[c], K, G,
+            P_point_dT(&F(RP)[c], &theta[c], F(P0)[c], F(divV)[c], F(Q)[c], F(dTargs)[o->dT_ghosted ? IX3(s->n[0] + 2, s->n[1] + 2, c % s->n[0] + 1, (c / s->n[0]) % s->n[1] + 1, c / ((size_t)s->n[0] * s->n[1]) + 1) : c], ratio_alpha(vc, vc->ph_center, nc, c), F(etatau)[c], K, G,
                        o->dt, o->r, o->theta_dtau);
         else
             P_point(&F(RP)[c], &theta[c], F(P0)[c], F(divV)[c], F(Q)[c], F(etatau)[c], K, G, o->dt, o->r, o->theta_dtau);

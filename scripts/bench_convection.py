@@ -46,10 +46,17 @@ def main():
     th = ThermalArrays(B200Backend, n, n, n)
     th.T.copy_(dev(s.T)); th.Told.copy_(th.T)
     pr = PhaseRatios.from_arrays(B200Backend, **s.ratios)
-    a = dict(T=th.T, P=st.P)
+    # args as the miniapp passes them (Blob3D.jl:280): ΔT = thermal.ΔT (ni .+ 2) switches compute_P! to the thermal-stress form
+    a = dict(T=th.T, P=st.P, dt=s.dt, ΔT=th.ΔT)
     z = lambda: dev(np.zeros(s.ni, order="F"))
     ρg = (z(), z(), z())
     jst.flow_bcs_(st, s.flow_bcs)
+    # lithostatic initial pressure from the buoyancy force (Blob3D.jl:296-299: compute_ρg! + init_P!, five fixed-point passes), on the GPU
+    for _ in range(5):
+        jst.compute_ρg_(ρg, pr, s.rheology, dict(T=th.T, P=st.P), st)
+        jst.compute_lithostatic_pressure_(st.P, ρg[2], float(s.di[2]), igg if world > 1 else None)
+    from justrelax_jl_b200 import zeros
+    Vv = [zeros(B200Backend, n + 1, n + 1, n + 1) for _ in range(3)]
     pt_th = jth.PTThermalCoeffs(B200Backend, s.rheology, pr, a, s.dt, s.ni, s.di, s.li, ϵ=1e-5, CFL=s.thermal_CFL)
     kw_s = dict(viscosity_cutoff=s.kwargs["viscosity_cutoff"])
     kw_t = dict(phase=pr, verbose=False, igg=igg)
@@ -64,7 +71,13 @@ def main():
         jst.compute_ρg_(ρg, pr, s.rheology, a, st)
         jst.compute_viscosity_(st, pr, a, s.rheology, s.kwargs["viscosity_cutoff"])
         rs = iterate3d_VC_(st, s.pt_stokes, s.grid, s.flow_bcs, ρg, pr, s.rheology, a, s.dt, args.stokes_iters, igg, finish=True, kwargs=kw_s)
-        rt = jth.thermal_iterate_(th, pt_th, s.thermal_bc, s.rheology, a, s.dt, s.grid, args.thermal_iters, kwargs=kw_t)
+        # between the solves, still on the GPU: τII/εII, time step, shear heating (Χ = 0 for this setup: the call is what is timed),
+        # vertex velocities for the advection step
+        jst.tensor_invariant_(st.ε, s.ni)
+        jst.compute_dt_(st, s.di, math.inf, igg if world > 1 else None)
+        jst.compute_shear_heating_(th, st, pr, s.rheology, s.dt)
+        jst.velocity2vertex_(Vv, (st.V.Vx, st.V.Vy, st.V.Vz), s.ni)
+        rt = jth.thermal_iterate_(th, pt_th, s.thermal_bc, s.rheology, dict(T=th.T, P=st.P), s.dt, s.grid, args.thermal_iters, kwargs=kw_t)
         return rs, rt
 
     step()

@@ -148,7 +148,7 @@ def _run_vc(oracle, ni, f, grid, pt, dt, rat, rheo, flags, niter, finish, free_s
     rows = R.lower_stokes(rheo)
     vc = oracle.vc_inputs(rows, R.gravity_of(rheo), rat, free_surface=dt if free_surface else 0.0)
     opts = oracle.make_opts(pt, grid._di.center, dt, flags, ni, iterMax=niter, nout=niter, viscosity_relaxation=0.3, lambda_relaxation=0.2,
-                            strain_increment=int(inc), displacement_bcs=int(dbc))
+                            strain_increment=int(inc), displacement_bcs=int(dbc), dT_ghosted=int(dT is not None and dT.shape != tuple(ni)))
     oracle.iterate2d_VC(d, ni, opts, vc, niter, finish=finish)
     pr = PhaseRatios.from_arrays(B200Backend, **rat)
     args = dict(T=extra["T"], P=st.P if alias_P else extra["Pargs"])
@@ -181,6 +181,9 @@ def test_vc_thermal_stress_pressure_form(oracle):
     for niter in (1, 4):
         st, d = _run_vc(oracle, ni, f, grid, pt, dt, rat, rheo, flags, niter, False, alias_P=True, dT=dT)
         compare_slots(st, d, VC_STATE + VC_DIAG, TOL, f"2D-VC with ΔT niter={niter}")
+    dTg = np.asfortranarray(np.random.default_rng(7).uniform(-2.0e3, 2.0e3, size=tuple(n + 2 for n in ni)))   # thermal.ΔT (ni .+ 2)
+    stg, dg = _run_vc(oracle, ni, f, grid, pt, dt, rat, rheo, flags, 4, False, alias_P=True, dT=dTg)
+    compare_slots(stg, dg, VC_STATE + VC_DIAG, TOL, "2D-VC with ghosted ΔT")
     st0, d0 = _run_vc(oracle, ni, f, grid, pt, dt, rat, rheo, flags, 4, False, alias_P=True)
     assert max_rel_diff(to_host(st["P"]), d0["P"]) > 1e-4, "ΔT must change the pressure"
 
