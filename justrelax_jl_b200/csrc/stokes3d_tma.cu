@@ -79,6 +79,22 @@ __device__ __forceinline__ void jr_push_v(const PushArgs &pu, int nrm, int gi, i
     }
 }
 
+// TRAIL: flow_bcs! inside the iteration launch, OFF the critical path.  The persistent grid gets `ntrail` extra CTAs (the CTA slots the
+// column tiles leave free: 296 − 288 at 255^3) that trail the z-march: main CTA c publishes the number of z-steps whose stores are
+// complete in done[c]; the trailing CTAs poll the minimum and fill, plane group by plane group, the "ring" of every velocity plane
+// (elements whose x or y index is a ghost / boundary-normal one) with the same gather as k_bc_box3.  The interior of the two z ghost
+// planes and of the z boundary-normal faces is written by the thread that holds its source, in the first / last z-steps (CTA-uniform
+// branches).  One launch per iteration instead of two, and the boundary work overlaps the z-march.
+struct TrailArgs {
+    unsigned long long *done;        // [main CTAs] done_base + complete z-steps of this launch
+    unsigned long long done_base;
+    const double *in;                // in-set base (generic loads of values no boundary condition touches)
+    int ntrail;                      // trailing CTAs = gridDim.x − main CTAs
+    int nb, nb_tail, tail_planes;    // plane groups per batch far from / within tail_planes of the end of the z-march
+    int sig_every;                   // main CTAs publish every sig_every-th step
+    int fs_lo[3], fs_hi[3], ns_lo[3], ns_hi[3];  // per dimension and side: free-slip / no-slip active (k_bc_box3's flags)
+};
+
 struct alignas(64) VaArgs {
     CUtensorMap mS5, mC1, mC4, mD1, mD2, mD7;  // in-state set (5-array boxes), const set, finite-dt set
     double *out;                               // out-state set base
@@ -107,6 +123,7 @@ struct alignas(64) VaArgs {
     // on one of this rank's send planes is stored a second (… eighth) time straight into the ghost planes of the neighbours'
     // out-sets over the CUDA-IPC mapping, as it is produced — the transfer rides on NVLink under the z-march.
     PushArgs push;
+    TrailArgs tr;
 };
 
 #define TXW 30  // owned columns per tile
@@ -121,6 +138,122 @@ __device__ __forceinline__ bool jr_elect_one()
     return pred != 0;
 }
 
+
+// ---- the trailing CTAs of a TRAIL launch (see TrailArgs) -------------------------------------------------------------------------
+// ring of plane K of velocity component q (extents n0 × n1 in x, y): the two x-rows first (coalesced), then the column pairs
+__device__ __forceinline__ void jr_ring_decode(int r, int n0, int n1, int &c0, int &c1)
+{
+    if (r < n0) { c0 = r; c1 = 0; }
+    else if (r < 2 * n0) { c0 = r - n0; c1 = n1 - 1; }
+    else { const int t = r - 2 * n0; c1 = 1 + (t >> 1); c0 = (t & 1) ? n0 - 1 : 0; }
+}
+// flow_bcs! value of element c of component q: the gather of k_bc_box3 (no_slip! → free_slip! as complete sweeps; every ghost value from
+// its fully clamped source with the product of the per-dimension signs).  Returns the out-set offsets of the element and of its source.
+__device__ __forceinline__ void jr_trail_gather(const VaArgs &a, int q, const int c[3], size_t &ic, size_t &is, double &sign, bool &zero,
+                                                bool &computed)
+{
+    const int nc[3] = {a.nx, a.ny, a.nz};
+    int n[3], s[3];
+#pragma unroll
+    for (int e = 0; e < 3; e++) { n[e] = nc[e] + (e == q ? 1 : 2); s[e] = c[e]; }
+    sign = 1.0; zero = false;
+#pragma unroll
+    for (int e = 0; e < 3; e++) {
+        const bool lo_e = c[e] == 0, hi_e = c[e] == n[e] - 1;
+        if (!lo_e && !hi_e) continue;
+        const bool fsl = lo_e ? a.tr.fs_lo[e] : a.tr.fs_hi[e], nsl = lo_e ? a.tr.ns_lo[e] : a.tr.ns_hi[e];
+        if (e == q) {
+            if (nsl) zero = true;
+        } else if (fsl || nsl) {
+            s[e] = lo_e ? 1 : n[e] - 2;
+            if (!fsl) sign = -sign;
+        }
+    }
+    computed = true;
+#pragma unroll
+    for (int e = 0; e < 3; e++) computed = computed && s[e] >= 1 && s[e] <= n[e] - 2;
+    const size_t pxy = (size_t)a.PX * a.PY;
+    const int ox = q == 0, oy = q == 1, oz = q == 2;
+    ic = ((size_t)(c[2] + oz) * S_N + (S_Vx + q)) * pxy + (size_t)(c[1] + oy) * a.PX + (c[0] + ox);
+    is = ((size_t)(s[2] + oz) * S_N + (S_Vx + q)) * pxy + (size_t)(s[1] + oy) * a.PX + (s[0] + ox);
+}
+
+#define TRAIL_UNROLL 8
+// Latency is the trailing CTAs' only cost (a poll and two dependent memory round trips per batch, on a memory system the z-march keeps
+// saturated), so a thread owns ring POSITIONS and takes all planes of a batch at once: TRAIL_UNROLL independent gathers in flight.
+// Batches are a.tr.nb plane groups while the z-march is far from its end and a.tr.nb_tail near it (the last batch — the groups
+// that wait for the final z-step — is what the launch pays on top of the z-march).
+template <int NTHREADS>
+__device__ __noinline__ void jr_va_trailer(const VaArgs &a, int t, int tid)
+{
+    __shared__ unsigned long long s_min[NTHREADS / 32];
+    const int nx = a.nx, ny = a.ny, nz = a.nz;
+    const int Gm = (int)gridDim.x - a.tr.ntrail;
+    const int R0 = 2 * (nx + 1) + 2 * ny, R1 = 2 * (nx + 2) + 2 * (ny - 1), R2 = 2 * (nx + 2) + 2 * ny;
+    const int per = R0 + R1 + R2;
+    const int nZ = nz + 2;  // plane groups: box planes Z = 0 … nz+1 (Vx, Vy: K = Z; Vz: K = Z − 1)
+    double *const outset = a.out;
+    const int stride = a.tr.ntrail * NTHREADS;
+    for (int z0 = 0; z0 < nZ;) {
+        // groups nz and nz+1 gather from plane nz (the final z-step): they form the last batch
+        int z1 = z0 + (z0 + a.tr.nb + a.tr.tail_planes <= nZ ? a.tr.nb : a.tr.nb_tail);
+        if (z1 > nZ - 2 && z0 < nZ - 2) z1 = nZ - 2;
+        if (z1 > nZ) z1 = nZ;
+        // box plane Z is stored in z-step Z + 1 (Z = 1 … nz); group 0 gathers from plane 1, group nz+1 from plane nz
+        const int zs = min(max(z1 - 1, 1), nz);
+        const unsigned long long need = a.tr.done_base + (unsigned long long)(zs + 2);
+        for (;;) {
+            unsigned long long m = ~0ull;
+            for (int c = tid; c < Gm; c += NTHREADS) {
+                unsigned long long v;
+                asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(a.tr.done + c) : "memory");
+                m = v < m ? v : m;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const unsigned long long w = __shfl_xor_sync(0xffffffffu, m, o);
+                m = w < m ? w : m;
+            }
+            if ((tid & 31) == 0) s_min[tid >> 5] = m;
+            __syncthreads();
+#pragma unroll
+            for (int w = 0; w < NTHREADS / 32; w++) m = s_min[w] < m ? s_min[w] : m;
+            __syncthreads();
+            if (m >= need) break;
+            __nanosleep(100);
+        }
+        __threadfence();  // acquire: the main CTAs' stores behind the published step counts are visible now
+        for (int r0 = t * NTHREADS + tid; r0 < per; r0 += stride) {
+            int q, c[3];
+            if (r0 < R0) { q = 0; jr_ring_decode(r0, nx + 1, ny + 2, c[0], c[1]); }
+            else if (r0 < R0 + R1) { q = 1; jr_ring_decode(r0 - R0, nx + 2, ny + 1, c[0], c[1]); }
+            else { q = 2; jr_ring_decode(r0 - R0 - R1, nx + 2, ny + 2, c[0], c[1]); }
+            const int oz = q == 2 ? 1 : 0;
+            for (int zb = z0; zb < z1; zb += TRAIL_UNROLL) {
+                size_t ic[TRAIL_UNROLL], is[TRAIL_UNROLL];
+                double sg[TRAIL_UNROLL], val[TRAIL_UNROLL];
+                bool ok[TRAIL_UNROLL], zero[TRAIL_UNROLL], comp[TRAIL_UNROLL];
+#pragma unroll
+                for (int u = 0; u < TRAIL_UNROLL; u++) {
+                    c[2] = zb + u - oz;
+                    ok[u] = zb + u < z1 && c[2] >= 0;  // Vz has no plane below box plane 1
+                    ic[u] = is[u] = 0; sg[u] = 1.0; zero[u] = true; comp[u] = false;
+                    if (ok[u]) jr_trail_gather(a, q, c, ic[u], is[u], sg[u], zero[u], comp[u]);
+                }
+#pragma unroll
+                for (int u = 0; u < TRAIL_UNROLL; u++) {
+                    val[u] = 0.0;
+                    if (ok[u] && !zero[u]) val[u] = comp[u] ? __ldcg(outset + is[u]) : __ldg(a.tr.in + is[u]);
+                }
+#pragma unroll
+                for (int u = 0; u < TRAIL_UNROLL; u++)
+                    if (ok[u]) outset[ic[u]] = zero[u] ? 0.0 : sg[u] * val[u];
+            }
+        }
+        z0 = z1;
+    }
+}
+
 // Persistent kernel.  grid = min(resident CTA slots, work items), launched cooperatively so that every CTA is
 // resident.  Work item = (column tile, z-chunk), numbered z-chunk-major / y / x-fastest; CTA c takes items
 // c, c+G, c+2G, …; every item is kchunk+2 z-steps (step 0 fills the register queue, step 1 is the warm-up plane).
@@ -133,7 +266,7 @@ __device__ __forceinline__ bool jr_elect_one()
 //   MULTI: the launch runs a.niter iterations (ping-pong S_in ↔ S_out, a grid-wide barrier with generic→async proxy
 //       fences between them) and applies flow_bcs! itself: every thread that holds the source of a ghost / boundary
 //       value (no_slip! → free_slip! as complete sweeps, same gather as k_bc_box3) also stores its images.
-template <int BY, bool FINITE_DT, bool DIAG, int NST, bool RHOG, bool MULTI, bool PUSH = false>
+template <int BY, bool FINITE_DT, bool DIAG, int NST, bool RHOG, bool MULTI, bool PUSH = false, bool TRAIL = false>
 __global__ void __launch_bounds__(32 * BY, (BY <= 8 ? (FINITE_DT ? 2 : JR_VA_MINB8) : BY <= 10 ? 2 : 1)) k_va_tma(const __grid_constant__ VaArgs a)
 {
     using M = SlotMap<FINITE_DT, RHOG>;
@@ -147,7 +280,11 @@ __global__ void __launch_bounds__(32 * BY, (BY <= 8 ? (FINITE_DT ? 2 : JR_VA_MIN
 
     const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 32 + tx;
     const int nx = a.nx, ny = a.ny, nz = a.nz;
-    const int G = gridDim.x, cta = blockIdx.x;
+    const int G = TRAIL ? (int)gridDim.x - a.tr.ntrail : (int)gridDim.x, cta = blockIdx.x;
+    if (TRAIL && cta >= G) {
+        jr_va_trailer<32 * BY>(a, cta - G, tid);
+        return;
+    }
     const int nstep = a.kchunk + 2;
     const int ntile = a.ntx * a.nty, nitem = ntile * a.nchunk;
     const int my_rounds = cta < nitem ? (nitem - cta + G - 1) / G : 0;
@@ -411,6 +548,13 @@ __global__ void __launch_bounds__(32 * BY, (BY <= 8 ? (FINITE_DT ? 2 : JR_VA_MIN
                     }
                 }
                 __syncwarp();
+            } else if (TRAIL && ty == BY - 1) {
+                // northern halo warp (no store work): every thread of the CTA has issued the stores of the steps before this barrier —
+                // publish their count for the trailing CTAs (release: fence, then the flag)
+                if (tx == 0 && l >= 1 && (l % a.tr.sig_every) == 0) {
+                    __threadfence();
+                    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(a.tr.done + cta), "l"(a.tr.done_base + (unsigned long long)l) : "memory");
+                }
             } else if (ty == BY - 1 && a.stagger_ns >= 0) {
                 // second half of the step's loads, from the northern halo warp (it has no store work either), a little later:
                 // the grid runs in lock-step, so issuing everything at the barrier makes the whole GPU's requests arrive in bursts
@@ -437,6 +581,14 @@ __global__ void __launch_bounds__(32 * BY, (BY <= 8 ? (FINITE_DT ? 2 : JR_VA_MIN
                 const bool bz = MULTI && (bxy || mz != 0);
 #define JR_MX (gi == 0 ? -1 : (gi == nx - 1 ? 1 : 0))
 #define JR_MY (gj == 0 ? -1 : (gj == ny - 1 ? 1 : 0))
+                // TRAIL: flow_bcs! on the two z faces for the elements whose source this thread holds (the x / y interior of the planes;
+                // their rings belong to the trailing CTAs).  Tangential ghost planes Z = 0 / nz+1: ± the new interior value (free slip /
+                // no slip) or, without a boundary condition on that side, the in-value; normal faces Vz(K = 0 / nz): 0 or the in-value.
+                const bool zlo_bc = TRAIL && (a.tr.fs_lo[2] | a.tr.ns_lo[2]), zhi_bc = TRAIL && (a.tr.fs_hi[2] | a.tr.ns_hi[2]);
+                if (TRAIL && k == -1 && !zlo_bc) {
+                    if (stVx) jr_st_hint(&po[S_Vx * pxy], vx0, pst);
+                    if (stVy) jr_st_hint(&po[S_Vy * pxy], vy0, pst);
+                }
                 if (kin) {
                     if (cell) {
                         jr_st_hint(&po[S_P * pxy], P_n, pst); jr_st_hint(&po[S_txx * pxy], txx_n, pst);
@@ -461,6 +613,10 @@ __global__ void __launch_bounds__(32 * BY, (BY <= 8 ? (FINITE_DT ? 2 : JR_VA_MIN
                                          0.5 * (RHOG ? (p[M::fx * TILE - 1] + p[M::fx * TILE]) : (a.fxc + a.fxc));
                         const double vn = vx0 + jr_div_nr(R * a.eta_dtau, 0.5 * (p[M::ett * TILE - 1] + c_ett));
                         jr_st_hint(&po[S_Vx * pxy], vn, pst);
+                        if (TRAIL) {
+                            if (k == 0 && zlo_bc) jr_st_hint(&po[S_Vx * pxy] - S_N * pxy, (a.tr.fs_lo[2] ? 1.0 : -1.0) * vn, pst);
+                            if (k == nz - 1) jr_st_hint(&po[S_Vx * pxy] + S_N * pxy, zhi_bc ? (a.tr.fs_hi[2] ? 1.0 : -1.0) * vn : p[T_Vx * TILE], pst);
+                        }
                         if (PUSH) jr_push_v(a.push, 0, gi, gj, k, nx, ny, nz, (size_t)(&po[S_Vx * pxy] - outset), vn);
                         if (DIAG) {
                             a.Rx[((size_t)k * ny + gj) * (nx - 1) + (gi - 1)] = R;
@@ -482,6 +638,10 @@ __global__ void __launch_bounds__(32 * BY, (BY <= 8 ? (FINITE_DT ? 2 : JR_VA_MIN
                                          0.5 * (RHOG ? (p[M::fy * TILE - 32] + p[M::fy * TILE]) : (a.fyc + a.fyc));
                         const double vn = vy0 + jr_div_nr(R * a.eta_dtau, 0.5 * (p[M::ett * TILE - 32] + c_ett));
                         jr_st_hint(&po[S_Vy * pxy], vn, pst);
+                        if (TRAIL) {
+                            if (k == 0 && zlo_bc) jr_st_hint(&po[S_Vy * pxy] - S_N * pxy, (a.tr.fs_lo[2] ? 1.0 : -1.0) * vn, pst);
+                            if (k == nz - 1) jr_st_hint(&po[S_Vy * pxy] + S_N * pxy, zhi_bc ? (a.tr.fs_hi[2] ? 1.0 : -1.0) * vn : p[T_Vy * TILE], pst);
+                        }
                         if (PUSH) jr_push_v(a.push, 1, gi, gj, k, nx, ny, nz, (size_t)(&po[S_Vy * pxy] - outset), vn);
                         if (DIAG) {
                             a.Ry[((size_t)k * (ny - 1) + (gj - 1)) * nx + gi] = R;
@@ -507,6 +667,12 @@ __global__ void __launch_bounds__(32 * BY, (BY <= 8 ? (FINITE_DT ? 2 : JR_VA_MIN
                             a.Uz[c] = vn * a.dt; a.dVz[c] = vn;
                         }
                         if (MULTI && bz) JR_GHOSTS(&po[S_Vz * pxy], vn, false, JR_MX, 1, 0, JR_MY, a.PX, 1);
+                    }
+                    if (TRAIL && cell) {
+                        // z boundary-normal faces: Vz(K = 0) = box plane 1 from the queue (k = 0), Vz(K = nz) = box plane nz+1 from the
+                        // arrival plane (k = nz − 1)
+                        if (k == 0) jr_st_hint(&po[S_Vz * pxy], a.tr.ns_lo[2] ? 0.0 : vz0, pst);
+                        if (k == nz - 1) jr_st_hint(&po[(S_N + S_Vz) * pxy], a.tr.ns_hi[2] ? 0.0 : p[T_Vz * TILE], pst);
                     }
                     if (MULTI && mz != 0 && cell) {
                         // z-normal boundary faces: Vz(K = 0) from the queue (k = 0), Vz(K = nz) from the arrival plane
@@ -543,6 +709,13 @@ __global__ void __launch_bounds__(32 * BY, (BY <= 8 ? (FINITE_DT ? 2 : JR_VA_MIN
             // ---- the queue for the next step: plane k+1 becomes plane k ----
             JR_FILL_QUEUE(p);
             if (++slot == NST) { slot = 0; parity ^= 1u; }
+        }
+    }
+    if (TRAIL) {
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(a.tr.done + cta), "l"(a.tr.done_base + (unsigned long long)nstep) : "memory");
         }
     }
     if (MULTI && it + 1 < niter) {
@@ -852,6 +1025,10 @@ struct VaPlan {
     void *zeroed[4] = {nullptr, nullptr, nullptr, nullptr};
     int zdims[4] = {0, 0, 0, 0};  // nx, ny, nz, finite_dt of the zeroed layout
     bool last_diag = false;       // the last iteration was an observable one: the user's dense arrays are current
+    // TRAIL (flow_bcs! by trailing CTAs inside the iteration launch, see TrailArgs)
+    bool trail = false;
+    int trail_max = 8, trail_nb = 16, trail_nb_tail = 4, trail_tail = 16, trail_sig = 1;
+    unsigned long long *done = nullptr, done_base = 0;
     // multi-GPU push exchange (see PushArgs): the state sets of every rank are CUDA-IPC mapped here
     bool push = false;
     void *shared_ptr[2] = {nullptr, nullptr};   // the S pointers the mappings below belong to
@@ -959,6 +1136,20 @@ int jr_stokes3d_VA_fused_begin(jr_context *ctx, const jr_fields *s, const jr_sto
     P.progress_base = 0;
     P.gbar_base = 0;
     JR_CUDA(cudaMemsetAsync(p, 0, 256, ctx->stream));
+    if ((st = jr_ctx_scratch(ctx, "va_done", 1024 * sizeof(unsigned long long), &p))) return st;
+    P.done = (unsigned long long *)p;
+    P.done_base = 0;
+    JR_CUDA(cudaMemsetAsync(p, 0, 1024 * sizeof(unsigned long long), ctx->stream));
+    // opt-in (JRB200_VA_TRAIL=1): bit-exact, but measured SLOWER (0.85–0.97 ms against 0.535 ms per iteration at 255^3,
+    // profiles/r02_trail_experiment.md): publishing "the stores of step l are complete" needs a gpu-scope release in every main CTA,
+    // and that fence waits for the SM's outstanding stores (≈ 1.7 µs under the z-march's load) in a warp the per-step barrier waits for
+    P.trail = false; P.trail_max = 8; P.trail_nb = 16; P.trail_nb_tail = 4; P.trail_tail = 16; P.trail_sig = 1;
+    if (const char *e = getenv("JRB200_VA_TRAIL")) P.trail = atoi(e) != 0;
+    if (const char *e = getenv("JRB200_VA_TRAIL_CTAS")) P.trail_max = atoi(e) < 1 ? 1 : atoi(e);
+    if (const char *e = getenv("JRB200_VA_TRAIL_NB")) P.trail_nb = atoi(e) < 1 ? 1 : atoi(e);
+    if (const char *e = getenv("JRB200_VA_TRAIL_SIG")) P.trail_sig = atoi(e) < 1 ? 1 : atoi(e);
+    if (const char *e = getenv("JRB200_VA_TRAIL_NBT")) P.trail_nb_tail = atoi(e) < 1 ? 1 : atoi(e);
+    if (const char *e = getenv("JRB200_VA_TRAIL_TAIL")) P.trail_tail = atoi(e) < 0 ? 0 : atoi(e);
     // constant body force?  (one pass over ρg per solve; ρg ≡ 0 in SolVi / Taylor-Green / Burstedde-type benchmarks)
     {
         void *part = nullptr, *mm = nullptr;
@@ -1044,18 +1235,19 @@ int jr_stokes3d_VA_fused_begin(jr_context *ctx, const jr_fields *s, const jr_sto
     return JR_OK;
 }
 
-template <int BY, bool FIN, bool DG, int NSTv, bool RHOG, bool MULTI = false, bool PUSH = false>
+#define JR_TRAIL_NA 7777  // internal: this plan leaves no CTA slot for trailing CTAs (or runs z-chunks): use the two-launch iteration
+template <int BY, bool FIN, bool DG, int NSTv, bool RHOG, bool MULTI = false, bool PUSH = false, bool TRAIL = false>
 static int launch_one(jr_context *ctx, VaPlan &P, VaArgs &a)
 {
     constexpr int TY = BY - 2;
     constexpr int smem = NSTv * SlotMap<FIN, RHOG>::NARR * 32 * BY * 8;
     static int cta_per_sm = 0;
     if (!cta_per_sm) {
-        JR_CUDA(cudaFuncSetAttribute(k_va_tma<BY, FIN, DG, NSTv, RHOG, MULTI, PUSH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        JR_CUDA(cudaFuncSetAttribute(k_va_tma<BY, FIN, DG, NSTv, RHOG, MULTI, PUSH>, cudaFuncAttributePreferredSharedMemoryCarveout,
+        JR_CUDA(cudaFuncSetAttribute(k_va_tma<BY, FIN, DG, NSTv, RHOG, MULTI, PUSH, TRAIL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        JR_CUDA(cudaFuncSetAttribute(k_va_tma<BY, FIN, DG, NSTv, RHOG, MULTI, PUSH, TRAIL>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                      cudaSharedmemCarveoutMaxShared));
         int nb = 0;
-        JR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_va_tma<BY, FIN, DG, NSTv, RHOG, MULTI, PUSH>, 32 * BY, smem));
+        JR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_va_tma<BY, FIN, DG, NSTv, RHOG, MULTI, PUSH, TRAIL>, 32 * BY, smem));
         JR_REQUIRE(nb >= 1, JR_ERR_CUDA, "k_va_tma<%d> does not fit on an SM (%d B shared memory)", BY, smem);
         cta_per_sm = nb;
         if (getenv("JRB200_VERBOSE"))
@@ -1067,7 +1259,17 @@ static int launch_one(jr_context *ctx, VaPlan &P, VaArgs &a)
     a.nchunk = (P.nz + a.kchunk - 1) / a.kchunk;
     const long items = (long)a.ntx * a.nty * a.nchunk;
     const long slots = (long)ctx->sm_count * cta_per_sm;
-    const int G = (int)(items < slots ? items : slots);
+    int G = (int)(items < slots ? items : slots);
+    if (TRAIL) {
+        // every column tile must be resident at once (one round, one z-chunk) with at least one CTA slot left for the trailing CTAs
+        if (a.nchunk != 1 || items + 1 > slots) return JR_TRAIL_NA;
+        const long nt = slots - items < P.trail_max ? slots - items : P.trail_max;
+        a.tr.ntrail = (int)nt;
+        a.tr.done = P.done;
+        a.tr.done_base = P.done_base;
+        P.done_base += (unsigned long long)(a.kchunk + 2);
+        G = (int)(items + nt);
+    }
     a.progress = P.progress;
     a.progress_base = P.progress_base;
     a.slack = P.slack;
@@ -1079,7 +1281,7 @@ static int launch_one(jr_context *ctx, VaPlan &P, VaArgs &a)
     P.gbar_base += (unsigned long long)(nit - 1) * G;
     void *args[1] = {(void *)&a};
     // cooperative launch: the soft lock-step spins on other CTAs, so all G CTAs must be resident
-    JR_CUDA(cudaLaunchCooperativeKernel((const void *)k_va_tma<BY, FIN, DG, NSTv, RHOG, MULTI, PUSH>, dim3(G, 1, 1), dim3(32, BY, 1), args, smem,
+    JR_CUDA(cudaLaunchCooperativeKernel((const void *)k_va_tma<BY, FIN, DG, NSTv, RHOG, MULTI, PUSH, TRAIL>, dim3(G, 1, 1), dim3(32, BY, 1), args, smem,
                                         ctx->stream));
     return JR_OK;
 }
@@ -1099,6 +1301,17 @@ static int launch_va(jr_context *ctx, VaPlan &P, VaArgs &a, int diag)
 {
     if (P.push) return P.rhog_const ? launch_va_t<false, true>(ctx, P, a, diag) : launch_va_t<true, true>(ctx, P, a, diag);
     return P.rhog_const ? launch_va_t<false, false>(ctx, P, a, diag) : launch_va_t<true, false>(ctx, P, a, diag);
+}
+// flow_bcs! by trailing CTAs of the same launch (never with diagnostics); JR_TRAIL_NA: not applicable to this plan
+template <bool RHOG>
+static int launch_va_trail_t(jr_context *ctx, VaPlan &P, VaArgs &a)
+{
+    if (P.finite_dt) return launch_one<8, true, false, 2, RHOG, false, false, true>(ctx, P, a);
+    switch (P.BY) {
+    case 8: return launch_one<8, false, false, 3, RHOG, false, false, true>(ctx, P, a);
+    case 10: return launch_one<10, false, false, 3, RHOG, false, false, true>(ctx, P, a);
+    default: return launch_one<16, false, false, 3, RHOG, false, false, true>(ctx, P, a);
+    }
 }
 // several iterations per launch, boundary conditions inside the kernel (never with diagnostics)
 template <bool RHOG>
@@ -1142,6 +1355,12 @@ static void fill_args(VaArgs &a, const VaPlan &P, const jr_fields *s, const jr_s
         a.bc_sg[q] = fsl[q] ? 1.0 : -1.0;
     }
     memset(&a.push, 0, sizeof(a.push));
+    memset(&a.tr, 0, sizeof(a.tr));
+    a.tr.in = P.S[parity ? 1 : 0];
+    a.tr.nb = P.trail_nb; a.tr.nb_tail = P.trail_nb_tail; a.tr.tail_planes = P.trail_tail; a.tr.sig_every = P.trail_sig;
+    a.tr.fs_lo[0] = fs[0]; a.tr.fs_hi[0] = fs[1]; a.tr.ns_lo[0] = ns[0]; a.tr.ns_hi[0] = ns[1];
+    a.tr.fs_lo[1] = fs[2]; a.tr.fs_hi[1] = fs[3]; a.tr.ns_lo[1] = ns[2]; a.tr.ns_hi[1] = ns[3];
+    a.tr.fs_lo[2] = fs[4]; a.tr.fs_hi[2] = fs[5]; a.tr.ns_lo[2] = ns[5]; a.tr.ns_hi[2] = ns[4];
 }
 
 // neighbour tables of the push exchange for the iteration that writes set `outq`
@@ -1225,8 +1444,14 @@ int jr_stokes3d_VA_fused_iter(jr_context *ctx, const jr_fields *s, const jr_stok
         fill_push(a.push, ctx, P, parity ? 0 : 1);
         a.push.epoch = ++ctx->comm->push_epoch;
     }
-    int st = launch_va(ctx, P, a, diag);
-    if (st) return st;
+    int st = JR_TRAIL_NA;
+    if (!diag && P.trail && !P.push) {
+        // one launch: the boundary conditions trail the z-march on the CTA slots the column tiles leave free
+        st = P.rhog_const ? launch_va_trail_t<false>(ctx, P, a) : launch_va_trail_t<true>(ctx, P, a);
+        if (st && st != JR_TRAIL_NA) return st;
+    }
+    const bool trailed = st == JR_OK;
+    if (!trailed && (st = launch_va(ctx, P, a, diag))) return st;
     P.last_diag = diag != 0;
 
     BcArgsB b;
@@ -1246,8 +1471,8 @@ int jr_stokes3d_VA_fused_iter(jr_context *ctx, const jr_fields *s, const jr_stok
     int m = nx > ny ? nx : ny;
     m = (m > nz ? m : nz) + 2;
     dim3 bgrid((m + 31) / 32, (m + 8 * BC_ROWS - 1) / (8 * BC_ROWS), 18), bblock(32, 8, 1);
-    k_bc_box3<<<bgrid, bblock, 0, ctx->stream>>>(b);
-    ctx->launches += 2;
+    if (!trailed) k_bc_box3<<<bgrid, bblock, 0, ctx->stream>>>(b);
+    ctx->launches += trailed ? 1 : 2;
     JR_CHECK_LAUNCH();
     // update_halo!(Vx, Vy, Vz)  Stokes3D.jl:120 — pushed by the two kernels above (P.push), else pack + pull on the box set
     if (ctx->comm && !P.push) {

@@ -111,6 +111,7 @@ def test_multi_iteration_launch(oracle, monkeypatch, bc, BY, nchunk, dt, finite_
 
     monkeypatch.setenv("JRB200_VA_BY", str(BY))
     monkeypatch.setenv("JRB200_VA_NCHUNK", str(nchunk))
+    monkeypatch.setenv("JRB200_VA_TRAIL", "0")   # the comparison below is against the kernel + BC kernel iteration
     ni = (64, 33, 29)
     s = setups.random_stokes3d(ni, seed=4242, dt=dt, finite_K=finite_K)
     flags = ALL_FLAGGED[bc]
@@ -122,6 +123,37 @@ def test_multi_iteration_launch(oracle, monkeypatch, bc, BY, nchunk, dt, finite_
             compare_slots(st.slots(), d, FIELDS_STATE + FIELDS_DIAG, TOL, f"multi={multi} bc={bc} BY={BY} nchunk={nchunk} niter={niter}")
         launches[multi] = st.last_result.kernel_launches
     assert launches["1"] == launches["0"] - 2 * 7 + 1, launches
+
+
+TRAIL_FLAGS = dict(ALL_FLAGGED, prescribed=dict(free_slip=[0] * 6, no_slip=[0] * 6, periodic=[0] * 6),
+                   half=dict(free_slip=[1, 0, 0, 0, 1, 0], no_slip=[0, 0, 0, 1, 0, 0], periodic=[0] * 6))
+
+
+@pytest.mark.parametrize("bc", list(TRAIL_FLAGS))
+@pytest.mark.parametrize("BY,nb,sig", [(8, 1, 1), (10, 4, 1), (10, 3, 2), (16, 7, 4)])
+@pytest.mark.parametrize("dt,finite_K", [(0.7, True), (np.inf, False)])
+def test_trailing_boundary_ctas(oracle, monkeypatch, bc, BY, nb, sig, dt, finite_K):
+    """opt-in (JRB200_VA_TRAIL=1), one z-chunk plans: flow_bcs! is applied by trailing CTAs of the iteration launch (plane rings) and by the
+    z-march itself (z ghost planes): one launch per iteration, same result as the oracle and as the two-launch iteration"""
+    from justrelax_jl_b200 import setups
+
+    if finite_K and BY != 8:
+        pytest.skip("finite dt runs the 8-row tile only")
+    monkeypatch.setenv("JRB200_VA_BY", str(BY))
+    monkeypatch.setenv("JRB200_VA_NCHUNK", "1")
+    monkeypatch.setenv("JRB200_VA_TRAIL_NB", str(nb))
+    monkeypatch.setenv("JRB200_VA_TRAIL_SIG", str(sig))
+    ni = (64, 33, 29)
+    s = setups.random_stokes3d(ni, seed=777, dt=dt, finite_K=finite_K)
+    flags = TRAIL_FLAGS[bc]
+    launches = {}
+    for trail in ("1", "0"):
+        monkeypatch.setenv("JRB200_VA_TRAIL", trail)
+        for niter in (2, 7):
+            st, d = _run_both(oracle, s, niter, flags, False)
+            compare_slots(st.slots(), d, FIELDS_STATE + FIELDS_DIAG, TOL, f"trail={trail} bc={bc} BY={BY} nb={nb} sig={sig} niter={niter}")
+        launches[trail] = st.last_result.kernel_launches
+    assert launches["1"] == launches["0"] - 6, launches
 
 
 def test_multi_iteration_capped_batches(oracle, monkeypatch):
