@@ -121,6 +121,112 @@ __global__ void k_halo_pull(const __grid_constant__ HaloArgs h, const __grid_con
     A.p[harr_idx(A, c)] = *src;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// z-ordered pull: the same exchange as k_halo_pull, but split along the slowest index.  A "head" launch (with the flag barrier, full
+// grid) takes the first planes; a "rest" launch of a few CTAs on a second stream walks the remaining planes in z order and publishes
+// its progress, so that a consumer which itself marches in z (the fused 3D-VA kernel of the next iteration) runs on top of it — the
+// @hide_communication of the reference (Stokes3D.jl:104-121).  Sources are the peers' packed staging buffers: reading the x faces
+// straight from the peers' arrays was measured at ≈ 20 µs per dependent access (every plane of a 255^3 set lies in another page of
+// the peer mapping), the packed planes are a handful of pages.
+struct ZArgs {
+    HaloArgs h;
+    int z0, z1, chunk;                   // planes [z0, z1) of the addressed space (index 2 + offset), published every `chunk` planes
+    unsigned long long *prog;            // [gridDim.x] progress slots: prog_base + planes complete (nullptr: nothing published)
+    unsigned long long prog_base;
+};
+
+__device__ __forceinline__ bool z_elem(const HaloArgs &h, const jr_comm_dev &cd, int q, const int c[3], const double *&src, double *&dst)
+{
+    const jr_harr &A = h.A[q];
+    int dr[3], s[3], first, fside;
+    if (!jr_halo_chase(A.n, A.ol, h.has_lo, h.has_hi, c, dr, s, first, fside)) return false;
+    const int peer = cd.nbr[(dr[2] + 1) * 9 + (dr[1] + 1) * 3 + (dr[0] + 1)];
+    src = cd.stage[peer][h.buf] + h.stage_off[q] + jr_stage_plane_off(A.n, first, fside) + jr_stage_elem(A.n, first, s);
+    dst = A.p + harr_idx(A, c);
+    return true;
+}
+// f(e, src, dst) → does element e exist; eight independent peer reads in flight per thread
+template <class F>
+__device__ __forceinline__ void z_batch(int total, int gt, int nthr, F f)
+{
+    for (int e0 = gt; e0 < total; e0 += 8 * nthr) {
+        const double *src[8];
+        double *dst[8];
+        double v[8];
+        bool ok[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int e = e0 + u * nthr;
+            src[u] = nullptr; dst[u] = nullptr;
+            ok[u] = e < total && f(e, src[u], dst[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) v[u] = ok[u] ? __ldcg(src[u]) : 0.0;
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+            if (ok[u]) *dst[u] = v[u];
+    }
+}
+
+__global__ void __launch_bounds__(256) k_halo_pull_z(const __grid_constant__ ZArgs z, const __grid_constant__ jr_comm_dev cd, unsigned long long epoch)
+{
+    const HaloArgs &h = z.h;
+    if (epoch) jr_comm_barrier_dev(cd, epoch);   // every rank has packed (and nobody still reads the buffer packed two exchanges ago)
+    const int nthr = gridDim.x * blockDim.x, gt = blockIdx.x * blockDim.x + threadIdx.x;
+    // x / y faces with a neighbour, per array: only elements the exchange really moves are enumerated, so that every one of a thread's
+    // eight slots is a peer read in flight (the launch is pure latency)
+    int W = 0;
+    for (int q = 0; q < h.narr; q++)
+        for (int f = 0; f < 4; f++) {
+            const int d = f >> 1;
+            if (h.A[q].ol[d] >= 2 && ((f & 1) ? h.has_hi[d] : h.has_lo[d])) W += h.A[q].n[1 - d];
+        }
+    for (int zc = z.z0; zc < z.z1; zc += z.chunk) {
+        const int ze = min(zc + z.chunk, z.z1);
+        // (1) the x / y ghost faces of the planes of this chunk
+        z_batch((ze - zc) * W, gt, nthr, [&](int e, const double *&src, double *&dst) {
+            int w = e % W;
+            const int Z = zc + e / W;
+            for (int q = 0; q < h.narr; q++) {
+                const jr_harr &A = h.A[q];
+                for (int f = 0; f < 4; f++) {
+                    const int d = f >> 1;
+                    if (!(A.ol[d] >= 2 && ((f & 1) ? h.has_hi[d] : h.has_lo[d]))) continue;
+                    const int L = A.n[1 - d];
+                    if (w >= L) { w -= L; continue; }
+                    int c[3];
+                    c[2] = Z - A.o[2];
+                    if (c[2] < 0 || c[2] >= A.n[2]) return false;
+                    if (A.ol[2] >= 2 && ((c[2] == 0 && h.has_lo[2]) || (c[2] == A.n[2] - 1 && h.has_hi[2]))) return false;  // whole plane: part (2)
+                    c[d] = (f & 1) ? A.n[d] - 1 : 0;
+                    c[1 - d] = w;
+                    return z_elem(h, cd, q, c, src, dst);
+                }
+            }
+            return false;
+        });
+        // (2) whole ghost planes of the z faces that fall into this chunk
+        for (int q = 0; q < h.narr; q++) {
+            const jr_harr &A = h.A[q];
+            if (A.ol[2] < 2) continue;
+            for (int side = 0; side < 2; side++) {
+                if (side == 0 ? !h.has_lo[2] : !h.has_hi[2]) continue;
+                const int c2 = side == 0 ? 0 : A.n[2] - 1, Z = c2 + A.o[2];
+                if (Z < zc || Z >= ze) continue;
+                z_batch(A.n[0] * A.n[1], gt, nthr, [&](int e, const double *&src, double *&dst) {
+                    const int c[3] = {e % A.n[0], e / A.n[0], c2};
+                    return z_elem(h, cd, q, c, src, dst);
+                });
+            }
+        }
+        if (z.prog) {
+            __syncthreads();
+            if (threadIdx.x == 0)
+                asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(z.prog + blockIdx.x), "l"(z.prog_base + (unsigned long long)ze) : "memory");
+        }
+    }
+}
+
 // deterministic all-reduce of n ≤ 16 doubles: every rank writes its partials into its slot on every rank, barrier,
 // then every rank combines the slots in rank order (bit-identical result everywhere).  op: 0 sum, 1 max, 2 min
 __global__ void k_allreduce(const __grid_constant__ jr_comm_dev cd, unsigned long long epoch, int buf, double *vals, int n, int op)
@@ -215,15 +321,13 @@ int jr_comm_reserve_stage(jr_context *ctx, size_t doubles)
     return comm_ensure_stage(ctx, cm, doubles);
 }
 
-int jr_comm_halo(jr_context *ctx, const jr_harr *arrs, int narr)
+
+static int halo_args(jr_context *ctx, jr_comm *cm, const jr_harr *arrs, int narr, HaloArgs &h, int &maxu, int &maxv)
 {
-    jr_comm *cm = ctx->comm;
-    if (!cm || cm->nranks == 1 || narr == 0) return JR_OK;
     JR_REQUIRE(narr <= JR_HALO_MAX_ARRAYS, JR_ERR_ARG, "at most %d arrays per halo update", JR_HALO_MAX_ARRAYS);
-    HaloArgs h;
     h.narr = narr;
     long off = 0;
-    int maxu = 1, maxv = 1;
+    maxu = 1; maxv = 1;
     for (int q = 0; q < narr; q++) {
         h.A[q] = arrs[q];
         h.stage_off[q] = off;
@@ -239,14 +343,58 @@ int jr_comm_halo(jr_context *ctx, const jr_harr *arrs, int narr)
     int st = comm_ensure_stage(ctx, cm, (size_t)off);
     if (st) return st;
     for (int d = 0; d < 3; d++) { h.has_lo[d] = cm->coords[d] > 0; h.has_hi[d] = cm->coords[d] < cm->dims[d] - 1; }
+    // staging buffers alternate strictly from one exchange to the next (a peer may still be pulling from the previous one)
+    h.buf = (int)(cm->halo_count++ & 1);
+    return JR_OK;
+}
+
+int jr_comm_halo(jr_context *ctx, const jr_harr *arrs, int narr)
+{
+    jr_comm *cm = ctx->comm;
+    if (!cm || cm->nranks == 1 || narr == 0) return JR_OK;
+    HaloArgs h;
+    int maxu, maxv;
+    int st = halo_args(ctx, cm, arrs, narr, h, maxu, maxv);
+    if (st) return st;
     const unsigned long long epoch = ++cm->epoch;
-    h.buf = (int)(epoch & 1);
     dim3 block(32, 8, 1), grid((maxu + 31) / 32, (maxv + 7) / 8, narr * 6);
     k_halo_pack<<<grid, block, 0, ctx->stream>>>(h, (double *)cm->stage_mine[h.buf]);
     k_halo_pull<<<grid, block, 0, ctx->stream>>>(h, cm->dev, epoch);
     ctx->launches += 2;
-    cm->halo_bytes += 0;
     JR_CHECK_LAUNCH();
+    return JR_OK;
+}
+
+// update_halo!(arrs...) split along the slowest index of the addressed space (pz planes): pack + flag barrier + planes [0, head) on
+// ctx->stream (ev_head recorded), planes [head, pz) by `rest_ctas` CTAs on `side`, which publish prog_base + planes complete into
+// prog[0 … rest_ctas) every `chunk` planes (ev_rest recorded).  The caller joins ev_rest before the next exchange.
+int jr_comm_halo_z(jr_context *ctx, const jr_harr *arrs, int narr, int pz, int head, int chunk, int rest_ctas, cudaStream_t side, cudaEvent_t ev_head,
+                   cudaEvent_t ev_rest, unsigned long long *prog, unsigned long long prog_base)
+{
+    jr_comm *cm = ctx->comm;
+    JR_REQUIRE(cm && cm->nranks > 1 && narr >= 1, JR_ERR_ARG, "z-ordered exchange without a multi-rank communicator");
+    ZArgs z;
+    memset(&z, 0, sizeof(z));
+    int maxu, maxv;
+    int st = halo_args(ctx, cm, arrs, narr, z.h, maxu, maxv);
+    if (st) return st;
+    const unsigned long long epoch = ++cm->epoch;
+    dim3 block(32, 8, 1), grid((maxu + 31) / 32, (maxv + 7) / 8, narr * 6);
+    k_halo_pack<<<grid, block, 0, ctx->stream>>>(z.h, (double *)cm->stage_mine[z.h.buf]);
+    if (head > pz) head = pz;
+    z.z0 = 0; z.z1 = head; z.chunk = head;
+    z.prog = nullptr; z.prog_base = 0;
+    k_halo_pull_z<<<4 * ctx->sm_count, 256, 0, ctx->stream>>>(z, cm->dev, epoch);
+    ctx->launches += 2;
+    JR_CHECK_LAUNCH();
+    JR_CUDA(cudaEventRecord(ev_head, ctx->stream));
+    JR_CUDA(cudaStreamWaitEvent(side, ev_head, 0));
+    z.z0 = head; z.z1 = pz; z.chunk = chunk < 1 ? 1 : chunk;
+    z.prog = prog; z.prog_base = prog_base;
+    k_halo_pull_z<<<rest_ctas, 256, 0, side>>>(z, cm->dev, 0ull);
+    ctx->launches += 1;
+    JR_CHECK_LAUNCH();
+    JR_CUDA(cudaEventRecord(ev_rest, side));
     return JR_OK;
 }
 

@@ -35,7 +35,7 @@ struct jr_comm {
     jr_comm_sig *sig_mine = nullptr;
     void *stage_mine[2] = {nullptr, nullptr};
     size_t stage_cap = 0;                         // doubles per staging buffer
-    unsigned long long epoch = 0, red_count = 0, push_epoch = 0;
+    unsigned long long epoch = 0, red_count = 0, push_epoch = 0, halo_count = 0;
     size_t halo_bytes = 0;
     std::map<std::string, void *> ipc_open;       // opened peer handles (handle bytes + rank → mapped pointer)
     std::vector<void *> retired;                  // outgrown staging buffers (freed at destroy)
@@ -61,6 +61,10 @@ int jr_comm_allreduce_dev(jr_context *ctx, double *d_vals, int n, int op);
 int jr_comm_share(jr_context *ctx, void *mine, void **out);
 // make sure every rank's staging buffers hold at least `doubles` elements (collective: all ranks call it with the same size)
 int jr_comm_reserve_stage(jr_context *ctx, size_t doubles);
+
+// update_halo!(arrs...) split along the slowest index (see comm.cu: k_halo_pull_z)
+int jr_comm_halo_z(jr_context *ctx, const jr_harr *arrs, int narr, int pz, int head, int chunk, int rest_ctas, cudaStream_t side, cudaEvent_t ev_head,
+                   cudaEvent_t ev_rest, unsigned long long *prog, unsigned long long prog_base);
 
 #ifdef __CUDACC__
 // ---------------------------------------------------------------------------------------------------------------

@@ -124,6 +124,14 @@ struct alignas(64) VaArgs {
     // out-sets over the CUDA-IPC mapping, as it is produced — the transfer rides on NVLink under the z-march.
     PushArgs push;
     TrailArgs tr;
+    // ---- overlapped halo exchange (multi-GPU): the direct exchange of the PREVIOUS iteration's velocities (comm.cu: k_halo_direct on a
+    // second stream) walks the planes of this launch's in-set in z order while this launch marches behind it: the producer lane waits
+    // until the arrival plane it is about to load has been exchanged
+    const unsigned long long *halo_prog;  // progress slots of the exchange in flight (nullptr: the in-set is complete)
+    unsigned long long halo_base;         // slot value = halo_base + planes complete
+    int halo_nslots, halo_head, halo_pz;  // planes < halo_head were exchanged before this launch; halo_pz = planes of the set
+    int halo_faces;                       // bit 2d + side: this rank has a neighbour there (only tiles on such a face wait)
+    int spin_cap;                         // > 0: polls after which the soft lock-step gives up (non-cooperative launches)
 };
 
 #define TXW 30  // owned columns per tile
@@ -206,7 +214,7 @@ __device__ __noinline__ void jr_va_trailer(const VaArgs &a, int t, int tid)
             unsigned long long m = ~0ull;
             for (int c = tid; c < Gm; c += NTHREADS) {
                 unsigned long long v;
-                asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(a.tr.done + c) : "memory");
+                asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(a.tr.done + c) : "memory");
                 m = v < m ? v : m;
             }
 #pragma unroll
@@ -222,7 +230,7 @@ __device__ __noinline__ void jr_va_trailer(const VaArgs &a, int t, int tid)
             if (m >= need) break;
             __nanosleep(100);
         }
-        __threadfence();  // acquire: the main CTAs' stores behind the published step counts are visible now
+        // (ld.acquire above + the CTA barriers: the main CTAs' stores behind the published step counts are visible now)
         for (int r0 = t * NTHREADS + tid; r0 < per; r0 += stride) {
             int q, c[3];
             if (r0 < R0) { q = 0; jr_ring_decode(r0, nx + 1, ny + 2, c[0], c[1]); }
@@ -355,6 +363,35 @@ __global__ void __launch_bounds__(32 * BY, (BY <= 8 ? (FINITE_DT ? 2 : JR_VA_MIN
             else jr_tma_load_4d_hint(d + M::ett * TILE, &a.mC1, p_x0, p_y0, C_ett, zc, bar, pld);
         }
     };
+    // overlapped halo exchange: the V planes of the in-set arrive in z order (see VaArgs::halo_prog)
+    unsigned long long halo_seen = 0;
+    auto p_halo_wait = [&]() {
+        if (a.halo_prog == nullptr) return;
+        const int za = p_kb + p_l;  // arrival plane of this step
+        if (za < a.halo_head) return;
+        // only tiles whose box touches a ghost face with a neighbour read exchanged values (the top z ghost plane: every tile)
+        const int hf = a.halo_faces;
+        const bool touch = ((hf & 1) && p_x0 == 0) || ((hf & 2) && p_x0 + 32 > nx + 1) || ((hf & 4) && p_y0 == 0) || ((hf & 8) && p_y0 + BY > ny + 1) ||
+                           ((hf & 32) && za >= nz + 1);
+        if (!touch) return;
+        const unsigned long long need = a.halo_base + (unsigned long long)min(za + 1, a.halo_pz);
+        if (halo_seen >= need) return;
+        for (;;) {
+            unsigned long long m = ~0ull;
+            for (int q = 0; q < a.halo_nslots; q++) {
+                unsigned long long v;
+                asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(a.halo_prog + q) : "memory");
+                m = v < m ? v : m;
+            }
+            if (m >= need) { halo_seen = m; break; }
+            __nanosleep(1000);   // polite: up to a few hundred lanes poll the same line
+        }
+        {
+            unsigned long long v;  // acquire (the values polled above were relaxed)
+            asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(a.halo_prog) : "memory");
+        }
+        asm volatile("fence.proxy.async.global;" ::: "memory");  // generic-proxy stores of the exchange → our TMA loads
+    };
     auto p_advance = [&]() {
         ++p_g;
         if (++p_slot == NST) p_slot = 0;
@@ -443,6 +480,7 @@ __global__ void __launch_bounds__(32 * BY, (BY <= 8 ? (FINITE_DT ? 2 : JR_VA_MIN
                         jr_tma_prefetch_desc(&a.mC4);
                         if (MULTI) jr_tma_prefetch_desc(&a.mS5b);
                     }
+                    p_halo_wait();
                     p_issue(0);
                 }
             }
@@ -541,8 +579,12 @@ __global__ void __launch_bounds__(32 * BY, (BY <= 8 ? (FINITE_DT ? 2 : JR_VA_MIN
                         const int gt = g - a.slack;  // soft lock-step: everybody has reached step g − slack
                         if (gt >= 0) {
                             const unsigned long long target = p_target(gt);
-                            while (seen < target) asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(a.progress) : "memory");
+                            // (the lock-step is a performance device — shared halo rows are fetched together — not a correctness one:
+                            //  a launch that is not cooperative gives up after spin_cap polls instead of relying on co-residency)
+                            for (int spins = 0; seen < target && (a.spin_cap == 0 || spins < a.spin_cap); ++spins)
+                                asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(a.progress) : "memory");
                         }
+                        p_halo_wait();
                         jr_fence_proxy_async();
                         p_issue(a.stagger_ns >= 0 ? 1 : 0);
                     }
@@ -552,8 +594,7 @@ __global__ void __launch_bounds__(32 * BY, (BY <= 8 ? (FINITE_DT ? 2 : JR_VA_MIN
                 // northern halo warp (no store work): every thread of the CTA has issued the stores of the steps before this barrier —
                 // publish their count for the trailing CTAs (release: fence, then the flag)
                 if (tx == 0 && l >= 1 && (l % a.tr.sig_every) == 0) {
-                    __threadfence();
-                    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(a.tr.done + cta), "l"(a.tr.done_base + (unsigned long long)l) : "memory");
+                    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(a.tr.done + cta), "l"(a.tr.done_base + (unsigned long long)l) : "memory");
                 }
             } else if (ty == BY - 1 && a.stagger_ns >= 0) {
                 // second half of the step's loads, from the northern halo warp (it has no store work either), a little later:
@@ -714,8 +755,7 @@ __global__ void __launch_bounds__(32 * BY, (BY <= 8 ? (FINITE_DT ? 2 : JR_VA_MIN
     if (TRAIL) {
         __syncthreads();
         if (tid == 0) {
-            __threadfence();
-            asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(a.tr.done + cta), "l"(a.tr.done_base + (unsigned long long)nstep) : "memory");
+            asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(a.tr.done + cta), "l"(a.tr.done_base + (unsigned long long)nstep) : "memory");
         }
     }
     if (MULTI && it + 1 < niter) {
@@ -1025,6 +1065,12 @@ struct VaPlan {
     void *zeroed[4] = {nullptr, nullptr, nullptr, nullptr};
     int zdims[4] = {0, 0, 0, 0};  // nx, ny, nz, finite_dt of the zeroed layout
     bool last_diag = false;       // the last iteration was an observable one: the user's dense arrays are current
+    // overlapped direct halo exchange (multi-GPU, see VaArgs::halo_prog)
+    bool ovl = false, ovl_pending = false;
+    int ovl_head = 8, ovl_chunk = 16, ovl_ctas = 6, halo_faces = 0;
+    cudaStream_t ovl_stream = nullptr;
+    cudaEvent_t ev_head = nullptr, ev_rest = nullptr;
+    unsigned long long *hprog = nullptr, hbase = 0, ovl_count = 0;
     // TRAIL (flow_bcs! by trailing CTAs inside the iteration launch, see TrailArgs)
     bool trail = false;
     int trail_max = 8, trail_nb = 16, trail_nb_tail = 4, trail_tail = 16, trail_sig = 1;
@@ -1175,6 +1221,42 @@ int jr_stokes3d_VA_fused_begin(jr_context *ctx, const jr_fields *s, const jr_sto
     // index 2 / n − 3 — to be interior).  Bit-exact (tests/mgpu_worker.py) but measured SLOWER than pack + pull on 2 B200s
     // (0.688 vs 0.582 ms per iteration at 255^3, profiles/r02_push_exchange.md): the x-face planes are columns of the box layout, i.e.
     // ≈ 2·10^5 scattered 8-byte NVLink stores per face and iteration issued from the CTAs that pace the lock-stepped grid.
+    // multi-GPU, opt-in (JRB200_VA_OVL=1): the pull of the exchange split along z, its bulk overlapped with the next iteration's z-march
+    // (the @hide_communication analogue).  Bit-exact on 2 GPUs, measured no faster than pack + pull after every iteration (0.563 vs
+    // 0.550 ms per iteration at 255^3 per GPU; the whole exchange costs 15 µs there, profiles/r02_overlap_exchange.md): default off.
+    P.ovl = false; P.ovl_pending = false;
+    {
+        const char *e = getenv("JRB200_VA_OVL");
+        const char *pu = getenv("JRB200_VA_PUSH");
+        const bool want = (e && atoi(e) != 0) && !(pu && atoi(pu) == 1);
+        if (ctx->comm && ctx->comm->nranks > 1 && want) {
+            if (!P.ovl_stream) {
+                int lo = 0, hi = 0;
+                JR_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+                JR_CUDA(cudaStreamCreateWithPriority(&P.ovl_stream, cudaStreamNonBlocking, hi));
+                JR_CUDA(cudaEventCreateWithFlags(&P.ev_head, cudaEventDisableTiming));
+                JR_CUDA(cudaEventCreateWithFlags(&P.ev_rest, cudaEventDisableTiming));
+            }
+            if ((st = jr_ctx_scratch(ctx, "va_halo_prog", 64 * sizeof(unsigned long long), &p))) return st;
+            if (P.hprog != (unsigned long long *)p) {
+                P.hprog = (unsigned long long *)p;
+                JR_CUDA(cudaMemsetAsync(p, 0, 64 * sizeof(unsigned long long), ctx->stream));
+                P.hbase = 0; P.ovl_count = 0;
+            }
+            // rest CTAs: 256 threads × 74 registers each — they fit beside ONE main CTA on an SM, and the 288 column tiles of 255^3 leave
+            // 8 such slots (2 × 148 − 288); whichever kernel becomes resident first, 296 − ovl_ctas ≥ 288 slots remain for the tiles
+            P.ovl_head = 8; P.ovl_chunk = 16; P.ovl_ctas = 6;
+            if (const char *h = getenv("JRB200_VA_OVL_HEAD")) P.ovl_head = atoi(h) < 1 ? 1 : atoi(h);
+            if (const char *h = getenv("JRB200_VA_OVL_CHUNK")) P.ovl_chunk = atoi(h) < 1 ? 1 : atoi(h);
+            if (const char *h = getenv("JRB200_VA_OVL_CTAS")) P.ovl_ctas = atoi(h) < 1 ? 1 : (atoi(h) > 32 ? 32 : atoi(h));
+            P.halo_faces = 0;
+            for (int d = 0; d < 3; d++) {
+                if (ctx->comm->coords[d] > 0) P.halo_faces |= 1 << (2 * d);
+                if (ctx->comm->coords[d] < ctx->comm->dims[d] - 1) P.halo_faces |= 2 << (2 * d);
+            }
+            P.ovl = true;
+        }
+    }
     P.push = false;
     if (ctx->comm && ctx->comm->nranks > 1 && nx >= 8 && ny >= 8 && nz >= 8 && getenv("JRB200_VA_PUSH") && atoi(getenv("JRB200_VA_PUSH")) == 1) {
         for (int q = 0; q < 2; q++) {
@@ -1259,10 +1341,18 @@ static int launch_one(jr_context *ctx, VaPlan &P, VaArgs &a)
     a.nchunk = (P.nz + a.kchunk - 1) / a.kchunk;
     const long items = (long)a.ntx * a.nty * a.nchunk;
     const long slots = (long)ctx->sm_count * cta_per_sm;
-    int G = (int)(items < slots ? items : slots);
+    // multi-GPU overlap: the direct exchange of this iteration's velocities runs UNDER the next launch on a second stream.  A cooperative
+    // launch never shares the GPU with another kernel (the driver serialises it: measured, the exchange then simply runs first), so
+    // these launches are ordinary ones; ovl_ctas CTA slots stay free for the exchange, and the soft lock-step no longer assumes
+    // co-residency (spin_cap)
+    const bool coop = !P.ovl;
+    const long reserve = coop ? 0 : P.ovl_ctas;
+    const long avail = slots - reserve > 1 ? slots - reserve : 1;
+    int G = (int)(items < avail ? items : avail);
+    a.spin_cap = coop ? 0 : 4096;
     if (TRAIL) {
         // every column tile must be resident at once (one round, one z-chunk) with at least one CTA slot left for the trailing CTAs
-        if (a.nchunk != 1 || items + 1 > slots) return JR_TRAIL_NA;
+        if (!coop || a.nchunk != 1 || items + 1 > slots) return JR_TRAIL_NA;
         const long nt = slots - items < P.trail_max ? slots - items : P.trail_max;
         a.tr.ntrail = (int)nt;
         a.tr.done = P.done;
@@ -1281,8 +1371,12 @@ static int launch_one(jr_context *ctx, VaPlan &P, VaArgs &a)
     P.gbar_base += (unsigned long long)(nit - 1) * G;
     void *args[1] = {(void *)&a};
     // cooperative launch: the soft lock-step spins on other CTAs, so all G CTAs must be resident
-    JR_CUDA(cudaLaunchCooperativeKernel((const void *)k_va_tma<BY, FIN, DG, NSTv, RHOG, MULTI, PUSH, TRAIL>, dim3(G, 1, 1), dim3(32, BY, 1), args, smem,
-                                        ctx->stream));
+    if (coop)
+        JR_CUDA(cudaLaunchCooperativeKernel((const void *)k_va_tma<BY, FIN, DG, NSTv, RHOG, MULTI, PUSH, TRAIL>, dim3(G, 1, 1), dim3(32, BY, 1), args,
+                                            smem, ctx->stream));
+    else
+        JR_CUDA(cudaLaunchKernel((const void *)k_va_tma<BY, FIN, DG, NSTv, RHOG, MULTI, PUSH, TRAIL>, dim3(G, 1, 1), dim3(32, BY, 1), args, smem,
+                                 ctx->stream));
     return JR_OK;
 }
 
@@ -1355,6 +1449,9 @@ static void fill_args(VaArgs &a, const VaPlan &P, const jr_fields *s, const jr_s
         a.bc_sg[q] = fsl[q] ? 1.0 : -1.0;
     }
     memset(&a.push, 0, sizeof(a.push));
+    a.halo_prog = P.ovl_pending ? P.hprog : nullptr;
+    a.halo_base = P.hbase; a.halo_nslots = P.ovl_ctas; a.halo_head = P.ovl_head; a.halo_pz = P.PZ;
+    a.halo_faces = P.halo_faces;
     memset(&a.tr, 0, sizeof(a.tr));
     a.tr.in = P.S[parity ? 1 : 0];
     a.tr.nb = P.trail_nb; a.tr.nb_tail = P.trail_nb_tail; a.tr.tail_planes = P.trail_tail; a.tr.sig_every = P.trail_sig;
@@ -1475,7 +1572,7 @@ int jr_stokes3d_VA_fused_iter(jr_context *ctx, const jr_fields *s, const jr_stok
     ctx->launches += trailed ? 1 : 2;
     JR_CHECK_LAUNCH();
     // update_halo!(Vx, Vy, Vz)  Stokes3D.jl:120 — pushed by the two kernels above (P.push), else pack + pull on the box set
-    if (ctx->comm && !P.push) {
+    if (ctx->comm && ctx->comm->nranks > 1 && !P.push) {
         jr_harr H[3];
         for (int q = 0; q < 3; q++) {
             const BcArrB &A = b.A[q];
@@ -1483,7 +1580,18 @@ int jr_stokes3d_VA_fused_iter(jr_context *ctx, const jr_fields *s, const jr_stok
             for (int d = 0; d < 3; d++) { H[q].n[d] = A.n[d]; H[q].o[d] = A.o[d]; }
             H[q].ol[0] = 2 + A.n[0] - nx; H[q].ol[1] = 2 + A.n[1] - ny; H[q].ol[2] = 2 + A.n[2] - nz;
         }
-        return jr_comm_halo(ctx, H, 3);
+        // the exchange of the previous iteration (second stream) has fed the kernel above; formally joined here, before the flag
+        // barrier below tells the peers that this rank no longer reads their previous set
+        if (P.ovl_pending) {
+            JR_CUDA(cudaStreamWaitEvent(ctx->stream, P.ev_rest, 0));
+            P.ovl_pending = false;
+        }
+        if (!P.ovl || diag) return jr_comm_halo(ctx, H, 3);
+        // head: flag barrier + the first planes (incl. the low z ghost plane) on the compute stream, with a full grid;
+        // rest: the other planes in z order by a few CTAs on the second stream, under the next iteration's z-march
+        P.hbase = (++P.ovl_count) * 65536ull;
+        if ((st = jr_comm_halo_z(ctx, H, 3, P.PZ, P.ovl_head, P.ovl_chunk, P.ovl_ctas, P.ovl_stream, P.ev_head, P.ev_rest, P.hprog, P.hbase))) return st;
+        P.ovl_pending = true;
     }
     return JR_OK;
 }
@@ -1496,9 +1604,13 @@ int jr_stokes3d_VA_fused_finish(jr_context *ctx, const jr_fields *s, int64_t nit
 {
     auto it = g_plans.find(ctx);
     JR_REQUIRE(it != g_plans.end() && it->second.S[0], JR_ERR_ARG, "fused finish without begin");
-    const VaPlan &P = it->second;
+    VaPlan &P = it->second;
     const int nx = P.nx, ny = P.ny, nz = P.nz;
     double *cur = P.S[niter & 1];
+    if (P.ovl_pending) {
+        JR_CUDA(cudaStreamWaitEvent(ctx->stream, P.ev_rest, 0));
+        P.ovl_pending = false;
+    }
     if (P.last_diag && !ctx->comm && niter > 0) return JR_OK;
     if (P.push && niter > 0) {
         // the neighbours' pushes of the last iteration must have landed before the halo planes are read back

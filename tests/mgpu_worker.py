@@ -58,9 +58,15 @@ def main():
     # ---- 3. 3D-VA, fixed number of iterations -----------------------------------------------------------------
     names = ["Vx", "Vy", "Vz", "P", "txx", "tyy", "tzz", "tyz", "txz", "txy", "Rx", "Ry", "Rz", "RP", "etatau"]
     # (push: the in-iteration push exchange of the fused kernel, JRB200_VA_PUSH=1, besides the default pack + pull)
-    for dt, finite_K, unfused, push in [(np.inf, False, False, "0"), (0.7, True, False, "0"), (0.7, True, True, "0"), (np.inf, False, False, "1"),
-                                        (0.7, True, False, "1")]:
+    # (ovl: the default direct exchange overlapped with the next iteration's z-march — head planes, planes per published chunk, CTAs of the
+    #  second-stream launch; None = pack + pull after every iteration, JRB200_VA_OVL=0)
+    for dt, finite_K, unfused, push, ovl in [(np.inf, False, False, "0", (8, 16, 6)), (0.7, True, False, "0", (8, 16, 6)), (0.7, True, True, "0", None),
+                                             (np.inf, False, False, "0", (1, 1, 1)), (0.7, True, False, "0", (3, 4, 2)), (np.inf, False, False, "0", None),
+                                             (np.inf, False, False, "1", None), (0.7, True, False, "1", None)]:
         os.environ["JRB200_VA_PUSH"] = push
+        os.environ["JRB200_VA_OVL"] = "0" if ovl is None else "1"
+        if ovl is not None:
+            os.environ["JRB200_VA_OVL_HEAD"], os.environ["JRB200_VA_OVL_CHUNK"], os.environ["JRB200_VA_OVL_CTAS"] = (str(v) for v in ovl)
         blocks = []
         for r in range(world):
             s = setups.random_stokes3d(ni, seed=500 + r, dt=dt, finite_K=finite_K)
@@ -79,8 +85,10 @@ def main():
         jst.iterate_(st, s.pt_stokes, s.grid, bcs, (extra["rhogx"], extra["rhogy"], extra["rhogz"]), extra["K"], extra["G"], dt, niter, igg)
         jst.set_flags(0)
         worst = max(max_rel_diff(to_host(st.slots()[nm]), blocks[rank][nm]) for nm in names)
-        assert worst <= 1e-12, ("3D-VA iterate", dt, unfused, push, rank, worst)
+        assert worst <= 1e-12, ("3D-VA iterate", dt, unfused, push, ovl, rank, worst)
     os.environ["JRB200_VA_PUSH"] = "0"
+    for k in ("JRB200_VA_OVL", "JRB200_VA_OVL_HEAD", "JRB200_VA_OVL_CHUNK", "JRB200_VA_OVL_CTAS"):
+        os.environ.pop(k, None)
 
     # ---- 4. SolVi3D solve across ranks: iteration count + norms ----------------------------------------------
     # (divergence-free pure shear + inclusion placed by global coordinates: the loop ends on its tolerance, see setups.solvi3d)
