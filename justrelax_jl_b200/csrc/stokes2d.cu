@@ -12,9 +12,11 @@
 // Arithmetic is operation for operation the reference's (fma only where it writes fma/muladd; -fmad=false).
 // Diagnostics nobody reads inside the loop (∇V, ε, ε_pl, RP, τII, η_vep, U, ρg) are only stored on the iterations whose
 // result can be observed (every `nout`, and the last).
+#include <algorithm>
 #include "rheo.cuh"
 #include "tma.cuh"
 #include "comm.cuh"
+#include "stokes2d_resident.cuh"
 
 #define F(name) (s->f[JR_F_##name])
 #define TX 32
@@ -550,6 +552,8 @@ struct Plan2 {
     bool periodic;
     int32_t fs[6], ns[6], pe[6];
     int ty;   // tile height (threads in y) of k_stokes2d for this grid
+    V2ResArgs rargs;   // 2D-V2: batches of non-observable iterations with the state resident in shared memory (stokes2d_resident.cu)
+    V2ResPlan rplan;
 };
 
 // ---- tile height ----------------------------------------------------------------------------------------------------------------
@@ -700,6 +704,39 @@ static int plan2_begin(jr_context *ctx, const jr_fields *s, const jr_stokes_opts
     }
     p->rare = vc && (p->inc || k.dbc || k.dTargs != nullptr || p->pt.any_soft);
     if ((st = plan2_tile(ctx, p))) return st;
+    p->rplan = V2ResPlan();
+    if (!vc && !p->periodic && !(ctx->flags & JR_FLAG_DIAG_EVERY_ITER)) {
+        V2ResArgs &r = p->rargs;
+        r.nx = nx; r.ny = ny; r._dx = k._dx; r._dy = k._dy; r.dt = k.dt; r.r = k.r; r.th = k.th; r.edt = k.edt;
+        r.fs_l = k.fs_l; r.fs_r = k.fs_r; r.fs_t = k.fs_t; r.fs_b = k.fs_b; r.ns_l = k.ns_l; r.ns_r = k.ns_r; r.ns_t = k.ns_t; r.ns_b = k.ns_b;
+        for (int q = 0; q < 2; q++) {
+            r.Vx[q] = p->set[q][S_Vx]; r.Vy[q] = p->set[q][S_Vy]; r.P[q] = p->set[q][S_P]; r.txx[q] = p->set[q][S_txx]; r.tyy[q] = p->set[q][S_tyy];
+            r.txy[q] = p->set[q][S_txy];
+        }
+        r.eta = F(eta); r.etatau = F(etatau); r.rhogx = F(rhogx); r.rhogy = F(rhogy); r.G = F(G); r.K = F(K); r.Q = F(Q);
+        if ((st = jr_v2_resident_plan(ctx, &r, &p->rplan))) return st;
+    }
+    return JR_OK;
+}
+
+// iterations it … it + n − 1, none of them observable: resident batch when the plan has one, else the fused kernel n times
+static int plan2_iter(jr_context *ctx, Plan2 *p, int64_t it, bool diag);
+static int plan2_batch(jr_context *ctx, Plan2 *p, int64_t it, int64_t n)
+{
+    if (n <= 0) return JR_OK;
+    if (p->rplan.ok && n >= 2) {
+        int st;
+        for (int64_t done = 0; done < n;) {
+            const int64_t m = n - done < (1 << 30) ? n - done : (1 << 30);
+            if ((st = jr_v2_resident_run(ctx, &p->rargs, &p->rplan, it + done, (int)m))) return st;
+            done += m;
+        }
+        return JR_OK;
+    }
+    for (int64_t q = 0; q < n; q++) {
+        int st = plan2_iter(ctx, p, it + q, false);
+        if (st) return st;
+    }
     return JR_OK;
 }
 
@@ -887,8 +924,13 @@ int jr_stokes2d_iterate_V2(jr_context *ctx, const jr_fields *s, const jr_stokes_
     if ((st = plan2_begin(ctx, s, o, false, nullptr, &p))) return st;
     if ((st = pre_V2(ctx, s))) return st;
     JR_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
-    for (int64_t it = 0; it < niter; it++)
-        if ((st = plan2_iter(ctx, &p, it, (ctx->flags & JR_FLAG_DIAG_EVERY_ITER) || it == niter - 1))) return st;
+    if (ctx->flags & JR_FLAG_DIAG_EVERY_ITER) {
+        for (int64_t it = 0; it < niter; it++)
+            if ((st = plan2_iter(ctx, &p, it, true))) return st;
+    } else if (niter >= 1) {
+        if ((st = plan2_batch(ctx, &p, 0, niter - 1))) return st;
+        if ((st = plan2_iter(ctx, &p, niter - 1, true))) return st;
+    }
     if ((st = plan2_finish(ctx, s, &p, niter))) return st;
     JR_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
     if ((st = launch_res2d(ctx, s, o, &p, 0))) return st;  // state is back in the caller's arrays (set 0)
@@ -913,6 +955,16 @@ int jr_stokes2d_solve_V2(jr_context *ctx, const jr_fields *s, const jr_stokes_op
     int64_t iter = 0, cont = 0;
     JR_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
     while (iter < 2 || (((err / err_it1) > o->eps_rel && err > o->eps_abs) && iter <= o->iterMax)) {  // Stokes2D.jl:222
+        // the iterations up to the next sample (or iterMax) whose result nobody can observe: one resident batch.  The loop condition
+        // cannot change in between (err is only updated at samples; iter stays ≤ iterMax)
+        if (p.rplan.ok && iter >= 1) {
+            const int64_t nb = std::min<int64_t>(o->nout - 1 - (iter % o->nout), o->iterMax - iter);
+            if (nb >= 2) {
+                if ((st = plan2_batch(ctx, &p, iter, nb))) return st;
+                iter += nb;
+                continue;
+            }
+        }
         const int64_t next = iter + 1;
         const bool diag = (ctx->flags & JR_FLAG_DIAG_EVERY_ITER) || (next % o->nout == 0) || next > o->iterMax || next < 2;
         if ((st = plan2_iter(ctx, &p, iter, diag))) return st;

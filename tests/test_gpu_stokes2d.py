@@ -63,6 +63,34 @@ def test_v2_fixed_iterations_random_state(oracle, ni, finite):
             compare_slots(st.slots(), d, V2_STATE + V2_DIAG, TOL, f"V2 ni={ni} niter={niter} flags={flags}")
 
 
+@pytest.mark.parametrize("ni", [(9, 7), (33, 17), (64, 64), (95, 130), (257, 131)])
+@pytest.mark.parametrize("dt", [0.6, np.inf])
+def test_v2_resident_batches(oracle, monkeypatch, ni, dt):
+    """non-observable 2D-V2 iterations with the state resident in shared memory (one persistent CTA per tile, velocities exchanged through
+    L2, neighbour flags): same result as the oracle and as the one-launch-per-iteration kernel, for every boundary-flag combination"""
+    from justrelax_jl_b200 import stokes as jst
+
+    f, grid, pt, _ = random_stokes2d(ni, 99 + ni[0], finite=False)
+    if np.isfinite(dt):
+        f["Q"] = np.zeros(ni, order="F")   # the resident kernel takes over when 1/(G dt) = 1/(K dt) = Q/dt = 0 everywhere
+    for flags in (dict(free_slip=[1, 1, 0, 0, 1, 1], no_slip=[0] * 6, periodic=[0] * 6),
+                  dict(free_slip=[1, 0, 0, 0, 0, 1], no_slip=[0, 1, 0, 0, 1, 0], periodic=[0] * 6),
+                  dict(free_slip=[0, 0, 0, 0, 1, 0], no_slip=[0, 0, 0, 0, 0, 1], periodic=[0] * 6),
+                  dict(free_slip=[0] * 6, no_slip=[0] * 6, periodic=[0] * 6)):
+        launches = {}
+        for resident in ("1", "0"):
+            monkeypatch.setenv("JRB200_2D_RESIDENT", resident)
+            for niter in (3, 10):
+                d = oracle.alloc_stokes(ni, f)
+                st, extra = device_stokes(ni, d)
+                opts = oracle.make_opts(pt, grid._di.center, dt, flags, ni, iterMax=niter, nout=niter)
+                oracle.iterate2d_V2(d, ni, opts, niter)
+                r = jst.iterate2d_V2_(st, pt, grid, _bcs(flags), (extra["rhogx"], extra["rhogy"]), extra["G"], extra["K"], dt, niter)
+                compare_slots(st.slots(), d, V2_STATE + V2_DIAG, TOL, f"V2 resident={resident} ni={ni} dt={dt} niter={niter} flags={flags}")
+            launches[resident] = r.kernel_launches
+        assert launches["1"] < launches["0"] - 5, launches
+
+
 def test_v2_periodic(oracle):
     from justrelax_jl_b200 import stokes as jst
 
