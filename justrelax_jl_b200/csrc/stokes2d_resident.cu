@@ -117,40 +117,58 @@ __global__ void __launch_bounds__(RX * RYMAX, 1) k_v2_resident(const __grid_cons
     const bool hy_val = tx < WY && cw_ >= 0 && cw_ <= nx + 1 && cw_ <= i1 + 1, hy_own = cxo(cw_);      // Vy window column ck = cw_
     const bool nzero_x = (vi == 1 && a.ns_l) || (vi == nx + 1 && a.ns_r);  // no_slip! zeroes the boundary-normal face (all rows)
 
-    // A: pressure and normal stresses (cells of tile + rim), shear stress (vertices of the tile).  part 0: every element; 1: the
-    // elements that read owned velocities only (they do not wait for the neighbours); 2: the others
-    auto phase_A = [&](int part) {
-        if (c_val)
-            for (int lj = ty; lj < HC; lj += BR) {
-                const int cj = j0 - 1 + lj;
-                if (cj < 1 || cj > ny || cj > j1 + 1) continue;
-                const bool inner = c_inx && ryo(cj) && fyo(cj) && fyo(cj + 1);
-                if (!(part == 0 || (part == 1) == inner)) continue;
-                const int e = lj * WC + tx, lx = lj * WX + tx, ly = lj * WY + tx;
-                const double dVx = (-sVx[lx] + sVx[lx + 1]) * _dx;
-                const double dVy = (-sVy[ly] + sVy[ly + WY]) * _dy;
-                const double divV = dVx + dVy;                     // compute_∇V!  VelocityKernels.jl:3-6
-                const double dV = divV * inv3;
-                const double exx = dVx - dV, eyy = dVy - dV;       // compute_strain_rate!  VelocityKernels.jl:10-44
-                const double eta = sEta[e], txx = sTxx[e], tyy = sTyy[e];
-                sP[e] = (-divV + 0.0) * sPsi[e] + sP[e];           // compute_P!: (P0/(K dt) − ∇V + Q/dt)·ψ + P, /(1 + ψ/(K dt)) = /1
-                sTxx[e] = txx + dtr * fma(2.0 * eta, exx, -txx);   // compute_τ!  StressKernels.jl:63-91 with 1/(G dt) = 0
-                sTyy[e] = tyy + dtr * fma(2.0 * eta, eyy, -tyy);
-            }
-        if (v_val)
-            for (int lj = ty; lj < HV; lj += BR) {
-                const int vj = j0 + lj;
-                if (vj > ny + 1 || vj > j1 + 1) continue;
-                const bool inner = v_inx && ryo(vj) && ryo(vj - 1) && fyo(vj);
-                if (!(part == 0 || (part == 1) == inner)) continue;
-                const int e = lj * WV + tx, lx = (lj + 1) * WX + tx + 1, ly = (lj + 1) * WY + tx + 1;   // Vx(vi, vj), Vy(vi, vj)
-                const double exy = 0.5 * (_dy * (sVx[lx] - sVx[lx - WX]) + _dx * (sVy[ly] - sVy[ly - 1]));
-                const double t0 = sTxy[e];
-                sTxy[e] = t0 + dtr * fma(2.0 * sEtav[e], exy, -t0);
-            }
+    // ---- CTA-uniform row ranges: the row part of every test, so that the loops below carry no per-element predicate ----
+    const int c_lo = max(j0 - 1, 1), c_hi = min(j1 + 1, ny);          // cell rows of tile + rim
+    const int ci_lo = j0, ci_hi = last_y ? j1 : j1 - 1;               // … whose four faces are owned (y part)
+    const int v_hi = j1 + 1;                                           // vertex rows [j0, j1 + 1]
+    const int vi_lo = j0 == 1 ? 1 : j0 + 1, vi_hi = last_y ? j1 + 1 : j1;   // … that read owned velocities only (y part)
+    // A: pressure and normal stresses (cells of tile + rim), shear stress (vertices of the tile)
+    auto cell_row = [&](int cj) {
+        const int lj = cj - (j0 - 1);
+        const int e = lj * WC + tx, lx = lj * WX + tx, ly = lj * WY + tx;
+        const double dVx = (-sVx[lx] + sVx[lx + 1]) * _dx;
+        const double dVy = (-sVy[ly] + sVy[ly + WY]) * _dy;
+        const double divV = dVx + dVy;                     // compute_∇V!  VelocityKernels.jl:3-6
+        const double dV = divV * inv3;
+        const double exx = dVx - dV, eyy = dVy - dV;       // compute_strain_rate!  VelocityKernels.jl:10-44
+        const double eta = sEta[e], txx = sTxx[e], tyy = sTyy[e];
+        sP[e] = (-divV + 0.0) * sPsi[e] + sP[e];           // compute_P!: (P0/(K dt) − ∇V + Q/dt)·ψ + P, /(1 + ψ/(K dt)) = /1
+        sTxx[e] = txx + dtr * fma(2.0 * eta, exx, -txx);   // compute_τ!  StressKernels.jl:63-91 with 1/(G dt) = 0
+        sTyy[e] = tyy + dtr * fma(2.0 * eta, eyy, -tyy);
+    };
+    auto vert_row = [&](int vj) {
+        const int lj = vj - j0;
+        const int e = lj * WV + tx, lx = (lj + 1) * WX + tx + 1, ly = (lj + 1) * WY + tx + 1;   // Vx(vi, vj), Vy(vi, vj)
+        const double exy = 0.5 * (_dy * (sVx[lx] - sVx[lx - WX]) + _dx * (sVy[ly] - sVy[ly - 1]));
+        const double t0 = sTxy[e];
+        sTxy[e] = t0 + dtr * fma(2.0 * sEtav[e], exy, -t0);
+    };
+    // part 1: the elements that read owned velocities only (they do not wait for the neighbours); part 2: the others
+    auto phase_A_inner = [&]() {
+        if (c_val && c_inx)
+            for (int cj = ci_lo + ty; cj <= ci_hi; cj += BR) cell_row(cj);
+        if (v_val && v_inx)
+            for (int vj = vi_lo + ty; vj <= vi_hi; vj += BR) vert_row(vj);
+    };
+    auto phase_A_outer = [&]() {
+        if (c_val) {
+            if (c_inx) {   // an inner column: only the rows next to the tile's y edges are left (≤ 3)
+                const int nlo = ci_lo - c_lo, nhi = c_hi - ci_hi;
+                for (int q = ty; q < nlo + nhi; q += BR) cell_row(q < nlo ? c_lo + q : ci_hi + 1 + (q - nlo));
+            } else
+                for (int cj = c_lo + ty; cj <= c_hi; cj += BR) cell_row(cj);
+        }
+        if (v_val) {
+            if (v_inx) {
+                const int nlo = vi_lo - j0, nhi = v_hi - vi_hi;
+                for (int q = ty; q < nlo + nhi; q += BR) vert_row(q < nlo ? j0 + q : vi_hi + 1 + (q - nlo));
+            } else
+                for (int vj = j0 + ty; vj <= v_hi; vj += BR) vert_row(vj);
+        }
     };
 
-    phase_A(0);
+    phase_A_inner();
+    phase_A_outer();
     for (int it = 0; it < a.niter; ++it) {
         const int outq = (int)((a.it0 + it + 1) & 1);
         double *const Vxo = a.Vx[outq], *const Vyo = a.Vy[outq];
@@ -220,7 +238,7 @@ __global__ void __launch_bounds__(RX * RYMAX, 1) k_v2_resident(const __grid_cons
         __syncthreads();
         const unsigned long long stamp = a.flag_base + (unsigned long long)(it + 1);
         if (tid == 0) asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(a.flags + blockIdx.x), "l"(stamp) : "memory");
-        phase_A(1);
+        phase_A_inner();
         if (nb_tile >= 0) {
             unsigned long long v;
             do {
@@ -228,20 +246,25 @@ __global__ void __launch_bounds__(RX * RYMAX, 1) k_v2_resident(const __grid_cons
             } while (v < stamp);
         }
         __syncthreads();
-        if (hx_val)
-            for (int lr = ty; lr < HX; lr += BR) {
-                const int rj = j0 - 1 + lr;
-                if (rj < 0 || rj > ny + 1 || rj > j1 + 1 || (hx_own && ryo(rj))) continue;
-                sVx[lr * WX + tx] = __ldcg(Vxo + IX2(nx + 1, cw_, rj + 1));
+        if (hx_val) {   // Vx window column fi = cw_: a column of the neighbours entirely, or only the rows beyond the tile's y edges
+            if (!hx_own) {
+                for (int rj = max(j0 - 1, 0) + ty; rj <= min(j1 + 1, ny + 1); rj += BR) sVx[(rj - (j0 - 1)) * WX + tx] = __ldcg(Vxo + IX2(nx + 1, cw_, rj + 1));
+            } else {
+                if (ty == 0 && j0 > 1) sVx[tx] = __ldcg(Vxo + IX2(nx + 1, cw_, j0));
+                if (ty == 1 && !last_y) sVx[(j1 + 2 - j0) * WX + tx] = __ldcg(Vxo + IX2(nx + 1, cw_, j1 + 2));
             }
-        if (hy_val)
-            for (int lf = ty; lf < HY; lf += BR) {
-                const int fj = j0 - 1 + lf;
-                if (fj < 1 || fj > ny + 1 || fj > j1 + 2 || (hy_own && fyo(fj))) continue;
-                sVy[lf * WY + tx] = __ldcg(Vyo + IX2(nx + 2, cw_ + 1, fj));
+        }
+        if (hy_val) {   // Vy window column ck = cw_
+            if (!hy_own) {
+                for (int fj = max(j0 - 1, 1) + ty; fj <= min(j1 + 2, ny + 1); fj += BR) sVy[(fj - (j0 - 1)) * WY + tx] = __ldcg(Vyo + IX2(nx + 2, cw_ + 1, fj));
+            } else {
+                if (ty == 2 && j0 > 1) sVy[tx] = __ldcg(Vyo + IX2(nx + 2, cw_ + 1, j0 - 1));
+                if (ty == 3 && !last_y) sVy[(j1 + 2 - j0) * WY + tx] = __ldcg(Vyo + IX2(nx + 2, cw_ + 1, j1 + 1));
+                if (ty == 4 && !last_y && j1 + 2 <= ny + 1) sVy[(j1 + 3 - j0) * WY + tx] = __ldcg(Vyo + IX2(nx + 2, cw_ + 1, j1 + 2));
             }
+        }
         __syncthreads();
-        phase_A(2);
+        phase_A_outer();
     }
     __syncthreads();
     // ---- store the owned part of the final state (dense set of the batch's last iteration) ---------------------------------------------
@@ -326,7 +349,7 @@ int jr_v2_resident_plan(jr_context *ctx, const V2ResArgs *r, V2ResPlan *p)
     JR_CUDA(cudaFuncSetAttribute(k_v2_resident, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
     int nb = 0;
     p->rows = RYMAX;
-    if (const char *e = getenv("JRB200_2D_RESIDENT_ROWS")) p->rows = atoi(e) < 1 ? 1 : (atoi(e) > RYMAX ? RYMAX : atoi(e));
+    if (const char *e = getenv("JRB200_2D_RESIDENT_ROWS")) p->rows = atoi(e) < 8 ? 8 : (atoi(e) > RYMAX ? RYMAX : atoi(e));   // (the halo read hands rows to ty = 0 … 4)
     JR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_v2_resident, RX * p->rows, p->smem));
     if (nb < 1 || (long)nb * ctx->sm_count < (long)p->gx * p->gy) return JR_OK;
     p->flags = (unsigned long long *)flag;
