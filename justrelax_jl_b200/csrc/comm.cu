@@ -49,32 +49,11 @@ __host__ __device__ bool jr_halo_chase(const int n[3], const int ol[3], const bo
     return moved;
 }
 
-// staging layout of one array: planes (d, side) in the order (0,0),(0,1),(1,0),(1,1),(2,0),(2,1); side 0 = plane ol−1
-// (wanted by the low neighbour), side 1 = plane n−ol (wanted by the high neighbour)
-__host__ __device__ inline long jr_stage_plane_size(const int n[3], int d) { return d == 0 ? (long)n[1] * n[2] : d == 1 ? (long)n[0] * n[2] : (long)n[0] * n[1]; }
-__host__ __device__ inline long jr_stage_plane_off(const int n[3], int d, int side)
-{
-    long off = 0;
-    for (int e = 0; e < d; e++) off += 2 * jr_stage_plane_size(n, e);
-    return off + side * jr_stage_plane_size(n, d);
-}
-__host__ __device__ inline long jr_stage_elem(const int n[3], int d, const int s[3])
-{
-    return d == 0 ? (long)s[2] * n[1] + s[1] : d == 1 ? (long)s[2] * n[0] + s[0] : (long)s[1] * n[0] + s[0];
-}
 static long stage_array_size(const int n[3]) { return 2 * (jr_stage_plane_size(n, 0) + jr_stage_plane_size(n, 1) + jr_stage_plane_size(n, 2)); }
 
 __global__ void k_comm_barrier(const __grid_constant__ jr_comm_dev cd, unsigned long long epoch) { jr_comm_barrier_dev(cd, epoch); }
 
 // ---------------------------------------------------------------------------------------------------------------
-struct HaloArgs {
-    jr_harr A[JR_HALO_MAX_ARRAYS];
-    long stage_off[JR_HALO_MAX_ARRAYS];  // offset (doubles) of each array's planes in the staging buffer
-    int narr;
-    int buf;                             // staging buffer 0/1 (epoch parity)
-    bool has_lo[3], has_hi[3];
-};
-
 __device__ __forceinline__ size_t harr_idx(const jr_harr &A, const int c[3])
 {
     return (size_t)(c[2] + A.o[2]) * A.sz + (size_t)(c[1] + A.o[1]) * A.sy + (size_t)(c[0] + A.o[0]);
@@ -361,6 +340,36 @@ int jr_comm_halo(jr_context *ctx, const jr_harr *arrs, int narr)
     k_halo_pack<<<grid, block, 0, ctx->stream>>>(h, (double *)cm->stage_mine[h.buf]);
     k_halo_pull<<<grid, block, 0, ctx->stream>>>(h, cm->dev, epoch);
     ctx->launches += 2;
+    JR_CHECK_LAUNCH();
+    return JR_OK;
+}
+
+// update_halo!(arrs...) in two parts, for a caller whose own kernel packs the send planes (k_bc_box3 of the fused 3D-VA iteration: one
+// launch less per exchange): begin → layout + this rank's staging buffer; pull → flag barrier + pull
+int jr_comm_halo_begin(jr_context *ctx, const jr_harr *arrs, int narr, HaloArgs *h, double **stage_mine)
+{
+    jr_comm *cm = ctx->comm;
+    JR_REQUIRE(cm && cm->nranks > 1 && narr >= 1, JR_ERR_ARG, "split exchange without a multi-rank communicator");
+    int maxu, maxv;
+    int st = halo_args(ctx, cm, arrs, narr, *h, maxu, maxv);
+    if (st) return st;
+    *stage_mine = (double *)cm->stage_mine[h->buf];
+    return JR_OK;
+}
+int jr_comm_halo_pull(jr_context *ctx, const HaloArgs *h)
+{
+    jr_comm *cm = ctx->comm;
+    int maxu = 1, maxv = 1;
+    for (int q = 0; q < h->narr; q++)
+        for (int d = 0; d < 3; d++) {
+            const int du = (d == 0) ? 1 : 0, dv = (d == 2) ? 1 : 2;
+            if (h->A[q].n[du] > maxu) maxu = h->A[q].n[du];
+            if (h->A[q].n[dv] > maxv) maxv = h->A[q].n[dv];
+        }
+    const unsigned long long epoch = ++cm->epoch;
+    dim3 block(32, 8, 1), grid((maxu + 31) / 32, (maxv + 7) / 8, h->narr * 6);
+    k_halo_pull<<<grid, block, 0, ctx->stream>>>(*h, cm->dev, epoch);
+    ctx->launches += 1;
     JR_CHECK_LAUNCH();
     return JR_OK;
 }

@@ -62,6 +62,31 @@ int jr_comm_share(jr_context *ctx, void *mine, void **out);
 // make sure every rank's staging buffers hold at least `doubles` elements (collective: all ranks call it with the same size)
 int jr_comm_reserve_stage(jr_context *ctx, size_t doubles);
 
+// staging layout of one array: planes (d, side) in the order (0,0),(0,1),(1,0),(1,1),(2,0),(2,1); side 0 = plane ol−1
+// (wanted by the low neighbour), side 1 = plane n−ol (wanted by the high neighbour)
+__host__ __device__ inline long jr_stage_plane_size(const int n[3], int d) { return d == 0 ? (long)n[1] * n[2] : d == 1 ? (long)n[0] * n[2] : (long)n[0] * n[1]; }
+__host__ __device__ inline long jr_stage_plane_off(const int n[3], int d, int side)
+{
+    long off = 0;
+    for (int e = 0; e < d; e++) off += 2 * jr_stage_plane_size(n, e);
+    return off + side * jr_stage_plane_size(n, d);
+}
+__host__ __device__ inline long jr_stage_elem(const int n[3], int d, const int s[3])
+{
+    return d == 0 ? (long)s[2] * n[1] + s[1] : d == 1 ? (long)s[2] * n[0] + s[0] : (long)s[1] * n[0] + s[0];
+}
+
+struct HaloArgs {
+    jr_harr A[JR_HALO_MAX_ARRAYS];
+    long stage_off[JR_HALO_MAX_ARRAYS];  // offset (doubles) of each array's planes in the staging buffer
+    int narr;
+    int buf;                             // staging buffer 0/1 (alternates per exchange)
+    bool has_lo[3], has_hi[3];
+};
+
+// exchange in two parts for a caller that packs the send planes itself (see comm.cu)
+int jr_comm_halo_begin(jr_context *ctx, const jr_harr *arrs, int narr, HaloArgs *h, double **stage_mine);
+int jr_comm_halo_pull(jr_context *ctx, const HaloArgs *h);
 // update_halo!(arrs...) split along the slowest index (see comm.cu: k_halo_pull_z)
 int jr_comm_halo_z(jr_context *ctx, const jr_harr *arrs, int narr, int pz, int head, int chunk, int rest_ctas, cudaStream_t side, cudaEvent_t ev_head,
                    cudaEvent_t ev_rest, unsigned long long *prog, unsigned long long prog_base);

@@ -850,6 +850,11 @@ struct BcArgsB {
     double dt;
     int do_push, ncell[3];                       // multi-GPU push exchange: elements on a send plane also go to the neighbours' ghosts,
     PushArgs push;                               // elements the neighbours push to us (halo planes) are left alone
+    int pack;                                    // multi-GPU: blocks 18 … 35 of the launch pack the send planes (post-flow_bcs! values: the
+    double *stage;                               // same gather evaluated on the planes ol − 1 / n − ol) into this rank's staging buffer,
+    long stage_off[3];                           // laid out as k_halo_pack does (comm.cuh) — one launch less per exchange
+    int skip_lo[3], skip_hi[3];                  // multi-GPU: this face has a neighbour — the exchange that follows overwrites the whole
+                                                 // plane, nobody reads it in between (the sources of every gather are interior values)
 };
 
 // signal + wait of the push protocol outside the iteration kernel (solve exit: everybody's last pushes have landed)
@@ -873,9 +878,14 @@ __global__ void k_push_sync(const __grid_constant__ PushArgs pu)
 #define BC_ROWS 4   // rows per thread: the four gathers are independent and issued back to back (the kernel is pure latency)
 __global__ void __launch_bounds__(256) k_bc_box3(const __grid_constant__ BcArgsB b)
 {
-    const int which = blockIdx.z / 6, plane = blockIdx.z % 6;  // component, (dim, lo/hi)
+    const bool packjob = blockIdx.z >= 18;
+    const int bz = packjob ? blockIdx.z - 18 : blockIdx.z;
+    const int which = bz / 6, plane = bz % 6;  // component, (dim, lo/hi)
     const BcArrB &A = b.A[which];
     const int d = plane >> 1, hi = plane & 1;
+    const bool nbr = hi ? b.skip_hi[d] : b.skip_lo[d];
+    if (packjob ? !nbr : (!b.diag && nbr)) return;
+    const int ol_d = 2 + A.n[d] - b.ncell[d];
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     // fastest-varying free coordinate on threadIdx.x: for d = 0 planes use (dim1, dim2), else dim0 first
     const int u = (d == 0) ? 1 : 0, v = (d == 2) ? 1 : 2;
@@ -891,7 +901,7 @@ __global__ void __launch_bounds__(256) k_bc_box3(const __grid_constant__ BcArgsB
         val[r] = 0.0; vin[r] = 0.0; ic[r] = 0; dc[r] = 0; rcv[r] = false; pf[r][0] = pf[r][1] = pf[r][2] = 0;
         if (!ok[r]) continue;
         int c[3];
-        c[d] = hi ? A.n[d] - 1 : 0;
+        c[d] = packjob ? (hi ? A.n[d] - ol_d : ol_d - 1) : (hi ? A.n[d] - 1 : 0);
         c[u] = p;
         c[v] = q;
         int s[3] = {c[0], c[1], c[2]};
@@ -930,10 +940,17 @@ __global__ void __launch_bounds__(256) k_bc_box3(const __grid_constant__ BcArgsB
 #pragma unroll
         for (int e = 0; e < 3; e++) computed = computed && s[e] >= 1 && s[e] <= A.n[e] - 2;
         val[r] = zero ? 0.0 : sign * (computed ? A.out.p[is] : A.in.p[is]);
-        if (b.diag) {
+        if (packjob) ic[r] = (size_t)(b.stage_off[which] + jr_stage_plane_off(A.n, d, hi)) + (size_t)q * A.n[u] + p;   // jr_stage_elem
+        else if (b.diag) {
             dc[r] = ((size_t)c[2] * A.n[1] + c[1]) * A.n[0] + c[0];
             vin[r] = A.in.p[ic[r]];
         }
+    }
+    if (packjob) {
+#pragma unroll
+        for (int r = 0; r < BC_ROWS; r++)
+            if (ok[r]) b.stage[ic[r]] = val[r];
+        return;
     }
 #pragma unroll
     for (int r = 0; r < BC_ROWS; r++) {
@@ -1565,27 +1582,44 @@ int jr_stokes3d_VA_fused_iter(jr_context *ctx, const jr_fields *s, const jr_stok
     if (P.push) b.push = a.push;
     else memset(&b.push, 0, sizeof(b.push));
     b.ncell[0] = nx; b.ncell[1] = ny; b.ncell[2] = nz;
-    int m = nx > ny ? nx : ny;
-    m = (m > nz ? m : nz) + 2;
-    dim3 bgrid((m + 31) / 32, (m + 8 * BC_ROWS - 1) / (8 * BC_ROWS), 18), bblock(32, 8, 1);
-    if (!trailed) k_bc_box3<<<bgrid, bblock, 0, ctx->stream>>>(b);
-    ctx->launches += trailed ? 1 : 2;
-    JR_CHECK_LAUNCH();
-    // update_halo!(Vx, Vy, Vz)  Stokes3D.jl:120 — pushed by the two kernels above (P.push), else pack + pull on the box set
-    if (ctx->comm && ctx->comm->nranks > 1 && !P.push) {
-        jr_harr H[3];
+    for (int d = 0; d < 3; d++) {
+        const bool mg = ctx->comm && ctx->comm->nranks > 1 && !P.push;
+        b.skip_lo[d] = mg && ctx->comm->coords[d] > 0;
+        b.skip_hi[d] = mg && ctx->comm->coords[d] < ctx->comm->dims[d] - 1;
+    }
+    // update_halo!(Vx, Vy, Vz)  Stokes3D.jl:120, first half: the BC launch also packs the send planes (default exchange)
+    const bool mg = ctx->comm && ctx->comm->nranks > 1 && !P.push;
+    jr_harr H[3];
+    HaloArgs hh;
+    b.pack = 0; b.stage = nullptr; b.stage_off[0] = b.stage_off[1] = b.stage_off[2] = 0;
+    if (mg) {
         for (int q = 0; q < 3; q++) {
             const BcArrB &A = b.A[q];
             H[q].p = A.out.p; H[q].sy = A.out.sy; H[q].sz = A.out.sz;
             for (int d = 0; d < 3; d++) { H[q].n[d] = A.n[d]; H[q].o[d] = A.o[d]; }
             H[q].ol[0] = 2 + A.n[0] - nx; H[q].ol[1] = 2 + A.n[1] - ny; H[q].ol[2] = 2 + A.n[2] - nz;
         }
-        // the exchange of the previous iteration (second stream) has fed the kernel above; formally joined here, before the flag
-        // barrier below tells the peers that this rank no longer reads their previous set
+        // the exchange of the previous iteration (second stream, opt-in overlap) has fed the kernel above; formally joined here,
+        // before the flag barrier below tells the peers that this rank no longer reads their previous set
         if (P.ovl_pending) {
             JR_CUDA(cudaStreamWaitEvent(ctx->stream, P.ev_rest, 0));
             P.ovl_pending = false;
         }
+        if (!trailed && !(P.ovl && !diag)) {
+            if ((st = jr_comm_halo_begin(ctx, H, 3, &hh, &b.stage))) return st;
+            b.pack = 1;
+            for (int q = 0; q < 3; q++) b.stage_off[q] = hh.stage_off[q];
+        }
+    }
+    int m = nx > ny ? nx : ny;
+    m = (m > nz ? m : nz) + 2;
+    dim3 bgrid((m + 31) / 32, (m + 8 * BC_ROWS - 1) / (8 * BC_ROWS), b.pack ? 36 : 18), bblock(32, 8, 1);
+    if (!trailed) k_bc_box3<<<bgrid, bblock, 0, ctx->stream>>>(b);
+    ctx->launches += trailed ? 1 : 2;
+    JR_CHECK_LAUNCH();
+    // update_halo!(Vx, Vy, Vz)  Stokes3D.jl:120, second half — pushed by the two kernels above (P.push), else flag barrier + pull
+    if (mg) {
+        if (b.pack) return jr_comm_halo_pull(ctx, &hh);
         if (!P.ovl || diag) return jr_comm_halo(ctx, H, 3);
         // head: flag barrier + the first planes (incl. the low z ghost plane) on the compute stream, with a full grid;
         // rest: the other planes in z order by a few CTAs on the second stream, under the next iteration's z-march
