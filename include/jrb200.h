@@ -346,6 +346,11 @@ typedef int (*jr_allgather_fn)(const void *sendbuf, void *recvbuf, size_t bytes_
 typedef struct jr_comm jr_comm;
 int jr_comm_create(jr_context *ctx, int rank, int nranks, const int32_t dims[3], const int32_t coords[3],
                    jr_allgather_fn allgather, void *user, jr_comm **out);
+/* the same with IGG's periodx / periody / periodz (init_global_grid keywords; test/test_periodic_boundary_conditions_MPI.jl:12-19,
+ * src/grid/Utils.jl:29-83): the grid of ranks wraps around in a periodic dimension — the first rank's low ghost planes come from the
+ * last rank and vice versa; with a single rank in that dimension the rank exchanges with itself.  periods == NULL: none. */
+int jr_comm_create_periodic(jr_context *ctx, int rank, int nranks, const int32_t dims[3], const int32_t coords[3], const int32_t periods[3],
+                            jr_allgather_fn allgather, void *user, jr_comm **out);
 int jr_comm_destroy(jr_comm *comm);
 /* solves / halo updates / reductions on `ctx` go through `comm` from now on (NULL detaches) */
 int jr_context_set_comm(jr_context *ctx, jr_comm *comm);
@@ -359,6 +364,9 @@ int jr_allreduce_f64(jr_context *ctx, double *vals_host, int n, int op);
  * Returns 1 if the element is overwritten by the exchange, 0 if not, < 0 on error. */
 int jr_halo_source(const int32_t dims[3], const int32_t coords[3], const int32_t ext[3], const int32_t ncell[3],
                    const int32_t idx[3], int32_t src_coords[3], int32_t src_idx[3]);
+
+int jr_halo_source_periodic(const int32_t dims[3], const int32_t periods[3], const int32_t coords[3], const int32_t ext[3],
+                            const int32_t ncell[3], const int32_t idx[3], int32_t src_coords[3], int32_t src_idx[3]);
 
 #ifdef __cplusplus
 }

@@ -196,12 +196,14 @@ def _declare(L):
     L.jr_thermal_bcs.argtypes = [vp, vp, C.c_int32, i32p, C.POINTER(ThermalOpts)]
     L.jr_thermal_pt_arrays.argtypes = [vp, C.POINTER(ThermalFields), C.POINTER(ThermalOpts)]
     L.jr_comm_create.argtypes = [vp, C.c_int, C.c_int, i32p, i32p, ALLGATHER_FN, vp, C.POINTER(vp)]
+    L.jr_comm_create_periodic.argtypes = [vp, C.c_int, C.c_int, i32p, i32p, i32p, ALLGATHER_FN, vp, C.POINTER(vp)]
     L.jr_comm_destroy.argtypes = [vp]
     L.jr_context_set_comm.argtypes = [vp, vp]
     L.jr_comm_barrier.argtypes = [vp]
     L.jr_update_halo3d.argtypes = [vp, C.c_int, C.POINTER(vp), i32p, i32p]
     L.jr_allreduce_f64.argtypes = [vp, C.POINTER(C.c_double), C.c_int, C.c_int]
     L.jr_halo_source.argtypes = [i32p, i32p, i32p, i32p, i32p, i32p, i32p]
+    L.jr_halo_source_periodic.argtypes = [i32p, i32p, i32p, i32p, i32p, i32p, i32p, i32p]
 
 
 def i32x(vals):

@@ -81,9 +81,12 @@ def _make_allgather_cb():
     return cb
 
 
-def init_global_grid(nx: int, ny: int, nz: int = 1, *, dims: Sequence[int] = (0, 0, 0), init_dist: bool = True) -> IGG:
-    """IGG(init_global_grid(nx, ny, nz; ...)...): Cartesian topology over the torch.distributed world
-    (overlaps = 2, halo width 1) and a libjrb200 communicator attached to this process's context."""
+def init_global_grid(nx: int, ny: int, nz: int = 1, *, dims: Sequence[int] = (0, 0, 0), init_dist: bool = True, periodx=0, periody=0,
+                     periodz=0) -> IGG:
+    """IGG(init_global_grid(nx, ny, nz; dimx, dimy, dimz, periodx, periody, periodz)...): Cartesian topology over the
+    torch.distributed world (overlaps = 2, halo width 1) and a libjrb200 communicator attached to this process's context.
+    A periodic dimension wraps around: the low ghost planes of the first rank come from the last rank (from the rank
+    itself when it is alone in that dimension), as in ImplicitGlobalGrid (test/test_periodic_boundary_conditions_MPI.jl:12-19)."""
     import torch
     import torch.distributed as dist
     from .stokes import context
@@ -94,11 +97,13 @@ def init_global_grid(nx: int, ny: int, nz: int = 1, *, dims: Sequence[int] = (0,
     ndims = 3 if nz > 1 else 2
     dims = dims_create(world, ndims, dims)
     coords = cart_coords(rank, dims)
-    igg = IGG(me=rank, dims=dims, nprocs=world, coords=coords, comm_cart=None, nxyz=(int(nx), int(ny), int(nz)))
+    periods = (int(bool(periodx)), int(bool(periody)), int(bool(periodz)))
+    igg = IGG(me=rank, dims=dims, nprocs=world, coords=coords, comm_cart=None, nxyz=(int(nx), int(ny), int(nz)), periods=periods)
     ctx = context()
     cb = _make_allgather_cb() if world > 1 else _abi.ALLGATHER_FN()
     h = C.c_void_p()
-    _abi.check(_abi.lib().jr_comm_create(ctx, rank, world, _abi.i32x(dims), _abi.i32x(coords), cb, None, C.byref(h)))
+    _abi.check(_abi.lib().jr_comm_create_periodic(ctx, rank, world, _abi.i32x(dims), _abi.i32x(coords), _abi.i32x(periods), cb, None,
+                                                  C.byref(h)))
     _abi.check(_abi.lib().jr_context_set_comm(ctx, h))
     _state.update(comm=h, cb=cb, igg=igg)
     igg.comm_cart = h
@@ -164,10 +169,11 @@ def norm_mpi(A, interior: bool = False) -> float:
     return math.sqrt(sum_mpi(sumsq_interior(A, interior)))
 
 
-def halo_source(dims, coords, ext, ncell, idx):
-    """host-only index arithmetic of the exchange (C ABI jr_halo_source; no GPU needed)."""
+def halo_source(dims, coords, ext, ncell, idx, periods=(0, 0, 0)):
+    """host-only index arithmetic of the exchange (C ABI jr_halo_source[_periodic]; no GPU needed)."""
     sc, si = (C.c_int32 * 3)(), (C.c_int32 * 3)()
-    r = _abi.lib().jr_halo_source(_abi.i32x(dims), _abi.i32x(coords), _abi.i32x(ext), _abi.i32x(ncell), _abi.i32x(idx), sc, si)
+    r = _abi.lib().jr_halo_source_periodic(_abi.i32x(dims), _abi.i32x(periods), _abi.i32x(coords), _abi.i32x(ext), _abi.i32x(ncell),
+                                           _abi.i32x(idx), sc, si)
     if r < 0:
         _abi.check(r)
     return bool(r), tuple(sc), tuple(si)

@@ -242,6 +242,7 @@ static int comm_allgather(jr_comm *cm, const void *send, void *recv, size_t byte
 // export `ptr` (a cudaMalloc base pointer), all-gather the handles, open the peers' → out[r] (out[rank] = ptr)
 static int comm_share(jr_comm *cm, void *ptr, std::vector<void *> &out)
 {
+    if (cm->nranks == 1) { out.assign(1, ptr); return JR_OK; }   // a periodic single rank is its own neighbour
     cudaIpcMemHandle_t mine;
     JR_CUDA(cudaIpcGetMemHandle(&mine, ptr));
     std::vector<cudaIpcMemHandle_t> all(cm->nranks);
@@ -296,7 +297,7 @@ int jr_comm_share(jr_context *ctx, void *mine, void **out)
 int jr_comm_reserve_stage(jr_context *ctx, size_t doubles)
 {
     jr_comm *cm = ctx->comm;
-    JR_REQUIRE(cm && cm->nranks > 1, JR_ERR_ARG, "no multi-rank communicator attached to this context");
+    JR_REQUIRE(cm && cm->active, JR_ERR_ARG, "no multi-rank communicator attached to this context");
     return comm_ensure_stage(ctx, cm, doubles);
 }
 
@@ -321,7 +322,7 @@ static int halo_args(jr_context *ctx, jr_comm *cm, const jr_harr *arrs, int narr
     }
     int st = comm_ensure_stage(ctx, cm, (size_t)off);
     if (st) return st;
-    for (int d = 0; d < 3; d++) { h.has_lo[d] = cm->coords[d] > 0; h.has_hi[d] = cm->coords[d] < cm->dims[d] - 1; }
+    for (int d = 0; d < 3; d++) { h.has_lo[d] = cm->has_lo[d]; h.has_hi[d] = cm->has_hi[d]; }
     // staging buffers alternate strictly from one exchange to the next (a peer may still be pulling from the previous one)
     h.buf = (int)(cm->halo_count++ & 1);
     return JR_OK;
@@ -330,7 +331,7 @@ static int halo_args(jr_context *ctx, jr_comm *cm, const jr_harr *arrs, int narr
 int jr_comm_halo(jr_context *ctx, const jr_harr *arrs, int narr)
 {
     jr_comm *cm = ctx->comm;
-    if (!cm || cm->nranks == 1 || narr == 0) return JR_OK;
+    if (!cm || !cm->active || narr == 0) return JR_OK;
     HaloArgs h;
     int maxu, maxv;
     int st = halo_args(ctx, cm, arrs, narr, h, maxu, maxv);
@@ -349,7 +350,7 @@ int jr_comm_halo(jr_context *ctx, const jr_harr *arrs, int narr)
 int jr_comm_halo_begin(jr_context *ctx, const jr_harr *arrs, int narr, HaloArgs *h, double **stage_mine)
 {
     jr_comm *cm = ctx->comm;
-    JR_REQUIRE(cm && cm->nranks > 1 && narr >= 1, JR_ERR_ARG, "split exchange without a multi-rank communicator");
+    JR_REQUIRE(cm && cm->active && narr >= 1, JR_ERR_ARG, "split exchange without a multi-rank / periodic communicator");
     int maxu, maxv;
     int st = halo_args(ctx, cm, arrs, narr, *h, maxu, maxv);
     if (st) return st;
@@ -381,7 +382,7 @@ int jr_comm_halo_z(jr_context *ctx, const jr_harr *arrs, int narr, int pz, int h
                    cudaEvent_t ev_rest, unsigned long long *prog, unsigned long long prog_base)
 {
     jr_comm *cm = ctx->comm;
-    JR_REQUIRE(cm && cm->nranks > 1 && narr >= 1, JR_ERR_ARG, "z-ordered exchange without a multi-rank communicator");
+    JR_REQUIRE(cm && cm->active && narr >= 1, JR_ERR_ARG, "z-ordered exchange without a multi-rank / periodic communicator");
     ZArgs z;
     memset(&z, 0, sizeof(z));
     int maxu, maxv;
@@ -410,12 +411,12 @@ int jr_comm_halo_z(jr_context *ctx, const jr_harr *arrs, int narr, int pz, int h
 // bytes a rank receives in one exchange of `arrs` (reporting: halo bytes per iteration vs NVLink bandwidth)
 size_t jr_comm_halo_bytes(const jr_comm *cm, const jr_harr *arrs, int narr)
 {
-    if (!cm || cm->nranks == 1) return 0;
+    if (!cm || !cm->active) return 0;
     size_t b = 0;
     for (int q = 0; q < narr; q++)
         for (int d = 0; d < 3; d++) {
             if (arrs[q].ol[d] < 2) continue;
-            const int nb = (cm->coords[d] > 0) + (cm->coords[d] < cm->dims[d] - 1);
+            const int nb = (int)cm->has_lo[d] + (int)cm->has_hi[d];
             b += (size_t)nb * jr_stage_plane_size(arrs[q].n, d) * sizeof(double);
         }
     return b;
@@ -444,8 +445,8 @@ int jr_comm_allreduce_dev(jr_context *ctx, double *d_vals, int n, int op)
 
 extern "C" {
 
-int jr_comm_create(jr_context *ctx, int rank, int nranks, const int32_t dims[3], const int32_t coords[3], jr_allgather_fn allgather,
-                   void *user, jr_comm **out)
+int jr_comm_create_periodic(jr_context *ctx, int rank, int nranks, const int32_t dims[3], const int32_t coords[3], const int32_t periods[3],
+                            jr_allgather_fn allgather, void *user, jr_comm **out)
 {
     JR_REQUIRE(ctx && out && dims && coords, JR_ERR_ARG, "jr_comm_create: null argument");
     JR_REQUIRE(nranks >= 1 && nranks <= JR_COMM_MAX_RANKS && rank >= 0 && rank < nranks, JR_ERR_ARG,
@@ -458,19 +459,36 @@ int jr_comm_create(jr_context *ctx, int rank, int nranks, const int32_t dims[3],
     JR_CUDA(cudaSetDevice(ctx->device));
     jr_comm *cm = new jr_comm();
     cm->rank = rank; cm->nranks = nranks; cm->allgather = allgather; cm->user = user;
-    for (int d = 0; d < 3; d++) { cm->dims[d] = dims[d]; cm->coords[d] = coords[d]; }
+    cm->active = nranks > 1;
+    for (int d = 0; d < 3; d++) {
+        cm->dims[d] = dims[d]; cm->coords[d] = coords[d];
+        cm->periods[d] = periods && periods[d] ? 1 : 0;
+        // ImplicitGlobalGrid: a periodic dimension wraps around (with one rank in it the rank is its own neighbour)
+        cm->has_lo[d] = coords[d] > 0 || cm->periods[d];
+        cm->has_hi[d] = coords[d] < dims[d] - 1 || cm->periods[d];
+        if (cm->periods[d]) cm->active = true;
+    }
     memset(&cm->dev, 0, sizeof(cm->dev));
     cm->dev.rank = rank; cm->dev.nranks = nranks;
     for (int q = 0; q < 27; q++) cm->dev.nbr[q] = -1;
-    if (nranks > 1) {
+    if (cm->active) {
         // rank of every coordinate triple
         std::vector<int32_t> allc(3 * nranks);
-        int st = comm_allgather(cm, coords, allc.data(), 3 * sizeof(int32_t));
+        int st = JR_OK;
+        if (nranks > 1) st = comm_allgather(cm, coords, allc.data(), 3 * sizeof(int32_t));
+        else for (int d = 0; d < 3; d++) allc[d] = coords[d];
         if (st) { delete cm; return st; }
         for (int dz = -1; dz <= 1; dz++)
             for (int dy = -1; dy <= 1; dy++)
                 for (int dx = -1; dx <= 1; dx++) {
-                    const int c[3] = {coords[0] + dx, coords[1] + dy, coords[2] + dz};
+                    int c[3] = {coords[0] + dx, coords[1] + dy, coords[2] + dz};
+                    bool exists = true;
+                    for (int d = 0; d < 3; d++) {
+                        if (c[d] >= 0 && c[d] < dims[d]) continue;
+                        if (cm->periods[d]) c[d] = (c[d] + dims[d]) % dims[d];
+                        else exists = false;
+                    }
+                    if (!exists) continue;
                     for (int r = 0; r < nranks; r++)
                         if (allc[3 * r] == c[0] && allc[3 * r + 1] == c[1] && allc[3 * r + 2] == c[2]) cm->dev.nbr[(dz + 1) * 9 + (dy + 1) * 3 + dx + 1] = r;
                 }
@@ -483,13 +501,21 @@ int jr_comm_create(jr_context *ctx, int rank, int nranks, const int32_t dims[3],
         st = comm_share(cm, cm->sig_mine, peers);
         if (st) { delete cm; return st; }
         for (int r = 0; r < nranks; r++) cm->dev.sig[r] = (jr_comm_sig *)peers[r];
-        // everybody has zeroed its page before anybody signals: one more host collective as a barrier
-        int32_t token = rank;
-        std::vector<int32_t> toks(nranks);
-        if ((st = comm_allgather(cm, &token, toks.data(), sizeof(token)))) { delete cm; return st; }
+        if (nranks > 1) {
+            // everybody has zeroed its page before anybody signals: one more host collective as a barrier
+            int32_t token = rank;
+            std::vector<int32_t> toks(nranks);
+            if ((st = comm_allgather(cm, &token, toks.data(), sizeof(token)))) { delete cm; return st; }
+        }
     }
     *out = cm;
     return JR_OK;
+}
+
+int jr_comm_create(jr_context *ctx, int rank, int nranks, const int32_t dims[3], const int32_t coords[3], jr_allgather_fn allgather,
+                   void *user, jr_comm **out)
+{
+    return jr_comm_create_periodic(ctx, rank, nranks, dims, coords, nullptr, allgather, user, out);
 }
 
 int jr_comm_destroy(jr_comm *cm)
@@ -565,8 +591,8 @@ int jr_allreduce_f64(jr_context *ctx, double *vals_host, int n, int op)
 
 // pure host arithmetic (no GPU): source of element idx of an array after update_halo! — the index logic of
 // k_halo_pull, exported so that it can be tested against a literal x → y → z message exchange on CPU ranks.
-int jr_halo_source(const int32_t dims[3], const int32_t coords[3], const int32_t ext[3], const int32_t ncell[3], const int32_t idx[3],
-                   int32_t src_coords[3], int32_t src_idx[3])
+int jr_halo_source_periodic(const int32_t dims[3], const int32_t periods[3], const int32_t coords[3], const int32_t ext[3], const int32_t ncell[3],
+                            const int32_t idx[3], int32_t src_coords[3], int32_t src_idx[3])
 {
     JR_REQUIRE(dims && coords && ext && ncell && idx && src_coords && src_idx, JR_ERR_ARG, "jr_halo_source: null argument");
     int n[3], ol[3], c[3], dr[3], s[3], first, fside;
@@ -574,11 +600,17 @@ int jr_halo_source(const int32_t dims[3], const int32_t coords[3], const int32_t
     for (int d = 0; d < 3; d++) {
         n[d] = ext[d]; c[d] = idx[d];
         ol[d] = ext[d] > 1 ? 2 + (ext[d] - ncell[d]) : 0;
-        lo[d] = coords[d] > 0; hi[d] = coords[d] < dims[d] - 1;
+        const bool per = periods && periods[d];
+        lo[d] = coords[d] > 0 || per; hi[d] = coords[d] < dims[d] - 1 || per;
     }
     const bool moved = jr_halo_chase(n, ol, lo, hi, c, dr, s, first, fside);
-    for (int d = 0; d < 3; d++) { src_coords[d] = coords[d] + dr[d]; src_idx[d] = s[d]; }
+    for (int d = 0; d < 3; d++) { src_coords[d] = ((coords[d] + dr[d]) % dims[d] + dims[d]) % dims[d]; src_idx[d] = s[d]; }
     return moved ? 1 : 0;
+}
+int jr_halo_source(const int32_t dims[3], const int32_t coords[3], const int32_t ext[3], const int32_t ncell[3], const int32_t idx[3],
+                   int32_t src_coords[3], int32_t src_idx[3])
+{
+    return jr_halo_source_periodic(dims, nullptr, coords, ext, ncell, idx, src_coords, src_idx);
 }
 
 } // extern "C"

@@ -29,6 +29,9 @@ struct jr_comm_dev {
 struct jr_comm {
     int rank = 0, nranks = 1;
     int dims[3] = {1, 1, 1}, coords[3] = {0, 0, 0};
+    int periods[3] = {0, 0, 0};                   // IGG's periodx/y/z: the grid of ranks wraps around in that dimension
+    bool has_lo[3] = {false, false, false}, has_hi[3] = {false, false, false};   // a neighbour (possibly this rank itself) on that side
+    bool active = false;                          // update_halo! moves data: more than one rank, or a periodic dimension
     jr_allgather_fn allgather = nullptr;
     void *user = nullptr;
     jr_comm_dev dev;
@@ -50,8 +53,9 @@ struct jr_harr {
     int ol[3];     // IGG overlap of this array per dimension: 2 + (n[d] − ncell[d]); < 2 = not exchanged
 };
 
+struct jr_context;
 jr_harr jr_harr_dense(double *p, const int32_t ext[3], const int32_t ncell[3]);
-// update_halo!(arrs...) on ctx's communicator (no-op without one / on a single rank); asynchronous on ctx->stream
+// update_halo!(arrs...) on ctx's communicator (no-op without one / on a single non-periodic rank); asynchronous on ctx->stream
 int jr_comm_halo(jr_context *ctx, const jr_harr *arrs, int narr);
 size_t jr_comm_halo_bytes(const jr_comm *cm, const jr_harr *arrs, int narr);
 // in-place all-reduce of n ≤ 16 device doubles (op 0 sum, 1 max, 2 min); asynchronous on ctx->stream

@@ -618,8 +618,9 @@ static int plan2_tile(jr_context *ctx, Plan2 *p)
 // of returning rank-local answers
 static int single_rank2d(const jr_context *ctx)
 {
-    JR_REQUIRE(!(ctx->comm && ctx->comm->nranks > 1), JR_ERR_UNSUPPORTED,
-               "the 2D Stokes solvers run on one rank only (a communicator with %d ranks is attached to this context)", ctx->comm->nranks);
+    JR_REQUIRE(!(ctx->comm && ctx->comm->active), JR_ERR_UNSUPPORTED,
+               "the 2D Stokes solvers run on one non-periodic rank only (a communicator with %d ranks%s is attached to this context)", ctx->comm->nranks,
+               ctx->comm->nranks > 1 ? "" : " and a periodic dimension");
     return JR_OK;
 }
 

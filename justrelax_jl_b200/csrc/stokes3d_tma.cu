@@ -1246,7 +1246,7 @@ int jr_stokes3d_VA_fused_begin(jr_context *ctx, const jr_fields *s, const jr_sto
         const char *e = getenv("JRB200_VA_OVL");
         const char *pu = getenv("JRB200_VA_PUSH");
         const bool want = (e && atoi(e) != 0) && !(pu && atoi(pu) == 1);
-        if (ctx->comm && ctx->comm->nranks > 1 && want) {
+        if (ctx->comm && ctx->comm->nranks > 1 && !(ctx->comm->periods[0] | ctx->comm->periods[1] | ctx->comm->periods[2]) && want) {
             if (!P.ovl_stream) {
                 int lo = 0, hi = 0;
                 JR_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
@@ -1268,14 +1268,14 @@ int jr_stokes3d_VA_fused_begin(jr_context *ctx, const jr_fields *s, const jr_sto
             if (const char *h = getenv("JRB200_VA_OVL_CTAS")) P.ovl_ctas = atoi(h) < 1 ? 1 : (atoi(h) > 32 ? 32 : atoi(h));
             P.halo_faces = 0;
             for (int d = 0; d < 3; d++) {
-                if (ctx->comm->coords[d] > 0) P.halo_faces |= 1 << (2 * d);
-                if (ctx->comm->coords[d] < ctx->comm->dims[d] - 1) P.halo_faces |= 2 << (2 * d);
+                if (ctx->comm->has_lo[d]) P.halo_faces |= 1 << (2 * d);
+                if (ctx->comm->has_hi[d]) P.halo_faces |= 2 << (2 * d);
             }
             P.ovl = true;
         }
     }
     P.push = false;
-    if (ctx->comm && ctx->comm->nranks > 1 && nx >= 8 && ny >= 8 && nz >= 8 && getenv("JRB200_VA_PUSH") && atoi(getenv("JRB200_VA_PUSH")) == 1) {
+    if (ctx->comm && ctx->comm->nranks > 1 && !(ctx->comm->periods[0] | ctx->comm->periods[1] | ctx->comm->periods[2]) && nx >= 8 && ny >= 8 && nz >= 8 && getenv("JRB200_VA_PUSH") && atoi(getenv("JRB200_VA_PUSH")) == 1) {
         for (int q = 0; q < 2; q++) {
             if (P.shared_ptr[q] != (void *)P.S[q] || (int)P.peerS[q].size() != ctx->comm->nranks) {
                 P.peerS[q].assign(ctx->comm->nranks, nullptr);
@@ -1492,7 +1492,7 @@ static void fill_push(PushArgs &pu, const jr_context *ctx, const VaPlan &P, int 
             pu.sig_peer[t] = cm->dev.sig[nb];
         }
     }
-    for (int d = 0; d < 3; d++) { pu.has_lo[d] = cm->coords[d] > 0; pu.has_hi[d] = cm->coords[d] < cm->dims[d] - 1; }
+    for (int d = 0; d < 3; d++) { pu.has_lo[d] = cm->has_lo[d]; pu.has_hi[d] = cm->has_hi[d]; }
     pu.delta[0] = (long)(P.nx - 2);
     pu.delta[1] = (long)(P.ny - 2) * P.PX;
     pu.delta[2] = (long)(P.nz - 2) * S_N * (long)P.pxy;
@@ -1583,12 +1583,12 @@ int jr_stokes3d_VA_fused_iter(jr_context *ctx, const jr_fields *s, const jr_stok
     else memset(&b.push, 0, sizeof(b.push));
     b.ncell[0] = nx; b.ncell[1] = ny; b.ncell[2] = nz;
     for (int d = 0; d < 3; d++) {
-        const bool mg = ctx->comm && ctx->comm->nranks > 1 && !P.push;
-        b.skip_lo[d] = mg && ctx->comm->coords[d] > 0;
-        b.skip_hi[d] = mg && ctx->comm->coords[d] < ctx->comm->dims[d] - 1;
+        const bool mg = ctx->comm && ctx->comm->active && !P.push;
+        b.skip_lo[d] = mg && ctx->comm->has_lo[d];
+        b.skip_hi[d] = mg && ctx->comm->has_hi[d];
     }
     // update_halo!(Vx, Vy, Vz)  Stokes3D.jl:120, first half: the BC launch also packs the send planes (default exchange)
-    const bool mg = ctx->comm && ctx->comm->nranks > 1 && !P.push;
+    const bool mg = ctx->comm && ctx->comm->active && !P.push;
     jr_harr H[3];
     HaloArgs hh;
     b.pack = 0; b.stage = nullptr; b.stage_off[0] = b.stage_off[1] = b.stage_off[2] = 0;

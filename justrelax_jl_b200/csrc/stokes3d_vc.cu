@@ -864,7 +864,7 @@ static int plan3_begin(jr_context *ctx, const jr_fields *s, const jr_stokes_opts
     p->eta[0] = F(eta); p->eta[1] = (double *)(B + o_eta);
     for (int q = 0; q < 3; q++) p->n[q] = s->n[q];
     for (int q = 0; q < 6; q++) { p->fs[q] = o->free_slip[q]; p->ns[q] = o->no_slip[q]; p->pe[q] = o->periodic[q]; }
-    p->multi = ctx->comm && ctx->comm->nranks > 1;
+    p->multi = ctx->comm && ctx->comm->active;
     if ((st = jr_make_phase_tab(in, &p->pt))) return st;
     JR_REQUIRE(!p->pt.any_soft, JR_ERR_UNSUPPORTED, "cohesion softening is supported by the 2D multiphase solve only (the 3D-VC kernels do not carry EII to the edges)");
     V3 &k = p->k;

@@ -336,8 +336,9 @@ def _common_checks(stokes, flow_bcs, arrays, *, allow_displacement=False):
 def _single_rank2d(igg):
     """the 2D solvers have no halo exchange / all-reduced norms (libjrb200 returns JR_ERR_UNSUPPORTED too): refuse loudly
     instead of returning rank-local answers"""
-    if igg is not None and igg.nprocs > 1:
-        raise NotImplementedError(f"the 2D Stokes solvers of the B200 backend run on one rank only (igg.nprocs = {igg.nprocs})")
+    if igg is not None and (igg.nprocs > 1 or any(getattr(igg, "periods", (0, 0, 0)))):
+        raise NotImplementedError(f"the 2D Stokes solvers of the B200 backend run on one non-periodic rank only (igg.nprocs = {igg.nprocs}, "
+                                  f"periods = {tuple(getattr(igg, 'periods', (0, 0, 0)))})")
 
 
 def _print_hist2(out, igg, verbose):

@@ -372,11 +372,11 @@ class IGG:
     comm_cart: object = None
     overlaps: Sequence[int] = (2, 2, 2)
     nxyz: Optional[Sequence[int]] = None   # local cell counts given to init_global_grid (IGG keeps them as nxyz)
+    periods: Sequence[int] = (0, 0, 0)     # periodx, periody, periodz of init_global_grid
 
     def n_g(self, ni: Sequence[int]):
-        """nx_g(), ny_g(), nz_g(): dims·(n − overlap) + overlap  (ImplicitGlobalGrid)."""
-        return tuple(int(self.dims[d] * (ni[d] - self.overlaps[d]) + self.overlaps[d]) if self.dims[d] > 1 else int(ni[d])
-                     for d in range(len(ni)))
+        """nx_g(), ny_g(), nz_g(): dims·(n − overlap) + overlap·(period == 0)  (ImplicitGlobalGrid init_global_grid)."""
+        return tuple(int(self.dims[d] * (ni[d] - self.overlaps[d]) + (0 if self.periods[d] else self.overlaps[d])) for d in range(len(ni)))
 
 
 class Geometry:

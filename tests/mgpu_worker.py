@@ -193,8 +193,57 @@ def main():
     except ValueError as e:
         assert "split across MPI ranks" in str(e)
 
+    # ---- 8. init_global_grid(...; periodx = true, periodz = true): the grid of ranks wraps around ----------------------------------------
+    comm.finalize_global_grid()
+    periods = (1, 0, 1)
+    iggp = comm.init_global_grid(*ni, periodx=1, periodz=1)
+    assert tuple(iggp.dims) == tuple(dims)
+    for grow in [(0, 0, 0), (1, 2, 2), (2, 1, 2), (2, 2, 1), (2, 2, 2)]:
+        ext = tuple(ni[d] + grow[d] for d in range(3))
+        hosts = [np.asfortranarray(np.random.default_rng(31 + r).uniform(size=ext)) for r in range(world)]
+        A = PTArray(B200Backend)(hosts[rank])
+        for _ in range(2):
+            comm.update_halo_(A)
+            mrank.update_halo(hosts, dims, ni, periods)
+        assert np.array_equal(to_host(A), hosts[rank]), ("periodic update_halo_", grow, rank)
+    # the reference's known-answer test (test/test_periodic_boundary_conditions_MPI.jl:22-48, here on 3D arrays and any number of ranks):
+    # T .= coords[1] + 1; thermal_bcs!(periodic left/right) ; update_halo!(T) → the x ghost planes hold the x-neighbours' values
+    from justrelax_jl_b200.types import TemperatureBoundaryConditions
+    cx, dimx = iggp.coords[0], dims[0]
+    Tp = PTArray(B200Backend)(np.full(tuple(n + 2 for n in ni), float(cx + 1), order="F"))
+    bcp = TemperatureBoundaryConditions(no_flux=dict(left=False, right=False, front=True, back=True, top=True, bot=True),
+                                        periodic=dict(left=True, right=True, front=False, back=False, top=False, bot=False))
+    jth.thermal_bcs_(Tp, bcp)
+    comm.update_halo_(Tp)
+    Th = to_host(Tp)
+    assert np.all(Th[0, 1:-1, 1:-1] == float((cx - 1) % dimx + 1)) and np.all(Th[-1, 1:-1, 1:-1] == float((cx + 1) % dimx + 1)), ("periodic KAT T", rank)
+    Vyp = PTArray(B200Backend)(np.full((ni[0] + 2, ni[1] + 1, ni[2] + 2), float(cx + 1), order="F"))
+    Vxp = PTArray(B200Backend)(np.full((ni[0] + 1, ni[1] + 2, ni[2] + 2), float(cx + 1), order="F"))
+    Vzp = PTArray(B200Backend)(np.full((ni[0] + 2, ni[1] + 2, ni[2] + 1), float(cx + 1), order="F"))
+    comm.update_halo_(Vxp, Vyp, Vzp)
+    Vh = to_host(Vyp)
+    assert np.all(Vh[0, :, 1:-1] == float((cx - 1) % dimx + 1)) and np.all(Vh[-1, :, 1:-1] == float((cx + 1) % dimx + 1)), ("periodic KAT Vy", rank)
+    # 3D-VA iterations on the periodic grid of ranks (fused and unfused) against the emulation
+    for dt, finite_K, unfused in [(np.inf, False, False), (0.7, True, False), (0.7, True, True)]:
+        blocks = []
+        for r in range(world):
+            s = setups.random_stokes3d(ni, seed=700 + r, dt=dt, finite_K=finite_K)
+            blocks.append(po.alloc_stokes(ni, s.fields))
+        flags = dict(free_slip=[0, 0, 1, 1, 0, 0], no_slip=[0] * 6, periodic=[0] * 6)
+        opts = po.make_opts(s.pt_stokes, s.grid._di.center, dt, flags, mrank.n_g(ni, dims, periods), iterMax=100, nout=100)
+        st, extra = device_stokes(ni, blocks[rank])
+        mrank.va_pre(po, blocks, dims, ni, periods)
+        mrank.va_iterate(po, blocks, opts, dims, ni, 5, periods)
+        bcsp = VelocityBoundaryConditions(free_slip=dict(left=False, right=False, front=True, back=True, top=False, bot=False),
+                                          no_slip=dict(left=False, right=False, front=False, back=False, top=False, bot=False))
+        jst.set_flags(_abi.JR_FLAG_UNFUSED if unfused else 0)
+        jst.iterate_(st, s.pt_stokes, s.grid, bcsp, (extra["rhogx"], extra["rhogy"], extra["rhogz"]), extra["K"], extra["G"], dt, 5, iggp)
+        jst.set_flags(0)
+        worst_p = max(max_rel_diff(to_host(st.slots()[nm]), blocks[rank][nm]) for nm in names)
+        assert worst_p <= 1e-12, ("3D-VA iterate on a periodic grid of ranks", dt, unfused, rank, worst_p)
+
     dist.barrier()
-    print(f"MGPU_OK rank {rank}/{world} dims {dims}: halo, all-reduce, 3D-VA iterate (fused+unfused), solve iter={out.iter} worst={worst:.2e}, 3D-VC worst={worst_vc:.2e}, thermal OK", flush=True)
+    print(f"MGPU_OK rank {rank}/{world} dims {dims}: halo, all-reduce, 3D-VA iterate (fused+unfused), solve iter={out.iter} worst={worst:.2e}, 3D-VC worst={worst_vc:.2e}, thermal OK, periodic ranks OK", flush=True)
     comm.finalize_global_grid()
     dist.destroy_process_group()
 
