@@ -607,16 +607,20 @@ function init_b200_comm!(igg::JustRelax.IGG)
     comm = igg.comm_cart
     out = Ref{Ptr{Cvoid}}(C_NULL)
     dims, coords = Int32[API.tuple3(igg.dims, 1)...], Int32[API.tuple3(igg.coords, 0)...]
+    # periodx / periody / periodz of init_global_grid (ImplicitGlobalGrid keeps them in its global grid object)
+    periods = Int32[ImplicitGlobalGrid.global_grid().periods...]
     GC.@preserve comm begin
-        LIB.check(ccall(jrsym(:jr_comm_create), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Int32}, Ptr{Int32}, Ptr{Cvoid}, Ptr{Cvoid}, Ref{Ptr{Cvoid}}),
-                        ctx(), igg.me, igg.nprocs, dims, coords, cb, pointer_from_objref(comm), out))
+        LIB.check(ccall(jrsym(:jr_comm_create_periodic), Cint,
+                        (Ptr{Cvoid}, Cint, Cint, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Cvoid}, Ptr{Cvoid}, Ref{Ptr{Cvoid}}),
+                        ctx(), igg.me, igg.nprocs, dims, coords, periods, cb, pointer_from_objref(comm), out))
     end
     LIB.check(ccall(jrsym(:jr_context_set_comm), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), ctx(), out[]))
     COMM[] = out[]
     return nothing
 end
 "attach the communicator the first time a multi-rank IGG reaches a solver / halo update"
-ensure_comm!(igg::JustRelax.IGG) = (igg.nprocs > 1 && COMM[] == C_NULL) ? init_b200_comm!(igg) : nothing
+ensure_comm!(igg::JustRelax.IGG) =
+    ((igg.nprocs > 1 || any(!iszero, ImplicitGlobalGrid.global_grid().periods)) && COMM[] == C_NULL) ? init_b200_comm!(igg) : nothing
 function finalize_b200_comm!()
     COMM[] == C_NULL && return nothing
     LIB.check(ccall(jrsym(:jr_context_set_comm), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), ctx(), C_NULL))

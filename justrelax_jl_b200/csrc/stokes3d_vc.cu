@@ -37,6 +37,8 @@ struct V3 {
     double *divV, *RP, *pxx, *pyy, *pzz, *pyz, *pxz, *pxy, *tII, *eta_vep, *e_vol_pl, *Rx, *Ry, *Rz;
     int dT_ghosted;   // args.ΔT is (ni.+2), indexed ΔT[i, j, k] without offset (the reference's compute_P_kernel!)
     int pf_next;   // L2 prefetch of the next plane's operands (JRB200_VC3_PREFETCH, default on)
+    int bo_x, bo_y, bo_z;             // block offsets of a stress launch that covers a slab of the node lattice only (the rim of the z-marching region)
+    int zm_i, zm_j, zm_k, zm_chunk;   // nodes i ≤ zm_i, j ≤ zm_j, k ≤ zm_k belong to the z-marching stress kernel (0: none); planes per CTA
     int xfull_c, xfull_n;   // block columns with full 32-wide tiles for the cell (nx) and node (nx+1) lattices; a further block
                             // column, if launched, packs the few remainder columns densely (nx = 257: 1 cell / 2 node columns)
 };
@@ -47,6 +49,15 @@ __device__ __forceinline__ void vc3_map_ij(int n0, int xfull, int &i, int &j)
         i = blockIdx.x * 32 + threadIdx.x + 1; j = blockIdx.y * 8 + threadIdx.y + 1;
     } else {
         const int rem = n0 - xfull * 32, lin = blockIdx.y * 256 + threadIdx.y * 32 + threadIdx.x, jj = lin / rem;
+        i = xfull * 32 + (lin - jj * rem) + 1; j = jj + 1;
+    }
+}
+__device__ __forceinline__ void vc3_map_ij_b(int n0, int xfull, int bx, int by, int &i, int &j)
+{
+    if (bx < xfull) {
+        i = bx * 32 + threadIdx.x + 1; j = by * 8 + threadIdx.y + 1;
+    } else {
+        const int rem = n0 - xfull * 32, lin = by * 256 + threadIdx.y * 32 + threadIdx.x, jj = lin / rem;
         i = xfull * 32 + (lin - jj * rem) + 1; j = jj + 1;
     }
 }
@@ -363,9 +374,10 @@ __device__ __forceinline__ void vc3_stress_body(const V3 &a, const jr_phase_tab 
 {
     const int nx = a.nx, ny = a.ny, nz = a.nz;
     int i, j;
-    vc3_map_ij(nx + 1, a.xfull_n, i, j);
-    const int k = blockIdx.z + 1;
+    vc3_map_ij_b(nx + 1, a.xfull_n, blockIdx.x + a.bo_x, blockIdx.y + a.bo_y, i, j);
+    const int k = blockIdx.z + a.bo_z + 1;
     if (i > nx + 1 || j > ny + 1 || k > nz + 1) return;
+    if (i <= a.zm_i && j <= a.zm_j && k <= a.zm_k) return;   // updated by k_vc3_stress_zm
     const size_t nc = (size_t)nx * ny * nz, nyz = (size_t)nx * (ny + 1) * (nz + 1), nxz = (size_t)(nx + 1) * ny * (nz + 1),
                  nxy = (size_t)(nx + 1) * (ny + 1) * nz;
     const int i0 = jr_clamp(i - 1, 1, nx), ic = jr_clamp(i, 1, nx), i1 = jr_clamp(i + 1, 1, nx);
@@ -521,13 +533,121 @@ __device__ __forceinline__ void mix_from(const jr_phase_tab &pt, const double (&
     }
 }
 
+// tile accessors of the staged stress kernels: g<s, I, J, K>() = entry of array slot s at column tx+I, row ty+J, plane K (0 / 1) of the thread's
+// 2 × 2 × 2 neighbourhood — per family: cell (i0|ic, j0|jc, k0|kc); yz (i0|ic, j|j+1, k|k+1); xz (i|i+1, j0|jc, k|k+1); xy (i|i+1, j|j+1, k0|kc)
+struct TilePair {   // k_vc3_stress_sm: two planes per array, staged per CTA
+    const double *sm;
+    int base;       // ty · SROW + tx
+    template <int s, int I, int J, int K> __device__ __forceinline__ double g() const { return sm[s * STILE + K * SPLANE + J * SROW + I + base]; }
+};
+template <int ZPLANE_, int ZROW_>
+struct TileRing {   // k_vc3_stress_zm: three-plane ring per array; the cell / xy families hold planes (k−1, k), the yz / xz families (k, k+1)
+    const double *sm;
+    int base;       // ty · ZROW + tx
+    int aLo, aHi, bLo, bHi;   // ring offsets (slot · ZPLANE) of the two planes of either group at this z-step
+    template <int s, int I, int J, int K> __device__ __forceinline__ double g() const
+    {
+        const int off = (s >= SL_tyz && s < SL_txy) ? (K ? bHi : bLo) : (K ? aHi : aLo);
+        return sm[s * (3 * ZPLANE_) + off + J * ZROW_ + I + base];
+    }
+};
+
+// the arithmetic of one node (centre first, then the three edges) from the staged tiles and the node's own-position operands
+template <bool DIAG, int NP, class Tile>
+__device__ __forceinline__ void vc3_sm_compute(const V3 &a, const jr_phase_tab &pt, const Tile &A, size_t c, size_t vyz, size_t vxz, size_t vxy,
+                                               const double (&rc)[NP], const double (&ryz)[NP], const double (&rxz)[NP], const double (&rxy)[NP],
+                                               double c_tyz, double c_txz, double c_txy, double c_oyz, double c_oxz, double c_oxy, double c_lam)
+{
+#define S(s, I, J, K) A.template g<(s), (I), (J), (K)>()
+#define SAV_YZ(s) (0.25 * (S(s, 1, 0, 0) + S(s, 1, 1, 0) + S(s, 1, 0, 1) + S(s, 1, 1, 1)))
+#define SAV_XZ(s) (0.25 * (S(s, 0, 1, 0) + S(s, 1, 1, 0) + S(s, 0, 1, 1) + S(s, 1, 1, 1)))
+#define SAV_XY(s) (0.25 * (S(s, 0, 0, 1) + S(s, 1, 0, 1) + S(s, 0, 1, 1) + S(s, 1, 1, 1)))
+#define SHARM_YZ(s) jr_div_nr(4.0, jr_inv_nr(S(s, 1, 0, 0)) + jr_inv_nr(S(s, 1, 1, 0)) + jr_inv_nr(S(s, 1, 0, 1)) + jr_inv_nr(S(s, 1, 1, 1)))
+#define SHARM_XZ(s) jr_div_nr(4.0, jr_inv_nr(S(s, 0, 1, 0)) + jr_inv_nr(S(s, 1, 1, 0)) + jr_inv_nr(S(s, 0, 1, 1)) + jr_inv_nr(S(s, 1, 1, 1)))
+#define SHARM_XY(s) jr_div_nr(4.0, jr_inv_nr(S(s, 0, 0, 1)) + jr_inv_nr(S(s, 1, 0, 1)) + jr_inv_nr(S(s, 0, 1, 1)) + jr_inv_nr(S(s, 1, 1, 1)))
+    /* harmonic means: η is strictly positive and in the normal range, so the branch-free IEEE-exact reciprocal / quotient sequences of
+       tma.cuh give the same bits as 1 / x and 4 / x without the slow-path call scaffolding (15 reciprocals per node) */
+#define SAV_YZ_Y(s) (0.25 * (S(s, 0, 0, 0) + S(s, 1, 0, 0) + S(s, 0, 1, 0) + S(s, 1, 1, 0)))   /* xz family: (ic,j0,kc),(i1,j0,kc),(ic,jc,kc),(i1,jc,kc) */
+#define SAV_YZ_Z(s) (0.25 * (S(s, 0, 0, 0) + S(s, 1, 0, 0) + S(s, 0, 0, 1) + S(s, 1, 0, 1)))   /* xy family: (ic,jc,k0),(i1,jc,k0),(ic,jc,kc),(i1,jc,kc) */
+#define SAV_XZ_X(s) (0.25 * (S(s, 0, 0, 0) + S(s, 1, 0, 0) + S(s, 1, 1, 0) + S(s, 0, 1, 0)))   /* yz family: (i0,jc,kc),(ic,jc,kc),(ic,j1,kc),(i0,j1,kc) */
+#define SAV_XZ_Z(s) (0.25 * (S(s, 0, 0, 0) + S(s, 0, 1, 0) + S(s, 0, 0, 1) + S(s, 0, 1, 1)))   /* xy family: (ic,jc,k0),(ic,j1,k0),(ic,jc,kc),(ic,j1,kc) */
+#define SAV_XY_X(s) (0.25 * (S(s, 0, 0, 0) + S(s, 1, 0, 0) + S(s, 0, 0, 1) + S(s, 1, 0, 1)))   /* yz family: (i0,jc,kc),(ic,jc,kc),(i0,jc,k1),(ic,jc,k1) */
+#define SAV_XY_Y(s) (0.25 * (S(s, 0, 0, 0) + S(s, 0, 1, 0) + S(s, 0, 0, 1) + S(s, 0, 1, 1)))   /* xz family: (ic,j0,kc),(ic,jc,kc),(ic,j0,k1),(ic,jc,k1) */
+    {   // ---- centre: cell (i, j, k) = S(·, 1, 1, 1); edge gathers in mysum order (quirk Q15)
+        const double eij[6] = {S(SL_exx, 1, 1, 1), S(SL_eyy, 1, 1, 1), S(SL_ezz, 1, 1, 1),
+                               0.25 * ((((0.0 + S(SL_eyz, 1, 0, 0)) + S(SL_eyz, 1, 1, 0)) + S(SL_eyz, 1, 0, 1)) + S(SL_eyz, 1, 1, 1)),
+                               0.25 * ((((0.0 + S(SL_exz, 0, 1, 0)) + S(SL_exz, 1, 1, 0)) + S(SL_exz, 0, 1, 1)) + S(SL_exz, 1, 1, 1)),
+                               0.25 * ((((0.0 + S(SL_exy, 0, 0, 1)) + S(SL_exy, 1, 0, 1)) + S(SL_exy, 0, 1, 1)) + S(SL_exy, 1, 1, 1))};
+        double tij[6] = {S(SL_txx, 1, 1, 1), S(SL_tyy, 1, 1, 1), S(SL_tzz, 1, 1, 1), c_tyz, c_txz, c_txy};
+        const double tijo[6] = {S(SL_oxx, 1, 1, 1), S(SL_oyy, 1, 1, 1), S(SL_ozz, 1, 1, 1), c_oyz, c_oxz, c_oxy};
+        Mix<NP> mc;
+        mix_from<NP>(pt, rc, mc);
+        vc3_centre<DIAG, NP>(a, pt, mc, c, S(SL_eta, 1, 1, 1), S(SL_theta, 1, 1, 1), eij, tij, tijo, c_lam);
+    }
+    // ---- the three edges advance together (straight-line code: three independent dependency chains), then the plastic branches
+    Mix<NP> myz, mxz, mxy;
+    mix_from<NP>(pt, ryz, myz);
+    mix_from<NP>(pt, rxz, mxz);
+    mix_from<NP>(pt, rxy, mxy);
+    EdgeAcc Eyz, Exz, Exy;
+    Eyz.etav = SHARM_YZ(SL_eta); Exz.etav = SHARM_XZ(SL_eta); Exy.etav = SHARM_XY(SL_eta);
+    Eyz.Pv = SAV_YZ(SL_theta); Exz.Pv = SAV_XZ(SL_theta); Exy.Pv = SAV_XY(SL_theta);
+    Eyz._Gdt = jr_inv(myz.G * a.dt); Exz._Gdt = jr_inv(mxz.G * a.dt); Exy._Gdt = jr_inv(mxy.G * a.dt);
+    Eyz.dtr = jr_inv_nr(a.th + Eyz.etav * Eyz._Gdt + 1.0);   // operand ≥ 1
+    Exz.dtr = jr_inv_nr(a.th + Exz.etav * Exz._Gdt + 1.0);
+    Exy.dtr = jr_inv_nr(a.th + Exy.etav * Exy._Gdt + 1.0);
+#define COMP(Q, OYZ, OXZ, OXY, TYZ, TXZ, TXY, OLDYZ, OLDXZ, OLDXY, EPYZ, EPXZ, EPXY)                                                   \
+    edge_comp<Q, OYZ>(Eyz, TYZ, OLDYZ, EPYZ);                                                                                          \
+    edge_comp<Q, OXZ>(Exz, TXZ, OLDXZ, EPXZ);                                                                                          \
+    edge_comp<Q, OXY>(Exy, TXY, OLDXY, EPXY);
+    COMP(0, false, false, false, SAV_YZ(SL_txx), SAV_XZ(SL_txx), SAV_XY(SL_txx), SAV_YZ(SL_oxx), SAV_XZ(SL_oxx), SAV_XY(SL_oxx), SAV_YZ(SL_exx),
+         SAV_XZ(SL_exx), SAV_XY(SL_exx))
+    COMP(1, false, false, false, SAV_YZ(SL_tyy), SAV_XZ(SL_tyy), SAV_XY(SL_tyy), SAV_YZ(SL_oyy), SAV_XZ(SL_oyy), SAV_XY(SL_oyy), SAV_YZ(SL_eyy),
+         SAV_XZ(SL_eyy), SAV_XY(SL_eyy))
+    COMP(2, false, false, false, SAV_YZ(SL_tzz), SAV_XZ(SL_tzz), SAV_XY(SL_tzz), SAV_YZ(SL_ozz), SAV_XZ(SL_ozz), SAV_XY(SL_ozz), SAV_YZ(SL_ezz),
+         SAV_XZ(SL_ezz), SAV_XY(SL_ezz))
+    // yz component: own on the yz edge (yz family (ic, j, k) = S(·, 1, 0, 0)); av_clamped_xz_x, av_clamped_xy_x elsewhere
+    COMP(3, true, false, false, S(SL_tyz, 1, 0, 0), SAV_XZ_X(SL_tyz), SAV_XY_X(SL_tyz), S(SL_oyz, 1, 0, 0), SAV_XZ_X(SL_oyz), SAV_XY_X(SL_oyz),
+         S(SL_eyz, 1, 0, 0), SAV_XZ_X(SL_eyz), SAV_XY_X(SL_eyz))
+    // xz component: own on the xz edge (xz family (i, jc, k) = S(·, 0, 1, 0))
+    COMP(4, false, true, false, SAV_YZ_Y(SL_txz), S(SL_txz, 0, 1, 0), SAV_XY_Y(SL_txz), SAV_YZ_Y(SL_oxz), S(SL_oxz, 0, 1, 0), SAV_XY_Y(SL_oxz),
+         SAV_YZ_Y(SL_exz), S(SL_exz, 0, 1, 0), SAV_XY_Y(SL_exz))
+    // xy component: own on the xy edge (xy family (i, j, kc) = S(·, 0, 0, 1))
+    COMP(5, false, false, true, SAV_YZ_Z(SL_txy), SAV_XZ_Z(SL_txy), S(SL_txy, 0, 0, 1), SAV_YZ_Z(SL_oxy), SAV_XZ_Z(SL_oxy), S(SL_oxy, 0, 0, 1),
+         SAV_YZ_Z(SL_exy), SAV_XZ_Z(SL_exy), S(SL_exy, 0, 0, 1))
+#undef COMP
+    edge_finish<DIAG, NP>(a, pt, myz, Eyz, vyz, a.lamyz, a.tyz_o, a.pyz);
+    edge_finish<DIAG, NP>(a, pt, mxz, Exz, vxz, a.lamxz, a.txz_o, a.pxz);
+    edge_finish<DIAG, NP>(a, pt, mxy, Exy, vxy, a.lamxy, a.txy_o, a.pxy);
+#undef S
+#undef SAV_YZ
+#undef SAV_XZ
+#undef SAV_XY
+#undef SHARM_YZ
+#undef SHARM_XZ
+#undef SHARM_XY
+#undef SAV_YZ_Y
+#undef SAV_YZ_Z
+#undef SAV_XZ_X
+#undef SAV_XZ_Z
+#undef SAV_XY_X
+#undef SAV_XY_Y
+}
+
 template <bool DIAG, int NP>
 __global__ void __launch_bounds__(32 * TYS, 16 / TYS) k_vc3_stress_sm(const __grid_constant__ V3 a, const __grid_constant__ jr_phase_tab pt)
 {
     extern __shared__ double sm[];
     const int nx = a.nx, ny = a.ny, nz = a.nz;
     const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 32 + tx;
-    const int ib = blockIdx.x * 32 + 1, jb = blockIdx.y * TYS + 1, k = blockIdx.z + 1;   // first node of the CTA (1-based)
+    const int ib = (blockIdx.x + a.bo_x) * 32 + 1, jb = (blockIdx.y + a.bo_y) * TYS + 1, k = blockIdx.z + a.bo_z + 1;   // first node of the CTA (1-based)
+    // nodes of the z-marching kernel's region (k_vc3_stress_zm): a CTA entirely inside it has nothing to do, one that straddles its rim
+    // takes the per-node body (which skips the region's nodes)
+    if (k <= a.zm_k && ib <= a.zm_i && jb <= a.zm_j) {
+        if (ib + 31 <= a.zm_i && jb + TYS - 1 <= a.zm_j) return;
+        vc3_stress_body_call<DIAG, NP>(a, pt);
+        return;
+    }
     // fast CTAs: every node has i+1 ≤ nx, j+1 ≤ ny, k+1 ≤ nz (no high-side clamp is active)
     if (!(ib + 31 <= nx - 1 && jb + TYS - 1 <= ny - 1 && k <= nz - 1)) {
         vc3_stress_body_call<DIAG, NP>(a, pt);
@@ -601,70 +721,117 @@ __global__ void __launch_bounds__(32 * TYS, 16 / TYS) k_vc3_stress_sm(const __gr
     ratios_load<NP>(pt, a.ph_xy, nxy, vxy, rxy);
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
-    // S(slot, I, J, K): tile entry at column tx+I, row ty+J, plane K — per family: cell (i0|ic, j0|jc, k0|kc); yz (i0|ic, j|j+1, k|k+1);
-    // xz (i|i+1, j0|jc, k|k+1); xy (i|i+1, j|j+1, k0|kc)
-#define S(s, I, J, K) sm[(s) * STILE + (K) * SPLANE + (ty + (J)) * SROW + tx + (I)]
-#define SAV_YZ(s) (0.25 * (S(s, 1, 0, 0) + S(s, 1, 1, 0) + S(s, 1, 0, 1) + S(s, 1, 1, 1)))
-#define SAV_XZ(s) (0.25 * (S(s, 0, 1, 0) + S(s, 1, 1, 0) + S(s, 0, 1, 1) + S(s, 1, 1, 1)))
-#define SAV_XY(s) (0.25 * (S(s, 0, 0, 1) + S(s, 1, 0, 1) + S(s, 0, 1, 1) + S(s, 1, 1, 1)))
-#define SHARM_YZ(s) jr_div_nr(4.0, jr_inv_nr(S(s, 1, 0, 0)) + jr_inv_nr(S(s, 1, 1, 0)) + jr_inv_nr(S(s, 1, 0, 1)) + jr_inv_nr(S(s, 1, 1, 1)))
-#define SHARM_XZ(s) jr_div_nr(4.0, jr_inv_nr(S(s, 0, 1, 0)) + jr_inv_nr(S(s, 1, 1, 0)) + jr_inv_nr(S(s, 0, 1, 1)) + jr_inv_nr(S(s, 1, 1, 1)))
-#define SHARM_XY(s) jr_div_nr(4.0, jr_inv_nr(S(s, 0, 0, 1)) + jr_inv_nr(S(s, 1, 0, 1)) + jr_inv_nr(S(s, 0, 1, 1)) + jr_inv_nr(S(s, 1, 1, 1)))
-    /* harmonic means: η is strictly positive and in the normal range, so the branch-free IEEE-exact reciprocal / quotient sequences of
-       tma.cuh give the same bits as 1 / x and 4 / x without the slow-path call scaffolding (15 reciprocals per node) */
-#define SAV_YZ_Y(s) (0.25 * (S(s, 0, 0, 0) + S(s, 1, 0, 0) + S(s, 0, 1, 0) + S(s, 1, 1, 0)))   /* xz family: (ic,j0,kc),(i1,j0,kc),(ic,jc,kc),(i1,jc,kc) */
-#define SAV_YZ_Z(s) (0.25 * (S(s, 0, 0, 0) + S(s, 1, 0, 0) + S(s, 0, 0, 1) + S(s, 1, 0, 1)))   /* xy family: (ic,jc,k0),(i1,jc,k0),(ic,jc,kc),(i1,jc,kc) */
-#define SAV_XZ_X(s) (0.25 * (S(s, 0, 0, 0) + S(s, 1, 0, 0) + S(s, 1, 1, 0) + S(s, 0, 1, 0)))   /* yz family: (i0,jc,kc),(ic,jc,kc),(ic,j1,kc),(i0,j1,kc) */
-#define SAV_XZ_Z(s) (0.25 * (S(s, 0, 0, 0) + S(s, 0, 1, 0) + S(s, 0, 0, 1) + S(s, 0, 1, 1)))   /* xy family: (ic,jc,k0),(ic,j1,k0),(ic,jc,kc),(ic,j1,kc) */
-#define SAV_XY_X(s) (0.25 * (S(s, 0, 0, 0) + S(s, 1, 0, 0) + S(s, 0, 0, 1) + S(s, 1, 0, 1)))   /* yz family: (i0,jc,kc),(ic,jc,kc),(i0,jc,k1),(ic,jc,k1) */
-#define SAV_XY_Y(s) (0.25 * (S(s, 0, 0, 0) + S(s, 0, 1, 0) + S(s, 0, 0, 1) + S(s, 0, 1, 1)))   /* xz family: (ic,j0,kc),(ic,jc,kc),(ic,j0,k1),(ic,jc,k1) */
-    {   // ---- centre: cell (i, j, k) = S(·, 1, 1, 1); edge gathers in mysum order (quirk Q15)
-        const double eij[6] = {S(SL_exx, 1, 1, 1), S(SL_eyy, 1, 1, 1), S(SL_ezz, 1, 1, 1),
-                               0.25 * ((((0.0 + S(SL_eyz, 1, 0, 0)) + S(SL_eyz, 1, 1, 0)) + S(SL_eyz, 1, 0, 1)) + S(SL_eyz, 1, 1, 1)),
-                               0.25 * ((((0.0 + S(SL_exz, 0, 1, 0)) + S(SL_exz, 1, 1, 0)) + S(SL_exz, 0, 1, 1)) + S(SL_exz, 1, 1, 1)),
-                               0.25 * ((((0.0 + S(SL_exy, 0, 0, 1)) + S(SL_exy, 1, 0, 1)) + S(SL_exy, 0, 1, 1)) + S(SL_exy, 1, 1, 1))};
-        double tij[6] = {S(SL_txx, 1, 1, 1), S(SL_tyy, 1, 1, 1), S(SL_tzz, 1, 1, 1), c_tyz, c_txz, c_txy};
-        const double tijo[6] = {S(SL_oxx, 1, 1, 1), S(SL_oyy, 1, 1, 1), S(SL_ozz, 1, 1, 1), c_oyz, c_oxz, c_oxy};
-        Mix<NP> mc;
-        mix_from<NP>(pt, rc, mc);
-        vc3_centre<DIAG, NP>(a, pt, mc, c, S(SL_eta, 1, 1, 1), S(SL_theta, 1, 1, 1), eij, tij, tijo, c_lam);
+    TilePair A;
+    A.sm = sm; A.base = ty * SROW + tx;
+    vc3_sm_compute<DIAG, NP>(a, pt, A, c, vyz, vxz, vxy, rc, ryz, rxz, rxy, c_tyz, c_txz, c_txy, c_oyz, c_oxz, c_oxy, c_lam);
+}
+
+// ---- z-marching variant ----------------------------------------------------------------------------------------------------------------
+// One CTA owns a column of 32 × TYZ nodes and marches a chunk of planes k = kbeg … kend−1.  Every array of the 20 keeps a ring of THREE tile
+// planes in shared memory: a z-step needs two planes per array (cell / xy families: k−1 and k; yz / xz families: k and k+1), so one new plane
+// per array arrives per step — half the staging traffic and instructions of k_vc3_stress_sm, no re-fetch of the shared plane — and it is
+// requested one step ahead (cp.async into the free ring slot), so the copies run under the arithmetic of the current step.  The node's
+// own-position operands (phase ratios of the four families, centre shear copies, λ) are loaded one step ahead into registers.  ONE barrier per
+// step: behind it every copy for step k has landed and every thread has left step k−1, whose oldest planes the next request overwrites.
+// Region: the nodes whose neighbourhood needs no high-side clamp (i ≤ 32·⌊(nx−1)/32⌋, j ≤ TYZ·⌊(ny−1)/TYZ⌋, k ≤ nz−1); the rim goes to
+// k_vc3_stress_sm / the per-node body, which skip the region (V3::zm_*).  Same arithmetic (vc3_sm_compute), bit-identical results.
+template <int NP>
+struct OwnOps {
+    double rc[NP], ryz[NP], rxz[NP], rxy[NP];
+    double tyz, txz, txy, oyz, oxz, oxy, lam;
+};
+template <int NP>
+__device__ __forceinline__ void own_load(const V3 &a, const jr_phase_tab &pt, size_t c, size_t vyz, size_t vxz, size_t vxy, size_t nc, size_t nyz, size_t nxz,
+                                         size_t nxy, OwnOps<NP> &o)
+{
+    ratios_load<NP>(pt, a.ph_c, nc, c, o.rc);
+    o.tyz = a.tyzc[c]; o.txz = a.txzc[c]; o.txy = a.txyc[c];
+    o.oyz = __ldg(a.oyzc + c); o.oxz = __ldg(a.oxzc + c); o.oxy = __ldg(a.oxyc + c); o.lam = a.lam[c];
+    ratios_load<NP>(pt, a.ph_yz, nyz, vyz, o.ryz);
+    ratios_load<NP>(pt, a.ph_xz, nxz, vxz, o.rxz);
+    ratios_load<NP>(pt, a.ph_xy, nxy, vxy, o.rxy);
+}
+
+template <int NP, int TYZ>
+__global__ void __launch_bounds__(32 * TYZ, 1) k_vc3_stress_zm(const __grid_constant__ V3 a, const __grid_constant__ jr_phase_tab pt)
+{
+    extern __shared__ double sm[];
+    constexpr int ZROW = 33, ZPLANE = ZROW * (TYZ + 1), ZTILE = 3 * ZPLANE, NTHR = 32 * TYZ, NIT = (ZPLANE + NTHR - 1) / NTHR;
+    const int nx = a.nx, ny = a.ny, nz = a.nz;
+    const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 32 + tx;
+    const int ib = blockIdx.x * 32 + 1, jb = blockIdx.y * TYZ + 1;
+    const int kbeg = blockIdx.z * a.zm_chunk + 1, kend = min(kbeg + a.zm_chunk, a.zm_k + 1);   // planes [kbeg, kend)
+    const int i = ib + tx, j = jb + ty;
+    const double *src[SL_COUNT] = {a.eta_o, a.theta, a.txx_i, a.tyy_i, a.tzz_i, a.oxx, a.oyy, a.ozz, a.exx, a.eyy, a.ezz,
+                                   a.tyz_i, a.oyz, a.eyz, a.txz_i, a.oxz, a.exz, a.txy_i, a.oxy, a.exy};
+    const size_t sc = (size_t)nx * ny, syz = (size_t)nx * (ny + 1), sxz = (size_t)(nx + 1) * ny, sxy = (size_t)(nx + 1) * (ny + 1);
+    // the tile elements this thread stages (the same ones for every plane): offsets of plane 1 in the four families
+    // (tile origins, low-side clamp to index 1: cell (i−1, j−1); yz (i−1, j); xz (i, j−1); xy (i, j))
+    size_t e_oc[NIT], e_oy[NIT], e_oz[NIT], e_ox[NIT];
+#pragma unroll
+    for (int it = 0; it < NIT; it++) {
+        const int e = tid + it * NTHR, r = e / ZROW, cc = e - r * ZROW;
+        const int im = max(ib - 1 + cc, 1), jm = max(jb - 1 + r, 1), ip = ib + cc, jp = jb + r;
+        e_oc[it] = IX3(nx, ny, im, jm, 1); e_oy[it] = IX3(nx, ny + 1, im, jp, 1); e_oz[it] = IX3(nx + 1, ny, ip, jm, 1); e_ox[it] = IX3(nx + 1, ny + 1, ip, jp, 1);
     }
-    // ---- the three edges advance together (straight-line code: three independent dependency chains), then the plastic branches
-    Mix<NP> myz, mxz, mxy;
-    mix_from<NP>(pt, ryz, myz);
-    mix_from<NP>(pt, rxz, mxz);
-    mix_from<NP>(pt, rxy, mxy);
-    EdgeAcc Eyz, Exz, Exy;
-    Eyz.etav = SHARM_YZ(SL_eta); Exz.etav = SHARM_XZ(SL_eta); Exy.etav = SHARM_XY(SL_eta);
-    Eyz.Pv = SAV_YZ(SL_theta); Exz.Pv = SAV_XZ(SL_theta); Exy.Pv = SAV_XY(SL_theta);
-    Eyz._Gdt = jr_inv(myz.G * a.dt); Exz._Gdt = jr_inv(mxz.G * a.dt); Exy._Gdt = jr_inv(mxy.G * a.dt);
-    Eyz.dtr = jr_inv_nr(a.th + Eyz.etav * Eyz._Gdt + 1.0);   // operand ≥ 1
-    Exz.dtr = jr_inv_nr(a.th + Exz.etav * Exz._Gdt + 1.0);
-    Exy.dtr = jr_inv_nr(a.th + Exy.etav * Exy._Gdt + 1.0);
-#define COMP(Q, OYZ, OXZ, OXY, TYZ, TXZ, TXY, OLDYZ, OLDXZ, OLDXY, EPYZ, EPXZ, EPXY)                                                   \
-    edge_comp<Q, OYZ>(Eyz, TYZ, OLDYZ, EPYZ);                                                                                          \
-    edge_comp<Q, OXZ>(Exz, TXZ, OLDXZ, EPXZ);                                                                                          \
-    edge_comp<Q, OXY>(Exy, TXY, OLDXY, EPXY);
-    COMP(0, false, false, false, SAV_YZ(SL_txx), SAV_XZ(SL_txx), SAV_XY(SL_txx), SAV_YZ(SL_oxx), SAV_XZ(SL_oxx), SAV_XY(SL_oxx), SAV_YZ(SL_exx),
-         SAV_XZ(SL_exx), SAV_XY(SL_exx))
-    COMP(1, false, false, false, SAV_YZ(SL_tyy), SAV_XZ(SL_tyy), SAV_XY(SL_tyy), SAV_YZ(SL_oyy), SAV_XZ(SL_oyy), SAV_XY(SL_oyy), SAV_YZ(SL_eyy),
-         SAV_XZ(SL_eyy), SAV_XY(SL_eyy))
-    COMP(2, false, false, false, SAV_YZ(SL_tzz), SAV_XZ(SL_tzz), SAV_XY(SL_tzz), SAV_YZ(SL_ozz), SAV_XZ(SL_ozz), SAV_XY(SL_ozz), SAV_YZ(SL_ezz),
-         SAV_XZ(SL_ezz), SAV_XY(SL_ezz))
-    // yz component: own on the yz edge (yz family (ic, j, k) = S(·, 1, 0, 0)); av_clamped_xz_x, av_clamped_xy_x elsewhere
-    COMP(3, true, false, false, S(SL_tyz, 1, 0, 0), SAV_XZ_X(SL_tyz), SAV_XY_X(SL_tyz), S(SL_oyz, 1, 0, 0), SAV_XZ_X(SL_oyz), SAV_XY_X(SL_oyz),
-         S(SL_eyz, 1, 0, 0), SAV_XZ_X(SL_eyz), SAV_XY_X(SL_eyz))
-    // xz component: own on the xz edge (xz family (i, jc, k) = S(·, 0, 1, 0))
-    COMP(4, false, true, false, SAV_YZ_Y(SL_txz), S(SL_txz, 0, 1, 0), SAV_XY_Y(SL_txz), SAV_YZ_Y(SL_oxz), S(SL_oxz, 0, 1, 0), SAV_XY_Y(SL_oxz),
-         SAV_YZ_Y(SL_exz), S(SL_exz, 0, 1, 0), SAV_XY_Y(SL_exz))
-    // xy component: own on the xy edge (xy family (i, j, kc) = S(·, 0, 0, 1))
-    COMP(5, false, false, true, SAV_YZ_Z(SL_txy), SAV_XZ_Z(SL_txy), S(SL_txy, 0, 0, 1), SAV_YZ_Z(SL_oxy), SAV_XZ_Z(SL_oxy), S(SL_oxy, 0, 0, 1),
-         SAV_YZ_Z(SL_exy), SAV_XZ_Z(SL_exy), S(SL_exy, 0, 0, 1))
-#undef COMP
-    edge_finish<DIAG, NP>(a, pt, myz, Eyz, vyz, a.lamyz, a.tyz_o, a.pyz);
-    edge_finish<DIAG, NP>(a, pt, mxz, Exz, vxz, a.lamxz, a.txz_o, a.pxz);
-    edge_finish<DIAG, NP>(a, pt, mxy, Exy, vxy, a.lamxy, a.txy_o, a.pxy);
-#undef S
+    // group A = cell + xy families (plane P → ring slot P % 3), group B = yz + xz families
+    auto stage_A = [&](int P) {
+        const int slot = (P % 3) * ZPLANE;
+#pragma unroll
+        for (int it = 0; it < NIT; it++) {
+            const int e = tid + it * NTHR;
+            if (e < ZPLANE) {
+                const size_t oc = e_oc[it] + (size_t)(P - 1) * sc, ox = e_ox[it] + (size_t)(P - 1) * sxy;
+#pragma unroll
+                for (int s = 0; s < SL_tyz; s++) cp_async8(sm + s * ZTILE + slot + e, src[s] + oc);
+#pragma unroll
+                for (int s = SL_txy; s < SL_COUNT; s++) cp_async8(sm + s * ZTILE + slot + e, src[s] + ox);
+            }
+        }
+    };
+    auto stage_B = [&](int P) {
+        const int slot = (P % 3) * ZPLANE;
+#pragma unroll
+        for (int it = 0; it < NIT; it++) {
+            const int e = tid + it * NTHR;
+            if (e < ZPLANE) {
+                const size_t oy = e_oy[it] + (size_t)(P - 1) * syz, oz = e_oz[it] + (size_t)(P - 1) * sxz;
+#pragma unroll
+                for (int s = SL_tyz; s < SL_txz; s++) cp_async8(sm + s * ZTILE + slot + e, src[s] + oy);
+#pragma unroll
+                for (int s = SL_txz; s < SL_txy; s++) cp_async8(sm + s * ZTILE + slot + e, src[s] + oz);
+            }
+        }
+    };
+    // prologue: the planes of step kbeg
+    if (kbeg > 1) stage_A(kbeg - 1);
+    stage_A(kbeg);
+    stage_B(kbeg);
+    stage_B(kbeg + 1);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    const size_t nc = sc * nz, nyz = syz * (nz + 1), nxz = sxz * (nz + 1), nxy = sxy * nz;
+    size_t c = IX3(nx, ny, i, j, kbeg), vyz = IX3(nx, ny + 1, i, j, kbeg), vxz = IX3(nx + 1, ny, i, j, kbeg), vxy = IX3(nx + 1, ny + 1, i, j, kbeg);
+    OwnOps<NP> cur, nxt;
+    own_load<NP>(a, pt, c, vyz, vxz, vxy, nc, nyz, nxz, nxy, cur);
+    TileRing<ZPLANE, ZROW> A;
+    A.sm = sm; A.base = ty * ZROW + tx;
+    for (int k = kbeg; k < kend; ++k) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        const bool more = k + 1 < kend;
+        if (more) {   // the planes step k+1 adds, and its own-position operands
+            stage_A(k + 1);
+            stage_B(k + 2);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            own_load<NP>(a, pt, c + sc, vyz + syz, vxz + sxz, vxy + sxy, nc, nyz, nxz, nxy, nxt);
+        }
+        A.aLo = (k == 1 ? 1 : (k - 1) % 3) * ZPLANE; A.aHi = (k % 3) * ZPLANE;
+        A.bLo = A.aHi; A.bHi = ((k + 1) % 3) * ZPLANE;
+        vc3_sm_compute<false, NP>(a, pt, A, c, vyz, vxz, vxy, cur.rc, cur.ryz, cur.rxz, cur.rxy, cur.tyz, cur.txz, cur.txy, cur.oyz, cur.oxz, cur.oxy,
+                                  cur.lam);
+        if (more) cur = nxt;
+        c += sc; vyz += syz; vxz += sxz; vxy += sxy;
+    }
 }
 
 // global-memory variant: 3 CTAs of 256 threads per SM (≤ 80 registers, a few spilled doubles) — bound by the latency of its ≈ 280 loads per
@@ -929,10 +1096,52 @@ static void launch_prep(bool diag, bool maxloc, int nphase, dim3 grd, cudaStream
     else launch_prep_np<JR_MAX_PHASES>(diag, maxloc, grd, st, k, pt);
 }
 
+// z-marching stress kernel (k_vc3_stress_zm): rows per CTA (0 = off: the per-plane staged kernel everywhere), planes per CTA
+static int zm_rows()
+{
+    // default OFF: measured slower than the per-plane kernel (257^3, three phases: 3.80 ms per iteration with 8 rows, 4.81 ms with 12, against
+    // 3.30 ms) — the three-plane ring leaves room for one CTA per SM (8 / 12 warps instead of 16), and the kernel is bound by the latency of its
+    // FP64 / shared-memory chains, not by DRAM (profiles/r02_vc3_zmarch.md).  Opt-in: JRB200_VC3_ZM=8 | 12.  (Read per call: the tests switch
+    // variants inside one process.)
+    int v = 0;
+    if (const char *e = getenv("JRB200_VC3_ZM")) v = atoi(e);
+    if (v != 0 && v != 8 && v != 12) v = 0;
+    return v;
+}
+static int zm_chunk_of(int planes, int ctas_per_layer, int sm_count)
+{
+    if (const char *e = getenv("JRB200_VC3_ZM_CHUNK")) { const int c = atoi(e); if (c >= 1) return c; }
+    // one CTA per SM: pick the number of z-chunks (≥ 16 planes each, so the two-plane prologue stays small) whose CTA count fills whole waves best
+    int best_n = 1;
+    double best = -1.0;
+    for (int n = 1; n <= planes / 16 || n == 1; n++) {
+        const long tot = (long)n * ctas_per_layer;
+        const long waves = (tot + sm_count - 1) / sm_count;
+        double eff = (double)tot / (double)(waves * sm_count);
+        if (waves < 4) eff *= 0.25 * waves;   // too few waves: the pipeline fill of every CTA is exposed
+        if (eff > best + 1e-9) { best = eff; best_n = n; }
+    }
+    return (planes + best_n - 1) / best_n;
+}
+
+template <int NP, int TYZ>
+static void launch_zm(dim3 g, cudaStream_t st, const V3 &k, const jr_phase_tab &pt)
+{
+    constexpr size_t smem = (size_t)SL_COUNT * 3 * 33 * (TYZ + 1) * sizeof(double);
+    static bool attr = false;   // per instantiation
+    if (!attr) {
+        cudaFuncSetAttribute(k_vc3_stress_zm<NP, TYZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr = true;
+    }
+    k_vc3_stress_zm<NP, TYZ><<<g, dim3(32, TYZ, 1), smem, st>>>(k, pt);
+}
+
+// returns the number of launches
 template <int NP>
-static void launch_stress_np(bool diag, dim3 grd, cudaStream_t st, const V3 &k, const jr_phase_tab &pt)
+static int launch_stress_np(bool diag, dim3 grd, cudaStream_t st, V3 k, const jr_phase_tab &pt, int sm_count)
 {
     static const bool use_sm = !(getenv("JRB200_VC_STRESS_GLOBAL") && atoi(getenv("JRB200_VC_STRESS_GLOBAL")));
+    k.bo_x = k.bo_y = k.bo_z = 0; k.zm_i = k.zm_j = k.zm_k = 0; k.zm_chunk = 1;
     if (use_sm) {
         const size_t smem = (size_t)SL_COUNT * STILE * sizeof(double);
         static bool attr = false;   // per instantiation
@@ -942,20 +1151,41 @@ static void launch_stress_np(bool diag, dim3 grd, cudaStream_t st, const V3 &k, 
             attr = true;
         }
         const dim3 blk(32, TYS, 1), g2(grd.x, (grd.y * 8 + TYS - 1) / TYS, grd.z);
+        const int rows = zm_rows();
+        const int zi = ((k.nx - 1) / 32) * 32, zj = rows ? ((k.ny - 1) / rows) * rows : 0, zk = k.nz - 1;
+        if (!diag && rows && TYS == 8 && zi >= 32 && zj >= rows && zk >= 2) {
+            // interior: z-marching CTAs; rim (high-side boundary columns / rows / planes): the per-plane kernel on three slabs of its grid
+            k.zm_i = zi; k.zm_j = zj; k.zm_k = zk;
+            k.zm_chunk = zm_chunk_of(zk, (zi / 32) * (zj / rows), sm_count);
+            const dim3 gz(zi / 32, zj / rows, (zk + k.zm_chunk - 1) / k.zm_chunk);
+            if (rows == 12) launch_zm<NP, 12>(gz, st, k, pt);
+            else launch_zm<NP, 8>(gz, st, k, pt);
+            int n = 1;
+            const int by0 = zj / 8, bx0 = zi / 32;   // first block row / column of the per-plane grid that is not entirely inside the region
+            V3 r = k;
+            r.bo_z = zk;   // (a) the planes above the region
+            if ((int)g2.z > zk) { k_vc3_stress_sm<false, NP><<<dim3(g2.x, g2.y, g2.z - zk), blk, smem, st>>>(r, pt); n++; }
+            r.bo_z = 0; r.bo_y = by0;   // (b) the block rows beyond the region
+            if ((int)g2.y > by0) { k_vc3_stress_sm<false, NP><<<dim3(g2.x, g2.y - by0, zk), blk, smem, st>>>(r, pt); n++; }
+            r.bo_y = 0; r.bo_x = bx0;   // (c) the block columns beyond the region, below (b)
+            if ((int)g2.x > bx0 && by0 > 0) { k_vc3_stress_sm<false, NP><<<dim3(g2.x - bx0, by0, zk), blk, smem, st>>>(r, pt); n++; }
+            return n;
+        }
         if (diag) k_vc3_stress_sm<true, NP><<<g2, blk, smem, st>>>(k, pt);
         else k_vc3_stress_sm<false, NP><<<g2, blk, smem, st>>>(k, pt);
-        return;
+        return 1;
     }
     if (diag) k_vc3_stress<true, NP><<<grd, BLK3, 0, st>>>(k, pt);
     else k_vc3_stress<false, NP><<<grd, BLK3, 0, st>>>(k, pt);
+    return 1;
 }
-static void launch_stress(bool diag, int nphase, dim3 grd, cudaStream_t st, const V3 &k, const jr_phase_tab &pt)
+static int launch_stress(bool diag, int nphase, dim3 grd, cudaStream_t st, const V3 &k, const jr_phase_tab &pt, int sm_count)
 {
-    if (nphase <= 1) launch_stress_np<1>(diag, grd, st, k, pt);
-    else if (nphase == 2) launch_stress_np<2>(diag, grd, st, k, pt);
-    else if (nphase == 3) launch_stress_np<3>(diag, grd, st, k, pt);
-    else if (nphase == 4) launch_stress_np<4>(diag, grd, st, k, pt);
-    else launch_stress_np<JR_MAX_PHASES>(diag, grd, st, k, pt);
+    if (nphase <= 1) return launch_stress_np<1>(diag, grd, st, k, pt, sm_count);
+    else if (nphase == 2) return launch_stress_np<2>(diag, grd, st, k, pt, sm_count);
+    else if (nphase == 3) return launch_stress_np<3>(diag, grd, st, k, pt, sm_count);
+    else if (nphase == 4) return launch_stress_np<4>(diag, grd, st, k, pt, sm_count);
+    return launch_stress_np<JR_MAX_PHASES>(diag, grd, st, k, pt, sm_count);
 }
 
 // one PT iteration: τ set (it & 1) → set ((it + 1) & 1), η likewise
@@ -976,8 +1206,7 @@ static int plan3_iter(jr_context *ctx, Plan3 *p, int64_t it, bool diag, const jr
         if ((rc = jr_comm_halo(ctx, &H, 1))) return rc;
     }
     launch_prep(diag, !p->multi, p->pt.n, grid3p(nx, ny, nz, k.xfull_c), st, k, p->pt);
-    launch_stress(diag, p->pt.n, grid3p(nx + 1, ny + 1, nz + 1, k.xfull_n), st, k, p->pt);
-    ctx->launches += 2;
+    ctx->launches += 1 + launch_stress(diag, p->pt.n, grid3p(nx + 1, ny + 1, nz + 1, k.xfull_n), st, k, p->pt, ctx->sm_count);
     JR_CHECK_LAUNCH();
     if (p->multi) {  // update_halo!(τyz); update_halo!(τxz); update_halo!(τxy)  :578-580
         const int32_t eyz[3] = {nx, ny + 1, nz + 1}, exz[3] = {nx + 1, ny, nz + 1}, exy[3] = {nx + 1, ny + 1, nz};

@@ -65,6 +65,23 @@ def test_vc3_fixed_iterations_random_state(oracle, ni):
         compare_slots(st, d, STATE + DIAG, TOL, f"3D-VC ni={ni} niter={niter}")
 
 
+@pytest.mark.parametrize("rows,chunk", [("0", None), ("8", None), ("8", "3"), ("12", None), ("12", "5")])
+@pytest.mark.parametrize("ni", [(70, 29, 21), (40, 40, 40), (33, 13, 3)])
+def test_vc3_stress_kernel_variants(oracle, monkeypatch, ni, rows, chunk):
+    """the z-marching stress kernel (interior) + the per-plane kernel on the rim slabs, for both tile heights and for z-chunks that do not
+    divide the plane count, against the oracle — and the per-plane kernel alone (JRB200_VC3_ZM=0): all the same bits"""
+    from justrelax_jl_b200 import setups
+
+    monkeypatch.setenv("JRB200_VC3_ZM", rows)
+    if chunk is not None:
+        monkeypatch.setenv("JRB200_VC3_ZM_CHUNK", chunk)
+    s = setups.random_vc3d(ni, seed=300 + ni[0])
+    flags = dict(free_slip=[1] * 6, no_slip=[0] * 6, periodic=[0] * 6)
+    st, d = _run(oracle, s, flags, 4, False)
+    assert d["lam"].max() > 0 and np.abs(d["pyz"]).max() > 0, "the random state must yield somewhere"
+    compare_slots(st, d, STATE + DIAG, TOL, f"3D-VC stress variants ni={ni} rows={rows} chunk={chunk}")
+
+
 def test_vc3_thermal_stress_pressure_form(oracle):
     """args.ΔT given: compute_P! takes the thermal-stress form (PressureKernels.jl:128-149,197-206) with α = fn_ratio(get_thermal_expansion, …);
     parity with the oracle, and the pressure really differs from the run without ΔT"""
