@@ -143,6 +143,53 @@ __device__ __forceinline__ void jr_plastic_grads(const jr_phase_tab &pt, const d
         dFdP = fma(r, fp, dFdP);
     }
 }
+// the same gradients in two parts, so that the divisions of ∂Q/∂τ are only paid where a node yields (and only for the components it uses):
+// jr_plastic_dP = the pressure derivatives (needed everywhere: the volumetric term of λ), jr_plastic_dQ<NC, C> = component C of ∂Q/∂τ.
+// Operation for operation the accumulations of jr_plastic_grads (same order over the phases, same fma), hence the same bits.
+__device__ __forceinline__ void jr_plastic_dP(const jr_phase_tab &pt, const double *__restrict__ ph, size_t stride, size_t q, double &dQdP, double &dFdP)
+{
+    dQdP = 0.0;
+    dFdP = 0.0;
+    for (int p = 0; p < pt.n; p++) {
+        const double r = ph[(size_t)p * stride + q];
+        if (r == 0.0) continue;
+        dQdP = fma(r, pt.has_pl[p] ? -pt.sinpsi[p] : 0.0, dQdP);
+        dFdP = fma(r, pt.has_pl[p] ? -pt.sinphi[p] : 0.0, dFdP);
+    }
+}
+// jr_ratio_G + jr_ratio_Kb + jr_plastic_params + jr_plastic_dP in ONE sweep over the phases (one load of each ratio; every accumulation keeps
+// its own order, so each result has the bits of the separate function)
+__device__ __forceinline__ void jr_mix_sweep(const jr_phase_tab &pt, const double *__restrict__ ph, size_t stride, size_t q, double &G, double &Kb,
+                                             bool &is_pl, double &eta_reg, double &dQdP, double &dFdP)
+{
+    G = 0.0; Kb = 0.0; eta_reg = 0.0; dQdP = 0.0; dFdP = 0.0;
+    is_pl = false;
+    for (int p = 0; p < pt.n; p++) {
+        const double r = ph[(size_t)p * stride + q];
+        const bool nz = r != 0.0, pl = nz && pt.has_pl[p];
+        G += nz ? pt.G[p] * r : 0.0;
+        Kb += nz ? pt.Kb[p] * r : 0.0;
+        if (pl) is_pl = true;
+        eta_reg += (pl ? pt.eta_vp[p] : 0.0) * r;
+        if (nz) {
+            dQdP = fma(r, pt.has_pl[p] ? -pt.sinpsi[p] : 0.0, dQdP);
+            dFdP = fma(r, pt.has_pl[p] ? -pt.sinphi[p] : 0.0, dFdP);
+        }
+    }
+}
+template <int NC, int C>
+__device__ __forceinline__ double jr_plastic_dQ(const jr_phase_tab &pt, const double *__restrict__ ph, size_t stride, size_t q, const double *t, double tII)
+{
+    constexpr int NN = NC == 3 ? 2 : 3;
+    double acc = 0.0;
+    for (int p = 0; p < pt.n; p++) {
+        const double r = ph[(size_t)p * stride + q];
+        if (r == 0.0) continue;
+        const double g = pt.has_pl[p] ? (C < NN ? 0.5 * t[C] / tII : 0.5 * (t[C] / tII)) : 0.0;
+        acc = fma(r, g, acc);
+    }
+    return acc;
+}
 __device__ __forceinline__ double jr_density(const jr_phase_tab &pt, int p, double T, double P)
 {
     if (pt.rho_kind[p] == 1) return pt.rho0[p] * (1.0 - pt.alpha[p] * (T - pt.T0[p]) + pt.beta[p] * (P - pt.P0[p]));

@@ -50,7 +50,7 @@ __device__ __forceinline__ void jr_prefetch_l1(const double *p) { asm volatile("
 // RARE (VC only): the seldom-used options — args.ΔT (thermal-stress pressure form), DisplacementBoundaryConditions, cohesion softening,
 // and INC — are compiled only into the RARE instantiations, so the common path keeps its register budget (no spills)
 template <bool VC, bool DIAG, int TYT, bool INC = false, bool RARE = false>
-__global__ void __launch_bounds__(TX * TYT) k_stokes2d(const __grid_constant__ K2 a, const __grid_constant__ jr_phase_tab pt)
+__global__ void __launch_bounds__(TX * TYT, TYT <= 16 ? 2 : 1) k_stokes2d(const __grid_constant__ K2 a, const __grid_constant__ jr_phase_tab pt)
 {
     constexpr int NTT = TX * TYT;
     extern __shared__ double sm[];
@@ -172,10 +172,9 @@ __global__ void __launch_bounds__(TX * TYT) k_stokes2d(const __grid_constant__ K
             const double txxov = AVC(s_txxo), tyyov = AVC(s_tyyo);
 #undef AVC
             bool is_pl;
-            double eta_reg;
-            jr_plastic_params(pt, a.ph_v, nv, v, is_pl, eta_reg);
-            const double Gv = jr_ratio_G(pt, a.ph_v, nv, v);
-            const double _Gdt = jr_inv(Gv * a.dt), _G = jr_inv(Gv), Kv = jr_ratio_Kb(pt, a.ph_v, nv, v);
+            double eta_reg, Gv, Kv, dQdP, dFdP;   // phase mixture at the vertex: one sweep over the ratios (jr_mix_sweep)
+            jr_mix_sweep(pt, a.ph_v, nv, v, Gv, Kv, is_pl, eta_reg, dQdP, dFdP);
+            const double _Gdt = jr_inv(Gv * a.dt), _G = jr_inv(Gv);
             // harmonic mean of η (> 0, normal range) and 1/(θ_dτ + η/(G dt) + 1) (operand ≥ 1): branch-free IEEE-exact sequences
             const double etav = jr_div_nr(4.0, jr_inv_nr(s_eta[q00]) + jr_inv_nr(s_eta[qcc]) + jr_inv_nr(s_eta[q0c]) + jr_inv_nr(s_eta[qc0]));
             const double dtr = INC ? jr_inv(a.th * a.dt + etav * _G + a.dt) : jr_inv_nr(a.th + etav * _Gdt + 1.0);
@@ -192,8 +191,7 @@ __global__ void __launch_bounds__(TX * TYT) k_stokes2d(const __grid_constant__ K
             }
             const double trial[3] = {txxv + dxx, tyyv + dyy, txyv + dxy};
             const double tIIv = inv2(dxx + txxv, dyy + tyyv, dxy + txyv);
-            double dQ[3], dQdP, dFdP;
-            jr_plastic_grads<3>(pt, a.ph_v, nv, v, trial, dQ, dQdP, dFdP);
+            // (∂Q/∂τxy itself only where the vertex yields — jr_plastic_dQ: the divisions of compute_plastic_gradients_phase)
             const double volume = isinf(Kv) ? 0.0 : Kv * a.dt * dFdP * dQdP;
             double Fv;
             if (RARE && pt.any_soft) {  // cohesion softening: EII interpolated to the vertex (av_clamped, StressKernels.jl:1031)
@@ -204,7 +202,7 @@ __global__ void __launch_bounds__(TX * TYT) k_stokes2d(const __grid_constant__ K
             lamv = a.lamv_i[v];
             if (is_pl && tIIv != 0.0 && Fv > 0) {
                 lamv = fma(a.rel, fmax(Fv, 0.0) / ((INC ? etav * dtr * a.dt : etav * dtr) + eta_reg + volume), (1.0 - a.rel) * lamv);
-                pxy = lamv * dQ[2];
+                pxy = lamv * jr_plastic_dQ<3, 2>(pt, a.ph_v, nv, v, trial, tIIv);   // tIIv = second invariant of `trial` (a + b = b + a exactly)
                 txyn = txyv + (INC ? fma(-2.0, etav * a.dt * pxy * dtr, dxy) : fma(-2.0, etav * pxy * dtr, dxy));
             } else {
                 txyn = txyv + dxy;
@@ -215,8 +213,8 @@ __global__ void __launch_bounds__(TX * TYT) k_stokes2d(const __grid_constant__ K
         if (cell && tx <= TX - 2 && ty <= TYT - 2) {
             const double _Gdt = jr_inv(Gc * a.dt);
             bool is_pl;
-            double eta_reg;
-            jr_plastic_params(pt, a.ph_c, nc, c, is_pl, eta_reg);
+            double eta_reg, dQdP, dFdP, G_unused, K_unused;
+            jr_mix_sweep(pt, a.ph_c, nc, c, G_unused, K_unused, is_pl, eta_reg, dQdP, dFdP);   // (G, K of the centre are stage-1 values: dead code here)
             const double _G = jr_inv(Gc);
             const double dtr = INC ? 1.0 / (a.th * a.dt + eta * _G + a.dt) : 1.0 / (a.th + eta * _Gdt + 1.0);
             // strain rate at the centre (INC: ε = Δε·(1/dt) element by element, then the same four-vertex average)
@@ -236,13 +234,14 @@ __global__ void __launch_bounds__(TX * TYT) k_stokes2d(const __grid_constant__ K
             }
             tII = inv2(dt_[0] + tij[0], dt_[1] + tij[1], dt_[2] + tij[2]);
             const double trial[3] = {tij[0] + dt_[0], tij[1] + dt_[1], tij[2] + dt_[2]};
-            double dQ[3], dQdP, dFdP;
-            jr_plastic_grads<3>(pt, a.ph_c, nc, c, trial, dQ, dQdP, dFdP);
             const double volume = isinf(Kc) ? 0.0 : Kc * a.dt * dFdP * dQdP;
             const double Fc = (RARE && pt.any_soft) ? jr_yield_F_soft(pt, a.ph_c, nc, c, thn, tII, a.EII[c]) : jr_yield_F(pt, a.ph_c, nc, c, thn, tII);
             lam = a.lam_i[c];
             if (is_pl && tII != 0.0 && Fc > 0) {
                 lam = fma(a.rel, fmax(Fc, 0.0) / ((INC ? eta * dtr * a.dt : eta * dtr) + eta_reg + volume), (1.0 - a.rel) * lam);
+                const double tIIt = tII;   // second invariant of `trial`
+                const double dQ[3] = {jr_plastic_dQ<3, 0>(pt, a.ph_c, nc, c, trial, tIIt), jr_plastic_dQ<3, 1>(pt, a.ph_c, nc, c, trial, tIIt),
+                                      jr_plastic_dQ<3, 2>(pt, a.ph_c, nc, c, trial, tIIt)};
                 double epl[3];
 #pragma unroll
                 for (int q = 0; q < 3; q++) {
