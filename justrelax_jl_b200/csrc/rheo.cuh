@@ -18,6 +18,10 @@ struct jr_phase_tab {
     double g[3];
     double fs;  // dt * free_surface factor of compute_V!/compute_Res! (2D), 0 when off
     double eta[JR_MAX_PHASES], G[JR_MAX_PHASES], Kb[JR_MAX_PHASES];
+    // composite viscosity of a phase at the local args of compute_viscosity (dt = Inf: the elastic element contributes 1 / (G · Inf)) and its
+    // reciprocal — per-phase constants of the LinearViscous subset, formed once on the host with the same IEEE divisions the kernels used to
+    // repeat per node: eta_c = 1 / (1 / η + 1 / (G · Inf)), ieta_c = 1 / eta_c
+    double eta_c[JR_MAX_PHASES], ieta_c[JR_MAX_PHASES];
     double C[JR_MAX_PHASES], sinphi[JR_MAX_PHASES], cosphi[JR_MAX_PHASES], sinpsi[JR_MAX_PHASES], eta_vp[JR_MAX_PHASES];
     double rho0[JR_MAX_PHASES], alpha[JR_MAX_PHASES], beta[JR_MAX_PHASES], T0[JR_MAX_PHASES], P0[JR_MAX_PHASES];
     int has_pl[JR_MAX_PHASES], rho_kind[JR_MAX_PHASES];
@@ -210,11 +214,11 @@ __device__ __forceinline__ double jr_ratio_density(const jr_phase_tab &pt, const
 __device__ __forceinline__ double jr_phase_viscosity(const jr_phase_tab &pt, const double *__restrict__ ph, size_t stride, size_t q)
 {
     for (int p = 0; p < pt.n; p++)
-        if (ph[(size_t)p * stride + q] > 0.999) return jr_inv(jr_inv(pt.eta[p]) + jr_inv(pt.G[p] * INFINITY));
+        if (ph[(size_t)p * stride + q] > 0.999) return pt.eta_c[p];
     double e = 0.0;
     for (int p = 0; p < pt.n; p++) {
         const double r = ph[(size_t)p * stride + q];
-        if (r != 0.0) e += jr_inv(jr_inv(jr_inv(pt.eta[p]) + jr_inv(pt.G[p] * INFINITY))) * r;
+        if (r != 0.0) e += pt.ieta_c[p] * r;
     }
     return jr_inv(e);
 }

@@ -19,6 +19,9 @@
 #include "stokes2d_resident.cuh"
 
 #define F(name) (s->f[JR_F_##name])
+// 2D arrays stay far below 2^31 elements (check2d refuses larger grids): the index arithmetic of this file runs in 32 bits
+#undef IX2
+#define IX2(n1, i, j) (((j) - 1) * (n1) + ((i) - 1))
 #define TX 32
 #define TY 16            /* default tile height (threads in y) */
 #define NT (TX * TY)
@@ -528,6 +531,12 @@ int jr_make_phase_tab(const jr_vc_inputs *vc, jr_phase_tab *out)
         out->eta[p] = q.eta; out->G[p] = q.G; out->Kb[p] = q.Kb; out->C[p] = q.C; out->sinphi[p] = q.sinphi; out->cosphi[p] = q.cosphi;
         out->sinpsi[p] = q.sinpsi; out->eta_vp[p] = q.eta_vp; out->rho0[p] = q.rho0; out->alpha[p] = q.alpha; out->beta[p] = q.beta;
         out->T0[p] = q.T0; out->P0[p] = q.P0; out->has_pl[p] = q.has_pl; out->rho_kind[p] = q.rho_kind;
+        {   // compute_viscosity_τII(CompositeRheology) with dt = Inf  (Viscosity.jl:510-522, 599-619): IEEE divisions, as on the device
+            volatile double ie = 1.0 / q.eta, ig = 1.0 / (q.G * INFINITY);
+            volatile double ec = 1.0 / (ie + ig);
+            out->eta_c[p] = ec;
+            out->ieta_c[p] = 1.0 / ec;
+        }
         if (q.rho_kind != 0) out->rho_const = 0;
         JR_REQUIRE(q.soft_C_kind >= 0 && q.soft_C_kind <= 2, JR_ERR_UNSUPPORTED, "phase %d: softening law %d outside the supported subset", p, q.soft_C_kind);
         out->soft_kind[p] = q.has_pl ? q.soft_C_kind : 0;
@@ -628,6 +637,7 @@ static int check2d(const jr_fields *s, const jr_stokes_opts *o, bool vc, const j
     JR_REQUIRE(s && o, JR_ERR_ARG, "null fields/opts");
     JR_REQUIRE(s->ndim == 2, JR_ERR_SHAPE, "2D solver called with ndim=%d", s->ndim);
     JR_REQUIRE(s->n[0] >= 3 && s->n[1] >= 3, JR_ERR_SHAPE, "grid must be at least 3 cells per dimension");
+    JR_REQUIRE(((long long)s->n[0] + 3) * ((long long)s->n[1] + 3) < (1ll << 30), JR_ERR_SHAPE, "2D grid too large for the 32-bit index arithmetic of the 2D kernels");
     JR_REQUIRE(o->nout >= 1, JR_ERR_ARG, "nout must be >= 1");
     static const int req_common[] = {JR_F_P, JR_F_P0, JR_F_divV, JR_F_Q, JR_F_Vx, JR_F_Vy, JR_F_txx, JR_F_tyy, JR_F_txy, JR_F_txx_o, JR_F_tyy_o, JR_F_txy_o,
                                      JR_F_exx, JR_F_eyy, JR_F_exy, JR_F_eta, JR_F_etatau, JR_F_Rx, JR_F_Ry, JR_F_RP, JR_F_rhogx, JR_F_rhogy};

@@ -183,12 +183,12 @@ __global__ void __launch_bounds__(256, JR_PREP_MINB) k_vc3_prep(const __grid_con
     bool single = false;
 #pragma unroll
     for (int p = 0; p < NP; p++)
-        if (p < pt.n && !single && r[p] > 0.999) { eph = jr_inv(jr_inv(pt.eta[p]) + jr_inv(pt.G[p] * INFINITY)); single = true; }
+        if (p < pt.n && !single && r[p] > 0.999) { eph = pt.eta_c[p]; single = true; }
     if (!single) {
         double e = 0.0;
 #pragma unroll
         for (int p = 0; p < NP; p++)
-            if (p < pt.n && r[p] != 0.0) e += jr_inv(jr_inv(jr_inv(pt.eta[p]) + jr_inv(pt.G[p] * INFINITY))) * r[p];
+            if (p < pt.n && r[p] != 0.0) e += pt.ieta_c[p] * r[p];
         eph = jr_inv(e);
     }
     a.eta_o[c] = jr_clampd((1 - a.nu) * eta + a.nu * eph, a.cut_lo, a.cut_hi);
