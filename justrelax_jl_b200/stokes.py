@@ -20,7 +20,7 @@ import numpy as np
 
 from . import _abi
 from . import rheology as _rheology
-from .types import (B200BackendTrait, CPUBackendTrait, Geometry, IGG, StokesArrays, VelocityBoundaryConditions,
+from .types import (require_uniform, B200BackendTrait, CPUBackendTrait, Geometry, IGG, StokesArrays, VelocityBoundaryConditions,
                     DisplacementBoundaryConditions, AbstractFlowBoundaryConditions, PhaseRatios, backend, data_ptr, is_device_array,
                     legacy_uniform_grid)
 
@@ -120,8 +120,11 @@ class _Hist:
 
 def _grid_of(stokes, grid_or_di, igg):
     if isinstance(grid_or_di, Geometry):
+        require_uniform(grid_or_di, "solve!")
         return grid_or_di
     di = grid_or_di.center if hasattr(grid_or_di, "center") else grid_or_di
+    if any(np.ndim(x) > 0 for x in di):
+        raise NotImplementedError("solve!: vector grid spacings (non-uniform grids) are outside the B200 backend's subset")
     return legacy_uniform_grid(stokes.ni, tuple(di), igg)
 
 

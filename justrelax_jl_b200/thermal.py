@@ -21,7 +21,7 @@ import numpy as np
 from . import _abi
 from .rheology import MaterialParams, lower_thermal
 from .stokes import context
-from .types import (B200Backend, CPUBackendTrait, Geometry, IGG, PTArray, TemperatureBoundaryConditions, ThermalArrays, backend,
+from .types import (require_uniform, B200Backend, CPUBackendTrait, Geometry, IGG, PTArray, TemperatureBoundaryConditions, ThermalArrays, backend,
                     data_ptr, is_device_array, legacy_uniform_grid, zeros)
 
 FACES = ("left", "right", "front", "back", "top", "bot")
@@ -139,8 +139,11 @@ def _phase_extra(phase):
 
 def _grid_of(thermal, grid_or_di, igg):
     if isinstance(grid_or_di, Geometry):
+        require_uniform(grid_or_di, "heatdiffusion_PT!")
         return grid_or_di
     di = grid_or_di.center if hasattr(grid_or_di, "center") else grid_or_di
+    if any(np.ndim(x) > 0 for x in di):
+        raise NotImplementedError("heatdiffusion_PT!: vector grid spacings (non-uniform grids) are outside the B200 backend's subset")
     return legacy_uniform_grid(thermal.ni, tuple(di), igg)
 
 

@@ -380,8 +380,14 @@ class IGG:
 
 
 class Geometry:
-    """Uniform staggered Cartesian grid, Geometry(ni, li; origin) — src/grid/Cartesian.jl:42-58,
-    geometry_nonMPI / geometry_MPI src/grid/Grid.jl:56-116."""
+    """Staggered Cartesian grid — src/grid/Cartesian.jl:9-19.
+
+    Geometry(ni, li; origin): uniform grid (src/grid/Cartesian.jl:42-58, geometry_nonMPI / geometry_MPI src/grid/Grid.jl:56-116).
+    Geometry.from_vertices(xv1, xv2[, xv3]) ≙ Geometry(TA, xvi...) / Geometry((xv1, xv2, …)): grid from explicit vertex coordinates
+    (refined / non-uniform meshes, src/grid/Cartesian.jl:76-99): di / _di are VECTORS per direction (`center` = spacing of the cell
+    centres, n−1 entries; `vertex` = cell widths, n entries; `velocity[c][d]` = spacing of component c's staggered grid along d).
+    `uniform` tells the two apart; the B200 kernels take scalar spacings, so the solvers refuse a non-uniform grid loudly
+    (`require_uniform`) — SURVEY §8f-3."""
 
     def __init__(self, ni: Sequence[int], li: Sequence[float], *, origin: Optional[Sequence[float]] = None, igg: Optional[IGG] = None):
         nD = len(ni)
@@ -389,6 +395,7 @@ class Geometry:
         self.li = tuple(float(l) for l in li)
         self.origin = tuple(float(o) for o in (origin if origin is not None else (0.0,) * nD))
         self.max_li = max(self.li)
+        self.uniform = True
         igg = igg or IGG()
         ni_g = igg.n_g(self.ni)
         self.ni_g = ni_g
@@ -410,6 +417,46 @@ class Geometry:
                 xci.append(_linrange(self.origin[d] + dx / 2, self.origin[d] + self.li[d] - dx / 2, n))
                 xvi.append(_linrange(self.origin[d], self.origin[d] + self.li[d], n + 1))
         self.xci, self.xvi = tuple(xci), tuple(xvi)
+        # velocity_grids(xci, xvi, di) for scalar spacings  src/grid/Grid.jl:161-169, 184-200: component c lives on the vertices along c and on
+        # the centres extended by one ghost point on either side along the transverse directions
+        ghost = tuple(_linrange(self.xci[d][0] - di[d], self.xci[d][-1] + di[d], self.ni[d] + 2) for d in range(nD))
+        self.xi_vel = tuple(tuple(self.xvi[d] if d == c else ghost[d] for d in range(nD)) for c in range(nD))
+
+    @classmethod
+    def from_vertices(cls, *xvi):
+        """Geometry(TA, xvi...) / Geometry((xv1, xv2, …))  src/grid/Cartesian.jl:76-99; velocity_grids for vector spacings Grid.jl:171-182, 202-215."""
+        if len(xvi) == 1 and isinstance(xvi[0], (tuple, list)) and len(xvi[0]) in (2, 3) and np.ndim(xvi[0][0]) == 1:
+            xvi = tuple(xvi[0])
+        xvi = tuple(np.asarray(x, dtype=np.float64) for x in xvi)
+        nD = len(xvi)
+        if nD not in (2, 3) or any(x.ndim != 1 or x.size < 2 for x in xvi):
+            raise ValueError("Geometry.from_vertices: one 1-D vertex-coordinate vector (≥ 2 entries) per dimension, 2 or 3 dimensions")
+        g = cls.__new__(cls)
+        g.uniform = False
+        g.ni = tuple(int(x.size) - 1 for x in xvi)
+        g.ni_g = g.ni
+        g.xvi = xvi
+        g.xci = tuple((x[:-1] + x[1:]) / 2 for x in xvi)
+        lims = tuple((float(x.min()), float(x.max())) for x in xvi)
+        g.li = tuple(hi - lo for lo, hi in lims)
+        g.max_li = max(g.li)
+        g.origin = tuple(lo for lo, _ in lims)
+        di_vertex = tuple(np.diff(x) for x in xvi)
+        di_center = tuple(np.diff(x) for x in g.xci)
+        # ghost points: the first / last centre spacing outwards (dxW = di_center[d][1], dxE = di_center[d][end])
+        ghost = tuple(np.concatenate(([g.xci[d][0] - di_center[d][0]], g.xci[d], [g.xci[d][-1] + di_center[d][-1]])) for d in range(nD))
+        g.xi_vel = tuple(tuple(g.xvi[d] if d == c else ghost[d] for d in range(nD)) for c in range(nD))
+        di_vel = tuple(tuple(np.diff(x) for x in g.xi_vel[c]) for c in range(nD))
+        g.di = SimpleNamespace(center=di_center, vertex=di_vertex, velocity=di_vel)
+        g._di = SimpleNamespace(center=tuple(1.0 / x for x in di_center), vertex=tuple(1.0 / x for x in di_vertex),
+                                velocity=tuple(tuple(1.0 / x for x in comp) for comp in di_vel))
+        return g
+
+
+def require_uniform(grid, what: str):
+    """The B200 kernels take scalar grid spacings (vector `_di` is a next-row): refuse a non-uniform Geometry loudly."""
+    if isinstance(grid, Geometry) and not grid.uniform:
+        raise NotImplementedError(f"{what}: non-uniform grids (Geometry.from_vertices, vector spacings) are outside the B200 backend's subset")
 
 
 def legacy_uniform_grid(ni, di, igg: Optional[IGG] = None) -> Geometry:
