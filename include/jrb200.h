@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define JRB200_ABI_VERSION 2
+#define JRB200_ABI_VERSION 3
 
 typedef enum {
     JR_OK = 0,
@@ -299,11 +299,18 @@ typedef struct {
 } jr_thermal_fields;
 
 /* one row of the flat thermal rheology table (GeoParams subset: Constant/PT_/T_Density, ConstantHeatCapacity,
- * ConstantConductivity, ConstantRadioactiveHeat) — lowered from rheology::NTuple{N,MaterialParams} once per solve */
+ * ConstantConductivity / TP_Conductivity, ConstantRadioactiveHeat) — lowered from rheology::NTuple{N,MaterialParams} once per solve.
+ * TP_Conductivity (miniapps/convection/Particles3D/Layered_rheology.jl:45-57, miniapps/benchmarks/stokes2D/shear_heating/
+ * Shearheating_rheology.jl:9-17): k(T, P) = (k_a + k_b / (T + k_c)) · (1 + k_d · P), evaluated where the reference evaluates
+ * compute_conductivity: at the faces with T = the mean of the two adjacent nodes and P of the (clamped) cell on either side
+ * (DiffusionPT_kernels.jl:93-100, 391-402), at the centres for the PT coefficients (DiffusionPT_coefficients.jl:122-135) */
 typedef struct {
     int32_t rho_kind; /* 0 ConstantDensity, 1 PT_Density, 2 T_Density */
     int32_t has_Hr;
     double rho0, alpha, beta, T0, P0, Cp, k, Hr;
+    int32_t k_kind;   /* 0 ConstantConductivity (k), 1 TP_Conductivity (k_a … k_d) */
+    int32_t _pad;
+    double k_a, k_b, k_c, k_d;
 } jr_thermal_phase;
 
 typedef struct {

@@ -26,7 +26,7 @@ struct B200Backend end
 const LIBPATH = Ref{String}("")
 const LIBHANDLE = Ref{Ptr{Cvoid}}(C_NULL)
 const CTX = Ref{Ptr{Cvoid}}(C_NULL)
-const ABI_VERSION = 2
+const ABI_VERSION = 3
 
 const JR_OK = Cint(0)
 const JR_ERR_CUDA = Cint(-1)

@@ -186,6 +186,12 @@ struct ThermalPhase
     Cp::Cdouble
     k::Cdouble
     Hr::Cdouble
+    k_kind::Int32                    # 0 ConstantConductivity (k), 1 TP_Conductivity: (k_a + k_b / (T + k_c)) (1 + k_d P)
+    _pad::Int32
+    k_a::Cdouble
+    k_b::Cdouble
+    k_c::Cdouble
+    k_d::Cdouble
 end
 
 struct ThermalOpts
@@ -226,7 +232,7 @@ function selfcheck()
     @assert sizeof(StokesPhase) == 21 * 8                  # 13 + 6 doubles + 2 × two int32 sharing one 8-byte slot
     @assert sizeof(VcInputs) == 8 + 8 + 24 + 5 * 8 + 8
     @assert sizeof(ThermalFields) == 16 + 24 * 8
-    @assert sizeof(ThermalPhase) == 8 + 8 * 8
+    @assert sizeof(ThermalPhase) == 8 + 8 * 8 + 8 + 4 * 8
     @assert sizeof(ThermalOpts) == 24 + 16 + 16 + 16 + 8 + 8 + 8 + 4 * 24 + 2 * 48
     @assert sizeof(ThermalResult) == 8 * 8
     return true

@@ -219,15 +219,22 @@ function lower_thermal_phase(p::GeoParams.MaterialParams)
     kind, ρ0, α, β, T0, P0 = lower_density(p)
     (length(p.HeatCapacity) == 1 && p.HeatCapacity[1] isa GeoParams.ConstantHeatCapacity) ||
         throw(ArgumentError("heat-capacity law outside the B200 backend's supported subset (ConstantHeatCapacity)"))
-    (length(p.Conductivity) == 1 && p.Conductivity[1] isa GeoParams.ConstantConductivity) ||
-        throw(ArgumentError("conductivity law outside the B200 backend's supported subset (ConstantConductivity)"))
+    length(p.Conductivity) == 1 || throw(ArgumentError("exactly one conductivity law per phase"))
+    κ = p.Conductivity[1]
+    k, k_kind, ka, kb, kc, kd = if κ isa GeoParams.ConstantConductivity
+        _val(κ.k), Int32(0), 0.0, 0.0, 0.0, 0.0
+    elseif κ isa GeoParams.TP_Conductivity           # k = (a + b / (T + c)) (1 + d P)   Layered_rheology.jl:45-57
+        0.0, Int32(1), _val(κ.a), _val(κ.b), _val(κ.c), _val(κ.d)
+    else
+        throw(ArgumentError("conductivity law outside the B200 backend's supported subset (ConstantConductivity, TP_Conductivity)"))
+    end
     has_Hr, Hr = Int32(0), 0.0
     if !isempty(p.RadioactiveHeat)                                                      # DiffusionPT_GeoParams.jl:145
         p.RadioactiveHeat[1] isa GeoParams.ConstantRadioactiveHeat ||
             throw(ArgumentError("radioactive-heat law outside the B200 backend's supported subset (ConstantRadioactiveHeat)"))
         has_Hr, Hr = Int32(1), _val(p.RadioactiveHeat[1].H_r)
     end
-    return API.ThermalPhase(kind, has_Hr, ρ0, α, β, T0, P0, _val(p.HeatCapacity[1].Cp), _val(p.Conductivity[1].k), Hr)
+    return API.ThermalPhase(kind, has_Hr, ρ0, α, β, T0, P0, _val(p.HeatCapacity[1].Cp), k, Hr, k_kind, Int32(0), ka, kb, kc, kd)
 end
 
 "compute_gravity(first(rheology)) (BuoyancyForces.jl:25,56): a Number acting along the last axis"

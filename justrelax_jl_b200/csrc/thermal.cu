@@ -41,6 +41,7 @@ struct ThArgs {
     double cfv_lo[3], cfv_hi[3];
     int write_q2, write_res, next_pt;   // next_pt: k_th_update also writes θr_dτ, dτ_ρ of the NEXT iteration (update_pt_thermal_arrays! fused)
     double *res_part;  // per-block partial sums of ResT²
+    int k_var;         // some phase has a T, P dependent conductivity (TP_Conductivity): K̄ is formed inside compute_flux! every iteration
     double *Kf[3];     // rheology form: face conductivities K̄ (static for the ConstantConductivity subset), computed once per call
 };
 
@@ -50,6 +51,11 @@ __device__ __forceinline__ double th_density(const jr_thermal_phase &p, double T
     if (p.rho_kind == 1) return p.rho0 * (1.0 - p.alpha * (T - p.T0) + p.beta * (P - p.P0));
     if (p.rho_kind == 2) return p.rho0 * (1.0 - p.alpha * (T - p.T0));
     return p.rho0;
+}
+// compute_conductivity: ConstantConductivity, or TP_Conductivity k = (a + b / (T + c)) · (1 + d · P)
+__device__ __forceinline__ double th_cond(const jr_thermal_phase &p, double T, double P)
+{
+    return p.k_kind == 1 ? (p.k_a + p.k_b / (T + p.k_c)) * (1.0 + p.k_d * P) : p.k;
 }
 // fn_ratio(fn, rheology, ratio, args)  src/phases/phases.jl:18-30 (a ratio equal to one returns that phase alone)
 __device__ __forceinline__ double th_rhoCp(const ThTable &t, const double *ph, size_t stride, size_t idx, double T, double P)
@@ -64,14 +70,14 @@ __device__ __forceinline__ double th_rhoCp(const ThTable &t, const double *ph, s
     }
     return x;
 }
-__device__ __forceinline__ double th_K(const ThTable &t, const double *ph, size_t stride, size_t idx)
+__device__ __forceinline__ double th_K(const ThTable &t, const double *ph, size_t stride, size_t idx, double T, double P)
 {
-    if (!ph) return t.p[0].k;
+    if (!ph) return th_cond(t.p[0], T, P);
     double x = 0.0;
     for (int q = 0; q < t.nphase; q++) {
         const double r = ph[(size_t)q * stride + idx];
-        if (r == 1.0) return t.p[q].k * r;
-        x += (r == 0.0) ? 0.0 : t.p[q].k * r;
+        if (r == 1.0) return th_cond(t.p[q], T, P) * r;
+        x += (r == 0.0) ? 0.0 : th_cond(t.p[q], T, P) * r;
     }
     return x;
 }
@@ -118,15 +124,15 @@ __device__ __forceinline__ double th_rhoCp_r(const ThTable &t, const ThRatios &R
         }
     return done ? out : x;
 }
-__device__ __forceinline__ double th_K_r(const ThTable &t, const ThRatios &R)
+__device__ __forceinline__ double th_K_r(const ThTable &t, const ThRatios &R, double T, double P)
 {
     double x = 0.0, out = 0.0;
     bool done = false;
 #pragma unroll
     for (int q = 0; q < TH_MAX_PHASES; q++)
         if (q < t.nphase && !done) {
-            if (R.r[q] == 1.0) { out = t.p[q].k * R.r[q]; done = true; }
-            else x += (R.r[q] == 0.0) ? 0.0 : t.p[q].k * R.r[q];
+            if (R.r[q] == 1.0) { out = th_cond(t.p[q], T, P) * R.r[q]; done = true; }
+            else x += (R.r[q] == 0.0) ? 0.0 : th_cond(t.p[q], T, P) * R.r[q];
         }
     return done ? out : x;
 }
@@ -150,7 +156,7 @@ __global__ void k_th_pt(const __grid_constant__ ThArgs a)
     const size_t nc = (size_t)d.nx * d.ny * d.nz, c = th_ci(d, i, j, k);
     const double T = a.f.T[th_ti(d, i + 1, j + 1, d.nd == 3 ? k + 1 : 0)], P = a.f.P ? a.f.P[c] : 0.0;
     const double rhoCp = th_rhoCp(a.tab, a.f.phase_c, nc, c, T, P);
-    const double _K = 1.0 / th_K(a.tab, a.f.phase_c, nc, c);
+    const double _K = 1.0 / th_K(a.tab, a.f.phase_c, nc, c, T, P);
     const double _Re = 1.0 / (TH_PI + sqrt(TH_PI * TH_PI + rhoCp * (a.L * a.L) * _K * a._dt));
     a.f.theta_r_dtau[c] = a.L / a.Vpdtau * _Re;
     a.f.dtau_rho[c] = a.Vpdtau * a.L * _K * _Re;
@@ -187,7 +193,10 @@ __device__ __forceinline__ void th_flux_dim(const ThArgs &a, int i, int j, int k
             const double *phf = DIM == 0 ? a.f.phase_x : DIM == 1 ? a.f.phase_y : a.f.phase_z;
             const size_t ps = (size_t)e[0] * e[1] * e[2];
             const size_t pL = ((size_t)L[2] * e[1] + L[1]) * e[0] + L[0], pR = ((size_t)R[2] * e[1] + R[1]) * e[0] + R[0];
-            K = (th_K(a.tab, phf, ps, pL) + th_K(a.tab, phf, ps, pR)) * 0.5;
+            // args of compute_conductivity: T = the mean of the two nodes adjacent to the face, P of the (clamped) cell on either side
+            // (DiffusionPT_kernels.jl:93-100, 391-402); only TP_Conductivity looks at them
+            const double Tf = (Tl + Th) * 0.5, PL = (a.k_var && a.f.P) ? a.f.P[cL] : 0.0, PR = (a.k_var && a.f.P) ? a.f.P[cR] : 0.0;
+            K = (th_K(a.tab, phf, ps, pL, Tf, PL) + th_K(a.tab, phf, ps, pR, Tf, PR)) * 0.5;
         }
     }
     const double th_ = (a.f.theta_r_dtau[cL] + a.f.theta_r_dtau[cR]) * 0.5;
@@ -218,7 +227,7 @@ __device__ __forceinline__ void th_kface_dim(const ThArgs &a, int i, int j, int 
     const double *phf = !a.f.phase_c ? nullptr : DIM == 0 ? a.f.phase_x : DIM == 1 ? a.f.phase_y : a.f.phase_z;
     const size_t ps = (size_t)e[0] * e[1] * e[2];
     const size_t pL = ((size_t)L[2] * e[1] + L[1]) * e[0] + L[0], pR = ((size_t)R[2] * e[1] + R[1]) * e[0] + R[0];
-    a.Kf[DIM][qi] = (th_K(a.tab, phf, ps, pL) + th_K(a.tab, phf, ps, pR)) * 0.5;
+    a.Kf[DIM][qi] = (th_K(a.tab, phf, ps, pL, 0.0, 0.0) + th_K(a.tab, phf, ps, pR, 0.0, 0.0)) * 0.5;   // (constant conductivities only: th_prepare_kface)
 }
 __global__ void __launch_bounds__(256) k_th_kface(const __grid_constant__ ThArgs a)
 {
@@ -286,7 +295,7 @@ __global__ void __launch_bounds__(256) k_th_update(const __grid_constant__ ThArg
             // update_pt_thermal_arrays! of the next iteration (solver.jl:233-234; DiffusionPT_coefficients.jl:105-151): it reads interior T only,
             // which neither thermal_bcs! nor update_halo!(T) touches, so evaluating it here from Tn is the same arithmetic on the same inputs
             const double rc = th_rhoCp_r(a.tab, R, Tn, a.f.P ? a.f.P[c] : 0.0);
-            const double _K = 1.0 / th_K_r(a.tab, R);
+            const double _K = 1.0 / th_K_r(a.tab, R, Tn, a.f.P ? a.f.P[c] : 0.0);
             const double _Re = 1.0 / (TH_PI + sqrt(TH_PI * TH_PI + rc * (a.L * a.L) * _K * a._dt));
             a.f.theta_r_dtau[c] = a.L / a.Vpdtau * _Re;
             a.f.dtau_rho[c] = a.Vpdtau * a.L * _K * _Re;
@@ -587,7 +596,13 @@ static int th_check(const jr_thermal_fields *f, const jr_thermal_opts *o, ThArgs
     a.d.nd = f->ndim; a.d.nx = f->n[0]; a.d.ny = f->n[1]; a.d.nz = f->ndim == 3 ? f->n[2] : 1;
     a.d.gx = a.d.nx + 2; a.d.gy = a.d.ny + 2; a.d.gz = f->ndim == 3 ? a.d.nz + 2 : 1;
     a.tab.nphase = o->form == 1 ? o->nphase : 0;
-    for (int q = 0; q < a.tab.nphase; q++) a.tab.p[q] = o->phases[q];
+    a.k_var = 0;
+    for (int q = 0; q < a.tab.nphase; q++) {
+        a.tab.p[q] = o->phases[q];
+        JR_REQUIRE(o->phases[q].k_kind == 0 || o->phases[q].k_kind == 1, JR_ERR_UNSUPPORTED, "phase %d: conductivity law %d outside the supported subset", q,
+                   o->phases[q].k_kind);
+        if (o->phases[q].k_kind == 1) a.k_var = 1;
+    }
     for (int q = 0; q < 3; q++) a._di[q] = o->_di[q];
     a.dt = o->dt; a._dt = 1.0 / o->dt; a.L = o->max_lxyz; a.Vpdtau = o->Vpdtau; a.dir_const = o->dir_const; a.form = o->form;
     int lo[3], hi[3];
@@ -645,6 +660,7 @@ static int th_halo(jr_context *ctx, const ThArgs &a) { return th_halo_of(ctx, a,
 static int th_prepare_kface(jr_context *ctx, ThArgs &a, bool all_forms = false)
 {
     if (!(a.form == 1 && a.f.phase_c) && !all_forms) return JR_OK;
+    if (a.form == 1 && a.k_var) return JR_OK;   // TP_Conductivity: K̄ depends on the iterate (k_th_flux forms it)
     const ThDims &d = a.d;
     const size_t nfx = (size_t)(d.nx + 1) * d.ny * d.nz, nfy = (size_t)d.nx * (d.ny + 1) * d.nz, nfz = d.nd == 3 ? (size_t)d.nx * d.ny * (d.nz + 1) : 0;
     void *buf = nullptr;
@@ -712,7 +728,7 @@ struct ThFused {
 static int th_fused_prepare(jr_context *ctx, ThArgs &a, ThFused &F)
 {
     const ThDims &d = a.d;
-    F.ok = d.nd == 3 && !a.f.dir_mask;
+    F.ok = d.nd == 3 && !a.f.dir_mask && !(a.form == 1 && a.k_var);   // (the fused kernel reads K̄ planes formed once per call)
     for (int q = 0; q < 3; q++) F.ok = F.ok && !a.cf_lo[q] && !a.cf_hi[q];
     if (const char *e = getenv("JRB200_TH_FUSED")) F.ok = F.ok && atoi(e) != 0;
     if (!F.ok) return th_prepare_kface(ctx, a);

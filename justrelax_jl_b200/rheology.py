@@ -54,6 +54,17 @@ class ConstantConductivity:
 
 
 @dataclass
+class TP_Conductivity:
+    """GeoParams TP_Conductivity: k(T, P) = (a + b / (T + c)) · (1 + d · P)  (T in the units of the model, P likewise; the miniapps pass
+    d per Pa: miniapps/convection/Particles3D/Layered_rheology.jl:45-57, benchmarks/stokes2D/shear_heating/Shearheating_rheology.jl:9-17).
+    Defaults = GeoParams' (a = 1.18 W/m/K, b = 474 W/m, c = 77 K, d = 0)."""
+    a: float = 1.18
+    b: float = 474.0
+    c: float = 77.0
+    d: float = 0.0
+
+
+@dataclass
 class ConstantRadioactiveHeat:
     H_r: float = 1e-6
 
@@ -172,7 +183,7 @@ def _as_tuple(rheology) -> Sequence[MaterialParams]:
 
 
 def lower_thermal(rheology):
-    """rows of jr_thermal_phase: dict(rho_kind, has_Hr, rho0, alpha, beta, T0, P0, Cp, k, Hr)"""
+    """rows of jr_thermal_phase: dict(rho_kind, has_Hr, rho0, alpha, beta, T0, P0, Cp, k, Hr, k_kind, k_a, k_b, k_c, k_d)"""
     rows = []
     for p in _as_tuple(rheology):
         ρ = p.Density
@@ -186,9 +197,15 @@ def lower_thermal(rheology):
             raise UnsupportedRheology(f"density law {type(ρ).__name__} is outside the supported subset")
         if not isinstance(p.HeatCapacity, ConstantHeatCapacity):
             raise UnsupportedRheology(f"heat-capacity law {type(p.HeatCapacity).__name__} is outside the supported subset")
-        if not isinstance(p.Conductivity, ConstantConductivity):
+        row["Cp"] = p.HeatCapacity.Cp
+        row.update(k=0.0, k_kind=0, k_a=0.0, k_b=0.0, k_c=0.0, k_d=0.0)
+        if isinstance(p.Conductivity, ConstantConductivity):
+            row["k"] = p.Conductivity.k
+        elif isinstance(p.Conductivity, TP_Conductivity):
+            κ = p.Conductivity
+            row.update(k_kind=1, k_a=float(κ.a), k_b=float(κ.b), k_c=float(κ.c), k_d=float(κ.d))
+        else:
             raise UnsupportedRheology(f"conductivity law {type(p.Conductivity).__name__} is outside the supported subset")
-        row["Cp"], row["k"] = p.HeatCapacity.Cp, p.Conductivity.k
         if p.RadioactiveHeat is None:
             row["has_Hr"], row["Hr"] = 0, 0.0
         elif isinstance(p.RadioactiveHeat, ConstantRadioactiveHeat):

@@ -224,7 +224,8 @@ class ThermalFields(C.Structure):
 
 class ThermalPhase(C.Structure):
     _fields_ = [("rho_kind", C.c_int32), ("has_Hr", C.c_int32), ("rho0", C.c_double), ("alpha", C.c_double), ("beta", C.c_double),
-                ("T0", C.c_double), ("P0", C.c_double), ("Cp", C.c_double), ("k", C.c_double), ("Hr", C.c_double)]
+                ("T0", C.c_double), ("P0", C.c_double), ("Cp", C.c_double), ("k", C.c_double), ("Hr", C.c_double),
+                ("k_kind", C.c_int32), ("_pad", C.c_int32), ("k_a", C.c_double), ("k_b", C.c_double), ("k_c", C.c_double), ("k_d", C.c_double)]
 
 
 class ThermalOpts(C.Structure):

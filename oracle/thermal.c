@@ -72,14 +72,20 @@ static double ratio_rhoCp(const orc_thermal_opts *o, const double *ph, size_t st
     }
     return x;
 }
-static double ratio_K(const orc_thermal_opts *o, const double *ph, size_t stride, size_t idx)
+/* compute_conductivity(phase, args): ConstantConductivity k, or TP_Conductivity k = (a + b / (T + c)) (1 + d P)
+ * (GeoParams.jl, not vendored: restated from its docstring; used by miniapps/convection/Particles3D/Layered_rheology.jl:45-57) */
+static inline double ph_cond(const orc_thermal_phase *p, double T, double P)
 {
-    if (!ph) return o->phases[0].k;
+    return p->k_kind == 1 ? (p->k_a + p->k_b / (T + p->k_c)) * (1.0 + p->k_d * P) : p->k;
+}
+static double ratio_K(const orc_thermal_opts *o, const double *ph, size_t stride, size_t idx, double T, double P)
+{
+    if (!ph) return ph_cond(&o->phases[0], T, P);
     double x = 0.0;
     for (int p = 0; p < o->nphase; p++) {
         const double r = ph[(size_t)p * stride + idx];
-        if (r == 1.0) return o->phases[p].k * r;
-        x += (r == 0.0) ? 0.0 : o->phases[p].k * r;
+        if (r == 1.0) return ph_cond(&o->phases[p], T, P) * r;
+        x += (r == 0.0) ? 0.0 : ph_cond(&o->phases[p], T, P) * r;
     }
     return x;
 }
@@ -117,7 +123,7 @@ void orc_thermal_pt_arrays(const orc_thermal_fields *f, const orc_thermal_opts *
                 const size_t c = CI(d, i, j, k);
                 const double T = f->T[TI(d, i + 1, j + 1, d.nd == 3 ? k + 1 : 0)], P = f->P ? f->P[c] : 0.0;
                 const double rhoCp = ratio_rhoCp(o, f->phase_c, nc, c, T, P);
-                const double _K = 1.0 / ratio_K(o, f->phase_c, nc, c);
+                const double _K = 1.0 / ratio_K(o, f->phase_c, nc, c, T, P);   /* args_ij = (T[I+1], P[I])  DiffusionPT_coefficients.jl:125 */
                 const double _Re = 1.0 / (PI_ + sqrt(PI_ * PI_ + rhoCp * (L * L) * _K * _dt));
                 f->theta_r_dtau[c] = L / o->Vpdtau * _Re;
                 f->dtau_rho[c] = o->Vpdtau * L * _K * _Re;
@@ -158,9 +164,11 @@ static void flux_dim(const orc_thermal_fields *f, const orc_thermal_opts *o, int
                 double K;
                 if (o->form == 0) K = (f->K[cL] + f->K[cR]) * 0.5;
                 else {
-                    /* conductivity laws of the subset do not depend on T, P: args are not needed */
+                    /* args: T = mean of the two nodes adjacent to the face, the other args (P) of the clamped cell on either side
+                     * DiffusionPT_kernels.jl:93-100 (3D), 391-402 (2D) */
                     const size_t pL = ((size_t)L[2] * e[1] + L[1]) * e[0] + L[0], pR = ((size_t)R[2] * e[1] + R[1]) * e[0] + R[0];
-                    K = (ratio_K(o, phf, pstride, pL) + ratio_K(o, phf, pstride, pR)) * 0.5;
+                    const double Tf = (Tl + Th) * 0.5, PL = f->P ? f->P[cL] : 0.0, PR = f->P ? f->P[cR] : 0.0;
+                    K = (ratio_K(o, phf, pstride, pL, Tf, PL) + ratio_K(o, phf, pstride, pR, Tf, PR)) * 0.5;
                 }
                 const double th_ = (f->theta_r_dtau[cL] + f->theta_r_dtau[cR]) * 0.5;
                 const double qx = -K * (Th - Tl) * o->_di[dim];

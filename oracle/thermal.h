@@ -21,6 +21,9 @@ typedef struct {
     int32_t rho_kind;   /* 0 ConstantDensity, 1 PT_Density, 2 T_Density */
     int32_t has_Hr;
     double rho0, alpha, beta, T0, P0, Cp, k, Hr;
+    int32_t k_kind;   /* 0 ConstantConductivity, 1 TP_Conductivity: k = (k_a + k_b / (T + k_c)) (1 + k_d P)  (GeoParams, restated from its docstring) */
+    int32_t _pad;
+    double k_a, k_b, k_c, k_d;
 } orc_thermal_phase;
 
 typedef struct {

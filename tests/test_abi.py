@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     assert len(names) >= 15
     for n in names:
         assert hasattr(L, n), f"libjrb200.so does not export {n}"
-    assert L.jr_abi_version() == 2
+    assert L.jr_abi_version() == 3
 
 
 def test_field_enum_matches_oracle(oracle):

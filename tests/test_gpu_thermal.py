@@ -80,6 +80,13 @@ PHASES = [dict(rho_kind=1, has_Hr=1, rho0=3.1e3, alpha=1.5e-5, beta=1e-11, T0=27
           dict(rho_kind=2, has_Hr=1, rho0=3.3e3, alpha=3e-5, beta=0.0, T0=300.0, P0=0.0, Cp=1.1e3, k=4.1, Hr=5e-8)]
 
 
+# the same table with GeoParams' TP_Conductivity k(T, P) = (a + b / (T + c)) (1 + d P) on two of the three phases (the parameters of
+# miniapps/convection/Particles3D/Layered_rheology.jl:45-57; d per Pa)
+PHASES_TP = [dict(PHASES[0], k=0.0, k_kind=1, k_a=0.64, k_b=807.0, k_c=0.77, k_d=0.00004e-6),
+             dict(PHASES[1]),
+             dict(PHASES[2], k=0.0, k_kind=1, k_a=0.73, k_b=1293.0, k_c=0.77, k_d=0.00004e-6)]
+
+
 def rheology_of(rows):
     from justrelax_jl_b200 import rheology as R
 
@@ -89,7 +96,8 @@ def rheology_of(rows):
              R.PT_Density(ρ0=r["rho0"], α=r["alpha"], β=r["beta"], T0=r["T0"], P0=r["P0"]) if r["rho_kind"] == 1 else
              R.T_Density(ρ0=r["rho0"], α=r["alpha"], T0=r["T0"]))
         out.append(R.SetMaterialParams(Phase=i + 1, Density=ρ, HeatCapacity=R.ConstantHeatCapacity(Cp=r["Cp"]),
-                                       Conductivity=R.ConstantConductivity(k=r["k"]),
+                                       Conductivity=(R.TP_Conductivity(a=r["k_a"], b=r["k_b"], c=r["k_c"], d=r["k_d"]) if r.get("k_kind", 0) == 1
+                                                     else R.ConstantConductivity(k=r["k"])),
                                        RadioactiveHeat=R.ConstantRadioactiveHeat(H_r=r["Hr"]) if r["has_Hr"] else None))
     return tuple(out)
 
@@ -113,14 +121,14 @@ class _Phase:
     pass
 
 
-def _run_case(oracle, ni, form, nphase, vb, bc, niter, seed_shift=0):
+def _run_case(oracle, ni, form, nphase, vb, bc, niter, seed_shift=0, table=None):
     """`niter` PT iterations (the last one sampled) from a random state on the B200 and in the oracle; returns the result"""
     from justrelax_jl_b200 import thermal as jth
     from justrelax_jl_b200.types import Geometry
 
     li = tuple(1.0e5 * (1 + 0.1 * d) for d in range(len(ni)))
     grid = Geometry(ni, li)
-    rows = PHASES[:max(nphase, 1)]
+    rows = (table or PHASES)[:max(nphase, 1)]
     host = random_thermal(ni, 77 + ni[0] + vb + seed_shift, nphase if nphase > 1 else 0)
     if vb == 1:  # Dirichlet mask on a block of nodes
         m = np.zeros(tuple(n + 2 for n in ni), order="F")
@@ -166,6 +174,16 @@ def test_fixed_iterations_random_state(oracle, ni, form, nphase):
     for vb, bc in enumerate(bc_variants(len(ni))):
         for niter in (1, 3):
             _run_case(oracle, ni, form, nphase, vb, bc, niter)
+
+
+@pytest.mark.parametrize("ni", [(17, 12), (33, 40), (9, 8, 7), (34, 17, 21)])
+@pytest.mark.parametrize("nphase", [1, 3])
+def test_tp_conductivity_fixed_iterations(oracle, ni, nphase):
+    """TP_Conductivity: K̄ at the faces from the mean of the two adjacent temperatures and the pressure of the cell on either
+    side, every iteration; the PT coefficients from T, P at the centres — single MaterialParams and three phases (two TP, one constant)"""
+    for vb, bc in enumerate(bc_variants(len(ni))):
+        for niter in (1, 3, 4):
+            _run_case(oracle, ni, 1, nphase, vb, bc, niter, table=PHASES_TP)
 
 
 @pytest.mark.parametrize("ni", [(9, 8, 7), (34, 17, 21), (40, 70, 37)])
@@ -260,9 +278,9 @@ def test_thermal_bcs_standalone(oracle, ni):
 def test_unsupported_law_fails_loudly():
     from justrelax_jl_b200 import rheology as R
 
-    class TP_Conductivity:
+    class T_Conductivity_Whittington:
         pass
 
-    p = R.SetMaterialParams(Density=R.ConstantDensity(), HeatCapacity=R.ConstantHeatCapacity(), Conductivity=TP_Conductivity())
+    p = R.SetMaterialParams(Density=R.ConstantDensity(), HeatCapacity=R.ConstantHeatCapacity(), Conductivity=T_Conductivity_Whittington())
     with pytest.raises(R.UnsupportedRheology):
         R.lower_thermal(p)

@@ -116,3 +116,62 @@ def test_diffusion3d_multiphase_reference_golden(oracle):
     assert abs(T[15, 15, 15] / 1816.8262937737384 - 1) < 1.0e-3
     assert abs(T[1:-1, 1:-1, 1:-1][15, 15, 15] / 1834.4197141500213 - 1) < 1.0e-3
     assert all(o["err"] <= 1e-8 for o in outs)
+
+
+def test_tp_conductivity_known_answers(oracle):
+    """TP_Conductivity (GeoParams, not vendored: k = (a + b / (T + c)) (1 + d P), its docstring; parameters of
+    miniapps/convection/Particles3D/Layered_rheology.jl:45-57).  Hand-evaluated known answers through the two places the reference
+    evaluates compute_conductivity: the PT coefficients at the centres (args T[I+1], P[I]; DiffusionPT_coefficients.jl:122-135) and the
+    face fluxes (T = mean of the two adjacent nodes, P of the cell on either side; DiffusionPT_kernels.jl:391-402).  A phase with d = 0 at
+    uniform T must reproduce ConstantConductivity with that k bit for bit."""
+    import ctypes as C
+
+    ni = (6, 5)
+    a, b, c, d = 0.64, 807.0, 0.77, 0.00004e-6
+    tp = dict(rho_kind=0, has_Hr=0, rho0=2.75e3, alpha=0.0, beta=0.0, T0=0.0, P0=0.0, Cp=7.5e2, k=0.0, Hr=0.0, k_kind=1, k_a=a, k_b=b, k_c=c, k_d=d)
+    T = np.zeros((8, 7), order="F")
+    T[:, :] = 900.0 + 50.0 * np.arange(8)[:, None] + 3.0 * np.arange(7)[None, :]
+    P = np.asfortranarray(np.full(ni, 2.0e8) + 1.0e7 * np.arange(6)[:, None])
+    L, Vp, dt, dx = 3.0e4, 120.0, 1.0e12, 250.0
+    f = oracle.alloc_thermal(ni, dict(T=T, P=P))
+    o = oracle.thermal_opts(_di=(1.0 / dx, 1.0 / dx), dt=dt, eps=1e-8, iterMax=1, nout=1, max_lxyz=L, Vpdtau=Vp, form=1, phases=[tp])
+    fs = oracle.thermal_fields(f, ni)
+    oracle.lib().orc_thermal_pt_arrays(C.byref(fs), C.byref(o))
+    k_of = lambda T_, P_: (a + b / (T_ + c)) * (1.0 + d * P_)
+    i, j = 3, 2
+    kc = k_of(T[i + 1, j + 1], P[i, j])
+    assert 1.3 < kc < 1.6                                              # ≈ 0.64 + 807 / 1106.8 = 1.369 (× 1.0092 for the pressure term)
+    rhoCp = 2.75e3 * 7.5e2
+    Re = 1.0 / (np.pi + np.sqrt(np.pi * np.pi + rhoCp * (L * L) * (1.0 / kc) * (1.0 / dt)))
+    assert abs(f["theta_r_dtau"][i, j] / (L / Vp * Re) - 1) < 1e-14
+    assert abs(f["dtau_rho"][i, j] / (Vp * L * (1.0 / kc) * Re) - 1) < 1e-14
+    # fluxes: qTx2 = −K̄ (T[i+1] − T[i]) / dx with K̄ = (k(Tf, P[iL]) + k(Tf, P[iR])) / 2, Tf = (T[i] + T[i+1]) / 2
+    oracle.lib().orc_thermal_flux(C.byref(fs), C.byref(o))
+    I, J = 3, 2                                                         # face between cells I−1 and I (0-based), row J
+    Tf = (T[I, J + 1] + T[I + 1, J + 1]) * 0.5
+    Kf = (k_of(Tf, P[I - 1, J]) + k_of(Tf, P[I, J])) * 0.5
+    assert abs(f["qTx2"][I, J] / (-Kf * (T[I + 1, J + 1] - T[I, J + 1]) / dx) - 1) < 1e-14
+    # boundary face: both sides clamp to the first cell
+    Tf0 = (T[0, J + 1] + T[1, J + 1]) * 0.5
+    assert abs(f["qTx2"][0, J] / (-k_of(Tf0, P[0, J]) * (T[1, J + 1] - T[0, J + 1]) / dx) - 1) < 1e-14
+    # d = 0, b = 0: a constant — the same bits as ConstantConductivity(k = a)
+    res = []
+    for row in (dict(tp, k_a=2.5, k_b=0.0, k_d=0.0), dict(tp, k_kind=0, k=2.5)):
+        g = oracle.alloc_thermal(ni, dict(T=T, P=P, theta_r_dtau=f["theta_r_dtau"], dtau_rho=f["dtau_rho"]))
+        oo = oracle.thermal_opts(_di=(1.0 / dx, 1.0 / dx), dt=dt, eps=1e-8, iterMax=1, nout=1, max_lxyz=L, Vpdtau=Vp, form=1, phases=[row])
+        gs = oracle.thermal_fields(g, ni)
+        for _ in range(3):
+            oracle.lib().orc_thermal_iterate_once(C.byref(gs), C.byref(oo))
+        res.append(g["T"].copy())
+    assert np.array_equal(res[0], res[1])
+
+
+def test_tp_conductivity_lowering():
+    from justrelax_jl_b200 import rheology as R
+
+    p = R.SetMaterialParams(Density=R.ConstantDensity(ρ=2.7e3), HeatCapacity=R.ConstantHeatCapacity(Cp=1050.0),
+                            Conductivity=R.TP_Conductivity(a=1.72, b=807.0, c=350, d=0.0))     # Shearheating_rheology.jl:9-17
+    row = R.lower_thermal(p)[0]
+    assert row["k_kind"] == 1 and (row["k_a"], row["k_b"], row["k_c"], row["k_d"]) == (1.72, 807.0, 350.0, 0.0)
+    q = R.SetMaterialParams(Density=R.ConstantDensity(ρ=2.7e3), HeatCapacity=R.ConstantHeatCapacity(Cp=1050.0), Conductivity=R.ConstantConductivity(k=2.5))
+    assert R.lower_thermal(q)[0]["k_kind"] == 0 and R.lower_thermal(q)[0]["k"] == 2.5
