@@ -207,6 +207,8 @@ int jr_lithostatic_pressure(jr_context *ctx, int32_t ndim, const int32_t n[3], d
         JR_CHECK_LAUNCH();
         return JR_OK;
     }
+    // Utils.jl:580-583
+    JR_REQUIRE(!cm->periods[vdim], JR_ERR_UNSUPPORTED, "the lithostatic pressure of a column that is periodic along the vertical direction is undefined");
     // cells at the bottom of the local column that the rank below also holds  Utils.jl:585-590
     const int nshared = nz - ncell_vertical + 2;
     JR_REQUIRE(nshared >= 0 && nshared < nz, JR_ERR_SHAPE,

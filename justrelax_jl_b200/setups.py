@@ -272,6 +272,33 @@ def diffusion2d(nx=32, ny=32, *, lx=100.0e3, ly=100.0e3, ρ0=3.3e3, Cp0=1.2e3, K
                            kwargs=dict(iterMax=50e3, nout=1e3, verbose=False))
 
 
+def diffusion3d(n=32, *, l=100.0e3, ρ0=3.3e3, Cp0=1.2e3, K0=3.0):
+    """test/test_diffusion3D.jl:52-141: the 3D twin of config 1 — rheology form with a single MaterialParams (PT_Density(ρ0=3.1e3, β=0, T0=0,
+    α=1.5e-5), ConstantHeatCapacity, ConstantConductivity), H = 1e-6, T(z) linear 1600–1900 K + 100 K sphere of radius 10 km, top 300 K /
+    bottom 3500 K, sides no-flux, PTThermalCoeffs(K, ρCp, dt, di, li; CFL = 0.95/√3.1), dt = 50 kyr, 10 steps, default kwargs, no thermal_bcs!
+    before the loop.  (The reference keeps this test's assertions commented out, :143-156; its golden numbers are used as a soft pin.)"""
+    from .types import TemperatureBoundaryConditions
+
+    kyr = 1.0e3 * 3600 * 24 * 365.25
+    dt = 50 * kyr
+    ni, li = (n, n, n), (l, l, l)
+    di = tuple(x / n for x in li)
+    grid = Geometry(ni, li, origin=(0.0, 0.0, -l))
+    xc, yc, zc = grid.xci
+    T = np.zeros((n + 2, n + 2, n + 2), order="F")
+    T[:, :, 1:-1] = (zc * (1900.0 - 1600.0) / zc.min() + 1600.0)[None, None, :]          # init_T! over (1:nx+2, 1:ny+2, 1:nz)  :30-33
+    bc = TemperatureBoundaryConditions(no_flux=dict(left=True, right=True, top=False, bot=False, front=True, back=True),
+                                       constant_value=dict(left=True, right=True, top=300.0, bot=3500.0, front=True, back=True))
+    ρCp = np.full(ni, Cp0 * ρ0, order="F")
+    K = np.full(ni, K0, order="F")
+    pt = pt_thermal_coeffs_arrays(K, ρCp, dt, di, li, CFL=0.95 / math.sqrt(3.1))
+    pert = ((xc[:, None, None] - l / 2) ** 2 + (yc[None, :, None] - l / 2) ** 2 + (zc[None, None, :] + l / 2) ** 2) <= 10.0e3 ** 2
+    phases = [dict(rho_kind=1, has_Hr=0, rho0=3.1e3, alpha=1.5e-5, beta=0.0, T0=0.0, P0=0.0, Cp=Cp0, k=K0, Hr=0.0)]
+    return SimpleNamespace(ni=ni, li=li, di=di, grid=grid, dt=dt, nt=10, T=T, bc=bc, pt=pt, perturbation=pert, δT=100.0,
+                           H=np.full(ni, 1.0e-6, order="F"), P=np.zeros(ni, order="F"), phases=phases, K=K, ρCp=ρCp,
+                           kwargs=dict(iterMax=50e3, nout=1e3, verbose=False))
+
+
 # ------------------------------------------------------------------------------------------------------------
 def _smooth2(A, fact):
     """smooth!  miniapps/benchmarks/stokes2D/solcx/SolCx.jl:6-11"""

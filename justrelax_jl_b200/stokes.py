@@ -596,6 +596,8 @@ def compute_lithostatic_pressure_(P, ρg, dz, igg: Optional[IGG] = None):
     if tuple(P.shape) != tuple(ρg.shape):
         raise ValueError(f"`P` and `ρg` must span the same cells, got axes {tuple(P.shape)} and {tuple(ρg.shape)}")   # DimensionMismatch
     nd = P.dim()
+    if igg is not None and igg.dims[nd - 1] > 1 and igg.periods[nd - 1]:   # Utils.jl:580-583 (test_lithostatic_pressure2D_MPI.jl:138-141)
+        raise RuntimeError("the lithostatic pressure of a column that is periodic along the vertical direction is undefined")
     dzv = None
     if not isinstance(dz, (int, float)):
         if int(np.prod(dz.shape)) != P.shape[-1]:

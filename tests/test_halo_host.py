@@ -84,6 +84,21 @@ def test_2d_solvers_refuse_a_periodic_grid_of_ranks():
     jst._single_rank2d(IGG())
 
 
+def test_lithostatic_pressure_rejects_vertically_periodic_columns():
+    """test/test_lithostatic_pressure2D_MPI.jl:131-143: the vertical direction split across ranks AND periodic → error"""
+    from justrelax_jl_b200 import stokes as jst
+    from justrelax_jl_b200.types import IGG
+
+    class A:
+        shape = (6, 5)
+
+        def dim(self):
+            return 2
+
+    with pytest.raises(RuntimeError, match="periodic along the vertical"):
+        jst.compute_lithostatic_pressure_(A(), A(), 0.5, IGG(dims=(1, 2, 1), nprocs=2, periods=(0, 1, 0)))
+
+
 def test_dims_create_and_cart_coords():
     from justrelax_jl_b200 import comm
 

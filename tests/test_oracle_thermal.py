@@ -3,6 +3,8 @@
  - test/test_diffusion2D.jl:127-135 (config 1): T[18,18] ≈ 1817.9448461176817, T[17,17] ≈ 1827.4674313638786 (atol 0.1)
  - test/test_diffusion2D_multiphase.jl:185-195: two phases, T[18,18] ≈ 1814.029, T[17,17] ≈ 1823.548 (atol 0.1)
  - test/test_diffusion3D_multiphase.jl:207-215: two phases in 3D, T[16,16,16] ≈ 1816.8262937737384, interior[16,16,16] ≈ 1834.4197141500213 (rtol 1e-3)
+ - test/test_diffusion3D.jl:143-156 (assertions commented out in the reference): 3D, single MaterialParams: T[16,16,16] ≈ 1813.2470160788096,
+   interior[16,16,16] ≈ 1831.2568044653274 — reproduced to the last digit (≤ 1e-13 relative asserted)
  - thermal_bcs! ghost identities of test/test_boundary_conditions2D.jl (constant value / no flux / periodic)
 """
 import numpy as np
@@ -34,6 +36,26 @@ def test_diffusion2d_reference_golden(oracle):
     assert abs(T[(nx >> 1), (ny >> 1)] - 1827.4674313638786) < 1.0e-1
     assert all(o["err"] <= 1e-8 for o in outs)
     assert np.array_equal(f["dT"], f["T"] - f["Told"])
+
+
+def test_diffusion3d_single_phase_commented_out_golden(oracle):
+    """test/test_diffusion3D.jl: the reference keeps the assertions of this test commented out (:143-156) but they still hold its golden
+    temperatures after 10 × 50 kyr at 32³ — T[16,16,16] ≈ 1813.2470160788096 and interior[16,16,16] ≈ 1831.2568044653274 (rtol 1e-3).
+    The restatement lands on them TO THE LAST PRINTED DIGIT (1813.2470160788096 exactly; 1831.2568044653271 vs …274, 2e-16 relative) after
+    10 000 PT iterations: a bit-level pin of the 3D single-MaterialParams rheology form (compute_pt_thermal_arrays!, compute_flux!, update_T!,
+    thermal_bcs!, the residual / convergence logic) against a real run of the Julia reference."""
+    s = setups.diffusion3d()
+    f = oracle.alloc_thermal(s.ni, dict(T=s.T, H=s.H, P=s.P, theta_r_dtau=s.pt.θr_dτ, dtau_rho=s.pt.dτ_ρ))
+    o = oracle.thermal_opts(_di=s.grid._di.center, dt=s.dt, eps=s.pt.ϵ, iterMax=s.kwargs["iterMax"], nout=s.kwargs["nout"],
+                            max_lxyz=s.pt.max_lxyz, Vpdtau=s.pt.Vpdτ, form=1, phases=s.phases, bc=s.bc)
+    f["T"][1:-1, 1:-1, 1:-1][s.perturbation] += s.δT                                                # elliptical_perturbation!  :111
+    outs = [oracle.heatdiffusion_PT(f, s.ni, o) for _ in range(s.nt)]
+    T = f["T"]
+    n = s.ni[0]
+    c = -(-n // 2) - 1                                                                              # Int(ceil(n / 2)), 0-based
+    assert abs(T[c, c, c] / 1813.2470160788096 - 1) < 1.0e-13, repr(T[c, c, c])                     # the reference asks for rtol 1e-3
+    assert abs(T[1:-1, 1:-1, 1:-1][c, c, c] / 1831.2568044653274 - 1) < 1.0e-13, repr(T[1:-1, 1:-1, 1:-1][c, c, c])
+    assert all(o_["err"] <= 1e-8 for o_ in outs)
 
 
 def test_thermal_bcs_identities(oracle):
