@@ -230,6 +230,38 @@ def test_config1_diffusion2d_golden_and_parity(oracle):
     compare(th, f, ["T", "Told", "dT", "qTx", "qTy", "ResT"], "config 1 after 20 steps")
 
 
+def test_diffusion3d_reference_golden_to_the_last_digit(oracle):
+    """test/test_diffusion3D.jl (assertions commented out in the reference, golden numbers kept): 10 × 50 kyr at 32³, rheology form, single
+    MaterialParams, through the public API — the solve loop runs the fused flux + update kernel in pairs between the samples.  The CPU
+    restatement reproduces the Julia golden to the last digit (tests/test_oracle_thermal.py); the B200 must land on the same numbers
+    (≤ 1e-12 relative against the golden itself), with the oracle's iteration counts and fields."""
+    from justrelax_jl_b200 import B200Backend, PTArray, setups, thermal as jth, to_host
+
+    s = setups.diffusion3d()
+    init = dict(T=s.T.copy(order="F"), H=s.H, P=s.P, theta_r_dtau=s.pt.θr_dτ, dtau_rho=s.pt.dτ_ρ)
+    f = oracle.alloc_thermal(s.ni, init)
+    th, extra = to_device(s.ni, oracle.alloc_thermal(s.ni, init))
+    o = oracle.thermal_opts(_di=s.grid._di.center, dt=s.dt, eps=s.pt.ϵ, iterMax=s.kwargs["iterMax"], nout=s.kwargs["nout"],
+                            max_lxyz=s.pt.max_lxyz, Vpdtau=s.pt.Vpdτ, form=1, phases=s.phases, bc=s.bc)
+    f["T"][1:-1, 1:-1, 1:-1][s.perturbation] += s.δT
+    outs = [oracle.heatdiffusion_PT(f, s.ni, o) for _ in range(s.nt)]
+    Tin = th.T[1:-1, 1:-1, 1:-1]
+    Tin += PTArray(B200Backend)(s.perturbation.astype(np.float64) * s.δT)
+    pt = type("PT", (), {})()
+    pt.ϵ, pt.max_lxyz, pt.Vpdτ = s.pt.ϵ, s.pt.max_lxyz, s.pt.Vpdτ
+    pt.θr_dτ, pt.dτ_ρ = extra["theta_r_dtau"], extra["dtau_rho"]
+    rheo = rheology_of(s.phases)[0]
+    iters = []
+    for _ in range(s.nt):
+        out = jth.heatdiffusion_PT_(th, pt, s.bc, rheo, dict(P=extra["P"], T=th.T), s.dt, s.grid, kwargs=dict(s.kwargs))
+        iters.append(int(out.iter_count[-1]))
+    assert iters == [int(o_["iter_count"][-1]) for o_ in outs]
+    T = to_host(th.T)
+    assert abs(T[15, 15, 15] / 1813.2470160788096 - 1) < 1.0e-12, repr(T[15, 15, 15])
+    assert abs(T[1:-1, 1:-1, 1:-1][15, 15, 15] / 1831.2568044653274 - 1) < 1.0e-12
+    compare(th, f, ["T", "Told", "dT", "qTx", "qTy", "qTz", "ResT"], "3D single-phase diffusion after 10 steps")
+
+
 def test_diffusion3d_multiphase_solve_parity(oracle):
     """test/test_diffusion3D_multiphase.jl through the public API (heatdiffusion_PT!, rheology form, two phases with ratios, nout = 100):
     the solve loop runs the fused flux + update kernel in pairs between the samples.  Same PT iteration counts as the oracle and the same
